@@ -1,0 +1,260 @@
+// C-ABI entry points for the rasterizer (include/gigs_b200.h): workspace layout, forward
+// orchestration (reference cuda_rasterizer/rasterizer_impl.cu:486-672) and backward orchestration
+// (:676-803). No torch types; the caller owns every buffer.
+#include <cstdarg>
+#include <cstring>
+#include <string>
+#include "common.cuh"
+
+namespace gigs {
+
+static thread_local std::string g_last_error;
+
+void set_error(const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+
+int cuda_fail(cudaError_t e, const char* what)
+{
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return (int)e;
+}
+
+// reference rasterizer_impl.cu:35-50 (number of key bits needed for the tile id)
+uint32_t higher_msb(uint32_t n)
+{
+    uint32_t msb = sizeof(n) * 4;
+    uint32_t step = msb;
+    while (step > 1) {
+        step /= 2;
+        if (n >> msb)
+            msb += step;
+        else
+            msb -= step;
+    }
+    if (n >> msb) msb++;
+    return msb;
+}
+
+uint32_t radix_sort_tiles(uint64_t R);
+
+Layout make_layout(int P, int W, int H, uint64_t R)
+{
+    Layout L;
+    memset(&L, 0, sizeof(L));
+    const uint64_t Pn = (uint64_t)(P > 0 ? P : 0);
+    const uint64_t N = (uint64_t)W * (uint64_t)H;
+    L.tiles_x = (W + TILE_X - 1) / TILE_X;
+    L.tiles_y = (H + TILE_Y - 1) / TILE_Y;
+    L.num_tiles = L.tiles_x * L.tiles_y;
+    L.num_blocks = (uint32_t)((Pn + 255) / 256);
+
+    uint64_t o = 0;
+    auto take = [&](uint64_t bytes) {
+        o = align_up(o, 128);
+        uint64_t r = o;
+        o += bytes;
+        return r;
+    };
+    // geom
+    L.off.g_record = take(Pn * REC_FLOATS * 4);
+    L.off.g_cov3D = take(Pn * 6 * 4);
+    L.off.g_clamped = take(Pn * 4);
+    L.off.g_tiles_touched = take(Pn * 4);
+    L.off.g_point_offsets = take(Pn * 4);
+    L.off.g_block_sums = take(((uint64_t)L.num_blocks + 1) * 4);
+    L.off.g_num_rendered = take(16);
+    L.size.geom_bytes = align_up(o, 128) + 128;
+    // img
+    o = 0;
+    L.off.i_final_T = take(N * 4);
+    L.off.i_n_contrib = take(N * 4);
+    L.off.i_ranges = take((uint64_t)L.num_tiles * 8);
+    L.size.img_bytes = align_up(o, 128) + 128;
+    // binning (kept for backward): sorted Gaussian ids only
+    o = 0;
+    L.off.b_point_list = take(R * 4);
+    L.size.binning_bytes = align_up(o, 128) + 128;
+    // sort scratch
+    o = 0;
+    L.sort_bits = 32 + higher_msb(L.num_tiles);
+    L.sort_passes = (L.sort_bits + 7) / 8;
+    L.sort_tiles = radix_sort_tiles(R);
+    L.off.s_keys_unsorted = take(R * 8);
+    L.off.s_vals_unsorted = take(R * 4);
+    L.s_keys_a = take(R * 8);
+    L.s_keys_b = take(R * 8);
+    L.s_vals_b = take(R * 4);
+    L.s_hist = take(8 * 256 * 4);
+    L.s_ticket = take(128);
+    L.s_status = take((uint64_t)L.sort_passes * L.sort_tiles * 256 * 4);
+    L.off.s_keys_sorted = L.s_keys_a;
+    L.size.sort_bytes = align_up(o, 128) + 128;
+    return L;
+}
+
+// launchers defined in the kernel files
+int launch_preprocess(const GigsRasterFwd* a, const Layout& L, cudaStream_t st);
+int launch_emit_keys(const GigsRasterFwd* a, const Layout& L, uint64_t* keys, uint32_t* vals, cudaStream_t st);
+int launch_tile_ranges(uint64_t R, const uint64_t* keys_sorted, uint2* ranges, uint32_t num_tiles, cudaStream_t st);
+int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t st);
+int launch_radix_sort(uint64_t R, int end_bit, const uint64_t* keys_u, const uint32_t* vals_u, uint64_t* keys_a,
+                      uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, uint32_t* hist, uint32_t* status,
+                      uint32_t* tickets, uint64_t status_bytes_total, cudaStream_t st);
+int launch_blend_forward(const GigsRasterFwd* a, const Layout& L, bool lite, cudaStream_t st);
+int launch_blend_backward(const GigsRasterBwd* a, const Layout& L, cudaStream_t st);
+int launch_gaussian_backward(const GigsRasterBwd* a, const Layout& L, cudaStream_t st);
+
+static int check_common(int P, const GigsCamera& c)
+{
+    if (P < 0) { set_error("P must be >= 0"); return -1; }
+    if (c.width <= 0 || c.height <= 0) { set_error("image size must be positive"); return -1; }
+    if (!c.viewmatrix || !c.projmatrix || !c.campos || !c.bg) { set_error("camera pointers must not be NULL"); return -1; }
+    return 0;
+}
+
+static int forward_finish_impl(GigsRasterFwd* a, bool lite)
+{
+    if (!a) { set_error("null args"); return -1; }
+    if (int e = check_common(a->P, a->cam)) return e;
+    cudaStream_t st = (cudaStream_t)a->stream;
+    if (a->P == 0) {
+        // the reference short-circuits to its zero-filled outputs (rasterize_points.cu:191)
+        const size_t N = (size_t)a->cam.width * a->cam.height * sizeof(float);
+        float* three[] = {a->out_color, lite ? nullptr : a->out_normal, lite ? nullptr : a->out_normal_view,
+                          lite ? nullptr : a->out_pos, lite ? nullptr : a->out_albedo};
+        float* one[] = {a->out_opacity, a->out_depth, lite ? nullptr : a->out_roughness,
+                        lite ? nullptr : a->out_metallic};
+        for (float* p : three)
+            if (p) GIGS_CUDA(cudaMemsetAsync(p, 0, 3 * N, st));
+        for (float* p : one)
+            if (p) GIGS_CUDA(cudaMemsetAsync(p, 0, N, st));
+        return 0;
+    }
+    const uint64_t R = (uint64_t)a->num_rendered;
+    const Layout L = make_layout(a->P, a->cam.width, a->cam.height, R);
+    if (a->geom_bytes < L.size.geom_bytes || a->img_bytes < L.size.img_bytes ||
+        a->binning_bytes < L.size.binning_bytes || a->sort_bytes < L.size.sort_bytes) {
+        set_error("workspace too small (geom %llu/%llu img %llu/%llu binning %llu/%llu sort %llu/%llu)",
+                  (unsigned long long)a->geom_bytes, (unsigned long long)L.size.geom_bytes,
+                  (unsigned long long)a->img_bytes, (unsigned long long)L.size.img_bytes,
+                  (unsigned long long)a->binning_bytes, (unsigned long long)L.size.binning_bytes,
+                  (unsigned long long)a->sort_bytes, (unsigned long long)L.size.sort_bytes);
+        return -2;
+    }
+    char* sc = (char*)a->sort;
+    char* im = (char*)a->img;
+    char* bn = (char*)a->binning;
+    uint64_t* keys_u = (uint64_t*)(sc + L.off.s_keys_unsorted);
+    uint32_t* vals_u = (uint32_t*)(sc + L.off.s_vals_unsorted);
+    if (a->P > 0 && R > 0) {
+        if (int e = launch_emit_keys(a, L, keys_u, vals_u, st)) return e;
+        const uint64_t status_total = (L.s_status - L.s_hist) + (uint64_t)L.sort_passes * L.sort_tiles * 256 * 4;
+        if (int e = launch_radix_sort(R, (int)L.sort_bits, keys_u, vals_u, (uint64_t*)(sc + L.s_keys_a),
+                                      (uint32_t*)(bn + L.off.b_point_list), (uint64_t*)(sc + L.s_keys_b),
+                                      (uint32_t*)(sc + L.s_vals_b), (uint32_t*)(sc + L.s_hist),
+                                      (uint32_t*)(sc + L.s_status), (uint32_t*)(sc + L.s_ticket), status_total, st))
+            return e;
+    }
+    if (int e = launch_tile_ranges(R, (const uint64_t*)(sc + L.s_keys_a), (uint2*)(im + L.off.i_ranges), L.num_tiles, st))
+        return e;
+    if (int e = launch_blend_forward(a, L, lite, st)) return e;
+    if (a->cam.debug) GIGS_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+}  // namespace gigs
+
+using namespace gigs;
+
+extern "C" {
+
+int gigs_abi_version(void) { return GIGS_ABI_VERSION; }
+const char* gigs_last_error(void) { return g_last_error.c_str(); }
+
+int gigs_raster_sizes(int32_t P, int32_t W, int32_t H, uint64_t R, GigsSizes* out)
+{
+    if (!out || P < 0 || W <= 0 || H <= 0) { set_error("gigs_raster_sizes: bad arguments"); return -1; }
+    *out = make_layout(P, W, H, R).size;
+    return 0;
+}
+
+int gigs_raster_layout(int32_t P, int32_t W, int32_t H, uint64_t R, GigsLayout* out)
+{
+    if (!out || P < 0 || W <= 0 || H <= 0) { set_error("gigs_raster_layout: bad arguments"); return -1; }
+    *out = make_layout(P, W, H, R).off;
+    return 0;
+}
+
+int gigs_raster_forward_begin(GigsRasterFwd* a)
+{
+    if (!a) { set_error("null args"); return -1; }
+    if (int e = check_common(a->P, a->cam)) return e;
+    a->num_rendered = 0;
+    if (a->P == 0) return 0;
+    if (!a->means3D || !a->opacities || !a->radii) { set_error("means3D/opacities/radii must not be NULL"); return -1; }
+    if ((a->shs == nullptr) == (a->colors_precomp == nullptr)) {
+        set_error("provide exactly one of shs / colors_precomp");
+        return -1;
+    }
+    if (a->cov3D_precomp == nullptr && (a->scales == nullptr || a->rotations == nullptr)) {
+        set_error("provide scales+rotations or cov3D_precomp");
+        return -1;
+    }
+    cudaStream_t st = (cudaStream_t)a->stream;
+    const Layout L = make_layout(a->P, a->cam.width, a->cam.height, 0);
+    if (a->geom_bytes < L.size.geom_bytes || a->img_bytes < L.size.img_bytes) {
+        set_error("geom/img workspace too small");
+        return -2;
+    }
+    if (int e = launch_preprocess(a, L, st)) return e;
+    uint32_t hostR = 0;
+    uint32_t* dst = a->pinned_num_rendered ? a->pinned_num_rendered : &hostR;
+    GIGS_CUDA(cudaMemcpyAsync(dst, (char*)a->geom + L.off.g_num_rendered, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    GIGS_CUDA(cudaStreamSynchronize(st));
+    a->num_rendered = (int64_t)*dst;
+    return 0;
+}
+
+int gigs_raster_forward_finish(GigsRasterFwd* a) { return forward_finish_impl(a, false); }
+int gigs_lite_forward_finish(GigsRasterFwd* a) { return forward_finish_impl(a, true); }
+
+int gigs_raster_backward(GigsRasterBwd* a)
+{
+    if (!a) { set_error("null args"); return -1; }
+    if (int e = check_common(a->P, a->cam)) return e;
+    if (a->P == 0) return 0;
+    if (!a->accum || !a->dL_dmean2D || !a->dL_dopacity || !a->dL_dcolor || !a->dL_dnormal || !a->dL_dalbedo ||
+        !a->dL_droughness || !a->dL_dmetallic || !a->dL_dmean3D || !a->dL_dcov3D) {
+        set_error("backward: required output pointer is NULL");
+        return -1;
+    }
+    if ((a->shs != nullptr) && !a->dL_dsh) { set_error("backward: dL_dsh required with shs"); return -1; }
+    if ((a->scales != nullptr) && (!a->dL_dscale || !a->dL_drot || !a->rotations)) {
+        set_error("backward: dL_dscale/dL_drot required with scales");
+        return -1;
+    }
+    cudaStream_t st = (cudaStream_t)a->stream;
+    const Layout L = make_layout(a->P, a->cam.width, a->cam.height, (uint64_t)a->num_rendered);
+    GIGS_CUDA(cudaMemsetAsync(a->accum, 0, (size_t)a->P * ACC_FLOATS * sizeof(float), st));
+    if (a->num_rendered > 0) {
+        if (int e = launch_blend_backward(a, L, st)) return e;
+    }
+    if (int e = launch_gaussian_backward(a, L, st)) return e;
+    if (a->cam.debug) GIGS_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int gigs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, uint8_t* present, void* stream)
+{
+    if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) { set_error("gigs_mark_visible: bad arguments"); return -1; }
+    return launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
+}
+
+}  // extern "C"

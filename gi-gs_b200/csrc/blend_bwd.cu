@@ -1,0 +1,350 @@
+// G-buffer alpha blend, backward. Replaces the backward renderCUDA
+// (reference cuda_rasterizer/backward.cu:404-630), which issues 19 scalar atomicAdds per
+// contributing (pixel, Gaussian) pair.
+//
+// Here each warp (a 16x2 pixel strip) reduces its 32 pixels' contributions with a transposing
+// butterfly (16+4 values in 22 shuffles instead of 19 x 5) and then issues ONE warp-wide
+// red.global.add over the Gaussian's packed 80-B accumulator row, so the L2 sees <=19 lane-atomics
+// per (warp, Gaussian) on 3 sectors instead of 19 x 32 on 19 arrays. Batches are staged with TMA
+// bulk copies like the forward. The tile walks only the prefix of its list that the forward
+// actually reached (max n_contrib over the tile), and a Gaussian whose 1/255 iso-ellipse cannot
+// reach a strip is rejected once per warp.
+//
+// MODE_MATERIAL is the PBR-stage fast path: when neither the colour nor the opacity map has an
+// upstream gradient, dL/dalpha is identically zero in the reference as well, so only the
+// w * dL/dpixel sums of albedo / roughness / metallic are needed (5 values, 9 shuffles).
+#include "common.cuh"
+
+namespace gigs {
+
+constexpr int BB_THREADS = 256;
+constexpr int BB_BATCH = 256;
+
+template <int RECF>
+struct BwdSmem {
+    float rec[2][BB_BATCH][RECF];
+    uint32_t ids[2][BB_BATCH];
+    uint64_t bar[2];
+    int red[BB_THREADS / 32];
+};
+
+__device__ __forceinline__ float xor_shfl(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+
+// sum over the 32 lanes of v[i]; afterwards lane l (l < 16) returns the total of v[l]
+__device__ __forceinline__ float warp_transpose_reduce16(float (&v)[16], int lane)
+{
+#pragma unroll
+    for (int off = 8; off >= 1; off >>= 1) {
+        const bool hi = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float send = hi ? v[i] : v[i + off];
+            const float keep = hi ? v[i + off] : v[i];
+            v[i] = keep + xor_shfl(send, off);
+        }
+    }
+    return v[0] + xor_shfl(v[0], 16);
+}
+// lane l returns the total of v[l & 3]
+__device__ __forceinline__ float warp_transpose_reduce4(float (&v)[4], int lane)
+{
+#pragma unroll
+    for (int off = 2; off >= 1; off >>= 1) {
+        const bool hi = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float send = hi ? v[i] : v[i + off];
+            const float keep = hi ? v[i + off] : v[i];
+            v[i] = keep + xor_shfl(send, off);
+        }
+    }
+    float r = v[0];
+    r += xor_shfl(r, 4);
+    r += xor_shfl(r, 8);
+    r += xor_shfl(r, 16);
+    return r;
+}
+// lane l returns the total of v[l & 7]
+__device__ __forceinline__ float warp_transpose_reduce8(float (&v)[8], int lane)
+{
+#pragma unroll
+    for (int off = 4; off >= 1; off >>= 1) {
+        const bool hi = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float send = hi ? v[i] : v[i + off];
+            const float keep = hi ? v[i + off] : v[i];
+            v[i] = keep + xor_shfl(send, off);
+        }
+    }
+    float r = v[0];
+    r += xor_shfl(r, 8);
+    r += xor_shfl(r, 16);
+    return r;
+}
+
+constexpr int MODE_FULL = 0, MODE_MATERIAL = 1;
+
+template <int MODE>
+__global__ void __launch_bounds__(BB_THREADS)
+blend_backward_kernel(const int W, const int H, const uint2* __restrict__ ranges,
+                      const uint32_t* __restrict__ point_list, const float* __restrict__ records,
+                      const float* __restrict__ bg_color, const float* __restrict__ final_Ts,
+                      const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpix_depth,
+                      const float* __restrict__ dL_dpix, const float* __restrict__ dL_dpix_opacity,
+                      const float* __restrict__ dL_dpix_normal, const float* __restrict__ dL_dpix_albedo,
+                      const float* __restrict__ dL_dpix_roughness, const float* __restrict__ dL_dpix_metallic,
+                      float* __restrict__ accum)
+{
+    constexpr int RECF = (MODE == MODE_FULL) ? 12 : 8;
+    constexpr uint32_t RECB = RECF * 4;
+    using Smem = BwdSmem<RECF>;
+    extern __shared__ __align__(128) unsigned char bb_smem_raw[];
+    Smem& S = *reinterpret_cast<Smem*>(bb_smem_raw);
+
+    const int tid = threadIdx.y * TILE_X + threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const uint32_t horizontal_blocks = (W + TILE_X - 1) / TILE_X;
+    const uint2 pix = {blockIdx.x * TILE_X + threadIdx.x, blockIdx.y * TILE_Y + threadIdx.y};
+    const uint32_t pix_id = W * pix.y + pix.x;
+    const float2 pixf = {(float)pix.x, (float)pix.y};
+    const bool inside = pix.x < (uint32_t)W && pix.y < (uint32_t)H;
+    const int HW = H * W;
+
+    const uint2 range = ranges[blockIdx.y * horizontal_blocks + blockIdx.x];
+    const int last_contributor = inside ? (int)n_contrib[pix_id] : 0;
+
+    // the forward never went past max(n_contrib) in this tile: walk only that prefix, back to front
+    int wmax = last_contributor;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    if (lane == 0) S.red[warp] = wmax;
+    if (tid == 0) {
+        mbar_init(&S.bar[0], 1);
+        mbar_init(&S.bar[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    int n = 0;
+#pragma unroll
+    for (int w = 0; w < BB_THREADS / 32; ++w) n = max(n, S.red[w]);
+    n = min(n, (int)(range.y - range.x));
+    const int rounds = (n + BB_BATCH - 1) / BB_BATCH;
+
+    const float strip_x0 = (float)(blockIdx.x * TILE_X);
+    const float strip_y0 = (float)(blockIdx.y * TILE_Y + (threadIdx.y & ~1));
+
+    auto issue = [&](int b) {
+        const int s = b & 1;
+        const int cnt = min(BB_BATCH, n - b * BB_BATCH);
+        if (tid == 0) mbar_arrive_expect_tx(&S.bar[s], (uint32_t)cnt * RECB);
+        if (tid < cnt) {
+            const uint32_t id = point_list[range.x + (n - 1 - (b * BB_BATCH + tid))];
+            S.ids[s][tid] = id;
+            bulk_g2s(&S.rec[s][tid][0], records + (size_t)id * REC_FLOATS, RECB, &S.bar[s]);
+        }
+    };
+
+    const float T_final = inside ? final_Ts[pix_id] : 0.f;
+    float T = T_final;
+    float last_alpha = 0.f, accum_opacity = 0.f;
+    float accum_rec[3] = {0.f, 0.f, 0.f}, last_color[3] = {0.f, 0.f, 0.f};
+    float g_col[3] = {0.f, 0.f, 0.f}, g_nrm[3] = {0.f, 0.f, 0.f}, g_alb[3] = {0.f, 0.f, 0.f};
+    float g_op = 0.f, g_rough = 0.f, g_metal = 0.f, g_depth = 0.f;
+    if (inside) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            if (MODE == MODE_FULL) {
+                g_col[i] = dL_dpix ? dL_dpix[i * HW + pix_id] : 0.f;
+                g_nrm[i] = dL_dpix_normal ? dL_dpix_normal[i * HW + pix_id] : 0.f;
+            }
+            g_alb[i] = dL_dpix_albedo ? dL_dpix_albedo[i * HW + pix_id] : 0.f;
+        }
+        if (MODE == MODE_FULL) {
+            g_op = dL_dpix_opacity ? dL_dpix_opacity[pix_id] : 0.f;
+            g_depth = dL_dpix_depth ? dL_dpix_depth[pix_id] : 0.f;
+        }
+        g_rough = dL_dpix_roughness ? dL_dpix_roughness[pix_id] : 0.f;
+        g_metal = dL_dpix_metallic ? dL_dpix_metallic[pix_id] : 0.f;
+    }
+    // the reference zeroes the normal gradient of image-border pixels (backward.cu:497-501)
+    if (pix.x == 0 || pix.x == (uint32_t)(W - 1) || pix.y == 0 || pix.y == (uint32_t)(H - 1)) {
+        g_nrm[0] = g_nrm[1] = g_nrm[2] = 0.f;
+    }
+    const float ddelx_dx = 0.5 * W;
+    const float ddely_dy = 0.5 * H;
+    float bg_dot_dpixel = 0.f;
+    if (MODE == MODE_FULL) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) bg_dot_dpixel += bg_color[i] * g_col[i];
+    }
+
+    if (rounds > 0) issue(0);
+    __syncthreads();  // ids of batch 0 are plain shared stores: make them visible
+    for (int b = 0; b < rounds; ++b) {
+        const int s = b & 1;
+        if (b + 1 < rounds) issue(b + 1);
+        mbar_wait(&S.bar[s], (uint32_t)((b >> 1) & 1));
+        const int cnt = min(BB_BATCH, n - b * BB_BATCH);
+        // forward index of entry j of this batch: n-1-(b*BATCH+j); entries at or beyond the warp's
+        // deepest contributor are skipped warp-wide
+        for (int jb = 0; jb < cnt; jb += 32) {
+            const int fwd_hi = n - 1 - (b * BB_BATCH + jb);  // largest forward index in this chunk
+            if (fwd_hi - 31 >= wmax) continue;               // whole chunk beyond this warp's reach
+            bool keep = false;
+            const int jl = jb + lane;
+            if (jl < cnt && (fwd_hi - lane) < wmax) {
+                const float4 t0 = *reinterpret_cast<const float4*>(&S.rec[s][jl][0]);
+                const float4 t1 = *reinterpret_cast<const float4*>(&S.rec[s][jl][4]);
+                const float cA = t0.z, cB = t0.w, cC = t1.x;
+                const float hx = t0.x - strip_x0;
+                const float hy = t0.y - strip_y0;
+                float qmin;
+                {
+                    const float dy = hy;
+                    const float dxs = fminf(hx, fmaxf(hx - 15.f, __fdividef(-cB * dy, cA)));
+                    const float ta = 0.5f * cA * dxs * dxs, tb = cB * dxs * dy, tc = 0.5f * cC * dy * dy;
+                    qmin = (ta + tb + tc) - 4e-6f * (fabsf(ta) + fabsf(tb) + fabsf(tc));
+                }
+                {
+                    const float dy = hy - 1.f;
+                    const float dxs = fminf(hx, fmaxf(hx - 15.f, __fdividef(-cB * dy, cA)));
+                    const float ta = 0.5f * cA * dxs * dxs, tb = cB * dxs * dy, tc = 0.5f * cC * dy * dy;
+                    qmin = fminf(qmin, (ta + tb + tc) - 4e-6f * (fabsf(ta) + fabsf(tb) + fabsf(tc)));
+                }
+                keep = !(cA > 0.f) || !(qmin > t1.w + 0.05f);
+            }
+            uint32_t mask = __ballot_sync(0xffffffffu, keep);
+            while (mask) {
+                const int jo = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const int j = jb + jo;
+                const int fwd_idx = fwd_hi - jo;
+
+                bool contrib = false;
+                float v16[16];
+                float v4[4];
+                float v8[8];
+                if (MODE == MODE_FULL) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v16[i] = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) v4[i] = 0.f;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v8[i] = 0.f;
+                }
+                if (fwd_idx < last_contributor) {
+                    const float4 q0 = *reinterpret_cast<const float4*>(&S.rec[s][j][0]);
+                    const float4 q1 = *reinterpret_cast<const float4*>(&S.rec[s][j][4]);
+                    const float2 d = {q0.x - pixf.x, q0.y - pixf.y};
+                    const float power = -0.5f * (q0.z * d.x * d.x + q1.x * d.y * d.y) - q0.w * d.x * d.y;
+                    if (!(power > 0.0f)) {
+                        const float G = expf(power);
+                        const float alpha = fminf(0.99f, q1.y * G);
+                        if (!(alpha < 1.0f / 255.0f)) {
+                            contrib = true;
+                            T = T / (1.f - alpha);
+                            const float w = alpha * T;
+                            if (MODE == MODE_FULL) {
+                                const float4 q2 = *reinterpret_cast<const float4*>(&S.rec[s][j][8]);
+                                const float col[3] = {q2.x, q2.y, q2.z};
+                                float dL_dalpha = 0.0f;
+#pragma unroll
+                                for (int ch = 0; ch < 3; ++ch) {
+                                    const float c = col[ch];
+                                    accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
+                                    last_color[ch] = c;
+                                    dL_dalpha += (c - accum_rec[ch]) * g_col[ch];
+                                    v16[A_COL + ch] = w * g_col[ch];
+                                    v16[A_NRM + ch] = w * g_nrm[ch];
+                                    v16[A_ALB + ch] = w * g_alb[ch];
+                                }
+                                v16[A_ROUGH] = w * g_rough;
+                                v16[A_METAL] = w * g_metal;
+                                v16[A_DEPTH] = w * g_depth;
+                                accum_opacity = last_alpha + (1.f - last_alpha) * accum_opacity;
+                                dL_dalpha += (1.0f - accum_opacity) * g_op;
+                                dL_dalpha *= T;
+                                last_alpha = alpha;
+                                dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+
+                                const float dL_dG = q1.y * dL_dalpha;
+                                const float gdx = G * d.x;
+                                const float gdy = G * d.y;
+                                const float dG_ddelx = -gdx * q0.z - gdy * q0.w;
+                                const float dG_ddely = -gdy * q1.x - gdx * q0.w;
+                                const float m2x = dL_dG * dG_ddelx * ddelx_dx;
+                                const float m2y = dL_dG * dG_ddely * ddely_dy;
+                                v16[A_M2X] = m2x;
+                                v16[A_M2Y] = m2y;
+                                v16[A_M2Z] = fabsf(m2x) + fabsf(m2y);
+                                v16[A_OPAC] = G * dL_dalpha;
+                                v4[0] = -0.5f * gdx * d.x * dL_dG;
+                                v4[1] = -0.5f * gdx * d.y * dL_dG;
+                                v4[2] = -0.5f * gdy * d.y * dL_dG;
+                            } else {
+                                v8[0] = w * g_rough;
+                                v8[1] = w * g_alb[0];
+                                v8[2] = w * g_alb[1];
+                                v8[3] = w * g_alb[2];
+                                v8[4] = w * g_metal;
+                            }
+                        }
+                    }
+                }
+                if (__any_sync(0xffffffffu, contrib)) {
+                    float* row = accum + (size_t)S.ids[s][j] * ACC_FLOATS;
+                    if (MODE == MODE_FULL) {
+                        const float r16 = warp_transpose_reduce16(v16, lane);
+                        const float r4 = warp_transpose_reduce4(v4, lane);
+                        const float r = (lane < 16) ? r16 : r4;
+                        if (lane < 19) red_add_f32(row + lane, r);
+                    } else {
+                        const float r = warp_transpose_reduce8(v8, lane);
+                        if (lane < 5) red_add_f32(row + A_ROUGH + lane, r);
+                    }
+                }
+            }
+        }
+        __syncthreads();  // release stage s
+    }
+}
+
+int launch_blend_backward(const GigsRasterBwd* a, const Layout& L, cudaStream_t st)
+{
+    const GigsCamera& c = a->cam;
+    const char* g = (const char*)a->geom;
+    const char* im = (const char*)a->img;
+    const char* bn = (const char*)a->binning;
+    dim3 grid(L.tiles_x, L.tiles_y, 1), block(TILE_X, TILE_Y, 1);
+    static bool attr_set = false;
+    if (!attr_set) {
+        GIGS_CUDA(cudaFuncSetAttribute(blend_backward_kernel<MODE_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(BwdSmem<12>)));
+        GIGS_CUDA(cudaFuncSetAttribute(blend_backward_kernel<MODE_MATERIAL>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem<8>)));
+        attr_set = true;
+    }
+    const uint2* ranges = (const uint2*)(im + L.off.i_ranges);
+    const uint32_t* plist = (const uint32_t*)(bn + L.off.b_point_list);
+    const float* recs = (const float*)(g + L.off.g_record);
+    const uint32_t* ncontrib = (const uint32_t*)(im + L.off.i_n_contrib);
+    const float* finalT = (const float*)(im + L.off.i_final_T);
+    const bool material_only = (a->dL_dpix == nullptr) && (a->dL_dpix_opacity == nullptr) &&
+                               (a->dL_dpix_normal == nullptr) && (a->dL_dpix_depth == nullptr);
+    if (material_only)
+        blend_backward_kernel<MODE_MATERIAL><<<grid, block, sizeof(BwdSmem<8>), st>>>(
+            c.width, c.height, ranges, plist, recs, c.bg, finalT, ncontrib, a->dL_dpix_depth, a->dL_dpix,
+            a->dL_dpix_opacity, a->dL_dpix_normal, a->dL_dpix_albedo, a->dL_dpix_roughness, a->dL_dpix_metallic,
+            a->accum);
+    else
+        blend_backward_kernel<MODE_FULL><<<grid, block, sizeof(BwdSmem<12>), st>>>(
+            c.width, c.height, ranges, plist, recs, c.bg, finalT, ncontrib, a->dL_dpix_depth, a->dL_dpix,
+            a->dL_dpix_opacity, a->dL_dpix_normal, a->dL_dpix_albedo, a->dL_dpix_roughness, a->dL_dpix_metallic,
+            a->accum);
+    GIGS_LAUNCH_CHECK("blend_backward_kernel");
+    return 0;
+}
+
+}  // namespace gigs

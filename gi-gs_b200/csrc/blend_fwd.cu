@@ -1,0 +1,249 @@
+// G-buffer alpha blend, forward. Replaces renderCUDA / liteRenderCUDA
+// (reference cuda_rasterizer/forward.cu:423-633, :279-418).
+//
+// One CTA per 16x16 tile, one thread per pixel, like the reference; what differs is the data path:
+//   * each tile batch (256 Gaussians) is staged into shared memory as packed 96-B records by
+//     per-thread TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier, double
+//     buffered so batch b+1 streams in while batch b is blended. The reference stages 28 B and
+//     re-gathers 60 B of features from global memory per contributing (pixel, Gaussian) pair.
+//   * warps (16x2 pixel strips) vote: a strip whose pixels are all saturated stops blending, and a
+//     Gaussian whose 1/255 iso-ellipse cannot reach the strip is rejected once per warp instead of
+//     once per pixel (conservative bound; the exact per-pixel test still runs for the survivors, so
+//     results are unchanged).
+// The per-pair arithmetic keeps the reference's expression order so n_contrib / final_T match.
+#include "common.cuh"
+
+namespace gigs {
+
+constexpr int BL_THREADS = 256;
+constexpr int BL_BATCH = 256;
+constexpr uint32_t REC_BYTES = REC_FLOATS * 4;
+
+struct BlendSmem {
+    float rec[2][BL_BATCH][REC_FLOATS];  // 2 x 24 KB
+    uint64_t bar[2];
+};
+
+template <bool LITE>
+__global__ void __launch_bounds__(BL_THREADS)
+blend_forward_kernel(const int W, const int H, const uint2* __restrict__ ranges,
+                     const uint32_t* __restrict__ point_list, const float* __restrict__ records,
+                     const float* __restrict__ viewmatrix, const float* __restrict__ bg_color,
+                     uint32_t* __restrict__ n_contrib, float* __restrict__ final_T, float* __restrict__ out_color,
+                     float* __restrict__ out_opacity, float* __restrict__ out_depth, float* __restrict__ out_normal,
+                     float* __restrict__ out_normal_view, float* __restrict__ out_pos,
+                     float* __restrict__ out_albedo, float* __restrict__ out_roughness,
+                     float* __restrict__ out_metallic, const bool argmax_depth, const bool inference)
+{
+    extern __shared__ __align__(128) unsigned char bl_smem_raw[];
+    BlendSmem& S = *reinterpret_cast<BlendSmem*>(bl_smem_raw);
+
+    const int tid = threadIdx.y * TILE_X + threadIdx.x;
+    const int lane = tid & 31;
+    const uint32_t horizontal_blocks = (W + TILE_X - 1) / TILE_X;
+    const uint2 pix = {blockIdx.x * TILE_X + threadIdx.x, blockIdx.y * TILE_Y + threadIdx.y};
+    const uint32_t pix_id = W * pix.y + pix.x;
+    const float2 pixf = {(float)pix.x, (float)pix.y};
+    const bool inside = pix.x < (uint32_t)W && pix.y < (uint32_t)H;
+    bool done = !inside;
+
+    const uint2 range = ranges[blockIdx.y * horizontal_blocks + blockIdx.x];
+    const int n = (int)(range.y - range.x);
+    const int rounds = (n + BL_BATCH - 1) / BL_BATCH;
+
+    if (tid == 0) {
+        mbar_init(&S.bar[0], 1);
+        mbar_init(&S.bar[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // strip bounds of this warp (2 rows x 16 columns) for the conservative rejection test
+    const float strip_x0 = (float)(blockIdx.x * TILE_X);
+    const float strip_y0 = (float)(blockIdx.y * TILE_Y + (threadIdx.y & ~1));
+
+    auto issue = [&](int b) {
+        const int s = b & 1;
+        const int cnt = min(BL_BATCH, n - b * BL_BATCH);
+        if (tid == 0) mbar_arrive_expect_tx(&S.bar[s], (uint32_t)cnt * REC_BYTES);
+        if (tid < cnt) {
+            const uint32_t id = point_list[range.x + b * BL_BATCH + tid];
+            bulk_g2s(&S.rec[s][tid][0], records + (size_t)id * REC_FLOATS, REC_BYTES, &S.bar[s]);
+        }
+    };
+
+    float T = 1.0f;
+    uint32_t last_contributor = 0;
+    float C[3] = {0.f, 0.f, 0.f}, N[3] = {0.f, 0.f, 0.f}, A[3] = {0.f, 0.f, 0.f};
+    float Rg = 0.f, Mt = 0.f, D = 0.f, O = 0.f;
+    float3 POS = {0.f, 0.f, 0.f};
+    float max_weight = 0.f, except_depth = 0.f;
+    float3 except_pos = {0.f, 0.f, 0.f};
+
+    if (rounds > 0) issue(0);
+    for (int b = 0; b < rounds; ++b) {
+        const int s = b & 1;
+        if (b + 1 < rounds) issue(b + 1);  // stage s^1 was released by the barrier ending round b-1
+        mbar_wait(&S.bar[s], (uint32_t)((b >> 1) & 1));
+
+        const int cnt = min(BL_BATCH, n - b * BL_BATCH);
+        bool warp_done = __all_sync(0xffffffffu, done);
+        for (int jb = 0; jb < cnt && !warp_done; jb += 32) {
+            // --- lane l tests Gaussian jb+l against this warp's 16x2 strip (conservative bound) ---
+            bool keep = false;
+            const int jl = jb + lane;
+            if (jl < cnt) {
+                const float4 t0 = *reinterpret_cast<const float4*>(&S.rec[s][jl][0]);
+                const float4 t1 = *reinterpret_cast<const float4*>(&S.rec[s][jl][4]);
+                const float cA = t0.z, cB = t0.w, cC = t1.x;
+                const float hx = t0.x - strip_x0;  // d.x over the strip: [hx-15, hx]
+                const float hy = t0.y - strip_y0;  // d.y over the strip: {hy, hy-1}
+                float qmin;
+                {
+                    const float dy = hy;
+                    const float dxs = fminf(hx, fmaxf(hx - 15.f, __fdividef(-cB * dy, cA)));
+                    const float ta = 0.5f * cA * dxs * dxs, tb = cB * dxs * dy, tc = 0.5f * cC * dy * dy;
+                    qmin = (ta + tb + tc) - 4e-6f * (fabsf(ta) + fabsf(tb) + fabsf(tc));
+                }
+                {
+                    const float dy = hy - 1.f;
+                    const float dxs = fminf(hx, fmaxf(hx - 15.f, __fdividef(-cB * dy, cA)));
+                    const float ta = 0.5f * cA * dxs * dxs, tb = cB * dxs * dy, tc = 0.5f * cC * dy * dy;
+                    qmin = fminf(qmin, (ta + tb + tc) - 4e-6f * (fabsf(ta) + fabsf(tb) + fabsf(tc)));
+                }
+                // reject only when provably alpha < 1/255 on all 32 pixels; NaNs / non-convex -> keep
+                keep = !(cA > 0.f) || !(qmin > t1.w + 0.05f);
+            }
+            uint32_t mask = __ballot_sync(0xffffffffu, keep);
+            while (mask) {
+                const int j = jb + __ffs(mask) - 1;
+                mask &= mask - 1;
+                if (done) continue;
+                const float4 q0 = *reinterpret_cast<const float4*>(&S.rec[s][j][0]);
+                const float4 q1 = *reinterpret_cast<const float4*>(&S.rec[s][j][4]);
+                const float2 d = {q0.x - pixf.x, q0.y - pixf.y};
+                const float power = -0.5f * (q0.z * d.x * d.x + q1.x * d.y * d.y) - q0.w * d.x * d.y;
+                if (power > 0.0f) continue;
+                const float alpha = fminf(0.99f, q1.y * expf(power));
+                if (alpha < 1.0f / 255.0f) continue;
+                const float test_T = T * (1 - alpha);
+                if (test_T < 0.0001f) {
+                    done = true;
+                    continue;
+                }
+                const float weight = alpha * T;
+                const float4 q2 = *reinterpret_cast<const float4*>(&S.rec[s][j][8]);
+                C[0] += q2.x * weight;
+                C[1] += q2.y * weight;
+                C[2] += q2.z * weight;
+                const float depth = q1.z;
+                if (!LITE) {
+                    const float4 q3 = *reinterpret_cast<const float4*>(&S.rec[s][j][12]);
+                    const float4 q4 = *reinterpret_cast<const float4*>(&S.rec[s][j][16]);
+                    const float2 q5 = *reinterpret_cast<const float2*>(&S.rec[s][j][20]);
+                    A[0] += q3.x * weight;
+                    A[1] += q3.y * weight;
+                    A[2] += q3.z * weight;
+                    N[0] += q4.x * weight;
+                    N[1] += q4.y * weight;
+                    N[2] += q4.z * weight;
+                    Rg += q2.w * weight;
+                    Mt += q3.w * weight;
+                    POS.x += q4.w * weight;
+                    POS.y += q5.x * weight;
+                    POS.z += q5.y * weight;
+                    if (weight > max_weight) except_pos = make_float3(q4.w, q5.x, q5.y);
+                }
+                D += depth * weight;
+                O += weight;
+                if (weight > max_weight) {
+                    except_depth = depth;
+                    max_weight = weight;
+                }
+                T = test_T;
+                last_contributor = (uint32_t)(b * BL_BATCH + j + 1);
+            }
+            warp_done = __all_sync(0xffffffffu, done);
+        }
+        // block vote doubles as the release barrier of stage s
+        if (__syncthreads_and(done)) {
+            if (b + 1 < rounds) mbar_wait(&S.bar[s ^ 1], (uint32_t)(((b + 1) >> 1) & 1));  // drain in-flight copy
+            break;
+        }
+    }
+
+    if (inside) {
+        const int HW = H * W;
+        final_T[pix_id] = T;
+        n_contrib[pix_id] = last_contributor;
+        for (int ch = 0; ch < 3; ch++) out_color[ch * HW + pix_id] = C[ch] + T * bg_color[ch];
+        if (!LITE) {
+            const float* V = viewmatrix;
+            float3 Nv;
+            Nv.x = V[0] * N[0] + V[4] * N[1] + V[8] * N[2];
+            Nv.y = V[1] * N[0] + V[5] * N[1] + V[9] * N[2];
+            Nv.z = V[2] * N[0] + V[6] * N[1] + V[10] * N[2];
+            Nv = normalize3(Nv);  // NaN where N == 0, as in the reference
+            out_normal_view[pix_id] = Nv.x;
+            out_normal_view[HW + pix_id] = Nv.y;
+            out_normal_view[2 * HW + pix_id] = Nv.z;
+            for (int ch = 0; ch < 3; ch++) {
+                out_normal[ch * HW + pix_id] = N[ch];
+                out_albedo[ch * HW + pix_id] = A[ch];
+            }
+            out_roughness[pix_id] = inference ? (Rg + T) : Rg;
+            out_metallic[pix_id] = Mt;
+        }
+        if (O > 1e-6) {
+            out_depth[pix_id] = argmax_depth ? except_depth : D / O;
+            if (!LITE) {
+                out_pos[pix_id] = argmax_depth ? except_pos.x : POS.x / O;
+                out_pos[HW + pix_id] = argmax_depth ? except_pos.y : POS.y / O;
+                out_pos[2 * HW + pix_id] = argmax_depth ? except_pos.z : POS.z / O;
+            }
+        } else {
+            out_depth[pix_id] = 0.0f;
+            if (!LITE) {
+                out_pos[pix_id] = 0.0f;
+                out_pos[HW + pix_id] = 0.0f;
+                out_pos[2 * HW + pix_id] = 0.0f;
+            }
+        }
+        out_opacity[pix_id] = O;
+    }
+}
+
+int launch_blend_forward(const GigsRasterFwd* a, const Layout& L, bool lite, cudaStream_t st)
+{
+    const GigsCamera& c = a->cam;
+    const char* g = (const char*)a->geom;
+    char* im = (char*)a->img;
+    const char* bn = (const char*)a->binning;
+    dim3 grid(L.tiles_x, L.tiles_y, 1), block(TILE_X, TILE_Y, 1);
+    static bool attr_set = false;
+    if (!attr_set) {
+        GIGS_CUDA(cudaFuncSetAttribute(blend_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(BlendSmem)));
+        GIGS_CUDA(cudaFuncSetAttribute(blend_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(BlendSmem)));
+        attr_set = true;
+    }
+    const uint2* ranges = (const uint2*)(im + L.off.i_ranges);
+    const uint32_t* plist = (const uint32_t*)(bn + L.off.b_point_list);
+    const float* recs = (const float*)(g + L.off.g_record);
+    uint32_t* ncontrib = (uint32_t*)(im + L.off.i_n_contrib);
+    float* finalT = (float*)(im + L.off.i_final_T);
+    if (lite)
+        blend_forward_kernel<true><<<grid, block, sizeof(BlendSmem), st>>>(
+            c.width, c.height, ranges, plist, recs, c.viewmatrix, c.bg, ncontrib, finalT, a->out_color, a->out_opacity,
+            a->out_depth, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, c.argmax_depth != 0, false);
+    else
+        blend_forward_kernel<false><<<grid, block, sizeof(BlendSmem), st>>>(
+            c.width, c.height, ranges, plist, recs, c.viewmatrix, c.bg, ncontrib, finalT, a->out_color, a->out_opacity,
+            a->out_depth, a->out_normal, a->out_normal_view, a->out_pos, a->out_albedo, a->out_roughness,
+            a->out_metallic, c.argmax_depth != 0, c.inference != 0);
+    GIGS_LAUNCH_CHECK("blend_forward_kernel");
+    return 0;
+}
+
+}  // namespace gigs

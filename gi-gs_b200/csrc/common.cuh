@@ -1,0 +1,208 @@
+// Shared device/host helpers for the gigs_b200 kernels (sm_100a only).
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+#include "../../include/gigs_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "gigs_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace gigs {
+
+constexpr int TILE_X = 16;       // reference config.h:16-17 (the tile size is part of the key contract)
+constexpr int TILE_Y = 16;
+constexpr int TILE_PIX = TILE_X * TILE_Y;
+constexpr int REC_FLOATS = 24;   // packed blend record, 96 B, 16-B aligned (DESIGN.md "HBM layout")
+constexpr int ACC_FLOATS = 20;   // packed per-Gaussian gradient accumulator, 80 B
+
+// record slots
+enum : int {
+    R_X = 0, R_Y = 1, R_CA = 2, R_CB = 3,           // float4 #0: mean2D.xy, conic.x, conic.y
+    R_CC = 4, R_OP = 5, R_DEPTH = 6, R_TAU = 7,      // float4 #1: conic.z, opacity, depth, ln(255*opacity)
+    R_RGB = 8, R_ROUGH = 11,                         // float4 #2
+    R_ALB = 12, R_METAL = 15,                        // float4 #3
+    R_NRM = 16, R_PX = 19,                           // float4 #4
+    R_PY = 20, R_PZ = 21                             // float4 #5 (22,23 spare)
+};
+// accumulator slots
+enum : int {
+    A_COL = 0, A_DEPTH = 3,      // {color3, depth}
+    A_NRM = 4, A_ROUGH = 7,      // {normal3, roughness}
+    A_ALB = 8, A_METAL = 11,     // {albedo3, metallic}
+    A_M2X = 12, A_M2Y = 13, A_M2Z = 14, A_OPAC = 15,  // {mean2D.xyz, opacity}
+    A_CX = 16, A_CY = 17, A_CW = 18                   // {conic.x, .y, .w, -}
+};
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define GIGS_CUDA(call)                                          \
+    do {                                                         \
+        cudaError_t _e = (call);                                 \
+        if (_e != cudaSuccess) return gigs::cuda_fail(_e, #call); \
+    } while (0)
+#define GIGS_LAUNCH_CHECK(name)                                  \
+    do {                                                         \
+        cudaError_t _e = cudaGetLastError();                     \
+        if (_e != cudaSuccess) return gigs::cuda_fail(_e, name); \
+    } while (0)
+
+__host__ __device__ inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------------
+// Workspace layout: pure function of (P, W, H, R).
+// ---------------------------------------------------------------------------------------------
+struct Layout {
+    GigsLayout off;
+    GigsSizes size;
+    uint32_t tiles_x, tiles_y, num_tiles, num_blocks;
+    // sort scratch internals
+    uint64_t s_keys_a, s_keys_b, s_vals_b, s_hist, s_status, s_ticket;
+    uint32_t sort_tiles, sort_passes, sort_bits;
+};
+Layout make_layout(int P, int W, int H, uint64_t R);
+uint32_t higher_msb(uint32_t n);
+
+// ---------------------------------------------------------------------------------------------
+// Minimal column-major 3x3 matrix with the SAME expression shapes as the math library the
+// reference uses for mat3*mat3 / transpose, so that nvcc contracts FMAs identically and tile keys
+// come out bit-exact (SURVEY.md "Hard parts"). m[c][r], constructor takes columns.
+// ---------------------------------------------------------------------------------------------
+struct Mat3 {
+    float m[3][3];
+};
+__device__ __forceinline__ Mat3 mat3_cols(float c00, float c01, float c02, float c10, float c11, float c12,
+                                          float c20, float c21, float c22)
+{
+    Mat3 r;
+    r.m[0][0] = c00; r.m[0][1] = c01; r.m[0][2] = c02;
+    r.m[1][0] = c10; r.m[1][1] = c11; r.m[1][2] = c12;
+    r.m[2][0] = c20; r.m[2][1] = c21; r.m[2][2] = c22;
+    return r;
+}
+__device__ __forceinline__ Mat3 mat3_mul(const Mat3& a, const Mat3& b)
+{
+    // result[c][r] = a[0][r]*b[c][0] + a[1][r]*b[c][1] + a[2][r]*b[c][2]
+    Mat3 r;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+        for (int rr = 0; rr < 3; ++rr) {
+            r.m[c][rr] = a.m[0][rr] * b.m[c][0] + a.m[1][rr] * b.m[c][1] + a.m[2][rr] * b.m[c][2];
+        }
+    }
+    return r;
+}
+__device__ __forceinline__ Mat3 mat3_transpose(const Mat3& a)
+{
+    Mat3 r;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int rr = 0; rr < 3; ++rr) r.m[c][rr] = a.m[rr][c];
+    return r;
+}
+
+// reference auxiliary.h:58-66 / :68-77 expression order (column-major 4x4 in a float[16])
+__device__ __forceinline__ float3 xform_point_4x3(const float3& p, const float* __restrict__ M)
+{
+    float3 t;
+    t.x = M[0] * p.x + M[4] * p.y + M[8] * p.z + M[12];
+    t.y = M[1] * p.x + M[5] * p.y + M[9] * p.z + M[13];
+    t.z = M[2] * p.x + M[6] * p.y + M[10] * p.z + M[14];
+    return t;
+}
+__device__ __forceinline__ float4 xform_point_4x4(const float3& p, const float* __restrict__ M)
+{
+    float4 t;
+    t.x = M[0] * p.x + M[4] * p.y + M[8] * p.z + M[12];
+    t.y = M[1] * p.x + M[5] * p.y + M[9] * p.z + M[13];
+    t.z = M[2] * p.x + M[6] * p.y + M[10] * p.z + M[14];
+    t.w = M[3] * p.x + M[7] * p.y + M[11] * p.z + M[15];
+    return t;
+}
+
+// reference auxiliary.h:41-44: evaluated in double because of the un-suffixed literals
+__device__ __forceinline__ float ndc_to_pix(float v, int S) { return ((v + 1.0) * S - 1.0) * 0.5; }
+
+// reference auxiliary.h:46-56
+__device__ __forceinline__ void tile_rect(float px, float py, int max_radius, uint32_t gx, uint32_t gy,
+                                          uint2& rmin, uint2& rmax)
+{
+    rmin.x = min(gx, (uint32_t)max((int)0, (int)((px - max_radius) / TILE_X)));
+    rmin.y = min(gy, (uint32_t)max((int)0, (int)((py - max_radius) / TILE_Y)));
+    rmax.x = min(gx, (uint32_t)max((int)0, (int)((px + max_radius + TILE_X - 1) / TILE_X)));
+    rmax.y = min(gy, (uint32_t)max((int)0, (int)((py + max_radius + TILE_Y - 1) / TILE_Y)));
+}
+
+// float3 helpers with the reference's vec_math.h shapes (normalize = v * (1/sqrtf(dot)))
+__device__ __forceinline__ float dot3(const float3& a, const float3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float3 cross3(const float3& a, const float3& b)
+{
+    return make_float3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ float3 normalize3(const float3& v)
+{
+    float inv = 1.0f / sqrtf(dot3(v, v));
+    return make_float3(v.x * inv, v.y * inv, v.z * inv);
+}
+__device__ __forceinline__ float3 sub3(const float3& a, const float3& b) { return make_float3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 add3(const float3& a, const float3& b) { return make_float3(a.x + b.x, a.y + b.y, a.z + b.z); }
+
+// ---------------------------------------------------------------------------------------------
+// PTX: mbarrier + bulk async copy (TMA, SASS UBLKCP) + vector reductions
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy; bytes multiple of 16, both addresses 16-B aligned
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red_add_f32(float* addr, float a)
+{
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
+}
+__device__ __forceinline__ float4 ld_nc_f4(const float* p)
+{
+    float4 r;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+}  // namespace gigs

@@ -1,0 +1,356 @@
+// Per-Gaussian backward: one fused kernel replacing computeCov2DCUDA + backward preprocessCUDA
+// (reference cuda_rasterizer/backward.cu:145-279, :351-401, SH/cov3D helpers :21-140, :283-346) and
+// the 14 torch::zeros fills that precede them (rasterize_points.cu:299-312).
+//
+// Reads the packed 80-B accumulator row the blend backward reduced into, chains through conic ->
+// cov2D -> cov3D -> (scale, quaternion), mean2D -> mean3D, colour -> SH (+ view-direction term),
+// and writes EVERY output element exactly once (zeros for Gaussians with radius <= 0), so the
+// caller can hand in uninitialised tensors.
+#include "common.cuh"
+
+namespace gigs {
+
+__device__ const float bSH_C0 = 0.28209479177387814f;
+__device__ const float bSH_C1 = 0.4886025119029199f;
+__device__ const float bSH_C2[] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                   -1.0925484305920792f, 0.5462742152960396f};
+__device__ const float bSH_C3[] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
+                                   -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f};
+
+struct B3 {
+    float x, y, z;
+};
+__device__ __forceinline__ B3 operator*(float s, const B3& v) { return {s * v.x, s * v.y, s * v.z}; }
+__device__ __forceinline__ B3 operator*(const B3& v, float s) { return {v.x * s, v.y * s, v.z * s}; }
+__device__ __forceinline__ B3 operator+(const B3& a, const B3& b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ B3 operator-(const B3& a) { return {-a.x, -a.y, -a.z}; }
+__device__ __forceinline__ void operator+=(B3& a, const B3& b) { a.x += b.x; a.y += b.y; a.z += b.z; }
+__device__ __forceinline__ float dotB(const B3& a, const B3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+
+constexpr int GB_THREADS = 128;
+
+__global__ void __launch_bounds__(GB_THREADS)
+gaussian_backward_kernel(const int P, const int D, const int M, const float* __restrict__ means3D,
+                         const int* __restrict__ radii, const float* __restrict__ shs,
+                         const uint8_t* __restrict__ clamped, const float* __restrict__ scales,
+                         const float* __restrict__ rotations, const float scale_modifier,
+                         const float* __restrict__ cov3Ds, const float* __restrict__ view_matrix,
+                         const float* __restrict__ proj, const float* __restrict__ campos, const float h_x,
+                         const float h_y, const float tan_fovx, const float tan_fovy,
+                         const float* __restrict__ accum,
+                         // outputs
+                         float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic_out,
+                         float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolor,
+                         float* __restrict__ dL_dnormal, float* __restrict__ dL_dalbedo,
+                         float* __restrict__ dL_droughness, float* __restrict__ dL_dmetallic,
+                         float* __restrict__ dL_dmean3D, float* __restrict__ dL_dcov3D, float* __restrict__ dL_dsh,
+                         float* __restrict__ dL_dscale, float* __restrict__ dL_drot)
+{
+    const int idx = blockIdx.x * GB_THREADS + threadIdx.x;
+    if (idx >= P) return;
+    const bool visible = radii[idx] > 0;
+
+    float acc[ACC_FLOATS];
+    if (visible) {
+        const float4* row = reinterpret_cast<const float4*>(accum + (size_t)idx * ACC_FLOATS);
+#pragma unroll
+        for (int k = 0; k < ACC_FLOATS / 4; ++k) {
+            const float4 t = row[k];
+            acc[4 * k + 0] = t.x; acc[4 * k + 1] = t.y; acc[4 * k + 2] = t.z; acc[4 * k + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < ACC_FLOATS; ++k) acc[k] = 0.f;
+    }
+
+    // direct per-Gaussian outputs of the blend backward
+    dL_dmean2D[3 * idx + 0] = acc[A_M2X];
+    dL_dmean2D[3 * idx + 1] = acc[A_M2Y];
+    dL_dmean2D[3 * idx + 2] = acc[A_M2Z];
+    if (dL_dconic_out) {
+        *reinterpret_cast<float4*>(dL_dconic_out + 4 * (size_t)idx) = make_float4(acc[A_CX], acc[A_CY], 0.f, acc[A_CW]);
+    }
+    dL_dopacity[idx] = acc[A_OPAC];
+    dL_droughness[idx] = acc[A_ROUGH];
+    dL_dmetallic[idx] = acc[A_METAL];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        dL_dcolor[3 * idx + c] = acc[A_COL + c];
+        dL_dnormal[3 * idx + c] = acc[A_NRM + c];
+        dL_dalbedo[3 * idx + c] = acc[A_ALB + c];
+    }
+
+    if (!visible) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) dL_dmean3D[3 * idx + c] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) dL_dcov3D[6 * idx + c] = 0.f;
+        if (dL_dsh)
+            for (int c = 0; c < 3 * M; ++c) dL_dsh[(size_t)idx * 3 * M + c] = 0.f;
+        if (dL_dscale)
+            for (int c = 0; c < 3; ++c) dL_dscale[3 * idx + c] = 0.f;
+        if (dL_drot)
+            *reinterpret_cast<float4*>(dL_drot + 4 * (size_t)idx) = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+
+    // ------------------------------------------------------------------ cov2D backward
+    const float* cov3D = cov3Ds + 6 * (size_t)idx;
+    const float3 mean = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
+    const float3 dL_dconic = {acc[A_CX], acc[A_CY], acc[A_CW]};
+    const float dL_ddepth = acc[A_DEPTH];
+    float3 t = xform_point_4x3(mean, view_matrix);
+
+    const float limx = 1.3f * tan_fovx;
+    const float limy = 1.3f * tan_fovy;
+    const float txtz = t.x / t.z;
+    const float tytz = t.y / t.z;
+    t.x = fminf(limx, fmaxf(-limx, txtz)) * t.z;
+    t.y = fminf(limy, fmaxf(-limy, tytz)) * t.z;
+    const float x_grad_mul = txtz < -limx || txtz > limx ? 0 : 1;
+    const float y_grad_mul = tytz < -limy || tytz > limy ? 0 : 1;
+
+    Mat3 J = mat3_cols(h_x / t.z, 0.0f, -(h_x * t.x) / (t.z * t.z), 0.0f, h_y / t.z, -(h_y * t.y) / (t.z * t.z), 0, 0,
+                       0);
+    Mat3 Wm = mat3_cols(view_matrix[0], view_matrix[4], view_matrix[8], view_matrix[1], view_matrix[5],
+                        view_matrix[9], view_matrix[2], view_matrix[6], view_matrix[10]);
+    Mat3 Vrk = mat3_cols(cov3D[0], cov3D[1], cov3D[2], cov3D[1], cov3D[3], cov3D[4], cov3D[2], cov3D[4], cov3D[5]);
+    Mat3 T = mat3_mul(Wm, J);
+    Mat3 cov2D = mat3_mul(mat3_mul(mat3_transpose(T), mat3_transpose(Vrk)), T);
+
+    const float a = cov2D.m[0][0] += 0.3f;
+    const float b = cov2D.m[0][1];
+    const float c = cov2D.m[1][1] += 0.3f;
+
+    const float denom = a * c - b * b;
+    float dL_da = 0, dL_db = 0, dL_dc = 0;
+    const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+
+    float dcov[6];
+    if (denom2inv != 0) {
+        dL_da = denom2inv * (-c * c * dL_dconic.x + 2 * b * c * dL_dconic.y + (denom - a * c) * dL_dconic.z);
+        dL_dc = denom2inv * (-a * a * dL_dconic.z + 2 * a * b * dL_dconic.y + (denom - a * c) * dL_dconic.x);
+        dL_db = denom2inv * 2 * (b * c * dL_dconic.x - (denom + 2 * b * b) * dL_dconic.y + a * b * dL_dconic.z);
+
+        dcov[0] = (T.m[0][0] * T.m[0][0] * dL_da + T.m[0][0] * T.m[1][0] * dL_db + T.m[1][0] * T.m[1][0] * dL_dc);
+        dcov[3] = (T.m[0][1] * T.m[0][1] * dL_da + T.m[0][1] * T.m[1][1] * dL_db + T.m[1][1] * T.m[1][1] * dL_dc);
+        dcov[5] = (T.m[0][2] * T.m[0][2] * dL_da + T.m[0][2] * T.m[1][2] * dL_db + T.m[1][2] * T.m[1][2] * dL_dc);
+        dcov[1] = 2 * T.m[0][0] * T.m[0][1] * dL_da + (T.m[0][0] * T.m[1][1] + T.m[0][1] * T.m[1][0]) * dL_db +
+                  2 * T.m[1][0] * T.m[1][1] * dL_dc;
+        dcov[2] = 2 * T.m[0][0] * T.m[0][2] * dL_da + (T.m[0][0] * T.m[1][2] + T.m[0][2] * T.m[1][0]) * dL_db +
+                  2 * T.m[1][0] * T.m[1][2] * dL_dc;
+        dcov[4] = 2 * T.m[0][2] * T.m[0][1] * dL_da + (T.m[0][1] * T.m[1][2] + T.m[0][2] * T.m[1][1]) * dL_db +
+                  2 * T.m[1][1] * T.m[1][2] * dL_dc;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 6; i++) dcov[i] = 0;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) dL_dcov3D[6 * (size_t)idx + i] = dcov[i];
+
+    const float dL_dT00 = 2 * (T.m[0][0] * Vrk.m[0][0] + T.m[0][1] * Vrk.m[0][1] + T.m[0][2] * Vrk.m[0][2]) * dL_da +
+                          (T.m[1][0] * Vrk.m[0][0] + T.m[1][1] * Vrk.m[0][1] + T.m[1][2] * Vrk.m[0][2]) * dL_db;
+    const float dL_dT01 = 2 * (T.m[0][0] * Vrk.m[1][0] + T.m[0][1] * Vrk.m[1][1] + T.m[0][2] * Vrk.m[1][2]) * dL_da +
+                          (T.m[1][0] * Vrk.m[1][0] + T.m[1][1] * Vrk.m[1][1] + T.m[1][2] * Vrk.m[1][2]) * dL_db;
+    const float dL_dT02 = 2 * (T.m[0][0] * Vrk.m[2][0] + T.m[0][1] * Vrk.m[2][1] + T.m[0][2] * Vrk.m[2][2]) * dL_da +
+                          (T.m[1][0] * Vrk.m[2][0] + T.m[1][1] * Vrk.m[2][1] + T.m[1][2] * Vrk.m[2][2]) * dL_db;
+    const float dL_dT10 = 2 * (T.m[1][0] * Vrk.m[0][0] + T.m[1][1] * Vrk.m[0][1] + T.m[1][2] * Vrk.m[0][2]) * dL_dc +
+                          (T.m[0][0] * Vrk.m[0][0] + T.m[0][1] * Vrk.m[0][1] + T.m[0][2] * Vrk.m[0][2]) * dL_db;
+    const float dL_dT11 = 2 * (T.m[1][0] * Vrk.m[1][0] + T.m[1][1] * Vrk.m[1][1] + T.m[1][2] * Vrk.m[1][2]) * dL_dc +
+                          (T.m[0][0] * Vrk.m[1][0] + T.m[0][1] * Vrk.m[1][1] + T.m[0][2] * Vrk.m[1][2]) * dL_db;
+    const float dL_dT12 = 2 * (T.m[1][0] * Vrk.m[2][0] + T.m[1][1] * Vrk.m[2][1] + T.m[1][2] * Vrk.m[2][2]) * dL_dc +
+                          (T.m[0][0] * Vrk.m[2][0] + T.m[0][1] * Vrk.m[2][1] + T.m[0][2] * Vrk.m[2][2]) * dL_db;
+
+    const float dL_dJ00 = Wm.m[0][0] * dL_dT00 + Wm.m[0][1] * dL_dT01 + Wm.m[0][2] * dL_dT02;
+    const float dL_dJ02 = Wm.m[2][0] * dL_dT00 + Wm.m[2][1] * dL_dT01 + Wm.m[2][2] * dL_dT02;
+    const float dL_dJ11 = Wm.m[1][0] * dL_dT10 + Wm.m[1][1] * dL_dT11 + Wm.m[1][2] * dL_dT12;
+    const float dL_dJ12 = Wm.m[2][0] * dL_dT10 + Wm.m[2][1] * dL_dT11 + Wm.m[2][2] * dL_dT12;
+
+    const float tz = 1.f / t.z;
+    const float tz2 = tz * tz;
+    const float tz3 = tz2 * tz;
+
+    const float dL_dtx = x_grad_mul * -h_x * tz2 * dL_dJ02;
+    const float dL_dty = y_grad_mul * -h_y * tz2 * dL_dJ12;
+    const float dL_dtz = -h_x * tz2 * dL_dJ00 - h_y * tz2 * dL_dJ11 + (2 * h_x * t.x) * tz3 * dL_dJ02 +
+                         (2 * h_y * t.y) * tz3 * dL_dJ12;
+
+    // transformVec4x3Transpose + depth term (backward.cu:270-273)
+    B3 dmean;
+    dmean.x = view_matrix[0] * dL_dtx + view_matrix[1] * dL_dty + view_matrix[2] * dL_dtz;
+    dmean.y = view_matrix[4] * dL_dtx + view_matrix[5] * dL_dty + view_matrix[6] * dL_dtz;
+    dmean.z = view_matrix[8] * dL_dtx + view_matrix[9] * dL_dty + view_matrix[10] * dL_dtz;
+    dmean.x += view_matrix[2] * dL_ddepth;
+    dmean.y += view_matrix[6] * dL_ddepth;
+    dmean.z += view_matrix[10] * dL_ddepth;
+
+    // ------------------------------------------------------------------ mean2D -> mean3D
+    {
+        const float3 m = mean;
+        const float4 m_hom = xform_point_4x4(m, proj);
+        const float m_w = 1.0f / (m_hom.w + 0.0000001f);
+        const float mul1 = (proj[0] * m.x + proj[4] * m.y + proj[8] * m.z + proj[12]) * m_w * m_w;
+        const float mul2 = (proj[1] * m.x + proj[5] * m.y + proj[9] * m.z + proj[13]) * m_w * m_w;
+        const float gx = acc[A_M2X], gy = acc[A_M2Y];
+        B3 d2;
+        d2.x = (proj[0] * m_w - proj[3] * mul1) * gx + (proj[1] * m_w - proj[3] * mul2) * gy;
+        d2.y = (proj[4] * m_w - proj[7] * mul1) * gx + (proj[5] * m_w - proj[7] * mul2) * gy;
+        d2.z = (proj[8] * m_w - proj[11] * mul1) * gx + (proj[9] * m_w - proj[11] * mul2) * gy;
+        dmean += d2;
+    }
+
+    // ------------------------------------------------------------------ colour -> SH (+ dir term)
+    if (shs) {
+        const B3 pos = {mean.x, mean.y, mean.z};
+        const B3 cam = {campos[0], campos[1], campos[2]};
+        const B3 dir_orig = {pos.x - cam.x, pos.y - cam.y, pos.z - cam.z};
+        const float len = sqrtf(dotB(dir_orig, dir_orig));
+        const B3 dir = {dir_orig.x / len, dir_orig.y / len, dir_orig.z / len};
+        const float* shp = shs + (size_t)idx * M * 3;
+        auto SH = [&](int i) -> B3 { return {shp[3 * i + 0], shp[3 * i + 1], shp[3 * i + 2]}; };
+        float* dshp = dL_dsh + (size_t)idx * M * 3;
+        auto DSH = [&](int i, const B3& v) {
+            dshp[3 * i + 0] = v.x;
+            dshp[3 * i + 1] = v.y;
+            dshp[3 * i + 2] = v.z;
+        };
+        const uchar4 cl = *reinterpret_cast<const uchar4*>(clamped + 4 * (size_t)idx);
+        B3 dL_dRGB = {acc[A_COL + 0], acc[A_COL + 1], acc[A_COL + 2]};
+        dL_dRGB.x *= cl.x ? 0 : 1;
+        dL_dRGB.y *= cl.y ? 0 : 1;
+        dL_dRGB.z *= cl.z ? 0 : 1;
+
+        B3 dRGBdx = {0, 0, 0}, dRGBdy = {0, 0, 0}, dRGBdz = {0, 0, 0};
+        const float x = dir.x, y = dir.y, z = dir.z;
+        DSH(0, bSH_C0 * dL_dRGB);
+        int written = 1;
+        if (D > 0) {
+            DSH(1, (-bSH_C1 * y) * dL_dRGB);
+            DSH(2, (bSH_C1 * z) * dL_dRGB);
+            DSH(3, (-bSH_C1 * x) * dL_dRGB);
+            written = 4;
+            dRGBdx = -bSH_C1 * SH(3);
+            dRGBdy = -bSH_C1 * SH(1);
+            dRGBdz = bSH_C1 * SH(2);
+            if (D > 1) {
+                const float xx = x * x, yy = y * y, zz = z * z;
+                const float xy = x * y, yz = y * z, xz = x * z;
+                DSH(4, (bSH_C2[0] * xy) * dL_dRGB);
+                DSH(5, (bSH_C2[1] * yz) * dL_dRGB);
+                DSH(6, (bSH_C2[2] * (2.f * zz - xx - yy)) * dL_dRGB);
+                DSH(7, (bSH_C2[3] * xz) * dL_dRGB);
+                DSH(8, (bSH_C2[4] * (xx - yy)) * dL_dRGB);
+                written = 9;
+                dRGBdx += bSH_C2[0] * y * SH(4) + bSH_C2[2] * 2.f * -x * SH(6) + bSH_C2[3] * z * SH(7) +
+                          bSH_C2[4] * 2.f * x * SH(8);
+                dRGBdy += bSH_C2[0] * x * SH(4) + bSH_C2[1] * z * SH(5) + bSH_C2[2] * 2.f * -y * SH(6) +
+                          bSH_C2[4] * 2.f * -y * SH(8);
+                dRGBdz += bSH_C2[1] * y * SH(5) + bSH_C2[2] * 2.f * 2.f * z * SH(6) + bSH_C2[3] * x * SH(7);
+                if (D > 2) {
+                    DSH(9, (bSH_C3[0] * y * (3.f * xx - yy)) * dL_dRGB);
+                    DSH(10, (bSH_C3[1] * xy * z) * dL_dRGB);
+                    DSH(11, (bSH_C3[2] * y * (4.f * zz - xx - yy)) * dL_dRGB);
+                    DSH(12, (bSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy)) * dL_dRGB);
+                    DSH(13, (bSH_C3[4] * x * (4.f * zz - xx - yy)) * dL_dRGB);
+                    DSH(14, (bSH_C3[5] * z * (xx - yy)) * dL_dRGB);
+                    DSH(15, (bSH_C3[6] * x * (xx - 3.f * yy)) * dL_dRGB);
+                    written = 16;
+                    dRGBdx += (bSH_C3[0] * SH(9) * 3.f * 2.f * xy + bSH_C3[1] * SH(10) * yz +
+                               bSH_C3[2] * SH(11) * -2.f * xy + bSH_C3[3] * SH(12) * -3.f * 2.f * xz +
+                               bSH_C3[4] * SH(13) * (-3.f * xx + 4.f * zz - yy) + bSH_C3[5] * SH(14) * 2.f * xz +
+                               bSH_C3[6] * SH(15) * 3.f * (xx - yy));
+                    dRGBdy += (bSH_C3[0] * SH(9) * 3.f * (xx - yy) + bSH_C3[1] * SH(10) * xz +
+                               bSH_C3[2] * SH(11) * (-3.f * yy + 4.f * zz - xx) +
+                               bSH_C3[3] * SH(12) * -3.f * 2.f * yz + bSH_C3[4] * SH(13) * -2.f * xy +
+                               bSH_C3[5] * SH(14) * -2.f * yz + bSH_C3[6] * SH(15) * -3.f * 2.f * xy);
+                    dRGBdz += (bSH_C3[1] * SH(10) * xy + bSH_C3[2] * SH(11) * 4.f * 2.f * yz +
+                               bSH_C3[3] * SH(12) * 3.f * (2.f * zz - xx - yy) +
+                               bSH_C3[4] * SH(13) * 4.f * 2.f * xz + bSH_C3[5] * SH(14) * (xx - yy));
+                }
+            }
+        }
+        // coefficients above the active degree get no gradient (zeros in the reference's pre-filled tensor)
+        for (int i = written; i < M; ++i) DSH(i, B3{0.f, 0.f, 0.f});
+
+        const B3 dL_ddir = {dotB(dRGBdx, dL_dRGB), dotB(dRGBdy, dL_dRGB), dotB(dRGBdz, dL_dRGB)};
+        // dnormvdv (auxiliary.h:120-131)
+        const B3 v = dir_orig, dv = dL_ddir;
+        const float sum2 = v.x * v.x + v.y * v.y + v.z * v.z;
+        const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
+        B3 dn;
+        dn.x = ((+sum2 - v.x * v.x) * dv.x - v.y * v.x * dv.y - v.z * v.x * dv.z) * invsum32;
+        dn.y = (-v.x * v.y * dv.x + (sum2 - v.y * v.y) * dv.y - v.z * v.y * dv.z) * invsum32;
+        dn.z = (-v.x * v.z * dv.x - v.y * v.z * dv.y + (sum2 - v.z * v.z) * dv.z) * invsum32;
+        dmean += dn;
+    }
+    dL_dmean3D[3 * idx + 0] = dmean.x;
+    dL_dmean3D[3 * idx + 1] = dmean.y;
+    dL_dmean3D[3 * idx + 2] = dmean.z;
+
+    // ------------------------------------------------------------------ cov3D -> scale, quaternion
+    if (scales) {
+        const float4 q = *reinterpret_cast<const float4*>(rotations + 4 * (size_t)idx);
+        const float r = q.x, x = q.y, y = q.z, z = q.w;
+        Mat3 R = mat3_cols(1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y),
+                           2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x),
+                           2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y));
+        Mat3 S = mat3_cols(1.0f, 0.0f, 0.0f, 0.0f, 1.0f, 0.0f, 0.0f, 0.0f, 1.0f);
+        const float3 s = {scale_modifier * scales[3 * idx], scale_modifier * scales[3 * idx + 1],
+                          scale_modifier * scales[3 * idx + 2]};
+        S.m[0][0] = s.x;
+        S.m[1][1] = s.y;
+        S.m[2][2] = s.z;
+        Mat3 Mm = mat3_mul(S, R);
+        Mat3 dL_dSigma = mat3_cols(dcov[0], 0.5f * dcov[1], 0.5f * dcov[2], 0.5f * dcov[1], dcov[3], 0.5f * dcov[4],
+                                   0.5f * dcov[2], 0.5f * dcov[4], dcov[5]);
+        // dL_dM = 2 * M * dL_dSigma  (scalar*matrix first, then product)
+        Mat3 M2;
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc)
+#pragma unroll
+            for (int rr = 0; rr < 3; ++rr) M2.m[cc][rr] = 2.0f * Mm.m[cc][rr];
+        Mat3 dL_dM = mat3_mul(M2, dL_dSigma);
+        Mat3 Rt = mat3_transpose(R);
+        Mat3 dL_dMt = mat3_transpose(dL_dM);
+
+        dL_dscale[3 * idx + 0] = Rt.m[0][0] * dL_dMt.m[0][0] + Rt.m[0][1] * dL_dMt.m[0][1] + Rt.m[0][2] * dL_dMt.m[0][2];
+        dL_dscale[3 * idx + 1] = Rt.m[1][0] * dL_dMt.m[1][0] + Rt.m[1][1] * dL_dMt.m[1][1] + Rt.m[1][2] * dL_dMt.m[1][2];
+        dL_dscale[3 * idx + 2] = Rt.m[2][0] * dL_dMt.m[2][0] + Rt.m[2][1] * dL_dMt.m[2][1] + Rt.m[2][2] * dL_dMt.m[2][2];
+
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            dL_dMt.m[0][k] *= s.x;
+            dL_dMt.m[1][k] *= s.y;
+            dL_dMt.m[2][k] *= s.z;
+        }
+        float4 dq;
+        dq.x = 2 * z * (dL_dMt.m[0][1] - dL_dMt.m[1][0]) + 2 * y * (dL_dMt.m[2][0] - dL_dMt.m[0][2]) +
+               2 * x * (dL_dMt.m[1][2] - dL_dMt.m[2][1]);
+        dq.y = 2 * y * (dL_dMt.m[1][0] + dL_dMt.m[0][1]) + 2 * z * (dL_dMt.m[2][0] + dL_dMt.m[0][2]) +
+               2 * r * (dL_dMt.m[1][2] - dL_dMt.m[2][1]) - 4 * x * (dL_dMt.m[2][2] + dL_dMt.m[1][1]);
+        dq.z = 2 * x * (dL_dMt.m[1][0] + dL_dMt.m[0][1]) + 2 * r * (dL_dMt.m[2][0] - dL_dMt.m[0][2]) +
+               2 * z * (dL_dMt.m[1][2] + dL_dMt.m[2][1]) - 4 * y * (dL_dMt.m[2][2] + dL_dMt.m[0][0]);
+        dq.w = 2 * r * (dL_dMt.m[0][1] - dL_dMt.m[1][0]) + 2 * x * (dL_dMt.m[2][0] + dL_dMt.m[0][2]) +
+               2 * y * (dL_dMt.m[1][2] + dL_dMt.m[2][1]) - 4 * z * (dL_dMt.m[1][1] + dL_dMt.m[0][0]);
+        // no quaternion-normalisation Jacobian, as in the reference (backward.cu:345)
+        *reinterpret_cast<float4*>(dL_drot + 4 * (size_t)idx) = dq;
+    }
+}
+
+int launch_gaussian_backward(const GigsRasterBwd* a, const Layout& L, cudaStream_t st)
+{
+    const GigsCamera& c = a->cam;
+    const char* g = (const char*)a->geom;
+    const float focal_y = c.height / (2.0f * c.tan_fovy);
+    const float focal_x = c.width / (2.0f * c.tan_fovx);
+    const float* cov3D_ptr = a->cov3D_precomp ? a->cov3D_precomp : (const float*)(g + L.off.g_cov3D);
+    gaussian_backward_kernel<<<(a->P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, st>>>(
+        a->P, c.sh_degree, c.sh_coeffs, a->means3D, a->radii, a->shs, (const uint8_t*)(g + L.off.g_clamped), a->scales,
+        a->rotations, c.scale_modifier, cov3D_ptr, c.viewmatrix, c.projmatrix, c.campos, focal_x, focal_y, c.tan_fovx,
+        c.tan_fovy, a->accum, a->dL_dmean2D, a->dL_dconic, a->dL_dopacity, a->dL_dcolor, a->dL_dnormal, a->dL_dalbedo,
+        a->dL_droughness, a->dL_dmetallic, a->dL_dmean3D, a->dL_dcov3D, a->dL_dsh, a->dL_dscale, a->dL_drot);
+    GIGS_LAUNCH_CHECK("gaussian_backward_kernel");
+    return 0;
+}
+
+}  // namespace gigs

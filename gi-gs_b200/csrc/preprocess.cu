@@ -1,0 +1,429 @@
+// Per-Gaussian forward stage: projection, EWA covariance, SH->RGB, tile rect, packed blend record,
+// fused block-sum for the tile-count scan; then key emission and tile ranges.
+//
+// Follows the arithmetic of (reference, read-only):
+//   cuda_rasterizer/forward.cu:22-80    SH -> RGB
+//   cuda_rasterizer/forward.cu:83-122   2D covariance (EWA)
+//   cuda_rasterizer/forward.cu:127-161  3D covariance from scale/quaternion
+//   cuda_rasterizer/forward.cu:164-276  preprocess
+//   cuda_rasterizer/rasterizer_impl.cu:70-138  duplicateWithKeys / identifyTileRanges
+//   cuda_rasterizer/auxiliary.h:41-66,150-176  ndc2Pix, getRect, transforms, in_frustum
+// The *expression order* is kept identical on purpose: tile keys (depth bits, rects) must be
+// bit-exact, which requires nvcc to contract the same FMAs. The data flow is ours: one packed 96-B
+// record per visible Gaussian instead of seven scattered arrays, block sums fused into this
+// kernel instead of a device-wide scan pass, warp-cooperative key emission.
+#include "common.cuh"
+
+namespace gigs {
+
+__device__ const float kSH_C0 = 0.28209479177387814f;
+__device__ const float kSH_C1 = 0.4886025119029199f;
+__device__ const float kSH_C2[] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                   -1.0925484305920792f, 0.5462742152960396f};
+__device__ const float kSH_C3[] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
+                                   -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f};
+
+struct V3 {
+    float x, y, z;
+};
+__device__ __forceinline__ V3 operator*(float s, const V3& v) { return {s * v.x, s * v.y, s * v.z}; }
+__device__ __forceinline__ V3 operator+(const V3& a, const V3& b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ V3 operator-(const V3& a, const V3& b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+
+// SH -> RGB for one Gaussian. sh points at this Gaussian's M x 3 coefficients.
+__device__ __forceinline__ V3 sh_to_rgb(int deg, const V3 pos, const V3 campos, const float* __restrict__ shp,
+                                        bool clamped[3])
+{
+    V3 dir = pos - campos;
+    float len = sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
+    dir.x = dir.x / len;
+    dir.y = dir.y / len;
+    dir.z = dir.z / len;
+    auto SH = [&](int i) -> V3 { return {shp[3 * i + 0], shp[3 * i + 1], shp[3 * i + 2]}; };
+
+    V3 result = kSH_C0 * SH(0);
+    if (deg > 0) {
+        float x = dir.x, y = dir.y, z = dir.z;
+        result = result - kSH_C1 * y * SH(1) + kSH_C1 * z * SH(2) - kSH_C1 * x * SH(3);
+        if (deg > 1) {
+            float xx = x * x, yy = y * y, zz = z * z;
+            float xy = x * y, yz = y * z, xz = x * z;
+            result = result + kSH_C2[0] * xy * SH(4) + kSH_C2[1] * yz * SH(5) +
+                     kSH_C2[2] * (2.0f * zz - xx - yy) * SH(6) + kSH_C2[3] * xz * SH(7) +
+                     kSH_C2[4] * (xx - yy) * SH(8);
+            if (deg > 2) {
+                result = result + kSH_C3[0] * y * (3.0f * xx - yy) * SH(9) + kSH_C3[1] * xy * z * SH(10) +
+                         kSH_C3[2] * y * (4.0f * zz - xx - yy) * SH(11) +
+                         kSH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * SH(12) +
+                         kSH_C3[4] * x * (4.0f * zz - xx - yy) * SH(13) + kSH_C3[5] * z * (xx - yy) * SH(14) +
+                         kSH_C3[6] * x * (xx - 3.0f * yy) * SH(15);
+            }
+        }
+    }
+    result.x += 0.5f;
+    result.y += 0.5f;
+    result.z += 0.5f;
+    clamped[0] = (result.x < 0);
+    clamped[1] = (result.y < 0);
+    clamped[2] = (result.z < 0);
+    // max(result, 0) with the (a < b) ? b : a shape (NaN stays NaN)
+    result.x = (result.x < 0.0f) ? 0.0f : result.x;
+    result.y = (result.y < 0.0f) ? 0.0f : result.y;
+    result.z = (result.z < 0.0f) ? 0.0f : result.z;
+    return result;
+}
+
+__device__ __forceinline__ void cov3d_from_scale_rot(const float3 scale, float mod, const float4 rot, float* cov3D)
+{
+    Mat3 S = mat3_cols(1.0f, 0.0f, 0.0f, 0.0f, 1.0f, 0.0f, 0.0f, 0.0f, 1.0f);
+    S.m[0][0] = mod * scale.x;
+    S.m[1][1] = mod * scale.y;
+    S.m[2][2] = mod * scale.z;
+    // quaternion used as given (the reference does not renormalise, forward.cu:136)
+    float r = rot.x, x = rot.y, y = rot.z, z = rot.w;
+    Mat3 R = mat3_cols(1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y),
+                       2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x),
+                       2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y));
+    Mat3 M = mat3_mul(S, R);
+    Mat3 Sigma = mat3_mul(mat3_transpose(M), M);
+    cov3D[0] = Sigma.m[0][0];
+    cov3D[1] = Sigma.m[0][1];
+    cov3D[2] = Sigma.m[0][2];
+    cov3D[3] = Sigma.m[1][1];
+    cov3D[4] = Sigma.m[1][2];
+    cov3D[5] = Sigma.m[2][2];
+}
+
+__device__ __forceinline__ float3 cov2d_ewa(const float3& mean, float focal_x, float focal_y, float tan_fovx,
+                                            float tan_fovy, const float* cov3D, const float* __restrict__ V)
+{
+    float3 t = xform_point_4x3(mean, V);
+    const float limx = 1.3f * tan_fovx;
+    const float limy = 1.3f * tan_fovy;
+    const float txtz = t.x / t.z;
+    const float tytz = t.y / t.z;
+    t.x = fminf(limx, fmaxf(-limx, txtz)) * t.z;
+    t.y = fminf(limy, fmaxf(-limy, tytz)) * t.z;
+
+    Mat3 J = mat3_cols(focal_x / t.z, 0.0f, -(focal_x * t.x) / (t.z * t.z), 0.0f, focal_y / t.z,
+                       -(focal_y * t.y) / (t.z * t.z), 0, 0, 0);
+    Mat3 W = mat3_cols(V[0], V[4], V[8], V[1], V[5], V[9], V[2], V[6], V[10]);
+    Mat3 T = mat3_mul(W, J);
+    Mat3 Vrk = mat3_cols(cov3D[0], cov3D[1], cov3D[2], cov3D[1], cov3D[3], cov3D[4], cov3D[2], cov3D[4], cov3D[5]);
+    Mat3 cov = mat3_mul(mat3_mul(mat3_transpose(T), mat3_transpose(Vrk)), T);
+    cov.m[0][0] += 0.3f;
+    cov.m[1][1] += 0.3f;
+    return make_float3(cov.m[0][0], cov.m[0][1], cov.m[1][1]);
+}
+
+constexpr int PRE_THREADS = 256;
+
+__global__ void __launch_bounds__(PRE_THREADS)
+preprocess_kernel(const int P, const int D, const int M, const float* __restrict__ means3D,
+                  const float* __restrict__ scales, const float scale_modifier, const float* __restrict__ rotations,
+                  const float* __restrict__ opacities, const float* __restrict__ shs,
+                  const float* __restrict__ cov3D_precomp, const float* __restrict__ colors_precomp,
+                  const float* __restrict__ normal, const float* __restrict__ albedo,
+                  const float* __restrict__ roughness, const float* __restrict__ metallic,
+                  const float* __restrict__ viewmatrix, const float* __restrict__ projmatrix,
+                  const float* __restrict__ cam_pos, const int W, const int H, const float tan_fovx,
+                  const float tan_fovy, const float focal_x, const float focal_y, const uint32_t grid_x,
+                  const uint32_t grid_y, const bool prefiltered,
+                  // outputs
+                  int* __restrict__ radii, float* __restrict__ records, float* __restrict__ cov3Ds,
+                  uint8_t* __restrict__ clamped, uint32_t* __restrict__ tiles_touched,
+                  uint32_t* __restrict__ block_sums)
+{
+    __shared__ float sV[16], sPM[16], sCam[3];
+    __shared__ uint32_t s_warp_sum[PRE_THREADS / 32];
+    if (threadIdx.x < 16) {
+        sV[threadIdx.x] = viewmatrix[threadIdx.x];
+        sPM[threadIdx.x] = projmatrix[threadIdx.x];
+    }
+    if (threadIdx.x < 3) sCam[threadIdx.x] = cam_pos[threadIdx.x];
+    __syncthreads();
+
+    const int idx = blockIdx.x * PRE_THREADS + threadIdx.x;
+    uint32_t touched = 0;
+    if (idx < P) {
+        int my_radius_i = 0;
+        do {
+            const float3 p_orig = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
+            // near culling (auxiliary.h:150-176); no x/y frustum test in this fork
+            const float3 p_view = xform_point_4x3(p_orig, sV);
+            if (p_view.z <= 0.2f) {
+                if (prefiltered) {
+                    printf("Point is filtered although prefiltered is set. This shouldn't happen!");
+                    __trap();
+                }
+                break;
+            }
+            const float4 p_hom = xform_point_4x4(p_orig, sPM);
+            const float p_w = 1.0f / (p_hom.w + 0.0000001f);
+            const float3 p_proj = {p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w};
+
+            const float* cov3D;
+            float cov_local[6];
+            if (cov3D_precomp != nullptr) {
+                cov3D = cov3D_precomp + idx * 6;
+            } else {
+                const float3 sc = {scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]};
+                const float4 rot = *reinterpret_cast<const float4*>(rotations + 4 * idx);
+                cov3d_from_scale_rot(sc, scale_modifier, rot, cov_local);
+#pragma unroll
+                for (int k = 0; k < 6; ++k) cov3Ds[idx * 6 + k] = cov_local[k];
+                cov3D = cov_local;
+            }
+            const float3 cov = cov2d_ewa(p_orig, focal_x, focal_y, tan_fovx, tan_fovy, cov3D, sV);
+
+            const float det = (cov.x * cov.z - cov.y * cov.y);
+            if (det == 0.0f) break;
+            const float det_inv = 1.f / det;
+            const float3 conic = {cov.z * det_inv, -cov.y * det_inv, cov.x * det_inv};
+
+            const float mid = 0.5f * (cov.x + cov.z);
+            const float lambda1 = mid + sqrtf(fmaxf(0.1f, mid * mid - det));
+            const float lambda2 = mid - sqrtf(fmaxf(0.1f, mid * mid - det));
+            const float my_radius = ceilf(3.f * sqrtf(fmaxf(lambda1, lambda2)));
+            const float2 point_image = {ndc_to_pix(p_proj.x, W), ndc_to_pix(p_proj.y, H)};
+            uint2 rect_min, rect_max;
+            tile_rect(point_image.x, point_image.y, (int)my_radius, grid_x, grid_y, rect_min, rect_max);
+            if ((rect_max.x - rect_min.x) * (rect_max.y - rect_min.y) == 0) break;
+
+            float3 rgb;
+            if (colors_precomp == nullptr) {
+                bool cl[3];
+                V3 c = sh_to_rgb(D, V3{p_orig.x, p_orig.y, p_orig.z}, V3{sCam[0], sCam[1], sCam[2]},
+                                 shs + (size_t)idx * M * 3, cl);
+                rgb = make_float3(c.x, c.y, c.z);
+                *reinterpret_cast<uchar4*>(clamped + 4 * (size_t)idx) =
+                    make_uchar4(cl[0] ? 1 : 0, cl[1] ? 1 : 0, cl[2] ? 1 : 0, 0);
+            } else {
+                rgb = make_float3(colors_precomp[3 * idx], colors_precomp[3 * idx + 1], colors_precomp[3 * idx + 2]);
+            }
+
+            my_radius_i = (int)my_radius;
+            touched = (rect_max.y - rect_min.y) * (rect_max.x - rect_min.x);
+
+            const float op = opacities[idx];
+            float4* rec = reinterpret_cast<float4*>(records + (size_t)idx * REC_FLOATS);
+            rec[0] = make_float4(point_image.x, point_image.y, conic.x, conic.y);
+            rec[1] = make_float4(conic.z, op, p_view.z, logf(255.0f * op));
+            if (normal != nullptr) {
+                rec[2] = make_float4(rgb.x, rgb.y, rgb.z, roughness[idx]);
+                rec[3] = make_float4(albedo[3 * idx], albedo[3 * idx + 1], albedo[3 * idx + 2], metallic[idx]);
+                rec[4] = make_float4(normal[3 * idx], normal[3 * idx + 1], normal[3 * idx + 2], p_view.x);
+            } else {  // lite path: colour/opacity/depth only
+                rec[2] = make_float4(rgb.x, rgb.y, rgb.z, 0.f);
+                rec[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+                rec[4] = make_float4(0.f, 0.f, 0.f, p_view.x);
+            }
+            rec[5] = make_float4(p_view.y, p_view.z, 0.f, 0.f);
+        } while (false);
+        radii[idx] = my_radius_i;
+        tiles_touched[idx] = touched;
+    }
+
+    // fused block sum of tiles_touched (feeds the single-block scan of block sums)
+    uint32_t v = touched;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) s_warp_sum[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t s = 0;
+#pragma unroll
+        for (int w = 0; w < PRE_THREADS / 32; ++w) s += s_warp_sum[w];
+        block_sums[blockIdx.x] = s;
+    }
+}
+
+// Exclusive scan of the per-block sums (in place) + total. One block; nb = ceil(P/256) is small
+// (23k at 6M Gaussians).
+__global__ void __launch_bounds__(1024) scan_block_sums_kernel(uint32_t* __restrict__ block_sums, int nb,
+                                                               uint32_t* __restrict__ total)
+{
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < nb; base += 1024) {
+        const int i = base + threadIdx.x;
+        uint32_t v = (i < nb) ? block_sums[i] : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_warp[lane];
+            uint32_t winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += t;
+            }
+            s_warp[lane] = winc - w;  // exclusive warp offsets
+        }
+        __syncthreads();
+        const uint32_t carry = s_carry;
+        const uint32_t excl = carry + s_warp[warp] + (inc - v);
+        if (i < nb) block_sums[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = s_carry;
+}
+
+// Key/value emission. One block = the same 256-Gaussian chunk as in preprocess; offsets are
+// block_offset + in-block exclusive scan. Each warp flattens its 32 Gaussians' tile lists and the
+// lanes emit consecutive entries (coalesced 8-B key / 4-B value stores), instead of one thread
+// looping over its whole rect.
+__global__ void __launch_bounds__(PRE_THREADS)
+emit_keys_kernel(const int P, const int* __restrict__ radii, const float* __restrict__ records,
+                 const uint32_t* __restrict__ tiles_touched, const uint32_t* __restrict__ block_offsets,
+                 const uint32_t grid_x, const uint32_t grid_y, uint32_t* __restrict__ point_offsets,
+                 uint64_t* __restrict__ keys, uint32_t* __restrict__ vals)
+{
+    __shared__ uint32_t s_warp_tot[PRE_THREADS / 32];
+    __shared__ uint32_t s_pref[PRE_THREADS / 32][32];
+    __shared__ uint4 s_info[PRE_THREADS / 32][32];  // rect_min.x, rect_min.y, rect width, depth bits
+
+    const int idx = blockIdx.x * PRE_THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t cnt = 0;
+    uint4 info = make_uint4(0, 0, 0, 0);
+    if (idx < P) {
+        cnt = tiles_touched[idx];
+        if (cnt > 0) {
+            const float4 q0 = *reinterpret_cast<const float4*>(records + (size_t)idx * REC_FLOATS);
+            const float4 q1 = *reinterpret_cast<const float4*>(records + (size_t)idx * REC_FLOATS + 4);
+            uint2 rmin, rmax;
+            tile_rect(q0.x, q0.y, radii[idx], grid_x, grid_y, rmin, rmax);
+            info = make_uint4(rmin.x, rmin.y, rmax.x - rmin.x, __float_as_uint(q1.z));
+        }
+    }
+    // warp inclusive scan
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp_tot[warp] = inc;
+    s_pref[warp][lane] = inc - cnt;
+    s_info[warp][lane] = info;
+    __syncthreads();
+    uint32_t warp_off = block_offsets[blockIdx.x];
+    for (int w = 0; w < warp; ++w) warp_off += s_warp_tot[w];
+    if (idx < P) point_offsets[idx] = warp_off + inc;
+
+    const uint32_t E = s_warp_tot[warp];
+    const int gbase = blockIdx.x * PRE_THREADS + warp * 32;
+    for (uint32_t e = lane; e < E; e += 32) {
+        // last g in [0,32) with pref[g] <= e
+        int g = 0;
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1)
+            if (s_pref[warp][g + s] <= e) g += s;
+        const uint4 inf = s_info[warp][g];
+        const uint32_t k = e - s_pref[warp][g];
+        const uint32_t ty = inf.y + k / inf.z;
+        const uint32_t tx = inf.x + k % inf.z;
+        uint64_t key = (uint64_t)(ty * grid_x + tx);
+        key <<= 32;
+        key |= (uint64_t)inf.w;
+        keys[(size_t)warp_off + e] = key;
+        vals[(size_t)warp_off + e] = (uint32_t)(gbase + g);
+    }
+}
+
+// Tile ranges from the sorted keys (rasterizer_impl.cu:117-138). ranges must be zeroed first.
+__global__ void __launch_bounds__(256)
+tile_ranges_kernel(const uint32_t L, const uint64_t* __restrict__ keys, uint2* __restrict__ ranges)
+{
+    const uint32_t idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= L) return;
+    const uint32_t cur = (uint32_t)(keys[idx] >> 32);
+    if (idx == 0)
+        ranges[cur].x = 0;
+    else {
+        const uint32_t prev = (uint32_t)(keys[idx - 1] >> 32);
+        if (cur != prev) {
+            ranges[prev].y = idx;
+            ranges[cur].x = idx;
+        }
+    }
+    if (idx == L - 1) ranges[cur].y = L;
+}
+
+__global__ void __launch_bounds__(256)
+mark_visible_kernel(const int P, const float* __restrict__ means3D, const float* __restrict__ viewmatrix,
+                    uint8_t* __restrict__ present)
+{
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= P) return;
+    const float3 p = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
+    const float3 pv = xform_point_4x3(p, viewmatrix);
+    present[idx] = (pv.z <= 0.2f) ? 0 : 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------
+int launch_preprocess(const GigsRasterFwd* a, const Layout& L, cudaStream_t st)
+{
+    const int P = a->P;
+    const GigsCamera& c = a->cam;
+    const float focal_y = c.height / (2.0f * c.tan_fovy);
+    const float focal_x = c.width / (2.0f * c.tan_fovx);
+    char* g = (char*)a->geom;
+    preprocess_kernel<<<L.num_blocks, PRE_THREADS, 0, st>>>(
+        P, c.sh_degree, c.sh_coeffs, a->means3D, a->scales, c.scale_modifier, a->rotations, a->opacities, a->shs,
+        a->cov3D_precomp, a->colors_precomp, a->normal, a->albedo, a->roughness, a->metallic, c.viewmatrix,
+        c.projmatrix, c.campos, c.width, c.height, c.tan_fovx, c.tan_fovy, focal_x, focal_y, L.tiles_x, L.tiles_y,
+        c.prefiltered != 0, a->radii, (float*)(g + L.off.g_record), (float*)(g + L.off.g_cov3D),
+        (uint8_t*)(g + L.off.g_clamped), (uint32_t*)(g + L.off.g_tiles_touched),
+        (uint32_t*)(g + L.off.g_block_sums));
+    GIGS_LAUNCH_CHECK("preprocess_kernel");
+    scan_block_sums_kernel<<<1, 1024, 0, st>>>((uint32_t*)(g + L.off.g_block_sums), (int)L.num_blocks,
+                                               (uint32_t*)(g + L.off.g_num_rendered));
+    GIGS_LAUNCH_CHECK("scan_block_sums_kernel");
+    return 0;
+}
+
+int launch_emit_keys(const GigsRasterFwd* a, const Layout& L, uint64_t* keys, uint32_t* vals, cudaStream_t st)
+{
+    char* g = (char*)a->geom;
+    emit_keys_kernel<<<L.num_blocks, PRE_THREADS, 0, st>>>(
+        a->P, a->radii, (const float*)(g + L.off.g_record), (const uint32_t*)(g + L.off.g_tiles_touched),
+        (const uint32_t*)(g + L.off.g_block_sums), L.tiles_x, L.tiles_y, (uint32_t*)(g + L.off.g_point_offsets), keys,
+        vals);
+    GIGS_LAUNCH_CHECK("emit_keys_kernel");
+    return 0;
+}
+
+int launch_tile_ranges(uint64_t R, const uint64_t* keys_sorted, uint2* ranges, uint32_t num_tiles, cudaStream_t st)
+{
+    GIGS_CUDA(cudaMemsetAsync(ranges, 0, (size_t)num_tiles * sizeof(uint2), st));
+    if (R > 0) {
+        tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>((uint32_t)R, keys_sorted, ranges);
+        GIGS_LAUNCH_CHECK("tile_ranges_kernel");
+    }
+    return 0;
+}
+
+int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t st)
+{
+    if (P <= 0) return 0;
+    mark_visible_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, means3D, viewmatrix, present);
+    GIGS_LAUNCH_CHECK("mark_visible_kernel");
+    return 0;
+}
+
+}  // namespace gigs

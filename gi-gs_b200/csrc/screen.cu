@@ -1,0 +1,718 @@
+// Screen-space passes over the G-buffer: 3x3 median / bilateral filters, depth -> pseudo-normal,
+// the fused geometry chain, SSAO and SSR (the "lightweight path tracer").
+//
+// Follows (reference, read-only):
+//   cuda_rasterizer/forward.cu:914-1032  depthmapToNormalCUDA     cuda_rasterizer/ssr.h:103-135
+//   cuda_rasterizer/forward.cu:635-724   SSAOCUDA                 cuda_rasterizer/forward.cu:726-909 SSRCUDA
+//   diff_gaussian_rasterization/__init__.py:475-517  (filter -> depth_to_normal -> filter -> SSAO glue)
+// and the documented semantics of the two third-party filters the reference calls
+// (kornia median_blur / bilateral_blur, SURVEY.md A.10 — "parity unpinned": kornia is not installable here).
+//
+// What is ours: the 512-direction hemisphere table is built once per CTA in shared memory with the
+// reference's exact float-accumulated phi/theta sequences (the reference recomputes 5 trig calls per
+// direction per pixel); the four-launch filter chain is one tiled kernel with a 4-pixel halo.
+// The probe arithmetic keeps the reference's operation order because every probe ends in a
+// threshold test: one flipped hit moves a pixel's occlusion by up to 3e-3.
+#include "common.cuh"
+
+namespace gigs {
+
+#ifndef M_PIf
+#define M_PIf 3.14159265358979323846f
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// 3x3 median (zero padded). A window holding a non-finite value yields NaN: the filter the
+// reference calls gathers the window with a one-hot convolution, where NaN*0 and inf*0 are NaN.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cswap(float& a, float& b)
+{
+    const float lo = fminf(a, b), hi = fmaxf(a, b);
+    a = lo;
+    b = hi;
+}
+__device__ __forceinline__ float median9(float v[9])
+{
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) bad |= !isfinite(v[i]);
+    if (bad) return __int_as_float(0x7fc00000);
+    // 19-exchange median-of-9 network
+    cswap(v[1], v[2]); cswap(v[4], v[5]); cswap(v[7], v[8]);
+    cswap(v[0], v[1]); cswap(v[3], v[4]); cswap(v[6], v[7]);
+    cswap(v[1], v[2]); cswap(v[4], v[5]); cswap(v[7], v[8]);
+    cswap(v[0], v[3]); cswap(v[5], v[8]); cswap(v[4], v[7]);
+    cswap(v[3], v[6]); cswap(v[1], v[4]); cswap(v[2], v[5]);
+    cswap(v[4], v[7]); cswap(v[4], v[2]); cswap(v[6], v[4]);
+    cswap(v[4], v[2]);
+    return v[4];
+}
+
+__global__ void __launch_bounds__(256)
+median3x3_kernel(const int C, const int W, const int H, const float* __restrict__ in, float* __restrict__ out)
+{
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= W || y >= H) return;
+    for (int c = 0; c < C; ++c) {
+        const float* p = in + (size_t)c * W * H;
+        float v[9];
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int xx = x + dx, yy = y + dy;
+                v[(dy + 1) * 3 + dx + 1] = (xx >= 0 && xx < W && yy >= 0 && yy < H) ? p[(size_t)yy * W + xx] : 0.f;
+            }
+        out[(size_t)c * W * H + (size_t)y * W + x] = median9(v);
+    }
+}
+
+// gradient goes to the window element that equals the median (first match in window order);
+// a selected zero-pad element receives nothing. grad_in must be zero on entry.
+__global__ void __launch_bounds__(256)
+median3x3_backward_kernel(const int C, const int W, const int H, const float* __restrict__ in,
+                          const float* __restrict__ grad_out, float* __restrict__ grad_in)
+{
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= W || y >= H) return;
+    for (int c = 0; c < C; ++c) {
+        const float* p = in + (size_t)c * W * H;
+        float v[9], s[9];
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int xx = x + dx, yy = y + dy;
+                const float t = (xx >= 0 && xx < W && yy >= 0 && yy < H) ? p[(size_t)yy * W + xx] : 0.f;
+                v[(dy + 1) * 3 + dx + 1] = t;
+                s[(dy + 1) * 3 + dx + 1] = t;
+            }
+        const float g = grad_out[(size_t)c * W * H + (size_t)y * W + x];
+        const float m = median9(s);
+        if (!(m == m)) {
+            // NaN output: route to the first non-finite element (gradient of a NaN is moot)
+            continue;
+        }
+        int sel = -1;
+#pragma unroll
+        for (int k = 8; k >= 0; --k)
+            if (v[k] == m) sel = k;
+        if (sel >= 0) {
+            const int xx = x + (sel % 3) - 1, yy = y + (sel / 3) - 1;
+            if (xx >= 0 && xx < W && yy >= 0 && yy < H) atomicAdd(grad_in + (size_t)c * W * H + (size_t)yy * W + xx, g);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3x3 bilateral blur: reflect border, colour distance = (sum_c |x_nb - x_c|)^2,
+// weight = exp(-0.5/sigma_color^2 * dist) * gauss_space, out = sum(w x) / sum(w)
+// ---------------------------------------------------------------------------------------------
+struct SpaceKernel {
+    float k[9];
+};
+static SpaceKernel make_space_kernel(float sigma)
+{
+    // 1-D gaussian on x = {-1,0,1}, normalised, outer product (float32 like the library does)
+    float g[3], s = 0.f;
+    for (int i = 0; i < 3; ++i) {
+        float x = (float)(i - 1);
+        g[i] = expf(-(x * x) / (2.f * sigma * sigma));
+        s += g[i];
+    }
+    for (int i = 0; i < 3; ++i) g[i] /= s;
+    SpaceKernel K;
+    for (int y = 0; y < 3; ++y)
+        for (int x = 0; x < 3; ++x) K.k[y * 3 + x] = g[y] * g[x];
+    return K;
+}
+__device__ __forceinline__ int reflect_idx(int i, int n)
+{
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * n - 2 - i;
+    return i;
+}
+
+__global__ void __launch_bounds__(256)
+bilateral3x3_kernel(const int C, const int W, const int H, const float color_coef, const SpaceKernel K,
+                    const float* __restrict__ in, float* __restrict__ out)
+{
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const size_t HW = (size_t)W * H;
+    float wsum = 0.f;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float w9[9];
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int xx = reflect_idx(x + dx, W), yy = reflect_idx(y + dy, H);
+            float dist = 0.f;
+            for (int c = 0; c < C; ++c) dist += fabsf(in[c * HW + (size_t)yy * W + xx] - in[c * HW + (size_t)y * W + x]);
+            const float w = K.k[(dy + 1) * 3 + dx + 1] * expf(color_coef * (dist * dist));
+            w9[(dy + 1) * 3 + dx + 1] = w;
+            wsum += w;
+        }
+    for (int c = 0; c < C; ++c) {
+        float a = 0.f;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int xx = reflect_idx(x + dx, W), yy = reflect_idx(y + dy, H);
+                a += in[c * HW + (size_t)yy * W + xx] * w9[(dy + 1) * 3 + dx + 1];
+            }
+        out[c * HW + (size_t)y * W + x] = a / wsum;
+    }
+    (void)acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// depth -> view-space position and pseudo-normal. DepthAt(x,y) returns the (filtered) depth of an
+// in-image pixel. Returns pos (0 on the border) and normal (0 unless all validity tests pass).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float3 back_project(int x, int y, float cx, float cy, float fx, float fy, float depth)
+{
+    const float3 dir = make_float3((float(x) - cx) / fx, (float(y) - cy) / fy, 1.0f);
+    return make_float3(dir.x * depth, dir.y * depth, dir.z * depth);
+}
+
+template <typename DepthAt>
+__device__ __forceinline__ void depth_to_normal_pixel(int x, int y, int W, int H, float fx, float fy,
+                                                      const float* __restrict__ V, DepthAt depth_at, float3& pos,
+                                                      float3& nrm)
+{
+    pos = make_float3(0.f, 0.f, 0.f);
+    nrm = make_float3(0.f, 0.f, 0.f);
+    if (x <= 0 || x >= W - 1 || y <= 0 || y >= H - 1) return;
+    const float depth_thresh = 0.01f;
+    const float depth = depth_at(x, y);
+    const float cx = float(W) / 2.0f, cy = float(H) / 2.0f;
+    pos = back_project(x, y, cx, cy, fx, fy, depth);
+    if (depth < depth_thresh) return;
+    for (int dx = -2; dx <= 2; ++dx) {
+        if (x + dx < 0 || x + dx > W - 1) return;
+        for (int dy = -2; dy <= 2; ++dy) {
+            if (y + dy < 0 || y + dy > H - 1) return;
+            if (depth_at(x + dx, y + dy) < depth_thresh) return;
+        }
+    }
+    const float3 p_aa = back_project(x, y - 1, cx, cy, fx, fy, depth_at(x, y - 1));
+    const float3 p_bb = back_project(x + 1, y, cx, cy, fx, fy, depth_at(x + 1, y));
+    const float3 p_cc = back_project(x, y + 1, cx, cy, fx, fy, depth_at(x, y + 1));
+    const float3 p_dd = back_project(x - 1, y, cx, cy, fx, fy, depth_at(x - 1, y));
+    const float3 p_ab = back_project(x + 1, y - 1, cx, cy, fx, fy, depth_at(x + 1, y - 1));
+    const float3 p_bc = back_project(x + 1, y + 1, cx, cy, fx, fy, depth_at(x + 1, y + 1));
+    const float3 p_cd = back_project(x - 1, y + 1, cx, cy, fx, fy, depth_at(x - 1, y + 1));
+    const float3 p_da = back_project(x - 1, y - 1, cx, cy, fx, fy, depth_at(x - 1, y - 1));
+    const float3 e_a = sub3(p_da, p_ab), e_b = sub3(p_ab, p_bc), e_c = sub3(p_bc, p_cd), e_d = sub3(p_cd, p_da);
+    const float3 e_ac = sub3(p_cc, p_aa), e_bd = sub3(p_dd, p_bb);
+    const float3 e_cdab = sub3(p_ab, p_cd), e_bcad = sub3(p_da, p_bc);
+    const float3 n1 = normalize3(cross3(e_a, e_d)), n2 = normalize3(cross3(e_d, e_c));
+    const float3 n3 = normalize3(cross3(e_c, e_b)), n4 = normalize3(cross3(e_b, e_a));
+    const float3 n5 = normalize3(cross3(e_ac, e_bd)), n6 = normalize3(cross3(e_bcad, e_cdab));
+    const float3 s = add3(add3(add3(add3(add3(n1, n2), n3), n4), n5), n6);
+    const float inv6 = 1.0f / 6.f;
+    const float3 n = make_float3(s.x * inv6, s.y * inv6, s.z * inv6);
+    // rotation by the upper 3x3 exactly as written in the reference (forward.cu:1022-1024)
+    nrm.x = V[0] * n.x + V[1] * n.y + V[2] * n.z;
+    nrm.y = V[4] * n.x + V[5] * n.y + V[6] * n.z;
+    nrm.z = V[8] * n.x + V[9] * n.y + V[10] * n.z;
+}
+
+__global__ void __launch_bounds__(256)
+depth_to_normal_kernel(const int W, const int H, const float fx, const float fy, const float* __restrict__ V,
+                       const float* __restrict__ depth, float* __restrict__ normal_map,
+                       float* __restrict__ depth_pos)
+{
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= W || y >= H) return;
+    float3 pos, nrm;
+    depth_to_normal_pixel(x, y, W, H, fx, fy, V, [&](int xx, int yy) { return depth[(size_t)yy * W + xx]; }, pos,
+                          nrm);
+    const size_t HW = (size_t)W * H, id = (size_t)y * W + x;
+    depth_pos[id] = pos.x; depth_pos[HW + id] = pos.y; depth_pos[2 * HW + id] = pos.z;
+    normal_map[id] = nrm.x; normal_map[HW + id] = nrm.y; normal_map[2 * HW + id] = nrm.z;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused chain: median(depth) -> depth_to_normal -> {bilateral(normal), median(depth_pos)}
+// Output tile 32x16 per CTA of 256 threads; raw depth staged with a 4-pixel halo.
+// ---------------------------------------------------------------------------------------------
+constexpr int GC_TW = 32, GC_TH = 16;
+constexpr int GC_RW = GC_TW + 8, GC_RH = GC_TH + 8;  // raw, halo 4
+constexpr int GC_FW = GC_TW + 6, GC_FH = GC_TH + 6;  // median-filtered depth, halo 3
+constexpr int GC_NW = GC_TW + 2, GC_NH = GC_TH + 2;  // pos / normal, halo 1
+
+__global__ void __launch_bounds__(256)
+geometry_chain_kernel(const int W, const int H, const float fx, const float fy, const float* __restrict__ V,
+                      const float color_coef, const SpaceKernel K, const float* __restrict__ depth,
+                      float* __restrict__ normal_out, float* __restrict__ pos_out)
+{
+    __shared__ float s_raw[GC_RH][GC_RW];
+    __shared__ float s_df[GC_FH][GC_FW];
+    __shared__ float s_pos[3][GC_NH][GC_NW];
+    __shared__ float s_nrm[3][GC_NH][GC_NW];
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int x0 = blockIdx.x * GC_TW, y0 = blockIdx.y * GC_TH;
+
+    for (int i = tid; i < GC_RH * GC_RW; i += 256) {
+        const int lx = i % GC_RW, ly = i / GC_RW;
+        const int gx = x0 - 4 + lx, gy = y0 - 4 + ly;
+        s_raw[ly][lx] = (gx >= 0 && gx < W && gy >= 0 && gy < H) ? depth[(size_t)gy * W + gx] : 0.f;
+    }
+    __syncthreads();
+    for (int i = tid; i < GC_FH * GC_FW; i += 256) {
+        const int lx = i % GC_FW, ly = i / GC_FW;  // image coords: x0-3+lx ; raw coords: lx+1
+        float v[9];
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) v[dy * 3 + dx] = s_raw[ly + dy][lx + dx];
+        s_df[ly][lx] = median9(v);
+    }
+    __syncthreads();
+    for (int i = tid; i < GC_NH * GC_NW; i += 256) {
+        const int lx = i % GC_NW, ly = i / GC_NW;
+        const int gx = x0 - 1 + lx, gy = y0 - 1 + ly;
+        float3 pos = make_float3(0.f, 0.f, 0.f), nrm = make_float3(0.f, 0.f, 0.f);
+        if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
+            depth_to_normal_pixel(gx, gy, W, H, fx, fy, V,
+                                  [&](int xx, int yy) { return s_df[yy - (y0 - 3)][xx - (x0 - 3)]; }, pos, nrm);
+        }
+        s_pos[0][ly][lx] = pos.x; s_pos[1][ly][lx] = pos.y; s_pos[2][ly][lx] = pos.z;
+        s_nrm[0][ly][lx] = nrm.x; s_nrm[1][ly][lx] = nrm.y; s_nrm[2][ly][lx] = nrm.z;
+    }
+    __syncthreads();
+    const size_t HW = (size_t)W * H;
+    for (int i = tid; i < GC_TH * GC_TW; i += 256) {
+        const int lx = i % GC_TW, ly = i / GC_TW;
+        const int gx = x0 + lx, gy = y0 + ly;
+        if (gx >= W || gy >= H) continue;
+        const size_t id = (size_t)gy * W + gx;
+        // median(depth_pos), zero padded (out-of-image halo entries were stored as 0)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float v[9];
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) v[dy * 3 + dx] = s_pos[c][ly + dy][lx + dx];
+            pos_out[c * HW + id] = median9(v);
+        }
+        // bilateral(normal), reflect border
+        float w9[9], wsum = 0.f;
+        const float c0 = s_nrm[0][ly + 1][lx + 1], c1 = s_nrm[1][ly + 1][lx + 1], c2 = s_nrm[2][ly + 1][lx + 1];
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int rx = reflect_idx(gx + dx, W) - (x0 - 1), ry = reflect_idx(gy + dy, H) - (y0 - 1);
+                float dist = 0.f;
+                dist += fabsf(s_nrm[0][ry][rx] - c0);
+                dist += fabsf(s_nrm[1][ry][rx] - c1);
+                dist += fabsf(s_nrm[2][ry][rx] - c2);
+                const float w = K.k[(dy + 1) * 3 + dx + 1] * expf(color_coef * (dist * dist));
+                w9[(dy + 1) * 3 + dx + 1] = w;
+                wsum += w;
+            }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float a = 0.f;
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int rx = reflect_idx(gx + dx, W) - (x0 - 1), ry = reflect_idx(gy + dy, H) - (y0 - 1);
+                    a += s_nrm[c][ry][rx] * w9[(dy + 1) * 3 + dx + 1];
+                }
+            normal_out[c * HW + id] = a / wsum;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Hemisphere direction table shared by SSAO and SSR.
+// The reference loops `for (float phi = 0; phi < 2.0*M_PIf; phi += d)` / `for (float theta = 0;
+// theta <= 0.5*M_PIf; theta += d*0.5)` with float accumulators and double comparisons; the host
+// replays exactly that to get the trip counts, the kernel replays it for the values.
+// ---------------------------------------------------------------------------------------------
+struct DirCounts {
+    int n_phi, n_theta;
+};
+static DirCounts count_dirs(float delta)
+{
+    DirCounts c{0, 0};
+    const float sampleDelta = delta * M_PIf;
+    if (!(sampleDelta > 0.f)) return c;
+    for (float phi = 0.0; phi < 2.0 * M_PIf; phi += sampleDelta) {
+        if (++c.n_phi > 4096) break;
+    }
+    for (float theta = 0.0; theta <= 0.5 * M_PIf; theta += sampleDelta * 0.5) {
+        if (++c.n_theta > 4096) break;
+    }
+    return c;
+}
+
+struct DirEntry {
+    float x, y, z, c, s;  // normalised tangent-space direction, cos(theta), sin(theta)
+};
+
+__device__ __forceinline__ void build_dir_table(DirEntry* tab, float* phis, float* thetas, int n_phi, int n_theta,
+                                                float delta, int tid, int nthreads)
+{
+    const float sampleDelta = delta * M_PIf;
+    if (tid == 0) {
+        float phi = 0.0;
+        for (int i = 0; i < n_phi; ++i) {
+            phis[i] = phi;
+            phi += sampleDelta;
+        }
+        float theta = 0.0;
+        for (int k = 0; k < n_theta; ++k) {
+            thetas[k] = theta;
+            theta += sampleDelta * 0.5;  // double multiply-add, float store
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < n_phi * n_theta; e += nthreads) {
+        const float phi = phis[e / n_theta], theta = thetas[e % n_theta];
+        const float3 t = normalize3(make_float3(sinf(theta) * cosf(phi), sinf(theta) * sinf(phi), cosf(theta)));
+        tab[e] = DirEntry{t.x, t.y, t.z, cosf(theta), sinf(theta)};
+    }
+    __syncthreads();
+}
+
+// reference ssr.h:120-135
+__device__ __forceinline__ int2 project_coord(float cx, float cy, float fx, float fy, const float3 pos)
+{
+    const float3 dir = make_float3(pos.x / (pos.z + 0.0000001f), pos.y / (pos.z + 0.0000001f), 1.0f);
+    int2 xy;
+    xy.x = (int)roundf(dir.x * fx + cx);
+    xy.y = (int)roundf(dir.y * fy + cy);
+    return xy;
+}
+
+struct Tbn {
+    float m[9];
+};
+__device__ __forceinline__ Tbn make_tbn(const float3 normal)
+{
+    const float3 up = {0.0f, 1.0f, 0.0f};
+    const float rndot = dot3(up, normal);
+    const float3 untangent = {up.x - normal.x * rndot, up.y - normal.y * rndot, up.z - normal.z * rndot};
+    const float3 tangent = normalize3(untangent);
+    const float3 bitangent = normalize3(cross3(normal, tangent));
+    Tbn t;
+    t.m[0] = tangent.x; t.m[1] = tangent.y; t.m[2] = tangent.z;
+    t.m[3] = bitangent.x; t.m[4] = bitangent.y; t.m[5] = bitangent.z;
+    t.m[6] = normal.x; t.m[7] = normal.y; t.m[8] = normal.z;
+    return t;
+}
+
+constexpr int GI_MAX_DIRS = 2048;
+
+template <bool IS_SSR>
+__global__ void __launch_bounds__(256)
+gi_march_kernel(const int W, const int H, const float focal_x, const float focal_y, const float radius,
+                const float bias, const float thick, const float delta, const int step, const int start,
+                const int n_phi, const int n_theta, const float* __restrict__ out_normal,
+                const float* __restrict__ out_pos, const float* __restrict__ out_rgb,
+                const float* __restrict__ out_albedo, const float* __restrict__ out_metallic,
+                const float* __restrict__ out_F0, float* __restrict__ out0 /*occlusion | color*/,
+                float* __restrict__ out1 /*- | abd*/)
+{
+    extern __shared__ __align__(16) unsigned char gi_smem_raw[];
+    DirEntry* tab = reinterpret_cast<DirEntry*>(gi_smem_raw);
+    float* phis = reinterpret_cast<float*>(tab + n_phi * n_theta);
+    float* thetas = phis + n_phi;
+    const int tid = threadIdx.y * TILE_X + threadIdx.x;
+    build_dir_table(tab, phis, thetas, n_phi, n_theta, delta, tid, 256);
+
+    const uint32_t px = blockIdx.x * TILE_X + threadIdx.x, py = blockIdx.y * TILE_Y + threadIdx.y;
+    if (px > (uint32_t)(W - 1) || py > (uint32_t)(H - 1)) return;
+    const int HW = H * W;
+    const uint32_t pix_id = W * py + px;
+
+    const float3 normal_un = {out_normal[pix_id], out_normal[HW + pix_id], out_normal[2 * HW + pix_id]};
+    const float3 normal = normalize3(normal_un);
+    const float3 pos = {out_pos[pix_id], out_pos[HW + pix_id], out_pos[2 * HW + pix_id]};
+    const Tbn tbn = make_tbn(normal);
+    const float* zbuf = out_pos + 2 * (size_t)HW;
+    const float cx = float(W) / 2.0f, cy = float(H) / 2.0f;
+    const float scale = (1 + pos.z / 100);
+    const float stepf = (float)step;
+    const int ndir = n_phi * n_theta;
+
+    float occ = 0.0f;
+    float nrSamples = 0.0f;
+    float3 diffuse = {0.0f, 0.0f, 0.0f};
+    for (int e = 0; e < ndir; ++e) {
+        const DirEntry de = tab[e];
+        float3 sv;
+        sv.x = tbn.m[0] * de.x + tbn.m[3] * de.y + tbn.m[6] * de.z;
+        sv.y = tbn.m[1] * de.x + tbn.m[4] * de.y + tbn.m[7] * de.z;
+        sv.z = tbn.m[2] * de.x + tbn.m[5] * de.y + tbn.m[8] * de.z;
+        if (IS_SSR)
+            nrSamples += 1;
+        else
+            nrSamples += de.c * de.s;
+        for (int j = start; j < step; ++j) {
+            float3 sp;
+            sp.x = pos.x + sv.x * j * scale * scale * radius / stepf;
+            sp.y = pos.y + sv.y * j * scale * scale * radius / stepf;
+            sp.z = pos.z + sv.z * j * scale * scale * radius / stepf;
+            const int2 id = project_coord(cx, cy, focal_x, focal_y, sp);
+            if (id.x < 0) break;
+            else if (id.x > W - 1) break;
+            if (id.y < 0) break;
+            else if (id.y > H - 1) break;
+            const float sampleDepth = zbuf[W * id.y + id.x];
+            if (sampleDepth <= sp.z + bias && sampleDepth >= sp.z - thick) {
+                if (IS_SSR) {
+                    const float r = out_rgb[W * id.y + id.x], g = out_rgb[HW + W * id.y + id.x],
+                                b = out_rgb[2 * HW + W * id.y + id.x];
+                    diffuse.x += r * de.c * de.s;
+                    diffuse.y += g * de.c * de.s;
+                    diffuse.z += b * de.c * de.s;
+                } else {
+                    occ += de.c * de.s;
+                }
+                break;
+            }
+        }
+    }
+
+    if (!IS_SSR) {
+        if (nrSamples > 0.0)
+            out0[pix_id] = fmaxf(0.0f, fminf(1.0f, 1.0 - (occ / nrSamples)));
+        else
+            out0[pix_id] = 1.0;
+    } else {
+        const float3 albedo = {out_albedo[pix_id], out_albedo[HW + pix_id], out_albedo[2 * HW + pix_id]};
+        const float3 F0 = {out_F0[pix_id], out_F0[HW + pix_id], out_F0[2 * HW + pix_id]};
+        const float metallic = out_metallic[pix_id];
+        const float3 Vd = normalize3(make_float3(-pos.x, -pos.y, -pos.z));
+        // fresnelSchlick (ssr.h:13-16): the un-suffixed literals make the base a double subtraction and
+        // the power a double pow, rounded to float before the float3 multiply
+        const float cosTheta = fmaxf(dot3(normal, Vd), 0.0000001);
+        const float fbase = fminf(fmaxf(1.0 - cosTheta, 0.000001), 1.0);
+        const float fpow = pow((double)fbase, 5.0);
+        float3 F;
+        F.x = F0.x + (1.0f - F0.x) * fpow;
+        F.y = F0.y + (1.0f - F0.y) * fpow;
+        F.z = F0.z + (1.0f - F0.z) * fpow;
+        float3 kD = {(float)(1.0 - F.x), (float)(1.0 - F.y), (float)(1.0 - F.z)};
+        kD.x *= 1.0 - metallic;
+        kD.y *= 1.0 - metallic;
+        kD.z *= 1.0 - metallic;
+        float3 gd;
+        if (nrSamples > 0.0) {
+            gd.x = M_PIf * diffuse.x * (1.0 / float(nrSamples)) * kD.x;
+            gd.y = M_PIf * diffuse.y * (1.0 / float(nrSamples)) * kD.y;
+            gd.z = M_PIf * diffuse.z * (1.0 / float(nrSamples)) * kD.z;
+            diffuse.x = gd.x * albedo.x;
+            diffuse.y = gd.y * albedo.y;
+            diffuse.z = gd.z * albedo.z;
+        } else {
+            diffuse.x = diffuse.y = diffuse.z = 0.0000001;
+            gd.x = gd.y = gd.z = 0.0000001;
+        }
+        out0[pix_id] = diffuse.x; out0[HW + pix_id] = diffuse.y; out0[2 * HW + pix_id] = diffuse.z;
+        out1[pix_id] = gd.x; out1[HW + pix_id] = gd.y; out1[2 * HW + pix_id] = gd.z;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+ssr_backward_kernel(const size_t n3, const size_t n1, const float* __restrict__ grad_color,
+                    const float* __restrict__ abd, float* __restrict__ g_albedo, float* __restrict__ g_rough,
+                    float* __restrict__ g_metal)
+{
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n3) g_albedo[i] = grad_color[i] * abd[i];
+    if (i < n1) {
+        if (g_rough) g_rough[i] = 0.f;
+        if (g_metal) g_metal[i] = 0.f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FFMA-throughput microbenchmark: the FP32-pipe roofline denominator for blend / SSAO / SSR.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters)
+{
+    float a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = threadIdx.x * 1e-3f + i;
+    const float b = 1.0000001f, c = 1e-7f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = fmaf(a[i], b, c);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += a[i];
+    if (s == 12345.678f) out[0] = s;
+}
+
+}  // namespace gigs
+
+using namespace gigs;
+
+extern "C" {
+
+int gigs_depth_to_normal(int32_t W, int32_t H, float fx, float fy, const float* viewmatrix, const float* depth,
+                         float* normal_map, float* depth_pos, void* stream)
+{
+    if (W <= 0 || H <= 0 || !viewmatrix || !depth || !normal_map || !depth_pos) { set_error("gigs_depth_to_normal: bad arguments"); return -1; }
+    dim3 grid((W + 31) / 32, (H + 7) / 8), block(32, 8);
+    depth_to_normal_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(W, H, fx, fy, viewmatrix, depth, normal_map, depth_pos);
+    GIGS_LAUNCH_CHECK("depth_to_normal_kernel");
+    return 0;
+}
+
+int gigs_median3x3(int32_t Cn, int32_t W, int32_t H, const float* in, float* out, void* stream)
+{
+    if (Cn <= 0 || W <= 0 || H <= 0 || !in || !out) { set_error("gigs_median3x3: bad arguments"); return -1; }
+    dim3 grid((W + 31) / 32, (H + 7) / 8), block(32, 8);
+    median3x3_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(Cn, W, H, in, out);
+    GIGS_LAUNCH_CHECK("median3x3_kernel");
+    return 0;
+}
+
+int gigs_median3x3_backward(int32_t Cn, int32_t W, int32_t H, const float* in, const float* grad_out, float* grad_in,
+                            void* stream)
+{
+    if (Cn <= 0 || W <= 0 || H <= 0 || !in || !grad_out || !grad_in) { set_error("gigs_median3x3_backward: bad arguments"); return -1; }
+    GIGS_CUDA(cudaMemsetAsync(grad_in, 0, (size_t)Cn * W * H * sizeof(float), (cudaStream_t)stream));
+    dim3 grid((W + 31) / 32, (H + 7) / 8), block(32, 8);
+    median3x3_backward_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(Cn, W, H, in, grad_out, grad_in);
+    GIGS_LAUNCH_CHECK("median3x3_backward_kernel");
+    return 0;
+}
+
+int gigs_bilateral3x3(int32_t Cn, int32_t W, int32_t H, float sigma_color, float sigma_space, const float* in,
+                      float* out, void* stream)
+{
+    if (Cn <= 0 || Cn > 4 || W <= 1 || H <= 1 || !in || !out) { set_error("gigs_bilateral3x3: bad arguments"); return -1; }
+    dim3 grid((W + 31) / 32, (H + 7) / 8), block(32, 8);
+    bilateral3x3_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(Cn, W, H, -0.5f / (sigma_color * sigma_color),
+                                                                  make_space_kernel(sigma_space), in, out);
+    GIGS_LAUNCH_CHECK("bilateral3x3_kernel");
+    return 0;
+}
+
+int gigs_geometry_chain(int32_t W, int32_t H, float fx, float fy, const float* viewmatrix, const float* depth,
+                        int32_t derive_normal, float* normal_from_depth, float* depth_pos_filter, void* stream)
+{
+    if (W <= 1 || H <= 1 || !normal_from_depth || !depth_pos_filter) { set_error("gigs_geometry_chain: bad arguments"); return -1; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!derive_normal) {
+        // zeros in, zeros out of both filters (diff_gaussian_rasterization/__init__.py:487-491,504)
+        GIGS_CUDA(cudaMemsetAsync(normal_from_depth, 0, (size_t)3 * W * H * sizeof(float), st));
+        GIGS_CUDA(cudaMemsetAsync(depth_pos_filter, 0, (size_t)3 * W * H * sizeof(float), st));
+        return 0;
+    }
+    if (!viewmatrix || !depth) { set_error("gigs_geometry_chain: bad arguments"); return -1; }
+    dim3 grid((W + GC_TW - 1) / GC_TW, (H + GC_TH - 1) / GC_TH), block(32, 8);
+    geometry_chain_kernel<<<grid, block, 0, st>>>(W, H, fx, fy, viewmatrix, -0.5f / (1.f * 1.f), make_space_kernel(3.f),
+                                                  depth, normal_from_depth, depth_pos_filter);
+    GIGS_LAUNCH_CHECK("geometry_chain_kernel");
+    return 0;
+}
+
+static int gi_launch(bool is_ssr, int W, int H, float fx, float fy, float radius, float bias, float thick, float delta,
+                     int step, int start, const float* normal, const float* pos, const float* rgb, const float* albedo,
+                     const float* metallic, const float* F0, float* out0, float* out1, cudaStream_t st)
+{
+    DirCounts dc = count_dirs(delta);
+    if (dc.n_phi * dc.n_theta > GI_MAX_DIRS || dc.n_phi > 4096 || dc.n_theta > 4096) {
+        set_error("GI: delta=%g gives %d x %d directions, more than the %d supported", delta, dc.n_phi, dc.n_theta,
+                  GI_MAX_DIRS);
+        return -4;
+    }
+    const size_t smem = (size_t)dc.n_phi * dc.n_theta * sizeof(DirEntry) + (dc.n_phi + dc.n_theta) * sizeof(float) + 16;
+    dim3 grid((W + TILE_X - 1) / TILE_X, (H + TILE_Y - 1) / TILE_Y), block(TILE_X, TILE_Y);
+    if (is_ssr) {
+        static bool attr = false;
+        if (!attr) { GIGS_CUDA(cudaFuncSetAttribute(gi_march_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr = true; }
+        gi_march_kernel<true><<<grid, block, smem, st>>>(W, H, fx, fy, radius, bias, thick, delta, step, start, dc.n_phi,
+                                                         dc.n_theta, normal, pos, rgb, albedo, metallic, F0, out0, out1);
+    } else {
+        static bool attr = false;
+        if (!attr) { GIGS_CUDA(cudaFuncSetAttribute(gi_march_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr = true; }
+        gi_march_kernel<false><<<grid, block, smem, st>>>(W, H, fx, fy, radius, bias, thick, delta, step, start, dc.n_phi,
+                                                          dc.n_theta, normal, pos, nullptr, nullptr, nullptr, nullptr, out0, nullptr);
+    }
+    GIGS_LAUNCH_CHECK("gi_march_kernel");
+    return 0;
+}
+
+int gigs_ssao(int32_t W, int32_t H, float fx, float fy, float radius, float bias, float thick, float delta,
+              int32_t step, int32_t start, const float* normal, const float* pos, float* occlusion, void* stream)
+{
+    if (W <= 0 || H <= 0 || !normal || !pos || !occlusion) { set_error("gigs_ssao: bad arguments"); return -1; }
+    return gi_launch(false, W, H, fx, fy, radius, bias, thick, delta, step, start, normal, pos, nullptr, nullptr, nullptr,
+                     nullptr, occlusion, nullptr, (cudaStream_t)stream);
+}
+
+int gigs_ssr(int32_t W, int32_t H, float fx, float fy, float radius, float bias, float thick, float delta, int32_t step,
+             int32_t start, const float* normal, const float* pos, const float* rgb, const float* albedo,
+             const float* roughness, const float* metallic, const float* F0, float* color, float* abd, void* stream)
+{
+    (void)roughness;  // read but unused by the reference kernel as well (forward.cu:781)
+    if (W <= 0 || H <= 0 || !normal || !pos || !rgb || !albedo || !metallic || !F0 || !color || !abd) { set_error("gigs_ssr: bad arguments"); return -1; }
+    return gi_launch(true, W, H, fx, fy, radius, bias, thick, delta, step, start, normal, pos, rgb, albedo, metallic, F0,
+                     color, abd, (cudaStream_t)stream);
+}
+
+int gigs_ssr_backward(int32_t W, int32_t H, const float* grad_color, const float* abd, float* grad_albedo,
+                      float* grad_roughness, float* grad_metallic, void* stream)
+{
+    if (W <= 0 || H <= 0 || !grad_color || !abd || !grad_albedo) { set_error("gigs_ssr_backward: bad arguments"); return -1; }
+    const size_t n1 = (size_t)W * H, n3 = 3 * n1;
+    ssr_backward_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n3, n1, grad_color, abd, grad_albedo,
+                                                                                      grad_roughness, grad_metallic);
+    GIGS_LAUNCH_CHECK("ssr_backward_kernel");
+    return 0;
+}
+
+int gigs_ffma_peak(double* tflops, void* stream)
+{
+    if (!tflops) { set_error("gigs_ffma_peak: null"); return -1; }
+    cudaStream_t st = (cudaStream_t)stream;
+    float* d = nullptr;
+    GIGS_CUDA(cudaMalloc(&d, 64));
+    cudaEvent_t e0, e1;
+    GIGS_CUDA(cudaEventCreate(&e0));
+    GIGS_CUDA(cudaEventCreate(&e1));
+    const int iters = 4096, blocks = 148 * 8;
+    ffma_peak_kernel<<<blocks, 256, 0, st>>>(d, 64);  // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        GIGS_CUDA(cudaEventRecord(e0, st));
+        ffma_peak_kernel<<<blocks, 256, 0, st>>>(d, iters);
+        GIGS_CUDA(cudaEventRecord(e1, st));
+        GIGS_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        GIGS_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double flop = 2.0 * 64.0 * iters * 256.0 * blocks;
+        const double tf = flop / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    *tflops = best;
+    return 0;
+}
+
+}  // extern "C"

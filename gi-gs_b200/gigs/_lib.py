@@ -1,0 +1,164 @@
+"""ctypes binding of the C-ABI in include/gigs_b200.h.
+
+There is NO fallback: if libgigs_b200.so is missing or a symbol is absent the import fails loudly
+(build with `python -c "import __graft_entry__ as g; g.build()"` or `make -C gi-gs_b200/csrc`).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libgigs_b200.so")
+
+c_f32p = C.c_void_p  # device pointers travel as integers
+
+
+class GigsCamera(C.Structure):
+    _fields_ = [
+        ("width", C.c_int32), ("height", C.c_int32),
+        ("tan_fovx", C.c_float), ("tan_fovy", C.c_float),
+        ("scale_modifier", C.c_float),
+        ("sh_degree", C.c_int32), ("sh_coeffs", C.c_int32),
+        ("prefiltered", C.c_int32), ("debug", C.c_int32), ("inference", C.c_int32), ("argmax_depth", C.c_int32),
+        ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("campos", C.c_void_p), ("bg", C.c_void_p),
+    ]
+
+
+class GigsSizes(C.Structure):
+    _fields_ = [("geom_bytes", C.c_uint64), ("img_bytes", C.c_uint64), ("binning_bytes", C.c_uint64),
+                ("sort_bytes", C.c_uint64)]
+
+
+class GigsLayout(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in (
+        "g_record", "g_cov3D", "g_clamped", "g_tiles_touched", "g_point_offsets", "g_block_sums", "g_num_rendered",
+        "i_final_T", "i_n_contrib", "i_ranges", "b_point_list", "s_keys_sorted", "s_keys_unsorted", "s_vals_unsorted")]
+
+
+class GigsRasterFwd(C.Structure):
+    _fields_ = [
+        ("P", C.c_int32), ("keep_unsorted", C.c_int32),
+        ("cam", GigsCamera),
+        ("means3D", C.c_void_p), ("shs", C.c_void_p), ("colors_precomp", C.c_void_p), ("opacities", C.c_void_p),
+        ("normal", C.c_void_p), ("albedo", C.c_void_p), ("roughness", C.c_void_p), ("metallic", C.c_void_p),
+        ("scales", C.c_void_p), ("rotations", C.c_void_p), ("cov3D_precomp", C.c_void_p),
+        ("out_color", C.c_void_p), ("out_opacity", C.c_void_p), ("out_depth", C.c_void_p), ("out_normal", C.c_void_p),
+        ("out_normal_view", C.c_void_p), ("out_pos", C.c_void_p), ("out_albedo", C.c_void_p),
+        ("out_roughness", C.c_void_p), ("out_metallic", C.c_void_p),
+        ("radii", C.c_void_p),
+        ("geom", C.c_void_p), ("geom_bytes", C.c_uint64),
+        ("img", C.c_void_p), ("img_bytes", C.c_uint64),
+        ("binning", C.c_void_p), ("binning_bytes", C.c_uint64),
+        ("sort", C.c_void_p), ("sort_bytes", C.c_uint64),
+        ("pinned_num_rendered", C.c_void_p),
+        ("num_rendered", C.c_int64),
+        ("stream", C.c_void_p),
+    ]
+
+
+class GigsRasterBwd(C.Structure):
+    _fields_ = [
+        ("P", C.c_int32), ("_pad", C.c_int32),
+        ("num_rendered", C.c_int64),
+        ("cam", GigsCamera),
+        ("means3D", C.c_void_p), ("shs", C.c_void_p), ("colors_precomp", C.c_void_p),
+        ("normal", C.c_void_p), ("albedo", C.c_void_p), ("roughness", C.c_void_p), ("metallic", C.c_void_p),
+        ("scales", C.c_void_p), ("rotations", C.c_void_p), ("cov3D_precomp", C.c_void_p),
+        ("radii", C.c_void_p),
+        ("geom", C.c_void_p), ("binning", C.c_void_p), ("img", C.c_void_p),
+        ("dL_dpix_depth", C.c_void_p), ("dL_dpix", C.c_void_p), ("dL_dpix_opacity", C.c_void_p),
+        ("dL_dpix_normal", C.c_void_p), ("dL_dpix_albedo", C.c_void_p), ("dL_dpix_roughness", C.c_void_p),
+        ("dL_dpix_metallic", C.c_void_p),
+        ("accum", C.c_void_p),
+        ("dL_dmean2D", C.c_void_p), ("dL_dconic", C.c_void_p), ("dL_dopacity", C.c_void_p), ("dL_dcolor", C.c_void_p),
+        ("dL_dnormal", C.c_void_p), ("dL_dalbedo", C.c_void_p), ("dL_droughness", C.c_void_p),
+        ("dL_dmetallic", C.c_void_p), ("dL_dmean3D", C.c_void_p), ("dL_dcov3D", C.c_void_p), ("dL_dsh", C.c_void_p),
+        ("dL_dscale", C.c_void_p), ("dL_drot", C.c_void_p),
+        ("stream", C.c_void_p),
+    ]
+
+
+class GigsShade(C.Structure):
+    _fields_ = [
+        ("W", C.c_int32), ("H", C.c_int32),
+        ("n_spec_levels", C.c_int32),
+        ("spec_res", C.c_int32 * 8),
+        ("spec", C.c_void_p * 8),
+        ("diffuse_res", C.c_int32),
+        ("diffuse", C.c_void_p),
+        ("brdf_lut", C.c_void_p),
+        ("lut_res", C.c_int32),
+        ("tone", C.c_int32), ("gamma", C.c_int32), ("has_metallic", C.c_int32), ("has_occlusion", C.c_int32),
+        ("min_roughness", C.c_float), ("max_roughness", C.c_float),
+        ("normals", C.c_void_p), ("view_dirs", C.c_void_p), ("albedo", C.c_void_p), ("roughness", C.c_void_p),
+        ("metallic", C.c_void_p), ("occlusion", C.c_void_p), ("mask", C.c_void_p), ("background", C.c_void_p),
+        ("render_rgb", C.c_void_p), ("diffuse_rgb", C.c_void_p), ("specular_rgb", C.c_void_p),
+        ("diffuse_light", C.c_void_p),
+        ("g_render_rgb", C.c_void_p), ("g_diffuse_rgb", C.c_void_p), ("g_specular_rgb", C.c_void_p),
+        ("g_albedo", C.c_void_p), ("g_roughness", C.c_void_p), ("g_metallic", C.c_void_p),
+        ("g_diffuse_tex", C.c_void_p),
+        ("g_spec", C.c_void_p * 8),
+        ("stream", C.c_void_p),
+    ]
+
+
+# every symbol include/gigs_b200.h declares: (name, restype, argtypes)
+_i32, _f, _vp, _u64 = C.c_int32, C.c_float, C.c_void_p, C.c_uint64
+SYMBOLS = {
+    "gigs_abi_version": (C.c_int, []),
+    "gigs_last_error": (C.c_char_p, []),
+    "gigs_raster_sizes": (C.c_int, [_i32, _i32, _i32, _u64, C.POINTER(GigsSizes)]),
+    "gigs_raster_layout": (C.c_int, [_i32, _i32, _i32, _u64, C.POINTER(GigsLayout)]),
+    "gigs_raster_forward_begin": (C.c_int, [C.POINTER(GigsRasterFwd)]),
+    "gigs_raster_forward_finish": (C.c_int, [C.POINTER(GigsRasterFwd)]),
+    "gigs_lite_forward_finish": (C.c_int, [C.POINTER(GigsRasterFwd)]),
+    "gigs_raster_backward": (C.c_int, [C.POINTER(GigsRasterBwd)]),
+    "gigs_mark_visible": (C.c_int, [_i32, _vp, _vp, _vp, _vp]),
+    "gigs_depth_to_normal": (C.c_int, [_i32, _i32, _f, _f, _vp, _vp, _vp, _vp, _vp]),
+    "gigs_median3x3": (C.c_int, [_i32, _i32, _i32, _vp, _vp, _vp]),
+    "gigs_median3x3_backward": (C.c_int, [_i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "gigs_bilateral3x3": (C.c_int, [_i32, _i32, _i32, _f, _f, _vp, _vp, _vp]),
+    "gigs_geometry_chain": (C.c_int, [_i32, _i32, _f, _f, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "gigs_ssao": (C.c_int, [_i32, _i32, _f, _f, _f, _f, _f, _f, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "gigs_ssr": (C.c_int, [_i32, _i32, _f, _f, _f, _f, _f, _f, _i32, _i32] + [_vp] * 10),
+    "gigs_ssr_backward": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gigs_shade_forward": (C.c_int, [C.POINTER(GigsShade)]),
+    "gigs_shade_backward": (C.c_int, [C.POINTER(GigsShade)]),
+    "gigs_dist2": (C.c_int, [_i32, _vp, _vp, _vp, C.POINTER(C.c_uint64), _vp]),
+    "gigs_ffma_peak": (C.c_int, [C.POINTER(C.c_double), _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libgigs_b200.so and bind every declared symbol. Raises (never falls back) on failure."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"gigs_b200: {LIB_PATH} not found. This package has no CPU or PyTorch fallback; build the CUDA "
+            f"library first (python -c 'import __graft_entry__ as g; g.build()').")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    if lib.gigs_abi_version() != 1:
+        raise ImportError("gigs_b200: ABI version mismatch between the python binding and libgigs_b200.so")
+    _lib = lib
+    return lib
+
+
+def check(status, what):
+    if status != 0:
+        msg = load().gigs_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed with status {status}: {msg}")
+
+
+def ptr(t):
+    """Device pointer of a tensor, or None (-> NULL) for None / empty tensors, as the reference's
+    C++ sees nullptr for torch.Tensor([]) (diff_gaussian_rasterization/__init__.py:435-445)."""
+    if t is None or t.numel() == 0:
+        return None
+    return t.data_ptr()

@@ -1,0 +1,251 @@
+/*
+ * gigs_b200 — C-ABI of the B200-native (sm_100a) GI-GS differentiable-rendering hot path.
+ *
+ * This is the drop-in boundary: plain pointers, sizes and a cudaStream_t (as void*); no torch
+ * types.  Every entry point returns 0 on success, a negative value for an argument error and a
+ * positive cudaError_t for a CUDA failure; gigs_last_error() gives the message.  All data
+ * pointers are DEVICE pointers unless a field says "host".  NULL = "not provided", exactly as
+ * the reference's C++ sees nullptr from empty tensors (cuda_rasterizer/forward.cu:217,254).
+ *
+ * Each entry point names the reference interface it replaces
+ * (paths relative to /root/reference/submodules/diff-gaussian-rasterization unless noted).
+ */
+#ifndef GIGS_B200_H
+#define GIGS_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GIGS_ABI_VERSION 1
+
+/* Per-view constants: the non-tensor fields of GaussianRasterizationSettings
+ * (diff_gaussian_rasterization/__init__.py:31-51). Matrices are the transposed (column-major)
+ * world_view / full_proj matrices, as in the reference. */
+typedef struct GigsCamera {
+    int32_t width, height;
+    float tan_fovx, tan_fovy;
+    float scale_modifier;
+    int32_t sh_degree;   /* D: active degree */
+    int32_t sh_coeffs;   /* M: stored coefficients per Gaussian (0 when colors_precomp is used) */
+    int32_t prefiltered, debug, inference, argmax_depth;
+    const float* viewmatrix; /* [16] */
+    const float* projmatrix; /* [16] */
+    const float* campos;     /* [3]  */
+    const float* bg;         /* [3]  */
+} GigsCamera;
+
+/* Workspace sizes. geom/img/binning are the three opaque blobs the reference saves for backward
+ * (rasterize_points.cu:183-188, rasterizer_impl.cu:155-199); their layout here is our own, a pure
+ * function of (P, W, H, R). sort_bytes is transient scratch that need not outlive the call. */
+typedef struct GigsSizes {
+    uint64_t geom_bytes, img_bytes, binning_bytes, sort_bytes;
+} GigsSizes;
+
+int gigs_abi_version(void);
+const char* gigs_last_error(void);
+int gigs_raster_sizes(int32_t P, int32_t W, int32_t H, uint64_t R, GigsSizes* out);
+
+/* Byte offsets of the fields inside the blobs (for tests that check keys / sort order / ranges
+ * bit-for-bit against the reference's GeometryState / BinningState / ImageState). */
+typedef struct GigsLayout {
+    /* geom blob */
+    uint64_t g_record;        /* float[P][24] packed blend record, see DESIGN.md */
+    uint64_t g_cov3D;         /* float[P][6]  */
+    uint64_t g_clamped;       /* uint8[P][4]  (3 used) */
+    uint64_t g_tiles_touched; /* uint32[P] */
+    uint64_t g_point_offsets; /* uint32[P] inclusive scan */
+    uint64_t g_block_sums;    /* uint32[ceil(P/256)+1] */
+    uint64_t g_num_rendered;  /* uint32[1] */
+    /* img blob */
+    uint64_t i_final_T;       /* float[N] */
+    uint64_t i_n_contrib;     /* uint32[N] */
+    uint64_t i_ranges;        /* uint2[T] */
+    /* binning blob */
+    uint64_t b_point_list;    /* uint32[R] sorted Gaussian ids */
+    /* sort scratch */
+    uint64_t s_keys_sorted;   /* uint64[R] */
+    uint64_t s_keys_unsorted; /* uint64[R] (valid only with keep_unsorted) */
+    uint64_t s_vals_unsorted; /* uint32[R] (valid only with keep_unsorted) */
+} GigsLayout;
+int gigs_raster_layout(int32_t P, int32_t W, int32_t H, uint64_t R, GigsLayout* out);
+
+/* Replaces RasterizeGaussiansCUDA (rasterize_points.cu:130-252) ->
+ * CudaRasterizer::Rasterizer::forward (cuda_rasterizer/rasterizer_impl.cu:486-672).
+ * Two phases because num_rendered sizes the binning blob, which the caller owns:
+ *   begin : preprocess + tile-count scan, stream-sync, num_rendered returned in *a->num_rendered
+ *   finish: key emission, onesweep radix sort, tile ranges, G-buffer blend
+ * Output maps are CHW planar float32, fully written by finish (no pre-fill needed). */
+typedef struct GigsRasterFwd {
+    int32_t P;
+    int32_t keep_unsorted; /* tests only: sort out-of-place into a fresh buffer so unsorted keys survive */
+    GigsCamera cam;
+    const float* means3D;        /* [P,3] */
+    const float* shs;            /* [P,M,3] or NULL */
+    const float* colors_precomp; /* [P,3] or NULL */
+    const float* opacities;      /* [P] */
+    const float* normal;         /* [P,3] */
+    const float* albedo;         /* [P,3] */
+    const float* roughness;      /* [P] */
+    const float* metallic;       /* [P] */
+    const float* scales;         /* [P,3] or NULL */
+    const float* rotations;      /* [P,4] or NULL */
+    const float* cov3D_precomp;  /* [P,6] or NULL */
+    float* out_color;       /* [3,H,W] */
+    float* out_opacity;     /* [1,H,W] */
+    float* out_depth;       /* [1,H,W] */
+    float* out_normal;      /* [3,H,W] */
+    float* out_normal_view; /* [3,H,W] */
+    float* out_pos;         /* [3,H,W] */
+    float* out_albedo;      /* [3,H,W] */
+    float* out_roughness;   /* [1,H,W] */
+    float* out_metallic;    /* [1,H,W] */
+    int32_t* radii;         /* [P] */
+    void* geom;    uint64_t geom_bytes;
+    void* img;     uint64_t img_bytes;
+    void* binning; uint64_t binning_bytes; /* finish only */
+    void* sort;    uint64_t sort_bytes;    /* finish only */
+    uint32_t* pinned_num_rendered;         /* host, page-locked, 4 bytes; may be NULL */
+    int64_t num_rendered;                  /* out of begin, in of finish */
+    void* stream;                          /* cudaStream_t */
+} GigsRasterFwd;
+int gigs_raster_forward_begin(GigsRasterFwd* a);
+int gigs_raster_forward_finish(GigsRasterFwd* a);
+
+/* Replaces LiteRasterizeGaussiansCUDA (rasterize_points.cu:39-127): colour + opacity + depth only.
+ * Same struct; normal/albedo/roughness/metallic inputs and the six PBR outputs are ignored. */
+int gigs_lite_forward_finish(GigsRasterFwd* a);
+
+/* Replaces RasterizeGaussiansBackwardCUDA (rasterize_points.cu:254-364) ->
+ * CudaRasterizer::Rasterizer::backward (cuda_rasterizer/rasterizer_impl.cu:676-803).
+ * Upstream gradients may be NULL (treated as all-zero; the result is identical to the
+ * reference fed a materialised zero tensor). Every output element is written exactly once. */
+typedef struct GigsRasterBwd {
+    int32_t P;
+    int32_t _pad;
+    int64_t num_rendered;
+    GigsCamera cam;
+    const float* means3D; const float* shs; const float* colors_precomp;
+    const float* normal; const float* albedo; const float* roughness; const float* metallic;
+    const float* scales; const float* rotations; const float* cov3D_precomp;
+    const int32_t* radii;
+    const void* geom; const void* binning; const void* img;
+    const float* dL_dpix_depth;     /* [1,H,W] */
+    const float* dL_dpix;           /* [3,H,W] */
+    const float* dL_dpix_opacity;   /* [1,H,W] */
+    const float* dL_dpix_normal;    /* [3,H,W] */
+    const float* dL_dpix_albedo;    /* [3,H,W] */
+    const float* dL_dpix_roughness; /* [1,H,W] */
+    const float* dL_dpix_metallic;  /* [1,H,W] */
+    float* accum;        /* scratch float[P][20], zero-initialised by the call */
+    float* dL_dmean2D;   /* [P,3] (xy + |grad| in z, backward.cu:616-619) */
+    float* dL_dconic;    /* [P,4] may be NULL (intermediate in the reference) */
+    float* dL_dopacity;  /* [P]   */
+    float* dL_dcolor;    /* [P,3] */
+    float* dL_dnormal;   /* [P,3] */
+    float* dL_dalbedo;   /* [P,3] */
+    float* dL_droughness;/* [P]   */
+    float* dL_dmetallic; /* [P]   */
+    float* dL_dmean3D;   /* [P,3] */
+    float* dL_dcov3D;    /* [P,6] */
+    float* dL_dsh;       /* [P,M,3] or NULL */
+    float* dL_dscale;    /* [P,3] or NULL */
+    float* dL_drot;      /* [P,4] or NULL */
+    void* stream;
+} GigsRasterBwd;
+int gigs_raster_backward(GigsRasterBwd* a);
+
+/* Replaces markVisible (rasterize_points.cu:366-385, rasterizer_impl.cu:54-66). present: uint8[P]. */
+int gigs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, uint8_t* present, void* stream);
+
+/* Replaces depthToNormal (rasterize_points.cu:387-405, forward.cu:914-1032).
+ * normal_map/depth_pos [3,H,W]; fully written (zeros where the reference leaves its fill). */
+int gigs_depth_to_normal(int32_t W, int32_t H, float fx, float fy, const float* viewmatrix,
+                         const float* depth, float* normal_map, float* depth_pos, void* stream);
+
+/* 3x3 zero-padded lower-median over C planes (kornia.filters.median_blur as called at
+ * diff_gaussian_rasterization/__init__.py:478,504); window containing NaN/inf -> NaN. */
+int gigs_median3x3(int32_t C, int32_t W, int32_t H, const float* in, float* out, void* stream);
+/* backward of the above: routes each output gradient to the selected input element. */
+int gigs_median3x3_backward(int32_t C, int32_t W, int32_t H, const float* in, const float* grad_out,
+                            float* grad_in /* zero-filled by the call */, void* stream);
+
+/* 3x3 bilateral blur, reflect border, L1 colour distance, sigma_color, sigma_space
+ * (kornia.filters.bilateral_blur as called at diff_gaussian_rasterization/__init__.py:491). */
+int gigs_bilateral3x3(int32_t C, int32_t W, int32_t H, float sigma_color, float sigma_space,
+                      const float* in, float* out, void* stream);
+
+/* Fused GaussianRasterizer.forward post-pass (diff_gaussian_rasterization/__init__.py:475-504):
+ * median(depth) -> depth_to_normal -> bilateral(normal) and median(depth_pos), one kernel. */
+int gigs_geometry_chain(int32_t W, int32_t H, float fx, float fy, const float* viewmatrix,
+                        const float* depth, int32_t derive_normal,
+                        float* normal_from_depth /*[3,H,W]*/, float* depth_pos_filter /*[3,H,W]*/,
+                        void* stream);
+
+/* Replaces SSAO (rasterize_points.cu:407-436, forward.cu:635-724). */
+int gigs_ssao(int32_t W, int32_t H, float fx, float fy, float radius, float bias, float thick,
+              float delta, int32_t step, int32_t start, const float* normal, const float* pos,
+              float* occlusion, void* stream);
+
+/* Replaces SSR (rasterize_points.cu:438-477, forward.cu:726-909). */
+int gigs_ssr(int32_t W, int32_t H, float fx, float fy, float radius, float bias, float thick,
+             float delta, int32_t step, int32_t start, const float* normal, const float* pos,
+             const float* rgb, const float* albedo, const float* roughness, const float* metallic,
+             const float* F0, float* color, float* abd, void* stream);
+
+/* Replaces SSR_BACKWARD (rasterize_points.cu:479-510). The reference's Python never calls its
+ * kernel (diff_gaussian_rasterization/__init__.py:666-673); the live semantics are
+ * grad_albedo = grad_color * abd, zeros for roughness/metallic, which is what this computes. */
+int gigs_ssr_backward(int32_t W, int32_t H, const float* grad_color, const float* abd,
+                      float* grad_albedo, float* grad_roughness, float* grad_metallic, void* stream);
+
+/* Fused split-sum deferred shading: pbr_shading (/root/reference/pbr/shade.py:104-237) with
+ * CubemapLight.get_mip (pbr/light.py:142-152) and nvdiffrast texture semantics restated.
+ * Maps are CHW planar (the layout the rasterizer produces); the HWC permutes of train.py:343-348
+ * are folded into the addressing. */
+typedef struct GigsShade {
+    int32_t W, H;
+    int32_t n_spec_levels;          /* len(light.specular), <= 8 */
+    int32_t spec_res[8];            /* per-level face resolution */
+    const float* spec[8];           /* per-level [6,res,res,3] */
+    int32_t diffuse_res;            /* 16 */
+    const float* diffuse;           /* [6,res,res,3] */
+    const float* brdf_lut;          /* [256,256,2] */
+    int32_t lut_res;
+    int32_t tone, gamma, has_metallic, has_occlusion;
+    float min_roughness, max_roughness; /* 0.08, 0.5 */
+    const float* normals;    /* [3,H,W] */
+    const float* view_dirs;  /* [3,H,W] */
+    const float* albedo;     /* [3,H,W] */
+    const float* roughness;  /* [1,H,W] */
+    const float* metallic;   /* [1,H,W] or NULL */
+    const float* occlusion;  /* [1,H,W] or NULL */
+    const uint8_t* mask;     /* [H,W] */
+    const float* background; /* [3,H,W] or NULL (zeros) */
+    /* forward outputs, CHW */
+    float* render_rgb; float* diffuse_rgb; float* specular_rgb; float* diffuse_light;
+    /* backward (all may be NULL in forward) */
+    const float* g_render_rgb; const float* g_diffuse_rgb; const float* g_specular_rgb;
+    float* g_albedo; float* g_roughness; float* g_metallic; /* written */
+    float* g_diffuse_tex;  /* [6,res,res,3], accumulated (+=) */
+    float* g_spec[8];      /* accumulated (+=) */
+    void* stream;
+} GigsShade;
+int gigs_shade_forward(GigsShade* a);
+int gigs_shade_backward(GigsShade* a);
+
+/* Replaces distCUDA2 / SimpleKNN::knn (/root/reference/submodules/simple-knn/spatial.cu,
+ * simple_knn.cu:165-207): mean squared distance to the 3 nearest other points.
+ * scratch_bytes: call with scratch==NULL to query. */
+int gigs_dist2(int32_t P, const float* points, float* mean_dist2, void* scratch,
+               uint64_t* scratch_bytes, void* stream);
+
+/* Measured-roofline helper: register-only FFMA throughput (flop/s) over all SMs. */
+int gigs_ffma_peak(double* tflops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GIGS_B200_H */
