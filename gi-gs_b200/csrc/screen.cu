@@ -461,7 +461,7 @@ gi_march_kernel(const int W, const int H, const float focal_x, const float focal
         if (IS_SSR)
             nrSamples += 1;
         else
-            nrSamples += de.c * de.s;
+            nrSamples = __fmaf_rn(de.c, de.s, nrSamples);  // the reference's SASS contracts both accumulations
         for (int j = start; j < step; ++j) {
             float3 sp;
             sp.x = pos.x + sv.x * j * scale * scale * radius / stepf;
@@ -481,7 +481,7 @@ gi_march_kernel(const int W, const int H, const float focal_x, const float focal
                     diffuse.y += g * de.c * de.s;
                     diffuse.z += b * de.c * de.s;
                 } else {
-                    occ += de.c * de.s;
+                    occ = __fmaf_rn(de.c, de.s, occ);
                 }
                 break;
             }

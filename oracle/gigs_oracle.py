@@ -1,0 +1,999 @@
+"""TEST INFRASTRUCTURE — CPU oracle for the GI-GS differentiable-rendering hot path.
+
+A PyTorch-CPU (float32; float64 only where the CUDA source promotes) restatement of the reference's
+algorithm. The reference has no CPU path, so this transcription is both the small-input oracle and the
+reported CPU baseline. It is NOT product code: only tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs may import it.
+
+PINNING: the reference ships no golden vectors for this path. This oracle is pinned
+against outputs of the reference's OWN CUDA kernels (oracle/_ref, built from /root/reference by
+oracle/Makefile) run on a B200 and committed under tests/golden/ by tests/make_golden.py. The nvdiffrast /
+kornia restatements (texture sampling, median / bilateral filters) have no reference implementation on this
+box: for those parts parity is UNPINNED and checked against analytic properties only.
+
+Each function cites the reference lines it follows (paths relative to
+/root/reference/submodules/diff-gaussian-rasterization/ unless noted). "rank-major" loops: instead of
+looping tiles and then Gaussians, the blend iterates the depth rank j and processes every tile's j-th
+Gaussian at once — per pixel this is exactly the reference's sequential front-to-back order.
+"""
+import math
+from typing import Dict, Optional
+
+import torch
+
+TILE = 16  # cuda_rasterizer/config.h:16-17
+
+SH_C0 = 0.28209479177387814
+SH_C1 = 0.4886025119029199
+SH_C2 = [1.0925484305920792, -1.0925484305920792, 0.31539156525252005, -1.0925484305920792, 0.5462742152960396]
+SH_C3 = [-0.5900435899266435, 2.890611442640554, -0.4570457994644658, 0.3731763325901154, -0.4570457994644658,
+         1.445305721320277, -0.5900435899266435]
+
+F32 = torch.float32
+
+
+def _f(x):
+    return torch.as_tensor(x, dtype=F32)
+
+
+# ------------------------------------------------------------------------------------------------
+# preprocess forward: cuda_rasterizer/forward.cu:164-276 (+ :22-161, auxiliary.h:41-66,150-176)
+# ------------------------------------------------------------------------------------------------
+def transform_point_4x3(p, M):
+    # auxiliary.h:58-66, M is the flattened column-major 4x4 (= the transposed torch matrix, row-major flatten)
+    m = M.reshape(-1)
+    x, y, z = p[:, 0], p[:, 1], p[:, 2]
+    return torch.stack([m[0] * x + m[4] * y + m[8] * z + m[12], m[1] * x + m[5] * y + m[9] * z + m[13],
+                        m[2] * x + m[6] * y + m[10] * z + m[14]], dim=1)
+
+
+def transform_point_4x4(p, M):
+    m = M.reshape(-1)
+    x, y, z = p[:, 0], p[:, 1], p[:, 2]
+    return torch.stack([m[0] * x + m[4] * y + m[8] * z + m[12], m[1] * x + m[5] * y + m[9] * z + m[13],
+                        m[2] * x + m[6] * y + m[10] * z + m[14], m[3] * x + m[7] * y + m[11] * z + m[15]], dim=1)
+
+
+def compute_cov3d(scales, mod, rot):
+    # forward.cu:127-161: M = S*R (glm column-major), Sigma = M^T M; quaternion NOT renormalised (:136)
+    r, x, y, z = rot[:, 0], rot[:, 1], rot[:, 2], rot[:, 3]
+    # glm::mat3(a,b,c, d,e,f, g,h,i): columns (a,b,c),(d,e,f),(g,h,i). As a math matrix Rm[row][col]:
+    Rm = torch.stack([
+        torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y + r * z), 2 * (x * z - r * y)], dim=1),
+        torch.stack([2 * (x * y - r * z), 1 - 2 * (x * x + z * z), 2 * (y * z + r * x)], dim=1),
+        torch.stack([2 * (x * z + r * y), 2 * (y * z - r * x), 1 - 2 * (x * x + y * y)], dim=1)], dim=1)
+    S = torch.diag_embed(mod * scales)
+    Mm = S @ Rm
+    Sigma = Mm.transpose(1, 2) @ Mm
+    return torch.stack([Sigma[:, 0, 0], Sigma[:, 0, 1], Sigma[:, 0, 2], Sigma[:, 1, 1], Sigma[:, 1, 2], Sigma[:, 2, 2]],
+                       dim=1)
+
+
+def _cov2d_parts(mean, fx, fy, tan_fovx, tan_fovy, cov3D, V):
+    # forward.cu:83-122
+    t = transform_point_4x3(mean, V)
+    limx, limy = 1.3 * tan_fovx, 1.3 * tan_fovy
+    txtz, tytz = t[:, 0] / t[:, 2], t[:, 1] / t[:, 2]
+    tx = torch.clamp(txtz, -limx, limx) * t[:, 2]
+    ty = torch.clamp(tytz, -limy, limy) * t[:, 2]
+    tz = t[:, 2]
+    zero = torch.zeros_like(tz)
+    # math-matrix form of the glm objects: J (3x3, rows), W = upper 3x3 of the world->view rotation
+    J = torch.stack([torch.stack([fx / tz, zero, -(fx * tx) / (tz * tz)], dim=1),
+                     torch.stack([zero, fy / tz, -(fy * ty) / (tz * tz)], dim=1),
+                     torch.stack([zero, zero, zero], dim=1)], dim=1)
+    m = V.reshape(-1)
+    Wm = torch.stack([torch.stack([m[0], m[4], m[8]]), torch.stack([m[1], m[5], m[9]]),
+                      torch.stack([m[2], m[6], m[10]])])  # rows of the view rotation
+    # glm: W = mat3(cols (m0,m4,m8),(m1,m5,m9),(m2,m6,m10)) => math matrix with those as COLUMNS = Wm^T;
+    # glm J has the rows above as COLUMNS => math matrix J^T. T = W*J => (Wm^T)(J^T) = (J Wm)^T.
+    # cov = T^T Vrk^T T = (J Wm) Vrk (J Wm)^T
+    Vrk = torch.stack([torch.stack([cov3D[:, 0], cov3D[:, 1], cov3D[:, 2]], dim=1),
+                       torch.stack([cov3D[:, 1], cov3D[:, 3], cov3D[:, 4]], dim=1),
+                       torch.stack([cov3D[:, 2], cov3D[:, 4], cov3D[:, 5]], dim=1)], dim=1)
+    A = J @ Wm.unsqueeze(0)
+    cov = A @ Vrk @ A.transpose(1, 2)
+    return cov, t, txtz, tytz, A
+
+
+def compute_cov2d(mean, fx, fy, tan_fovx, tan_fovy, cov3D, V):
+    cov, *_ = _cov2d_parts(mean, fx, fy, tan_fovx, tan_fovy, cov3D, V)
+    return torch.stack([cov[:, 0, 0] + 0.3, cov[:, 0, 1], cov[:, 1, 1] + 0.3], dim=1)
+
+
+def sh_basis(deg, d):
+    """Coefficients b_k(dir) such that rgb = sum_k b_k * sh_k + 0.5 (forward.cu:22-80)."""
+    x, y, z = d[:, 0], d[:, 1], d[:, 2]
+    one = torch.ones_like(x)
+    b = [SH_C0 * one]
+    if deg > 0:
+        b += [-SH_C1 * y, SH_C1 * z, -SH_C1 * x]
+        if deg > 1:
+            xx, yy, zz, xy, yz, xz = x * x, y * y, z * z, x * y, y * z, x * z
+            b += [SH_C2[0] * xy, SH_C2[1] * yz, SH_C2[2] * (2.0 * zz - xx - yy), SH_C2[3] * xz, SH_C2[4] * (xx - yy)]
+            if deg > 2:
+                b += [SH_C3[0] * y * (3.0 * xx - yy), SH_C3[1] * xy * z, SH_C3[2] * y * (4.0 * zz - xx - yy),
+                      SH_C3[3] * z * (2.0 * zz - 3.0 * xx - 3.0 * yy), SH_C3[4] * x * (4.0 * zz - xx - yy),
+                      SH_C3[5] * z * (xx - yy), SH_C3[6] * x * (xx - 3.0 * yy)]
+    return torch.stack(b, dim=1)
+
+
+def compute_color_from_sh(deg, means, campos, shs):
+    d = means - campos[None]
+    d = d / d.norm(dim=1, keepdim=True)
+    B = sh_basis(deg, d)  # [P, K]
+    K = B.shape[1]
+    result = (B[:, :, None] * shs[:, :K, :]).sum(1) + 0.5
+    clamped = result < 0
+    return torch.clamp_min(result, 0.0), clamped
+
+
+def ndc2pix(v, S):
+    # auxiliary.h:41-44: evaluated in double
+    return (((v.double() + 1.0) * S - 1.0) * 0.5).float()
+
+
+def get_rect(p, radius, grid_x, grid_y):
+    # auxiliary.h:46-56: float division by 16, C truncation, clamp to the grid
+    r = radius.float()
+    rmin_x = torch.clamp(torch.trunc((p[:, 0] - r) / TILE).long(), 0, grid_x)
+    rmin_y = torch.clamp(torch.trunc((p[:, 1] - r) / TILE).long(), 0, grid_y)
+    rmax_x = torch.clamp(torch.trunc((p[:, 0] + r + TILE - 1) / TILE).long(), 0, grid_x)
+    rmax_y = torch.clamp(torch.trunc((p[:, 1] + r + TILE - 1) / TILE).long(), 0, grid_y)
+    return rmin_x, rmin_y, rmax_x, rmax_y
+
+
+def preprocess(g: Dict, cam, scale_modifier=1.0, colors_precomp=None, cov3D_precomp=None) -> Dict:
+    means = g["means3D"].float()
+    P = means.shape[0]
+    W, H = cam.image_width, cam.image_height
+    V, PM, campos = cam.world_view_transform.float(), cam.full_proj_transform.float(), cam.camera_center.float()
+    fx, fy = W / (2.0 * cam.tanfovx), H / (2.0 * cam.tanfovy)
+    fx, fy = float(_f(fx)), float(_f(fy))
+    grid_x, grid_y = (W + TILE - 1) // TILE, (H + TILE - 1) // TILE
+    p_view = transform_point_4x3(means, V)
+    ok = p_view[:, 2] > 0.2  # in_frustum, auxiliary.h:166 (no x/y test in this fork)
+    p_hom = transform_point_4x4(means, PM)
+    p_w = 1.0 / (p_hom[:, 3] + 0.0000001)
+    p_proj = p_hom[:, :3] * p_w[:, None]
+    cov3D = cov3D_precomp.float() if cov3D_precomp is not None else compute_cov3d(g["scales"].float(), scale_modifier,
+                                                                                  g["rotations"].float())
+    cov = compute_cov2d(means, fx, fy, float(_f(cam.tanfovx)), float(_f(cam.tanfovy)), cov3D, V)
+    det = cov[:, 0] * cov[:, 2] - cov[:, 1] * cov[:, 1]
+    ok = ok & (det != 0)
+    det_inv = 1.0 / det
+    conic = torch.stack([cov[:, 2] * det_inv, -cov[:, 1] * det_inv, cov[:, 0] * det_inv], dim=1)
+    mid = 0.5 * (cov[:, 0] + cov[:, 2])
+    s = torch.sqrt(torch.clamp_min(mid * mid - det, 0.1))
+    lam = torch.maximum(mid + s, mid - s)
+    my_radius = torch.ceil(3.0 * torch.sqrt(lam))
+    my_radius = torch.nan_to_num(my_radius, nan=0.0, posinf=0.0, neginf=0.0)
+    pix = torch.stack([ndc2pix(p_proj[:, 0], W), ndc2pix(p_proj[:, 1], H)], dim=1)
+    rmin_x, rmin_y, rmax_x, rmax_y = get_rect(torch.nan_to_num(pix), my_radius.long(), grid_x, grid_y)
+    area = (rmax_x - rmin_x) * (rmax_y - rmin_y)
+    ok = ok & (area != 0)
+    if colors_precomp is None:
+        rgb, clamped = compute_color_from_sh(g["sh_degree"], means, campos, g["shs"].float())
+    else:
+        rgb, clamped = colors_precomp.float(), torch.zeros(P, 3, dtype=torch.bool)
+    z = torch.zeros((), dtype=torch.long)
+    return dict(ok=ok, depths=p_view[:, 2], pos_view=p_view, radii=torch.where(ok, my_radius.long(), z).int(),
+                means2D=pix, conic=conic, cov2D=cov, cov3D=cov3D, rgb=rgb, clamped=clamped,
+                tiles_touched=torch.where(ok, area, z), rect=(rmin_x, rmin_y, rmax_x, rmax_y), grid=(grid_x, grid_y))
+
+
+# ------------------------------------------------------------------------------------------------
+# binning: cuda_rasterizer/rasterizer_impl.cu:70-138, 582-630
+# ------------------------------------------------------------------------------------------------
+def higher_msb(n: int) -> int:
+    # rasterizer_impl.cu:35-50
+    msb = 16
+    step = 16
+    while step > 1:
+        step //= 2
+        if n >> msb:
+            msb += step
+        else:
+            msb -= step
+    if n >> msb:
+        msb += 1
+    return msb
+
+
+def binning(pre: Dict) -> Dict:
+    ok = pre["ok"]
+    grid_x, grid_y = pre["grid"]
+    rmin_x, rmin_y, rmax_x, rmax_y = pre["rect"]
+    touched = pre["tiles_touched"]
+    offsets = torch.cumsum(touched, 0)  # InclusiveSum
+    R = int(offsets[-1]) if offsets.numel() else 0
+    ids = torch.nonzero(ok).squeeze(1)
+    cnt = touched[ids]
+    gid = torch.repeat_interleave(ids, cnt)                      # Gaussian of each instance, emission order
+    start = (offsets - touched)[ids]
+    k = torch.arange(R) - torch.repeat_interleave(start, cnt)    # local index inside the rect, y outer / x inner
+    w = (rmax_x - rmin_x)[gid]
+    ty = rmin_y[gid] + k // w
+    tx = rmin_x[gid] + k % w
+    tile = ty * grid_x + tx
+    depth_bits = pre["depths"].contiguous().view(torch.int32).long() & 0xFFFFFFFF
+    keys = (tile << 32) | depth_bits[gid]
+    bit = higher_msb(grid_x * grid_y)
+    masked = keys & ((1 << (32 + bit)) - 1)
+    order = torch.sort(masked, stable=True).indices              # stable LSD radix sort == stable sort
+    keys_sorted = keys[order]
+    point_list = gid[order]
+    T = grid_x * grid_y
+    ranges = torch.zeros(T, 2, dtype=torch.long)
+    if R > 0:
+        tiles_sorted = keys_sorted >> 32
+        first = torch.ones(R, dtype=torch.bool)
+        first[1:] = tiles_sorted[1:] != tiles_sorted[:-1]
+        starts = torch.nonzero(first).squeeze(1)
+        ends = torch.cat([starts[1:], torch.tensor([R])])
+        ranges[tiles_sorted[starts], 0] = starts
+        ranges[tiles_sorted[starts], 1] = ends
+    return dict(num_rendered=R, point_offsets=offsets, keys_unsorted=keys, vals_unsorted=gid, keys_sorted=keys_sorted,
+                point_list=point_list, ranges=ranges)
+
+
+# ------------------------------------------------------------------------------------------------
+# blend forward: cuda_rasterizer/forward.cu:423-633 (rank-major)
+# ------------------------------------------------------------------------------------------------
+def _tile_pixels(W, H, grid_x, grid_y):
+    t = torch.arange(grid_x * grid_y)
+    ty, tx = t // grid_x, t % grid_x
+    l = torch.arange(TILE * TILE)
+    ly, lx = l // TILE, l % TILE
+    px = tx[:, None] * TILE + lx[None]
+    py = ty[:, None] * TILE + ly[None]
+    inside = (px < W) & (py < H)
+    return px, py, inside
+
+
+def blend_forward(pre: Dict, binn: Dict, g: Dict, cam, bg, inference=False, argmax_depth=False,
+                  tiles: Optional[torch.Tensor] = None) -> Dict:
+    """tiles: optional subset of tile ids (used for the bounded CPU-baseline sample); maps are still full size."""
+    W, H = cam.image_width, cam.image_height
+    grid_x, grid_y = pre["grid"]
+    px, py, inside = _tile_pixels(W, H, grid_x, grid_y)
+    ranges, plist = binn["ranges"], binn["point_list"]
+    if tiles is not None:
+        px, py, inside, ranges = px[tiles], py[tiles], inside[tiles], ranges[tiles]
+    Tn = px.shape[0]
+    pixf_x, pixf_y = px.float(), py.float()
+    lens = ranges[:, 1] - ranges[:, 0]
+    maxlen = int(lens.max()) if Tn else 0
+    shp = (Tn, TILE * TILE)
+    Tr = torch.ones(shp)
+    done = ~inside
+    last_contrib = torch.zeros(shp, dtype=torch.long)
+    C = torch.zeros(shp + (3,)); A = torch.zeros(shp + (3,)); N = torch.zeros(shp + (3,)); POS = torch.zeros(shp + (3,))
+    Rg = torch.zeros(shp); Mt = torch.zeros(shp); D = torch.zeros(shp); O = torch.zeros(shp)
+    maxw = torch.zeros(shp); exd = torch.zeros(shp); exp_ = torch.zeros(shp + (3,))
+    xy, conic, op = pre["means2D"], pre["conic"], g["opacity"].reshape(-1).float()
+    feats = pre["rgb"]
+    alb, nrm = g["albedo"].float(), g["normal"].float()
+    rough, metal = g["roughness"].reshape(-1).float(), g["metallic"].reshape(-1).float()
+    depth, posv = pre["depths"], pre["pos_view"]
+    Rtot = plist.numel()
+    for j in range(maxlen):
+        if bool(done.all()):
+            break
+        valid = (j < lens)
+        idx = torch.clamp(ranges[:, 0] + j, max=max(Rtot - 1, 0))
+        gid = plist[idx] if Rtot else torch.zeros(Tn, dtype=torch.long)
+        act = valid[:, None] & ~done
+        dx = xy[gid, 0][:, None] - pixf_x
+        dy = xy[gid, 1][:, None] - pixf_y
+        cn = conic[gid]
+        power = -0.5 * (cn[:, 0:1] * dx * dx + cn[:, 2:3] * dy * dy) - cn[:, 1:2] * dx * dy
+        alpha = torch.clamp_max(op[gid][:, None] * torch.exp(power), 0.99)
+        keep = act & ~(power > 0) & ~(alpha < 1.0 / 255.0)
+        test_T = Tr * (1 - alpha)
+        term = keep & (test_T < 0.0001)
+        done = done | term
+        contrib = keep & ~term
+        w = torch.where(contrib, alpha * Tr, torch.zeros(()))
+        C += feats[gid][:, None, :] * w[..., None]
+        A += alb[gid][:, None, :] * w[..., None]
+        N += nrm[gid][:, None, :] * w[..., None]
+        Rg += rough[gid][:, None] * w
+        Mt += metal[gid][:, None] * w
+        D += depth[gid][:, None] * w
+        POS += posv[gid][:, None, :] * w[..., None]
+        O += w
+        peak = contrib & (w > maxw)
+        exd = torch.where(peak, depth[gid][:, None].expand(shp), exd)
+        exp_ = torch.where(peak[..., None], posv[gid][:, None, :].expand(shp + (3,)), exp_)
+        maxw = torch.where(peak, w, maxw)
+        Tr = torch.where(contrib, test_T, Tr)
+        last_contrib = torch.where(contrib, torch.full((), j + 1), last_contrib)
+
+    HW = H * W
+    out = dict(color=torch.zeros(3, HW), normal=torch.zeros(3, HW), normal_view=torch.zeros(3, HW),
+               pos=torch.zeros(3, HW), albedo=torch.zeros(3, HW), opacity=torch.zeros(1, HW), depth=torch.zeros(1, HW),
+               roughness=torch.zeros(1, HW), metallic=torch.zeros(1, HW), final_T=torch.zeros(HW),
+               n_contrib=torch.zeros(HW, dtype=torch.long))
+    pid = (py * W + px)[inside]
+    sel = inside
+    bg = bg.float()
+    out["final_T"][pid] = Tr[sel]
+    out["n_contrib"][pid] = last_contrib[sel]
+    out["color"][:, pid] = (C[sel] + Tr[sel][:, None] * bg[None]).t()
+    out["normal"][:, pid] = N[sel].t()
+    out["albedo"][:, pid] = A[sel].t()
+    V = cam.world_view_transform.float().reshape(-1)
+    Ns = N[sel]
+    nv = torch.stack([V[0] * Ns[:, 0] + V[4] * Ns[:, 1] + V[8] * Ns[:, 2], V[1] * Ns[:, 0] + V[5] * Ns[:, 1] + V[9] * Ns[:, 2],
+                      V[2] * Ns[:, 0] + V[6] * Ns[:, 1] + V[10] * Ns[:, 2]], dim=1)
+    nv = nv * (1.0 / torch.sqrt((nv * nv).sum(1, keepdim=True)))  # vec_math.h:538, NaN where N == 0
+    out["normal_view"][:, pid] = nv.t()
+    out["roughness"][0, pid] = (Rg + Tr)[sel] if inference else Rg[sel]
+    out["metallic"][0, pid] = Mt[sel]
+    has = O[sel].double() > 1e-6
+    Os = O[sel]
+    zero = torch.zeros(())
+    out["depth"][0, pid] = torch.where(has, exd[sel] if argmax_depth else D[sel] / Os, zero)
+    posn = exp_[sel] if argmax_depth else POS[sel] / Os[:, None]
+    out["pos"][:, pid] = torch.where(has[:, None], posn, zero).t()
+    out["opacity"][0, pid] = Os
+    for k in ("color", "normal", "normal_view", "pos", "albedo"):
+        out[k] = out[k].reshape(3, H, W)
+    for k in ("opacity", "depth", "roughness", "metallic"):
+        out[k] = out[k].reshape(1, H, W)
+    out["pairs_visited"] = int(last_contrib[sel].sum())
+    return out
+
+
+def rasterize_forward(g: Dict, cam, bg, scale_modifier=1.0, inference=False, argmax_depth=False,
+                      colors_precomp=None, cov3D_precomp=None) -> Dict:
+    """cuda_rasterizer/rasterizer_impl.cu:486-672."""
+    P = g["means3D"].shape[0]
+    H, W = cam.image_height, cam.image_width
+    if P == 0:  # rasterize_points.cu:191: zero-filled outputs
+        z3, z1 = torch.zeros(3, H, W), torch.zeros(1, H, W)
+        return dict(color=z3, normal=z3.clone(), normal_view=z3.clone(), pos=z3.clone(), albedo=z3.clone(),
+                    opacity=z1, depth=z1.clone(), roughness=z1.clone(), metallic=z1.clone(), num_rendered=0,
+                    radii=torch.zeros(0, dtype=torch.int32), pre=None, binning=None)
+    pre = preprocess(g, cam, scale_modifier, colors_precomp, cov3D_precomp)
+    binn = binning(pre)
+    out = blend_forward(pre, binn, g, cam, bg, inference, argmax_depth)
+    out.update(num_rendered=binn["num_rendered"], radii=pre["radii"], pre=pre, binning=binn)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# blend backward: cuda_rasterizer/backward.cu:404-630 (rank-major, back to front)
+# ------------------------------------------------------------------------------------------------
+def blend_backward(pre: Dict, binn: Dict, g: Dict, cam, bg, fwd: Dict, grads: Dict,
+                   tiles: Optional[torch.Tensor] = None) -> Dict:
+    W, H = cam.image_width, cam.image_height
+    P = g["means3D"].shape[0]
+    grid_x, grid_y = pre["grid"]
+    px, py, inside = _tile_pixels(W, H, grid_x, grid_y)
+    ranges, plist = binn["ranges"], binn["point_list"]
+    if tiles is not None:
+        px, py, inside, ranges = px[tiles], py[tiles], inside[tiles], ranges[tiles]
+    Tn = px.shape[0]
+    shp = (Tn, TILE * TILE)
+    pid = torch.where(inside, py * W + px, torch.zeros((), dtype=torch.long))
+
+    def gmap(name, c):
+        t = grads.get(name)
+        if t is None:
+            return torch.zeros(shp + (c,))
+        v = t.float().reshape(c, H * W)[:, pid.reshape(-1)].t().reshape(shp + (c,))
+        return torch.where(inside[..., None], v, torch.zeros(()))
+
+    g_col, g_nrm, g_alb = gmap("color", 3), gmap("normal", 3), gmap("albedo", 3)
+    g_op, g_rough, g_metal, g_depth = (gmap(n, 1)[..., 0] for n in ("opacity", "roughness", "metallic", "depth"))
+    edge = (px == 0) | (px == W - 1) | (py == 0) | (py == H - 1)  # backward.cu:497-501
+    g_nrm = torch.where(edge[..., None], torch.zeros(()), g_nrm)
+    T_final = torch.where(inside, fwd["final_T"][pid], torch.zeros(()))
+    last_contributor = torch.where(inside, fwd["n_contrib"][pid], torch.zeros((), dtype=torch.long))
+    lens = ranges[:, 1] - ranges[:, 0]
+    maxlen = int(last_contributor.max()) if Tn else 0
+    Tr = T_final.clone()
+    last_alpha = torch.zeros(shp); accum_op = torch.zeros(shp)
+    accum_rec = torch.zeros(shp + (3,)); last_color = torch.zeros(shp + (3,))
+    ddelx_dx, ddely_dy = float(_f(0.5 * W)), float(_f(0.5 * H))
+    bg_dot = (bg.float()[None, None, :] * g_col).sum(-1)
+    xy, conic, op = pre["means2D"], pre["conic"], g["opacity"].reshape(-1).float()
+    feats = pre["rgb"]
+    acc = dict(mean2D=torch.zeros(P, 3), conic=torch.zeros(P, 4), opacity=torch.zeros(P), colors=torch.zeros(P, 3),
+               normal=torch.zeros(P, 3), albedo=torch.zeros(P, 3), roughness=torch.zeros(P), metallic=torch.zeros(P),
+               depth=torch.zeros(P))
+    pixf_x, pixf_y = px.float(), py.float()
+    Rtot = plist.numel()
+    for j in range(maxlen - 1, -1, -1):
+        valid = (j < lens)
+        idx = torch.clamp(ranges[:, 0] + j, max=max(Rtot - 1, 0))
+        gid = plist[idx]
+        act = valid[:, None] & inside & (j < last_contributor)
+        dx = xy[gid, 0][:, None] - pixf_x
+        dy = xy[gid, 1][:, None] - pixf_y
+        cn = conic[gid]
+        o = op[gid][:, None]
+        power = -0.5 * (cn[:, 0:1] * dx * dx + cn[:, 2:3] * dy * dy) - cn[:, 1:2] * dx * dy
+        G = torch.exp(power)
+        alpha = torch.clamp_max(o * G, 0.99)
+        k = act & ~(power > 0) & ~(alpha < 1.0 / 255.0)
+        kf = k.float()
+        Tr = torch.where(k, Tr / (1.0 - alpha), Tr)
+        w = alpha * Tr * kf
+        c = feats[gid][:, None, :].expand(shp + (3,))
+        accum_rec = torch.where(k[..., None], last_alpha[..., None] * last_color + (1.0 - last_alpha[..., None]) * accum_rec,
+                                accum_rec)
+        last_color = torch.where(k[..., None], c, last_color)
+        dL_dalpha = ((c - accum_rec) * g_col).sum(-1)
+        accum_op = torch.where(k, last_alpha + (1.0 - last_alpha) * accum_op, accum_op)
+        dL_dalpha = dL_dalpha + (1.0 - accum_op) * g_op
+        dL_dalpha = dL_dalpha * Tr
+        last_alpha = torch.where(k, alpha, last_alpha)
+        dL_dalpha = dL_dalpha + (-T_final / (1.0 - alpha)) * bg_dot
+        dL_dalpha = torch.where(k, dL_dalpha, torch.zeros(()))
+        dL_dG = o * dL_dalpha
+        gdx, gdy = G * dx, G * dy
+        dG_ddelx = -gdx * cn[:, 0:1] - gdy * cn[:, 1:2]
+        dG_ddely = -gdy * cn[:, 2:3] - gdx * cn[:, 1:2]
+        m2x = dL_dG * dG_ddelx * ddelx_dx
+        m2y = dL_dG * dG_ddely * ddely_dy
+        z = torch.zeros(())
+        contrib = torch.stack([m2x, m2y, m2x.abs() + m2y.abs()], -1)
+        acc["mean2D"].index_add_(0, gid, torch.where(k[..., None], contrib, z).sum(1))
+        cg = torch.stack([-0.5 * gdx * dx * dL_dG, -0.5 * gdx * dy * dL_dG, torch.zeros(shp), -0.5 * gdy * dy * dL_dG], -1)
+        acc["conic"].index_add_(0, gid, torch.where(k[..., None], cg, z).sum(1))
+        acc["opacity"].index_add_(0, gid, torch.where(k, G * dL_dalpha, z).sum(1))
+        acc["colors"].index_add_(0, gid, (w[..., None] * g_col).sum(1))
+        acc["normal"].index_add_(0, gid, (w[..., None] * g_nrm).sum(1))
+        acc["albedo"].index_add_(0, gid, (w[..., None] * g_alb).sum(1))
+        acc["roughness"].index_add_(0, gid, (w * g_rough).sum(1))
+        acc["metallic"].index_add_(0, gid, (w * g_metal).sum(1))
+        acc["depth"].index_add_(0, gid, (w * g_depth).sum(1))
+    return acc
+
+
+# ------------------------------------------------------------------------------------------------
+# per-Gaussian backward: cuda_rasterizer/backward.cu:145-279 (cov2D), :351-401 (preprocess),
+# :21-140 (SH), :283-346 (cov3D)
+# ------------------------------------------------------------------------------------------------
+def gaussian_backward(pre: Dict, g: Dict, cam, acc: Dict, scale_modifier=1.0, colors_precomp=None,
+                      cov3D_precomp=None) -> Dict:
+    means = g["means3D"].float()
+    P = means.shape[0]
+    W, H = cam.image_width, cam.image_height
+    V, PM, campos = cam.world_view_transform.float(), cam.full_proj_transform.float(), cam.camera_center.float()
+    h_x, h_y = float(_f(W / (2.0 * cam.tanfovx))), float(_f(H / (2.0 * cam.tanfovy)))
+    tan_fovx, tan_fovy = float(_f(cam.tanfovx)), float(_f(cam.tanfovy))
+    vis = pre["radii"] > 0
+    cov3D = pre["cov3D"]
+    cov, t, txtz, tytz, A = _cov2d_parts(means, h_x, h_y, tan_fovx, tan_fovy, cov3D, V)
+    limx, limy = 1.3 * tan_fovx, 1.3 * tan_fovy
+    tx = torch.clamp(txtz, -limx, limx) * t[:, 2]
+    ty = torch.clamp(tytz, -limy, limy) * t[:, 2]
+    x_grad_mul = (~((txtz < -limx) | (txtz > limx))).float()
+    y_grad_mul = (~((tytz < -limy) | (tytz > limy))).float()
+    a, b, c = cov[:, 0, 0] + 0.3, cov[:, 0, 1], cov[:, 1, 1] + 0.3
+    dconic = acc["conic"]
+    cx, cy, cz = dconic[:, 0], dconic[:, 1], dconic[:, 3]
+    denom = a * c - b * b
+    denom2inv = 1.0 / (denom * denom + 0.0000001)
+    nz = denom2inv != 0
+    dL_da = denom2inv * (-c * c * cx + 2 * b * c * cy + (denom - a * c) * cz)
+    dL_dc = denom2inv * (-a * a * cz + 2 * a * b * cy + (denom - a * c) * cx)
+    dL_db = denom2inv * 2 * (b * c * cx - (denom + 2 * b * b) * cy + a * b * cz)
+    zero = torch.zeros(())
+    dL_da, dL_dc, dL_db = (torch.where(nz, v, zero) for v in (dL_da, dL_dc, dL_db))
+    # glm T[c][r] (column c, row r) = math (A^T)[r][c] = A[c][r]: T[0][k] = A[0,k], T[1][k] = A[1,k]
+    T0, T1 = A[:, 0, :], A[:, 1, :]
+    dcov = torch.stack([
+        T0[:, 0] * T0[:, 0] * dL_da + T0[:, 0] * T1[:, 0] * dL_db + T1[:, 0] * T1[:, 0] * dL_dc,
+        2 * T0[:, 0] * T0[:, 1] * dL_da + (T0[:, 0] * T1[:, 1] + T0[:, 1] * T1[:, 0]) * dL_db + 2 * T1[:, 0] * T1[:, 1] * dL_dc,
+        2 * T0[:, 0] * T0[:, 2] * dL_da + (T0[:, 0] * T1[:, 2] + T0[:, 2] * T1[:, 0]) * dL_db + 2 * T1[:, 0] * T1[:, 2] * dL_dc,
+        T0[:, 1] * T0[:, 1] * dL_da + T0[:, 1] * T1[:, 1] * dL_db + T1[:, 1] * T1[:, 1] * dL_dc,
+        2 * T0[:, 2] * T0[:, 1] * dL_da + (T0[:, 1] * T1[:, 2] + T0[:, 2] * T1[:, 1]) * dL_db + 2 * T1[:, 1] * T1[:, 2] * dL_dc,
+        T0[:, 2] * T0[:, 2] * dL_da + T0[:, 2] * T1[:, 2] * dL_db + T1[:, 2] * T1[:, 2] * dL_dc], dim=1)
+    Vrk = torch.stack([torch.stack([cov3D[:, 0], cov3D[:, 1], cov3D[:, 2]], dim=1),
+                       torch.stack([cov3D[:, 1], cov3D[:, 3], cov3D[:, 4]], dim=1),
+                       torch.stack([cov3D[:, 2], cov3D[:, 4], cov3D[:, 5]], dim=1)], dim=1)
+    # dL_dT0k = 2 (T0 . Vrk[k]) dL_da + (T1 . Vrk[k]) dL_db ;  dL_dT1k = 2 (T1 . Vrk[k]) dL_dc + (T0 . Vrk[k]) dL_db
+    T0V = torch.einsum("pi,pki->pk", T0, Vrk)
+    T1V = torch.einsum("pi,pki->pk", T1, Vrk)
+    dT0 = 2 * T0V * dL_da[:, None] + T1V * dL_db[:, None]
+    dT1 = 2 * T1V * dL_dc[:, None] + T0V * dL_db[:, None]
+    m = V.reshape(-1)
+    # glm W[c][r]: W[0]=(m0,m4,m8), W[1]=(m1,m5,m9), W[2]=(m2,m6,m10)
+    W0 = torch.stack([m[0], m[4], m[8]]); W1 = torch.stack([m[1], m[5], m[9]]); W2 = torch.stack([m[2], m[6], m[10]])
+    dJ00 = (W0[None] * dT0).sum(1)
+    dJ02 = (W2[None] * dT0).sum(1)
+    dJ11 = (W1[None] * dT1).sum(1)
+    dJ12 = (W2[None] * dT1).sum(1)
+    tz = 1.0 / t[:, 2]
+    tz2 = tz * tz
+    tz3 = tz2 * tz
+    dtx = x_grad_mul * -h_x * tz2 * dJ02
+    dty = y_grad_mul * -h_y * tz2 * dJ12
+    dtz = -h_x * tz2 * dJ00 - h_y * tz2 * dJ11 + (2 * h_x * tx) * tz3 * dJ02 + (2 * h_y * ty) * tz3 * dJ12
+    dmean = torch.stack([m[0] * dtx + m[1] * dty + m[2] * dtz, m[4] * dtx + m[5] * dty + m[6] * dtz,
+                         m[8] * dtx + m[9] * dty + m[10] * dtz], dim=1)
+    ddepth = acc["depth"]
+    dmean = dmean + torch.stack([m[2] * ddepth, m[6] * ddepth, m[10] * ddepth], dim=1)
+    # mean2D -> mean3D (backward.cu:378-392)
+    pm = PM.reshape(-1)
+    m_hom = transform_point_4x4(means, PM)
+    m_w = 1.0 / (m_hom[:, 3] + 0.0000001)
+    mul1 = (pm[0] * means[:, 0] + pm[4] * means[:, 1] + pm[8] * means[:, 2] + pm[12]) * m_w * m_w
+    mul2 = (pm[1] * means[:, 0] + pm[5] * means[:, 1] + pm[9] * means[:, 2] + pm[13]) * m_w * m_w
+    gx, gy = acc["mean2D"][:, 0], acc["mean2D"][:, 1]
+    dmean = dmean + torch.stack([
+        (pm[0] * m_w - pm[3] * mul1) * gx + (pm[1] * m_w - pm[3] * mul2) * gy,
+        (pm[4] * m_w - pm[7] * mul1) * gx + (pm[5] * m_w - pm[7] * mul2) * gy,
+        (pm[8] * m_w - pm[11] * mul1) * gx + (pm[9] * m_w - pm[11] * mul2) * gy], dim=1)
+    out = {}
+    # SH backward (backward.cu:21-140) via the basis and its analytic derivative w.r.t. the direction
+    if colors_precomp is None:
+        shs = g["shs"].float()
+        Mc = shs.shape[1]
+        deg = g["sh_degree"]
+        dir_orig = means - campos[None]
+        d = (dir_orig / dir_orig.norm(dim=1, keepdim=True)).detach().requires_grad_(True)
+        with torch.enable_grad():
+            B = sh_basis(deg, d)
+            K = B.shape[1]
+            dRGB = acc["colors"] * (~pre["clamped"]).float()
+            val = ((B[:, :, None] * shs[:, :K, :]).sum(1) * dRGB).sum()
+            (dL_ddir,) = torch.autograd.grad(val, d)
+        dsh = torch.zeros(P, Mc, 3)
+        dsh[:, :K, :] = B.detach()[:, :, None] * dRGB[:, None, :]
+        v, dv = dir_orig, dL_ddir
+        sum2 = (v * v).sum(1)
+        inv32 = 1.0 / torch.sqrt(sum2 * sum2 * sum2)
+        dn = torch.stack([
+            ((sum2 - v[:, 0] * v[:, 0]) * dv[:, 0] - v[:, 1] * v[:, 0] * dv[:, 1] - v[:, 2] * v[:, 0] * dv[:, 2]) * inv32,
+            (-v[:, 0] * v[:, 1] * dv[:, 0] + (sum2 - v[:, 1] * v[:, 1]) * dv[:, 1] - v[:, 2] * v[:, 1] * dv[:, 2]) * inv32,
+            (-v[:, 0] * v[:, 2] * dv[:, 0] - v[:, 1] * v[:, 2] * dv[:, 1] + (sum2 - v[:, 2] * v[:, 2]) * dv[:, 2]) * inv32],
+            dim=1)
+        dmean = dmean + dn
+        out["sh"] = torch.where(vis[:, None, None], dsh, zero)
+    # cov3D -> scale / rotation (backward.cu:283-346)
+    if cov3D_precomp is None:
+        rot, s = g["rotations"].float(), scale_modifier * g["scales"].float()
+        r, x, y, z = rot[:, 0], rot[:, 1], rot[:, 2], rot[:, 3]
+        Rm = torch.stack([
+            torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y + r * z), 2 * (x * z - r * y)], dim=1),
+            torch.stack([2 * (x * y - r * z), 1 - 2 * (x * x + z * z), 2 * (y * z + r * x)], dim=1),
+            torch.stack([2 * (x * z + r * y), 2 * (y * z - r * x), 1 - 2 * (x * x + y * y)], dim=1)], dim=1)
+        Mm = torch.diag_embed(s) @ Rm                       # math form of glm S*R
+        dSig = torch.stack([torch.stack([dcov[:, 0], 0.5 * dcov[:, 1], 0.5 * dcov[:, 2]], dim=1),
+                            torch.stack([0.5 * dcov[:, 1], dcov[:, 3], 0.5 * dcov[:, 4]], dim=1),
+                            torch.stack([0.5 * dcov[:, 2], 0.5 * dcov[:, 4], dcov[:, 5]], dim=1)], dim=1)
+        # Sigma = Mm^T Mm  =>  dL/dMm = 2 Mm dSig ; Mm = diag(s) Rm => dL/ds_i = sum_j Rm[i,j] dMm[i,j]
+        dMm = 2.0 * Mm @ dSig
+        out["scales"] = torch.where(vis[:, None], (Rm * dMm).sum(2), zero)
+        dR = s[:, :, None] * dMm                            # dL/dRm (math form)
+        # derivative of Rm w.r.t. the (un-normalised) quaternion, no normalisation Jacobian (:345)
+        q = rot.detach().requires_grad_(True)
+        with torch.enable_grad():
+            r_, x_, y_, z_ = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+            Rq = torch.stack([
+                torch.stack([1 - 2 * (y_ * y_ + z_ * z_), 2 * (x_ * y_ + r_ * z_), 2 * (x_ * z_ - r_ * y_)], dim=1),
+                torch.stack([2 * (x_ * y_ - r_ * z_), 1 - 2 * (x_ * x_ + z_ * z_), 2 * (y_ * z_ + r_ * x_)], dim=1),
+                torch.stack([2 * (x_ * z_ + r_ * y_), 2 * (y_ * z_ - r_ * x_), 1 - 2 * (x_ * x_ + y_ * y_)], dim=1)], dim=1)
+            (dq,) = torch.autograd.grad((Rq * dR).sum(), q)
+        out["rotations"] = torch.where(vis[:, None], dq, zero)
+    out["means3D"] = torch.where(vis[:, None], dmean, zero)
+    out["cov3D"] = torch.where(vis[:, None], dcov, zero)
+    out["means2D"] = acc["mean2D"]
+    out["colors"] = acc["colors"]
+    out["opacity"] = acc["opacity"][:, None]
+    out["normal"] = acc["normal"]
+    out["albedo"] = acc["albedo"]
+    out["roughness"] = acc["roughness"][:, None]
+    out["metallic"] = acc["metallic"][:, None]
+    return out
+
+
+def rasterize_backward(g, cam, bg, fwd: Dict, grads: Dict, scale_modifier=1.0, colors_precomp=None,
+                       cov3D_precomp=None) -> Dict:
+    """cuda_rasterizer/rasterizer_impl.cu:676-803."""
+    acc = blend_backward(fwd["pre"], fwd["binning"], g, cam, bg, fwd, grads)
+    return gaussian_backward(fwd["pre"], g, cam, acc, scale_modifier, colors_precomp, cov3D_precomp)
+
+
+# ------------------------------------------------------------------------------------------------
+# filters (kornia semantics, SURVEY.md A.10 — unpinned)
+# ------------------------------------------------------------------------------------------------
+def _windows3x3(x, mode):
+    C, H, W = x.shape
+    if mode == "zero":
+        xp = torch.nn.functional.pad(x[None], (1, 1, 1, 1), mode="constant", value=0.0)[0]
+    else:
+        xp = torch.nn.functional.pad(x[None], (1, 1, 1, 1), mode="reflect")[0]
+    return torch.stack([xp[:, dy:dy + H, dx:dx + W] for dy in range(3) for dx in range(3)], dim=-1)  # [C,H,W,9]
+
+
+def median3x3(x):
+    """kornia.filters.median_blur(x[None],(3,3))[0]: zero pad, lower median; any non-finite in the window -> NaN
+    (the one-hot conv2d that gathers the window turns NaN*0 / inf*0 into NaN)."""
+    w = _windows3x3(x, "zero")
+    bad = ~torch.isfinite(w).all(-1)
+    med = torch.nan_to_num(w, nan=0.0, posinf=0.0, neginf=0.0).median(dim=-1).values
+    return torch.where(bad, torch.full((), float("nan")), med)
+
+
+def bilateral3x3(x, sigma_color=1.0, sigma_space=3.0):
+    """kornia.filters.bilateral_blur(x[None],(3,3),sigma_color,(sigma_space,)*2)[0] (reflect border, L1 colour)."""
+    w = _windows3x3(x, "reflect")                                 # [C,H,W,9]
+    diff = w - x[..., None]
+    dist = diff.abs().sum(0, keepdim=True) ** 2
+    ck = torch.exp(-0.5 / (sigma_color ** 2) * dist)
+    xs = torch.tensor([-1.0, 0.0, 1.0])
+    g1 = torch.exp(-xs * xs / (2.0 * sigma_space ** 2))
+    g1 = g1 / g1.sum()
+    sk = (g1[:, None] * g1[None, :]).reshape(9)
+    k = sk * ck
+    return (w * k).sum(-1) / k.sum(-1)
+
+
+# ------------------------------------------------------------------------------------------------
+# depth -> normal: cuda_rasterizer/forward.cu:914-1032, ssr.h:103-118
+# ------------------------------------------------------------------------------------------------
+def depth_to_normal(W, H, fx, fy, viewmatrix, depth):
+    d = depth.reshape(H, W).float()
+    fx, fy = float(_f(fx)), float(_f(fy))
+    cx, cy = W / 2.0, H / 2.0
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=F32), torch.arange(W, dtype=F32), indexing="ij")
+    ray = torch.stack([(xs - cx) / fx, (ys - cy) / fy, torch.ones_like(xs)], 0)
+    pos_all = ray * d[None]
+    interior = torch.zeros(H, W, dtype=torch.bool)
+    interior[1:H - 1, 1:W - 1] = True
+    depth_pos = torch.where(interior[None], pos_all, torch.zeros(()))
+    # 5x5 validity window: every pixel in it must be inside the image and have depth >= 0.01
+    okd = (d >= 0.01).float()
+    pad = torch.nn.functional.pad(okd[None, None], (2, 2, 2, 2), value=0.0)
+    win = torch.nn.functional.avg_pool2d(pad, 5, stride=1)[0, 0] > (1.0 - 1e-6)
+    valid = interior & (d >= 0.01) & win
+
+    def sh(dx, dy):  # position of neighbour (x+dx, y+dy)
+        return torch.roll(pos_all, shifts=(-dy, -dx), dims=(1, 2))
+
+    p_aa, p_bb, p_cc, p_dd = sh(0, -1), sh(1, 0), sh(0, 1), sh(-1, 0)
+    p_ab, p_bc, p_cd, p_da = sh(1, -1), sh(1, 1), sh(-1, 1), sh(-1, -1)
+    e_a, e_b, e_c, e_d = p_da - p_ab, p_ab - p_bc, p_bc - p_cd, p_cd - p_da
+    e_ac, e_bd, e_cdab, e_bcad = p_cc - p_aa, p_dd - p_bb, p_ab - p_cd, p_da - p_bc
+
+    def nrm(v):
+        return v * (1.0 / torch.sqrt((v * v).sum(0, keepdim=True)))
+
+    def cross(a, b):
+        return torch.stack([a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]], 0)
+
+    n = (nrm(cross(e_a, e_d)) + nrm(cross(e_d, e_c)) + nrm(cross(e_c, e_b)) + nrm(cross(e_b, e_a)) +
+         nrm(cross(e_ac, e_bd)) + nrm(cross(e_bcad, e_cdab))) * (1.0 / 6.0)
+    V = viewmatrix.float().reshape(-1)
+    nout = torch.stack([V[0] * n[0] + V[1] * n[1] + V[2] * n[2], V[4] * n[0] + V[5] * n[1] + V[6] * n[2],
+                        V[8] * n[0] + V[9] * n[1] + V[10] * n[2]], 0)
+    normal = torch.where(valid[None], nout, torch.zeros(()))
+    return normal, depth_pos
+
+
+def geometry_chain(W, H, fx, fy, viewmatrix, depth, derive_normal=True):
+    """diff_gaussian_rasterization/__init__.py:475-504."""
+    if derive_normal:
+        n, p = depth_to_normal(W, H, fx, fy, viewmatrix, median3x3(depth.reshape(1, H, W)))
+    else:
+        n, p = torch.zeros(3, H, W), torch.zeros(3, H, W)
+    return bilateral3x3(n, 1.0, 3.0), median3x3(p)
+
+
+# ------------------------------------------------------------------------------------------------
+# SSAO / SSR: cuda_rasterizer/forward.cu:635-909, ssr.h:13-16,120-135
+# ------------------------------------------------------------------------------------------------
+M_PIf = float(_f(3.14159265358979323846))
+
+
+def hemisphere_dirs(delta):
+    """The reference's float-accumulated loops (forward.cu:679-681): phi float += float, compare in double;
+    theta += sampleDelta*0.5 in double then stored as float."""
+    sd = float(_f(float(_f(delta)) * M_PIf))
+    phis, thetas = [], []
+    phi = 0.0
+    while phi < 2.0 * M_PIf:
+        phis.append(phi)
+        phi = float(_f(phi + sd))          # float add (exact in double, then rounded)
+    theta = 0.0
+    while theta <= 0.5 * M_PIf:
+        thetas.append(theta)
+        theta = float(_f(theta + sd * 0.5))
+    return phis, thetas
+
+
+def _normalize3(v):
+    return v * (1.0 / torch.sqrt((v * v).sum(0, keepdim=True)))
+
+
+def _gi_march(W, H, fx, fy, radius, bias, thick, delta, step, start, normal, pos, on_dir, pix_sel=None):
+    """Shared marcher. on_dir(cs, hit_mask, hx, hy) is called once per direction with cos*sin weight pieces.
+    pix_sel: optional flat pixel subset (bounded CPU-baseline sample)."""
+    HW = H * W
+    nrm_un = normal.reshape(3, HW).float()
+    posf = pos.reshape(3, HW).float()
+    zbuf = posf[2].clone()
+    if pix_sel is not None:
+        nrm_un, posq = nrm_un[:, pix_sel], posf[:, pix_sel]
+    else:
+        posq = posf
+    n = _normalize3(nrm_un)
+    up = torch.tensor([0.0, 1.0, 0.0])[:, None]
+    rndot = (up * n).sum(0, keepdim=True)
+    tangent = _normalize3(up - n * rndot)
+    bitangent = _normalize3(torch.stack([n[1] * tangent[2] - n[2] * tangent[1], n[2] * tangent[0] - n[0] * tangent[2],
+                                         n[0] * tangent[1] - n[1] * tangent[0]], 0))
+    fx, fy = float(_f(fx)), float(_f(fy))
+    cx, cy = W / 2.0, H / 2.0
+    scale = 1 + posq[2] / 100
+    phis, thetas = hemisphere_dirs(delta)
+    stepf = float(step)
+    for phi in phis:
+        for theta in thetas:
+            st, ct = float(_f(math.sin(theta))), float(_f(math.cos(theta)))
+            sp_, cp_ = float(_f(math.sin(phi))), float(_f(math.cos(phi)))
+            ts = _f([st * cp_, st * sp_, ct])
+            ts = ts * (1.0 / torch.sqrt((ts * ts).sum()))
+            sv = tangent * ts[0] + bitangent * ts[1] + n * ts[2]
+            active = torch.ones(posq.shape[1], dtype=torch.bool)
+            hit = torch.zeros(posq.shape[1], dtype=torch.bool)
+            hx = torch.zeros(posq.shape[1], dtype=torch.long)
+            hy = torch.zeros(posq.shape[1], dtype=torch.long)
+            for j in range(start, step):
+                if not bool(active.any()):
+                    break
+                sp = posq + sv * float(j) * scale[None] * scale[None] * radius / stepf
+                dirx = sp[0] / (sp[2] + 0.0000001)
+                diry = sp[1] / (sp[2] + 0.0000001)
+                # roundf = half away from zero; float->int of NaN is 0 in CUDA
+                rx = dirx * fx + cx
+                ry = diry * fy + cy
+                ix = torch.nan_to_num(torch.sign(rx) * torch.floor(rx.abs() + 0.5), nan=0.0).clamp(-2**31, 2**31 - 1).long()
+                iy = torch.nan_to_num(torch.sign(ry) * torch.floor(ry.abs() + 0.5), nan=0.0).clamp(-2**31, 2**31 - 1).long()
+                inb = (ix >= 0) & (ix <= W - 1) & (iy >= 0) & (iy <= H - 1)
+                leave = active & ~inb
+                chk = active & inb
+                sd = zbuf[(iy.clamp(0, H - 1) * W + ix.clamp(0, W - 1))]
+                h = chk & (sd <= sp[2] + bias) & (sd >= sp[2] - thick)
+                hit = hit | h
+                hx = torch.where(h, ix, hx)
+                hy = torch.where(h, iy, hy)
+                active = active & ~leave & ~h
+            on_dir(ct, st, hit, hx, hy)
+    return n, posq
+
+
+def ssao(W, H, fx, fy, radius, bias, thick, delta, step, start, normal, pos, pix_sel=None):
+    """forward.cu:635-724. Returns [1,H,W] (or the flat subset when pix_sel is given)."""
+    n_q = pos.reshape(3, -1).shape[1] if pix_sel is None else pix_sel.numel()
+    state = dict(occ=torch.zeros(n_q), nr=0.0)
+
+    def on_dir(ct, st, hit, hx, hy):
+        wgt = float(_f(ct * st))
+        state["nr"] = float(_f(state["nr"] + wgt))
+        state["occ"] = state["occ"] + torch.where(hit, torch.full((), wgt), torch.zeros(()))
+
+    _gi_march(W, H, fx, fy, radius, bias, thick, delta, step, start, normal, pos, on_dir, pix_sel)
+    if state["nr"] > 0.0:
+        out = torch.clamp(1.0 - state["occ"] / state["nr"], 0.0, 1.0)
+    else:
+        out = torch.ones(n_q)
+    return out if pix_sel is not None else out.reshape(1, H, W)
+
+
+def ssr(W, H, fx, fy, radius, bias, thick, delta, step, start, normal, pos, rgb, albedo, roughness, metallic, F0,
+        pix_sel=None):
+    """forward.cu:726-909 (+ fresnelSchlick ssr.h:13-16). Returns (color, abd) as [3,H,W]."""
+    HW = H * W
+    rgbf = rgb.reshape(3, HW).float()
+    n_q = HW if pix_sel is None else pix_sel.numel()
+    state = dict(diff=torch.zeros(3, n_q), nr=0)
+
+    def on_dir(ct, st, hit, hx, hy):
+        state["nr"] += 1
+        c = rgbf[:, hy * W + hx]
+        state["diff"] = state["diff"] + torch.where(hit[None], c * ct * st, torch.zeros(()))
+
+    n, posq = _gi_march(W, H, fx, fy, radius, bias, thick, delta, step, start, normal, pos, on_dir, pix_sel)
+    sel = (lambda t, c: t.reshape(c, HW).float() if pix_sel is None else t.reshape(c, HW).float()[:, pix_sel])
+    alb, F0f, met = sel(albedo, 3), sel(F0, 3), sel(metallic, 1)[0]
+    Vd = _normalize3(-posq)
+    cosT = torch.clamp_min(torch.nan_to_num((n * Vd).sum(0), nan=-1.0), 0.0000001)
+    # NaN normal: fmaxf(NaN, 1e-7) = 1e-7
+    base = torch.clamp((1.0 - cosT.double()).float(), 0.000001, 1.0)
+    fpow = (base.double() ** 5.0).float()
+    F = F0f + (1.0 - F0f) * fpow[None]
+    kD = (1.0 - F.double()).float()
+    kD = (kD.double() * (1.0 - met.double())[None]).float()
+    nr = state["nr"]
+    if nr > 0:
+        gd = ((M_PIf * state["diff"]).double() * (1.0 / float(nr)) * kD.double()).float()
+        color = gd * alb
+    else:
+        gd = torch.full((3, n_q), 0.0000001)
+        color = gd.clone()
+    if pix_sel is not None:
+        return color, gd
+    return color.reshape(3, H, W), gd.reshape(3, H, W)
+
+
+# ------------------------------------------------------------------------------------------------
+# split-sum shading: /root/reference/pbr/shade.py:104-237 with the nvdiffrast texture semantics restated
+# (SURVEY.md A.9 — unpinned). Differentiable torch ops, so autograd of this function is the oracle for the
+# shade backward.
+# ------------------------------------------------------------------------------------------------
+def _cube_face_uv(d):
+    x, y, z = d[..., 0], d[..., 1], d[..., 2]
+    ax, ay, az = x.abs(), y.abs(), z.abs()
+    is_z = az > torch.maximum(ax, ay)
+    is_y = (~is_z) & (ay > ax)
+    is_x = ~(is_z | is_y)
+    c = torch.where(is_z, z, torch.where(is_y, y, x))
+    face = torch.where(is_z, 4, torch.where(is_y, 2, 0)) + (c < 0).long()
+    uu = torch.where(is_x, z, x)
+    vv = torch.where(is_y, z, y)
+    m = 0.5 / c.abs()
+    m0 = torch.where((face == 0) | (face == 5), -m, m)
+    m1 = torch.where(face != 2, -m, m)
+    u = (uu * m0 + 0.5).clamp(0.0, 1.0)
+    v = (vv * m1 + 0.5).clamp(0.0, 1.0)
+    return face, u, v
+
+
+def _cube_texel_index(face, iu, iv, w):
+    """(face, iu, iv) with iu/iv possibly one step outside -> linear texel index on the adjacent face, -1 at corners."""
+    ou = (iu < 0) | (iu >= w)
+    ov = (iv < 0) | (iv >= w)
+    s = 2 * iu + 1 - w
+    t = 2 * iv + 1 - w
+    wv = torch.full_like(s, w)
+    P = torch.zeros(face.shape + (3,), dtype=torch.long)
+    for f, (a, b, c) in enumerate([(wv, -t, -s), (-wv, -t, s), (s, wv, t), (s, -wv, -t), (s, -t, wv), (-s, -t, -wv)]):
+        mk = face == f
+        P[..., 0] = torch.where(mk, a, P[..., 0]); P[..., 1] = torch.where(mk, b, P[..., 1]); P[..., 2] = torch.where(mk, c, P[..., 2])
+    major = face // 2
+    ar = torch.arange(3)
+    is_major = ar == major[..., None]
+    over = (~is_major) & (P.abs() > w)
+    any_over = over.any(-1)
+    over_axis = over.long().argmax(-1)
+    sgn_major = torch.sign(torch.gather(P, -1, major[..., None])[..., 0])
+    sgn_over = torch.sign(torch.gather(P, -1, over_axis[..., None])[..., 0])
+    P2 = P.clone()
+    P2 = torch.where(is_major, (sgn_major * (w - 1))[..., None], P2)
+    P2 = torch.where(ar == over_axis[..., None], (sgn_over * w)[..., None], P2)
+    P = torch.where(any_over[..., None], P2, P)
+    nf = torch.where(any_over, 2 * over_axis + (sgn_over < 0).long(), face)
+    s2 = torch.zeros_like(s); t2 = torch.zeros_like(t)
+    inv = [(-P[..., 2], -P[..., 1]), (P[..., 2], -P[..., 1]), (P[..., 0], P[..., 2]), (P[..., 0], -P[..., 2]),
+           (P[..., 0], -P[..., 1]), (-P[..., 0], -P[..., 1])]
+    for f, (a, b) in enumerate(inv):
+        mk = nf == f
+        s2 = torch.where(mk, a, s2); t2 = torch.where(mk, b, t2)
+    iu2 = (s2 + w - 1) // 2
+    iv2 = (t2 + w - 1) // 2
+    idx = (nf * w + iv2) * w + iu2
+    return torch.where(ou & ov, torch.full_like(idx, -1), idx)
+
+
+def tex_cube(tex, d):
+    """tex [6,w,w,C], d [...,3] -> [...,C]; linear filtering with seamless edges / 3-texel corners."""
+    w = tex.shape[1]
+    face, u, v = _cube_face_uv(d)
+    u = u * w - 0.5
+    v = v * w - 0.5
+    iu0, iv0 = torch.floor(u).long(), torch.floor(v).long()
+    fu, fv = u - iu0.float(), v - iv0.float()
+    flat = tex.reshape(-1, tex.shape[-1])
+    idxs = [_cube_texel_index(face, iu0 + a, iv0 + b, w) for b in (0, 1) for a in (0, 1)]
+    wts = [(1 - fu) * (1 - fv), fu * (1 - fv), (1 - fu) * fv, fu * fv]
+    idx = torch.stack(idxs, -1)
+    wt = torch.stack(wts, -1)
+    missing = idx < 0
+    share = (wt * missing.float()).sum(-1, keepdim=True) * 0.33333333
+    wt = torch.where(missing, torch.zeros(()), wt + torch.where(missing.any(-1, keepdim=True), share, torch.zeros(())))
+    vals = flat[idx.clamp_min(0)]
+    bad = ~torch.isfinite(d).all(-1)
+    out = (vals * wt[..., None]).sum(-2)
+    return torch.where(bad[..., None], torch.zeros(()), out)
+
+
+def tex_2d_clamp(tex, uv):
+    """tex [h,w,C], uv [...,2] (u->x, v->y), linear, clamp to edge-texel centres."""
+    h, w = tex.shape[0], tex.shape[1]
+    u = (uv[..., 0] * w - 0.5).clamp(0.0, w - 1.0)
+    v = (uv[..., 1] * h - 0.5).clamp(0.0, h - 1.0)
+    iu0, iv0 = torch.floor(u.detach()).long(), torch.floor(v.detach()).long()
+    iu1 = iu0 + ((u.detach() != 0) & (u.detach() != w - 1)).long()
+    iv1 = iv0 + ((v.detach() != 0) & (v.detach() != h - 1)).long()
+    fu, fv = u - iu0.float(), v - iv0.float()
+    a00, a10, a01, a11 = tex[iv0, iu0], tex[iv0, iu1], tex[iv1, iu0], tex[iv1, iu1]
+    b0 = a00 + fu[..., None] * (a10 - a00)
+    b1 = a01 + fu[..., None] * (a11 - a01)
+    return b0 + fv[..., None] * (b1 - b0)
+
+
+def get_mip(roughness, n_levels, rmin=0.08, rmax=0.5):
+    # /root/reference/pbr/light.py:142-152
+    return torch.where(roughness < rmax,
+                       (torch.clamp(roughness, rmin, rmax) - rmin) / (rmax - rmin) * (n_levels - 2),
+                       (torch.clamp(roughness, rmax, 1.0) - rmax) / (1.0 - rmax) + n_levels - 2)
+
+
+def linear_to_srgb(x):
+    eps = torch.finfo(torch.float32).eps
+    s0 = 323 / 25 * x
+    s1 = (211 * torch.clamp(x, min=eps) ** (5 / 12) - 11) / 200
+    return torch.where(x <= 0.0031308, s0, s1)
+
+
+def aces_film(x):
+    a, b, c, d, e = 2.51, 0.03, 2.43, 0.59, 0.14
+    return ((x * (a * x + b)) / (x * (c * x + d) + e)).clamp(0.0, 1.0)
+
+
+def pbr_shading(light: Dict, normals, view_dirs, albedo, roughness, mask, tone=False, gamma=False, occlusion=None,
+                metallic=None, brdf_lut=None, background=None) -> Dict:
+    """HWC tensors like the reference (normals/view_dirs/albedo [H,W,3], roughness/mask/occlusion/metallic [H,W,1])."""
+    H, W, _ = normals.shape
+    if background is None:
+        background = torch.zeros_like(normals)
+    ref = 2.0 * (normals * view_dirs).sum(-1, keepdim=True).clamp(min=0.0) * normals - view_dirs
+    Tm = torch.tensor([[0.0, -1.0, 0.0], [0.0, 0.0, 1.0], [-1.0, 0.0, 0.0]])
+    diffuse_light = tex_cube(light["diffuse"], normals @ Tm.T)
+    if occlusion is not None:
+        diffuse_light = diffuse_light * occlusion
+    diffuse_rgb = diffuse_light * albedo
+    NoV = ((normals @ Tm.T) * (view_dirs @ Tm.T)).sum(-1, keepdim=True).clamp(1e-4, 1.0)
+    fg = tex_2d_clamp(brdf_lut.reshape(brdf_lut.shape[-3], brdf_lut.shape[-2], 2), torch.cat([NoV, roughness], -1))
+    spec_levels = light["specular"]
+    nl = len(spec_levels)
+    lvl = get_mip(roughness[..., 0], nl).clamp(0.0, nl - 1.0)
+    l0 = torch.floor(lvl.detach()).long()
+    l1 = torch.clamp(l0 + 1, max=nl - 1)
+    fl = lvl - l0.float()
+    rT = ref @ Tm.T
+    per_level = torch.stack([tex_cube(s, rT) for s in spec_levels], 0)  # [L,H,W,3]
+    s0 = torch.gather(per_level, 0, l0[None, ..., None].expand(1, H, W, 3))[0]
+    s1 = torch.gather(per_level, 0, l1[None, ..., None].expand(1, H, W, 3))[0]
+    spec = s0 + fl[..., None] * (s1 - s0)
+    if metallic is None:
+        F0 = torch.ones_like(albedo) * 0.04
+    else:
+        F0 = (1.0 - metallic) * 0.04 + albedo * metallic
+    reflectance = F0 * fg[..., 0:1] + fg[..., 1:2]
+    specular_rgb = spec * reflectance
+    render_rgb = diffuse_rgb + specular_rgb
+    render_rgb = aces_film(render_rgb) if tone else render_rgb.clamp(0.0, 1.0)
+    if gamma:
+        render_rgb = linear_to_srgb(render_rgb)
+        diffuse_rgb = linear_to_srgb(diffuse_rgb)
+        specular_rgb = linear_to_srgb(specular_rgb)
+    render_rgb = torch.where(mask, render_rgb, background)
+    return dict(render_rgb=render_rgb, diffuse_rgb=diffuse_rgb, specular_rgb=specular_rgb, diffuse_light=diffuse_light)
+
+
+# ------------------------------------------------------------------------------------------------
+# distCUDA2: /root/reference/submodules/simple-knn/simple_knn.cu:106-163 — exact brute force restatement
+# ------------------------------------------------------------------------------------------------
+def dist2(points, chunk=2048):
+    pts = points.float()
+    P = pts.shape[0]
+    out = torch.empty(P)
+    for s in range(0, P, chunk):
+        q = pts[s:s + chunk]
+        d = q[:, None, :] - pts[None, :, :]                      # point - ref sign is irrelevant for squares
+        d2 = d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1] + d[..., 2] * d[..., 2]
+        d2[torch.arange(q.shape[0]), torch.arange(s, s + q.shape[0])] = float("inf")  # exclude self by index
+        b = torch.topk(d2, k=min(3, P - 1), dim=1, largest=False).values if P > 1 else torch.full((q.shape[0], 0), 0.0)
+        if b.shape[1] < 3:
+            b = torch.cat([b, torch.full((q.shape[0], 3 - b.shape[1]), 3.4028234663852886e38)], 1)
+        out[s:s + chunk] = (b[:, 0] + b[:, 1] + b[:, 2]) / 3.0
+    return out
