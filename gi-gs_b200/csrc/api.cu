@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstring>
 #include <string>
+#include <vector>
 #include "common.cuh"
 
 namespace gigs {
@@ -24,6 +25,26 @@ int cuda_fail(cudaError_t e, const char* what)
 {
     set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
     return (int)e;
+}
+
+// ---- optional per-stage event timing -------------------------------------------------------------
+struct ProfRec { int stage; cudaEvent_t e0, e1; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+int prof_begin(int stage, cudaStream_t st)
+{
+    if (!g_prof_on) return -1;
+    ProfRec r;
+    r.stage = stage;
+    if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return -1;
+    cudaEventRecord(r.e0, st);
+    g_prof.push_back(r);
+    return (int)g_prof.size() - 1;
+}
+void prof_end(int token, cudaStream_t st)
+{
+    if (token < 0 || token >= (int)g_prof.size()) return;
+    cudaEventRecord(g_prof[token].e1, st);
 }
 
 // reference rasterizer_impl.cu:35-50 (number of key bits needed for the tile id)
@@ -154,7 +175,11 @@ static int forward_finish_impl(GigsRasterFwd* a, bool lite)
     uint64_t* keys_u = (uint64_t*)(sc + L.off.s_keys_unsorted);
     uint32_t* vals_u = (uint32_t*)(sc + L.off.s_vals_unsorted);
     if (a->P > 0 && R > 0) {
-        if (int e = launch_emit_keys(a, L, keys_u, vals_u, st)) return e;
+        {
+            ProfScope ps(ST_EMIT_KEYS, st);
+            if (int e = launch_emit_keys(a, L, keys_u, vals_u, st)) return e;
+        }
+        ProfScope ps(ST_SORT, st);
         const uint64_t status_total = (L.s_status - L.s_hist) + (uint64_t)L.sort_passes * L.sort_tiles * 256 * 4;
         if (int e = launch_radix_sort(R, (int)L.sort_bits, keys_u, vals_u, (uint64_t*)(sc + L.s_keys_a),
                                       (uint32_t*)(bn + L.off.b_point_list), (uint64_t*)(sc + L.s_keys_b),
@@ -162,9 +187,15 @@ static int forward_finish_impl(GigsRasterFwd* a, bool lite)
                                       (uint32_t*)(sc + L.s_status), (uint32_t*)(sc + L.s_ticket), status_total, st))
             return e;
     }
-    if (int e = launch_tile_ranges(R, (const uint64_t*)(sc + L.s_keys_a), (uint2*)(im + L.off.i_ranges), L.num_tiles, st))
-        return e;
-    if (int e = launch_blend_forward(a, L, lite, st)) return e;
+    {
+        ProfScope ps(ST_RANGES, st);
+        if (int e = launch_tile_ranges(R, (const uint64_t*)(sc + L.s_keys_a), (uint2*)(im + L.off.i_ranges), L.num_tiles, st))
+            return e;
+    }
+    {
+        ProfScope ps(ST_BLEND_FWD, st);
+        if (int e = launch_blend_forward(a, L, lite, st)) return e;
+    }
     if (a->cam.debug) GIGS_CUDA(cudaStreamSynchronize(st));
     return 0;
 }
@@ -177,6 +208,31 @@ extern "C" {
 
 int gigs_abi_version(void) { return GIGS_ABI_VERSION; }
 const char* gigs_last_error(void) { return g_last_error.c_str(); }
+
+int gigs_profile_enable(int32_t on)
+{
+    g_prof_on = on != 0;
+    return 0;
+}
+
+int gigs_profile_read(int32_t* stages, float* ms, int32_t cap)
+{
+    int n = 0;
+    for (auto& r : g_prof) {
+        float t = 0.f;
+        if (cudaEventSynchronize(r.e1) == cudaSuccess && cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) {
+            if (n < cap && stages && ms) {
+                stages[n] = r.stage;
+                ms[n] = t;
+                ++n;
+            }
+        }
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    g_prof.clear();
+    return n;
+}
 
 int gigs_raster_sizes(int32_t P, int32_t W, int32_t H, uint64_t R, GigsSizes* out)
 {
@@ -213,7 +269,10 @@ int gigs_raster_forward_begin(GigsRasterFwd* a)
         set_error("geom/img workspace too small");
         return -2;
     }
-    if (int e = launch_preprocess(a, L, st)) return e;
+    {
+        ProfScope ps(ST_PREPROCESS, st);
+        if (int e = launch_preprocess(a, L, st)) return e;
+    }
     uint32_t hostR = 0;
     uint32_t* dst = a->pinned_num_rendered ? a->pinned_num_rendered : &hostR;
     GIGS_CUDA(cudaMemcpyAsync(dst, (char*)a->geom + L.off.g_num_rendered, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -242,11 +301,17 @@ int gigs_raster_backward(GigsRasterBwd* a)
     }
     cudaStream_t st = (cudaStream_t)a->stream;
     const Layout L = make_layout(a->P, a->cam.width, a->cam.height, (uint64_t)a->num_rendered);
-    GIGS_CUDA(cudaMemsetAsync(a->accum, 0, (size_t)a->P * ACC_FLOATS * sizeof(float), st));
-    if (a->num_rendered > 0) {
-        if (int e = launch_blend_backward(a, L, st)) return e;
+    {
+        ProfScope ps(ST_BLEND_BWD, st);
+        GIGS_CUDA(cudaMemsetAsync(a->accum, 0, (size_t)a->P * ACC_FLOATS * sizeof(float), st));
+        if (a->num_rendered > 0) {
+            if (int e = launch_blend_backward(a, L, st)) return e;
+        }
     }
-    if (int e = launch_gaussian_backward(a, L, st)) return e;
+    {
+        ProfScope ps(ST_GAUSS_BWD, st);
+        if (int e = launch_gaussian_backward(a, L, st)) return e;
+    }
     if (a->cam.debug) GIGS_CUDA(cudaStreamSynchronize(st));
     return 0;
 }

@@ -49,6 +49,20 @@ int cuda_fail(cudaError_t e, const char* what);
         if (_e != cudaSuccess) return gigs::cuda_fail(_e, name); \
     } while (0)
 
+// optional per-stage event timing (api.cu)
+enum Stage : int {
+    ST_PREPROCESS = 0, ST_EMIT_KEYS, ST_SORT, ST_RANGES, ST_BLEND_FWD, ST_BLEND_BWD, ST_GAUSS_BWD, ST_GEOM_CHAIN,
+    ST_SSAO, ST_SSR, ST_SHADE_FWD, ST_SHADE_BWD, ST_MEDIAN, ST_MEDIAN_BWD, ST_BILATERAL, ST_D2N, ST_SSR_BWD, ST_DIST2
+};
+int prof_begin(int stage, cudaStream_t st);   // returns a token (<0 when profiling is off)
+void prof_end(int token, cudaStream_t st);
+struct ProfScope {
+    int tok;
+    cudaStream_t st;
+    ProfScope(int stage, cudaStream_t s) : tok(prof_begin(stage, s)), st(s) {}
+    ~ProfScope() { prof_end(tok, st); }
+};
+
 __host__ __device__ inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
 // ---------------------------------------------------------------------------------------------

@@ -251,6 +251,7 @@ extern "C" int gigs_dist2(int32_t P, const float* points, float* mean_dist2, voi
     cudaStream_t st = (cudaStream_t)stream;
     char* s = (char*)scratch;
     uint32_t* bounds = (uint32_t*)(s + o_bounds);
+    ProfScope ps(ST_DIST2, st);
     knn_init_bounds<<<1, 32, 0, st>>>(bounds);
     knn_bounds_kernel<<<min((P + 255) / 256, 148 * 8), 256, 0, st>>>(P, points, bounds);
     GIGS_LAUNCH_CHECK("knn_bounds_kernel");

@@ -574,6 +574,7 @@ int gigs_depth_to_normal(int32_t W, int32_t H, float fx, float fy, const float* 
 {
     if (W <= 0 || H <= 0 || !viewmatrix || !depth || !normal_map || !depth_pos) { set_error("gigs_depth_to_normal: bad arguments"); return -1; }
     dim3 grid((W + 31) / 32, (H + 7) / 8), block(32, 8);
+    ProfScope ps(ST_D2N, (cudaStream_t)stream);
     depth_to_normal_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(W, H, fx, fy, viewmatrix, depth, normal_map, depth_pos);
     GIGS_LAUNCH_CHECK("depth_to_normal_kernel");
     return 0;
@@ -583,6 +584,7 @@ int gigs_median3x3(int32_t Cn, int32_t W, int32_t H, const float* in, float* out
 {
     if (Cn <= 0 || W <= 0 || H <= 0 || !in || !out) { set_error("gigs_median3x3: bad arguments"); return -1; }
     dim3 grid((W + 31) / 32, (H + 7) / 8), block(32, 8);
+    ProfScope ps(ST_MEDIAN, (cudaStream_t)stream);
     median3x3_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(Cn, W, H, in, out);
     GIGS_LAUNCH_CHECK("median3x3_kernel");
     return 0;
@@ -592,6 +594,7 @@ int gigs_median3x3_backward(int32_t Cn, int32_t W, int32_t H, const float* in, c
                             void* stream)
 {
     if (Cn <= 0 || W <= 0 || H <= 0 || !in || !grad_out || !grad_in) { set_error("gigs_median3x3_backward: bad arguments"); return -1; }
+    ProfScope ps(ST_MEDIAN_BWD, (cudaStream_t)stream);
     GIGS_CUDA(cudaMemsetAsync(grad_in, 0, (size_t)Cn * W * H * sizeof(float), (cudaStream_t)stream));
     dim3 grid((W + 31) / 32, (H + 7) / 8), block(32, 8);
     median3x3_backward_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(Cn, W, H, in, grad_out, grad_in);
@@ -604,6 +607,7 @@ int gigs_bilateral3x3(int32_t Cn, int32_t W, int32_t H, float sigma_color, float
 {
     if (Cn <= 0 || Cn > 4 || W <= 1 || H <= 1 || !in || !out) { set_error("gigs_bilateral3x3: bad arguments"); return -1; }
     dim3 grid((W + 31) / 32, (H + 7) / 8), block(32, 8);
+    ProfScope ps(ST_BILATERAL, (cudaStream_t)stream);
     bilateral3x3_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(Cn, W, H, -0.5f / (sigma_color * sigma_color),
                                                                   make_space_kernel(sigma_space), in, out);
     GIGS_LAUNCH_CHECK("bilateral3x3_kernel");
@@ -623,6 +627,7 @@ int gigs_geometry_chain(int32_t W, int32_t H, float fx, float fy, const float* v
     }
     if (!viewmatrix || !depth) { set_error("gigs_geometry_chain: bad arguments"); return -1; }
     dim3 grid((W + GC_TW - 1) / GC_TW, (H + GC_TH - 1) / GC_TH), block(32, 8);
+    ProfScope ps(ST_GEOM_CHAIN, st);
     geometry_chain_kernel<<<grid, block, 0, st>>>(W, H, fx, fy, viewmatrix, -0.5f / (1.f * 1.f), make_space_kernel(3.f),
                                                   depth, normal_from_depth, depth_pos_filter);
     GIGS_LAUNCH_CHECK("geometry_chain_kernel");
@@ -641,6 +646,7 @@ static int gi_launch(bool is_ssr, int W, int H, float fx, float fy, float radius
     }
     const size_t smem = (size_t)dc.n_phi * dc.n_theta * sizeof(DirEntry) + (dc.n_phi + dc.n_theta) * sizeof(float) + 16;
     dim3 grid((W + TILE_X - 1) / TILE_X, (H + TILE_Y - 1) / TILE_Y), block(TILE_X, TILE_Y);
+    ProfScope ps(is_ssr ? ST_SSR : ST_SSAO, st);
     if (is_ssr) {
         static bool attr = false;
         if (!attr) { GIGS_CUDA(cudaFuncSetAttribute(gi_march_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr = true; }
@@ -679,6 +685,7 @@ int gigs_ssr_backward(int32_t W, int32_t H, const float* grad_color, const float
 {
     if (W <= 0 || H <= 0 || !grad_color || !abd || !grad_albedo) { set_error("gigs_ssr_backward: bad arguments"); return -1; }
     const size_t n1 = (size_t)W * H, n3 = 3 * n1;
+    ProfScope ps(ST_SSR_BWD, (cudaStream_t)stream);
     ssr_backward_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n3, n1, grad_color, abd, grad_albedo,
                                                                                       grad_roughness, grad_metallic);
     GIGS_LAUNCH_CHECK("ssr_backward_kernel");

@@ -482,6 +482,7 @@ int gigs_shade_forward(GigsShade* a)
     if (int e = fill_params(a, p, false)) return e;
     if (!p.render_rgb) { set_error("shade_forward: render_rgb is NULL"); return -1; }
     const size_t HW = (size_t)p.W * p.H;
+    ProfScope ps(ST_SHADE_FWD, (cudaStream_t)a->stream);
     shade_forward_kernel<<<(unsigned)((HW + 255) / 256), 256, 0, (cudaStream_t)a->stream>>>(p);
     GIGS_LAUNCH_CHECK("shade_forward_kernel");
     return 0;
@@ -496,6 +497,7 @@ int gigs_shade_backward(GigsShade* a)
     const size_t HW = (size_t)p.W * p.H;
     unsigned blocks = (unsigned)((HW + 255) / 256);
     if (blocks > 148u * 4u) blocks = 148u * 4u;
+    ProfScope ps(ST_SHADE_BWD, (cudaStream_t)a->stream);
     shade_backward_kernel<<<blocks, 256, SHB_MAX_DIFFUSE * sizeof(float), (cudaStream_t)a->stream>>>(p);
     GIGS_LAUNCH_CHECK("shade_backward_kernel");
     return 0;

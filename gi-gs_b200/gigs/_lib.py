@@ -125,6 +125,8 @@ SYMBOLS = {
     "gigs_shade_backward": (C.c_int, [C.POINTER(GigsShade)]),
     "gigs_dist2": (C.c_int, [_i32, _vp, _vp, _vp, C.POINTER(C.c_uint64), _vp]),
     "gigs_ffma_peak": (C.c_int, [C.POINTER(C.c_double), _vp]),
+    "gigs_profile_enable": (C.c_int, [_i32]),
+    "gigs_profile_read": (C.c_int, [C.POINTER(C.c_int32), C.POINTER(C.c_float), _i32]),
 }
 
 _lib = None

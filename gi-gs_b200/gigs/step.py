@@ -1,0 +1,92 @@
+"""The PBR-stage training step on one view (the unit BASELINE.json's metric counts: one "frame" =
+G-buffer forward + SSAO + split-sum shading + SSR + loss + full backward), and its view-sharded multi-GPU
+form. Mirrors /root/reference/train.py:240-422 for the parts on the hot path; the optimiser, densification,
+TV losses and build_mips are outside it.
+"""
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import scene as _scene
+from .renderer import pbr_forward, pbr_loss
+from .shade import Light
+
+PARAM_KEYS = ("xyz", "f_dc", "f_rest", "opacity", "normal", "albedo", "roughness", "metallic", "log_scale", "rot")
+PARAM_WIDTH = {"xyz": 3, "f_dc": 3, "f_rest": 45, "opacity": 1, "normal": 3, "albedo": 3, "roughness": 1,
+               "metallic": 1, "log_scale": 3, "rot": 4}  # 67 floats = 268 B per Gaussian
+
+
+class GaussianParams:
+    """Raw (pre-activation) parameters as leaf tensors whose .grad tensors are VIEWS into one flat buffer,
+    so the per-Gaussian gradient all-reduce of the view-sharded step is a single collective with no packing
+    copy (autograd accumulates into an existing .grad in place)."""
+
+    def __init__(self, raw: Dict, device, light: Optional[Dict] = None):
+        P = raw["xyz"].shape[0]
+        self.P = P
+        self.sh_degree = raw["sh_degree"]
+        self.leaves: Dict[str, torch.Tensor] = {}
+        for k in PARAM_KEYS:
+            self.leaves[k] = raw[k].to(device).float().contiguous().requires_grad_(True)
+        self.light_leaves: List[torch.Tensor] = []
+        if light is not None:
+            self.light_leaves = [t.to(device).float().contiguous().requires_grad_(True)
+                                 for t in (light["diffuse"], *light["specular"])]
+        n = sum(t.numel() for t in self.leaves.values()) + sum(t.numel() for t in self.light_leaves)
+        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=device)
+        o = 0
+        for t in list(self.leaves.values()) + self.light_leaves:
+            t.grad = self.flat_grad[o:o + t.numel()].view_as(t)
+            o += t.numel()
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+
+    def activated(self) -> Dict:
+        """scene/gaussian_model.py:178-266 getters, autograd-tracked."""
+        L = self.leaves
+        return dict(means3D=L["xyz"], opacity=torch.sigmoid(L["opacity"]), normal=F.normalize(L["normal"], dim=-1),
+                    albedo=torch.sigmoid(L["albedo"]), roughness=torch.sigmoid(L["roughness"]),
+                    metallic=torch.sigmoid(L["metallic"]), scales=torch.exp(L["log_scale"]),
+                    rotations=F.normalize(L["rot"], dim=-1), shs=torch.cat((L["f_dc"], L["f_rest"]), dim=1),
+                    sh_degree=self.sh_degree)
+
+    def light(self) -> Optional[Light]:
+        if not self.light_leaves:
+            return None
+        return Light(specular=list(self.light_leaves[1:]), diffuse=self.light_leaves[0])
+
+
+def training_step(params: GaussianParams, cam, light: Light, brdf_lut, rays, gt_image, background, gi: Dict,
+                  metallic=True, gamma=True, tone=False, indirect=True, loss_scale: float = 1.0) -> torch.Tensor:
+    """forward + loss + backward for ONE view; gradients accumulate into params.flat_grad."""
+    g = params.activated()
+    res = pbr_forward(cam, g, light, brdf_lut, rays, background, indirect=indirect, metallic=metallic, tone=tone,
+                      gamma=gamma, gi=gi)
+    loss = pbr_loss(res, gt_image) * loss_scale
+    loss.backward()
+    return loss.detach()
+
+
+def multi_view_step(params: GaussianParams, cams: List, light: Light, brdf_lut, rays_of, gts: List, background,
+                    gi: Dict, rank: int = 0, world: int = 1, **kw) -> torch.Tensor:
+    """K-view step, views sharded round-robin over `world` ranks (BASELINE C4): loss = mean over
+    the K views; each rank back-propagates its own views, then ONE all-reduce(sum) of the flat gradient buffer
+    (268 B per Gaussian + the light texels). With world == 1 this is plain gradient accumulation."""
+    K = len(cams)
+    params.zero_grad()
+    total = torch.zeros((), device=params.flat_grad.device)
+    for k in range(rank, K, world):
+        total = total + training_step(params, cams[k], light, brdf_lut, rays_of(cams[k]), gts[k], background, gi,
+                                      loss_scale=1.0 / K, **kw)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(params.flat_grad, op=dist.ReduceOp.SUM)
+        dist.all_reduce(total, op=dist.ReduceOp.SUM)
+    return total
+
+
+def shard_views(n_views: int, rank: int, world: int) -> List[int]:
+    """Camera-sharded eval / relight sweep (BASELINE C5): independent views, round-robin, no data-path collective."""
+    return list(range(rank, n_views, world))

@@ -242,6 +242,15 @@ int gigs_shade_backward(GigsShade* a);
 int gigs_dist2(int32_t P, const float* points, float* mean_dist2, void* scratch,
                uint64_t* scratch_bytes, void* stream);
 
+/* Per-stage device timing (CUDA events on the launching stream), for bench.py's roofline numbers.
+ * Stage ids: 0 preprocess+scan, 1 emit_keys, 2 radix_sort, 3 tile_ranges, 4 blend_forward, 5 blend_backward,
+ * 6 gaussian_backward, 7 geometry_chain, 8 ssao, 9 ssr, 10 shade_forward, 11 shade_backward, 12 median3x3,
+ * 13 median3x3_backward, 14 bilateral3x3, 15 depth_to_normal, 16 ssr_backward, 17 dist2.
+ * gigs_profile_read synchronises the recorded events, writes up to cap (stage, ms) pairs, clears the log and
+ * returns the number written (negative on error). Off by default; costs two event records per stage when on. */
+int gigs_profile_enable(int32_t on);
+int gigs_profile_read(int32_t* stages, float* ms, int32_t cap);
+
 /* Measured-roofline helper: register-only FFMA throughput (flop/s) over all SMs. */
 int gigs_ffma_peak(double* tflops, void* stream);
 

@@ -543,7 +543,10 @@ def gaussian_backward(pre: Dict, g: Dict, cam, acc: Dict, scale_modifier=1.0, co
             K = B.shape[1]
             dRGB = acc["colors"] * (~pre["clamped"]).float()
             val = ((B[:, :, None] * shs[:, :K, :]).sum(1) * dRGB).sum()
-            (dL_ddir,) = torch.autograd.grad(val, d)
+            if val.requires_grad:
+                (dL_ddir,) = torch.autograd.grad(val, d)
+            else:  # degree 0: the colour does not depend on the view direction
+                dL_ddir = torch.zeros_like(d)
         dsh = torch.zeros(P, Mc, 3)
         dsh[:, :K, :] = B.detach()[:, :, None] * dRGB[:, None, :]
         v, dv = dir_orig, dL_ddir
