@@ -1,0 +1,65 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/gigs_b200.h declares."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "gigs_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gigs_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_the_expected_entry_points():
+    syms = declared_symbols()
+    for must in ("gigs_raster_forward_begin", "gigs_raster_forward_finish", "gigs_raster_backward", "gigs_ssao",
+                 "gigs_ssr", "gigs_shade_forward", "gigs_shade_backward", "gigs_dist2", "gigs_geometry_chain",
+                 "gigs_mark_visible", "gigs_depth_to_normal", "gigs_lite_forward_finish", "gigs_ssr_backward"):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol():
+    from gigs import _lib
+    assert os.path.exists(_lib.LIB_PATH), "build first: python -c 'import __graft_entry__ as g; g.build()'"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for s in declared_symbols():
+        assert hasattr(lib, s), f"{s} declared in include/gigs_b200.h but not exported by libgigs_b200.so"
+
+
+def test_python_binding_covers_every_declared_symbol():
+    from gigs import _lib
+    assert sorted(_lib.SYMBOLS) == declared_symbols()
+    lib = _lib.load()
+    assert lib.gigs_abi_version() == 1
+
+
+def test_workspace_sizes_are_a_pure_function_of_shape():
+    from gigs import _lib
+    L = _lib.load()
+    a, b = _lib.GigsSizes(), _lib.GigsSizes()
+    assert L.gigs_raster_sizes(1000, 800, 800, 12345, ctypes.byref(a)) == 0
+    assert L.gigs_raster_sizes(1000, 800, 800, 12345, ctypes.byref(b)) == 0
+    assert (a.geom_bytes, a.img_bytes, a.binning_bytes, a.sort_bytes) == (b.geom_bytes, b.img_bytes, b.binning_bytes,
+                                                                          b.sort_bytes)
+    assert a.geom_bytes % 128 == 0 and a.img_bytes % 128 == 0 and a.binning_bytes >= 4 * 12345
+    lay = _lib.GigsLayout()
+    assert L.gigs_raster_layout(1000, 800, 800, 12345, ctypes.byref(lay)) == 0
+    for f, _ in lay._fields_:
+        assert getattr(lay, f) % 128 == 0, f
+    # bad arguments -> negative status + message, never a crash
+    assert L.gigs_raster_sizes(-1, 800, 800, 0, ctypes.byref(a)) < 0
+    assert b"bad arguments" in L.gigs_last_error()
+
+
+def test_missing_library_is_a_loud_import_error(tmp_path, monkeypatch):
+    from gigs import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    try:
+        _lib.load()
+    except ImportError as e:
+        assert "no CPU or PyTorch fallback" in str(e)
+    else:
+        raise AssertionError("expected ImportError")
