@@ -73,9 +73,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -85,7 +85,12 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for ts, r in self.rows if t0 is None or (t0 <= ts <= t1 + 0.15)]
+        window = "timed region"
+        if not rows:  # timed region shorter than one sampling period: fall back to everything seen under load
+            rows = [r for ts, r in self.rows]
+            window = "warm-up + timed region (timed region shorter than the 100 ms sampling period)"
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -97,7 +102,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nme)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def measured_peaks():
@@ -216,11 +221,12 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def timed(gi, steps, warmup, e2e=False, sampler=None):
+        if sampler:
+            sampler.start()
         for i in range(warmup):
             one_step(i, gi, e2e)
         barrier()
-        if sampler:
-            sampler.start()
+        t_wall0 = time.time()
         tot_ms = 0.0
         for i in range(steps):
             flush_buf.fill_(float(i))          # L2 flush, outside the timed span
@@ -238,7 +244,7 @@ def run_ours(args):
                 torch.cuda.synchronize()
                 tot_ms += e0.elapsed_time(e1)
         barrier()
-        clocks = sampler.stop() if sampler else None
+        clocks = sampler.stop(t_wall0, time.time()) if sampler else None
         t = torch.tensor([tot_ms], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -118,9 +118,9 @@ def test_full_pbr_frame_runs_and_matches_composed_oracle_pieces():
     g = params.activated()
     res = renderer.pbr_forward(cam, g, params.light(), lut, rays, torch.zeros(3, device=DEV), gi=gi)
     fx, fy = W / (2 * cam.tanfovx), H / (2 * cam.tanfovy)
-    occ_o = O.ssao(W, H, fx, fy, 0.8, 0.01, 0.05, 0.0625, 16, 8, res["out_normal_view"].detach().cpu() * 0 +
-                   U.ours_forward({k: (v.detach() if torch.is_tensor(v) else v) for k, v in g.items()}, cam,
-                                  torch.zeros(3, device=DEV))["normal_view"].cpu(), res["depth_pos"].cpu())
+    raw_nv = U.ours_forward({k: (v.detach() if torch.is_tensor(v) else v) for k, v in g.items()}, cam,
+                            torch.zeros(3, device=DEV))["normal_view"]          # SSAO consumes the RAW view normals
+    occ_o = O.ssao(W, H, fx, fy, 0.8, 0.01, 0.05, 0.0625, 16, 8, raw_nv.cpu(), res["depth_pos"].cpu())
     assert (res["occlusion_map"].cpu() - occ_o).abs().max() < 1e-4
     assert torch.isfinite(res["render_rgb"]).all()
     gt = torch.rand(3, H, W, device=DEV)
