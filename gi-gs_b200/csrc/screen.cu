@@ -417,7 +417,7 @@ __device__ __forceinline__ Tbn make_tbn(const float3 normal)
 
 constexpr int GI_MAX_DIRS = 2048;
 
-template <bool IS_SSR>
+template <bool IS_SSR, bool POW2_STEP>
 __global__ void __launch_bounds__(256)
 gi_march_kernel(const int W, const int H, const float focal_x, const float focal_y, const float radius,
                 const float bias, const float thick, const float delta, const int step, const int start,
@@ -447,6 +447,7 @@ gi_march_kernel(const int W, const int H, const float focal_x, const float focal
     const float cx = float(W) / 2.0f, cy = float(H) / 2.0f;
     const float scale = (1 + pos.z / 100);
     const float stepf = (float)step;
+    const float inv_stepf = 1.0f / stepf;
     const int ndir = n_phi * n_theta;
 
     float occ = 0.0f;
@@ -464,9 +465,17 @@ gi_march_kernel(const int W, const int H, const float focal_x, const float focal
             nrSamples = __fmaf_rn(de.c, de.s, nrSamples);  // the reference's SASS contracts both accumulations
         for (int j = start; j < step; ++j) {
             float3 sp;
-            sp.x = pos.x + sv.x * j * scale * scale * radius / stepf;
-            sp.y = pos.y + sv.y * j * scale * scale * radius / stepf;
-            sp.z = pos.z + sv.z * j * scale * scale * radius / stepf;
+            if (POW2_STEP) {
+                // step is a power of two: x / step == x * (1/step) bit-for-bit (both are the correctly rounded
+                // quotient), which removes three IEEE divisions per probe
+                sp.x = pos.x + sv.x * j * scale * scale * radius * inv_stepf;
+                sp.y = pos.y + sv.y * j * scale * scale * radius * inv_stepf;
+                sp.z = pos.z + sv.z * j * scale * scale * radius * inv_stepf;
+            } else {
+                sp.x = pos.x + sv.x * j * scale * scale * radius / stepf;
+                sp.y = pos.y + sv.y * j * scale * scale * radius / stepf;
+                sp.z = pos.z + sv.z * j * scale * scale * radius / stepf;
+            }
             const int2 id = project_coord(cx, cy, focal_x, focal_y, sp);
             if (id.x < 0) break;
             else if (id.x > W - 1) break;
@@ -647,17 +656,24 @@ static int gi_launch(bool is_ssr, int W, int H, float fx, float fy, float radius
     const size_t smem = (size_t)dc.n_phi * dc.n_theta * sizeof(DirEntry) + (dc.n_phi + dc.n_theta) * sizeof(float) + 16;
     dim3 grid((W + TILE_X - 1) / TILE_X, (H + TILE_Y - 1) / TILE_Y), block(TILE_X, TILE_Y);
     ProfScope ps(is_ssr ? ST_SSR : ST_SSAO, st);
-    if (is_ssr) {
-        static bool attr = false;
-        if (!attr) { GIGS_CUDA(cudaFuncSetAttribute(gi_march_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr = true; }
-        gi_march_kernel<true><<<grid, block, smem, st>>>(W, H, fx, fy, radius, bias, thick, delta, step, start, dc.n_phi,
-                                                         dc.n_theta, normal, pos, rgb, albedo, metallic, F0, out0, out1);
-    } else {
-        static bool attr = false;
-        if (!attr) { GIGS_CUDA(cudaFuncSetAttribute(gi_march_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr = true; }
-        gi_march_kernel<false><<<grid, block, smem, st>>>(W, H, fx, fy, radius, bias, thick, delta, step, start, dc.n_phi,
-                                                          dc.n_theta, normal, pos, nullptr, nullptr, nullptr, nullptr, out0, nullptr);
+    const bool pow2 = step > 0 && (step & (step - 1)) == 0;
+    static bool attr = false;
+    if (!attr) {
+        GIGS_CUDA(cudaFuncSetAttribute(gi_march_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        GIGS_CUDA(cudaFuncSetAttribute(gi_march_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        GIGS_CUDA(cudaFuncSetAttribute(gi_march_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        GIGS_CUDA(cudaFuncSetAttribute(gi_march_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr = true;
     }
+#define GI_ARGS W, H, fx, fy, radius, bias, thick, delta, step, start, dc.n_phi, dc.n_theta, normal, pos, rgb, albedo, metallic, F0, out0, out1
+    if (is_ssr) {
+        if (pow2) gi_march_kernel<true, true><<<grid, block, smem, st>>>(GI_ARGS);
+        else gi_march_kernel<true, false><<<grid, block, smem, st>>>(GI_ARGS);
+    } else {
+        if (pow2) gi_march_kernel<false, true><<<grid, block, smem, st>>>(GI_ARGS);
+        else gi_march_kernel<false, false><<<grid, block, smem, st>>>(GI_ARGS);
+    }
+#undef GI_ARGS
     GIGS_LAUNCH_CHECK("gi_march_kernel");
     return 0;
 }
