@@ -1,0 +1,288 @@
+// Device core of the split-sum shading: texture sampling (cube / LUT), mip selection, tone curves and the per-pixel
+// evaluation shared by shade.cu (reference-shaped pbr_shading op) and deferred.cu (fused deferred frame pass).
+#pragma once
+#include "common.cuh"
+
+namespace gigs {
+
+struct CubeTaps {
+    int idx[4];   // linear texel index into [6,res,res] (multiply by 3 for channels), -1 = unused
+    float w[4];
+};
+
+// direction -> face, (u,v) in [0,1]; returns -1 for a non-finite / zero direction
+__device__ __forceinline__ int cube_face_uv(float x, float y, float z, float& u, float& v)
+{
+    const float ax = fabsf(x), ay = fabsf(y), az = fabsf(z);
+    int idx;
+    float c;
+    if (az > fmaxf(ax, ay)) { idx = 4; c = z; }
+    else if (ay > ax) { idx = 2; c = y; y = z; }
+    else { idx = 0; c = x; x = z; }
+    if (c < 0.f) idx += 1;
+    const float m = __frcp_rn(fabsf(c)) * .5f;
+    const float m0 = (idx == 0 || idx == 5) ? -m : m;
+    const float m1 = (idx != 2) ? -m : m;
+    u = x * m0 + .5f;
+    v = y * m1 + .5f;
+    if (!isfinite(u) || !isfinite(v)) return -1;
+    u = fminf(fmaxf(u, 0.f), 1.f);
+    v = fminf(fmaxf(v, 0.f), 1.f);
+    return idx;
+}
+
+// texel (iu,iv) of `face`, possibly one step outside the face, -> linear index on the adjacent face.
+// Works in doubled integer coordinates: texel centres are the odd integers in [-w+1, w-1], face planes at +-w.
+__device__ __forceinline__ int cube_wrap_texel(int face, int iu, int iv, int w)
+{
+    const bool ou = (iu < 0 || iu >= w), ov = (iv < 0 || iv >= w);
+    if (!ou && !ov) return (face * w + iv) * w + iu;
+    if (ou && ov) return -1;  // cube corner: no such texel
+    const int s = 2 * iu + 1 - w, t = 2 * iv + 1 - w;
+    int p[3];
+    switch (face) {
+        case 0: p[0] = w;  p[1] = -t; p[2] = -s; break;
+        case 1: p[0] = -w; p[1] = -t; p[2] = s;  break;
+        case 2: p[0] = s;  p[1] = w;  p[2] = t;  break;
+        case 3: p[0] = s;  p[1] = -w; p[2] = -t; break;
+        case 4: p[0] = s;  p[1] = -t; p[2] = w;  break;
+        default: p[0] = -s; p[1] = -t; p[2] = -w; break;
+    }
+    const int major = face >> 1;
+    int over = -1;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+        if (a != major && (p[a] > w || p[a] < -w)) over = a;
+    // fold across the edge: the overflowing axis becomes the new face plane, the old plane steps one texel in
+    p[major] = (p[major] > 0) ? (w - 1) : -(w - 1);
+    p[over] = (p[over] > 0) ? w : -w;
+    const int nf = 2 * over + (p[over] < 0 ? 1 : 0);
+    int s2, t2;
+    switch (nf) {
+        case 0: t2 = -p[1]; s2 = -p[2]; break;
+        case 1: t2 = -p[1]; s2 = p[2];  break;
+        case 2: s2 = p[0];  t2 = p[2];  break;
+        case 3: s2 = p[0];  t2 = -p[2]; break;
+        case 4: s2 = p[0];  t2 = -p[1]; break;
+        default: s2 = -p[0]; t2 = -p[1]; break;
+    }
+    const int iu2 = (s2 + w - 1) >> 1, iv2 = (t2 + w - 1) >> 1;
+    return (nf * w + iv2) * w + iu2;
+}
+
+__device__ __forceinline__ CubeTaps cube_taps(float dx, float dy, float dz, int w)
+{
+    CubeTaps T;
+    float u, v;
+    const int face = cube_face_uv(dx, dy, dz, u, v);
+    if (face < 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { T.idx[k] = -1; T.w[k] = 0.f; }
+        return T;
+    }
+    u = u * (float)w - 0.5f;
+    v = v * (float)w - 0.5f;
+    const int iu0 = __float2int_rd(u), iv0 = __float2int_rd(v);
+    const float fu = u - (float)iu0, fv = v - (float)iv0;
+    T.idx[0] = cube_wrap_texel(face, iu0, iv0, w);         T.w[0] = (1.f - fu) * (1.f - fv);
+    T.idx[1] = cube_wrap_texel(face, iu0 + 1, iv0, w);     T.w[1] = fu * (1.f - fv);
+    T.idx[2] = cube_wrap_texel(face, iu0, iv0 + 1, w);     T.w[2] = (1.f - fu) * fv;
+    T.idx[3] = cube_wrap_texel(face, iu0 + 1, iv0 + 1, w); T.w[3] = fu * fv;
+    // at a cube corner the missing texel is the mean of the other three
+    int missing = -1;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (T.idx[k] < 0) missing = k;
+    if (missing >= 0) {
+        const float share = T.w[missing] * 0.33333333f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) T.w[k] = (k == missing) ? 0.f : T.w[k] + share;
+    }
+    return T;
+}
+
+__device__ __forceinline__ float3 cube_fetch(const float* __restrict__ tex, const CubeTaps& T)
+{
+    float3 r = make_float3(0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (T.idx[k] >= 0) {
+            const float* p = tex + 3 * (size_t)T.idx[k];
+            r.x += T.w[k] * p[0];
+            r.y += T.w[k] * p[1];
+            r.z += T.w[k] * p[2];
+        }
+    }
+    return r;
+}
+
+struct LutTaps {
+    int i00, i10, i01, i11;
+    float fu, fv;
+    bool clampV;
+};
+__device__ __forceinline__ LutTaps lut_taps(float u, float v, int res)
+{
+    LutTaps L;
+    u = u * (float)res - 0.5f;
+    v = v * (float)res - 0.5f;
+    u = fminf(fmaxf(u, 0.f), res - 1.f);
+    v = fminf(fmaxf(v, 0.f), res - 1.f);
+    const bool clampU = (u == 0.f || u == res - 1.f);
+    L.clampV = (v == 0.f || v == res - 1.f);
+    const int iu0 = __float2int_rd(u), iv0 = __float2int_rd(v);
+    const int iu1 = iu0 + (clampU ? 0 : 1), iv1 = iv0 + (L.clampV ? 0 : 1);
+    L.fu = u - (float)iu0;
+    L.fv = v - (float)iv0;
+    L.i00 = iv0 * res + iu0; L.i10 = iv0 * res + iu1;
+    L.i01 = iv1 * res + iu0; L.i11 = iv1 * res + iu1;
+    return L;
+}
+
+__device__ __forceinline__ float mip_level(float r, float rmin, float rmax, int nlev, float& dlevel_dr)
+{
+    // pbr/light.py:142-152
+    float lvl;
+    if (r < rmax) {
+        const float rc = fminf(fmaxf(r, rmin), rmax);
+        lvl = (rc - rmin) / (rmax - rmin) * (float)(nlev - 2);
+        dlevel_dr = (r >= rmin && r <= rmax) ? (float)(nlev - 2) / (rmax - rmin) : 0.f;
+    } else {
+        const float rc = fminf(fmaxf(r, rmax), 1.0f);
+        lvl = (rc - rmax) / (1.0f - rmax) + (float)nlev - 2.f;
+        dlevel_dr = (r >= rmax && r <= 1.0f) ? 1.f / (1.0f - rmax) : 0.f;
+    }
+    return lvl;
+}
+
+__device__ __forceinline__ float srgb_fwd(float x)
+{
+    // pbr/shade.py:46-52
+    const float eps = 1.1920928955078125e-07f;
+    const float s0 = (323.f / 25.f) * x;
+    const float s1 = (211.f * powf(fmaxf(x, eps), 5.f / 12.f) - 11.f) / 200.f;
+    return (x <= 0.0031308f) ? s0 : s1;
+}
+__device__ __forceinline__ float srgb_bwd(float x)
+{
+    const float eps = 1.1920928955078125e-07f;
+    if (x <= 0.0031308f) return 323.f / 25.f;
+    if (x < eps) return 0.f;
+    return (211.f / 200.f) * (5.f / 12.f) * powf(x, 5.f / 12.f - 1.f);
+}
+__device__ __forceinline__ float aces_raw(float x)
+{
+    const float a = 2.51f, b = 0.03f, c = 2.43f, d = 0.59f, e = 0.14f;
+    return (x * (a * x + b)) / (x * (c * x + d) + e);
+}
+__device__ __forceinline__ float aces_raw_bwd(float x)
+{
+    const float a = 2.51f, b = 0.03f, c = 2.43f, d = 0.59f, e = 0.14f;
+    const float num = x * (a * x + b), den = x * (c * x + d) + e;
+    return ((2.f * a * x + b) * den - num * (2.f * c * x + d)) / (den * den);
+}
+
+struct ShadeParams {
+    int W, H, n_lev, diffuse_res, lut_res, tone, gamma;
+    int spec_res[8];
+    const float* spec[8];
+    const float* diffuse;
+    const float* lut;
+    float rmin, rmax;
+    const float *normals, *view_dirs, *albedo, *roughness, *metallic, *occlusion, *background;
+    const uint8_t* mask;
+    float *render_rgb, *diffuse_rgb, *specular_rgb, *diffuse_light;
+    const float *g_render, *g_diffuse, *g_specular;
+    float *g_albedo, *g_roughness, *g_metallic, *g_diffuse_tex;
+    float* g_spec[8];
+};
+
+// everything the forward computes for one pixel, kept for reuse by the backward
+struct PixelShade {
+    float3 alb, dl, spec, F0, diffuse_rgb, specular_rgb, lin;  // lin = pre-tone linear sum
+    float rough, metal, occ, fgx, fgy, flevel, dlevel_dr;
+    int l0, l1;
+    CubeTaps td, t0, t1;
+    LutTaps lt;
+    float3 s0, s1;
+};
+
+struct ShadeIn {
+    float3 n, v, alb;
+    float rough, metal, occ;
+};
+
+__device__ __forceinline__ void shade_eval(const ShadeParams& p, const ShadeIn& in, PixelShade& S);
+
+__device__ __forceinline__ void shade_pixel(const ShadeParams& p, size_t id, size_t HW, PixelShade& S)
+{
+    ShadeIn in;
+    in.n = make_float3(p.normals[id], p.normals[HW + id], p.normals[2 * HW + id]);
+    in.v = make_float3(p.view_dirs[id], p.view_dirs[HW + id], p.view_dirs[2 * HW + id]);
+    in.alb = make_float3(p.albedo[id], p.albedo[HW + id], p.albedo[2 * HW + id]);
+    in.rough = p.roughness[id];
+    in.metal = p.metallic ? p.metallic[id] : 0.f;
+    in.occ = p.occlusion ? p.occlusion[id] : 1.f;
+    shade_eval(p, in, S);
+}
+
+__device__ __forceinline__ void shade_eval(const ShadeParams& p, const ShadeIn& in, PixelShade& S)
+{
+    const float3 n = in.n, v = in.v;
+    S.alb = in.alb;
+    S.rough = in.rough;
+    S.metal = in.metal;
+    S.occ = in.occ;
+
+    const float ndv = fmaxf(n.x * v.x + n.y * v.y + n.z * v.z, 0.0f);
+    const float3 ref = make_float3(2.0f * ndv * n.x - v.x, 2.0f * ndv * n.y - v.y, 2.0f * ndv * n.z - v.z);
+    // x @ T^T with T = [[0,-1,0],[0,0,1],[-1,0,0]]  ->  (-x.y, x.z, -x.x)
+    const float3 nT = make_float3(-n.y, n.z, -n.x);
+    const float3 vT = make_float3(-v.y, v.z, -v.x);
+    const float3 rT = make_float3(-ref.y, ref.z, -ref.x);
+
+    S.td = cube_taps(nT.x, nT.y, nT.z, p.diffuse_res);
+    S.dl = cube_fetch(p.diffuse, S.td);
+    if (p.occlusion) { S.dl.x *= S.occ; S.dl.y *= S.occ; S.dl.z *= S.occ; }
+    S.diffuse_rgb = make_float3(S.dl.x * S.alb.x, S.dl.y * S.alb.y, S.dl.z * S.alb.z);
+
+    const float NoV = fminf(fmaxf(nT.x * vT.x + nT.y * vT.y + nT.z * vT.z, 1e-4f), 1.0f);
+    S.lt = lut_taps(NoV, S.rough, p.lut_res);
+    {
+        const float2* L = reinterpret_cast<const float2*>(p.lut);
+        const float2 a00 = L[S.lt.i00], a10 = L[S.lt.i10], a01 = L[S.lt.i01], a11 = L[S.lt.i11];
+        const float bx0 = a00.x + S.lt.fu * (a10.x - a00.x), bx1 = a01.x + S.lt.fu * (a11.x - a01.x);
+        const float by0 = a00.y + S.lt.fu * (a10.y - a00.y), by1 = a01.y + S.lt.fu * (a11.y - a01.y);
+        S.fgx = bx0 + S.lt.fv * (bx1 - bx0);
+        S.fgy = by0 + S.lt.fv * (by1 - by0);
+    }
+    float lvl = mip_level(S.rough, p.rmin, p.rmax, p.n_lev, S.dlevel_dr);
+    const float lmax = (float)(p.n_lev - 1);
+    if (lvl < 0.f || lvl > lmax) S.dlevel_dr = 0.f;
+    lvl = fminf(fmaxf(lvl, 0.f), lmax);
+    S.l0 = __float2int_rd(lvl);
+    S.l1 = min(S.l0 + 1, p.n_lev - 1);
+    S.flevel = lvl - (float)S.l0;
+    S.t0 = cube_taps(rT.x, rT.y, rT.z, p.spec_res[S.l0]);
+    S.s0 = cube_fetch(p.spec[S.l0], S.t0);
+    if (S.l1 != S.l0) {
+        S.t1 = cube_taps(rT.x, rT.y, rT.z, p.spec_res[S.l1]);
+        S.s1 = cube_fetch(p.spec[S.l1], S.t1);
+        S.spec = make_float3(S.s0.x + S.flevel * (S.s1.x - S.s0.x), S.s0.y + S.flevel * (S.s1.y - S.s0.y),
+                             S.s0.z + S.flevel * (S.s1.z - S.s0.z));
+    } else {
+        S.s1 = S.s0;
+        S.spec = S.s0;
+    }
+    if (p.metallic)
+        S.F0 = make_float3((1.0f - S.metal) * 0.04f + S.alb.x * S.metal, (1.0f - S.metal) * 0.04f + S.alb.y * S.metal,
+                           (1.0f - S.metal) * 0.04f + S.alb.z * S.metal);
+    else
+        S.F0 = make_float3(0.04f, 0.04f, 0.04f);
+    const float3 refl = make_float3(S.F0.x * S.fgx + S.fgy, S.F0.y * S.fgx + S.fgy, S.F0.z * S.fgx + S.fgy);
+    S.specular_rgb = make_float3(S.spec.x * refl.x, S.spec.y * refl.y, S.spec.z * refl.z);
+    S.lin = make_float3(S.diffuse_rgb.x + S.specular_rgb.x, S.diffuse_rgb.y + S.specular_rgb.y,
+                        S.diffuse_rgb.z + S.specular_rgb.z);
+}
+
+}  // namespace gigs
