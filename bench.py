@@ -6,7 +6,9 @@
     python bench.py --impl reference ...     # the CPU oracle port timed on the host cores (the reference has no CPU path)
 
 A "step" is ONE PBR-stage training frame per GPU (train.py:240-422 semantics on the hot path): activations,
-rasterize -> G-buffer, fused depth/normal filter chain, SSAO, split-sum shading, SSR, loss, full backward.
+rasterize -> G-buffer, fused depth/normal filter chain, SSAO, split-sum shading, SSR, loss, full backward, run
+through the repo's public step API (gigs.step.training_step -> the fused frame path, two C-ABI calls per view;
+"variants.unfused_operator_path" times the same frame through the reference-shaped operator modules + autograd).
 Workload = BASELINE configs[1]: lego-shaped synthetic scene, 300k random Gaussians (trained-like regime),
 800x800, SH degree 3, --metallic --indirect --gamma, GI radius 0.8 / bias 0.01 / thick 0.05 / delta 0.0625 /
 step 16 / start 64 (the README flags, under which the march loop runs zero iterations — the same frame with
@@ -28,12 +30,14 @@ sys.path.insert(0, os.path.join(ROOT, "gi-gs_b200"))
 GI_BASE = dict(radius=0.8, bias=0.01, thick=0.05, delta=0.0625, step=16)
 STAGE_NAMES = ["preprocess", "emit_keys", "radix_sort", "tile_ranges", "blend_forward", "blend_backward",
                "gaussian_backward", "geometry_chain", "ssao", "ssr", "shade_forward", "shade_backward", "median3x3",
-               "median3x3_backward", "bilateral3x3", "depth_to_normal", "ssr_backward", "dist2"]
+               "median3x3_backward", "bilateral3x3", "depth_to_normal", "ssr_backward", "dist2", "deferred_shade",
+               "deferred_loss", "deferred_backward", "param_grad", "radix_sort_pass"]
 # kernels launched per stage record (radix_sort: histogram + scan + passes, filled in at run time)
 STAGE_LAUNCHES = {"preprocess": 2, "emit_keys": 1, "tile_ranges": 1, "blend_forward": 1, "blend_backward": 1,
                   "gaussian_backward": 1, "geometry_chain": 1, "ssao": 1, "ssr": 1, "shade_forward": 1,
                   "shade_backward": 1, "median3x3": 1, "median3x3_backward": 1, "bilateral3x3": 1,
-                  "depth_to_normal": 1, "ssr_backward": 1, "dist2": 9}
+                  "depth_to_normal": 1, "ssr_backward": 1, "dist2": 9, "deferred_shade": 1, "deferred_loss": 1,
+                  "deferred_backward": 1, "param_grad": 1, "radix_sort_pass": 0}
 
 
 def parse():
@@ -196,7 +200,7 @@ def run_ours(args):
     bg = torch.zeros(3, device=dev)
     flush_buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
 
-    def one_step(i, gi, e2e=False):
+    def one_step(i, gi, e2e=False, fused=True):
         k = (i * world + rank) % K_cams
         params.zero_grad()
         if e2e:
@@ -208,7 +212,7 @@ def run_ours(args):
             gt = gts_host[k].to(dev, non_blocking=True)
         else:
             cam, gt = cams[k], gts[k]
-        loss = gstep.training_step(params, cam, light, lut, rays, gt, bg, gi, loss_scale=1.0 / world)
+        loss = gstep.training_step(params, cam, light, lut, rays, gt, bg, gi, loss_scale=1.0 / world, fused=fused)
         if world > 1:
             dist.all_reduce(params.flat_grad, op=dist.ReduceOp.SUM)
         if e2e:
@@ -220,11 +224,11 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(gi, steps, warmup, e2e=False, sampler=None):
+    def timed(gi, steps, warmup, e2e=False, sampler=None, fused=True):
         if sampler:
             sampler.start()
         for i in range(warmup):
-            one_step(i, gi, e2e)
+            one_step(i, gi, e2e, fused)
         barrier()
         t_wall0 = time.time()
         tot_ms = 0.0
@@ -233,13 +237,13 @@ def run_ours(args):
             torch.cuda.synchronize()
             if e2e:
                 t0 = time.perf_counter()
-                one_step(warmup + i, gi, True)
+                one_step(warmup + i, gi, True, fused)
                 torch.cuda.synchronize()
                 tot_ms += (time.perf_counter() - t0) * 1e3
             else:
                 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
                 e0.record()
-                one_step(warmup + i, gi, False)
+                one_step(warmup + i, gi, False, fused)
                 e1.record()
                 torch.cuda.synchronize()
                 tot_ms += e0.elapsed_time(e1)
@@ -313,6 +317,10 @@ def run_ours(args):
             "blend_forward": ("fp32", 50.0 * pairs),
             "blend_backward": ("fp32", 30.0 * pairs),  # material-only path of the PBR stage (110 for the full path)
             "gaussian_backward": ("hbm", args.P * 84 + vis * (236 + 256)),
+            "radix_sort_pass": ("hbm", 24 * R),
+            "deferred_shade": ("hbm", 129 * N),
+            "deferred_loss": ("hbm", 63 * N),
+            "deferred_backward": ("hbm", 108 * N),
         }
         rooflines = {}
         for nm, (bound, amount) in alg.items():
@@ -326,12 +334,23 @@ def run_ours(args):
                     ach = amount / per_launch_s / 1e12
                     rooflines[nm] = {"bound": "fp32", "achieved": ach, "peak": peak_tf.value, "unit": "TFLOP/s",
                                      "frac": ach / peak_tf.value if peak_tf.value else None, "ms": per_launch_s * 1e3}
-        dom = max(stage_ms, key=lambda s: stage_ms[s])
+        # dominant KERNEL = largest per-launch time among the single-kernel stages (the sort stage is 8 launches;
+        # its pass kernel is listed on its own as radix_sort_pass)
+        per_launch = {nm: stage_ms[nm] / max(stage_calls[nm], 1) for nm in stage_ms if nm != "radix_sort"}
+        dom = max(per_launch, key=lambda s2: per_launch[s2])
         rf = dict(rooflines.get(dom, {"bound": "fp32", "achieved": None, "peak": peak_tf.value, "unit": "TFLOP/s",
                                       "frac": None}))
-        rf.update(kernel=dom, traffic=None, peak_source=f"hbm: {hbm_src}; fp32: gigs_ffma_peak measured in this run",
+        traffic = None
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+                traffic = json.load(fh).get(dom, {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        rf.update(kernel=dom, traffic=traffic,
+                  peak_source=f"hbm: {hbm_src}; fp32: gigs_ffma_peak measured in this run",
                   note="bound 'fp32' = FP32 FMA pipe (no tensor-core work on this path); algorithmic flops = 50 (fwd) "
-                       "/ 30 (material-only bwd) per visited (pixel,Gaussian) pair, pairs = sum(n_contrib)")
+                       "/ 30 (material-only bwd) per visited (pixel,Gaussian) pair, pairs = sum(n_contrib); traffic = "
+                       "DRAM bytes per launch from profiles/traffic.json (ncu --set full), null if not captured")
         line["roofline"] = rf
         line["rooflines"] = rooflines
         line["stage_ms"] = stage_ms
@@ -360,6 +379,11 @@ def run_ours(args):
                                                 "note": "upper bound on probes (512 dirs x 8 steps per pixel, early "
                                                         "exits not counted)"}
                 line["variants"] = {"gi_start8": v8}
+                tu, _ = timed(gi, max(5, args.steps // 2), 3, fused=False)
+                msu = tu / max(5, args.steps // 2)
+                line["variants"]["unfused_operator_path"] = {
+                    "value": 1e3 / msu, "unit": "frames/s", "ms_per_step": msu,
+                    "note": "same frame through GaussianRasterizer / pbr_shading / Gaussian_SSR modules + autograd"}
             # ---- the reference's own CUDA kernels on the same inputs (second reported point) ----
             if world == 1:
                 line["ref_cuda"] = ref_cuda_point(args, params, cams[0], bg, dev)

@@ -121,7 +121,7 @@ Layout make_layout(int P, int W, int H, uint64_t R)
 }
 
 // launchers defined in the kernel files
-int launch_preprocess(const GigsRasterFwd* a, const Layout& L, cudaStream_t st);
+int launch_preprocess(const GigsRasterFwd* a, const Layout& L, cudaStream_t st, const float* sh_rest);
 int launch_emit_keys(const GigsRasterFwd* a, const Layout& L, uint64_t* keys, uint32_t* vals, cudaStream_t st);
 int launch_tile_ranges(uint64_t R, const uint64_t* keys_sorted, uint2* ranges, uint32_t num_tiles, cudaStream_t st);
 int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t st);
@@ -140,7 +140,7 @@ static int check_common(int P, const GigsCamera& c)
     return 0;
 }
 
-static int forward_finish_impl(GigsRasterFwd* a, bool lite)
+int forward_finish_impl(GigsRasterFwd* a, bool lite)
 {
     if (!a) { set_error("null args"); return -1; }
     if (int e = check_common(a->P, a->cam)) return e;
@@ -207,6 +207,21 @@ using namespace gigs;
 extern "C" {
 
 int gigs_abi_version(void) { return GIGS_ABI_VERSION; }
+
+int gigs_sizeof(int32_t which)
+{
+    switch (which) {
+        case 0: return (int)sizeof(GigsCamera);
+        case 1: return (int)sizeof(GigsSizes);
+        case 2: return (int)sizeof(GigsLayout);
+        case 3: return (int)sizeof(GigsRasterFwd);
+        case 4: return (int)sizeof(GigsRasterBwd);
+        case 5: return (int)sizeof(GigsShade);
+        case 6: return (int)sizeof(GigsFrameLayout);
+        case 7: return (int)sizeof(GigsFrame);
+        default: return -1;
+    }
+}
 const char* gigs_last_error(void) { return g_last_error.c_str(); }
 
 int gigs_profile_enable(int32_t on)
@@ -271,7 +286,7 @@ int gigs_raster_forward_begin(GigsRasterFwd* a)
     }
     {
         ProfScope ps(ST_PREPROCESS, st);
-        if (int e = launch_preprocess(a, L, st)) return e;
+        if (int e = launch_preprocess(a, L, st, nullptr)) return e;
     }
     uint32_t hostR = 0;
     uint32_t* dst = a->pinned_num_rendered ? a->pinned_num_rendered : &hostR;

@@ -31,17 +31,19 @@ __device__ __forceinline__ V3 operator+(const V3& a, const V3& b) { return {a.x 
 __device__ __forceinline__ V3 operator-(const V3& a, const V3& b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
 
 // SH -> RGB for one Gaussian. sh points at this Gaussian's M x 3 coefficients.
-__device__ __forceinline__ V3 sh_to_rgb(int deg, const V3 pos, const V3 campos, const float* __restrict__ shp,
-                                        bool clamped[3])
+// sh0 points at coefficient 0, shr at "coefficient 0" of the array that holds coefficients >= 1 (so coefficient i
+// lives at shr + 3*i); the two coincide for the API's [P,M,3] tensor and differ for raw f_dc / f_rest leaves.
+__device__ __forceinline__ V3 sh_to_rgb(int deg, const V3 pos, const V3 campos, const float* __restrict__ sh0,
+                                        const float* __restrict__ shr, bool clamped[3])
 {
     V3 dir = pos - campos;
     float len = sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
     dir.x = dir.x / len;
     dir.y = dir.y / len;
     dir.z = dir.z / len;
-    auto SH = [&](int i) -> V3 { return {shp[3 * i + 0], shp[3 * i + 1], shp[3 * i + 2]}; };
+    auto SH = [&](int i) -> V3 { return {shr[3 * i + 0], shr[3 * i + 1], shr[3 * i + 2]}; };
 
-    V3 result = kSH_C0 * SH(0);
+    V3 result = kSH_C0 * V3{sh0[0], sh0[1], sh0[2]};
     if (deg > 0) {
         float x = dir.x, y = dir.y, z = dir.z;
         result = result - kSH_C1 * y * SH(1) + kSH_C1 * z * SH(2) - kSH_C1 * x * SH(3);
@@ -118,11 +120,18 @@ __device__ __forceinline__ float3 cov2d_ewa(const float3& mean, float focal_x, f
 
 constexpr int PRE_THREADS = 256;
 
+// the GaussianModel getters (scene/gaussian_model.py:178-266) for the RAW variant of the kernel
+__device__ __forceinline__ float act_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// RAW: the parameter pointers are the trainer's pre-activation leaves (logits, log-scales, un-normalised
+// quaternion / normal, f_dc and f_rest as two tensors) and the activations are applied on load, which removes
+// ~10 elementwise launches and the 192 B/Gaussian torch.cat per frame.
+template <bool RAW>
 __global__ void __launch_bounds__(PRE_THREADS)
 preprocess_kernel(const int P, const int D, const int M, const float* __restrict__ means3D,
                   const float* __restrict__ scales, const float scale_modifier, const float* __restrict__ rotations,
                   const float* __restrict__ opacities, const float* __restrict__ shs,
-                  const float* __restrict__ cov3D_precomp, const float* __restrict__ colors_precomp,
+                  const float* __restrict__ sh_rest, const float* __restrict__ cov3D_precomp, const float* __restrict__ colors_precomp,
                   const float* __restrict__ normal, const float* __restrict__ albedo,
                   const float* __restrict__ roughness, const float* __restrict__ metallic,
                   const float* __restrict__ viewmatrix, const float* __restrict__ projmatrix,
@@ -167,8 +176,13 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
             if (cov3D_precomp != nullptr) {
                 cov3D = cov3D_precomp + idx * 6;
             } else {
-                const float3 sc = {scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]};
-                const float4 rot = *reinterpret_cast<const float4*>(rotations + 4 * idx);
+                float3 sc = {scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]};
+                float4 rot = *reinterpret_cast<const float4*>(rotations + 4 * idx);
+                if (RAW) {
+                    sc = make_float3(expf(sc.x), expf(sc.y), expf(sc.z));
+                    const float qn = fmaxf(sqrtf(rot.x * rot.x + rot.y * rot.y + rot.z * rot.z + rot.w * rot.w), 1e-12f);
+                    rot = make_float4(rot.x / qn, rot.y / qn, rot.z / qn, rot.w / qn);
+                }
                 cov3d_from_scale_rot(sc, scale_modifier, rot, cov_local);
 #pragma unroll
                 for (int k = 0; k < 6; ++k) cov3Ds[idx * 6 + k] = cov_local[k];
@@ -193,8 +207,9 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
             float3 rgb;
             if (colors_precomp == nullptr) {
                 bool cl[3];
-                V3 c = sh_to_rgb(D, V3{p_orig.x, p_orig.y, p_orig.z}, V3{sCam[0], sCam[1], sCam[2]},
-                                 shs + (size_t)idx * M * 3, cl);
+                const float* sh0 = RAW ? shs + (size_t)idx * 3 : shs + (size_t)idx * M * 3;
+                const float* shr = RAW ? sh_rest + ((size_t)idx * (M - 1) - 1) * 3 : sh0;
+                V3 c = sh_to_rgb(D, V3{p_orig.x, p_orig.y, p_orig.z}, V3{sCam[0], sCam[1], sCam[2]}, sh0, shr, cl);
                 rgb = make_float3(c.x, c.y, c.z);
                 *reinterpret_cast<uchar4*>(clamped + 4 * (size_t)idx) =
                     make_uchar4(cl[0] ? 1 : 0, cl[1] ? 1 : 0, cl[2] ? 1 : 0, 0);
@@ -205,14 +220,24 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
             my_radius_i = (int)my_radius;
             touched = (rect_max.y - rect_min.y) * (rect_max.x - rect_min.x);
 
-            const float op = opacities[idx];
+            const float op = RAW ? act_sigmoid(opacities[idx]) : opacities[idx];
             float4* rec = reinterpret_cast<float4*>(records + (size_t)idx * REC_FLOATS);
             rec[0] = make_float4(point_image.x, point_image.y, conic.x, conic.y);
             rec[1] = make_float4(conic.z, op, p_view.z, logf(255.0f * op));
             if (normal != nullptr) {
-                rec[2] = make_float4(rgb.x, rgb.y, rgb.z, roughness[idx]);
-                rec[3] = make_float4(albedo[3 * idx], albedo[3 * idx + 1], albedo[3 * idx + 2], metallic[idx]);
-                rec[4] = make_float4(normal[3 * idx], normal[3 * idx + 1], normal[3 * idx + 2], p_view.x);
+                float3 nr = {normal[3 * idx], normal[3 * idx + 1], normal[3 * idx + 2]};
+                float3 al = {albedo[3 * idx], albedo[3 * idx + 1], albedo[3 * idx + 2]};
+                float ro = roughness[idx], me = metallic[idx];
+                if (RAW) {
+                    const float nn = fmaxf(sqrtf(nr.x * nr.x + nr.y * nr.y + nr.z * nr.z), 1e-12f);
+                    nr = make_float3(nr.x / nn, nr.y / nn, nr.z / nn);
+                    al = make_float3(act_sigmoid(al.x), act_sigmoid(al.y), act_sigmoid(al.z));
+                    ro = act_sigmoid(ro);
+                    me = act_sigmoid(me);
+                }
+                rec[2] = make_float4(rgb.x, rgb.y, rgb.z, ro);
+                rec[3] = make_float4(al.x, al.y, al.z, me);
+                rec[4] = make_float4(nr.x, nr.y, nr.z, p_view.x);
             } else {  // lite path: colour/opacity/depth only
                 rec[2] = make_float4(rgb.x, rgb.y, rgb.z, 0.f);
                 rec[3] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -376,20 +401,26 @@ mark_visible_kernel(const int P, const float* __restrict__ means3D, const float*
 // ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
-int launch_preprocess(const GigsRasterFwd* a, const Layout& L, cudaStream_t st)
+// sh_rest != nullptr selects the RAW variant: a->shs is then f_dc [P,1,3], sh_rest is f_rest [P,M-1,3], and
+// opacities / normal / albedo / roughness / metallic / scales / rotations are pre-activation leaves.
+int launch_preprocess(const GigsRasterFwd* a, const Layout& L, cudaStream_t st, const float* sh_rest)
 {
     const int P = a->P;
     const GigsCamera& c = a->cam;
     const float focal_y = c.height / (2.0f * c.tan_fovy);
     const float focal_x = c.width / (2.0f * c.tan_fovx);
     char* g = (char*)a->geom;
-    preprocess_kernel<<<L.num_blocks, PRE_THREADS, 0, st>>>(
-        P, c.sh_degree, c.sh_coeffs, a->means3D, a->scales, c.scale_modifier, a->rotations, a->opacities, a->shs,
-        a->cov3D_precomp, a->colors_precomp, a->normal, a->albedo, a->roughness, a->metallic, c.viewmatrix,
-        c.projmatrix, c.campos, c.width, c.height, c.tan_fovx, c.tan_fovy, focal_x, focal_y, L.tiles_x, L.tiles_y,
-        c.prefiltered != 0, a->radii, (float*)(g + L.off.g_record), (float*)(g + L.off.g_cov3D),
-        (uint8_t*)(g + L.off.g_clamped), (uint32_t*)(g + L.off.g_tiles_touched),
-        (uint32_t*)(g + L.off.g_block_sums));
+#define PRE_ARGS                                                                                                      \
+    P, c.sh_degree, c.sh_coeffs, a->means3D, a->scales, c.scale_modifier, a->rotations, a->opacities, a->shs, sh_rest, \
+        a->cov3D_precomp, a->colors_precomp, a->normal, a->albedo, a->roughness, a->metallic, c.viewmatrix,           \
+        c.projmatrix, c.campos, c.width, c.height, c.tan_fovx, c.tan_fovy, focal_x, focal_y, L.tiles_x, L.tiles_y,    \
+        c.prefiltered != 0, a->radii, (float*)(g + L.off.g_record), (float*)(g + L.off.g_cov3D),                      \
+        (uint8_t*)(g + L.off.g_clamped), (uint32_t*)(g + L.off.g_tiles_touched), (uint32_t*)(g + L.off.g_block_sums)
+    if (sh_rest != nullptr)
+        preprocess_kernel<true><<<L.num_blocks, PRE_THREADS, 0, st>>>(PRE_ARGS);
+    else
+        preprocess_kernel<false><<<L.num_blocks, PRE_THREADS, 0, st>>>(PRE_ARGS);
+#undef PRE_ARGS
     GIGS_LAUNCH_CHECK("preprocess_kernel");
     scan_block_sums_kernel<<<1, 1024, 0, st>>>((uint32_t*)(g + L.off.g_block_sums), (int)L.num_blocks,
                                                (uint32_t*)(g + L.off.g_num_rendered));

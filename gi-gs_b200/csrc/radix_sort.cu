@@ -230,6 +230,7 @@ static int launch_passes(uint32_t n, int end_bit, const uint64_t* keys_u, const 
         uint32_t* vout = to_a ? vals_a : vals_b;
         const int shift = p * 8;
         const int bits = (end_bit - shift) < 8 ? (end_bit - shift) : 8;
+        ProfScope ps(ST_SORT_PASS, st);
         rs_onesweep_kernel<T, I><<<tiles, T, sizeof(Smem), st>>>(kin, kout, vin, vout, n, shift, (1u << bits) - 1u,
                                                                  hist + p * RS_RADIX,
                                                                  status + (size_t)p * status_tiles * RS_RADIX,

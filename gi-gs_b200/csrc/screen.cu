@@ -14,6 +14,7 @@
 // The probe arithmetic keeps the reference's operation order because every probe ends in a
 // threshold test: one flipped hit moves a pixel's occlusion by up to 3e-3.
 #include "common.cuh"
+#include "filters.cuh"
 
 namespace gigs {
 
@@ -25,29 +26,6 @@ namespace gigs {
 // 3x3 median (zero padded). A window holding a non-finite value yields NaN: the filter the
 // reference calls gathers the window with a one-hot convolution, where NaN*0 and inf*0 are NaN.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cswap(float& a, float& b)
-{
-    const float lo = fminf(a, b), hi = fmaxf(a, b);
-    a = lo;
-    b = hi;
-}
-__device__ __forceinline__ float median9(float v[9])
-{
-    bool bad = false;
-#pragma unroll
-    for (int i = 0; i < 9; ++i) bad |= !isfinite(v[i]);
-    if (bad) return __int_as_float(0x7fc00000);
-    // 19-exchange median-of-9 network
-    cswap(v[1], v[2]); cswap(v[4], v[5]); cswap(v[7], v[8]);
-    cswap(v[0], v[1]); cswap(v[3], v[4]); cswap(v[6], v[7]);
-    cswap(v[1], v[2]); cswap(v[4], v[5]); cswap(v[7], v[8]);
-    cswap(v[0], v[3]); cswap(v[5], v[8]); cswap(v[4], v[7]);
-    cswap(v[3], v[6]); cswap(v[1], v[4]); cswap(v[2], v[5]);
-    cswap(v[4], v[7]); cswap(v[4], v[2]); cswap(v[6], v[4]);
-    cswap(v[4], v[2]);
-    return v[4];
-}
-
 __global__ void __launch_bounds__(256)
 median3x3_kernel(const int C, const int W, const int H, const float* __restrict__ in, float* __restrict__ out)
 {

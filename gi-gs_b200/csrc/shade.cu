@@ -46,47 +46,9 @@ __global__ void __launch_bounds__(256) shade_forward_kernel(const ShadeParams p)
     }
 }
 
-// Backward: persistent CTAs. Texel gradients are the hot spot: neighbouring pixels hit the same few texels
-// (a 16x16 face texel covers ~50 px at 800x800), so per-lane atomics serialise 32-way. Each tap is therefore
-// reduced over runs of equal texel index inside the warp first (segmented scan, 5 shuffle steps, flags shared by the
-// three channels) and only the last lane of a run issues the atomic. The diffuse texture (18 KB) accumulates in
-// shared memory and is flushed once per CTA; specular texels take red.global directly.
-constexpr int SHB_MAX_DIFFUSE = 6 * 16 * 16 * 3;
-
-// key < 0 = nothing to add. All 32 lanes must call this.
-__device__ __forceinline__ void warp_run_reduce3(const int key, float a, float b, float c, float* dst, const bool shared,
-                                                 const int lane)
-{
-    const unsigned full = 0xffffffffu;
-    if (__all_sync(full, key < 0)) return;
-    const int prev = __shfl_up_sync(full, key, 1);
-    int f = (lane == 0 || prev != key) ? 1 : 0;  // a run head lies within the last d lanes
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const float au = __shfl_up_sync(full, a, d), bu = __shfl_up_sync(full, b, d), cu = __shfl_up_sync(full, c, d);
-        const int fu = __shfl_up_sync(full, f, d);
-        if (lane >= d && !f) {
-            a += au;
-            b += bu;
-            c += cu;
-            f = fu;
-        }
-    }
-    const int next = __shfl_down_sync(full, key, 1);
-    const bool tail = (lane == 31) || (next != key);
-    if (tail && key >= 0) {
-        if (shared) {
-            if (a != 0.f) atomicAdd(dst + 0, a);
-            if (b != 0.f) atomicAdd(dst + 1, b);
-            if (c != 0.f) atomicAdd(dst + 2, c);
-        } else {
-            if (a != 0.f) red_add_f32(dst + 0, a);
-            if (b != 0.f) red_add_f32(dst + 1, b);
-            if (c != 0.f) red_add_f32(dst + 2, c);
-        }
-    }
-}
-
+// Backward: persistent CTAs; per-pixel maths and the warp run-reduction of texel gradients live in shade_core.cuh.
+// The diffuse texture (18 KB) accumulates in shared memory and is flushed once per CTA; specular texels take
+// red.global directly.
 __global__ void __launch_bounds__(256) shade_backward_kernel(const ShadeParams p)
 {
     extern __shared__ float s_dtex[];
@@ -102,7 +64,7 @@ __global__ void __launch_bounds__(256) shade_backward_kernel(const ShadeParams p
         const size_t id = base + threadIdx.x;
         const bool live = id < HW;   // dead lanes still take part in the warp reductions below
         PixelShade S;
-        float g_dl[3] = {0.f, 0.f, 0.f}, g_spec[3] = {0.f, 0.f, 0.f};
+        ShadeGrad G;
         if (live) {
             shade_pixel(p, id, HW, S);
             const bool m = p.mask[id] != 0;
@@ -112,99 +74,21 @@ __global__ void __launch_bounds__(256) shade_backward_kernel(const ShadeParams p
             float gd[3], gs[3];  // dL/d diffuse_rgb, dL/d specular_rgb (linear)
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                float g = (m && p.g_render) ? p.g_render[k * HW + id] : 0.f;
-                const float x = lin[k];
-                float y;  // post tone/clamp value (input of the gamma curve)
-                float dy_dx;
-                if (p.tone) {
-                    const float r = aces_raw(x);
-                    y = fminf(fmaxf(r, 0.f), 1.f);
-                    dy_dx = (r >= 0.f && r <= 1.f) ? aces_raw_bwd(x) : 0.f;
-                } else {
-                    y = fminf(fmaxf(x, 0.f), 1.f);
-                    dy_dx = (x >= 0.f && x <= 1.f) ? 1.f : 0.f;
-                }
-                if (p.gamma) g *= srgb_bwd(y);
-                g *= dy_dx;
+                const float g = shade_tone_bwd(p, lin[k], (m && p.g_render) ? p.g_render[k * HW + id] : 0.f);
                 gd[k] = g;
                 gs[k] = g;
                 if (p.g_diffuse) gd[k] += p.g_diffuse[k * HW + id] * (p.gamma ? srgb_bwd(drgb[k]) : 1.f);
                 if (p.g_specular) gs[k] += p.g_specular[k * HW + id] * (p.gamma ? srgb_bwd(srgbv[k]) : 1.f);
             }
-            const float alb[3] = {S.alb.x, S.alb.y, S.alb.z};
-            const float dl[3] = {S.dl.x, S.dl.y, S.dl.z};
-            const float spec[3] = {S.spec.x, S.spec.y, S.spec.z};
-            const float F0[3] = {S.F0.x, S.F0.y, S.F0.z};
-            const float s0[3] = {S.s0.x, S.s0.y, S.s0.z}, s1[3] = {S.s1.x, S.s1.y, S.s1.z};
-            float g_alb[3];
-            float g_fgx = 0.f, g_fgy = 0.f, g_metal = 0.f, g_level = 0.f;
+            shade_material_bwd(p, S, gd, gs, G);
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                g_alb[k] = gd[k] * dl[k];
-                g_dl[k] = gd[k] * alb[k] * (p.occlusion ? S.occ : 1.f);
-                const float refl = F0[k] * S.fgx + S.fgy;
-                g_spec[k] = gs[k] * refl;
-                const float g_refl = gs[k] * spec[k];
-                const float g_F0 = g_refl * S.fgx;
-                g_fgx += g_refl * F0[k];
-                g_fgy += g_refl;
-                if (p.metallic) {
-                    g_alb[k] += g_F0 * S.metal;
-                    g_metal += g_F0 * (alb[k] - 0.04f);
-                }
-                g_level += g_spec[k] * (s1[k] - s0[k]);
-            }
-            // roughness: LUT v-coordinate + mip level
-            float g_rough = 0.f;
-            if (!S.lt.clampV) {
-                const float2* L = reinterpret_cast<const float2*>(p.lut);
-                const float2 a00 = L[S.lt.i00], a10 = L[S.lt.i10], a01 = L[S.lt.i01], a11 = L[S.lt.i11];
-                const float dfx = ((a01.x - a00.x) * (1.f - S.lt.fu) + (a11.x - a10.x) * S.lt.fu) * (float)p.lut_res;
-                const float dfy = ((a01.y - a00.y) * (1.f - S.lt.fu) + (a11.y - a10.y) * S.lt.fu) * (float)p.lut_res;
-                g_rough += g_fgx * dfx + g_fgy * dfy;
-            }
-            if (S.l1 != S.l0) g_rough += g_level * S.dlevel_dr;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) p.g_albedo[k * HW + id] = g_alb[k];
-            p.g_roughness[id] = g_rough;
-            if (p.g_metallic) p.g_metallic[id] = g_metal;
+            for (int k = 0; k < 3; ++k) p.g_albedo[k * HW + id] = G.g_alb[k];
+            p.g_roughness[id] = G.g_rough;
+            if (p.g_metallic) p.g_metallic[id] = G.g_metal;
         } else {
-#pragma unroll
-            for (int t = 0; t < 4; ++t) { S.td.idx[t] = S.t0.idx[t] = S.t1.idx[t] = -1; S.td.w[t] = S.t0.w[t] = S.t1.w[t] = 0.f; }
-            S.l0 = S.l1 = 0;
-            S.flevel = 0.f;
+            shade_dead_lane(S, G);
         }
-
-        // texel gradients (warp-uniform control flow: every lane reaches every reduction)
-        if (p.g_diffuse_tex) {
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int key = (S.td.w[t] != 0.f) ? S.td.idx[t] : -1;
-                float* dst = use_smem ? (s_dtex + 3 * max(key, 0)) : (p.g_diffuse_tex + 3 * (size_t)max(key, 0));
-                warp_run_reduce3(key, g_dl[0] * S.td.w[t], g_dl[1] * S.td.w[t], g_dl[2] * S.td.w[t], dst, use_smem, lane);
-            }
-        }
-        {
-            const float w0 = (S.l1 != S.l0) ? (1.f - S.flevel) : 1.f;
-            float* tex0 = p.g_spec[S.l0];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int idx = (tex0 != nullptr) ? S.t0.idx[t] : -1;
-                const int key = (idx >= 0) ? ((S.l0 << 24) | idx) : -1;
-                const float w = S.t0.w[t] * w0;
-                warp_run_reduce3(key, g_spec[0] * w, g_spec[1] * w, g_spec[2] * w,
-                                 tex0 ? tex0 + 3 * (size_t)max(idx, 0) : nullptr, false, lane);
-            }
-            float* tex1 = (S.l1 != S.l0) ? p.g_spec[S.l1] : nullptr;
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int idx = (tex1 != nullptr) ? S.t1.idx[t] : -1;
-                const int key = (idx >= 0) ? ((S.l1 << 24) | idx) : -1;
-                const float w = S.t1.w[t] * S.flevel;
-                warp_run_reduce3(key, g_spec[0] * w, g_spec[1] * w, g_spec[2] * w,
-                                 tex1 ? tex1 + 3 * (size_t)max(idx, 0) : nullptr, false, lane);
-            }
-        }
+        shade_texel_scatter(p, S, G, s_dtex, use_smem, lane);
     }
     __syncthreads();
     if (use_smem) {

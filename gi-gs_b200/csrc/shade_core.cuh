@@ -285,4 +285,156 @@ __device__ __forceinline__ void shade_eval(const ShadeParams& p, const ShadeIn& 
                         S.diffuse_rgb.z + S.specular_rgb.z);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Backward pieces shared by shade_backward_kernel (shade.cu) and deferred_backward_kernel (deferred.cu)
+// ------------------------------------------------------------------------------------------------
+struct ShadeGrad {
+    float g_alb[3], g_rough, g_metal;   // dL/d albedo, roughness (the value the LUT / mip lookup saw), metallic
+    float g_dl[3], g_spec[3];           // dL/d (diffuse cube sample), dL/d (specular cube sample)
+};
+
+// Chain through gamma and tone/clamp: g (dL/d render value of channel k, already masked) -> dL/d linear sum.
+__device__ __forceinline__ float shade_tone_bwd(const ShadeParams& p, float x, float g)
+{
+    float y, dy_dx;
+    if (p.tone) {
+        const float r = aces_raw(x);
+        y = fminf(fmaxf(r, 0.f), 1.f);
+        dy_dx = (r >= 0.f && r <= 1.f) ? aces_raw_bwd(x) : 0.f;
+    } else {
+        y = fminf(fmaxf(x, 0.f), 1.f);
+        dy_dx = (x >= 0.f && x <= 1.f) ? 1.f : 0.f;
+    }
+    if (p.gamma) g *= srgb_bwd(y);
+    return g * dy_dx;
+}
+
+// gd / gs: dL/d diffuse_rgb and dL/d specular_rgb (linear) of the pixel S was evaluated for.
+__device__ __forceinline__ void shade_material_bwd(const ShadeParams& p, const PixelShade& S, const float gd[3],
+                                                   const float gs[3], ShadeGrad& G)
+{
+    const float alb[3] = {S.alb.x, S.alb.y, S.alb.z};
+    const float dl[3] = {S.dl.x, S.dl.y, S.dl.z};
+    const float spec[3] = {S.spec.x, S.spec.y, S.spec.z};
+    const float F0[3] = {S.F0.x, S.F0.y, S.F0.z};
+    const float s0[3] = {S.s0.x, S.s0.y, S.s0.z}, s1[3] = {S.s1.x, S.s1.y, S.s1.z};
+    float g_fgx = 0.f, g_fgy = 0.f, g_metal = 0.f, g_level = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        G.g_alb[k] = gd[k] * dl[k];
+        G.g_dl[k] = gd[k] * alb[k] * (p.occlusion ? S.occ : 1.f);
+        const float refl = F0[k] * S.fgx + S.fgy;
+        G.g_spec[k] = gs[k] * refl;
+        const float g_refl = gs[k] * spec[k];
+        const float g_F0 = g_refl * S.fgx;
+        g_fgx += g_refl * F0[k];
+        g_fgy += g_refl;
+        if (p.metallic) {
+            G.g_alb[k] += g_F0 * S.metal;
+            g_metal += g_F0 * (alb[k] - 0.04f);
+        }
+        g_level += G.g_spec[k] * (s1[k] - s0[k]);
+    }
+    // roughness: LUT v-coordinate + mip level
+    float g_rough = 0.f;
+    if (!S.lt.clampV) {
+        const float2* L = reinterpret_cast<const float2*>(p.lut);
+        const float2 a00 = L[S.lt.i00], a10 = L[S.lt.i10], a01 = L[S.lt.i01], a11 = L[S.lt.i11];
+        const float dfx = ((a01.x - a00.x) * (1.f - S.lt.fu) + (a11.x - a10.x) * S.lt.fu) * (float)p.lut_res;
+        const float dfy = ((a01.y - a00.y) * (1.f - S.lt.fu) + (a11.y - a10.y) * S.lt.fu) * (float)p.lut_res;
+        g_rough += g_fgx * dfx + g_fgy * dfy;
+    }
+    if (S.l1 != S.l0) g_rough += g_level * S.dlevel_dr;
+    G.g_rough = g_rough;
+    G.g_metal = g_metal;
+}
+
+// a lane that shades nothing: taps that add nothing, so it can still take part in the warp reductions
+__device__ __forceinline__ void shade_dead_lane(PixelShade& S, ShadeGrad& G)
+{
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        S.td.idx[t] = S.t0.idx[t] = S.t1.idx[t] = -1;
+        S.td.w[t] = S.t0.w[t] = S.t1.w[t] = 0.f;
+    }
+    S.l0 = S.l1 = 0;
+    S.flevel = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) G.g_dl[k] = G.g_spec[k] = 0.f;
+}
+
+// Texel gradients are the hot spot of the shading backward: neighbouring pixels hit the same few texels (a 16x16
+// face texel covers ~50 px at 800x800), so per-lane atomics serialise 32-way. Each tap is therefore reduced over
+// runs of equal texel index inside the warp first (segmented scan, 5 shuffle steps, flags shared by the three
+// channels) and only the last lane of a run issues the atomic.  key < 0 = nothing to add. All 32 lanes must call.
+constexpr int SHB_MAX_DIFFUSE = 6 * 16 * 16 * 3;
+
+__device__ __forceinline__ void warp_run_reduce3(const int key, float a, float b, float c, float* dst, const bool shared,
+                                                 const int lane)
+{
+    const unsigned full = 0xffffffffu;
+    if (__all_sync(full, key < 0)) return;
+    const int prev = __shfl_up_sync(full, key, 1);
+    int f = (lane == 0 || prev != key) ? 1 : 0;  // a run head lies within the last d lanes
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const float au = __shfl_up_sync(full, a, d), bu = __shfl_up_sync(full, b, d), cu = __shfl_up_sync(full, c, d);
+        const int fu = __shfl_up_sync(full, f, d);
+        if (lane >= d && !f) {
+            a += au;
+            b += bu;
+            c += cu;
+            f = fu;
+        }
+    }
+    const int next = __shfl_down_sync(full, key, 1);
+    const bool tail = (lane == 31) || (next != key);
+    if (tail && key >= 0) {
+        if (shared) {
+            if (a != 0.f) atomicAdd(dst + 0, a);
+            if (b != 0.f) atomicAdd(dst + 1, b);
+            if (c != 0.f) atomicAdd(dst + 2, c);
+        } else {
+            if (a != 0.f) red_add_f32(dst + 0, a);
+            if (b != 0.f) red_add_f32(dst + 1, b);
+            if (c != 0.f) red_add_f32(dst + 2, c);
+        }
+    }
+}
+
+// Warp-uniform: every lane of the warp must reach this call (dead lanes via shade_dead_lane).
+// The diffuse texture accumulates in shared memory (s_dtex, flushed by the caller) when use_smem.
+__device__ __forceinline__ void shade_texel_scatter(const ShadeParams& p, const PixelShade& S, const ShadeGrad& G,
+                                                    float* s_dtex, const bool use_smem, const int lane)
+{
+    if (p.g_diffuse_tex) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int key = (S.td.w[t] != 0.f) ? S.td.idx[t] : -1;
+            float* dst = use_smem ? (s_dtex + 3 * max(key, 0)) : (p.g_diffuse_tex + 3 * (size_t)max(key, 0));
+            warp_run_reduce3(key, G.g_dl[0] * S.td.w[t], G.g_dl[1] * S.td.w[t], G.g_dl[2] * S.td.w[t], dst, use_smem,
+                             lane);
+        }
+    }
+    const float w0 = (S.l1 != S.l0) ? (1.f - S.flevel) : 1.f;
+    float* tex0 = p.g_spec[S.l0];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int idx = (tex0 != nullptr) ? S.t0.idx[t] : -1;
+        const int key = (idx >= 0) ? ((S.l0 << 24) | idx) : -1;
+        const float w = S.t0.w[t] * w0;
+        warp_run_reduce3(key, G.g_spec[0] * w, G.g_spec[1] * w, G.g_spec[2] * w,
+                         tex0 ? tex0 + 3 * (size_t)max(idx, 0) : nullptr, false, lane);
+    }
+    float* tex1 = (S.l1 != S.l0) ? p.g_spec[S.l1] : nullptr;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int idx = (tex1 != nullptr) ? S.t1.idx[t] : -1;
+        const int key = (idx >= 0) ? ((S.l1 << 24) | idx) : -1;
+        const float w = S.t1.w[t] * S.flevel;
+        warp_run_reduce3(key, G.g_spec[0] * w, G.g_spec[1] * w, G.g_spec[2] * w,
+                         tex1 ? tex1 + 3 * (size_t)max(idx, 0) : nullptr, false, lane);
+    }
+}
+
 }  // namespace gigs

@@ -101,11 +101,49 @@ class GigsShade(C.Structure):
     ]
 
 
+class GigsFrameLayout(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in (
+        "color", "opacity", "depth", "normal", "normal_view", "pos", "albedo", "roughness", "metallic",
+        "normal_from_depth", "depth_pos", "occlusion", "shade_normal", "ssr_normal", "render_direct", "linear_rgb",
+        "F0", "rough_remap", "metal_used", "ssr_color", "ssr_abd", "render_rgb", "g_rgb", "g_albedo", "g_roughness",
+        "g_metallic", "mask", "median_sel", "partials", "stats", "total_bytes")]
+
+
+class GigsFrame(C.Structure):
+    _fields_ = [
+        ("P", C.c_int32), ("raw_params", C.c_int32),
+        ("cam", GigsCamera),
+        ("means3D", C.c_void_p), ("sh_dc", C.c_void_p), ("sh_rest", C.c_void_p), ("opacities", C.c_void_p),
+        ("normal", C.c_void_p), ("albedo", C.c_void_p), ("roughness", C.c_void_p), ("metallic", C.c_void_p),
+        ("scales", C.c_void_p), ("rotations", C.c_void_p),
+        ("radius", C.c_float), ("bias", C.c_float), ("thick", C.c_float), ("delta", C.c_float),
+        ("step", C.c_int32), ("start", C.c_int32),
+        ("indirect", C.c_int32), ("use_metallic", C.c_int32), ("tone", C.c_int32), ("gamma", C.c_int32),
+        ("n_spec_levels", C.c_int32), ("spec_res", C.c_int32 * 8), ("spec", C.c_void_p * 8),
+        ("diffuse_res", C.c_int32), ("diffuse", C.c_void_p), ("brdf_lut", C.c_void_p), ("lut_res", C.c_int32),
+        ("min_roughness", C.c_float), ("max_roughness", C.c_float),
+        ("canonical_rays", C.c_void_p), ("gt_image", C.c_void_p),
+        ("loss_scale", C.c_float), ("lamb_weight", C.c_float),
+        ("geom", C.c_void_p), ("geom_bytes", C.c_uint64), ("img", C.c_void_p), ("img_bytes", C.c_uint64),
+        ("binning", C.c_void_p), ("binning_bytes", C.c_uint64), ("sort", C.c_void_p), ("sort_bytes", C.c_uint64),
+        ("maps", C.c_void_p), ("maps_bytes", C.c_uint64),
+        ("radii", C.c_void_p), ("accum", C.c_void_p), ("pinned_num_rendered", C.c_void_p),
+        ("num_rendered", C.c_int64), ("resume", C.c_int32), ("_pad", C.c_int32),
+        ("need_binning_bytes", C.c_uint64), ("need_sort_bytes", C.c_uint64),
+        ("g_albedo", C.c_void_p), ("g_roughness", C.c_void_p), ("g_metallic", C.c_void_p),
+        ("g_diffuse_tex", C.c_void_p), ("g_spec", C.c_void_p * 8),
+        ("stream", C.c_void_p),
+    ]
+
+
+GIGS_E_GROW = -5
+
 # every symbol include/gigs_b200.h declares: (name, restype, argtypes)
 _i32, _f, _vp, _u64 = C.c_int32, C.c_float, C.c_void_p, C.c_uint64
 SYMBOLS = {
     "gigs_abi_version": (C.c_int, []),
     "gigs_last_error": (C.c_char_p, []),
+    "gigs_sizeof": (C.c_int, [_i32]),
     "gigs_raster_sizes": (C.c_int, [_i32, _i32, _i32, _u64, C.POINTER(GigsSizes)]),
     "gigs_raster_layout": (C.c_int, [_i32, _i32, _i32, _u64, C.POINTER(GigsLayout)]),
     "gigs_raster_forward_begin": (C.c_int, [C.POINTER(GigsRasterFwd)]),
@@ -123,6 +161,9 @@ SYMBOLS = {
     "gigs_ssr_backward": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gigs_shade_forward": (C.c_int, [C.POINTER(GigsShade)]),
     "gigs_shade_backward": (C.c_int, [C.POINTER(GigsShade)]),
+    "gigs_frame_layout": (C.c_int, [_i32, _i32, C.POINTER(GigsFrameLayout)]),
+    "gigs_frame_forward": (C.c_int, [C.POINTER(GigsFrame)]),
+    "gigs_frame_backward": (C.c_int, [C.POINTER(GigsFrame)]),
     "gigs_dist2": (C.c_int, [_i32, _vp, _vp, _vp, C.POINTER(C.c_uint64), _vp]),
     "gigs_ffma_peak": (C.c_int, [C.POINTER(C.c_double), _vp]),
     "gigs_profile_enable": (C.c_int, [_i32]),
@@ -148,6 +189,11 @@ def load():
         fn.argtypes = args
     if lib.gigs_abi_version() != 1:
         raise ImportError("gigs_b200: ABI version mismatch between the python binding and libgigs_b200.so")
+    for which, st in enumerate((GigsCamera, GigsSizes, GigsLayout, GigsRasterFwd, GigsRasterBwd, GigsShade,
+                                GigsFrameLayout, GigsFrame)):
+        if lib.gigs_sizeof(which) != C.sizeof(st):
+            raise ImportError(f"gigs_b200: struct {st.__name__} is {C.sizeof(st)} bytes in the python binding but "
+                              f"{lib.gigs_sizeof(which)} in libgigs_b200.so")
     _lib = lib
     return lib
 

@@ -1,0 +1,201 @@
+"""Fused PBR-stage frame: host side of gigs_frame_forward / gigs_frame_backward (include/gigs_b200.h).
+
+One view of /root/reference/train.py:266-404 — getters, rasterize, geometry chain + SSAO, render() post-processing,
+pbr_shading, SSR, loss, and the whole backward — as two C-ABI calls on the caller's current stream, with every
+workspace and intermediate map in buffers that persist across frames (no per-frame allocation). The unfused
+operator path (gigs.renderer / diff_gaussian_rasterization) computes the same thing op by op and is what the parity
+tests compare this against.
+"""
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from ._lib import GIGS_E_GROW, GigsCamera, GigsFrame, GigsFrameLayout, GigsSizes, check
+
+_L = _lib.load()
+
+_FLOAT_PLANES = dict(color=3, opacity=1, depth=1, normal=3, normal_view=3, pos=3, albedo=3, roughness=1, metallic=1,
+                     normal_from_depth=3, depth_pos=3, occlusion=1, shade_normal=3, ssr_normal=3, render_direct=3,
+                     linear_rgb=3, F0=3, rough_remap=1, metal_used=1, ssr_color=3, ssr_abd=3, render_rgb=3, g_rgb=3,
+                     g_albedo=3, g_roughness=1, g_metallic=1)
+
+
+class FrameWorkspace:
+    """Device buffers of one (P, W, H) frame shape. geom / img / maps / radii / accum are sized by shape; binning and
+    the sort scratch grow (x1.25) when a frame needs more than any before it."""
+
+    def __init__(self, P: int, W: int, H: int, device):
+        self.P, self.W, self.H, self.device = P, W, H, torch.device(device)
+        sz = GigsSizes()
+        check(_L.gigs_raster_sizes(P, W, H, 0, C.byref(sz)), "gigs_raster_sizes")
+        self.layout = GigsFrameLayout()
+        check(_L.gigs_frame_layout(W, H, C.byref(self.layout)), "gigs_frame_layout")
+        u8 = dict(dtype=torch.uint8, device=self.device)
+        self.geom = torch.empty(sz.geom_bytes, **u8)
+        self.img = torch.empty(sz.img_bytes, **u8)
+        self.maps = torch.empty(self.layout.total_bytes, **u8)
+        self.radii = torch.empty(P, dtype=torch.int32, device=self.device)
+        self.accum = torch.empty((P, 20), dtype=torch.float32, device=self.device)
+        self.binning: Optional[torch.Tensor] = None
+        self.sort: Optional[torch.Tensor] = None
+        self.pinned = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.num_rendered = 0
+
+    def grow(self, binning_bytes: int, sort_bytes: int):
+        u8 = dict(dtype=torch.uint8, device=self.device)
+        if self.binning is None or self.binning.numel() < binning_bytes:
+            self.binning = torch.empty(int(binning_bytes * 1.25) + 1024, **u8)
+        if self.sort is None or self.sort.numel() < sort_bytes:
+            self.sort = torch.empty(int(sort_bytes * 1.25) + 1024, **u8)
+
+    def map(self, name: str) -> torch.Tensor:
+        """View of one intermediate map of the last frame ([c,H,W] float32; 'mask' [H,W] / 'median_sel' [3,H,W] uint8;
+        'stats' float32[8] = loss, l1_mean, mask_count, sum((1-rough)*mask), sum(metal*mask))."""
+        off = getattr(self.layout, name)
+        N = self.W * self.H
+        if name in _FLOAT_PLANES:
+            c = _FLOAT_PLANES[name]
+            return self.maps[off:off + 4 * c * N].view(torch.float32).view(c, self.H, self.W)
+        if name == "mask":
+            return self.maps[off:off + N].view(self.H, self.W)
+        if name == "median_sel":
+            return self.maps[off:off + 3 * N].view(3, self.H, self.W)
+        if name == "stats":
+            return self.maps[off:off + 32].view(torch.float32)
+        raise KeyError(name)
+
+
+_workspaces: Dict = {}
+
+
+def workspace(P: int, W: int, H: int, device) -> FrameWorkspace:
+    key = (P, W, H, torch.device(device).index or 0)
+    ws = _workspaces.get(key)
+    if ws is None:
+        ws = _workspaces[key] = FrameWorkspace(P, W, H, device)
+    return ws
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _fill(ws: FrameWorkspace, cam, bg, params: Dict, raw: bool, sh_degree: int, light, brdf_lut, rays, gt, gi: Dict,
+          indirect: bool, metallic: bool, tone: bool, gamma: bool, loss_scale: float, lamb_weight: float, keep: list):
+    """params: raw leaves (xyz, f_dc, f_rest, opacity, normal, albedo, roughness, metallic, log_scale, rot) when `raw`,
+    else activated tensors (means3D, shs, opacity, normal, albedo, roughness, metallic, scales, rotations)."""
+    f = GigsFrame()
+    f.P = ws.P
+    f.raw_params = int(raw)
+
+    def c32(t):
+        t = t.detach()
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            t = t.float().contiguous()
+        keep.append(t)
+        return t
+
+    vm, pm, cp, bgc = c32(cam.world_view_transform), c32(cam.full_proj_transform), c32(cam.camera_center), c32(bg)
+    if raw:
+        M = 1 + params["f_rest"].shape[1]
+        f.means3D = _p(c32(params["xyz"])); f.sh_dc = _p(c32(params["f_dc"])); f.sh_rest = _p(c32(params["f_rest"]))
+        f.opacities = _p(c32(params["opacity"])); f.scales = _p(c32(params["log_scale"]))
+        f.rotations = _p(c32(params["rot"]))
+    else:
+        M = params["shs"].shape[1]
+        f.means3D = _p(c32(params["means3D"])); f.sh_dc = _p(c32(params["shs"])); f.sh_rest = None
+        f.opacities = _p(c32(params["opacity"])); f.scales = _p(c32(params["scales"]))
+        f.rotations = _p(c32(params["rotations"]))
+    f.normal = _p(c32(params["normal"])); f.albedo = _p(c32(params["albedo"]))
+    f.roughness = _p(c32(params["roughness"])); f.metallic = _p(c32(params["metallic"]))
+    f.cam = GigsCamera(int(cam.image_width), int(cam.image_height), float(cam.tanfovx), float(cam.tanfovy), 1.0,
+                       int(sh_degree), int(M), 0, 0, 0, 0, _p(vm), _p(pm), _p(cp), _p(bgc))
+    f.radius = float(gi.get("radius", 0.8)); f.bias = float(gi.get("bias", 0.01)); f.thick = float(gi.get("thick", 0.05))
+    f.delta = float(gi.get("delta", 0.0625)); f.step = int(gi.get("step", 16)); f.start = int(gi.get("start", 8))
+    f.indirect = int(bool(indirect)); f.use_metallic = int(bool(metallic)); f.tone = int(bool(tone))
+    f.gamma = int(bool(gamma))
+    spec = [c32(s) for s in light.specular]
+    f.n_spec_levels = len(spec)
+    for i, s in enumerate(spec):
+        f.spec_res[i] = s.shape[1]
+        f.spec[i] = s.data_ptr()
+    dtex = c32(light.diffuse)
+    f.diffuse_res = dtex.shape[1]; f.diffuse = dtex.data_ptr()
+    lut = c32(brdf_lut)
+    f.brdf_lut = lut.data_ptr(); f.lut_res = lut.shape[-2]
+    f.min_roughness = float(getattr(light, "MIN_ROUGHNESS", 0.08))
+    f.max_roughness = float(getattr(light, "MAX_ROUGHNESS", 0.5))
+    f.canonical_rays = _p(c32(rays))
+    f.gt_image = _p(c32(gt)) if gt is not None else None
+    f.loss_scale = float(loss_scale); f.lamb_weight = float(lamb_weight)
+    f.geom = ws.geom.data_ptr(); f.geom_bytes = ws.geom.numel()
+    f.img = ws.img.data_ptr(); f.img_bytes = ws.img.numel()
+    f.maps = ws.maps.data_ptr(); f.maps_bytes = ws.maps.numel()
+    f.radii = ws.radii.data_ptr(); f.accum = ws.accum.data_ptr()
+    f.pinned_num_rendered = ws.pinned.data_ptr()
+    f.stream = torch.cuda.current_stream().cuda_stream
+    return f
+
+
+def _set_sort(ws: FrameWorkspace, f: GigsFrame):
+    f.binning = _p(ws.binning); f.binning_bytes = 0 if ws.binning is None else ws.binning.numel()
+    f.sort = _p(ws.sort); f.sort_bytes = 0 if ws.sort is None else ws.sort.numel()
+
+
+def frame_forward(ws: FrameWorkspace, f: GigsFrame) -> torch.Tensor:
+    """Runs the forward; returns the device scalar holding the loss (a view into the maps blob)."""
+    with torch.cuda.device(ws.device):
+        _set_sort(ws, f)
+        f.resume = 0
+        st = _L.gigs_frame_forward(C.byref(f))
+        if st == GIGS_E_GROW:
+            ws.grow(f.need_binning_bytes, f.need_sort_bytes)
+            _set_sort(ws, f)
+            f.resume = 1
+            st = _L.gigs_frame_forward(C.byref(f))
+        check(st, "gigs_frame_forward")
+    ws.num_rendered = int(f.num_rendered)
+    return ws.map("stats")[0]
+
+
+def frame_backward(ws: FrameWorkspace, f: GigsFrame, g_albedo, g_roughness, g_metallic, g_diffuse_tex, g_spec):
+    """Accumulates (+=) into the given gradient tensors (contiguous float32; None = not wanted)."""
+    f.g_albedo = _p(g_albedo); f.g_roughness = _p(g_roughness); f.g_metallic = _p(g_metallic)
+    f.g_diffuse_tex = _p(g_diffuse_tex)
+    for i in range(8):
+        f.g_spec[i] = _p(g_spec[i]) if (g_spec is not None and i < len(g_spec)) else None
+    with torch.cuda.device(ws.device):
+        check(_L.gigs_frame_backward(C.byref(f)), "gigs_frame_backward")
+
+
+def _grad_of(t: torch.Tensor) -> Optional[torch.Tensor]:
+    """The tensor autograd would accumulate into (allocated zero-filled on first use), None for non-leaves."""
+    if not t.requires_grad:
+        return None
+    if t.grad is None:
+        t.grad = torch.zeros_like(t, memory_format=torch.contiguous_format)
+    if t.grad.dtype != torch.float32 or not t.grad.is_contiguous():
+        raise RuntimeError("fused frame: parameter gradients must be contiguous float32")
+    return t.grad
+
+
+def pbr_frame_step(params, cam, light, brdf_lut, rays, gt_image, background, gi: Dict, metallic=True, gamma=True,
+                   tone=False, indirect=True, loss_scale: float = 1.0, lamb_weight: float = 0.001,
+                   backward: bool = True) -> torch.Tensor:
+    """forward (+ backward) of one PBR-stage view for a gigs.step.GaussianParams: gradients accumulate into
+    params.flat_grad exactly as autograd would through the unfused path. Returns the (detached) loss scalar."""
+    L = params.leaves
+    dev = L["xyz"].device
+    ws = workspace(params.P, int(cam.image_width), int(cam.image_height), dev)
+    keep: list = []
+    f = _fill(ws, cam, background, L, True, params.sh_degree, light, brdf_lut, rays, gt_image, gi, indirect, metallic,
+              tone, gamma, loss_scale, lamb_weight, keep)
+    loss = frame_forward(ws, f)
+    if backward:
+        frame_backward(ws, f, _grad_of(L["albedo"]), _grad_of(L["roughness"]),
+                       _grad_of(L["metallic"]) if metallic else None, _grad_of(light.diffuse),
+                       [_grad_of(t) for t in light.specular])
+    params.last_workspace = ws
+    return loss.clone()

@@ -59,8 +59,18 @@ class GaussianParams:
 
 
 def training_step(params: GaussianParams, cam, light: Light, brdf_lut, rays, gt_image, background, gi: Dict,
-                  metallic=True, gamma=True, tone=False, indirect=True, loss_scale: float = 1.0) -> torch.Tensor:
-    """forward + loss + backward for ONE view; gradients accumulate into params.flat_grad."""
+                  metallic=True, gamma=True, tone=False, indirect=True, loss_scale: float = 1.0,
+                  fused: bool = True) -> torch.Tensor:
+    """forward + loss + backward for ONE view; gradients accumulate into params.flat_grad.
+
+    fused=True (default) runs the frame as two C-ABI calls (gigs.frame: activations, rasterizer, deferred shading /
+    SSR / loss kernels and the material-only backward, ~25 kernel launches). fused=False runs the same frame
+    operator by operator through the drop-in modules and autograd (~200 launches): same result to float rounding,
+    kept as the reference-shaped path and as the parity check of the fused one."""
+    if fused:
+        from .frame import pbr_frame_step
+        return pbr_frame_step(params, cam, light, brdf_lut, rays, gt_image, background, gi, metallic=metallic,
+                              gamma=gamma, tone=tone, indirect=indirect, loss_scale=loss_scale)
     g = params.activated()
     res = pbr_forward(cam, g, light, brdf_lut, rays, background, indirect=indirect, metallic=metallic, tone=tone,
                       gamma=gamma, gi=gi)

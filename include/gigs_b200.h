@@ -46,6 +46,10 @@ typedef struct GigsSizes {
 
 int gigs_abi_version(void);
 const char* gigs_last_error(void);
+/* sizeof() of the argument structs, so a foreign-language binding can verify its mirror of the layout:
+ * which = 0 GigsCamera, 1 GigsSizes, 2 GigsLayout, 3 GigsRasterFwd, 4 GigsRasterBwd, 5 GigsShade,
+ * 6 GigsFrameLayout, 7 GigsFrame; negative for an unknown id. */
+int gigs_sizeof(int32_t which);
 int gigs_raster_sizes(int32_t P, int32_t W, int32_t H, uint64_t R, GigsSizes* out);
 
 /* Byte offsets of the fields inside the blobs (for tests that check keys / sort order / ranges
@@ -236,6 +240,75 @@ typedef struct GigsShade {
 int gigs_shade_forward(GigsShade* a);
 int gigs_shade_backward(GigsShade* a);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fused PBR-stage frame: the whole per-view training step of /root/reference/train.py:266-404 that lies on the
+ * hot path, as TWO calls (forward, backward) instead of ~200 framework launches:
+ *   forward : GaussianModel getters fused into preprocess (scene/gaussian_model.py:178-266, when raw_params) ->
+ *             rasterize (rasterizer_impl.cu:486-672) -> geometry chain + SSAO
+ *             (diff_gaussian_rasterization/__init__.py:475-517) -> render() post-processing
+ *             (gaussian_renderer/__init__.py:157-199) + pbr_shading (pbr/shade.py:104-237) + srgb_to_linear
+ *             (train.py:70-75) in one deferred kernel -> SSR (forward.cu:726-909) -> linear_to_srgb + 3x3 median +
+ *             L1 / "lamb" loss (train.py:380-386,402-404) in one kernel.
+ *   backward: median / sRGB / SSR (g*abd, __init__.py:671-673) / shading backward in one kernel -> material-only
+ *             blend backward (backward.cu:404-630 with dL/dcolor = dL/dopacity = 0, which is what the PBR stage
+ *             feeds it) -> sigmoid backward into the parameter gradients (accumulated, +=).
+ * In the PBR stage normals / occlusion / SSR inputs are detached by the caller (train.py:343-351,378), so albedo,
+ * roughness, metallic and the light textures are the only parameters that receive a gradient; that is the
+ * reference's semantics, not a shortcut.
+ * Every intermediate map lives in ONE caller-owned blob (`maps`, layout from gigs_frame_layout) and stays
+ * inspectable after the call. */
+typedef struct GigsFrameLayout {
+    /* float planes, element offsets in BYTES into the maps blob; [c,H,W] planar */
+    uint64_t color, opacity, depth, normal, normal_view, pos, albedo, roughness, metallic; /* rasterizer outputs */
+    uint64_t normal_from_depth, depth_pos, occlusion;                                      /* geometry chain, SSAO */
+    uint64_t shade_normal;   /* [3] normalised, median-filtered, view-rotated normal the shading uses */
+    uint64_t ssr_normal;     /* [3] normalised + median-filtered out_normal_view the SSR uses */
+    uint64_t render_direct, linear_rgb, F0, rough_remap, metal_used;
+    uint64_t ssr_color, ssr_abd, render_rgb;
+    uint64_t g_rgb;          /* [3] dL/d render_rgb */
+    uint64_t g_albedo, g_roughness, g_metallic; /* dL/d G-buffer maps (backward) */
+    uint64_t mask;           /* uint8 [H,W] normal_mask */
+    uint64_t median_sel;     /* uint8 [3,H,W] window index the IRR median selected (255 = none) */
+    uint64_t partials;       /* float scratch for the deterministic loss reduction */
+    uint64_t stats;          /* float[8]: loss, l1_mean, mask_count, sum((1-rough)*mask), sum(metal*mask), - */
+    uint64_t total_bytes;
+} GigsFrameLayout;
+int gigs_frame_layout(int32_t W, int32_t H, GigsFrameLayout* out);
+
+typedef struct GigsFrame {
+    int32_t P;
+    int32_t raw_params;   /* 1: parameter pointers are pre-activation leaves; sh_dc=[P,1,3], sh_rest=[P,M-1,3].
+                             0: activated tensors as GaussianRasterizer takes them; sh_dc=[P,M,3], sh_rest=NULL */
+    GigsCamera cam;
+    const float* means3D; const float* sh_dc; const float* sh_rest; const float* opacities; const float* normal;
+    const float* albedo; const float* roughness; const float* metallic; const float* scales; const float* rotations;
+    float radius, bias, thick, delta; int32_t step, start;      /* GI settings (GaussianRasterizationSettings) */
+    int32_t indirect, use_metallic, tone, gamma;                 /* train.py --indirect --metallic --tone --gamma */
+    int32_t n_spec_levels; int32_t spec_res[8]; const float* spec[8];
+    int32_t diffuse_res; const float* diffuse; const float* brdf_lut; int32_t lut_res;
+    float min_roughness, max_roughness;
+    const float* canonical_rays; /* [H*W,3] (scene/__init__.py:157-167) */
+    const float* gt_image;       /* [3,H,W]; NULL = forward only, no loss */
+    float loss_scale, lamb_weight;
+    void* geom; uint64_t geom_bytes; void* img; uint64_t img_bytes;
+    void* binning; uint64_t binning_bytes; void* sort; uint64_t sort_bytes;
+    void* maps; uint64_t maps_bytes;
+    int32_t* radii;              /* [P] */
+    float* accum;                /* [P,20] scratch (backward) */
+    uint32_t* pinned_num_rendered;
+    int64_t num_rendered;        /* out of forward */
+    int32_t resume;              /* in: 1 = preprocess already ran for this frame (retry after GIGS_E_GROW) */
+    int32_t _pad;
+    uint64_t need_binning_bytes, need_sort_bytes; /* out: sizes this frame needs (set when returning GIGS_E_GROW) */
+    /* backward outputs, accumulated (+=); per-Gaussian ones are in raw-parameter space when raw_params */
+    float* g_albedo; float* g_roughness; float* g_metallic;   /* [P,3], [P], [P] */
+    float* g_diffuse_tex; float* g_spec[8];
+    void* stream;
+} GigsFrame;
+#define GIGS_E_GROW (-5) /* binning / sort workspace too small: grow to need_*_bytes and call again with resume=1 */
+int gigs_frame_forward(GigsFrame* f);
+int gigs_frame_backward(GigsFrame* f);
+
 /* Replaces distCUDA2 / SimpleKNN::knn (/root/reference/submodules/simple-knn/spatial.cu,
  * simple_knn.cu:165-207): mean squared distance to the 3 nearest other points.
  * scratch_bytes: call with scratch==NULL to query. */
@@ -245,7 +318,8 @@ int gigs_dist2(int32_t P, const float* points, float* mean_dist2, void* scratch,
 /* Per-stage device timing (CUDA events on the launching stream), for bench.py's roofline numbers.
  * Stage ids: 0 preprocess+scan, 1 emit_keys, 2 radix_sort, 3 tile_ranges, 4 blend_forward, 5 blend_backward,
  * 6 gaussian_backward, 7 geometry_chain, 8 ssao, 9 ssr, 10 shade_forward, 11 shade_backward, 12 median3x3,
- * 13 median3x3_backward, 14 bilateral3x3, 15 depth_to_normal, 16 ssr_backward, 17 dist2.
+ * 13 median3x3_backward, 14 bilateral3x3, 15 depth_to_normal, 16 ssr_backward, 17 dist2, 18 deferred_shade,
+ * 19 deferred_loss, 20 deferred_backward, 21 param_grad, 22 one radix-sort pass (nested inside 2).
  * gigs_profile_read synchronises the recorded events, writes up to cap (stage, ms) pairs, clears the log and
  * returns the number written (negative on error). Off by default; costs two event records per stage when on. */
 int gigs_profile_enable(int32_t on);

@@ -16,7 +16,8 @@ def test_header_declares_the_expected_entry_points():
     syms = declared_symbols()
     for must in ("gigs_raster_forward_begin", "gigs_raster_forward_finish", "gigs_raster_backward", "gigs_ssao",
                  "gigs_ssr", "gigs_shade_forward", "gigs_shade_backward", "gigs_dist2", "gigs_geometry_chain",
-                 "gigs_mark_visible", "gigs_depth_to_normal", "gigs_lite_forward_finish", "gigs_ssr_backward"):
+                 "gigs_mark_visible", "gigs_depth_to_normal", "gigs_lite_forward_finish", "gigs_ssr_backward",
+                 "gigs_frame_forward", "gigs_frame_backward", "gigs_frame_layout", "gigs_sizeof"):
         assert must in syms
 
 
@@ -63,3 +64,33 @@ def test_missing_library_is_a_loud_import_error(tmp_path, monkeypatch):
         assert "no CPU or PyTorch fallback" in str(e)
     else:
         raise AssertionError("expected ImportError")
+
+
+def test_struct_mirrors_match_the_library():
+    """ctypes mirrors of the argument structs have the C sizes (checked again at load time)."""
+    from gigs import _lib
+    L = _lib.load()
+    for which, st in enumerate((_lib.GigsCamera, _lib.GigsSizes, _lib.GigsLayout, _lib.GigsRasterFwd,
+                                _lib.GigsRasterBwd, _lib.GigsShade, _lib.GigsFrameLayout, _lib.GigsFrame)):
+        assert L.gigs_sizeof(which) == ctypes.sizeof(st), st.__name__
+    assert L.gigs_sizeof(99) < 0
+
+
+def test_frame_layout_is_aligned_disjoint_and_shape_determined():
+    from gigs import _lib
+    L = _lib.load()
+    a, b = _lib.GigsFrameLayout(), _lib.GigsFrameLayout()
+    assert L.gigs_frame_layout(800, 800, ctypes.byref(a)) == 0
+    assert L.gigs_frame_layout(800, 800, ctypes.byref(b)) == 0
+    offs = [getattr(a, f) for f, _ in a._fields_]
+    assert offs == [getattr(b, f) for f, _ in b._fields_]
+    fields = offs[:-1]
+    assert all(o % 256 == 0 for o in fields) and fields == sorted(fields) and len(set(fields)) == len(fields)
+    assert a.total_bytes > fields[-1]
+    # 60 float planes + 4 byte planes at 800x800, plus small tails
+    assert 60 * 4 * 640000 + 4 * 640000 <= a.total_bytes <= 60 * 4 * 640000 + 4 * 640000 + (1 << 20)
+    assert L.gigs_frame_layout(0, 10, ctypes.byref(a)) < 0
+    # frame entry points validate their arguments without touching the GPU
+    f = _lib.GigsFrame()
+    assert L.gigs_frame_forward(ctypes.byref(f)) < 0 and L.gigs_frame_backward(ctypes.byref(f)) < 0
+    assert L.gigs_frame_forward(None) < 0

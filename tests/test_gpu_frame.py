@@ -1,0 +1,189 @@
+"""GPU: the fused PBR-stage frame (gigs_frame_forward / gigs_frame_backward, csrc/deferred.cu) against the unfused
+operator path (GaussianRasterizer -> render() post-processing -> pbr_shading -> Gaussian_SSR -> loss, autograd),
+which the other -m gpu tests pin to the reference's own kernels and to the CPU oracle.
+
+Two input modes:
+  * activated parameters (raw_params = 0): the rasterizer sees bit-identical inputs in both paths, so the G-buffer,
+    the geometry chain and the SSAO must be BIT-EXACT; the deferred kernels replace chains of float32 framework ops
+    and agree to rounding (1e-5), gradients to 1e-3 relative (north_star tolerance);
+  * raw leaves (raw_params = 1): the getters are evaluated inside preprocess; expf / division round like the
+    framework's kernels but not bit-for-bit, so thresholded results (tile rects, alpha cut-offs, GI hits) may flip
+    for isolated Gaussians: the gates are the loss (1e-5 relative), >= 99.9 % of pixels within 1e-4, and gradients
+    within 1e-3 relative at the README GI setting (start = 64, no march).
+"""
+import ctypes as C
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import gpu_util as U
+from gigs import frame as gframe
+from gigs import renderer, scene, shade, step as gstep
+
+DEV = "cuda:0"
+GI8 = dict(radius=0.8, bias=0.01, thick=0.05, delta=0.0625, step=16, start=8)
+GI64 = dict(GI8, start=64)
+
+
+def _setup(P, W, H, seed=3, base_res=64, lut_res=64):
+    raw = scene.make_scene(P, seed=seed, regime="trained")
+    cam = scene.orbit_camera(1, 8, W, H).to(DEV)
+    lut = shade.make_brdf_lut(lut_res, 64).to(DEV)
+    rays = scene.canonical_rays(cam, DEV)
+    gt = torch.rand(3, H, W, generator=torch.Generator().manual_seed(5)).to(DEV)
+    bg = torch.zeros(3, device=DEV)
+    return raw, cam, lut, rays, gt, bg
+
+
+def _unfused(raw, cam, lut, rays, gt, bg, gi, base_res, **kw):
+    params = gstep.GaussianParams(raw, DEV, light=scene.make_light(0, base_res=base_res))
+    params.zero_grad()
+    loss = gstep.training_step(params, cam, params.light(), lut, rays, gt, bg, gi, fused=False, **kw)
+    return params, float(loss)
+
+
+def _named_grads(params):
+    out, o = {}, 0
+    names = list(params.leaves) + ["light_diffuse"] + [f"light_spec{i}" for i in range(len(params.light_leaves) - 1)]
+    for nm, t in zip(names, list(params.leaves.values()) + params.light_leaves):
+        out[nm] = params.flat_grad[o:o + t.numel()].clone()
+        o += t.numel()
+    return out
+
+
+@pytest.mark.parametrize("gi,metallic", [(GI8, True), (GI64, True), (GI8, False)])
+def test_frame_with_activated_inputs_matches_the_operator_path(gi, metallic):
+    P, W, H, base = 20000, 400, 300, 64
+    raw, cam, lut, rays, gt, bg = _setup(P, W, H)
+    ref, loss_ref = _unfused(raw, cam, lut, rays, gt, bg, gi, base, metallic=metallic)
+    g = {k: (v.detach() if torch.is_tensor(v) else v) for k, v in ref.activated().items()}
+    with torch.no_grad():
+        res = renderer.pbr_forward(cam, g, ref.light(), lut, rays, bg, gi=gi, metallic=metallic)
+
+    # the frame, fed the SAME activated tensors; gradients w.r.t. the activated material tensors
+    light = ref.light()
+    ws = gframe.workspace(P, W, H, DEV)
+    keep = []
+    f = gframe._fill(ws, cam, bg, g, False, 3, light, lut, rays, gt, gi, True, metallic, False, True, 1.0, 0.001, keep)
+    loss = float(gframe.frame_forward(ws, f))
+    # rasterizer / geometry chain / SSAO: same kernels, same inputs -> same bits
+    for nm, key in (("color", "render"), ("opacity", "opacity_map"), ("depth", "depth_map"), ("albedo", "albedo_map"),
+                    ("roughness", "roughness_map"), ("metallic", "metallic_map"), ("depth_pos", "depth_pos"),
+                    ("occlusion", "occlusion_map")):
+        assert torch.equal(ws.map(nm), res[key]), nm
+    assert torch.equal(ws.map("mask").bool(), res["normal_mask"][0])
+    # deferred kernels vs the framework-op chains they replace
+    U.assert_close_map(ws.map("shade_normal"), res["normal_map"], 2e-5, "shade_normal")
+    U.assert_close_map(ws.map("ssr_normal"), res["out_normal_view"], 2e-5, "ssr_normal")
+    U.assert_close_map(ws.map("rough_remap"), res["roughness_remap"], 1e-6, "rough_remap")
+    d_direct = (ws.map("render_direct") - res["render_direct"]).abs()
+    d_rgb = (ws.map("render_rgb") - res["render_rgb"]).abs()
+    assert d_direct.max().item() <= 1e-4, d_direct.max().item()
+    if gi["start"] >= gi["step"]:
+        assert d_rgb.max().item() <= 1e-4, d_rgb.max().item()
+    else:  # the march thresholds may flip a hit for a pixel whose inputs differ in the last bit
+        assert (d_rgb > 1e-4).float().mean().item() < 1e-3
+    assert abs(loss - loss_ref) <= 1e-5 * abs(loss_ref)
+
+    ga, gr, gm = (torch.zeros_like(g["albedo"]), torch.zeros_like(g["roughness"]), torch.zeros_like(g["metallic"]))
+    gd = torch.zeros_like(light.diffuse)
+    gs = [torch.zeros_like(s) for s in light.specular]
+    gframe.frame_backward(ws, f, ga, gr, gm if metallic else None, gd, gs)
+    # reference gradients w.r.t. the activated tensors through autograd on the operator path
+    leaves = {k: g[k].clone().requires_grad_(True) for k in ("albedo", "roughness", "metallic")}
+    g2 = dict(g, **leaves)
+    lt = shade.Light(specular=[s.detach().clone().requires_grad_(True) for s in light.specular],
+                     diffuse=light.diffuse.detach().clone().requires_grad_(True))
+    out = renderer.pbr_forward(cam, g2, lt, lut, rays, bg, gi=gi, metallic=metallic)
+    renderer.pbr_loss(out, gt).backward()
+    tol = 1e-3 if gi["start"] >= gi["step"] else 5e-3
+    U.assert_grad_close(ga, leaves["albedo"].grad, "albedo", tol)
+    U.assert_grad_close(gr, leaves["roughness"].grad, "roughness", tol)
+    if metallic:
+        U.assert_grad_close(gm, leaves["metallic"].grad, "metallic", tol)
+    U.assert_grad_close(gd, lt.diffuse.grad, "light.diffuse", tol)
+    for i, (a, b) in enumerate(zip(gs, lt.specular)):
+        if b.grad is not None and float(b.grad.abs().max()) > 0:
+            U.assert_grad_close(a, b.grad, f"light.specular[{i}]", tol)
+
+
+def test_frame_with_raw_leaves_matches_the_operator_path():
+    P, W, H, base = 20000, 400, 300, 64
+    raw, cam, lut, rays, gt, bg = _setup(P, W, H)
+    ref, loss_ref = _unfused(raw, cam, lut, rays, gt, bg, GI64, base)
+    fus = gstep.GaussianParams(raw, DEV, light=scene.make_light(0, base_res=base))
+    fus.zero_grad()
+    loss = float(gstep.training_step(fus, cam, fus.light(), lut, rays, gt, bg, GI64, fused=True))
+    assert abs(loss - loss_ref) <= 1e-5 * abs(loss_ref)
+    ws = fus.last_workspace
+    with torch.no_grad():
+        g = ref.activated()
+        res = renderer.pbr_forward(cam, g, ref.light(), lut, rays, bg, gi=GI64)
+    for nm, key in (("color", "render"), ("albedo", "albedo_map"), ("render_rgb", "render_rgb")):
+        d = (ws.map(nm) - res[key]).abs()
+        assert (d > 1e-4).float().mean().item() < 1e-3, (nm, d.max().item())
+    ga, gb = _named_grads(ref), _named_grads(fus)
+    for nm in ga:
+        if float(ga[nm].abs().max()) == 0.0:
+            assert float(gb[nm].abs().max()) == 0.0, nm   # geometry / SH / opacity get no gradient in the PBR stage
+        else:
+            U.assert_grad_close(gb[nm], ga[nm], nm, 1e-3)
+
+
+def test_frame_accumulates_gradients_and_is_deterministic_in_the_forward():
+    P, W, H, base = 6000, 160, 96, 32
+    raw, cam, lut, rays, gt, bg = _setup(P, W, H)
+    p = gstep.GaussianParams(raw, DEV, light=scene.make_light(0, base_res=base))
+    p.zero_grad()
+    l1 = float(gstep.training_step(p, cam, p.light(), lut, rays, gt, bg, GI8))
+    rgb1 = p.last_workspace.map("render_rgb").clone()
+    g1 = p.flat_grad.clone()
+    l2 = float(gstep.training_step(p, cam, p.light(), lut, rays, gt, bg, GI8))   # no zero_grad: accumulates
+    assert l1 == l2 and torch.equal(rgb1, p.last_workspace.map("render_rgb"))
+    assert torch.allclose(p.flat_grad, 2 * g1, rtol=1e-4, atol=1e-9)
+    # loss_scale scales loss and gradients
+    p.zero_grad()
+    l3 = float(gstep.training_step(p, cam, p.light(), lut, rays, gt, bg, GI8, loss_scale=0.25))
+    assert abs(l3 - 0.25 * l1) <= 1e-6 * abs(l1)
+    assert torch.allclose(p.flat_grad, 0.25 * g1, rtol=1e-4, atol=1e-9)
+
+
+def test_frame_workspace_growth_and_error_paths():
+    from gigs import _lib
+    L = _lib.load()
+    P, W, H = 3000, 96, 80
+    raw, cam, lut, rays, gt, bg = _setup(P, W, H)
+    p = gstep.GaussianParams(raw, DEV, light=scene.make_light(0, base_res=32))
+    ws = gframe.FrameWorkspace(P, W, H, DEV)   # fresh: no binning / sort buffers yet
+    keep = []
+    f = gframe._fill(ws, cam, bg, p.leaves, True, 3, p.light(), lut, rays, gt, GI8, True, True, False, True, 1.0,
+                     0.001, keep)
+    gframe._set_sort(ws, f)
+    st = L.gigs_frame_forward(C.byref(f))
+    assert st == _lib.GIGS_E_GROW and f.need_binning_bytes >= 4 * f.num_rendered and f.need_sort_bytes > 0
+    assert b"too small" in L.gigs_last_error()
+    loss = float(gframe.frame_forward(ws, f))          # grows and resumes
+    assert loss == loss and ws.num_rendered == f.num_rendered > 0
+    # backward without gradient buffers is an argument error, not a crash
+    f.g_albedo = None
+    assert L.gigs_frame_backward(C.byref(f)) < 0
+    # a maps blob that is too small is refused
+    f.maps_bytes = 16
+    assert L.gigs_frame_forward(C.byref(f)) == -2
+
+
+def test_frame_forward_only_without_ground_truth():
+    P, W, H = 4000, 128, 96
+    raw, cam, lut, rays, gt, bg = _setup(P, W, H)
+    p = gstep.GaussianParams(raw, DEV, light=scene.make_light(0, base_res=32))
+    ws = gframe.workspace(P, W, H, DEV)
+    keep = []
+    f = gframe._fill(ws, cam, bg, p.leaves, True, 3, p.light(), lut, rays, None, GI8, True, True, False, True, 1.0,
+                     0.001, keep)
+    gframe.frame_forward(ws, f)
+    rgb = ws.map("render_rgb").clone()
+    with torch.no_grad():
+        res = renderer.pbr_forward(cam, p.activated(), p.light(), lut, rays, bg, gi=GI8, inference=False)
+    assert ((rgb - res["render_rgb"]).abs() > 1e-4).float().mean().item() < 2e-3
