@@ -33,7 +33,7 @@ static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 int prof_begin(int stage, cudaStream_t st)
 {
-    if (!g_prof_on) return -1;
+    if (!g_prof_on || stage < 0) return -1;
     ProfRec r;
     r.stage = stage;
     if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return -1;
@@ -88,9 +88,21 @@ Layout make_layout(int P, int W, int H, uint64_t R)
     L.off.g_cov3D = take(Pn * 6 * 4);
     L.off.g_clamped = take(Pn * 4);
     L.off.g_tiles_touched = take(Pn * 4);
-    L.off.g_point_offsets = take(Pn * 4);
+    L.off.g_depth_keys = take(Pn * 4);
+    L.off.g_order = take(Pn * 4);
     L.off.g_block_sums = take(((uint64_t)L.num_blocks + 1) * 4);
+    L.g_block_sums2 = take(((uint64_t)L.num_blocks + 1) * 4);
     L.off.g_num_rendered = take(16);
+    {   // depth argsort of the Gaussians: 32-bit keys, 4 passes
+        const uint32_t ptiles = radix_sort_tiles(Pn);
+        L.p_keys_a = take(Pn * 4);
+        L.p_keys_b = take(Pn * 4);
+        L.p_vals_b = take(Pn * 4);
+        L.p_hist = take(8 * 256 * 4);
+        L.p_ticket = take(128);
+        L.p_status = take((uint64_t)4 * ptiles * 256 * 4);
+        L.p_zero_bytes = (L.p_status - L.p_hist) + (uint64_t)4 * ptiles * 256 * 4;
+    }
     L.size.geom_bytes = align_up(o, 128) + 128;
     // img
     o = 0;
@@ -102,32 +114,34 @@ Layout make_layout(int P, int W, int H, uint64_t R)
     o = 0;
     L.off.b_point_list = take(R * 4);
     L.size.binning_bytes = align_up(o, 128) + 128;
-    // sort scratch
+    // instance sort scratch: (tile id, Gaussian id) pairs, tile-id bits only
     o = 0;
-    L.sort_bits = 32 + higher_msb(L.num_tiles);
-    L.sort_passes = (L.sort_bits + 7) / 8;
+    L.sort_bits = higher_msb(L.num_tiles);
+    L.sort_passes = (uint32_t)radix_sort_passes((int)L.sort_bits);
     L.sort_tiles = radix_sort_tiles(R);
-    L.off.s_keys_unsorted = take(R * 8);
+    L.off.s_tiles_unsorted = take(R * 4);
     L.off.s_vals_unsorted = take(R * 4);
-    L.s_keys_a = take(R * 8);
-    L.s_keys_b = take(R * 8);
+    L.s_keys_a = take(R * 4);
+    L.s_keys_b = take(R * 4);
     L.s_vals_b = take(R * 4);
     L.s_hist = take(8 * 256 * 4);
     L.s_ticket = take(128);
     L.s_status = take((uint64_t)L.sort_passes * L.sort_tiles * 256 * 4);
-    L.off.s_keys_sorted = L.s_keys_a;
+    L.s_zero_bytes = (L.s_status - L.s_hist) + (uint64_t)L.sort_passes * L.sort_tiles * 256 * 4;
+    L.off.s_tiles_sorted = L.s_keys_a;
     L.size.sort_bytes = align_up(o, 128) + 128;
     return L;
 }
 
 // launchers defined in the kernel files
 int launch_preprocess(const GigsRasterFwd* a, const Layout& L, cudaStream_t st, const float* sh_rest);
-int launch_emit_keys(const GigsRasterFwd* a, const Layout& L, uint64_t* keys, uint32_t* vals, cudaStream_t st);
-int launch_tile_ranges(uint64_t R, const uint64_t* keys_sorted, uint2* ranges, uint32_t num_tiles, cudaStream_t st);
+int launch_depth_argsort(const GigsRasterFwd* a, const Layout& L, cudaStream_t st);
+int launch_emit_keys(const GigsRasterFwd* a, const Layout& L, uint32_t* keys, uint32_t* vals, cudaStream_t st);
+int launch_tile_ranges(uint64_t R, const uint32_t* tiles_sorted, uint2* ranges, uint32_t num_tiles, cudaStream_t st);
 int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t st);
-int launch_radix_sort(uint64_t R, int end_bit, const uint64_t* keys_u, const uint32_t* vals_u, uint64_t* keys_a,
-                      uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, uint32_t* hist, uint32_t* status,
-                      uint32_t* tickets, uint64_t status_bytes_total, cudaStream_t st);
+int launch_radix_sort32(uint64_t R, int end_bit, const uint32_t* keys_u, const uint32_t* vals_u, uint32_t* keys_a,
+                        uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint32_t* hist, uint32_t* status,
+                        uint32_t* tickets, uint64_t zero_bytes, int pass_stage, cudaStream_t st);
 int launch_blend_forward(const GigsRasterFwd* a, const Layout& L, bool lite, cudaStream_t st);
 int launch_blend_backward(const GigsRasterBwd* a, const Layout& L, cudaStream_t st);
 int launch_gaussian_backward(const GigsRasterBwd* a, const Layout& L, cudaStream_t st);
@@ -137,6 +151,26 @@ static int check_common(int P, const GigsCamera& c)
     if (P < 0) { set_error("P must be >= 0"); return -1; }
     if (c.width <= 0 || c.height <= 0) { set_error("image size must be positive"); return -1; }
     if (!c.viewmatrix || !c.projmatrix || !c.campos || !c.bg) { set_error("camera pointers must not be NULL"); return -1; }
+    return 0;
+}
+
+// Copies num_rendered to the host and waits for THAT copy only: the depth argsort of the Gaussians (which does not
+// depend on num_rendered) is queued behind the copy, so the GPU keeps working while the host sizes the binning blob.
+int read_back_num_rendered(GigsRasterFwd* a, const Layout& L, cudaStream_t st)
+{
+    static thread_local cudaEvent_t ev = nullptr;
+    if (!ev) GIGS_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    static thread_local uint32_t* pinned = nullptr;
+    if (!a->pinned_num_rendered && !pinned) GIGS_CUDA(cudaMallocHost((void**)&pinned, 64));
+    uint32_t* dst = a->pinned_num_rendered ? a->pinned_num_rendered : pinned;
+    GIGS_CUDA(cudaMemcpyAsync(dst, (char*)a->geom + L.off.g_num_rendered, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    GIGS_CUDA(cudaEventRecord(ev, st));
+    {
+        ProfScope ps(ST_DEPTH_SORT, st);
+        if (int e = launch_depth_argsort(a, L, st)) return e;
+    }
+    GIGS_CUDA(cudaEventSynchronize(ev));
+    a->num_rendered = (int64_t)*dst;
     return 0;
 }
 
@@ -172,7 +206,7 @@ int forward_finish_impl(GigsRasterFwd* a, bool lite)
     char* sc = (char*)a->sort;
     char* im = (char*)a->img;
     char* bn = (char*)a->binning;
-    uint64_t* keys_u = (uint64_t*)(sc + L.off.s_keys_unsorted);
+    uint32_t* keys_u = (uint32_t*)(sc + L.off.s_tiles_unsorted);
     uint32_t* vals_u = (uint32_t*)(sc + L.off.s_vals_unsorted);
     if (a->P > 0 && R > 0) {
         {
@@ -180,16 +214,15 @@ int forward_finish_impl(GigsRasterFwd* a, bool lite)
             if (int e = launch_emit_keys(a, L, keys_u, vals_u, st)) return e;
         }
         ProfScope ps(ST_SORT, st);
-        const uint64_t status_total = (L.s_status - L.s_hist) + (uint64_t)L.sort_passes * L.sort_tiles * 256 * 4;
-        if (int e = launch_radix_sort(R, (int)L.sort_bits, keys_u, vals_u, (uint64_t*)(sc + L.s_keys_a),
-                                      (uint32_t*)(bn + L.off.b_point_list), (uint64_t*)(sc + L.s_keys_b),
-                                      (uint32_t*)(sc + L.s_vals_b), (uint32_t*)(sc + L.s_hist),
-                                      (uint32_t*)(sc + L.s_status), (uint32_t*)(sc + L.s_ticket), status_total, st))
+        if (int e = launch_radix_sort32(R, (int)L.sort_bits, keys_u, vals_u, (uint32_t*)(sc + L.s_keys_a),
+                                        (uint32_t*)(bn + L.off.b_point_list), (uint32_t*)(sc + L.s_keys_b),
+                                        (uint32_t*)(sc + L.s_vals_b), (uint32_t*)(sc + L.s_hist),
+                                        (uint32_t*)(sc + L.s_status), (uint32_t*)(sc + L.s_ticket), L.s_zero_bytes, ST_SORT_PASS, st))
             return e;
     }
     {
         ProfScope ps(ST_RANGES, st);
-        if (int e = launch_tile_ranges(R, (const uint64_t*)(sc + L.s_keys_a), (uint2*)(im + L.off.i_ranges), L.num_tiles, st))
+        if (int e = launch_tile_ranges(R, (const uint32_t*)(sc + L.s_keys_a), (uint2*)(im + L.off.i_ranges), L.num_tiles, st))
             return e;
     }
     {
@@ -288,11 +321,7 @@ int gigs_raster_forward_begin(GigsRasterFwd* a)
         ProfScope ps(ST_PREPROCESS, st);
         if (int e = launch_preprocess(a, L, st, nullptr)) return e;
     }
-    uint32_t hostR = 0;
-    uint32_t* dst = a->pinned_num_rendered ? a->pinned_num_rendered : &hostR;
-    GIGS_CUDA(cudaMemcpyAsync(dst, (char*)a->geom + L.off.g_num_rendered, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    GIGS_CUDA(cudaStreamSynchronize(st));
-    a->num_rendered = (int64_t)*dst;
+    if (int e = read_back_num_rendered(a, L, st)) return e;
     return 0;
 }
 

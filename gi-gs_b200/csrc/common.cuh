@@ -53,7 +53,7 @@ int cuda_fail(cudaError_t e, const char* what);
 enum Stage : int {
     ST_PREPROCESS = 0, ST_EMIT_KEYS, ST_SORT, ST_RANGES, ST_BLEND_FWD, ST_BLEND_BWD, ST_GAUSS_BWD, ST_GEOM_CHAIN,
     ST_SSAO, ST_SSR, ST_SHADE_FWD, ST_SHADE_BWD, ST_MEDIAN, ST_MEDIAN_BWD, ST_BILATERAL, ST_D2N, ST_SSR_BWD, ST_DIST2,
-    ST_DEFER_SHADE, ST_DEFER_LOSS, ST_DEFER_BWD, ST_PARAM_GRAD, ST_SORT_PASS
+    ST_DEFER_SHADE, ST_DEFER_LOSS, ST_DEFER_BWD, ST_PARAM_GRAD, ST_SORT_PASS, ST_DEPTH_SORT
 };
 int prof_begin(int stage, cudaStream_t st);   // returns a token (<0 when profiling is off)
 void prof_end(int token, cudaStream_t st);
@@ -73,12 +73,16 @@ struct Layout {
     GigsLayout off;
     GigsSizes size;
     uint32_t tiles_x, tiles_y, num_tiles, num_blocks;
-    // sort scratch internals
-    uint64_t s_keys_a, s_keys_b, s_vals_b, s_hist, s_status, s_ticket;
+    // instance sort (by tile id) scratch internals
+    uint64_t s_keys_a, s_keys_b, s_vals_b, s_hist, s_status, s_ticket, s_zero_bytes;
     uint32_t sort_tiles, sort_passes, sort_bits;
+    // Gaussian depth argsort internals (geom blob) + block sums of tiles_touched in depth order
+    uint64_t p_keys_a, p_keys_b, p_vals_b, p_hist, p_status, p_ticket, p_zero_bytes, g_block_sums2;
 };
 Layout make_layout(int P, int W, int H, uint64_t R);
 uint32_t higher_msb(uint32_t n);
+int radix_digit_bits(int bits);
+int radix_sort_passes(int bits);
 
 // ---------------------------------------------------------------------------------------------
 // Minimal column-major 3x3 matrix with the SAME expression shapes as the math library the

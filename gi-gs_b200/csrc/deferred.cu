@@ -25,6 +25,7 @@ namespace gigs {
 
 int launch_preprocess(const GigsRasterFwd* a, const Layout& L, cudaStream_t st, const float* sh_rest);
 int forward_finish_impl(GigsRasterFwd* a, bool lite);
+int read_back_num_rendered(GigsRasterFwd* a, const Layout& L, cudaStream_t st);
 int launch_blend_backward(const GigsRasterBwd* a, const Layout& L, cudaStream_t st);
 
 constexpr int DF_TW = 32, DF_TH = 8;              // output tile of one CTA pass (256 threads, a warp = one row)
@@ -541,11 +542,8 @@ int gigs_frame_forward(GigsFrame* f)
             ProfScope ps(ST_PREPROCESS, st);
             if (int e = launch_preprocess(&a, L0, st, f->raw_params ? (f->sh_rest ? f->sh_rest : f->sh_dc) : nullptr)) return e;
         }
-        uint32_t hostR = 0;
-        uint32_t* dst = f->pinned_num_rendered ? f->pinned_num_rendered : &hostR;
-        GIGS_CUDA(cudaMemcpyAsync(dst, (char*)f->geom + L0.off.g_num_rendered, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        GIGS_CUDA(cudaStreamSynchronize(st));
-        f->num_rendered = (int64_t)*dst;
+        if (int e = read_back_num_rendered(&a, L0, st)) return e;
+        f->num_rendered = a.num_rendered;
     }
     a.num_rendered = f->num_rendered;
     const Layout L = make_layout(f->P, c.width, c.height, (uint64_t)f->num_rendered);

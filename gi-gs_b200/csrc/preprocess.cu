@@ -6,7 +6,8 @@
 //   cuda_rasterizer/forward.cu:83-122   2D covariance (EWA)
 //   cuda_rasterizer/forward.cu:127-161  3D covariance from scale/quaternion
 //   cuda_rasterizer/forward.cu:164-276  preprocess
-//   cuda_rasterizer/rasterizer_impl.cu:70-138  duplicateWithKeys / identifyTileRanges
+//   cuda_rasterizer/rasterizer_impl.cu:70-138  duplicateWithKeys / identifyTileRanges (here: depth argsort of the
+//                                              Gaussians + (tile, id) pair emission in depth order, see radix_sort.cu)
 //   cuda_rasterizer/auxiliary.h:41-66,150-176  ndc2Pix, getRect, transforms, in_frustum
 // The *expression order* is kept identical on purpose: tile keys (depth bits, rects) must be
 // bit-exact, which requires nvcc to contract the same FMAs. The data flow is ours: one packed 96-B
@@ -141,7 +142,7 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
                   // outputs
                   int* __restrict__ radii, float* __restrict__ records, float* __restrict__ cov3Ds,
                   uint8_t* __restrict__ clamped, uint32_t* __restrict__ tiles_touched,
-                  uint32_t* __restrict__ block_sums)
+                  uint32_t* __restrict__ depth_keys, uint32_t* __restrict__ block_sums)
 {
     __shared__ float sV[16], sPM[16], sCam[3];
     __shared__ uint32_t s_warp_sum[PRE_THREADS / 32];
@@ -156,6 +157,7 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
     uint32_t touched = 0;
     if (idx < P) {
         int my_radius_i = 0;
+        uint32_t depth_key = 0xffffffffu;  // Gaussians that emit nothing sort last
         do {
             const float3 p_orig = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
             // near culling (auxiliary.h:150-176); no x/y frustum test in this fork
@@ -219,6 +221,7 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
 
             my_radius_i = (int)my_radius;
             touched = (rect_max.y - rect_min.y) * (rect_max.x - rect_min.x);
+            depth_key = __float_as_uint(p_view.z);  // the low 32 bits of the reference's key (rasterizer_impl.cu:104)
 
             const float op = RAW ? act_sigmoid(opacities[idx]) : opacities[idx];
             float4* rec = reinterpret_cast<float4*>(records + (size_t)idx * REC_FLOATS);
@@ -247,6 +250,7 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
         } while (false);
         radii[idx] = my_radius_i;
         tiles_touched[idx] = touched;
+        depth_keys[idx] = depth_key;
     }
 
     // fused block sum of tiles_touched (feeds the single-block scan of block sums)
@@ -305,32 +309,54 @@ __global__ void __launch_bounds__(1024) scan_block_sums_kernel(uint32_t* __restr
     if (threadIdx.x == 0) *total = s_carry;
 }
 
-// Key/value emission. One block = the same 256-Gaussian chunk as in preprocess; offsets are
-// block_offset + in-block exclusive scan. Each warp flattens its 32 Gaussians' tile lists and the
-// lanes emit consecutive entries (coalesced 8-B key / 4-B value stores), instead of one thread
-// looping over its whole rect.
+// Block sums of tiles_touched taken in DEPTH order (order[] = argsort of the depth keys): feeds the same
+// single-block scan as the index-order sums of preprocess.
 __global__ void __launch_bounds__(PRE_THREADS)
-emit_keys_kernel(const int P, const int* __restrict__ radii, const float* __restrict__ records,
-                 const uint32_t* __restrict__ tiles_touched, const uint32_t* __restrict__ block_offsets,
-                 const uint32_t grid_x, const uint32_t grid_y, uint32_t* __restrict__ point_offsets,
-                 uint64_t* __restrict__ keys, uint32_t* __restrict__ vals)
+ordered_block_sums_kernel(const int P, const uint32_t* __restrict__ order, const uint32_t* __restrict__ tiles_touched,
+                          uint32_t* __restrict__ block_sums)
+{
+    __shared__ uint32_t s_warp_sum[PRE_THREADS / 32];
+    const int i = blockIdx.x * PRE_THREADS + threadIdx.x;
+    uint32_t v = (i < P) ? tiles_touched[order[i]] : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) s_warp_sum[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int w = 0; w < PRE_THREADS / 32; ++w) t += s_warp_sum[w];
+        block_sums[blockIdx.x] = t;
+    }
+}
+
+// (tile id, Gaussian id) pair emission in depth order. Thread i of the grid owns the i-th Gaussian of the depth
+// argsort; offsets are block_offset + in-block exclusive scan. Each warp flattens its 32 Gaussians' tile lists and
+// the lanes emit consecutive entries (coalesced 4-B stores), instead of one thread looping over its whole rect.
+// Because the pairs leave here ordered by (depth bits, Gaussian id), the stable sort by tile id that follows yields
+// the reference's (tile, depth) order without ever materialising or moving the 64-bit keys.
+__global__ void __launch_bounds__(PRE_THREADS)
+emit_keys_kernel(const int P, const uint32_t* __restrict__ order, const int* __restrict__ radii,
+                 const float* __restrict__ records, const uint32_t* __restrict__ tiles_touched,
+                 const uint32_t* __restrict__ block_offsets, const uint32_t grid_x, const uint32_t grid_y,
+                 uint32_t* __restrict__ keys, uint32_t* __restrict__ vals)
 {
     __shared__ uint32_t s_warp_tot[PRE_THREADS / 32];
     __shared__ uint32_t s_pref[PRE_THREADS / 32][32];
-    __shared__ uint4 s_info[PRE_THREADS / 32][32];  // rect_min.x, rect_min.y, rect width, depth bits
+    __shared__ uint4 s_info[PRE_THREADS / 32][32];  // rect_min.x, rect_min.y, rect width, Gaussian id
 
-    const int idx = blockIdx.x * PRE_THREADS + threadIdx.x;
+    const int i = blockIdx.x * PRE_THREADS + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t cnt = 0;
     uint4 info = make_uint4(0, 0, 0, 0);
-    if (idx < P) {
+    if (i < P) {
+        const uint32_t idx = order[i];
         cnt = tiles_touched[idx];
         if (cnt > 0) {
-            const float4 q0 = *reinterpret_cast<const float4*>(records + (size_t)idx * REC_FLOATS);
-            const float4 q1 = *reinterpret_cast<const float4*>(records + (size_t)idx * REC_FLOATS + 4);
+            const float2 q0 = *reinterpret_cast<const float2*>(records + (size_t)idx * REC_FLOATS);
             uint2 rmin, rmax;
             tile_rect(q0.x, q0.y, radii[idx], grid_x, grid_y, rmin, rmax);
-            info = make_uint4(rmin.x, rmin.y, rmax.x - rmin.x, __float_as_uint(q1.z));
+            info = make_uint4(rmin.x, rmin.y, rmax.x - rmin.x, idx);
         }
     }
     // warp inclusive scan
@@ -346,10 +372,8 @@ emit_keys_kernel(const int P, const int* __restrict__ radii, const float* __rest
     __syncthreads();
     uint32_t warp_off = block_offsets[blockIdx.x];
     for (int w = 0; w < warp; ++w) warp_off += s_warp_tot[w];
-    if (idx < P) point_offsets[idx] = warp_off + inc;
 
     const uint32_t E = s_warp_tot[warp];
-    const int gbase = blockIdx.x * PRE_THREADS + warp * 32;
     for (uint32_t e = lane; e < E; e += 32) {
         // last g in [0,32) with pref[g] <= e
         int g = 0;
@@ -360,25 +384,22 @@ emit_keys_kernel(const int P, const int* __restrict__ radii, const float* __rest
         const uint32_t k = e - s_pref[warp][g];
         const uint32_t ty = inf.y + k / inf.z;
         const uint32_t tx = inf.x + k % inf.z;
-        uint64_t key = (uint64_t)(ty * grid_x + tx);
-        key <<= 32;
-        key |= (uint64_t)inf.w;
-        keys[(size_t)warp_off + e] = key;
-        vals[(size_t)warp_off + e] = (uint32_t)(gbase + g);
+        keys[(size_t)warp_off + e] = ty * grid_x + tx;
+        vals[(size_t)warp_off + e] = inf.w;
     }
 }
 
 // Tile ranges from the sorted keys (rasterizer_impl.cu:117-138). ranges must be zeroed first.
 __global__ void __launch_bounds__(256)
-tile_ranges_kernel(const uint32_t L, const uint64_t* __restrict__ keys, uint2* __restrict__ ranges)
+tile_ranges_kernel(const uint32_t L, const uint32_t* __restrict__ tiles, uint2* __restrict__ ranges)
 {
     const uint32_t idx = blockIdx.x * 256 + threadIdx.x;
     if (idx >= L) return;
-    const uint32_t cur = (uint32_t)(keys[idx] >> 32);
+    const uint32_t cur = tiles[idx];
     if (idx == 0)
         ranges[cur].x = 0;
     else {
-        const uint32_t prev = (uint32_t)(keys[idx - 1] >> 32);
+        const uint32_t prev = tiles[idx - 1];
         if (cur != prev) {
             ranges[prev].y = idx;
             ranges[cur].x = idx;
@@ -415,7 +436,8 @@ int launch_preprocess(const GigsRasterFwd* a, const Layout& L, cudaStream_t st, 
         a->cov3D_precomp, a->colors_precomp, a->normal, a->albedo, a->roughness, a->metallic, c.viewmatrix,           \
         c.projmatrix, c.campos, c.width, c.height, c.tan_fovx, c.tan_fovy, focal_x, focal_y, L.tiles_x, L.tiles_y,    \
         c.prefiltered != 0, a->radii, (float*)(g + L.off.g_record), (float*)(g + L.off.g_cov3D),                      \
-        (uint8_t*)(g + L.off.g_clamped), (uint32_t*)(g + L.off.g_tiles_touched), (uint32_t*)(g + L.off.g_block_sums)
+        (uint8_t*)(g + L.off.g_clamped), (uint32_t*)(g + L.off.g_tiles_touched), (uint32_t*)(g + L.off.g_depth_keys), \
+        (uint32_t*)(g + L.off.g_block_sums)
     if (sh_rest != nullptr)
         preprocess_kernel<true><<<L.num_blocks, PRE_THREADS, 0, st>>>(PRE_ARGS);
     else
@@ -428,22 +450,41 @@ int launch_preprocess(const GigsRasterFwd* a, const Layout& L, cudaStream_t st, 
     return 0;
 }
 
-int launch_emit_keys(const GigsRasterFwd* a, const Layout& L, uint64_t* keys, uint32_t* vals, cudaStream_t st)
+int launch_radix_sort32(uint64_t R, int end_bit, const uint32_t* keys_u, const uint32_t* vals_u, uint32_t* keys_a,
+                        uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint32_t* hist, uint32_t* status,
+                        uint32_t* tickets, uint64_t zero_bytes, int pass_stage, cudaStream_t st);
+
+// argsort of the Gaussians by depth bits (stable: ties keep ascending Gaussian index) -> g_order
+int launch_depth_argsort(const GigsRasterFwd* a, const Layout& L, cudaStream_t st)
 {
     char* g = (char*)a->geom;
-    emit_keys_kernel<<<L.num_blocks, PRE_THREADS, 0, st>>>(
-        a->P, a->radii, (const float*)(g + L.off.g_record), (const uint32_t*)(g + L.off.g_tiles_touched),
-        (const uint32_t*)(g + L.off.g_block_sums), L.tiles_x, L.tiles_y, (uint32_t*)(g + L.off.g_point_offsets), keys,
-        vals);
+    return launch_radix_sort32((uint64_t)a->P, 32, (const uint32_t*)(g + L.off.g_depth_keys), nullptr,
+                               (uint32_t*)(g + L.p_keys_a), (uint32_t*)(g + L.off.g_order), (uint32_t*)(g + L.p_keys_b),
+                               (uint32_t*)(g + L.p_vals_b), (uint32_t*)(g + L.p_hist), (uint32_t*)(g + L.p_status),
+                               (uint32_t*)(g + L.p_ticket), L.p_zero_bytes, -1, st);
+}
+
+int launch_emit_keys(const GigsRasterFwd* a, const Layout& L, uint32_t* keys, uint32_t* vals, cudaStream_t st)
+{
+    char* g = (char*)a->geom;
+    const uint32_t* order = (const uint32_t*)(g + L.off.g_order);
+    const uint32_t* touched = (const uint32_t*)(g + L.off.g_tiles_touched);
+    uint32_t* sums2 = (uint32_t*)(g + L.g_block_sums2);
+    ordered_block_sums_kernel<<<L.num_blocks, PRE_THREADS, 0, st>>>(a->P, order, touched, sums2);
+    GIGS_LAUNCH_CHECK("ordered_block_sums_kernel");
+    scan_block_sums_kernel<<<1, 1024, 0, st>>>(sums2, (int)L.num_blocks, sums2 + L.num_blocks);
+    GIGS_LAUNCH_CHECK("scan_block_sums_kernel");
+    emit_keys_kernel<<<L.num_blocks, PRE_THREADS, 0, st>>>(a->P, order, a->radii, (const float*)(g + L.off.g_record),
+                                                          touched, sums2, L.tiles_x, L.tiles_y, keys, vals);
     GIGS_LAUNCH_CHECK("emit_keys_kernel");
     return 0;
 }
 
-int launch_tile_ranges(uint64_t R, const uint64_t* keys_sorted, uint2* ranges, uint32_t num_tiles, cudaStream_t st)
+int launch_tile_ranges(uint64_t R, const uint32_t* tiles_sorted, uint2* ranges, uint32_t num_tiles, cudaStream_t st)
 {
     GIGS_CUDA(cudaMemsetAsync(ranges, 0, (size_t)num_tiles * sizeof(uint2), st));
     if (R > 0) {
-        tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>((uint32_t)R, keys_sorted, ranges);
+        tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>((uint32_t)R, tiles_sorted, ranges);
         GIGS_LAUNCH_CHECK("tile_ranges_kernel");
     }
     return 0;

@@ -1,52 +1,61 @@
-// Onesweep LSD radix sort of (u64 key, u32 value) pairs — replaces cub::DeviceRadixSort::SortPairs at
-// reference cuda_rasterizer/rasterizer_impl.cu:612-617. Stable, so the result is bit-identical to any
-// other stable sort on the same key bits [0, end_bit).
+// Onesweep LSD radix sort of (key, u32 value) pairs, keys u32 or u64, digits of 6/7/8 bits.
 //
-// Structure (Adinets & Merrill, "Onesweep"): one histogram kernel computes the digit histograms of ALL
-// passes in a single read of the keys; each pass is then ONE kernel that ranks a 4096-key tile in
-// shared memory, resolves its global digit offsets with a decoupled look-back over the preceding
-// tiles (chained scan, tiles ordered by an atomic ticket so look-back never waits on a tile that has
-// not started), and scatters key+value together. HBM traffic per pass = read 12 B + write 12 B per pair.
+// The reference sorts R (tile << 32 | depth) keys with cub::DeviceRadixSort::SortPairs over 32 + log2(tiles) bits
+// (cuda_rasterizer/rasterizer_impl.cu:612-617): 6 passes x 24 B per instance at 800x800. Here the same ordering is
+// produced by two much smaller sorts (see preprocess.cu / api.cu):
+//   1. the P Gaussians are sorted by their 32 depth bits (4 passes over P pairs of 8 B), instances are then EMITTED
+//      in that order, and
+//   2. the R instances are sorted by tile id only (12 bits at 800x800: 2 passes of 6-bit digits over 8-B pairs).
+// Both sorts are stable, so the composition equals the stable sort on the full 44-bit key bit for bit (ties: same
+// tile and same depth bits -> ascending Gaussian index, exactly what stability gives the reference).
+//
+// Structure of a pass (Adinets & Merrill, "Onesweep"): one histogram kernel computes the digit histograms of ALL
+// passes in a single read of the keys; each pass is then ONE kernel that ranks a tile of keys in shared memory
+// (match.any multisplit per warp), resolves its global digit offsets with a decoupled look-back over the preceding
+// tiles (chained scan, tiles ordered by an atomic ticket so look-back never waits on a tile that has not started),
+// and scatters key+value together through shared memory so global stores are coalesced runs.
 #include <cstdlib>
 #include "common.cuh"
 
 namespace gigs {
 
-constexpr int RS_HTHREADS = 256;  // histogram kernel
-constexpr int RS_RADIX = 256;
+constexpr int RS_HTHREADS = 256;   // histogram kernel
+constexpr int RS_MAX_RADIX = 256;  // histogram / status rows are laid out for 8-bit digits
 constexpr int RS_MAX_PASSES = 8;
+constexpr int RS_MIN_TILE = 2048;  // smallest tile of any configuration: sizes the look-back status array
 
 constexpr uint32_t FLAG_AGG = 1u, FLAG_INC = 2u;
 
+template <typename K>
 __global__ void __launch_bounds__(RS_HTHREADS)
-rs_histogram_kernel(const uint64_t* __restrict__ keys, const uint32_t n, const int passes, const int end_bit,
+rs_histogram_kernel(const K* __restrict__ keys, const uint32_t n, const int passes, const int digit_bits, const int end_bit,
                     uint32_t* __restrict__ hist /*[passes][256]*/)
 {
-    __shared__ uint32_t s_hist[RS_MAX_PASSES][RS_RADIX];
-    for (int i = threadIdx.x; i < passes * RS_RADIX; i += RS_HTHREADS) (&s_hist[0][0])[i] = 0;
+    __shared__ uint32_t s_hist[RS_MAX_PASSES][RS_MAX_RADIX];
+    for (int i = threadIdx.x; i < passes * RS_MAX_RADIX; i += RS_HTHREADS) (&s_hist[0][0])[i] = 0;
     __syncthreads();
     const uint32_t stride = gridDim.x * RS_HTHREADS;
     for (uint32_t i = blockIdx.x * RS_HTHREADS + threadIdx.x; i < n; i += stride) {
-        const uint64_t k = keys[i];
+        const K k = keys[i];
         for (int p = 0; p < passes; ++p) {
-            const int shift = p * 8;
-            const int bits = min(8, end_bit - shift);
+            const int shift = p * digit_bits;
+            const int bits = min(digit_bits, end_bit - shift);
             const uint32_t d = (uint32_t)(k >> shift) & ((1u << bits) - 1u);
             atomicAdd(&s_hist[p][d], 1u);
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < passes * RS_RADIX; i += RS_HTHREADS) {
+    for (int i = threadIdx.x; i < passes * RS_MAX_RADIX; i += RS_HTHREADS) {
         const uint32_t v = (&s_hist[0][0])[i];
         if (v) atomicAdd(&hist[i], v);
     }
 }
 
 // exclusive scan of each pass's 256-bin histogram (in place)
-__global__ void __launch_bounds__(RS_RADIX) rs_scan_hist_kernel(uint32_t* __restrict__ hist)
+__global__ void __launch_bounds__(RS_MAX_RADIX) rs_scan_hist_kernel(uint32_t* __restrict__ hist)
 {
-    __shared__ uint32_t s_warp[RS_RADIX / 32];
-    uint32_t* h = hist + blockIdx.x * RS_RADIX;
+    __shared__ uint32_t s_warp[RS_MAX_RADIX / 32];
+    uint32_t* h = hist + blockIdx.x * RS_MAX_RADIX;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t v = h[threadIdx.x];
     uint32_t inc = v;
@@ -62,53 +71,56 @@ __global__ void __launch_bounds__(RS_RADIX) rs_scan_hist_kernel(uint32_t* __rest
     h[threadIdx.x] = off + inc - v;
 }
 
-template <int RS_THREADS, int RS_ITEMS>
+template <typename K, int BITS, int THREADS, int ITEMS>
 struct RsSmem {
-    static constexpr int RS_WARPS = RS_THREADS / 32;
-    static constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
-    uint64_t keys[RS_TILE];
-    uint32_t vals[RS_TILE];
-    uint32_t warp_hist[RS_WARPS][RS_RADIX];
-    uint32_t digit_start[RS_RADIX];
-    uint32_t global_off[RS_RADIX];
-    uint32_t warp_tot[RS_RADIX / 32];
+    static constexpr int RADIX = 1 << BITS;
+    static constexpr int WARPS = THREADS / 32;
+    static constexpr int TILE = THREADS * ITEMS;
+    K keys[TILE];
+    uint32_t vals[TILE];
+    uint32_t warp_hist[WARPS][RADIX];
+    uint32_t digit_start[RADIX];
+    uint32_t global_off[RADIX];
+    uint32_t warp_tot[RADIX / 32];
     uint32_t tile;
 };
 
-template <int RS_THREADS, int RS_ITEMS>
-__global__ void __launch_bounds__(RS_THREADS)
-rs_onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out,
-                   const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out, const uint32_t n,
-                   const int shift, const uint32_t digit_mask, const uint32_t* __restrict__ digit_base,
-                   volatile uint32_t* __restrict__ status /*[tiles][256]*/, uint32_t* __restrict__ ticket)
+// vals_in == nullptr: the value of element i is i (first pass of an argsort; saves materialising an iota)
+template <typename K, int BITS, int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS)
+rs_onesweep_kernel(const K* __restrict__ keys_in, K* __restrict__ keys_out, const uint32_t* __restrict__ vals_in,
+                   uint32_t* __restrict__ vals_out, const uint32_t n, const int shift, const uint32_t digit_mask,
+                   const uint32_t* __restrict__ digit_base, volatile uint32_t* __restrict__ status /*[tiles][RADIX]*/,
+                   uint32_t* __restrict__ ticket)
 {
-    constexpr int RS_WARPS = RS_THREADS / 32;
-    constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
+    using Smem = RsSmem<K, BITS, THREADS, ITEMS>;
+    constexpr int RADIX = Smem::RADIX, WARPS = Smem::WARPS, TILE = Smem::TILE;
+    static_assert(RADIX % 32 == 0 && RADIX <= THREADS, "digit threads must be whole warps of the block");
     extern __shared__ __align__(16) unsigned char rs_smem_raw[];
-    RsSmem<RS_THREADS, RS_ITEMS>& S = *reinterpret_cast<RsSmem<RS_THREADS, RS_ITEMS>*>(rs_smem_raw);
+    Smem& S = *reinterpret_cast<Smem*>(rs_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     if (tid == 0) S.tile = atomicAdd(ticket, 1u);
-    for (int i = tid; i < RS_WARPS * RS_RADIX; i += RS_THREADS) (&S.warp_hist[0][0])[i] = 0;
+    for (int i = tid; i < WARPS * RADIX; i += THREADS) (&S.warp_hist[0][0])[i] = 0;
     __syncthreads();
     const uint32_t tile = S.tile;
-    const uint32_t base = tile * (uint32_t)RS_TILE;
-    const uint32_t count = min((uint32_t)RS_TILE, n - base);
+    const uint32_t base = tile * (uint32_t)TILE;
+    const uint32_t count = min((uint32_t)TILE, n - base);
 
-    // warp-striped load: item i of lane l in warp w = base + w*512 + i*32 + l (keeps stability)
-    uint64_t key[RS_ITEMS];
-    uint16_t rank[RS_ITEMS];
-    const uint32_t wbase = warp * (32 * RS_ITEMS) + lane;
+    // warp-striped load: item i of lane l in warp w = base + w*32*ITEMS + i*32 + l (keeps stability)
+    K key[ITEMS];
+    uint16_t rank[ITEMS];
+    const uint32_t wbase = warp * (32 * ITEMS) + lane;
 #pragma unroll
-    for (int i = 0; i < RS_ITEMS; ++i) {
+    for (int i = 0; i < ITEMS; ++i) {
         const uint32_t loc = wbase + i * 32;
-        key[i] = (loc < count) ? keys_in[base + loc] : ~0ull;
+        key[i] = (loc < count) ? keys_in[base + loc] : (K)~(K)0;
     }
 
     // rank keys within the warp, item by item (match-any multisplit)
     const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
-    for (int i = 0; i < RS_ITEMS; ++i) {
+    for (int i = 0; i < ITEMS; ++i) {
         const uint32_t loc = wbase + i * 32;
         const bool valid = loc < count;
         const uint32_t d = valid ? ((uint32_t)(key[i] >> shift) & digit_mask) : 0xffffffffu;
@@ -126,24 +138,24 @@ rs_onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ 
     __syncthreads();
 
     // values are fetched now so that their latency overlaps the look-back below
-    uint32_t val[RS_ITEMS];
+    uint32_t val[ITEMS];
 #pragma unroll
-    for (int i = 0; i < RS_ITEMS; ++i) {
+    for (int i = 0; i < ITEMS; ++i) {
         const uint32_t loc = wbase + i * 32;
-        val[i] = (loc < count) ? vals_in[base + loc] : 0u;
+        val[i] = (loc < count) ? (vals_in ? vals_in[base + loc] : base + loc) : 0u;
     }
 
     // thread d: exclusive scan over the warps' counts of digit d; tile total; look-back
-    if (tid < RS_RADIX) {
+    if (tid < RADIX) {
         const int d = tid;
         uint32_t sum = 0;
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; ++w) {
+        for (int w = 0; w < WARPS; ++w) {
             const uint32_t t = S.warp_hist[w][d];
             S.warp_hist[w][d] = sum;
             sum += t;
         }
-        volatile uint32_t* my_status = status + (size_t)tile * RS_RADIX + d;
+        volatile uint32_t* my_status = status + (size_t)tile * RADIX + d;
         uint32_t excl = 0;
         if (tile == 0) {
             *my_status = (sum << 2) | FLAG_INC;
@@ -153,7 +165,7 @@ rs_onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ 
             while (true) {
                 uint32_t v;
                 do {
-                    v = status[(size_t)t * RS_RADIX + d];
+                    v = status[(size_t)t * RADIX + d];
                 } while ((v & 3u) == 0u);
                 excl += v >> 2;
                 if (v & FLAG_INC) break;
@@ -161,7 +173,7 @@ rs_onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ 
             }
             *my_status = ((excl + sum) << 2) | FLAG_INC;
         }
-        // block exclusive scan of the tile's digit totals -> position of each digit inside the tile
+        // exclusive scan of the tile's digit totals -> position of each digit inside the tile
         uint32_t inc = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -169,8 +181,8 @@ rs_onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ 
             if (lane >= o) inc += t;
         }
         if (lane == 31) S.warp_tot[warp] = inc;
-        // barrier among the RS_RADIX digit threads only (the block may be larger)
-        asm volatile("bar.sync 1, %0;" ::"n"(RS_RADIX) : "memory");
+        // barrier among the RADIX digit threads only (the block is larger)
+        asm volatile("bar.sync 1, %0;" ::"n"(RADIX) : "memory");
         uint32_t woff = 0;
         for (int w = 0; w < warp; ++w) woff += S.warp_tot[w];
         const uint32_t dstart = woff + inc - sum;
@@ -181,7 +193,7 @@ rs_onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ 
 
     // scatter keys into tile-sorted order in shared memory
 #pragma unroll
-    for (int i = 0; i < RS_ITEMS; ++i) {
+    for (int i = 0; i < ITEMS; ++i) {
         const uint32_t loc = wbase + i * 32;
         if (loc < count) {
             const uint32_t d = (uint32_t)(key[i] >> shift) & digit_mask;
@@ -192,14 +204,14 @@ rs_onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ 
     }
     // values follow the same permutation
 #pragma unroll
-    for (int i = 0; i < RS_ITEMS; ++i) {
+    for (int i = 0; i < ITEMS; ++i) {
         const uint32_t loc = wbase + i * 32;
         if (loc < count) S.vals[rank[i]] = val[i];
     }
     __syncthreads();
     // coalesced write-out: consecutive smem positions of one digit go to consecutive global slots
-    for (uint32_t p = tid; p < count; p += RS_THREADS) {
-        const uint64_t k = S.keys[p];
+    for (uint32_t p = tid; p < count; p += THREADS) {
+        const K k = S.keys[p];
         const uint32_t d = (uint32_t)(k >> shift) & digit_mask;
         const uint32_t g = S.global_off[d] + p;
         keys_out[g] = k;
@@ -207,34 +219,34 @@ rs_onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ 
     }
 }
 
-template <int T, int I>
-static int launch_passes(uint32_t n, int end_bit, const uint64_t* keys_u, const uint32_t* vals_u, uint64_t* keys_a,
-                         uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, uint32_t* hist, uint32_t* status,
-                         uint32_t* tickets, uint32_t status_tiles, cudaStream_t st)
+template <typename K, int BITS, int T, int I>
+static int launch_passes(uint32_t n, int end_bit, const K* keys_u, const uint32_t* vals_u, K* keys_a, uint32_t* vals_a,
+                         K* keys_b, uint32_t* vals_b, uint32_t* hist, uint32_t* status, uint32_t* tickets,
+                         uint32_t status_tiles, int pass_stage, cudaStream_t st)
 {
-    using Smem = RsSmem<T, I>;
+    using Smem = RsSmem<K, BITS, T, I>;
+    static_assert(T * I <= 65536 && T * I >= RS_MIN_TILE, "tile must fit the u16 ranks and the status allocation");
     static bool attr_set = false;
     if (!attr_set) {
-        GIGS_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel<T, I>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        GIGS_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel<K, BITS, T, I>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(Smem)));
         attr_set = true;
     }
-    const int passes = (end_bit + 7) / 8;
+    const int passes = (end_bit + BITS - 1) / BITS;
     const uint32_t tiles = (n + T * I - 1) / (T * I);
-    const uint64_t* kin = keys_u;
+    const K* kin = keys_u;
     const uint32_t* vin = vals_u;
     for (int p = 0; p < passes; ++p) {
         // choose outputs so that the last pass lands in (keys_a, vals_a)
         const bool to_a = ((passes - 1 - p) % 2) == 0;
-        uint64_t* kout = to_a ? keys_a : keys_b;
+        K* kout = to_a ? keys_a : keys_b;
         uint32_t* vout = to_a ? vals_a : vals_b;
-        const int shift = p * 8;
-        const int bits = (end_bit - shift) < 8 ? (end_bit - shift) : 8;
-        ProfScope ps(ST_SORT_PASS, st);
-        rs_onesweep_kernel<T, I><<<tiles, T, sizeof(Smem), st>>>(kin, kout, vin, vout, n, shift, (1u << bits) - 1u,
-                                                                 hist + p * RS_RADIX,
-                                                                 status + (size_t)p * status_tiles * RS_RADIX,
-                                                                 tickets + p);
+        const int shift = p * BITS;
+        const int bits = (end_bit - shift) < BITS ? (end_bit - shift) : BITS;
+        ProfScope ps(pass_stage, st);
+        rs_onesweep_kernel<K, BITS, T, I><<<tiles, T, sizeof(Smem), st>>>(
+            kin, kout, vin, vout, n, shift, (1u << bits) - 1u, hist + p * RS_MAX_RADIX,
+            status + (size_t)p * status_tiles * RS_MAX_RADIX, tickets + p);
         GIGS_LAUNCH_CHECK("rs_onesweep_kernel");
         kin = kout;
         vin = vout;
@@ -242,43 +254,82 @@ static int launch_passes(uint32_t n, int end_bit, const uint64_t* keys_u, const 
     return 0;
 }
 
-constexpr int RS_MIN_TILE = 3072;  // smallest tile of any configuration: sizes the look-back status array
+static int env_int(const char* name, int dflt)
+{
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
 
-// Sort R pairs on key bits [0, end_bit). Input in (keys_u, vals_u) (left intact); result in
-// (keys_a, vals_a). keys_b/vals_b are the ping-pong partners.
-int launch_radix_sort(uint64_t R, int end_bit, const uint64_t* keys_u, const uint32_t* vals_u, uint64_t* keys_a,
-                      uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, uint32_t* hist, uint32_t* status,
-                      uint32_t* tickets, uint64_t status_bytes_total, cudaStream_t st)
+// digit width for a key of `bits` significant bits: the fewest passes, then the narrowest digit that still covers
+// the key (narrow digits = small per-warp histograms and short look-back rows)
+int radix_digit_bits(int bits)
+{
+    const int passes = (bits + 7) / 8;
+    int d = (bits + passes - 1) / passes;
+    if (d < 6) d = 6;
+    return d;
+}
+int radix_sort_passes(int bits) { return (bits + 7) / 8; }
+
+template <typename K>
+static int sort_pairs(uint64_t R, int end_bit, const K* keys_u, const uint32_t* vals_u, K* keys_a, uint32_t* vals_a,
+                      K* keys_b, uint32_t* vals_b, uint32_t* hist, uint32_t* status, uint32_t* tickets,
+                      uint64_t zero_bytes, int pass_stage, cudaStream_t st)
 {
     if (R == 0) return 0;
     if (R >= (1ull << 30)) {
-        set_error("radix sort: %llu instances exceeds the 2^30 limit", (unsigned long long)R);
+        set_error("radix sort: %llu pairs exceeds the 2^30 limit", (unsigned long long)R);
         return -3;
     }
-    const int passes = (end_bit + 7) / 8;
     const uint32_t n = (uint32_t)R;
+    const int digit_bits = radix_digit_bits(end_bit);
+    const int passes = (end_bit + digit_bits - 1) / digit_bits;
     const uint32_t status_tiles = (n + RS_MIN_TILE - 1) / RS_MIN_TILE;
     // hist, tickets and status are contiguous in the scratch blob: one memset
-    GIGS_CUDA(cudaMemsetAsync(hist, 0, status_bytes_total, st));
+    GIGS_CUDA(cudaMemsetAsync(hist, 0, zero_bytes, st));
     const uint32_t hblocks = min((n + 4095u) / 4096u, 148u * 8u);
-    rs_histogram_kernel<<<hblocks, RS_HTHREADS, 0, st>>>(keys_u, n, passes, end_bit, hist);
+    rs_histogram_kernel<K><<<hblocks, RS_HTHREADS, 0, st>>>(keys_u, n, passes, digit_bits, end_bit, hist);
     GIGS_LAUNCH_CHECK("rs_histogram_kernel");
-    rs_scan_hist_kernel<<<passes, RS_RADIX, 0, st>>>(hist);
+    rs_scan_hist_kernel<<<passes, RS_MAX_RADIX, 0, st>>>(hist);
     GIGS_LAUNCH_CHECK("rs_scan_hist_kernel");
-    static int cfg = -1;
-    if (cfg < 0) {
-        const char* e = getenv("GIGS_RS_CFG");
-        cfg = e ? atoi(e) : 2;
-    }
-#define RS_GO(T, I) return launch_passes<T, I>(n, end_bit, keys_u, vals_u, keys_a, vals_a, keys_b, vals_b, hist, status, tickets, status_tiles, st)
-    switch (cfg) {
-        case 1: RS_GO(256, 12);
-        case 2: RS_GO(512, 16);
-        case 3: RS_GO(384, 16);
-        case 4: RS_GO(512, 12);
-        default: RS_GO(256, 16);
+    static const int cfg = env_int("GIGS_RS_CFG", 0);
+#define RS_GO(B, T, I) \
+    return launch_passes<K, B, T, I>(n, end_bit, keys_u, vals_u, keys_a, vals_a, keys_b, vals_b, hist, status, tickets, status_tiles, pass_stage, st)
+    // small inputs: small tiles so that every SM gets work; large inputs: big tiles for long coalesced runs
+    const bool small = n < 148u * 8192u;
+    if (digit_bits == 6) {
+        if (cfg == 1) RS_GO(6, 256, 8);
+        if (cfg == 2) RS_GO(6, 512, 16);
+        if (cfg == 3) RS_GO(6, 256, 16);
+        if (small) RS_GO(6, 256, 8);
+        RS_GO(6, 512, 8);
+    } else if (digit_bits == 7) {
+        if (small) RS_GO(7, 256, 8);
+        RS_GO(7, 512, 8);
+    } else {
+        if (cfg == 1) RS_GO(8, 256, 8);
+        if (cfg == 2) RS_GO(8, 512, 16);
+        if (cfg == 3) RS_GO(8, 256, 16);
+        if (small) RS_GO(8, 256, 8);
+        RS_GO(8, 512, 16);
     }
 #undef RS_GO
+}
+
+// Sort R pairs on key bits [0, end_bit). Input in (keys_u, vals_u) (left intact; vals_u == nullptr means value i = i);
+// result in (keys_a, vals_a). keys_b/vals_b are the ping-pong partners. hist / tickets / status are contiguous and
+// zero_bytes long (see radix_scratch_bytes).
+int launch_radix_sort(uint64_t R, int end_bit, const uint64_t* keys_u, const uint32_t* vals_u, uint64_t* keys_a,
+                      uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, uint32_t* hist, uint32_t* status,
+                      uint32_t* tickets, uint64_t zero_bytes, cudaStream_t st)
+{
+    return sort_pairs<uint64_t>(R, end_bit, keys_u, vals_u, keys_a, vals_a, keys_b, vals_b, hist, status, tickets, zero_bytes, -1, st);
+}
+int launch_radix_sort32(uint64_t R, int end_bit, const uint32_t* keys_u, const uint32_t* vals_u, uint32_t* keys_a,
+                        uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint32_t* hist, uint32_t* status,
+                        uint32_t* tickets, uint64_t zero_bytes, int pass_stage, cudaStream_t st)
+{
+    return sort_pairs<uint32_t>(R, end_bit, keys_u, vals_u, keys_a, vals_a, keys_b, vals_b, hist, status, tickets, zero_bytes, pass_stage, st);
 }
 
 uint32_t radix_sort_tiles(uint64_t R) { return (uint32_t)((R + RS_MIN_TILE - 1) / RS_MIN_TILE); }

@@ -410,7 +410,10 @@ gi_march_kernel(const int W, const int H, const float focal_x, const float focal
     float* phis = reinterpret_cast<float*>(tab + n_phi * n_theta);
     float* thetas = phis + n_phi;
     const int tid = threadIdx.y * TILE_X + threadIdx.x;
-    build_dir_table(tab, phis, thetas, n_phi, n_theta, delta, tid, 256);
+    // start >= step (the README's --start 64 --step 16): the march loop body never runs, so no direction is ever
+    // used. SSAO's normaliser is then a positive sum and occ = 0 (occlusion exactly 1); SSR's is the direction count.
+    const bool no_march = start >= step;
+    if (!no_march) build_dir_table(tab, phis, thetas, n_phi, n_theta, delta, tid, 256);
 
     const uint32_t px = blockIdx.x * TILE_X + threadIdx.x, py = blockIdx.y * TILE_Y + threadIdx.y;
     if (px > (uint32_t)(W - 1) || py > (uint32_t)(H - 1)) return;
@@ -431,7 +434,8 @@ gi_march_kernel(const int W, const int H, const float focal_x, const float focal
     float occ = 0.0f;
     float nrSamples = 0.0f;
     float3 diffuse = {0.0f, 0.0f, 0.0f};
-    for (int e = 0; e < ndir; ++e) {
+    if (no_march) nrSamples = IS_SSR ? (float)ndir : (ndir > 0 ? 1.0f : 0.0f);
+    for (int e = 0; e < (no_march ? 0 : ndir); ++e) {
         const DirEntry de = tab[e];
         float3 sv;
         sv.x = tbn.m[0] * de.x + tbn.m[3] * de.y + tbn.m[6] * de.z;

@@ -84,6 +84,15 @@ __device__ __forceinline__ CubeTaps cube_taps(float dx, float dy, float dz, int 
     v = v * (float)w - 0.5f;
     const int iu0 = __float2int_rd(u), iv0 = __float2int_rd(v);
     const float fu = u - (float)iu0, fv = v - (float)iv0;
+    if (iu0 >= 0 && iv0 >= 0 && iu0 + 1 < w && iv0 + 1 < w) {
+        // all four taps inside the face (the common case): no edge / corner folding
+        const int base = (face * w + iv0) * w + iu0;
+        T.idx[0] = base;         T.w[0] = (1.f - fu) * (1.f - fv);
+        T.idx[1] = base + 1;     T.w[1] = fu * (1.f - fv);
+        T.idx[2] = base + w;     T.w[2] = (1.f - fu) * fv;
+        T.idx[3] = base + w + 1; T.w[3] = fu * fv;
+        return T;
+    }
     T.idx[0] = cube_wrap_texel(face, iu0, iv0, w);         T.w[0] = (1.f - fu) * (1.f - fv);
     T.idx[1] = cube_wrap_texel(face, iu0 + 1, iv0, w);     T.w[1] = fu * (1.f - fv);
     T.idx[2] = cube_wrap_texel(face, iu0, iv0 + 1, w);     T.w[2] = (1.f - fu) * fv;

@@ -30,8 +30,9 @@ class GigsSizes(C.Structure):
 
 class GigsLayout(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
-        "g_record", "g_cov3D", "g_clamped", "g_tiles_touched", "g_point_offsets", "g_block_sums", "g_num_rendered",
-        "i_final_T", "i_n_contrib", "i_ranges", "b_point_list", "s_keys_sorted", "s_keys_unsorted", "s_vals_unsorted")]
+        "g_record", "g_cov3D", "g_clamped", "g_tiles_touched", "g_depth_keys", "g_order", "g_block_sums",
+        "g_num_rendered", "i_final_T", "i_n_contrib", "i_ranges", "b_point_list", "s_tiles_sorted",
+        "s_tiles_unsorted", "s_vals_unsorted")]
 
 
 class GigsRasterFwd(C.Structure):
@@ -187,7 +188,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the .so does not export it
         fn.restype = res
         fn.argtypes = args
-    if lib.gigs_abi_version() != 1:
+    if lib.gigs_abi_version() != 2:
         raise ImportError("gigs_b200: ABI version mismatch between the python binding and libgigs_b200.so")
     for which, st in enumerate((GigsCamera, GigsSizes, GigsLayout, GigsRasterFwd, GigsRasterBwd, GigsShade,
                                 GigsFrameLayout, GigsFrame)):

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define GIGS_ABI_VERSION 1
+#define GIGS_ABI_VERSION 2
 
 /* Per-view constants: the non-tensor fields of GaussianRasterizationSettings
  * (diff_gaussian_rasterization/__init__.py:31-51). Matrices are the transposed (column-major)
@@ -53,14 +53,19 @@ int gigs_sizeof(int32_t which);
 int gigs_raster_sizes(int32_t P, int32_t W, int32_t H, uint64_t R, GigsSizes* out);
 
 /* Byte offsets of the fields inside the blobs (for tests that check keys / sort order / ranges
- * bit-for-bit against the reference's GeometryState / BinningState / ImageState). */
+ * bit-for-bit against the reference's GeometryState / BinningState / ImageState).
+ * Binning here is two small stable sorts instead of the reference's one 44-bit sort: the Gaussians
+ * are argsorted by depth bits (g_order), instances are emitted in that order as (tile id, Gaussian id) pairs and
+ * sorted by tile id only. The reference's 64-bit key of sorted slot i is
+ * (s_tiles_sorted[i] << 32) | depth_bits(record[b_point_list[i]]). */
 typedef struct GigsLayout {
     /* geom blob */
     uint64_t g_record;        /* float[P][24] packed blend record, see DESIGN.md */
     uint64_t g_cov3D;         /* float[P][6]  */
     uint64_t g_clamped;       /* uint8[P][4]  (3 used) */
     uint64_t g_tiles_touched; /* uint32[P] */
-    uint64_t g_point_offsets; /* uint32[P] inclusive scan */
+    uint64_t g_depth_keys;    /* uint32[P] depth bits (0xFFFFFFFF for Gaussians that touch no tile) */
+    uint64_t g_order;         /* uint32[P] Gaussian ids in ascending (depth bits, id) order */
     uint64_t g_block_sums;    /* uint32[ceil(P/256)+1] */
     uint64_t g_num_rendered;  /* uint32[1] */
     /* img blob */
@@ -70,21 +75,22 @@ typedef struct GigsLayout {
     /* binning blob */
     uint64_t b_point_list;    /* uint32[R] sorted Gaussian ids */
     /* sort scratch */
-    uint64_t s_keys_sorted;   /* uint64[R] */
-    uint64_t s_keys_unsorted; /* uint64[R] (valid only with keep_unsorted) */
-    uint64_t s_vals_unsorted; /* uint32[R] (valid only with keep_unsorted) */
+    uint64_t s_tiles_sorted;   /* uint32[R] tile id of each sorted slot */
+    uint64_t s_tiles_unsorted; /* uint32[R] tile ids in emission order */
+    uint64_t s_vals_unsorted;  /* uint32[R] Gaussian ids in emission order */
 } GigsLayout;
 int gigs_raster_layout(int32_t P, int32_t W, int32_t H, uint64_t R, GigsLayout* out);
 
 /* Replaces RasterizeGaussiansCUDA (rasterize_points.cu:130-252) ->
  * CudaRasterizer::Rasterizer::forward (cuda_rasterizer/rasterizer_impl.cu:486-672).
  * Two phases because num_rendered sizes the binning blob, which the caller owns:
- *   begin : preprocess + tile-count scan, stream-sync, num_rendered returned in *a->num_rendered
- *   finish: key emission, onesweep radix sort, tile ranges, G-buffer blend
+ *   begin : preprocess + tile-count scan, num_rendered read back (the depth argsort of the Gaussians is queued
+ *           behind the read-back so the GPU keeps working while the host sizes the binning blob)
+ *   finish: pair emission in depth order, onesweep radix sort by tile id, tile ranges, G-buffer blend
  * Output maps are CHW planar float32, fully written by finish (no pre-fill needed). */
 typedef struct GigsRasterFwd {
     int32_t P;
-    int32_t keep_unsorted; /* tests only: sort out-of-place into a fresh buffer so unsorted keys survive */
+    int32_t keep_unsorted; /* unused (the sort is always out of place; emission-order pairs survive in the scratch) */
     GigsCamera cam;
     const float* means3D;        /* [P,3] */
     const float* shs;            /* [P,M,3] or NULL */
@@ -319,7 +325,8 @@ int gigs_dist2(int32_t P, const float* points, float* mean_dist2, void* scratch,
  * Stage ids: 0 preprocess+scan, 1 emit_keys, 2 radix_sort, 3 tile_ranges, 4 blend_forward, 5 blend_backward,
  * 6 gaussian_backward, 7 geometry_chain, 8 ssao, 9 ssr, 10 shade_forward, 11 shade_backward, 12 median3x3,
  * 13 median3x3_backward, 14 bilateral3x3, 15 depth_to_normal, 16 ssr_backward, 17 dist2, 18 deferred_shade,
- * 19 deferred_loss, 20 deferred_backward, 21 param_grad, 22 one radix-sort pass (nested inside 2).
+ * 19 deferred_loss, 20 deferred_backward, 21 param_grad, 22 one radix-sort pass (nested inside 2 / 23),
+ * 23 depth argsort of the Gaussians.
  * gigs_profile_read synchronises the recorded events, writes up to cap (stage, ms) pairs, clears the log and
  * returns the number written (negative on error). Off by default; costs two event records per stage when on. */
 int gigs_profile_enable(int32_t on);

@@ -75,19 +75,16 @@ def main():
     print("visible", int(vis.sum()), "of", P)
     cmp("radii", radii, ro["radii"], report, True)
     cmp("tiles_touched", view(geom, lay.g_tiles_touched, 4 * P, torch.int32, (P,)), rs["tiles_touched"], report, True)
-    cmp("point_offsets", view(geom, lay.g_point_offsets, 4 * P, torch.int32, (P,)), rs["point_offsets"], report, True)
     cmp("means2D", rec[vis][:, 0:2], rs["means2D"][vis], report, True)
     cmp("conic", rec[vis][:, 2:5], rs["conic_opacity"][vis][:, 0:3], report, True)
     cmp("depths", rec[vis][:, 6], rs["depths"][vis], report, True)
     cmp("rgb", rec[vis][:, 8:11], rs["rgb"][vis], report, True)
     cmp("cov3D", view(geom, lay.g_cov3D, 24 * P, torch.float32, (P, 6))[vis], rs["cov3D"][vis], report, True)
     if R2 == R:
-        ku = view(sc, lay.s_keys_unsorted, 8 * R, torch.int64, (R,))
-        vu = view(sc, lay.s_vals_unsorted, 4 * R, torch.int32, (R,))
-        ks = view(sc, lay.s_keys_sorted, 8 * R, torch.int64, (R,))
-        pl = view(binning, lay.b_point_list, 4 * R, torch.int32, (R,))
-        for nm, a, b in (("keys_unsorted", ku, rs["keys_unsorted"]), ("vals_unsorted", vu, rs["vals_unsorted"]),
-                         ("keys_sorted", ks, rs["keys_sorted"]), ("point_list", pl, rs["point_list"])):
+        import gpu_util as U
+        st = U.decode_state(dict(num_rendered=R2, color=color, geom=geom, img=img, binning=binning), P, W, H)
+        for nm in ("keys_unsorted", "vals_unsorted", "keys_sorted", "point_list"):
+            a, b = st[nm], rs[nm]
             nd = int((a != b).sum())
             report[nm] = dict(n_diff=nd, n=int(a.numel()))
             print(("OK " if nd == 0 else "BAD"), nm, "n_diff", nd, "/", a.numel())

@@ -42,7 +42,16 @@ def ours_backward(g, cam, bg, fwd, grads, deg=3, colors_precomp=None, cov3D_prec
 
 
 def decode_state(fwd, P, W, H):
-    """Our workspace blobs -> the same named arrays refshim.RefRasterizer.state() returns."""
+    """Our workspace blobs -> the same named arrays refshim.RefRasterizer.state() returns.
+
+    Our binning never materialises the reference's 64-bit keys (depth argsort of the Gaussians + stable
+    sort of (tile, id) pairs by tile id), so they are REBUILT here from what it does produce:
+      keys_sorted[i]  = tile_of_sorted_slot[i] << 32 | depth_bits(point_list[i])
+      keys_unsorted / vals_unsorted = our emitted (tile, id) pairs put back into the reference's emission order
+                        (ascending Gaussian id, row-major tiles inside a Gaussian's rect) with the depth bits attached
+      point_offsets   = inclusive scan of tiles_touched (rasterizer_impl.cu:585)
+    which makes the comparisons against the reference's arrays bit-for-bit checks of our pair multiset, of every
+    Gaussian's tile rect, of the final order and of the ranges."""
     R = fwd["num_rendered"]
     lay = dgr.raster_layout(P, W, H, R)
     sc = dgr.sort_scratch(fwd["color"].device)
@@ -54,16 +63,26 @@ def decode_state(fwd, P, W, H):
     rec = view(geom, lay.g_record, P * 96, torch.float32, (P, 24))
     T = ((W + 15) // 16) * ((H + 15) // 16)
     N = W * H
+    depth_bits = rec[:, 6].contiguous().view(torch.int32).long() & 0xFFFFFFFF
+    tiles_touched = view(geom, lay.g_tiles_touched, 4 * P, torch.int32, (P,))
+    tiles_sorted = view(sc, lay.s_tiles_sorted, 4 * R, torch.int32, (R,)).long()
+    tiles_unsorted = view(sc, lay.s_tiles_unsorted, 4 * R, torch.int32, (R,)).long()
+    vals_emitted = view(sc, lay.s_vals_unsorted, 4 * R, torch.int32, (R,))
+    point_list = view(binning, lay.b_point_list, 4 * R, torch.int32, (R,))
+    ref_order = torch.sort(vals_emitted.long() * (1 << 20) + tiles_unsorted, stable=True).indices
     return dict(
         record=rec, means2D=rec[:, 0:2], conic=rec[:, 2:5], depths=rec[:, 6], rgb=rec[:, 8:11],
         cov3D=view(geom, lay.g_cov3D, 24 * P, torch.float32, (P, 6)),
         clamped=view(geom, lay.g_clamped, 4 * P, torch.uint8, (P, 4))[:, :3],
-        tiles_touched=view(geom, lay.g_tiles_touched, 4 * P, torch.int32, (P,)),
-        point_offsets=view(geom, lay.g_point_offsets, 4 * P, torch.int32, (P,)),
-        keys_unsorted=view(sc, lay.s_keys_unsorted, 8 * R, torch.int64, (R,)),
-        vals_unsorted=view(sc, lay.s_vals_unsorted, 4 * R, torch.int32, (R,)),
-        keys_sorted=view(sc, lay.s_keys_sorted, 8 * R, torch.int64, (R,)),
-        point_list=view(binning, lay.b_point_list, 4 * R, torch.int32, (R,)),
+        tiles_touched=tiles_touched,
+        point_offsets=torch.cumsum(tiles_touched.long(), 0).int(),
+        depth_keys=view(geom, lay.g_depth_keys, 4 * P, torch.int32, (P,)),
+        order=view(geom, lay.g_order, 4 * P, torch.int32, (P,)),
+        tiles_emitted=tiles_unsorted, vals_emitted=vals_emitted, tiles_sorted=tiles_sorted,
+        keys_unsorted=(tiles_unsorted[ref_order] << 32) | depth_bits[vals_emitted.long()[ref_order]],
+        vals_unsorted=vals_emitted[ref_order],
+        keys_sorted=(tiles_sorted << 32) | depth_bits[point_list.long()],
+        point_list=point_list,
         final_T=view(img, lay.i_final_T, 4 * N, torch.float32, (N,)),
         n_contrib=view(img, lay.i_n_contrib, 4 * N, torch.int32, (N,)),
         ranges=view(img, lay.i_ranges, 8 * T, torch.int32, (T, 2)))

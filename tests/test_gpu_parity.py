@@ -237,6 +237,13 @@ def test_full_size_properties_c2():
     # the sort is a permutation of the emitted pairs and stable: (key, value) pairs match a stable torch sort
     order = torch.sort(st["keys_unsorted"] & ((1 << 44) - 1), stable=True).indices
     assert torch.equal(st["point_list"], st["vals_unsorted"][order])
+    # the two-level sort's own pieces: depth argsort is the stable argsort of the depth keys, pairs are emitted in
+    # that order, and the instance sort is the stable sort of the emitted pairs by tile id
+    dk = st["depth_keys"].long() & 0xFFFFFFFF
+    assert torch.equal(st["order"].long(), torch.sort(dk, stable=True).indices)
+    emitted_gauss = st["vals_emitted"].long()
+    assert bool((dk[emitted_gauss][1:] >= dk[emitted_gauss][:-1]).all()), "pairs not emitted in depth order"
+    assert torch.equal(st["point_list"].long(), emitted_gauss[torch.sort(st["tiles_emitted"], stable=True).indices])
     # ranges partition [0, R) by tile id
     tiles = (st["keys_sorted"] >> 32).int()
     rg = st["ranges"].long()
