@@ -25,6 +25,8 @@ constexpr int RS_MAX_PASSES = 8;
 constexpr int RS_MIN_TILE = 2048;  // smallest tile of any configuration: sizes the look-back status array
 
 constexpr uint32_t FLAG_AGG = 1u, FLAG_INC = 2u;
+constexpr int LB_W = 8;  // look-back window: predecessor status words fetched per round
+
 
 template <typename K>
 __global__ void __launch_bounds__(RS_HTHREADS)
@@ -117,23 +119,30 @@ rs_onesweep_kernel(const K* __restrict__ keys_in, K* __restrict__ keys_out, cons
         key[i] = (loc < count) ? keys_in[base + loc] : (K)~(K)0;
     }
 
-    // rank keys within the warp, item by item (match-any multisplit)
+    // rank keys within the warp, item by item (multisplit). The set of lanes holding the same digit is built from
+    // one ballot per digit bit (VOTE is a cheap ALU-side op; MATCH.ANY measured ~100 cycles of issue per warp
+    // instruction per SM here and bounded the whole pass). All lanes of a digit read its running count (a shared
+    // memory broadcast), then the lowest lane of the set adds the set size.
     const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
         const uint32_t loc = wbase + i * 32;
         const bool valid = loc < count;
-        const uint32_t d = valid ? ((uint32_t)(key[i] >> shift) & digit_mask) : 0xffffffffu;
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const uint32_t d = (uint32_t)(key[i] >> shift) & digit_mask;
+        uint32_t peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+        for (int bit = 0; bit < BITS; ++bit) {
+            const bool on = (d >> bit) & 1u;
+            const uint32_t m = __ballot_sync(0xffffffffu, on);
+            peers &= on ? m : ~m;
+        }
         const uint32_t below = peers & lt_mask;
         uint32_t old = 0;
-        if (valid && below == 0) {
-            old = S.warp_hist[warp][d];
-            S.warp_hist[warp][d] = old + __popc(peers);
-        }
-        old = __shfl_sync(0xffffffffu, old, __ffs(peers) - 1);
-        rank[i] = (uint16_t)(old + __popc(below));
+        if (valid) old = S.warp_hist[warp][d];
         __syncwarp();
+        if (valid && below == 0) S.warp_hist[warp][d] = old + __popc(peers);
+        __syncwarp();
+        rank[i] = (uint16_t)(old + __popc(below));
     }
     __syncthreads();
 
@@ -161,15 +170,24 @@ rs_onesweep_kernel(const K* __restrict__ keys_in, K* __restrict__ keys_out, cons
             *my_status = (sum << 2) | FLAG_INC;
         } else {
             *my_status = (sum << 2) | FLAG_AGG;
+            // Look-back with LB_W predecessors in flight per round: the loads are independent, so a round costs one
+            // L2 round trip instead of LB_W (measured serial depth at 300k / 800x800: 16 tiles on average, 35 max).
             int64_t t = (int64_t)tile - 1;
-            while (true) {
-                uint32_t v;
-                do {
-                    v = status[(size_t)t * RADIX + d];
-                } while ((v & 3u) == 0u);
-                excl += v >> 2;
-                if (v & FLAG_INC) break;
-                --t;
+            bool found = false;
+            while (!found) {
+                uint32_t v[LB_W];
+#pragma unroll
+                for (int k = 0; k < LB_W; ++k)
+                    v[k] = (t - k >= 0) ? status[(size_t)(t - k) * RADIX + d] : (uint32_t)2u /* FLAG_INC: before tile 0 the prefix is 0 */;
+#pragma unroll
+                for (int k = 0; k < LB_W; ++k) {
+                    if (!found) {
+                        while ((v[k] & 3u) == 0u) v[k] = status[(size_t)(t - k) * RADIX + d];
+                        excl += v[k] >> 2;
+                        found = (v[k] & FLAG_INC) != 0u;
+                    }
+                }
+                t -= LB_W;
             }
             *my_status = ((excl + sum) << 2) | FLAG_INC;
         }
@@ -301,8 +319,10 @@ static int sort_pairs(uint64_t R, int end_bit, const K* keys_u, const uint32_t* 
         if (cfg == 1) RS_GO(6, 256, 8);
         if (cfg == 2) RS_GO(6, 512, 16);
         if (cfg == 3) RS_GO(6, 256, 16);
+        if (cfg == 4) RS_GO(6, 1024, 4);
+        if (cfg == 5) RS_GO(6, 512, 4);
         if (small) RS_GO(6, 256, 8);
-        RS_GO(6, 512, 8);
+        RS_GO(6, 1024, 4);  // measured best at R = 4.2M (B200): 40.6 us / pass vs 43.3 for 512 x 8
     } else if (digit_bits == 7) {
         if (small) RS_GO(7, 256, 8);
         RS_GO(7, 512, 8);
@@ -310,7 +330,9 @@ static int sort_pairs(uint64_t R, int end_bit, const K* keys_u, const uint32_t* 
         if (cfg == 1) RS_GO(8, 256, 8);
         if (cfg == 2) RS_GO(8, 512, 16);
         if (cfg == 3) RS_GO(8, 256, 16);
-        if (small) RS_GO(8, 256, 8);
+        if (cfg == 4) RS_GO(8, 512, 4);
+        if (cfg == 5) RS_GO(8, 1024, 2);
+        if (small) RS_GO(8, 512, 4);  // measured best for the 300k-key depth argsort: 60 us vs 70 for 256 x 8
         RS_GO(8, 512, 16);
     }
 #undef RS_GO
@@ -331,6 +353,7 @@ int launch_radix_sort32(uint64_t R, int end_bit, const uint32_t* keys_u, const u
 {
     return sort_pairs<uint32_t>(R, end_bit, keys_u, vals_u, keys_a, vals_a, keys_b, vals_b, hist, status, tickets, zero_bytes, pass_stage, st);
 }
+
 
 uint32_t radix_sort_tiles(uint64_t R) { return (uint32_t)((R + RS_MIN_TILE - 1) / RS_MIN_TILE); }
 
