@@ -17,6 +17,7 @@
 //
 // The arithmetic of each step follows the framework ops it replaces (same operation order where the op defines
 // one); they are float32 elementwise chains, so agreement with the unfused path is to rounding, not bit-exact.
+#include <cstdlib>
 #include <cstring>
 #include "filters.cuh"
 #include "shade_core.cuh"
@@ -53,7 +54,7 @@ __device__ __forceinline__ float srgb_to_linear_px(float s)
 {
     // train.py:70-75
     const float l0 = (25.f / 323.f) * s;
-    const float l1 = powf((s + 0.055f) / 1.055f, 2.4f);
+    const float l1 = fast_pow((s + 0.055f) / 1.055f, 2.4f);
     return (s <= 0.04045f) ? l0 : l1;
 }
 
@@ -291,7 +292,8 @@ __global__ void __launch_bounds__(256) deferred_loss_kernel(const DeferParams p)
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) deferred_backward_kernel(const DeferParams p, const int tiles_x, const int ntiles)
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) deferred_backward_kernel(const DeferParams p, const int tiles_x, const int ntiles)
 {
     extern __shared__ __align__(16) unsigned char dfb_raw[];
     float* s_dtex = reinterpret_cast<float*>(dfb_raw);                              // [SHB_MAX_DIFFUSE]
@@ -601,15 +603,14 @@ int gigs_frame_backward(GigsFrame* f)
     fill_defer(f, FL, p, true);
     const int tiles_x = (W + DF_TW - 1) / DF_TW, ntiles = p.nblk;
     const size_t smem = SHB_MAX_DIFFUSE * sizeof(float) + 3 * DF_HH1 * DF_HW1 * (sizeof(float) + 1) + 16;
-    static bool attr = false;
-    if (!attr) {
-        GIGS_CUDA(cudaFuncSetAttribute(deferred_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
     {
         ProfScope ps(ST_DEFER_BWD, st);
-        const int blocks = ntiles < 148 * 4 ? ntiles : 148 * 4;
-        deferred_backward_kernel<<<blocks, dim3(DF_TW, DF_TH), smem, st>>>(p, tiles_x, ntiles);
+        static const int variant = getenv("GIGS_DFB") ? atoi(getenv("GIGS_DFB")) : 3;  // 3 CTAs/SM measured best (203 vs 214 us)
+        const int per_sm = variant == 3 ? 3 : (variant == 4 ? 4 : 2);
+        const int blocks = ntiles < 148 * per_sm * 2 ? ntiles : 148 * per_sm * 2;
+        if (variant == 3) deferred_backward_kernel<3><<<blocks, dim3(DF_TW, DF_TH), smem, st>>>(p, tiles_x, ntiles);
+        else if (variant == 4) deferred_backward_kernel<4><<<blocks, dim3(DF_TW, DF_TH), smem, st>>>(p, tiles_x, ntiles);
+        else deferred_backward_kernel<2><<<blocks, dim3(DF_TW, DF_TH), smem, st>>>(p, tiles_x, ntiles);
         GIGS_LAUNCH_CHECK("deferred_backward_kernel");
     }
     GigsRasterBwd b;

@@ -67,7 +67,9 @@ def main():
                       ", ".join(f"{n}={v:.2f}" for v, n in stalls[:7]))
             dr, dw = col.get("dram__bytes_read.sum"), col.get("dram__bytes_write.sum")
             if dr is not None and r[dr]:
-                print(f"   traffic (DRAM read+write)        {float(r[dr]) + float(r[dw]):16.3f} {units[dr]}")
+                mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                tot = float(r[dr]) * mult.get(units[dr], 1.0) + float(r[dw]) * mult.get(units[dw], 1.0)
+                print(f"   traffic (DRAM read+write)        {tot / 1e6:16.3f} MB per launch")
             print()
 
 
