@@ -36,12 +36,36 @@ class GaussianParams:
         n = sum(t.numel() for t in self.leaves.values()) + sum(t.numel() for t in self.light_leaves)
         self.flat_grad = torch.zeros(n, dtype=torch.float32, device=device)
         o = 0
-        for t in list(self.leaves.values()) + self.light_leaves:
+        self._span = {}
+        for k, t in list(self.leaves.items()) + [(f"light{i}", t) for i, t in enumerate(self.light_leaves)]:
             t.grad = self.flat_grad[o:o + t.numel()].view_as(t)
+            self._span[k] = (o, o + t.numel())
             o += t.numel()
+        self._dirty = None   # spans the fused path has written since the last zero_grad; None = unknown / anything
 
-    def zero_grad(self):
-        self.flat_grad.zero_()
+    def mark_dirty(self, keys=None):
+        if keys is None:
+            self._dirty = None
+        elif self._dirty is not None:
+            self._dirty.extend(self._span[k] for k in keys)
+
+    def zero_grad(self, fused_only: bool = False):
+        """Zero the flat gradient buffer. fused_only=True is the caller's statement that nothing but the fused PBR
+        frame path (training_step(fused=True)) has written gradients since the last zero_grad: that path only
+        produces material and light gradients (train.py:343-351 detaches everything else), so 12.6 MB are cleared
+        instead of the whole 87 MB buffer (300k Gaussians). Falls back to a full clear whenever that is not known."""
+        if not fused_only or self._dirty is None:
+            self.flat_grad.zero_()
+        else:
+            merged = []
+            for lo, hi in sorted(set(self._dirty)):
+                if merged and lo <= merged[-1][1]:
+                    merged[-1][1] = max(merged[-1][1], hi)
+                else:
+                    merged.append([lo, hi])
+            for lo, hi in merged:
+                self.flat_grad[lo:hi].zero_()
+        self._dirty = []
 
     def activated(self) -> Dict:
         """scene/gaussian_model.py:178-266 getters, autograd-tracked."""
@@ -69,8 +93,10 @@ def training_step(params: GaussianParams, cam, light: Light, brdf_lut, rays, gt_
     kept as the reference-shaped path and as the parity check of the fused one."""
     if fused:
         from .frame import pbr_frame_step
+        params.mark_dirty(["albedo", "roughness", "metallic"] + [f"light{i}" for i in range(len(params.light_leaves))])
         return pbr_frame_step(params, cam, light, brdf_lut, rays, gt_image, background, gi, metallic=metallic,
                               gamma=gamma, tone=tone, indirect=indirect, loss_scale=loss_scale)
+    params.mark_dirty(None)
     g = params.activated()
     res = pbr_forward(cam, g, light, brdf_lut, rays, background, indirect=indirect, metallic=metallic, tone=tone,
                       gamma=gamma, gi=gi)
@@ -85,7 +111,7 @@ def multi_view_step(params: GaussianParams, cams: List, light: Light, brdf_lut, 
     the K views; each rank back-propagates its own views, then ONE all-reduce(sum) of the flat gradient buffer
     (268 B per Gaussian + the light texels). With world == 1 this is plain gradient accumulation."""
     K = len(cams)
-    params.zero_grad()
+    params.zero_grad(fused_only=bool(kw.get("fused", True)))
     total = torch.zeros((), device=params.flat_grad.device)
     for k in range(rank, K, world):
         total = total + training_step(params, cams[k], light, brdf_lut, rays_of(cams[k]), gts[k], background, gi,
