@@ -13,6 +13,7 @@
 // MODE_MATERIAL is the PBR-stage fast path: when neither the colour nor the opacity map has an
 // upstream gradient, dL/dalpha is identically zero in the reference as well, so only the
 // w * dL/dpixel sums of albedo / roughness / metallic are needed (5 values, 9 shuffles).
+#include <cstdlib>
 #include "common.cuh"
 
 namespace gigs {
@@ -311,6 +312,204 @@ blend_backward_kernel(const int W, const int H, const uint2* __restrict__ ranges
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Material-only backward, the PBR-stage path (dL/dcolor = dL/dopacity = 0 => dL/dalpha = 0 in the reference too):
+//     dL/d{roughness, albedo, metallic}_g = sum over pixels of w(p,g) * dL/dpixel_p,   w = alpha * T.
+// Differences from the general kernel above, all aimed at the instruction count (the general kernel is issue bound,
+// 85 % of issue slots busy, ~50 warp instructions per visited (warp, Gaussian) pair of which ~23 are the cross-lane
+// reduction):
+//   * the tile list is walked FRONT TO BACK with the forward's own recurrence (w = alpha*T; T *= 1-alpha), so the
+//     weights are bit-identical to what the forward blended and the per-pair IEEE division T/(1-alpha) is gone;
+//   * the cross-lane reduction is a small dense contraction through shared memory instead of a shuffle butterfly per
+//     Gaussian: each surviving Gaussian's 32 per-pixel weights go into a per-warp 32 x 16 queue (one STS per lane);
+//     when 16 Gaussians are queued, lane l sums w[p][l & 15] * dL/dpixel_p over 16 of the 32 pixels (half l >> 4),
+//     one shuffle joins the halves, and lanes 0..15 issue the 5 reductions of "their" Gaussian. Amortised cost
+//     ~9 instructions per Gaussian instead of ~23, and 5 red instructions per 16 Gaussians instead of 16.
+// ---------------------------------------------------------------------------------------------
+constexpr int MQ = 16;  // queue slots per warp
+
+struct MatSmem {
+    float rec[2][BB_BATCH][8];
+    uint32_t ids[2][BB_BATCH];
+    float4 g4[BB_THREADS];                 // per pixel: dL/d{roughness, albedo.xyz}
+    float g1[BB_THREADS];                  // per pixel: dL/dmetallic
+    float w[BB_THREADS / 32][32][MQ + 1];  // per warp: weights of the queued Gaussians, [pixel][slot]
+    uint32_t qid[BB_THREADS / 32][MQ];     // per warp: Gaussian id of each slot
+    uint64_t bar[2];
+    int red[BB_THREADS / 32];
+};
+
+__global__ void __launch_bounds__(BB_THREADS)
+blend_backward_material_kernel(const int W, const int H, const uint2* __restrict__ ranges,
+                               const uint32_t* __restrict__ point_list, const float* __restrict__ records,
+                               const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpix_albedo,
+                               const float* __restrict__ dL_dpix_roughness, const float* __restrict__ dL_dpix_metallic,
+                               float* __restrict__ accum)
+{
+    constexpr uint32_t RECB = 32;
+    extern __shared__ __align__(128) unsigned char bb_smem_raw[];
+    MatSmem& S = *reinterpret_cast<MatSmem*>(bb_smem_raw);
+
+    const int tid = threadIdx.y * TILE_X + threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const uint32_t horizontal_blocks = (W + TILE_X - 1) / TILE_X;
+    const uint2 pix = {blockIdx.x * TILE_X + threadIdx.x, blockIdx.y * TILE_Y + threadIdx.y};
+    const uint32_t pix_id = W * pix.y + pix.x;
+    const float2 pixf = {(float)pix.x, (float)pix.y};
+    const bool inside = pix.x < (uint32_t)W && pix.y < (uint32_t)H;
+    const int HW = H * W;
+
+    const uint2 range = ranges[blockIdx.y * horizontal_blocks + blockIdx.x];
+    const int last_contributor = inside ? (int)n_contrib[pix_id] : 0;
+    {
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        float gm = 0.f;
+        if (inside) {
+            g.x = dL_dpix_roughness ? dL_dpix_roughness[pix_id] : 0.f;
+            if (dL_dpix_albedo) {
+                g.y = dL_dpix_albedo[pix_id];
+                g.z = dL_dpix_albedo[HW + pix_id];
+                g.w = dL_dpix_albedo[2 * HW + pix_id];
+            }
+            gm = dL_dpix_metallic ? dL_dpix_metallic[pix_id] : 0.f;
+        }
+        S.g4[tid] = g;
+        S.g1[tid] = gm;
+    }
+    // the forward never went past max(n_contrib) in this tile: walk only that prefix
+    int wmax = last_contributor;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    if (lane == 0) S.red[warp] = wmax;
+    if (tid == 0) {
+        mbar_init(&S.bar[0], 1);
+        mbar_init(&S.bar[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    int n = 0;
+#pragma unroll
+    for (int w = 0; w < BB_THREADS / 32; ++w) n = max(n, S.red[w]);
+    n = min(n, (int)(range.y - range.x));
+    const int rounds = (n + BB_BATCH - 1) / BB_BATCH;
+
+    const float strip_x0 = (float)(blockIdx.x * TILE_X);
+    const float strip_y0 = (float)(blockIdx.y * TILE_Y + (threadIdx.y & ~1));
+
+    auto issue = [&](int b) {
+        const int s = b & 1;
+        const int cnt = min(BB_BATCH, n - b * BB_BATCH);
+        if (tid == 0) mbar_arrive_expect_tx(&S.bar[s], (uint32_t)cnt * RECB);
+        if (tid < cnt) {
+            const uint32_t id = point_list[range.x + b * BB_BATCH + tid];
+            S.ids[s][tid] = id;
+            bulk_g2s(&S.rec[s][tid][0], records + (size_t)id * REC_FLOATS, RECB, &S.bar[s]);
+        }
+    };
+
+    // drain the warp's queue: q Gaussians (q <= MQ) x 32 pixels -> 5 sums per Gaussian
+    auto flush = [&](int q) {
+        __syncwarp();
+        const int slot = lane & (MQ - 1), half = lane >> 4;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int p = half * 16 + k;
+            const float wv = S.w[warp][p][slot];
+            const float4 g = S.g4[warp * 32 + p];
+            const float gm = S.g1[warp * 32 + p];
+            a0 = fmaf(wv, g.x, a0);
+            a1 = fmaf(wv, g.y, a1);
+            a2 = fmaf(wv, g.z, a2);
+            a3 = fmaf(wv, g.w, a3);
+            a4 = fmaf(wv, gm, a4);
+        }
+        a0 += __shfl_xor_sync(0xffffffffu, a0, 16);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, 16);
+        a3 += __shfl_xor_sync(0xffffffffu, a3, 16);
+        a4 += __shfl_xor_sync(0xffffffffu, a4, 16);
+        if (half == 0 && slot < q) {
+            float* row = accum + (size_t)S.qid[warp][slot] * ACC_FLOATS + A_ROUGH;  // {rough, albedo.xyz, metallic}
+            red_add_f32(row + 0, a0);
+            red_add_f32(row + 1, a1);
+            red_add_f32(row + 2, a2);
+            red_add_f32(row + 3, a3);
+            red_add_f32(row + 4, a4);
+        }
+        __syncwarp();
+    };
+
+    float T = 1.0f;
+    int q = 0;  // queued Gaussians of this warp (warp-uniform)
+    if (rounds > 0) issue(0);
+    __syncthreads();  // ids of batch 0 and the g4/g1 staging are plain shared stores: make them visible
+    for (int b = 0; b < rounds; ++b) {
+        const int s = b & 1;
+        if (b + 1 < rounds) issue(b + 1);
+        mbar_wait(&S.bar[s], (uint32_t)((b >> 1) & 1));
+        const int cnt = min(BB_BATCH, n - b * BB_BATCH);
+        for (int jb = 0; jb < cnt; jb += 32) {
+            const int fwd_lo = b * BB_BATCH + jb;  // forward index of the first entry of this chunk
+            if (fwd_lo >= wmax) break;             // this warp's pixels were all finished before this chunk
+            bool keep = false;
+            const int jl = jb + lane;
+            if (jl < cnt && (fwd_lo + lane) < wmax) {
+                const float4 t0 = *reinterpret_cast<const float4*>(&S.rec[s][jl][0]);
+                const float4 t1 = *reinterpret_cast<const float4*>(&S.rec[s][jl][4]);
+                const float cA = t0.z, cB = t0.w, cC = t1.x;
+                const float hx = t0.x - strip_x0;
+                const float hy = t0.y - strip_y0;
+                float qmin;
+                {
+                    const float dy = hy;
+                    const float dxs = fminf(hx, fmaxf(hx - 15.f, __fdividef(-cB * dy, cA)));
+                    const float ta = 0.5f * cA * dxs * dxs, tb = cB * dxs * dy, tc = 0.5f * cC * dy * dy;
+                    qmin = (ta + tb + tc) - 4e-6f * (fabsf(ta) + fabsf(tb) + fabsf(tc));
+                }
+                {
+                    const float dy = hy - 1.f;
+                    const float dxs = fminf(hx, fmaxf(hx - 15.f, __fdividef(-cB * dy, cA)));
+                    const float ta = 0.5f * cA * dxs * dxs, tb = cB * dxs * dy, tc = 0.5f * cC * dy * dy;
+                    qmin = fminf(qmin, (ta + tb + tc) - 4e-6f * (fabsf(ta) + fabsf(tb) + fabsf(tc)));
+                }
+                keep = !(cA > 0.f) || !(qmin > t1.w + 0.05f);
+            }
+            uint32_t mask = __ballot_sync(0xffffffffu, keep);
+            while (mask) {
+                const int jo = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const int j = jb + jo;
+                float wgt = 0.f;
+                if (fwd_lo + jo < last_contributor) {
+                    // forward.cu:540-560 recurrence, same expressions as blend_fwd.cu
+                    const float4 q0 = *reinterpret_cast<const float4*>(&S.rec[s][j][0]);
+                    const float4 q1 = *reinterpret_cast<const float4*>(&S.rec[s][j][4]);
+                    const float2 d = {q0.x - pixf.x, q0.y - pixf.y};
+                    const float power = -0.5f * (q0.z * d.x * d.x + q1.x * d.y * d.y) - q0.w * d.x * d.y;
+                    if (!(power > 0.0f)) {
+                        const float alpha = fminf(0.99f, q1.y * expf(power));
+                        if (!(alpha < 1.0f / 255.0f)) {
+                            wgt = alpha * T;
+                            T = T * (1.f - alpha);
+                        }
+                    }
+                }
+                if (__any_sync(0xffffffffu, wgt != 0.f)) {
+                    S.w[warp][lane][q] = wgt;
+                    if (lane == 0) S.qid[warp][q] = S.ids[s][j];
+                    if (++q == MQ) {
+                        flush(MQ);
+                        q = 0;
+                    }
+                }
+            }
+        }
+        __syncthreads();  // release stage s
+    }
+    if (q > 0) flush(q);
+}
+
 int launch_blend_backward(const GigsRasterBwd* a, const Layout& L, cudaStream_t st)
 {
     const GigsCamera& c = a->cam;
@@ -333,7 +532,18 @@ int launch_blend_backward(const GigsRasterBwd* a, const Layout& L, cudaStream_t 
     const float* finalT = (const float*)(im + L.off.i_final_T);
     const bool material_only = (a->dL_dpix == nullptr) && (a->dL_dpix_opacity == nullptr) &&
                                (a->dL_dpix_normal == nullptr) && (a->dL_dpix_depth == nullptr);
-    if (material_only)
+    static const bool legacy_material = getenv("GIGS_BB_LEGACY") != nullptr;
+    if (material_only && !legacy_material) {
+        static bool mattr = false;
+        if (!mattr) {
+            GIGS_CUDA(cudaFuncSetAttribute(blend_backward_material_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sizeof(MatSmem)));
+            mattr = true;
+        }
+        blend_backward_material_kernel<<<grid, block, sizeof(MatSmem), st>>>(
+            c.width, c.height, ranges, plist, recs, ncontrib, a->dL_dpix_albedo, a->dL_dpix_roughness,
+            a->dL_dpix_metallic, a->accum);
+    } else if (material_only)
         blend_backward_kernel<MODE_MATERIAL><<<grid, block, sizeof(BwdSmem<8>), st>>>(
             c.width, c.height, ranges, plist, recs, c.bg, finalT, ncontrib, a->dL_dpix_depth, a->dL_dpix,
             a->dL_dpix_opacity, a->dL_dpix_normal, a->dL_dpix_albedo, a->dL_dpix_roughness, a->dL_dpix_metallic,
