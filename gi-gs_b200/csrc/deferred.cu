@@ -29,6 +29,10 @@ int forward_finish_impl(GigsRasterFwd* a, bool lite);
 int read_back_num_rendered(GigsRasterFwd* a, const Layout& L, cudaStream_t st);
 int launch_blend_backward(const GigsRasterBwd* a, const Layout& L, cudaStream_t st);
 
+constexpr int TEX_PRIV_RES = 32;                                   // textures up to this face size are privatised
+constexpr int TEX_PRIV_FLOATS = 6 * TEX_PRIV_RES * TEX_PRIV_RES * 3;  // floats of one copy slot
+constexpr int TEX_PRIV_MAX = 4;                                     // diffuse + up to 3 specular levels
+
 constexpr int DF_TW = 32, DF_TH = 8;              // output tile of one CTA pass (256 threads, a warp = one row)
 constexpr int DF_HW1 = DF_TW + 2, DF_HH1 = DF_TH + 2;  // + 1-pixel halo
 
@@ -305,7 +309,7 @@ __global__ void __launch_bounds__(256, MINB) deferred_backward_kernel(const Defe
     const int W = p.W, H = p.H;
     const size_t HW = (size_t)W * H;
     const int ndt = 6 * p.sh.diffuse_res * p.sh.diffuse_res * 3;
-    const bool use_smem = (p.sh.g_diffuse_tex != nullptr) && (ndt <= SHB_MAX_DIFFUSE);
+    const bool use_smem = (p.sh.g_diffuse_tex != nullptr) && (ndt <= SHB_MAX_DIFFUSE) && (p.sh.g_diffuse_stride == 0);
     if (use_smem)
         for (int i = tid; i < ndt; i += 256) s_dtex[i] = 0.f;
     if (tid == 0) c2w_rotation(p.viewmatrix, s_C);
@@ -383,6 +387,18 @@ __global__ void __launch_bounds__(256, MINB) deferred_backward_kernel(const Defe
     }
 }
 
+// grad[i] += sum over the TEX_COPIES private copies (fixed order: deterministic given the copies)
+__global__ void __launch_bounds__(256)
+texel_fold_kernel(const float* __restrict__ priv, const int n, float* __restrict__ grad)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    float s = 0.f;
+#pragma unroll 8
+    for (int c = 0; c < TEX_COPIES; ++c) s += priv[(size_t)c * TEX_PRIV_FLOATS + i];
+    if (s != 0.f) grad[i] += s;
+}
+
 // ------------------------------------------------------------------------------------------------
 template <bool RAW>
 __global__ void __launch_bounds__(256)
@@ -433,6 +449,7 @@ static GigsFrameLayout frame_layout(int W, int H)
     L.mask = take(N);
     L.median_sel = take(3 * N);
     const uint64_t nblk = (uint64_t)((W + DF_TW - 1) / DF_TW) * ((H + DF_TH - 1) / DF_TH);
+    L.tex_scratch = take((uint64_t)TEX_PRIV_MAX * TEX_PRIV_FLOATS * TEX_COPIES * 4);
     L.partials = take(5 * nblk * 4);
     L.stats = take(64);
     L.total_bytes = align_up(o, 256) + 256;
@@ -493,6 +510,22 @@ static void fill_defer(const GigsFrame* f, const GigsFrameLayout& FL, DeferParam
     }
     s.diffuse = f->diffuse; s.lut = f->brdf_lut; s.rmin = f->min_roughness; s.rmax = f->max_roughness;
     s.g_diffuse_tex = backward ? f->g_diffuse_tex : nullptr;
+    if (backward) {
+        // small textures accumulate into private copies in the maps blob (folded into the user's gradient
+        // tensors by texel_fold_kernel after the backward kernel)
+        float* scratch = (float*)(m + FL.tex_scratch);
+        int slot = 0;
+        if (s.g_diffuse_tex && f->diffuse_res <= TEX_PRIV_RES) {
+            s.g_diffuse_tex = scratch + (size_t)(slot++) * TEX_PRIV_FLOATS * TEX_COPIES;
+            s.g_diffuse_stride = TEX_PRIV_FLOATS;
+        }
+        for (int i = f->n_spec_levels - 1; i >= 0 && slot < TEX_PRIV_MAX; --i) {
+            if (s.g_spec[i] && f->spec_res[i] <= TEX_PRIV_RES) {
+                s.g_spec[i] = scratch + (size_t)(slot++) * TEX_PRIV_FLOATS * TEX_COPIES;
+                s.g_spec_stride[i] = TEX_PRIV_FLOATS;
+            }
+        }
+    }
     p.W = c.width; p.H = c.height; p.use_metallic = f->use_metallic;
     p.viewmatrix = c.viewmatrix;
     p.normal_map = (float*)(m + FL.normal); p.normal_view_raw = (float*)(m + FL.normal_view);
@@ -605,6 +638,23 @@ int gigs_frame_backward(GigsFrame* f)
     const size_t smem = SHB_MAX_DIFFUSE * sizeof(float) + 3 * DF_HH1 * DF_HW1 * (sizeof(float) + 1) + 16;
     {
         ProfScope ps(ST_DEFER_BWD, st);
+        char* m = (char*)f->maps;
+        float* scratch = (float*)(m + FL.tex_scratch);
+        // the same slot assignment as fill_defer: diffuse first, then the specular levels from coarse to fine
+        float* fold_dst[TEX_PRIV_MAX];
+        int fold_n[TEX_PRIV_MAX], slots = 0;
+        if (f->g_diffuse_tex && f->diffuse_res <= TEX_PRIV_RES) {
+            fold_dst[slots] = f->g_diffuse_tex;
+            fold_n[slots++] = 6 * f->diffuse_res * f->diffuse_res * 3;
+        }
+        for (int i = f->n_spec_levels - 1; i >= 0 && slots < TEX_PRIV_MAX; --i) {
+            if (f->g_spec[i] && f->spec_res[i] <= TEX_PRIV_RES) {
+                fold_dst[slots] = f->g_spec[i];
+                fold_n[slots++] = 6 * f->spec_res[i] * f->spec_res[i] * 3;
+            }
+        }
+        if (slots > 0)
+            GIGS_CUDA(cudaMemsetAsync(scratch, 0, (size_t)slots * TEX_PRIV_FLOATS * TEX_COPIES * sizeof(float), st));
         static const int variant = getenv("GIGS_DFB") ? atoi(getenv("GIGS_DFB")) : 3;  // 3 CTAs/SM measured best (203 vs 214 us)
         const int per_sm = variant == 3 ? 3 : (variant == 4 ? 4 : 2);
         const int blocks = ntiles < 148 * per_sm * 2 ? ntiles : 148 * per_sm * 2;
@@ -612,6 +662,11 @@ int gigs_frame_backward(GigsFrame* f)
         else if (variant == 4) deferred_backward_kernel<4><<<blocks, dim3(DF_TW, DF_TH), smem, st>>>(p, tiles_x, ntiles);
         else deferred_backward_kernel<2><<<blocks, dim3(DF_TW, DF_TH), smem, st>>>(p, tiles_x, ntiles);
         GIGS_LAUNCH_CHECK("deferred_backward_kernel");
+        for (int k = 0; k < slots; ++k) {
+            texel_fold_kernel<<<(fold_n[k] + 255) / 256, 256, 0, st>>>(
+                scratch + (size_t)k * TEX_PRIV_FLOATS * TEX_COPIES, fold_n[k], fold_dst[k]);
+            GIGS_LAUNCH_CHECK("texel_fold_kernel");
+        }
     }
     GigsRasterBwd b;
     memset(&b, 0, sizeof(b));

@@ -113,6 +113,7 @@ static int fill_params(const GigsShade* a, ShadeParams& p, bool backward)
         p.spec_res[i] = i < a->n_spec_levels ? a->spec_res[i] : 0;
         p.spec[i] = i < a->n_spec_levels ? a->spec[i] : nullptr;
         p.g_spec[i] = (backward && i < a->n_spec_levels) ? a->g_spec[i] : nullptr;
+        p.g_spec_stride[i] = 0;
         if (i < a->n_spec_levels && (!a->spec[i] || a->spec_res[i] <= 0)) { set_error("shade: specular level %d missing", i); return -1; }
     }
     p.diffuse = a->diffuse; p.lut = a->brdf_lut; p.rmin = a->min_roughness; p.rmax = a->max_roughness;
@@ -125,6 +126,7 @@ static int fill_params(const GigsShade* a, ShadeParams& p, bool backward)
     p.g_render = a->g_render_rgb; p.g_diffuse = a->g_diffuse_rgb; p.g_specular = a->g_specular_rgb;
     p.g_albedo = a->g_albedo; p.g_roughness = a->g_roughness; p.g_metallic = a->g_metallic;
     p.g_diffuse_tex = a->g_diffuse_tex;
+    p.g_diffuse_stride = 0;
     return 0;
 }
 

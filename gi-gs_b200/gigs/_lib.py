@@ -107,7 +107,7 @@ class GigsFrameLayout(C.Structure):
         "color", "opacity", "depth", "normal", "normal_view", "pos", "albedo", "roughness", "metallic",
         "normal_from_depth", "depth_pos", "occlusion", "shade_normal", "ssr_normal", "render_direct", "linear_rgb",
         "F0", "rough_remap", "metal_used", "ssr_color", "ssr_abd", "render_rgb", "g_rgb", "g_albedo", "g_roughness",
-        "g_metallic", "mask", "median_sel", "partials", "stats", "total_bytes")]
+        "g_metallic", "mask", "median_sel", "tex_scratch", "partials", "stats", "total_bytes")]
 
 
 class GigsFrame(C.Structure):

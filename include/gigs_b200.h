@@ -275,6 +275,7 @@ typedef struct GigsFrameLayout {
     uint64_t g_albedo, g_roughness, g_metallic; /* dL/d G-buffer maps (backward) */
     uint64_t mask;           /* uint8 [H,W] normal_mask */
     uint64_t median_sel;     /* uint8 [3,H,W] window index the IRR median selected (255 = none) */
+    uint64_t tex_scratch;    /* float scratch: private copies of the small light-gradient textures (backward) */
     uint64_t partials;       /* float scratch for the deterministic loss reduction */
     uint64_t stats;          /* float[8]: loss, l1_mean, mask_count, sum((1-rough)*mask), sum(metal*mask), - */
     uint64_t total_bytes;
