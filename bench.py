@@ -216,7 +216,7 @@ def run_ours(args):
             cam, gt = cams[k], gts[k]
         loss = gstep.training_step(params, cam, light, lut, rays, gt, bg, gi, loss_scale=1.0 / world, fused=fused)
         if world > 1:
-            dist.all_reduce(params.flat_grad, op=dist.ReduceOp.SUM)
+            params.all_reduce_grads(fused_only=fused)
         if e2e:
             return float(loss.item())
         return loss

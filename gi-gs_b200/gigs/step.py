@@ -57,15 +57,29 @@ class GaussianParams:
         if not fused_only or self._dirty is None:
             self.flat_grad.zero_()
         else:
-            merged = []
-            for lo, hi in sorted(set(self._dirty)):
-                if merged and lo <= merged[-1][1]:
-                    merged[-1][1] = max(merged[-1][1], hi)
-                else:
-                    merged.append([lo, hi])
-            for lo, hi in merged:
+            for lo, hi in self._merged_dirty():
                 self.flat_grad[lo:hi].zero_()
         self._dirty = []
+
+    def _merged_dirty(self):
+        merged = []
+        for lo, hi in sorted(set(self._dirty)):
+            if merged and lo <= merged[-1][1]:
+                merged[-1][1] = max(merged[-1][1], hi)
+            else:
+                merged.append([lo, hi])
+        return merged
+
+    def all_reduce_grads(self, fused_only: bool = False):
+        """Sum the gradient buffer over the ranks of the default process group (view-sharded training).
+        With fused_only (same contract as zero_grad) only the spans the fused PBR path writes are exchanged:
+        12.6 MB instead of 87 MB at 300k Gaussians; everything else is zero on every rank."""
+        import torch.distributed as dist
+        if not fused_only or self._dirty is None:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)
+            return
+        for lo, hi in self._merged_dirty():
+            dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.SUM)
 
     def activated(self) -> Dict:
         """scene/gaussian_model.py:178-266 getters, autograd-tracked."""
@@ -118,7 +132,7 @@ def multi_view_step(params: GaussianParams, cams: List, light: Light, brdf_lut, 
                                       loss_scale=1.0 / K, **kw)
     if world > 1:
         import torch.distributed as dist
-        dist.all_reduce(params.flat_grad, op=dist.ReduceOp.SUM)
+        params.all_reduce_grads(fused_only=bool(kw.get("fused", True)))
         dist.all_reduce(total, op=dist.ReduceOp.SUM)
     return total
 

@@ -60,3 +60,46 @@ def test_sharded_allreduce_equals_single_rank_sum(tmp_path):
     ref = params.flat_grad
     assert sharded.shape == ref.shape
     assert float((sharded - ref).abs().max()) <= 1e-6 * float(ref.abs().max()) + 1e-9
+
+
+def _worker_spans(rank, world, port, out):
+    """The fused path's contract: only the material + light spans are written, zero_grad / all_reduce_grads with
+    fused_only=True touch exactly those spans (what bench.py and multi_view_step do on N GPUs)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    raw = scene.make_scene(40, seed=2)
+    params = gstep.GaussianParams(raw, "cpu", light=scene.make_light(0, base_res=32))
+    params.zero_grad()                       # unknown history -> full clear, tracking starts
+    keys = ["albedo", "roughness", "metallic"] + [f"light{i}" for i in range(len(params.light_leaves))]
+    params.mark_dirty(keys)
+    with torch.no_grad():
+        for k in ("albedo", "roughness", "metallic"):
+            params.leaves[k].grad.add_(float(rank + 1))
+        for t in params.light_leaves:
+            t.grad.add_(0.5 * (rank + 1))
+    params.all_reduce_grads(fused_only=True)
+    if rank == 0:
+        torch.save(dict(flat=params.flat_grad.clone(), spans=params._merged_dirty()), out)
+    params.zero_grad(fused_only=True)
+    assert float(params.flat_grad.abs().sum()) == 0.0
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_span_limited_allreduce_and_zero(tmp_path):
+    world = 2
+    out = str(tmp_path / "s.pt")
+    mp.spawn(_worker_spans, args=(world, _free_port(), out), nprocs=world, join=True)
+    r = torch.load(out)
+    raw = scene.make_scene(40, seed=2)
+    params = gstep.GaussianParams(raw, "cpu", light=scene.make_light(0, base_res=32))
+    assert len(r["spans"]) == 2              # [albedo|roughness|metallic] and the light textures: two collectives
+    want = torch.zeros_like(params.flat_grad)
+    for k in ("albedo", "roughness", "metallic"):
+        lo, hi = params._span[k]
+        want[lo:hi] = 3.0                    # (1) + (2)
+    for i in range(len(params.light_leaves)):
+        lo, hi = params._span[f"light{i}"]
+        want[lo:hi] = 1.5
+    assert torch.equal(r["flat"], want)
