@@ -24,7 +24,9 @@ struct BlendSmem {
     uint64_t bar[2];
 };
 
-template <bool LITE>
+// ARGMAX: track the heaviest contributor's depth / position (settings.argmax_depth); the training and evaluation
+// drivers leave it off, and then the three selects + two compares per contributing pair are dead weight.
+template <bool LITE, bool ARGMAX>
 __global__ void __launch_bounds__(BL_THREADS)
 blend_forward_kernel(const int W, const int H, const uint2* __restrict__ ranges,
                      const uint32_t* __restrict__ point_list, const float* __restrict__ records,
@@ -33,7 +35,7 @@ blend_forward_kernel(const int W, const int H, const uint2* __restrict__ ranges,
                      float* __restrict__ out_opacity, float* __restrict__ out_depth, float* __restrict__ out_normal,
                      float* __restrict__ out_normal_view, float* __restrict__ out_pos,
                      float* __restrict__ out_albedo, float* __restrict__ out_roughness,
-                     float* __restrict__ out_metallic, const bool argmax_depth, const bool inference)
+                     float* __restrict__ out_metallic, const bool inference)
 {
     extern __shared__ __align__(128) unsigned char bl_smem_raw[];
     BlendSmem& S = *reinterpret_cast<BlendSmem*>(bl_smem_raw);
@@ -74,9 +76,9 @@ blend_forward_kernel(const int W, const int H, const uint2* __restrict__ ranges,
 
     float T = 1.0f;
     uint32_t last_contributor = 0;
-    float C[3] = {0.f, 0.f, 0.f}, N[3] = {0.f, 0.f, 0.f}, A[3] = {0.f, 0.f, 0.f};
-    float Rg = 0.f, Mt = 0.f, D = 0.f, O = 0.f;
-    float3 POS = {0.f, 0.f, 0.f};
+    // accumulators in FFMA2 pairs: {C0,C1} {C2,roughness} {A0,A1} {A2,metallic} {N0,N1} {N2,pos.x} {pos.y,pos.z} {D,O}
+    const float2 z2 = make_float2(0.f, 0.f);
+    float2 C01 = z2, C2R = z2, A01 = z2, A2M = z2, N01 = z2, N2P = z2, PYZ = z2, DO = z2;
     float max_weight = 0.f, except_depth = 0.f;
     float3 except_pos = {0.f, 0.f, 0.f};
 
@@ -133,30 +135,24 @@ blend_forward_kernel(const int W, const int H, const uint2* __restrict__ ranges,
                 }
                 const float weight = alpha * T;
                 const float4 q2 = *reinterpret_cast<const float4*>(&S.rec[s][j][8]);
-                C[0] += q2.x * weight;
-                C[1] += q2.y * weight;
-                C[2] += q2.z * weight;
                 const float depth = q1.z;
+                const float2 w2 = make_float2(weight, weight);
+                // the 17 accumulations as 8 packed FMAs (FFMA2); halves round exactly like the scalar fma
+                C01 = ffma2(make_float2(q2.x, q2.y), w2, C01);
+                C2R = ffma2(make_float2(q2.z, q2.w), w2, C2R);
                 if (!LITE) {
                     const float4 q3 = *reinterpret_cast<const float4*>(&S.rec[s][j][12]);
                     const float4 q4 = *reinterpret_cast<const float4*>(&S.rec[s][j][16]);
                     const float2 q5 = *reinterpret_cast<const float2*>(&S.rec[s][j][20]);
-                    A[0] += q3.x * weight;
-                    A[1] += q3.y * weight;
-                    A[2] += q3.z * weight;
-                    N[0] += q4.x * weight;
-                    N[1] += q4.y * weight;
-                    N[2] += q4.z * weight;
-                    Rg += q2.w * weight;
-                    Mt += q3.w * weight;
-                    POS.x += q4.w * weight;
-                    POS.y += q5.x * weight;
-                    POS.z += q5.y * weight;
-                    if (weight > max_weight) except_pos = make_float3(q4.w, q5.x, q5.y);
+                    A01 = ffma2(make_float2(q3.x, q3.y), w2, A01);
+                    A2M = ffma2(make_float2(q3.z, q3.w), w2, A2M);
+                    N01 = ffma2(make_float2(q4.x, q4.y), w2, N01);
+                    N2P = ffma2(make_float2(q4.z, q4.w), w2, N2P);
+                    PYZ = ffma2(q5, w2, PYZ);
+                    if (ARGMAX && weight > max_weight) except_pos = make_float3(q4.w, q5.x, q5.y);
                 }
-                D += depth * weight;
-                O += weight;
-                if (weight > max_weight) {
+                DO = ffma2(make_float2(depth, 1.0f), w2, DO);
+                if (ARGMAX && weight > max_weight) {
                     except_depth = depth;
                     max_weight = weight;
                 }
@@ -173,6 +169,9 @@ blend_forward_kernel(const int W, const int H, const uint2* __restrict__ ranges,
     }
 
     if (inside) {
+        const float C[3] = {C01.x, C01.y, C2R.x}, N[3] = {N01.x, N01.y, N2P.x}, A[3] = {A01.x, A01.y, A2M.x};
+        const float Rg = C2R.y, Mt = A2M.y, D = DO.x, O = DO.y;
+        const float3 POS = make_float3(N2P.y, PYZ.x, PYZ.y);
         const int HW = H * W;
         final_T[pix_id] = T;
         n_contrib[pix_id] = last_contributor;
@@ -195,11 +194,11 @@ blend_forward_kernel(const int W, const int H, const uint2* __restrict__ ranges,
             out_metallic[pix_id] = Mt;
         }
         if (O > 1e-6) {
-            out_depth[pix_id] = argmax_depth ? except_depth : D / O;
+            out_depth[pix_id] = ARGMAX ? except_depth : D / O;
             if (!LITE) {
-                out_pos[pix_id] = argmax_depth ? except_pos.x : POS.x / O;
-                out_pos[HW + pix_id] = argmax_depth ? except_pos.y : POS.y / O;
-                out_pos[2 * HW + pix_id] = argmax_depth ? except_pos.z : POS.z / O;
+                out_pos[pix_id] = ARGMAX ? except_pos.x : POS.x / O;
+                out_pos[HW + pix_id] = ARGMAX ? except_pos.y : POS.y / O;
+                out_pos[2 * HW + pix_id] = ARGMAX ? except_pos.z : POS.z / O;
             }
         } else {
             out_depth[pix_id] = 0.0f;
@@ -222,10 +221,11 @@ int launch_blend_forward(const GigsRasterFwd* a, const Layout& L, bool lite, cud
     dim3 grid(L.tiles_x, L.tiles_y, 1), block(TILE_X, TILE_Y, 1);
     static bool attr_set = false;
     if (!attr_set) {
-        GIGS_CUDA(cudaFuncSetAttribute(blend_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sizeof(BlendSmem)));
-        GIGS_CUDA(cudaFuncSetAttribute(blend_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sizeof(BlendSmem)));
+        const int sm = (int)sizeof(BlendSmem);
+        GIGS_CUDA(cudaFuncSetAttribute(blend_forward_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        GIGS_CUDA(cudaFuncSetAttribute(blend_forward_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        GIGS_CUDA(cudaFuncSetAttribute(blend_forward_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        GIGS_CUDA(cudaFuncSetAttribute(blend_forward_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
         attr_set = true;
     }
     const uint2* ranges = (const uint2*)(im + L.off.i_ranges);
@@ -233,15 +233,18 @@ int launch_blend_forward(const GigsRasterFwd* a, const Layout& L, bool lite, cud
     const float* recs = (const float*)(g + L.off.g_record);
     uint32_t* ncontrib = (uint32_t*)(im + L.off.i_n_contrib);
     float* finalT = (float*)(im + L.off.i_final_T);
-    if (lite)
-        blend_forward_kernel<true><<<grid, block, sizeof(BlendSmem), st>>>(
-            c.width, c.height, ranges, plist, recs, c.viewmatrix, c.bg, ncontrib, finalT, a->out_color, a->out_opacity,
-            a->out_depth, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, c.argmax_depth != 0, false);
-    else
-        blend_forward_kernel<false><<<grid, block, sizeof(BlendSmem), st>>>(
-            c.width, c.height, ranges, plist, recs, c.viewmatrix, c.bg, ncontrib, finalT, a->out_color, a->out_opacity,
-            a->out_depth, a->out_normal, a->out_normal_view, a->out_pos, a->out_albedo, a->out_roughness,
-            a->out_metallic, c.argmax_depth != 0, c.inference != 0);
+    const bool am = c.argmax_depth != 0;
+#define BL_LITE_ARGS c.width, c.height, ranges, plist, recs, c.viewmatrix, c.bg, ncontrib, finalT, a->out_color, a->out_opacity, \
+                     a->out_depth, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, false
+#define BL_FULL_ARGS c.width, c.height, ranges, plist, recs, c.viewmatrix, c.bg, ncontrib, finalT, a->out_color, a->out_opacity, \
+                     a->out_depth, a->out_normal, a->out_normal_view, a->out_pos, a->out_albedo, a->out_roughness,             \
+                     a->out_metallic, c.inference != 0
+    if (lite && am) blend_forward_kernel<true, true><<<grid, block, sizeof(BlendSmem), st>>>(BL_LITE_ARGS);
+    else if (lite) blend_forward_kernel<true, false><<<grid, block, sizeof(BlendSmem), st>>>(BL_LITE_ARGS);
+    else if (am) blend_forward_kernel<false, true><<<grid, block, sizeof(BlendSmem), st>>>(BL_FULL_ARGS);
+    else blend_forward_kernel<false, false><<<grid, block, sizeof(BlendSmem), st>>>(BL_FULL_ARGS);
+#undef BL_LITE_ARGS
+#undef BL_FULL_ARGS
     GIGS_LAUNCH_CHECK("blend_forward_kernel");
     return 0;
 }

@@ -217,6 +217,23 @@ __device__ __forceinline__ void red_add_f32(float* addr, float a)
 {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
 }
+// Blackwell packed FP32: d = a * b + c on two lanes of a 64-bit register pair (SASS FFMA2). Each half rounds exactly
+// like a scalar fma, so accumulations stay bit-identical while the FMA instruction count halves.
+__device__ __forceinline__ float2 ffma2(const float2 a, const float2 b, const float2 c)
+{
+    float2 d;
+    asm("{\n"
+        ".reg .b64 ra, rb, rc, rd;\n"
+        "mov.b64 ra, {%2, %3};\n"
+        "mov.b64 rb, {%4, %5};\n"
+        "mov.b64 rc, {%6, %7};\n"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n"
+        "mov.b64 {%0, %1}, rd;\n"
+        "}\n"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
 __device__ __forceinline__ float4 ld_nc_f4(const float* p)
 {
     float4 r;
