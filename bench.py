@@ -191,10 +191,10 @@ def run_ours(args):
     K_cams = 8
     cams_host = [scene.orbit_camera(k, K_cams, args.W, args.H) for k in range(K_cams)]
     cams = [c.to(dev) for c in cams_host]
-    for c in cams_host:  # page-locked host copies for the e2e leg
-        c.world_view_transform = c.world_view_transform.pin_memory()
-        c.full_proj_transform = c.full_proj_transform.pin_memory()
-        c.camera_center = c.camera_center.pin_memory()
+    # page-locked host copies for the e2e leg: view matrix, projection matrix and camera centre packed per view
+    cam_packed_host = [torch.cat([c.world_view_transform.reshape(-1), c.full_proj_transform.reshape(-1),
+                                  c.camera_center.reshape(-1)]).float().contiguous().pin_memory() for c in cams_host]
+    copy_stream = torch.cuda.Stream(device=dev)
     rays = scene.canonical_rays(cams[0], dev)
     ggen = torch.Generator().manual_seed(7)
     gts_host = [torch.rand(3, args.H, args.W, generator=ggen).pin_memory() for _ in range(K_cams)]
@@ -205,16 +205,27 @@ def run_ours(args):
     def one_step(i, gi, e2e=False, fused=True):
         k = (i * world + rank) % K_cams
         params.zero_grad(fused_only=fused)
+        gt_ready = None
         if e2e:
+            # this step's inputs come from pinned HOST memory: the camera (one packed 35-float copy on the compute
+            # stream, preprocess needs it first) and the ground-truth image (7.7 MB on a copy stream; the frame waits
+            # for it only right before the loss kernel, so the transfer overlaps the rasterizer)
             ch = cams_host[k]
-            cam = scene.Camera(ch.image_width, ch.image_height, ch.FoVx, ch.FoVy,
-                               ch.world_view_transform.to(dev, non_blocking=True),
-                               ch.full_proj_transform.to(dev, non_blocking=True),
-                               ch.camera_center.to(dev, non_blocking=True))
-            gt = gts_host[k].to(dev, non_blocking=True)
+            cp = cam_packed_host[k].to(dev, non_blocking=True)
+            cam = scene.Camera(ch.image_width, ch.image_height, ch.FoVx, ch.FoVy, cp[0:16].view(4, 4),
+                               cp[16:32].view(4, 4), cp[32:35])
+            if fused:
+                with torch.cuda.stream(copy_stream):
+                    gt = gts_host[k].to(dev, non_blocking=True)
+                    gt_ready = torch.cuda.Event()
+                    gt_ready.record(copy_stream)
+                gt.record_stream(torch.cuda.current_stream())
+            else:
+                gt = gts_host[k].to(dev, non_blocking=True)
         else:
             cam, gt = cams[k], gts[k]
-        loss = gstep.training_step(params, cam, light, lut, rays, gt, bg, gi, loss_scale=1.0 / world, fused=fused)
+        loss = gstep.training_step(params, cam, light, lut, rays, gt, bg, gi, loss_scale=1.0 / world, fused=fused,
+                                   gt_ready=gt_ready)
         if world > 1:
             params.all_reduce_grads(fused_only=fused)
         if e2e:

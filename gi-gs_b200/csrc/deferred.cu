@@ -613,6 +613,7 @@ int gigs_frame_forward(GigsFrame* f)
                          (float*)(m + FL.depth_pos), p.linear_rgb, p.albedo, p.rough_remap, p.metal_used, p.F0,
                          (float*)(m + FL.ssr_color), (float*)(m + FL.ssr_abd), f->stream))
         return e;
+    if (f->gt_ready_event) GIGS_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)f->gt_ready_event, 0));
     {
         ProfScope ps(ST_DEFER_LOSS, st);
         deferred_loss_kernel<<<grid, block, 0, st>>>(p);

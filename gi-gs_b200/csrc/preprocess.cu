@@ -13,6 +13,7 @@
 // bit-exact, which requires nvcc to contract the same FMAs. The data flow is ours: one packed 96-B
 // record per visible Gaussian instead of seven scattered arrays, block sums fused into this
 // kernel instead of a device-wide scan pass, warp-cooperative key emission.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace gigs {
@@ -138,7 +139,7 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
                   const float* __restrict__ viewmatrix, const float* __restrict__ projmatrix,
                   const float* __restrict__ cam_pos, const int W, const int H, const float tan_fovx,
                   const float tan_fovy, const float focal_x, const float focal_y, const uint32_t grid_x,
-                  const uint32_t grid_y, const bool prefiltered,
+                  const uint32_t grid_y, const bool prefiltered, const bool stage_sh,
                   // outputs
                   int* __restrict__ radii, float* __restrict__ records, float* __restrict__ cov3Ds,
                   uint8_t* __restrict__ clamped, uint32_t* __restrict__ tiles_touched,
@@ -151,6 +152,27 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
         sPM[threadIdx.x] = projmatrix[threadIdx.x];
     }
     if (threadIdx.x < 3) sCam[threadIdx.x] = cam_pos[threadIdx.x];
+
+    // The SH coefficients are the bulk of this kernel's traffic (180 B of its 244 B per Gaussian at degree 3) and an
+    // array of structures: one thread reading its own 45 floats touches a new 128-B line with every load (measured:
+    // long-scoreboard + lg_throttle stalls, 35 % of HBM peak). The 256 Gaussians of a CTA own one CONTIGUOUS 46 KB
+    // slab of it, so a single TMA bulk copy stages the slab while the threads do the projection / covariance maths;
+    // each thread then reads its coefficients from shared memory (stride 45 words: conflict free).
+    extern __shared__ __align__(128) float s_sh[];
+    __shared__ uint64_t s_bar;
+    const int sh_stride = RAW ? (M - 1) * 3 : M * 3;                       // floats per Gaussian in the staged array
+    const float* sh_src = RAW ? sh_rest : shs;
+    const int cta_cnt = min(PRE_THREADS, P - (int)blockIdx.x * PRE_THREADS);
+    const uint32_t sh_bytes = (uint32_t)cta_cnt * sh_stride * 4u;
+    // staged only when the slab is a whole number of 16-B units (always true for full CTAs at the usual degrees)
+    const bool staged = (colors_precomp == nullptr) && sh_src != nullptr && sh_stride > 0 && (sh_bytes % 16u == 0u) &&
+                        (((size_t)blockIdx.x * PRE_THREADS * sh_stride * 4u) % 16u == 0u) && stage_sh;
+    if (threadIdx.x == 0 && staged) {
+        mbar_init(&s_bar, 1);
+        mbar_fence_init();
+        mbar_arrive_expect_tx(&s_bar, sh_bytes);
+        bulk_g2s(s_sh, sh_src + (size_t)blockIdx.x * PRE_THREADS * sh_stride, sh_bytes, &s_bar);
+    }
     __syncthreads();
 
     const int idx = blockIdx.x * PRE_THREADS + threadIdx.x;
@@ -211,6 +233,15 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
                 bool cl[3];
                 const float* sh0 = RAW ? shs + (size_t)idx * 3 : shs + (size_t)idx * M * 3;
                 const float* shr = RAW ? sh_rest + ((size_t)idx * (M - 1) - 1) * 3 : sh0;
+                if (staged) {
+                    mbar_wait(&s_bar, 0);
+                    if (RAW) {
+                        shr = s_sh + (int)threadIdx.x * sh_stride - 3;
+                    } else {
+                        sh0 = s_sh + (int)threadIdx.x * sh_stride;
+                        shr = sh0;
+                    }
+                }
                 V3 c = sh_to_rgb(D, V3{p_orig.x, p_orig.y, p_orig.z}, V3{sCam[0], sCam[1], sCam[2]}, sh0, shr, cl);
                 rgb = make_float3(c.x, c.y, c.z);
                 *reinterpret_cast<uchar4*>(clamped + 4 * (size_t)idx) =
@@ -252,6 +283,9 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
         tiles_touched[idx] = touched;
         depth_keys[idx] = depth_key;
     }
+
+    // never leave the CTA with the bulk copy into its shared memory still in flight (culled threads did not wait)
+    if (staged) mbar_wait(&s_bar, 0);
 
     // fused block sum of tiles_touched (feeds the single-block scan of block sums)
     uint32_t v = touched;
@@ -435,13 +469,24 @@ int launch_preprocess(const GigsRasterFwd* a, const Layout& L, cudaStream_t st, 
     P, c.sh_degree, c.sh_coeffs, a->means3D, a->scales, c.scale_modifier, a->rotations, a->opacities, a->shs, sh_rest, \
         a->cov3D_precomp, a->colors_precomp, a->normal, a->albedo, a->roughness, a->metallic, c.viewmatrix,           \
         c.projmatrix, c.campos, c.width, c.height, c.tan_fovx, c.tan_fovy, focal_x, focal_y, L.tiles_x, L.tiles_y,    \
-        c.prefiltered != 0, a->radii, (float*)(g + L.off.g_record), (float*)(g + L.off.g_cov3D),                      \
+        c.prefiltered != 0, stage_sh, a->radii, (float*)(g + L.off.g_record), (float*)(g + L.off.g_cov3D),            \
         (uint8_t*)(g + L.off.g_clamped), (uint32_t*)(g + L.off.g_tiles_touched), (uint32_t*)(g + L.off.g_depth_keys), \
         (uint32_t*)(g + L.off.g_block_sums)
+    // dynamic shared memory: the CTA's slab of SH coefficients (see the kernel); not staged if it would not fit
+    const size_t sh_floats = (size_t)PRE_THREADS * (sh_rest ? (c.sh_coeffs - 1) * 3 : c.sh_coeffs * 3);
+    static const bool no_stage = getenv("GIGS_PRE_NOSTAGE") != nullptr;
+    const bool stage_sh = !no_stage && a->colors_precomp == nullptr && sh_floats > 0 && sh_floats * 4 <= 96 * 1024;
+    const size_t smem = stage_sh ? sh_floats * 4 : 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GIGS_CUDA(cudaFuncSetAttribute(preprocess_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        GIGS_CUDA(cudaFuncSetAttribute(preprocess_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr_set = true;
+    }
     if (sh_rest != nullptr)
-        preprocess_kernel<true><<<L.num_blocks, PRE_THREADS, 0, st>>>(PRE_ARGS);
+        preprocess_kernel<true><<<L.num_blocks, PRE_THREADS, smem, st>>>(PRE_ARGS);
     else
-        preprocess_kernel<false><<<L.num_blocks, PRE_THREADS, 0, st>>>(PRE_ARGS);
+        preprocess_kernel<false><<<L.num_blocks, PRE_THREADS, smem, st>>>(PRE_ARGS);
 #undef PRE_ARGS
     GIGS_LAUNCH_CHECK("preprocess_kernel");
     scan_block_sums_kernel<<<1, 1024, 0, st>>>((uint32_t*)(g + L.off.g_block_sums), (int)L.num_blocks,

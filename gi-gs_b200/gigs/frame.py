@@ -82,9 +82,13 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
-def _fill(ws: FrameWorkspace, cam, bg, params: Dict, raw: bool, sh_degree: int, light, brdf_lut, rays, gt, gi: Dict,
-          indirect: bool, metallic: bool, tone: bool, gamma: bool, loss_scale: float, lamb_weight: float, keep: list):
-    """params: raw leaves (xyz, f_dc, f_rest, opacity, normal, albedo, roughness, metallic, log_scale, rot) when `raw`,
+def make_frame(ws: FrameWorkspace, cam, bg, params: Dict, raw: bool, sh_degree: int, light, brdf_lut, rays, gt,
+               gi: Dict, indirect: bool, metallic: bool, tone: bool, gamma: bool, loss_scale: float, lamb_weight: float,
+               keep: list, gt_ready: Optional[torch.cuda.Event] = None) -> GigsFrame:
+    """Fill the C-ABI argument struct of one frame. `keep` receives every tensor whose pointer went into the struct
+    (hold it until the calls are done). gt_ready: an event recorded on the stream that copies `gt` to the device; the
+    frame's stream waits on it only right before the loss kernel, so the copy overlaps the rasterizer.
+    params: raw leaves (xyz, f_dc, f_rest, opacity, normal, albedo, roughness, metallic, log_scale, rot) when `raw`,
     else activated tensors (means3D, shs, opacity, normal, albedo, roughness, metallic, scales, rotations)."""
     f = GigsFrame()
     f.P = ws.P
@@ -135,8 +139,14 @@ def _fill(ws: FrameWorkspace, cam, bg, params: Dict, raw: bool, sh_degree: int, 
     f.maps = ws.maps.data_ptr(); f.maps_bytes = ws.maps.numel()
     f.radii = ws.radii.data_ptr(); f.accum = ws.accum.data_ptr()
     f.pinned_num_rendered = ws.pinned.data_ptr()
+    if gt_ready is not None:
+        keep.append(gt_ready)
+        f.gt_ready_event = gt_ready.cuda_event
     f.stream = torch.cuda.current_stream().cuda_stream
     return f
+
+
+_fill = make_frame
 
 
 def _set_sort(ws: FrameWorkspace, f: GigsFrame):
@@ -183,15 +193,15 @@ def _grad_of(t: torch.Tensor) -> Optional[torch.Tensor]:
 
 def pbr_frame_step(params, cam, light, brdf_lut, rays, gt_image, background, gi: Dict, metallic=True, gamma=True,
                    tone=False, indirect=True, loss_scale: float = 1.0, lamb_weight: float = 0.001,
-                   backward: bool = True) -> torch.Tensor:
+                   backward: bool = True, gt_ready: Optional[torch.cuda.Event] = None) -> torch.Tensor:
     """forward (+ backward) of one PBR-stage view for a gigs.step.GaussianParams: gradients accumulate into
     params.flat_grad exactly as autograd would through the unfused path. Returns the (detached) loss scalar."""
     L = params.leaves
     dev = L["xyz"].device
     ws = workspace(params.P, int(cam.image_width), int(cam.image_height), dev)
     keep: list = []
-    f = _fill(ws, cam, background, L, True, params.sh_degree, light, brdf_lut, rays, gt_image, gi, indirect, metallic,
-              tone, gamma, loss_scale, lamb_weight, keep)
+    f = make_frame(ws, cam, background, L, True, params.sh_degree, light, brdf_lut, rays, gt_image, gi, indirect,
+                   metallic, tone, gamma, loss_scale, lamb_weight, keep, gt_ready=gt_ready)
     loss = frame_forward(ws, f)
     if backward:
         frame_backward(ws, f, _grad_of(L["albedo"]), _grad_of(L["roughness"]),

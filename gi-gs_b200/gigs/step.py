@@ -98,7 +98,7 @@ class GaussianParams:
 
 def training_step(params: GaussianParams, cam, light: Light, brdf_lut, rays, gt_image, background, gi: Dict,
                   metallic=True, gamma=True, tone=False, indirect=True, loss_scale: float = 1.0,
-                  fused: bool = True) -> torch.Tensor:
+                  fused: bool = True, gt_ready=None) -> torch.Tensor:
     """forward + loss + backward for ONE view; gradients accumulate into params.flat_grad.
 
     fused=True (default) runs the frame as two C-ABI calls (gigs.frame: activations, rasterizer, deferred shading /
@@ -109,7 +109,9 @@ def training_step(params: GaussianParams, cam, light: Light, brdf_lut, rays, gt_
         from .frame import pbr_frame_step
         params.mark_dirty(["albedo", "roughness", "metallic"] + [f"light{i}" for i in range(len(params.light_leaves))])
         return pbr_frame_step(params, cam, light, brdf_lut, rays, gt_image, background, gi, metallic=metallic,
-                              gamma=gamma, tone=tone, indirect=indirect, loss_scale=loss_scale)
+                              gamma=gamma, tone=tone, indirect=indirect, loss_scale=loss_scale, gt_ready=gt_ready)
+    if gt_ready is not None:
+        torch.cuda.current_stream().wait_event(gt_ready)
     params.mark_dirty(None)
     g = params.activated()
     res = pbr_forward(cam, g, light, brdf_lut, rays, background, indirect=indirect, metallic=metallic, tone=tone,

@@ -310,6 +310,8 @@ typedef struct GigsFrame {
     /* backward outputs, accumulated (+=); per-Gaussian ones are in raw-parameter space when raw_params */
     float* g_albedo; float* g_roughness; float* g_metallic;   /* [P,3], [P], [P] */
     float* g_diffuse_tex; float* g_spec[8];
+    void* gt_ready_event;        /* cudaEvent_t or NULL: the stream waits on it right before the loss kernel, so the
+                                    host->device copy of gt_image (issued on another stream) overlaps the rasterizer */
     void* stream;
 } GigsFrame;
 #define GIGS_E_GROW (-5) /* binning / sort workspace too small: grow to need_*_bytes and call again with resume=1 */

@@ -187,3 +187,25 @@ def test_frame_forward_only_without_ground_truth():
     with torch.no_grad():
         res = renderer.pbr_forward(cam, p.activated(), p.light(), lut, rays, bg, gi=GI8, inference=False)
     assert ((rgb - res["render_rgb"]).abs() > 1e-4).float().mean().item() < 2e-3
+
+
+def test_frame_waits_for_the_ground_truth_event():
+    """gt_ready: the ground-truth image is copied on a side stream and the frame waits for it only before the loss."""
+    P, W, H = 4000, 128, 96
+    raw, cam, lut, rays, gt, bg = _setup(P, W, H)
+    p = gstep.GaussianParams(raw, DEV, light=scene.make_light(0, base_res=32))
+    p.zero_grad()
+    l_ref = float(gstep.training_step(p, cam, p.light(), lut, rays, gt, bg, GI8))
+    g_ref = p.flat_grad.clone()
+    host = gt.cpu().pin_memory()
+    side = torch.cuda.Stream()
+    p.zero_grad()
+    with torch.cuda.stream(side):
+        torch.cuda._sleep(20_000_000)                  # make the copy late on purpose
+        gt2 = host.to(DEV, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(side)
+    gt2.record_stream(torch.cuda.current_stream())
+    l2 = float(gstep.training_step(p, cam, p.light(), lut, rays, gt2, bg, GI8, gt_ready=ev))
+    assert l2 == l_ref
+    assert torch.allclose(p.flat_grad, g_ref, rtol=1e-5, atol=1e-10)
