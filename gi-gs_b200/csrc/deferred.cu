@@ -480,7 +480,7 @@ static void fill_raster_fwd(const GigsFrame* f, const GigsFrameLayout& FL, GigsR
     char* m = (char*)f->maps;
     a.P = f->P;
     a.cam = f->cam;
-    a.cam.prefiltered = 0; a.cam.inference = 0; a.cam.argmax_depth = 0;
+    a.cam.prefiltered = 0; a.cam.argmax_depth = 0;   // cam.inference is honoured (eval / relight sweeps, forward only)
     a.means3D = f->means3D; a.shs = f->sh_dc; a.opacities = f->opacities; a.normal = f->normal; a.albedo = f->albedo;
     a.roughness = f->roughness; a.metallic = f->metallic; a.scales = f->scales; a.rotations = f->rotations;
     a.out_color = (float*)(m + FL.color); a.out_opacity = (float*)(m + FL.opacity); a.out_depth = (float*)(m + FL.depth);

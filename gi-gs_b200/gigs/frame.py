@@ -84,7 +84,7 @@ def _p(t):
 
 def make_frame(ws: FrameWorkspace, cam, bg, params: Dict, raw: bool, sh_degree: int, light, brdf_lut, rays, gt,
                gi: Dict, indirect: bool, metallic: bool, tone: bool, gamma: bool, loss_scale: float, lamb_weight: float,
-               keep: list, gt_ready: Optional[torch.cuda.Event] = None) -> GigsFrame:
+               keep: list, gt_ready: Optional[torch.cuda.Event] = None, inference: bool = False) -> GigsFrame:
     """Fill the C-ABI argument struct of one frame. `keep` receives every tensor whose pointer went into the struct
     (hold it until the calls are done). gt_ready: an event recorded on the stream that copies `gt` to the device; the
     frame's stream waits on it only right before the loss kernel, so the copy overlaps the rasterizer.
@@ -115,7 +115,7 @@ def make_frame(ws: FrameWorkspace, cam, bg, params: Dict, raw: bool, sh_degree: 
     f.normal = _p(c32(params["normal"])); f.albedo = _p(c32(params["albedo"]))
     f.roughness = _p(c32(params["roughness"])); f.metallic = _p(c32(params["metallic"]))
     f.cam = GigsCamera(int(cam.image_width), int(cam.image_height), float(cam.tanfovx), float(cam.tanfovy), 1.0,
-                       int(sh_degree), int(M), 0, 0, 0, 0, _p(vm), _p(pm), _p(cp), _p(bgc))
+                       int(sh_degree), int(M), 0, 0, int(bool(inference)), 0, _p(vm), _p(pm), _p(cp), _p(bgc))
     f.radius = float(gi.get("radius", 0.8)); f.bias = float(gi.get("bias", 0.01)); f.thick = float(gi.get("thick", 0.05))
     f.delta = float(gi.get("delta", 0.0625)); f.step = int(gi.get("step", 16)); f.start = int(gi.get("start", 8))
     f.indirect = int(bool(indirect)); f.use_metallic = int(bool(metallic)); f.tone = int(bool(tone))
@@ -178,6 +178,22 @@ def frame_backward(ws: FrameWorkspace, f: GigsFrame, g_albedo, g_roughness, g_me
         f.g_spec[i] = _p(g_spec[i]) if (g_spec is not None and i < len(g_spec)) else None
     with torch.cuda.device(ws.device):
         check(_L.gigs_frame_backward(C.byref(f)), "gigs_frame_backward")
+
+
+def pbr_frame_eval(g: Dict, cam, light, brdf_lut, rays, background, gi: Dict, metallic=True, gamma=True, tone=False,
+                   indirect=True, inference=True, raw: bool = False, sh_degree: Optional[int] = None) -> FrameWorkspace:
+    """Forward-only frame for the evaluation / relighting sweeps (render.py:202-333, relight.py:114-251): G-buffer,
+    SSAO, shading, SSR, final image, no loss. `g` holds activated tensors (scene.activate / GaussianParams.activated)
+    or raw leaves (raw=True). Returns the workspace; ws.map("render_rgb") etc. are views valid until the next frame."""
+    P = (g["xyz"] if raw else g["means3D"]).shape[0]
+    dev = (g["xyz"] if raw else g["means3D"]).device
+    ws = workspace(P, int(cam.image_width), int(cam.image_height), dev)
+    keep: list = []
+    deg = g["sh_degree"] if sh_degree is None else sh_degree
+    f = make_frame(ws, cam, background, g, raw, deg, light, brdf_lut, rays, None, gi, indirect, metallic, tone, gamma,
+                   1.0, 0.0, keep, inference=inference)
+    frame_forward(ws, f)
+    return ws
 
 
 def _grad_of(t: torch.Tensor) -> Optional[torch.Tensor]:

@@ -114,6 +114,14 @@ def test_c5_camera_sharded_inference_sweep():
         for k in range(V):
             assert torch.equal(torch.nan_to_num(got[k]), torch.nan_to_num(full[k]))
     assert all(torch.isfinite(f).all() for f in full)
+    # the fused forward-only frame renders the same views (eval sweeps do not need the operator path)
+    from gigs import frame as gframe
+    for k in (0, 3):
+        ws = gframe.pbr_frame_eval(g, cams[k], light, lut, rays, bg, gi8, inference=True)
+        d = (ws.map("render_rgb") - full[k]).abs()
+        assert (torch.nan_to_num(d) > 1e-4).float().mean().item() < 2e-3, float(torch.nan_to_num(d).max())
+        assert torch.equal(ws.map("roughness"), renderer.render(cams[k], g, bg, inference=True, derive_normal=True,
+                                                                **gi8)["roughness_map"])
     # inference adds the residual transmittance to roughness (forward.cu:612-613)
     a = U.ours_forward(g, cams[0], bg, inference=True)
     b = U.ours_forward(g, cams[0], bg, inference=False)
