@@ -224,9 +224,12 @@ def run_ours(args):
                 gt = gts_host[k].to(dev, non_blocking=True)
         else:
             cam, gt = cams[k], gts[k]
+        light_ready = torch.cuda.Event() if (world > 1 and fused) else None
         loss = gstep.training_step(params, cam, light, lut, rays, gt, bg, gi, loss_scale=1.0 / world, fused=fused,
-                                   gt_ready=gt_ready)
+                                   gt_ready=gt_ready, light_ready=light_ready)
         if world > 1:
+            if light_ready is not None:
+                params.begin_light_all_reduce(light_ready)   # overlaps the blend backward
             params.all_reduce_grads(fused_only=fused)
         if e2e:
             return float(loss.item())

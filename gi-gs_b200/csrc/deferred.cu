@@ -669,6 +669,7 @@ int gigs_frame_backward(GigsFrame* f)
             GIGS_LAUNCH_CHECK("texel_fold_kernel");
         }
     }
+    if (f->light_ready_event) GIGS_CUDA(cudaEventRecord((cudaEvent_t)f->light_ready_event, st));
     GigsRasterBwd b;
     memset(&b, 0, sizeof(b));
     b.P = f->P; b.num_rendered = f->num_rendered; b.cam = c;

@@ -134,6 +134,7 @@ class GigsFrame(C.Structure):
         ("g_albedo", C.c_void_p), ("g_roughness", C.c_void_p), ("g_metallic", C.c_void_p),
         ("g_diffuse_tex", C.c_void_p), ("g_spec", C.c_void_p * 8),
         ("gt_ready_event", C.c_void_p),
+        ("light_ready_event", C.c_void_p),
         ("stream", C.c_void_p),
     ]
 

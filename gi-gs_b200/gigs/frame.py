@@ -170,8 +170,17 @@ def frame_forward(ws: FrameWorkspace, f: GigsFrame) -> torch.Tensor:
     return ws.map("stats")[0]
 
 
-def frame_backward(ws: FrameWorkspace, f: GigsFrame, g_albedo, g_roughness, g_metallic, g_diffuse_tex, g_spec):
-    """Accumulates (+=) into the given gradient tensors (contiguous float32; None = not wanted)."""
+def frame_backward(ws: FrameWorkspace, f: GigsFrame, g_albedo, g_roughness, g_metallic, g_diffuse_tex, g_spec,
+                   light_ready: Optional[torch.cuda.Event] = None):
+    """Accumulates (+=) into the given gradient tensors (contiguous float32; None = not wanted). light_ready is
+    recorded on the stream as soon as the light-texture gradients are final (before the blend backward)."""
+    if light_ready is not None:
+        # torch creates the cudaEvent lazily on first record: materialise the handle (the C side re-records it at the
+        # right point; a wait issued after this call returns sees that later record)
+        light_ready.record()
+        f.light_ready_event = light_ready.cuda_event
+    else:
+        f.light_ready_event = None
     f.g_albedo = _p(g_albedo); f.g_roughness = _p(g_roughness); f.g_metallic = _p(g_metallic)
     f.g_diffuse_tex = _p(g_diffuse_tex)
     for i in range(8):
@@ -209,7 +218,8 @@ def _grad_of(t: torch.Tensor) -> Optional[torch.Tensor]:
 
 def pbr_frame_step(params, cam, light, brdf_lut, rays, gt_image, background, gi: Dict, metallic=True, gamma=True,
                    tone=False, indirect=True, loss_scale: float = 1.0, lamb_weight: float = 0.001,
-                   backward: bool = True, gt_ready: Optional[torch.cuda.Event] = None) -> torch.Tensor:
+                   backward: bool = True, gt_ready: Optional[torch.cuda.Event] = None,
+                   light_ready: Optional[torch.cuda.Event] = None) -> torch.Tensor:
     """forward (+ backward) of one PBR-stage view for a gigs.step.GaussianParams: gradients accumulate into
     params.flat_grad exactly as autograd would through the unfused path. Returns the (detached) loss scalar."""
     L = params.leaves
@@ -222,6 +232,6 @@ def pbr_frame_step(params, cam, light, brdf_lut, rays, gt_image, background, gi:
     if backward:
         frame_backward(ws, f, _grad_of(L["albedo"]), _grad_of(L["roughness"]),
                        _grad_of(L["metallic"]) if metallic else None, _grad_of(light.diffuse),
-                       [_grad_of(t) for t in light.specular])
+                       [_grad_of(t) for t in light.specular], light_ready=light_ready)
     params.last_workspace = ws
     return loss.clone()

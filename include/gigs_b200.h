@@ -312,6 +312,8 @@ typedef struct GigsFrame {
     float* g_diffuse_tex; float* g_spec[8];
     void* gt_ready_event;        /* cudaEvent_t or NULL: the stream waits on it right before the loss kernel, so the
                                     host->device copy of gt_image (issued on another stream) overlaps the rasterizer */
+    void* light_ready_event;     /* cudaEvent_t or NULL: recorded in backward once the light-texture gradients are final
+                                    (before the blend backward), so their all-reduce can overlap the rest */
     void* stream;
 } GigsFrame;
 #define GIGS_E_GROW (-5) /* binning / sort workspace too small: grow to need_*_bytes and call again with resume=1 */

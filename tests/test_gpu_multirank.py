@@ -1,0 +1,65 @@
+"""GPU, 2 ranks, NCCL: the view-sharded K-view step (BASELINE C4) with the span-limited, overlapped all-reduce equals
+the single-process K-view step. Skipped on boxes with one GPU (the driver's -m gpu tier); run with gpurun --gpus 2."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+from gigs import scene, shade, step as gstep
+
+GI = dict(radius=0.8, bias=0.01, thick=0.05, delta=0.0625, step=16, start=64)
+P, W, H, K = 20000, 160, 128, 4
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _inputs(dev):
+    raw = scene.make_scene(P, seed=3)
+    params = gstep.GaussianParams(raw, dev, light=scene.make_light(0, base_res=64))
+    lut = shade.make_brdf_lut(64, 64).to(dev)
+    cams = [scene.orbit_camera(k, 8, W, H).to(dev) for k in range(K)]
+    gen = torch.Generator().manual_seed(0)
+    gts = [torch.rand(3, H, W, generator=gen).to(dev) for _ in range(K)]
+    return params, lut, cams, gts, scene.canonical_rays(cams[0], dev), torch.zeros(3, device=dev)
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    params, lut, cams, gts, rays, bg = _inputs(dev)
+    for _ in range(2):   # twice: the second step exercises zero_grad(fused_only) + a reused comm stream
+        total = gstep.multi_view_step(params, cams, params.light(), lut, lambda c: rays, gts, bg, GI, rank=rank,
+                                      world=world)
+    torch.cuda.synchronize()
+    if rank == 0:
+        torch.save(dict(grad=params.flat_grad.cpu(), total=float(total)), out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_rank_multi_view_step_matches_single_process(tmp_path):
+    out = str(tmp_path / "r.pt")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    r = torch.load(out)
+    dev = torch.device("cuda", 0)
+    params, lut, cams, gts, rays, bg = _inputs(dev)
+    total = gstep.multi_view_step(params, cams, params.light(), lut, lambda c: rays, gts, bg, GI)
+    ref = params.flat_grad.cpu()
+    assert abs(r["total"] - float(total)) <= 1e-6 * abs(float(total))
+    rel = float((r["grad"] - ref).norm() / ref.norm())
+    assert rel <= 1e-4, rel
