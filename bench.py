@@ -37,7 +37,7 @@ STAGE_LAUNCHES = {"preprocess": 2, "emit_keys": 1, "tile_ranges": 1, "blend_forw
                   "gaussian_backward": 1, "geometry_chain": 1, "ssao": 1, "ssr": 1, "shade_forward": 1,
                   "shade_backward": 1, "median3x3": 1, "median3x3_backward": 1, "bilateral3x3": 1,
                   "depth_to_normal": 1, "ssr_backward": 1, "dist2": 9, "deferred_shade": 1, "deferred_loss": 1,
-                  "deferred_backward": 1, "param_grad": 1, "radix_sort_pass": 0}
+                  "deferred_backward": 4, "param_grad": 1, "radix_sort_pass": 0}
 
 
 def parse():
