@@ -252,6 +252,7 @@ int gigs_sizeof(int32_t which)
         case 5: return (int)sizeof(GigsShade);
         case 6: return (int)sizeof(GigsFrameLayout);
         case 7: return (int)sizeof(GigsFrame);
+        case 8: return (int)sizeof(GigsLightLayout);
         default: return -1;
     }
 }

@@ -110,6 +110,17 @@ class GigsFrameLayout(C.Structure):
         "g_metallic", "mask", "median_sel", "tex_scratch", "partials", "stats", "total_bytes")]
 
 
+class GigsLightLayout(C.Structure):
+    _fields_ = ([("n_levels", C.c_int32), ("res", C.c_int32 * 8), ("roughness", C.c_float * 8),
+                 ("cutoff", C.c_float * 8), ("pad_", C.c_int32)]
+                + [(n, C.c_uint64 * 8) for n in ("table", "bounds", "chain", "spec", "wsum", "gq", "g_chain", "g_spec")]
+                + [(n, C.c_uint64 * 9) for n in ("rowptr", "wptr")]
+                + [(n, C.c_uint64) for n in ("counts", "totals", "diffuse", "gq_diffuse", "g_diffuse_in", "g_diffuse",
+                                             "grad_begin", "grad_bytes", "total_bytes")]
+                + [(n, C.c_uint64 * 9) for n in ("n_runs", "n_weights", "w_rows", "w_fwd", "w_bwd")]
+                + [("weights_bytes", C.c_uint64)])
+
+
 class GigsFrame(C.Structure):
     _fields_ = [
         ("P", C.c_int32), ("raw_params", C.c_int32),
@@ -167,6 +178,19 @@ SYMBOLS = {
     "gigs_frame_layout": (C.c_int, [_i32, _i32, C.POINTER(GigsFrameLayout)]),
     "gigs_frame_forward": (C.c_int, [C.POINTER(GigsFrame)]),
     "gigs_frame_backward": (C.c_int, [C.POINTER(GigsFrame)]),
+    "gigs_cubemap_table": (C.c_int, [_i32, _vp, _vp]),
+    "gigs_specular_bounds": (C.c_int, [_i32, _f, _vp, _vp, _vp]),
+    "gigs_cubemap_mip_forward": (C.c_int, [_i32, _vp, _vp, _vp]),
+    "gigs_cubemap_mip_backward": (C.c_int, [_i32, _vp, _vp, _i32, _vp]),
+    "gigs_diffuse_cubemap_forward": (C.c_int, [_i32, _vp, _vp, _vp, _vp]),
+    "gigs_diffuse_cubemap_backward": (C.c_int, [_i32, _vp, _vp, _vp, _vp]),
+    "gigs_specular_cubemap_forward": (C.c_int, [_i32, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp]),
+    "gigs_specular_cubemap_backward": (C.c_int, [_i32, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp]),
+    "gigs_light_layout": (C.c_int, [_i32, _i32, C.POINTER(GigsLightLayout)]),
+    "gigs_light_prepare": (C.c_int, [C.POINTER(GigsLightLayout), _vp, _vp]),
+    "gigs_light_weights": (C.c_int, [C.POINTER(GigsLightLayout), _vp, _vp, _vp]),
+    "gigs_light_build": (C.c_int, [C.POINTER(GigsLightLayout), _vp, _vp, _vp, _vp]),
+    "gigs_light_backward": (C.c_int, [C.POINTER(GigsLightLayout), _vp, _vp, _vp, _i32, _i32, _vp]),
     "gigs_dist2": (C.c_int, [_i32, _vp, _vp, _vp, C.POINTER(C.c_uint64), _vp]),
     "gigs_ffma_peak": (C.c_int, [C.POINTER(C.c_double), _vp]),
     "gigs_profile_enable": (C.c_int, [_i32]),
@@ -193,7 +217,7 @@ def load():
     if lib.gigs_abi_version() != 2:
         raise ImportError("gigs_b200: ABI version mismatch between the python binding and libgigs_b200.so")
     for which, st in enumerate((GigsCamera, GigsSizes, GigsLayout, GigsRasterFwd, GigsRasterBwd, GigsShade,
-                                GigsFrameLayout, GigsFrame)):
+                                GigsFrameLayout, GigsFrame, GigsLightLayout)):
         if lib.gigs_sizeof(which) != C.sizeof(st):
             raise ImportError(f"gigs_b200: struct {st.__name__} is {C.sizeof(st)} bytes in the python binding but "
                               f"{lib.gigs_sizeof(which)} in libgigs_b200.so")

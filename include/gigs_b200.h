@@ -48,7 +48,7 @@ int gigs_abi_version(void);
 const char* gigs_last_error(void);
 /* sizeof() of the argument structs, so a foreign-language binding can verify its mirror of the layout:
  * which = 0 GigsCamera, 1 GigsSizes, 2 GigsLayout, 3 GigsRasterFwd, 4 GigsRasterBwd, 5 GigsShade,
- * 6 GigsFrameLayout, 7 GigsFrame; negative for an unknown id. */
+ * 6 GigsFrameLayout, 7 GigsFrame, 8 GigsLightLayout; negative for an unknown id. */
 int gigs_sizeof(int32_t which);
 int gigs_raster_sizes(int32_t P, int32_t W, int32_t H, uint64_t R, GigsSizes* out);
 
@@ -320,6 +320,81 @@ typedef struct GigsFrame {
 int gigs_frame_forward(GigsFrame* f);
 int gigs_frame_backward(GigsFrame* f);
 
+/* ------------------------------------------------------------------------------------------------
+ * Cubemap prefilter = CubemapLight.build_mips (/root/reference/pbr/light.py:154-170), SURVEY.md §8f-1: the producer of
+ * the light textures the shading consumes, run by the reference once per PBR training step (train.py:340).
+ * Replaces the nvdiffrec renderutils plugin entry points diffuse_cubemap_fwd/bwd, specular_bounds,
+ * specular_cubemap_fwd/bwd (pbr/renderutils/c_src/torch_bindings.cpp:740-889 -> c_src/cubemap.cu:110-350) and
+ * cubemap_mip (pbr/light.py:54-79). Cubemaps are [6,res,res,3] float32 (the reference's NHWC layout).
+ *   table  : float[6*res*res][4]  = unit direction of each texel centre (cubemap.cu:32-47) + pixel_area (:17-30)
+ *   bounds : int16[6*res*res][6][4] = (xmin,xmax,ymin,ymax) of the GGX cone on each face (cubemap.cu:182-246)
+ * Both depend only on (res, cutoff): build once, reuse every step. Backward entry points WRITE grad_in (gather, no
+ * atomics, deterministic); the specular pair is fused with the col / wsum division of renderutils/ops.py:456. */
+int gigs_cubemap_table(int32_t res, float* table, void* stream);
+int gigs_specular_bounds(int32_t res, float costheta_cutoff, const float* table, int16_t* bounds, void* stream);
+int gigs_cubemap_mip_forward(int32_t res_out, const float* in /*[6,2r,2r,3]*/, float* out /*[6,r,r,3]*/, void* stream);
+int gigs_cubemap_mip_backward(int32_t res_coarse, const float* grad_coarse, float* grad_fine /*[6,2r,2r,3]*/,
+                              int32_t accumulate, void* stream);
+int gigs_diffuse_cubemap_forward(int32_t res, const float* table, const float* cubemap, float* out, void* stream);
+int gigs_diffuse_cubemap_backward(int32_t res, const float* table, const float* grad_out, float* grad_in, void* stream);
+int gigs_specular_cubemap_forward(int32_t res, const float* table, const int16_t* bounds, float roughness,
+                                  float costheta_cutoff, const float* cubemap, float* out /*[6,r,r,3]*/,
+                                  float* wsum /*[6,r,r]*/, void* stream);
+int gigs_specular_cubemap_backward(int32_t res, const float* table, const int16_t* bounds, float roughness,
+                                   float costheta_cutoff, const float* grad_out, const float* wsum, float* grad_in,
+                                   void* stream);
+
+/* The whole light in one go = CubemapLight.build_mips (pbr/light.py:154-170) and its backward, for the training step
+ * (train.py:340 rebuilds the mips every PBR iteration). Two caller-owned blobs:
+ *   workspace (layout.total_bytes, a pure function of (base_res, min_res)): tables, bounds, the mip chain, the filtered
+ *     levels, wsum, the texture-gradient span and scratch;
+ *   weights (layout.weights_bytes, known after gigs_light_prepare; ~1.3 GB at base_res 256): the filters as STORED
+ *     sparse operators. Their weights depend only on (resolution, roughness, cutoff), so they are evaluated once, with
+ *     the reference's per-pair arithmetic to the bit, and every step streams them from HBM instead of recomputing
+ *     ~100 instructions per (output texel, light texel) pair. Pass weights = NULL to gigs_light_build / _backward to
+ *     compute the same sums on the fly instead (no extra memory, ~5x slower).
+ * Sequence:
+ *   gigs_light_layout  fills res[] (base_res, base_res/2, ... min_res), roughness[] (light.py:165-170) and the offsets;
+ *                      the caller then sets cutoff[l] = cos(theta) keeping `cutoff` of the GGX energy at roughness[l]
+ *                      (renderutils/ops.py:430-441 __ndfBounds — a 1e6-sample numpy cumulative sum in the reference,
+ *                      kept on the host side of the binding so that the threshold is the reference's to the bit);
+ *   gigs_light_prepare builds table[] / bounds[], counts the operators' runs and weights (one stream synchronise), fills
+ *                      n_runs[] / n_weights[] / w_*[] / weights_bytes and clears the gradient span;
+ *   gigs_light_weights fills the weights blob (run records, forward operators + wsum in the reference's summation
+ *                      order, transposed backward operators with 1 / wsum folded in);
+ *   gigs_light_build   base [6,R,R,3] -> chain[] (average-pool mips, 16-byte padded texels), spec[l] [6,r,r,3] (GGX
+ *                      filtered, divided by wsum[l]) and diffuse [6,min_res,min_res,3]: 2 launches;
+ *   gigs_light_backward reads the texture gradients g_spec[l] / g_diffuse (the span [grad_begin, +grad_bytes) that the
+ *                      shading backward accumulates into: pass those pointers as GigsFrame.g_spec / g_diffuse_tex) and
+ *                      writes (accumulate=0) or adds (accumulate=1) d loss / d base; clear_grads=1 re-zeroes the span.
+ * Filter index f in the [GIGS_MAX_LIGHT_LEVELS + 1] arrays: 0..n_levels-1 = GGX levels, n_levels = the cosine filter. */
+#define GIGS_MAX_LIGHT_LEVELS 8
+typedef struct GigsLightLayout {
+    int32_t n_levels;
+    int32_t res[GIGS_MAX_LIGHT_LEVELS];
+    float roughness[GIGS_MAX_LIGHT_LEVELS];
+    float cutoff[GIGS_MAX_LIGHT_LEVELS];
+    int32_t pad_;
+    /* offsets into the workspace blob */
+    uint64_t table[GIGS_MAX_LIGHT_LEVELS], bounds[GIGS_MAX_LIGHT_LEVELS], chain[GIGS_MAX_LIGHT_LEVELS];
+    uint64_t spec[GIGS_MAX_LIGHT_LEVELS], wsum[GIGS_MAX_LIGHT_LEVELS], gq[GIGS_MAX_LIGHT_LEVELS];
+    uint64_t g_chain[GIGS_MAX_LIGHT_LEVELS], g_spec[GIGS_MAX_LIGHT_LEVELS];
+    uint64_t rowptr[GIGS_MAX_LIGHT_LEVELS + 1], wptr[GIGS_MAX_LIGHT_LEVELS + 1];
+    uint64_t counts, totals;
+    uint64_t diffuse, gq_diffuse, g_diffuse_in, g_diffuse;
+    uint64_t grad_begin, grad_bytes, total_bytes;
+    /* the stored operators (filled by gigs_light_prepare): sizes and offsets into the weights blob */
+    uint64_t n_runs[GIGS_MAX_LIGHT_LEVELS + 1], n_weights[GIGS_MAX_LIGHT_LEVELS + 1];
+    uint64_t w_rows[GIGS_MAX_LIGHT_LEVELS + 1], w_fwd[GIGS_MAX_LIGHT_LEVELS + 1], w_bwd[GIGS_MAX_LIGHT_LEVELS + 1];
+    uint64_t weights_bytes;
+} GigsLightLayout;
+int gigs_light_layout(int32_t base_res, int32_t min_res, GigsLightLayout* layout);
+int gigs_light_prepare(GigsLightLayout* layout, void* workspace, void* stream);
+int gigs_light_weights(const GigsLightLayout* layout, void* workspace, void* weights, void* stream);
+int gigs_light_build(const GigsLightLayout* layout, const float* base, void* workspace, const void* weights, void* stream);
+int gigs_light_backward(const GigsLightLayout* layout, void* workspace, const void* weights, float* grad_base,
+                        int32_t accumulate, int32_t clear_grads, void* stream);
+
 /* Replaces distCUDA2 / SimpleKNN::knn (/root/reference/submodules/simple-knn/spatial.cu,
  * simple_knn.cu:165-207): mean squared distance to the 3 nearest other points.
  * scratch_bytes: call with scratch==NULL to query. */
@@ -331,7 +406,7 @@ int gigs_dist2(int32_t P, const float* points, float* mean_dist2, void* scratch,
  * 6 gaussian_backward, 7 geometry_chain, 8 ssao, 9 ssr, 10 shade_forward, 11 shade_backward, 12 median3x3,
  * 13 median3x3_backward, 14 bilateral3x3, 15 depth_to_normal, 16 ssr_backward, 17 dist2, 18 deferred_shade,
  * 19 deferred_loss, 20 deferred_backward, 21 param_grad, 22 one radix-sort pass (nested inside 2 / 23),
- * 23 depth argsort of the Gaussians.
+ * 23 depth argsort of the Gaussians, 24 cubemap prefilter forward, 25 cubemap prefilter backward.
  * gigs_profile_read synchronises the recorded events, writes up to cap (stage, ms) pairs, clears the log and
  * returns the number written (negative on error). Off by default; costs two event records per stage when on. */
 int gigs_profile_enable(int32_t on);

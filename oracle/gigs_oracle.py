@@ -1000,3 +1000,262 @@ def dist2(points, chunk=2048):
             b = torch.cat([b, torch.full((q.shape[0], 3 - b.shape[1]), 3.4028234663852886e38)], 1)
         out[s:s + chunk] = (b[:, 0] + b[:, 1] + b[:, 2]) / 3.0
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Cubemap prefilter = CubemapLight.build_mips: /root/reference/pbr/light.py:154-170 (SURVEY §8f-1).
+# Restates the nvdiffrec renderutils kernels the reference vendors (pbr/renderutils/c_src/cubemap.cu:17-47
+# pixel_area / cube_to_dir, :110-168 diffuse, :173-246 bounds, :248-350 specular) as dense weight matrices
+# W[V, L] in float32, the Python around them (pbr/renderutils/ops.py:391-459: ndf cutoff, col / wsum) and
+# cubemap_mip (pbr/light.py:54-79, whose backward samples dout with the nvdiffrast cube lookup restated
+# above — that one part is unpinned). PINNED on the GPU box against the reference's own kernels
+# (oracle/_ref/libgigs_ref_cubemap.so, tests/test_gpu_cubemap.py). Summation order differs from the CUDA
+# loops (matrix products), so values agree to float32 rounding, not bit for bit.
+# ------------------------------------------------------------------------------------------------
+def cm_cube_to_dir(N: int, corners: bool = False):
+    """[6,n,n,3] unit directions, n = N (texel centres... as the kernel computes them for integer x,y in [0,N))
+    or N+1 with corners=True (the bounds kernel evaluates x,y = N too). c_src/cubemap.cu:32-47."""
+    n = N + 1 if corners else N
+    k = torch.arange(n, dtype=F32)
+    f = 2.0 * ((k + 0.5) / float(N)) - 1.0
+    fy, fx = torch.meshgrid(f, f, indexing="ij")
+    one = torch.ones_like(fx)
+    faces = [(one, -fy, -fx), (-one, -fy, fx), (fx, one, fy), (fx, -one, -fy), (fx, -fy, one), (-fx, -fy, -one)]
+    d = torch.stack([torch.stack(c, -1) for c in faces], 0)
+    # safeNormalize (vec3f.h:90-94) with nvcc's FMA contraction of x*x + y*y + z*z. Each `case` of cube_to_dir is
+    # compiled with its constant folded: on faces 0/1 (x = +-1) the sum becomes fma(z, z, fma(y, y, 1.0f)) — y*y is NOT
+    # rounded on its own there, unlike the generic pattern of _dot3_cuda, which the other four faces keep.
+    l2 = _dot3_cuda(d, d)
+    l2[0:2] = _fma32(d[0:2, ..., 2], d[0:2, ..., 2], _fma32(d[0:2, ..., 1], d[0:2, ..., 1], torch.ones(())))
+    return d / _sqrt32(l2)[..., None]
+
+
+def cm_pixel_area(N: int):
+    """[N,N] (y,x): c_src/cubemap.cu:17-30."""
+    if N <= 1:
+        return torch.ones(N, N)
+    Hh = N // 2
+    k = (torch.arange(N) - Hh).abs().float()
+    d1 = torch.atan((k + 1.0) / float(Hh)) - torch.atan(k / float(Hh))
+    return d1[:, None] * d1[None, :]
+
+
+def cm_diffuse_weights(N: int):
+    """W[V, L] = clamp(dot(V, L), 0, 0.999) * area(L) / 3.141592 (c_src/cubemap.cu:125-137)."""
+    d = cm_cube_to_dir(N).reshape(-1, 3)
+    area = cm_pixel_area(N)[None].expand(6, N, N).reshape(-1)
+    return (d @ d.T).clamp(0.0, 0.999) * area[None, :] / 3.141592
+
+
+def diffuse_cubemap(cube):
+    N = cube.shape[1]
+    return (cm_diffuse_weights(N) @ cube.reshape(-1, 3).float()).reshape(6, N, N, 3)
+
+
+def diffuse_cubemap_backward(grad):
+    """DiffuseCubemapBwdKernel (c_src/cubemap.cu:141-168): scatter grad(V) * w(V, L) to L."""
+    N = grad.shape[1]
+    return (cm_diffuse_weights(N).T @ grad.reshape(-1, 3).float()).reshape(6, N, N, 3)
+
+
+def ndf_cutoff(roughness: float, cutoff: float = 0.99) -> float:
+    """pbr/renderutils/ops.py:430-441 (__ndfBounds): cos(theta) keeping `cutoff` of the GGX NDF's energy."""
+    import numpy as np
+
+    def ndf_ggx(alpha_sqr, costheta):
+        costheta = np.clip(costheta, 0.0, 1.0)
+        d = (costheta * alpha_sqr - costheta) * costheta + 1.0
+        return alpha_sqr / (d * d * np.pi)
+    n = 1000000
+    costheta = np.cos(np.linspace(0, np.pi / 2.0, n))
+    D = np.cumsum(ndf_ggx(roughness ** 4, costheta))
+    return float(costheta[np.argmax(D >= D[..., -1] * cutoff)])
+
+
+def specular_bounds(N: int, costheta_cutoff: float, chunk: int = 4096):
+    """[6,N,N,6,4] int (xmin,xmax,ymin,ymax) per face; empty = (N-1,0,N-1,0). c_src/cubemap.cu:182-246, INCLUDING its
+    16x16-tile cull: a tile is skipped when an interval bound built from its four CORNER directions stays below the
+    cutoff. Corner values do not bound the normalised directions inside a tile (the major-axis component peaks in the
+    interior), so the cull is not conservative: near face edges it drops tiles that do hold in-cone texels, and those
+    texels then fall outside the box and are never filtered. That is the reference's behaviour, restated here."""
+    d = cm_cube_to_dir(N)                               # [6,N,N,3]
+    dc = cm_cube_to_dir(N, corners=True)                # [6,N+1,N+1,3]: the kernel evaluates x, y = N as well
+    TS = 16
+    nt = (N + TS - 1) // TS
+    lo = torch.arange(nt) * TS
+    hi = torch.clamp((torch.arange(nt) + 1) * TS, max=N)
+    # corners of tile (ty, tx) on face s: (lo|hi) x (lo|hi)
+    corner = torch.stack([dc[:, lo][:, :, lo], dc[:, lo][:, :, hi], dc[:, hi][:, :, lo], dc[:, hi][:, :, hi]], 0)
+    cmin, cmax = corner.min(0).values, corner.max(0).values          # [6,nt(y),nt(x),3]
+    cut = torch.tensor(costheta_cutoff, dtype=F32)
+    flat = d.reshape(-1, 3)
+    T = flat.shape[0]
+    v, l, _ = _cone_pairs(N, costheta_cutoff)                         # every (V, L) with dot(L, V) >= cutoff
+    lf, ly, lx = l // (N * N), (l // N) % N, l % N
+    tile_ok = torch.empty(T, 6, nt, nt, dtype=torch.bool)
+    for s0 in range(0, T, chunk):
+        Vb = flat[s0:s0 + chunk][:, None, None, None, :]
+        m = torch.maximum(cmin[None] * Vb, cmax[None] * Vb)           # [c,6,nt,nt,3]
+        tile_ok[s0:s0 + chunk] = ((m[..., 0] + m[..., 1]) + m[..., 2]) >= cut
+    keep = tile_ok[v, lf, ly // TS, lx // TS]
+    v, lf, ly, lx = v[keep], lf[keep], ly[keep], lx[keep]
+    key = v * 6 + lf
+    out = torch.empty(T * 6, 4, dtype=torch.long)
+    out[:, 0] = torch.full((T * 6,), N - 1).scatter_reduce(0, key, lx, "amin", include_self=True)
+    out[:, 1] = torch.zeros(T * 6, dtype=torch.long).scatter_reduce(0, key, lx, "amax", include_self=True)
+    out[:, 2] = torch.full((T * 6,), N - 1).scatter_reduce(0, key, ly, "amin", include_self=True)
+    out[:, 3] = torch.zeros(T * 6, dtype=torch.long).scatter_reduce(0, key, ly, "amax", include_self=True)
+    return out.reshape(6, N, N, 6, 4)
+
+
+_cone_cache: Dict = {}
+
+
+def _cone_pairs(N: int, costheta_cutoff: float, chunk: int = 2048):
+    """All (v, l, dot) with dot(L, V) >= cutoff, dot evaluated as the CUDA kernels do (a float32 matmul only proposes
+    candidates)."""
+    key = (N, float(costheta_cutoff))
+    if key not in _cone_cache:
+        d = cm_cube_to_dir(N).reshape(-1, 3)
+        cut = torch.tensor(costheta_cutoff, dtype=F32)
+        vs, ls = [], []
+        for s in range(0, d.shape[0], chunk):
+            cand = ((d[s:s + chunk] @ d.T) >= cut - 1e-5).nonzero()
+            vs.append(cand[:, 0] + s); ls.append(cand[:, 1])
+        v, l = torch.cat(vs), torch.cat(ls)
+        dot = _dot3_cuda(d[l], d[v])
+        keep = dot >= cut
+        _cone_cache[key] = (v[keep], l[keep], dot[keep])
+    return _cone_cache[key]
+
+
+def _fma32(a, b, c):
+    """float32 fma(a, b, c) emulated in float64 (the product of two float32 is exact in float64)."""
+    return (a.double() * b.double() + c.double()).float()
+
+
+def _sqrt32(x):
+    """Correctly rounded float32 sqrt (CUDA's sqrtf is; torch's vectorised CPU float32 sqrt is NOT — it is off by one ulp
+    on near-ties, which roughness 0.08 amplifies to 0.3 % of a weight). sqrt in double, then one rounding."""
+    return torch.sqrt(x.double()).float()
+
+
+def _dot3_cuda(a, b):
+    """a.x*b.x + a.y*b.y + a.z*b.z as nvcc 12.9 contracts it for sm_100a (read off the SASS of the kernels built
+    from the reference source: FMUL y*y, FFMA x*x + ., FFMA z*z + .): fma(a.z, b.z, fma(a.x, b.x, a.y*b.y))."""
+    return _fma32(a[..., 2], b[..., 2], _fma32(a[..., 0], b[..., 0], a[..., 1] * b[..., 1]))
+
+
+_pairs_cache: Dict = {}
+
+
+def cm_specular_pairs_boxed(N: int, roughness: float, costheta_cutoff: float):
+    """cm_specular_pairs restricted to the boxes of specular_bounds — what the filter kernels visit. Cached: geometry only."""
+    key = (N, float(roughness), float(costheta_cutoff))
+    if key not in _pairs_cache:
+        _pairs_cache[key] = cm_specular_pairs(N, roughness, costheta_cutoff,
+                                              bounds=specular_bounds(N, costheta_cutoff))
+    return _pairs_cache[key]
+
+
+def cm_specular_pairs(N: int, roughness: float, costheta_cutoff: float, chunk: int = 2048, bounds=None):
+    """COO list (v, l, w) of the pairs with dot(L,V) >= cutoff and their weights
+    w = max(dot(L,V),0) * D_ggx(alpha^2, max(dot(V,H),0)) * area(L) / 4, H = safeNormalize(L+V)
+    (c_src/cubemap.cu:268-285; ndfGGX :173-178 divides by the double M_PI). At small roughness D_ggx is
+    ill-conditioned in dot(V,H) near 1 (one float32 ulp moves the central weights by ~0.3 % at roughness 0.08), so
+    the dot products and the normalisation follow the CUDA expression forms with emulated FMA contraction."""
+    d = cm_cube_to_dir(N).reshape(-1, 3)
+    area = cm_pixel_area(N)[None].expand(6, N, N).reshape(-1)
+    v, l, dot = _cone_pairs(N, costheta_cutoff)
+    keep = torch.ones_like(v, dtype=torch.bool)
+    if bounds is not None:                 # the filter kernels only visit the box of specular_bounds (see there)
+        b = bounds.reshape(-1, 6, 4)[v, l // (N * N)]
+        lx, ly = l % N, (l // N) % N
+        keep &= (lx >= b[:, 0]) & (lx <= b[:, 1]) & (ly >= b[:, 2]) & (ly <= b[:, 3])
+    v, l, dot = v[keep], l[keep], dot[keep]
+    V, L = d[v], d[l]
+    Hs = L + V
+    ln = _sqrt32(_dot3_cuda(Hs, Hs))
+    Hn = torch.where(ln[..., None] > 0, Hs / ln[..., None], torch.zeros(()))
+    vdoth = _dot3_cuda(V, Hn).clamp(min=0.0).clamp(0.0, 1.0)
+    a = torch.tensor(float(roughness), dtype=F32)
+    a = a * a
+    a2 = a * a
+    dd = _fma32(_fma32(vdoth, a2, -vdoth), vdoth, torch.ones(()))
+    ndf = (a2.double() / ((dd * dd).double() * math.pi)).float()
+    w = dot.clamp(min=0.0) * ndf * area[l] / 4.0
+    return v, l, w
+
+
+def specular_cubemap(cube, roughness: float, cutoff: float = 0.99, costheta_cutoff=None):
+    """renderutils.specular_cubemap (ops.py:446-456): returns (out = col / wsum, wsum)."""
+    N = cube.shape[1]
+    c = ndf_cutoff(roughness, cutoff) if costheta_cutoff is None else costheta_cutoff
+    flat = cube.reshape(-1, 3).float()
+    v, l, w = cm_specular_pairs_boxed(N, roughness, c)
+    wsum = torch.zeros(flat.shape[0]).index_add_(0, v, w)
+    col = torch.zeros_like(flat).index_add_(0, v, flat[l] * w[:, None])
+    return (col / wsum[:, None]).reshape(6, N, N, 3), wsum.reshape(6, N, N)
+
+
+def specular_cubemap_backward(grad, roughness: float, cutoff: float = 0.99, costheta_cutoff=None):
+    """autograd of out[...,0:3] / out[...,3:] into SpecularCubemapBwdKernel (c_src/cubemap.cu:306-350): the kernel
+    reads only the 3 colour channels of the upstream gradient, i.e. grad / wsum."""
+    N = grad.shape[1]
+    c = ndf_cutoff(roughness, cutoff) if costheta_cutoff is None else costheta_cutoff
+    g = grad.reshape(-1, 3).float()
+    v, l, w = cm_specular_pairs_boxed(N, roughness, c)
+    wsum = torch.zeros(g.shape[0]).index_add_(0, v, w)
+    gin = torch.zeros_like(g).index_add_(0, l, (g / wsum[:, None])[v] * w[:, None])
+    return gin.reshape(6, N, N, 3)
+
+
+def cubemap_mip(cube):
+    """pbr/light.py:56-60: 2x2 average pool, NHWC."""
+    n, h, w, c = cube.shape
+    return cube.reshape(n, h // 2, 2, w // 2, 2, c).mean(dim=(2, 4))
+
+
+def cubemap_mip_backward(dout):
+    """pbr/light.py:62-79: NOT the pool's adjoint — a seamless bilinear cube lookup of 0.25 * dout at the fine
+    texel-centre directions."""
+    res = dout.shape[1] * 2
+    g = torch.linspace(-1.0 + 1.0 / res, 1.0 - 1.0 / res, res)
+    gy, gx = torch.meshgrid(g, g, indexing="ij")
+    one = torch.ones_like(gx)
+    faces = [(one, -gy, -gx), (-one, -gy, gx), (gx, one, gy), (gx, -one, -gy), (gx, -gy, one), (-gx, -gy, -one)]
+    out = []
+    for c in faces:
+        v = torch.nn.functional.normalize(torch.stack(c, -1), p=2, dim=-1)
+        out.append(tex_cube(dout.float() * 0.25, v))
+    return torch.stack(out, 0)
+
+
+def light_roughness_levels(n_levels: int, rmin=0.08, rmax=0.5):
+    """pbr/light.py:165-170: roughness each specular level is filtered for."""
+    return [(i / (n_levels - 2)) * (rmax - rmin) + rmin for i in range(n_levels - 1)] + [1.0]
+
+
+def build_mips(base, cutoff: float = 0.99, min_res: int = 16) -> Dict:
+    """CubemapLight.build_mips (pbr/light.py:154-170) -> dict(specular=[...fine to coarse], diffuse=, chain=, wsum=)."""
+    chain = [base.float()]
+    while chain[-1].shape[1] > min_res:
+        chain.append(cubemap_mip(chain[-1]))
+    rough = light_roughness_levels(len(chain))
+    spec, wsum = [], []
+    for lvl, r in zip(chain, rough):
+        o, w = specular_cubemap(lvl, r, cutoff)
+        spec.append(o); wsum.append(w)
+    return dict(specular=spec, diffuse=diffuse_cubemap(chain[-1]), chain=chain, wsum=wsum, roughness=rough)
+
+
+def build_mips_backward(base_res: int, grad_specular, grad_diffuse, cutoff: float = 0.99, min_res: int = 16):
+    """Gradient of build_mips w.r.t. base: filter backwards per level, then down the chain from coarse to fine with
+    the reference's cubemap_mip backward."""
+    n = len(grad_specular)
+    rough = light_roughness_levels(n)
+    g_chain = [specular_cubemap_backward(g, r, cutoff) for g, r in zip(grad_specular, rough)]
+    g_chain[-1] = g_chain[-1] + diffuse_cubemap_backward(grad_diffuse)
+    for i in range(n - 1, 0, -1):
+        g_chain[i - 1] = g_chain[i - 1] + cubemap_mip_backward(g_chain[i])
+    return g_chain[0]

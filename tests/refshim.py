@@ -202,3 +202,76 @@ def knn(points):
     lib.ref_knn(C.c_int(P), _p(pts), _p(out))
     torch.cuda.synchronize()
     return out
+
+
+# ---- the reference's cubemap prefilter kernels (pbr/renderutils/c_src/cubemap.cu via oracle/ref_cubemap_shim.cu) ----
+REF_CUBEMAP_SO = os.path.join(ROOT, "oracle", "_ref", "libgigs_ref_cubemap.so")
+_cm = None
+
+
+def cubemap_available() -> bool:
+    return os.path.exists(REF_CUBEMAP_SO)
+
+
+class RefCubemap:
+    """The reference's renderutils plugin entry points (torch_bindings.cpp:740-889), same names and tensor shapes:
+    cubemaps [6,N,N,3], bounds float [6,N,N,24], specular_cubemap_fwd output [6,N,N,4] = (sum col*w, wsum)."""
+
+    def __init__(self):
+        global _cm
+        if _cm is None:
+            _cm = C.CDLL(REF_CUBEMAP_SO)
+        self.lib = _cm
+
+    @staticmethod
+    def _chk(rc, what):
+        if rc != 0:
+            raise RuntimeError(f"reference cubemap kernel {what} failed: cudaError {rc}")
+
+    def diffuse_cubemap_fwd(self, cubemap):
+        x = cubemap.float().contiguous()
+        out = torch.empty_like(x)
+        torch.cuda.synchronize()
+        self._chk(self.lib.ref_diffuse_cubemap_fwd(C.c_int(x.shape[1]), _p(x), _p(out)), "diffuse fwd")
+        return out
+
+    def diffuse_cubemap_bwd(self, cubemap, grad):
+        x, g = cubemap.float().contiguous(), grad.float().contiguous()
+        out = torch.empty_like(x)
+        torch.cuda.synchronize()
+        self._chk(self.lib.ref_diffuse_cubemap_bwd(C.c_int(x.shape[1]), _p(x), _p(g), _p(out)), "diffuse bwd")
+        return out
+
+    def specular_bounds(self, res, costheta_cutoff, device="cuda"):
+        out = torch.empty(6, res, res, 24, dtype=torch.float32, device=device)
+        torch.cuda.synchronize()
+        self._chk(self.lib.ref_specular_bounds(C.c_int(res), C.c_float(costheta_cutoff), _p(out)), "bounds")
+        return out
+
+    def specular_cubemap_fwd(self, cubemap, bounds, roughness, costheta_cutoff):
+        x = cubemap.float().contiguous()
+        out = torch.empty(6, x.shape[1], x.shape[1], 4, dtype=torch.float32, device=x.device)
+        torch.cuda.synchronize()
+        self._chk(self.lib.ref_specular_cubemap_fwd(C.c_int(x.shape[1]), _p(x), _p(bounds), C.c_float(roughness),
+                                                    C.c_float(costheta_cutoff), _p(out)), "specular fwd")
+        return out
+
+    def specular_cubemap_bwd(self, cubemap, bounds, grad4, roughness, costheta_cutoff):
+        x, g = cubemap.float().contiguous(), grad4.float().contiguous()
+        out = torch.empty_like(x)
+        torch.cuda.synchronize()
+        self._chk(self.lib.ref_specular_cubemap_bwd(C.c_int(x.shape[1]), _p(x), _p(bounds), _p(g), C.c_float(roughness),
+                                                    C.c_float(costheta_cutoff), _p(out)), "specular bwd")
+        return out
+
+    def specular_cubemap(self, cubemap, roughness, cutoff, costheta_cutoff):
+        """renderutils.specular_cubemap (ops.py:446-456) on the reference kernels -> (out, wsum, bounds)."""
+        b = self.specular_bounds(cubemap.shape[1], costheta_cutoff, cubemap.device)
+        o = self.specular_cubemap_fwd(cubemap, b, roughness, costheta_cutoff)
+        return o[..., 0:3] / o[..., 3:], o[..., 3], b
+
+    def specular_cubemap_grad(self, cubemap, bounds, wsum, dout, roughness, costheta_cutoff):
+        """autograd of out[...,0:3] / out[...,3:] feeding specular_cubemap_bwd (which reads only channels 0..2)."""
+        g4 = torch.zeros(*dout.shape[:3], 4, dtype=torch.float32, device=dout.device)
+        g4[..., 0:3] = dout / wsum[..., None]
+        return self.specular_cubemap_bwd(cubemap, bounds, g4, roughness, costheta_cutoff)

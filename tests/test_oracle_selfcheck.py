@@ -216,3 +216,43 @@ def test_camera_convention_matches_reference_helpers():
     ph = O.transform_point_4x4(torch.zeros(1, 3), cam.full_proj_transform)
     assert abs(float(ph[0, 3]) - 4.031) < 1e-4
     assert torch.allclose(cam.camera_center.norm(), torch.tensor(4.031), atol=1e-4)
+
+
+# ---- cubemap prefilter restatement (oracle section "Cubemap prefilter") ---------------------------------------------
+def test_cubemap_texel_geometry():
+    d = O.cm_cube_to_dir(16)
+    assert torch.allclose(d.norm(dim=-1), torch.ones(6, 16, 16), atol=1e-6)
+    # face s points along its major axis (c_src/cubemap.cu:36-45)
+    for s, (ax, sg) in enumerate([(0, 1), (0, -1), (1, 1), (1, -1), (2, 1), (2, -1)]):
+        assert (d[s, ..., ax] * sg > 0.5).all()
+    # pixel_area is d(atan x) * d(atan y), the reference's (separable) approximation of the texel's solid angle: over
+    # a face it sums to ~(pi/2)^2, not to 4*pi/6 (and |x - H| shifts the negative half by one texel)
+    assert abs(O.cm_pixel_area(256).sum().item() - (math.pi / 2) ** 2) < 0.02
+
+
+def test_cubemap_filters_preserve_constants_and_are_adjoint():
+    c = torch.full((6, 16, 16, 3), 0.7)
+    o, w = O.specular_cubemap(c, 1.0)
+    assert (o - 0.7).abs().max().item() < 3e-6 and (w > 0).all()
+    x = torch.randn(6, 16, 16, 3, generator=torch.Generator().manual_seed(1))
+    g = torch.randn(6, 16, 16, 3, generator=torch.Generator().manual_seed(2))
+    for fwd, bwd in ((lambda t: O.specular_cubemap(t, 0.5)[0], lambda t: O.specular_cubemap_backward(t, 0.5)),
+                     (O.diffuse_cubemap, O.diffuse_cubemap_backward)):
+        lhs, rhs = (fwd(x) * g).sum().item(), (bwd(g) * x).sum().item()
+        assert abs(lhs - rhs) < 1e-3 * max(1.0, abs(lhs))
+    # the cone of the bounds contains the texel itself and, at roughness 1, (almost) the whole hemisphere
+    b = O.specular_bounds(16, O.ndf_cutoff(1.0))
+    assert (b[0, 8, 8, 0] == torch.tensor([0, 15, 0, 15])).all()        # own face: everything
+    assert (b[0, 8, 8, 1, 0] > b[0, 8, 8, 1, 1])                        # opposite face: empty box
+
+
+def test_cubemap_mip_chain_and_its_reference_backward():
+    x = torch.rand(6, 64, 64, 3, generator=torch.Generator().manual_seed(3))
+    y = O.cubemap_mip(x)
+    yt = torch.nn.functional.avg_pool2d(x.permute(0, 3, 1, 2), (2, 2)).permute(0, 2, 3, 1)
+    assert torch.allclose(y, yt, atol=1e-7)
+    # backward = bilinear lookup of 0.25 * dout: a constant upstream gradient c gives 0.25 c everywhere
+    g = O.cubemap_mip_backward(torch.full((6, 32, 32, 3), 2.0))
+    assert (g - 0.5).abs().max().item() < 1e-6 and g.shape == (6, 64, 64, 3)
+    with pytest.raises(ZeroDivisionError):
+        O.build_mips(torch.rand(6, 32, 32, 3))      # two levels: the reference's schedule divides by zero too
