@@ -117,6 +117,7 @@ class GigsLightLayout(C.Structure):
                 + [(n, C.c_uint64 * 9) for n in ("rowptr", "wptr")]
                 + [(n, C.c_uint64) for n in ("counts", "totals", "diffuse", "gq_diffuse", "g_diffuse_in", "g_diffuse",
                                              "grad_begin", "grad_bytes", "total_bytes")]
+                + [("lanes_log2", C.c_int32 * 9), ("pad2_", C.c_int32)]
                 + [(n, C.c_uint64 * 9) for n in ("n_runs", "n_weights", "w_rows", "w_fwd", "w_bwd")]
                 + [("weights_bytes", C.c_uint64)])
 

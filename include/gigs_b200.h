@@ -348,7 +348,7 @@ int gigs_specular_cubemap_backward(int32_t res, const float* table, const int16_
  * (train.py:340 rebuilds the mips every PBR iteration). Two caller-owned blobs:
  *   workspace (layout.total_bytes, a pure function of (base_res, min_res)): tables, bounds, the mip chain, the filtered
  *     levels, wsum, the texture-gradient span and scratch;
- *   weights (layout.weights_bytes, known after gigs_light_prepare; ~1.3 GB at base_res 256): the filters as STORED
+ *   weights (layout.weights_bytes, known after gigs_light_prepare; ~1.5 GB at base_res 256): the filters as STORED
  *     sparse operators. Their weights depend only on (resolution, roughness, cutoff), so they are evaluated once, with
  *     the reference's per-pair arithmetic to the bit, and every step streams them from HBM instead of recomputing
  *     ~100 instructions per (output texel, light texel) pair. Pass weights = NULL to gigs_light_build / _backward to
@@ -384,7 +384,9 @@ typedef struct GigsLightLayout {
     uint64_t diffuse, gq_diffuse, g_diffuse_in, g_diffuse;
     uint64_t grad_begin, grad_bytes, total_bytes;
     /* the stored operators (filled by gigs_light_prepare): sizes and offsets into the weights blob */
-    uint64_t n_runs[GIGS_MAX_LIGHT_LEVELS + 1], n_weights[GIGS_MAX_LIGHT_LEVELS + 1];
+    int32_t lanes_log2[GIGS_MAX_LIGHT_LEVELS + 1];   /* lanes per 4-texel block = length the runs are cut into */
+    int32_t pad2_;
+    uint64_t n_runs[GIGS_MAX_LIGHT_LEVELS + 1], n_weights[GIGS_MAX_LIGHT_LEVELS + 1];   /* run pieces, float4 entries */
     uint64_t w_rows[GIGS_MAX_LIGHT_LEVELS + 1], w_fwd[GIGS_MAX_LIGHT_LEVELS + 1], w_bwd[GIGS_MAX_LIGHT_LEVELS + 1];
     uint64_t weights_bytes;
 } GigsLightLayout;

@@ -25,7 +25,7 @@ def run(fn, n=10):
     return ts[len(ts) // 2]
 res = dict(build_ms=run(fl.build), backward_ms=run(lambda: fl.backward(gb, accumulate=False)),
            compute_build_ms=run(fc.build), compute_backward_ms=run(lambda: fc.backward(gb, accumulate=False)),
-           weights_MB=fl.layout.weights_bytes / 1e6, n_weights=list(fl.layout.n_weights), n_runs=list(fl.layout.n_runs))
+           weights_MB=fl.layout.weights_bytes / 1e6, n_weights=list(fl.layout.n_weights), n_runs=list(fl.layout.n_runs), lanes_log2=list(fl.layout.lanes_log2))
 print(json.dumps(res)); sys.exit(0)
 # per-level timings through the single-op entry points
 for lvl in range(fl.layout.n_levels):
