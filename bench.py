@@ -31,13 +31,14 @@ GI_BASE = dict(radius=0.8, bias=0.01, thick=0.05, delta=0.0625, step=16)
 STAGE_NAMES = ["preprocess", "emit_keys", "radix_sort", "tile_ranges", "blend_forward", "blend_backward",
                "gaussian_backward", "geometry_chain", "ssao", "ssr", "shade_forward", "shade_backward", "median3x3",
                "median3x3_backward", "bilateral3x3", "depth_to_normal", "ssr_backward", "dist2", "deferred_shade",
-               "deferred_loss", "deferred_backward", "param_grad", "radix_sort_pass", "depth_sort"]
+               "deferred_loss", "deferred_backward", "param_grad", "radix_sort_pass", "depth_sort", "light_build",
+               "light_backward"]
 # kernels launched per stage record (radix_sort: histogram + scan + passes, filled in at run time)
 STAGE_LAUNCHES = {"preprocess": 2, "emit_keys": 1, "tile_ranges": 1, "blend_forward": 1, "blend_backward": 1,
                   "gaussian_backward": 1, "geometry_chain": 1, "ssao": 1, "ssr": 1, "shade_forward": 1,
                   "shade_backward": 1, "median3x3": 1, "median3x3_backward": 1, "bilateral3x3": 1,
                   "depth_to_normal": 1, "ssr_backward": 1, "dist2": 9, "deferred_shade": 1, "deferred_loss": 1,
-                  "deferred_backward": 4, "param_grad": 1, "radix_sort_pass": 0}
+                  "deferred_backward": 4, "param_grad": 1, "radix_sort_pass": 0, "light_build": 2, "light_backward": 6}
 
 
 def parse():
@@ -202,7 +203,10 @@ def run_ours(args):
     bg = torch.zeros(3, device=dev)
     flush_buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
 
+    ctx = {"params": params, "light": light}   # the build_mips variant swaps in a light given as its base cubemap
+
     def one_step(i, gi, e2e=False, fused=True):
+        params, light = ctx["params"], ctx["light"]
         k = (i * world + rank) % K_cams
         params.zero_grad(fused_only=fused)
         gt_ready = None
@@ -424,6 +428,36 @@ def run_ours(args):
                                                 "note": "upper bound on probes (512 dirs x 8 steps per pixel, early "
                                                         "exits not counted)"}
                 line["variants"] = {"gi_start8": v8}
+                # ---- the same frame with the light given as its trainable base cubemap: CubemapLight.build_mips
+                # (GGX / cosine prefilter of all mip levels) before the frame and its backward after, every step, as
+                # train.py:340 does (the headline keeps the light textures as inputs) ----
+                try:
+                    gl = torch.Generator().manual_seed(1000)
+                    base = torch.rand(6, 256, 256, 3, generator=gl) * 0.5 + 0.25       # CubemapLight init
+                    p2 = gstep.GaussianParams(raw, dev, light_base=base)
+                    ctx.update(params=p2, light=p2.light())
+                    nm_ = max(5, args.steps // 2)
+                    tm, _ = timed(gi, nm_, 3)
+                    stm, stc = staged(gi, 3)
+                    lay_ = p2.prefiltered.layout
+                    wbytes = sum(16 * lay_.n_weights[f] + 8 * lay_.n_runs[f] for f in range(lay_.n_levels + 1))
+                    vm = {"value": 1e3 / (tm / nm_), "unit": "frames/s", "ms_per_step": tm / nm_,
+                          "light_base_res": 256, "stage_ms": {k2: stm.get(k2) for k2 in ("light_build", "light_backward")},
+                          "stored_operator_bytes": int(lay_.weights_bytes),
+                          "note": "build_mips forward before the frame, its backward on a side stream under the blend "
+                                  "backward; filters stored as sparse operators in HBM and streamed each step"}
+                    for nm in ("light_build", "light_backward"):
+                        if stm.get(nm):
+                            ach = wbytes / (stm[nm] / max(stc[nm], 1) * 1e-3) / 1e9
+                            vm[nm + "_roofline"] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                                                    "frac": ach / hbm_peak,
+                                                    "note": "algorithmic bytes = the stored weights + run records of one "
+                                                            "direction, streamed once"}
+                    line["variants"]["with_build_mips"] = vm
+                except Exception as ex:
+                    line["variants"]["with_build_mips"] = {"failed": str(ex)}
+                finally:
+                    ctx.update(params=params, light=light)
                 tu, _ = timed(gi, max(5, args.steps // 2), 3, fused=False)
                 msu = tu / max(5, args.steps // 2)
                 line["variants"]["unfused_operator_path"] = {

@@ -1,7 +1,9 @@
 """The PBR-stage training step on one view (the unit BASELINE.json's metric counts: one "frame" =
 G-buffer forward + SSAO + split-sum shading + SSR + loss + full backward), and its view-sharded multi-GPU
-form. Mirrors /root/reference/train.py:240-422 for the parts on the hot path; the optimiser, densification,
-TV losses and build_mips are outside it.
+form. Mirrors /root/reference/train.py:240-422 for the parts on the hot path; the optimiser, densification and
+TV losses are outside it. The light can be given as ready-made textures (leaves: `light=`) or as the
+trainable base cubemap (`light_base=`), in which case every step rebuilds the mips from it like train.py:340 does
+(gigs.light.PrefilteredLight: CubemapLight.build_mips and its backward).
 """
 from typing import Dict, List, Optional
 
@@ -22,7 +24,10 @@ class GaussianParams:
     so the per-Gaussian gradient all-reduce of the view-sharded step is a single collective with no packing
     copy (autograd accumulates into an existing .grad in place)."""
 
-    def __init__(self, raw: Dict, device, light: Optional[Dict] = None):
+    def __init__(self, raw: Dict, device, light: Optional[Dict] = None, light_base: Optional[torch.Tensor] = None,
+                 cutoff: float = 0.99):
+        if light is not None and light_base is not None:
+            raise ValueError("give the light either as textures (light=) or as the base cubemap (light_base=)")
         P = raw["xyz"].shape[0]
         self.P = P
         self.sh_degree = raw["sh_degree"]
@@ -33,15 +38,24 @@ class GaussianParams:
         if light is not None:
             self.light_leaves = [t.to(device).float().contiguous().requires_grad_(True)
                                  for t in (light["diffuse"], *light["specular"])]
-        n = sum(t.numel() for t in self.leaves.values()) + sum(t.numel() for t in self.light_leaves)
+        self.light_base: Optional[torch.Tensor] = None
+        extra = [(f"light{i}", t) for i, t in enumerate(self.light_leaves)]
+        if light_base is not None:
+            self.light_base = light_base.to(device).float().contiguous().requires_grad_(True)
+            extra = [("light_base", self.light_base)]
+        n = sum(t.numel() for t in self.leaves.values()) + sum(t.numel() for _, t in extra)
         self.flat_grad = torch.zeros(n, dtype=torch.float32, device=device)
         o = 0
         self._span = {}
-        for k, t in list(self.leaves.items()) + [(f"light{i}", t) for i, t in enumerate(self.light_leaves)]:
+        for k, t in list(self.leaves.items()) + extra:
             t.grad = self.flat_grad[o:o + t.numel()].view_as(t)
             self._span[k] = (o, o + t.numel())
             o += t.numel()
         self._dirty = None   # spans the fused path has written since the last zero_grad; None = unknown / anything
+        self.prefiltered = None
+        if self.light_base is not None:
+            from .light import PrefilteredLight
+            self.prefiltered = PrefilteredLight(self.light_base, cutoff=cutoff)
 
     def mark_dirty(self, keys=None):
         if keys is None:
@@ -75,14 +89,19 @@ class GaussianParams:
         fused backward records before its blend backward) fires, so the exchange overlaps the rest of the backward.
         all_reduce_grads(fused_only=True) then exchanges the remaining spans and waits for this one."""
         import torch.distributed as dist
-        if not self.light_leaves:
+        if not self.light_leaves and self.prefiltered is None:
             return
         if getattr(self, "_comm", None) is None:
             self._comm = torch.cuda.Stream(device=self.flat_grad.device)
-        lo = self._span["light0"][0]
-        hi = self._span[f"light{len(self.light_leaves) - 1}"][1]
+        if self.prefiltered is not None:
+            lo, hi = self._span["light_base"]
+        else:
+            lo = self._span["light0"][0]
+            hi = self._span[f"light{len(self.light_leaves) - 1}"][1]
         with torch.cuda.stream(self._comm):
             self._comm.wait_event(light_ready)
+            if self.prefiltered is not None:     # texture gradients -> d loss / d base, then exchange the base's
+                self.prefiltered.backward(self.light_base.grad, accumulate=True)
             work = dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.SUM, async_op=True)
         self._pending_light = (work, lo, hi)
 
@@ -121,27 +140,60 @@ class GaussianParams:
                     rotations=F.normalize(L["rot"], dim=-1), shs=torch.cat((L["f_dc"], L["f_rest"]), dim=1),
                     sh_degree=self.sh_degree)
 
-    def light(self) -> Optional[Light]:
+    def light(self):
+        """The light the shading reads: ready-made leaf textures, or the PrefilteredLight built from `light_base`."""
+        if self.prefiltered is not None:
+            return self.prefiltered
         if not self.light_leaves:
             return None
         return Light(specular=list(self.light_leaves[1:]), diffuse=self.light_leaves[0])
 
+    def light_keys(self) -> List[str]:
+        return ["light_base"] if self.prefiltered is not None else [f"light{i}" for i in range(len(self.light_leaves))]
 
-def training_step(params: GaussianParams, cam, light: Light, brdf_lut, rays, gt_image, background, gi: Dict,
+    def light_backward_overlapped(self, light_ready) -> None:
+        """Single-rank form of begin_light_all_reduce: run the mips' backward on a side stream as soon as the texture
+        gradients are final (`light_ready`, recorded before the blend backward), then make the main stream wait for
+        it — the 0.23 ms of filter backward run under the blend backward instead of after it."""
+        if getattr(self, "_comm", None) is None:
+            self._comm = torch.cuda.Stream(device=self.flat_grad.device)
+        with torch.cuda.stream(self._comm):
+            self._comm.wait_event(light_ready)
+            self.prefiltered.backward(self.light_base.grad, accumulate=True)
+            done = torch.cuda.Event()
+            done.record()
+        torch.cuda.current_stream().wait_event(done)
+
+
+def training_step(params: GaussianParams, cam, light, brdf_lut, rays, gt_image, background, gi: Dict,
                   metallic=True, gamma=True, tone=False, indirect=True, loss_scale: float = 1.0,
-                  fused: bool = True, gt_ready=None, light_ready=None) -> torch.Tensor:
+                  fused: bool = True, gt_ready=None, light_ready=None, build_light: bool = True,
+                  finish_light: bool = True) -> torch.Tensor:
     """forward + loss + backward for ONE view; gradients accumulate into params.flat_grad.
+
+    When `light` is params.prefiltered (the light given as its trainable base cubemap), build_light rebuilds the mips
+    first (train.py:340) and finish_light back-propagates the texture gradients into the base afterwards, on a side
+    stream under the blend backward; a multi-view step builds once, finishes once (multi_view_step).
 
     fused=True (default) runs the frame as two C-ABI calls (gigs.frame: activations, rasterizer, deferred shading /
     SSR / loss kernels and the material-only backward, ~25 kernel launches). fused=False runs the same frame
     operator by operator through the drop-in modules and autograd (~200 launches): same result to float rounding,
     kept as the reference-shaped path and as the parity check of the fused one."""
+    pre = params.prefiltered if (params.prefiltered is not None and light is params.prefiltered) else None
+    if pre is not None and build_light:
+        pre.build()
     if fused:
         from .frame import pbr_frame_step
-        params.mark_dirty(["albedo", "roughness", "metallic"] + [f"light{i}" for i in range(len(params.light_leaves))])
-        return pbr_frame_step(params, cam, light, brdf_lut, rays, gt_image, background, gi, metallic=metallic,
+        params.mark_dirty(["albedo", "roughness", "metallic"] + params.light_keys())
+        own_event = pre is not None and finish_light and light_ready is None
+        if own_event:
+            light_ready = torch.cuda.Event()
+        loss = pbr_frame_step(params, cam, light, brdf_lut, rays, gt_image, background, gi, metallic=metallic,
                               gamma=gamma, tone=tone, indirect=indirect, loss_scale=loss_scale, gt_ready=gt_ready,
                               light_ready=light_ready)
+        if own_event:
+            params.light_backward_overlapped(light_ready)
+        return loss
     if gt_ready is not None:
         torch.cuda.current_stream().wait_event(gt_ready)
     params.mark_dirty(None)
@@ -150,6 +202,8 @@ def training_step(params: GaussianParams, cam, light: Light, brdf_lut, rays, gt_
                       gamma=gamma, gi=gi)
     loss = pbr_loss(res, gt_image) * loss_scale
     loss.backward()
+    if pre is not None and finish_light:
+        pre.backward(params.light_base.grad, accumulate=True)
     return loss.detach()
 
 
@@ -163,12 +217,16 @@ def multi_view_step(params: GaussianParams, cams: List, light: Light, brdf_lut, 
     total = torch.zeros((), device=params.flat_grad.device)
     mine = list(range(rank, K, world))
     fused = bool(kw.get("fused", True))
+    pre = params.prefiltered if (params.prefiltered is not None and light is params.prefiltered) else None
     for k in mine:
         ev = None
-        if world > 1 and fused and k == mine[-1]:
+        last = k == mine[-1]
+        if world > 1 and fused and last:
             ev = torch.cuda.Event()   # light gradients are final after the last local view's deferred backward
+        # the mips are built once per step and back-propagated once, after the last local view (both are linear)
         total = total + training_step(params, cams[k], light, brdf_lut, rays_of(cams[k]), gts[k], background, gi,
-                                      loss_scale=1.0 / K, light_ready=ev, **kw)
+                                      loss_scale=1.0 / K, light_ready=ev, build_light=(k == mine[0]),
+                                      finish_light=(last and ev is None), **kw)
         if ev is not None:
             params.begin_light_all_reduce(ev)
     if world > 1:

@@ -209,3 +209,35 @@ def test_frame_waits_for_the_ground_truth_event():
     l2 = float(gstep.training_step(p, cam, p.light(), lut, rays, gt2, bg, GI8, gt_ready=ev))
     assert l2 == l_ref
     assert torch.allclose(p.flat_grad, g_ref, rtol=1e-5, atol=1e-10)
+
+
+def test_step_with_the_light_as_base_cubemap_matches_autograd_through_build_mips():
+    """training_step with GaussianParams(light_base=...): build_mips before the frame, the mips' backward after (on a
+    side stream, fused path) == autograd through the op-by-op CubemapLight.build_mips feeding the operator path."""
+    from gigs import light as GL
+    P, W, H = 20000, 400, 300
+    raw, cam, lut, rays, gt, bg = _setup(P, W, H)
+    base = (torch.rand(6, 64, 64, 3, generator=torch.Generator().manual_seed(21)) * 0.5 + 0.25).to(DEV)
+    # autograd reference: base -> cubemap_mip / specular_cubemap / diffuse_cubemap -> shading -> loss
+    ref = gstep.GaussianParams(raw, DEV)
+    cl = GL.CubemapLight(64, device=DEV, base=base.clone())
+    cl.build_mips()
+    res = renderer.pbr_forward(cam, ref.activated(), shade.Light(specular=cl.specular, diffuse=cl.diffuse), lut, rays,
+                               bg, gi=GI64)
+    loss_ref = renderer.pbr_loss(res, gt)
+    loss_ref.backward()
+    g_ref = cl.base.grad
+    assert float(g_ref.abs().max()) > 0
+    for fused in (True, False):
+        p = gstep.GaussianParams(raw, DEV, light_base=base.clone())
+        p.zero_grad()
+        loss = gstep.training_step(p, cam, p.light(), lut, rays, gt, bg, GI64, fused=fused)
+        torch.cuda.synchronize()
+        assert abs(float(loss) - float(loss_ref)) <= 1e-5 * abs(float(loss_ref)), fused
+        U.assert_grad_close(p.light_base.grad, g_ref, f"light_base (fused={fused})", 1e-3)
+        U.assert_grad_close(p.leaves["albedo"].grad, ref.leaves["albedo"].grad, f"albedo (fused={fused})", 1e-3)
+        assert float(p.prefiltered.texture_grads.abs().max()) == 0.0    # consumed and cleared
+        # a second step accumulates (zero_grad not called): twice the gradient
+        gstep.training_step(p, cam, p.light(), lut, rays, gt, bg, GI64, fused=fused)
+        torch.cuda.synchronize()
+        U.assert_grad_close(p.light_base.grad, 2.0 * g_ref, f"light_base, two steps (fused={fused})", 1e-3)
