@@ -160,7 +160,8 @@ def run_reference(args):
 def workload_config(args, world):
     return {"workload": f"BASELINE configs[1]: lego-shaped synthetic scene, {args.P} Gaussians (trained-like regime), "
                         f"{args.W}x{args.H}, SH degree 3, PBR-stage training frame fwd+bwd "
-                        f"(G-buffer + SSAO + split-sum shade + SSR), --metallic --indirect --gamma",
+                        f"(G-buffer + SSAO + split-sum shade + SSR; loss = L1 + BRDF TV prior (weight 1.0) + lamb prior as "
+                        f"train.py:385-404), --metallic --indirect --gamma",
             "gi": dict(GI_BASE, start=args.start), "views_per_step": world, "parallelism": f"view-sharded dp{world}",
             "l2": "256 MiB L2 flush between timed steps (and the working set exceeds the 126 MB L2)"}
 
@@ -229,8 +230,11 @@ def run_ours(args):
         else:
             cam, gt = cams[k], gts[k]
         light_ready = torch.cuda.Event() if (world > 1 and fused) else None
+        # the two smoothness priors of the reference's PBR-stage loss at its default weights (train.py:185-186); the
+        # env-map one needs the base cubemap, i.e. only the build_mips variant has it
         loss = gstep.training_step(params, cam, light, lut, rays, gt, bg, gi, loss_scale=1.0 / world, fused=fused,
-                                   gt_ready=gt_ready, light_ready=light_ready)
+                                   gt_ready=gt_ready, light_ready=light_ready, brdf_tv_weight=1.0,
+                                   env_tv_weight=0.01 if params.prefiltered is not None else 0.0)
         if world > 1:
             if light_ready is not None:
                 params.begin_light_all_reduce(light_ready)   # overlaps the blend backward
@@ -445,7 +449,8 @@ def run_ours(args):
                           "light_base_res": 256, "stage_ms": {k2: stm.get(k2) for k2 in ("light_build", "light_backward")},
                           "stored_operator_bytes": int(lay_.weights_bytes),
                           "note": "build_mips forward before the frame, its backward on a side stream under the blend "
-                                  "backward; filters stored as sparse operators in HBM and streamed each step"}
+                                  "backward; filters stored as sparse operators in HBM and streamed each step; the "
+                                  "env-map TV prior (weight 0.01, train.py:406-420) is part of this variant's loss"}
                     for nm in ("light_build", "light_backward"):
                         if stm.get(nm):
                             ach = wbytes / (stm[nm] / max(stc[nm], 1) * 1e-3) / 1e9

@@ -677,6 +677,87 @@ __global__ void __launch_bounds__(256, MINB) cm_sparse_kernel(const __grid_const
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Env-map smoothness prior (train.py:406-420): envmap = seamless bilinear lookup of the BASE cubemap along a fixed
+// [EH,EW] lat-long grid of directions; loss = mean((env[1:] - env[:-1])^2) + mean((env[:,1:] - env[:,:-1])^2).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+env_lookup_kernel(const int N, const float* __restrict__ base, const float* __restrict__ dirs, const int n, float* __restrict__ env)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const CubeTaps T = cube_taps(dirs[3 * (size_t)i], dirs[3 * (size_t)i + 1], dirs[3 * (size_t)i + 2], N);
+    const float3 v = cube_fetch(base, T);
+    env[3 * (size_t)i] = v.x; env[3 * (size_t)i + 1] = v.y; env[3 * (size_t)i + 2] = v.z;
+}
+
+// per pixel: its two forward differences (loss partials, one per CTA) and, if grad_base, d loss / d env(pixel) from the
+// (up to) four differences that touch it, scattered through the pixel's four bilinear taps
+__global__ void __launch_bounds__(256)
+env_tv_kernel(const int N, const int EH, const int EW, const float* __restrict__ env, const float* __restrict__ dirs,
+              const float scale /*weight * loss_scale*/, float* __restrict__ partials, float* __restrict__ grad_base)
+{
+    __shared__ float s_red[8];
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const int n = EH * EW;
+    float part = 0.f;
+    if (i < n) {
+        const int x = i % EW, y = i / EW;
+        const float kh = 1.0f / (3.0f * (float)(EH - 1) * (float)EW), kw = 1.0f / (3.0f * (float)EH * (float)(EW - 1));
+        const float* e = env + 3 * (size_t)i;
+        float g[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float v = e[c];
+            if (y + 1 < EH) { const float d = e[3 * EW + c] - v; part += d * d * kh; g[c] -= 2.f * kh * d; }
+            if (x + 1 < EW) { const float d = e[3 + c] - v; part += d * d * kw; g[c] -= 2.f * kw * d; }
+            if (y > 0) g[c] += 2.f * kh * (v - e[c - 3 * EW]);
+            if (x > 0) g[c] += 2.f * kw * (v - e[c - 3]);
+        }
+        if (grad_base) {
+            const CubeTaps T = cube_taps(dirs[3 * (size_t)i], dirs[3 * (size_t)i + 1], dirs[3 * (size_t)i + 2], N);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (T.idx[k] >= 0 && T.w[k] != 0.f) {
+                    float* o = grad_base + 3 * (size_t)T.idx[k];
+                    const float w = T.w[k] * scale;
+                    red_add_f32(o, g[0] * w); red_add_f32(o + 1, g[1] * w); red_add_f32(o + 2, g[2] * w);
+                }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += s_red[w];
+        partials[blockIdx.x] = t;
+    }
+}
+
+// fixed-order sum of the per-CTA partials (deterministic); loss_out = [accumulate ? loss_out : 0] + scale * sum
+__global__ void __launch_bounds__(256)
+env_tv_sum_kernel(const int nblk, const float* __restrict__ partials, const float scale, float* __restrict__ loss_out,
+                  const bool accumulate)
+{
+    __shared__ float s_red[8];
+    float a = 0.f;
+    for (int i = threadIdx.x; i < nblk; i += 256) a += partials[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += s_red[w];
+        loss_out[0] = (accumulate ? loss_out[0] : 0.f) + scale * t;
+    }
+}
+
 }  // namespace gigs
 
 using namespace gigs;
@@ -1043,6 +1124,29 @@ int gigs_light_backward(const GigsLightLayout* L, void* ws, const void* weights,
     }
     if (clear_grads)
         GIGS_CUDA(cudaMemsetAsync(at(ws, L->grad_begin), 0, L->grad_bytes, st));
+    return 0;
+}
+
+int gigs_env_tv(int32_t base_res, const float* base, const float* dirs, int32_t env_h, int32_t env_w, float scale,
+                void* scratch, uint64_t* scratch_bytes, float* grad_base, float* loss_out, int32_t accumulate_loss,
+                void* stream)
+{
+    if (base_res <= 0 || env_h < 2 || env_w < 2 || !scratch_bytes) { set_error("gigs_env_tv: bad arguments"); return -1; }
+    const int n = env_h * env_w, nblk = (n + 255) / 256;
+    const uint64_t need = ((uint64_t)n * 12 + 255) / 256 * 256 + (uint64_t)nblk * 4;
+    if (!scratch) { *scratch_bytes = need; return 0; }
+    if (*scratch_bytes < need || !base || !dirs) { set_error("gigs_env_tv: scratch too small or NULL input"); return -1; }
+    cudaStream_t st = (cudaStream_t)stream;
+    float* env = (float*)scratch;
+    float* partials = (float*)((char*)scratch + ((uint64_t)n * 12 + 255) / 256 * 256);
+    env_lookup_kernel<<<nblk, 256, 0, st>>>(base_res, base, dirs, n, env);
+    GIGS_LAUNCH_CHECK("env_lookup_kernel");
+    env_tv_kernel<<<nblk, 256, 0, st>>>(base_res, env_h, env_w, env, dirs, scale, partials, grad_base);
+    GIGS_LAUNCH_CHECK("env_tv_kernel");
+    if (loss_out) {
+        env_tv_sum_kernel<<<1, 256, 0, st>>>(nblk, partials, scale, loss_out, accumulate_loss != 0);
+        GIGS_LAUNCH_CHECK("env_tv_sum_kernel");
+    }
     return 0;
 }
 

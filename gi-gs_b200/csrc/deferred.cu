@@ -47,10 +47,12 @@ struct DeferParams {
     float *render_rgb, *g_rgb;
     float *g_albedo, *g_roughness, *g_metallic;
     uint8_t *mask, *median_sel;
-    float* partials;         // [0 .. 4*nblk): shade partials {cnt, s1, s2, -}; [4*nblk .. 5*nblk): L1 partials
+    float* partials;         // [0 .. 4*nblk): shade partials {cnt, s1, s2, -}; [4*nblk .. 5*nblk): L1 partials;
+                             // [5*nblk .. 7*nblk): BRDF TV partials {vertical, horizontal}
     uint32_t* counter;       // CTAs of the loss kernel that have finished
     float* stats;
-    float loss_scale, lamb_weight;
+    float* tv_edge;          // [2,H,W]: exp(-mean_c |d gt|) * mask * mask of the edge below / right of each pixel
+    float loss_scale, lamb_weight, brdf_tv_weight;
     int nblk;
 };
 
@@ -260,10 +262,43 @@ __global__ void __launch_bounds__(256) deferred_loss_kernel(const DeferParams p)
         }
     }
     if (!p.gt) return;
+    // BRDF smoothness prior (train.py:388-402, get_masked_tv_loss :118-142; with a full mask it equals get_tv_loss):
+    // squared forward differences of [albedo, roughness (remapped), metallic] weighted by exp(-mean_c |d gt|) and by the
+    // mask of both pixels of the edge. The edge weights are kept for the backward kernel.
+    float tvh = 0.f, tvw = 0.f;
+    if (p.brdf_tv_weight != 0.f && x < W && y < H) {
+        const size_t id = (size_t)y * W + x;
+        const float pr[5] = {p.albedo[id], p.albedo[HW + id], p.albedo[2 * HW + id], p.rough_remap[id], p.metal_used[id]};
+        const float g0[3] = {p.gt[id], p.gt[HW + id], p.gt[2 * HW + id]};
+        const float m0 = p.mask[id] ? 1.f : 0.f;
+        float eh = 0.f, ew = 0.f;
+        if (y + 1 < H) {
+            const size_t jd = id + W;
+            const float dg = (fabsf(p.gt[jd] - g0[0]) + fabsf(p.gt[HW + jd] - g0[1]) + fabsf(p.gt[2 * HW + jd] - g0[2])) / 3.0f;
+            eh = expf(-dg) * (m0 * (p.mask[jd] ? 1.f : 0.f));
+            const float q[5] = {p.albedo[jd], p.albedo[HW + jd], p.albedo[2 * HW + jd], p.rough_remap[jd], p.metal_used[jd]};
+#pragma unroll
+            for (int c = 0; c < 5; ++c) tvh += (q[c] - pr[c]) * (q[c] - pr[c]) * eh;
+        }
+        if (x + 1 < W) {
+            const size_t jd = id + 1;
+            const float dg = (fabsf(p.gt[jd] - g0[0]) + fabsf(p.gt[HW + jd] - g0[1]) + fabsf(p.gt[2 * HW + jd] - g0[2])) / 3.0f;
+            ew = expf(-dg) * (m0 * (p.mask[jd] ? 1.f : 0.f));
+            const float q[5] = {p.albedo[jd], p.albedo[HW + jd], p.albedo[2 * HW + jd], p.rough_remap[jd], p.metal_used[jd]};
+#pragma unroll
+            for (int c = 0; c < 5; ++c) tvw += (q[c] - pr[c]) * (q[c] - pr[c]) * ew;
+        }
+        p.tv_edge[id] = eh;
+        p.tv_edge[HW + id] = ew;
+    }
     const int blk = blockIdx.y * gridDim.x + blockIdx.x;
     const float t = block_sum_256(l1, s_red, tid);
+    const float th = block_sum_256(tvh, s_red, tid);
+    const float tw = block_sum_256(tvw, s_red, tid);
     if (tid == 0) {
         p.partials[4 * p.nblk + blk] = t;
+        p.partials[5 * p.nblk + blk] = th;
+        p.partials[6 * p.nblk + blk] = tw;
         __threadfence();
         const uint32_t done = atomicAdd(p.counter, 1u);
         s_last = (done == (uint32_t)p.nblk - 1u);
@@ -272,26 +307,34 @@ __global__ void __launch_bounds__(256) deferred_loss_kernel(const DeferParams p)
     if (!s_last) return;
     __threadfence();
     // last CTA: fixed-order sum of the per-CTA partials (deterministic, unlike a float atomic)
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f;
     for (int i = tid; i < p.nblk; i += 256) {
         a0 += __ldcg(p.partials + 4 * i + 0);
         a1 += __ldcg(p.partials + 4 * i + 1);
         a2 += __ldcg(p.partials + 4 * i + 2);
         a3 += __ldcg(p.partials + 4 * p.nblk + i);
+        a4 += __ldcg(p.partials + 5 * p.nblk + i);
+        a5 += __ldcg(p.partials + 6 * p.nblk + i);
     }
     const float cnt = block_sum_256(a0, s_red, tid);
     const float s1 = block_sum_256(a1, s_red, tid);
     const float s2 = block_sum_256(a2, s_red, tid);
     const float l1s = block_sum_256(a3, s_red, tid);
+    const float tvhs = block_sum_256(a4, s_red, tid);
+    const float tvws = block_sum_256(a5, s_red, tid);
     if (tid == 0) {
         const float l1_mean = l1s / (float)(3 * HW);
         const float c = fmaxf(cnt, 1.0f);
-        const float loss = (l1_mean + p.lamb_weight * (s1 / c + s2 / c)) * p.loss_scale;   // train.py:384-386,402-404
-        p.stats[0] = loss;
+        // .mean() over [5,H-1,W] and [5,H,W-1] (a 1-pixel-high / -wide image has an empty mean: NaN in the reference)
+        const float tv = tvhs / (5.0f * (float)(H - 1) * (float)W) + tvws / (5.0f * (float)H * (float)(W - 1));
+        float loss = l1_mean + p.lamb_weight * (s1 / c + s2 / c);                    // train.py:384-386,402-404
+        if (p.brdf_tv_weight != 0.f) loss += p.brdf_tv_weight * tv;                 // train.py:402
+        p.stats[0] = loss * p.loss_scale;
         p.stats[1] = l1_mean;
         p.stats[2] = cnt;
         p.stats[3] = s1;
         p.stats[4] = s2;
+        p.stats[5] = tv;
     }
 }
 
@@ -315,6 +358,9 @@ __global__ void __launch_bounds__(256, MINB) deferred_backward_kernel(const Defe
     if (tid == 0) c2w_rotation(p.viewmatrix, s_C);
     const float cnt = fmaxf(p.stats[2], 1.0f);
     const float lamb_g = p.lamb_weight * p.loss_scale / cnt;
+    const bool tv_on = p.brdf_tv_weight != 0.f;
+    const float tv_kh = 2.0f * p.brdf_tv_weight * p.loss_scale / (5.0f * (float)(H - 1) * (float)W);
+    const float tv_kw = 2.0f * p.brdf_tv_weight * p.loss_scale / (5.0f * (float)H * (float)(W - 1));
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int x0 = (tile % tiles_x) * DF_TW, y0 = (tile / tiles_x) * DF_TH;
@@ -368,11 +414,28 @@ __global__ void __launch_bounds__(256, MINB) deferred_backward_kernel(const Defe
 #pragma unroll
             for (int k = 0; k < 3; ++k) gd[k] = shade_tone_bwd(p.sh, lin[k], g_ren[k]);
             shade_material_bwd(p.sh, S, gd, gd, G);
+            // BRDF TV backward: d/d pred(p) of the four squared differences that touch p
+            float g_tv[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+            if (tv_on) {
+                const float pr[5] = {in.alb.x, in.alb.y, in.alb.z, in.rough, in.metal};
+                const float e_dn = p.tv_edge[id], e_rt = p.tv_edge[HW + id];
+                const float e_up = y > 0 ? p.tv_edge[id - W] : 0.f, e_lf = x > 0 ? p.tv_edge[HW + id - 1] : 0.f;
+                const size_t nb[4] = {y > 0 ? id - W : id, y + 1 < H ? id + W : id, x > 0 ? id - 1 : id, x + 1 < W ? id + 1 : id};
+                const float ke[4] = {tv_kh * e_up, tv_kh * e_dn, tv_kw * e_lf, tv_kw * e_rt};
 #pragma unroll
-            for (int k = 0; k < 3; ++k) p.g_albedo[k * HW + id] = G.g_alb[k] + g_alb_ssr[k];
+                for (int k = 0; k < 4; ++k) {
+                    if (ke[k] == 0.f) continue;
+                    const size_t jd = nb[k];
+                    const float q[5] = {p.albedo[jd], p.albedo[HW + jd], p.albedo[2 * HW + jd], p.rough_remap[jd], p.metal_used[jd]};
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) g_tv[c] += (pr[c] - q[c]) * ke[k];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) p.g_albedo[k * HW + id] = G.g_alb[k] + g_alb_ssr[k] + g_tv[k];
             // roughness_map * 0.96 + 0.04 and the lamb prior (1 - rough).mean() + metal.mean() over the mask
-            p.g_roughness[id] = (G.g_rough - (m ? lamb_g : 0.f)) * (1.0f - 0.04f);
-            p.g_metallic[id] = p.use_metallic ? (G.g_metal + (m ? lamb_g : 0.f)) : 0.f;
+            p.g_roughness[id] = (G.g_rough - (m ? lamb_g : 0.f) + g_tv[3]) * (1.0f - 0.04f);
+            p.g_metallic[id] = p.use_metallic ? (G.g_metal + (m ? lamb_g : 0.f) + g_tv[4]) : 0.f;
         } else {
             shade_dead_lane(S, G);
         }
@@ -450,8 +513,9 @@ static GigsFrameLayout frame_layout(int W, int H)
     L.median_sel = take(3 * N);
     const uint64_t nblk = (uint64_t)((W + DF_TW - 1) / DF_TW) * ((H + DF_TH - 1) / DF_TH);
     L.tex_scratch = take((uint64_t)TEX_PRIV_MAX * TEX_PRIV_FLOATS * TEX_COPIES * 4);
-    L.partials = take(5 * nblk * 4);
+    L.partials = take(7 * nblk * 4);
     L.stats = take(64);
+    L.tv_edge = f(2);
     L.total_bytes = align_up(o, 256) + 256;
     return L;
 }
@@ -545,7 +609,8 @@ static void fill_defer(const GigsFrame* f, const GigsFrameLayout& FL, DeferParam
     p.partials = (float*)(m + FL.partials);
     p.stats = (float*)(m + FL.stats);
     p.counter = (uint32_t*)(m + FL.stats + 32);
-    p.loss_scale = f->loss_scale; p.lamb_weight = f->lamb_weight;
+    p.loss_scale = f->loss_scale; p.lamb_weight = f->lamb_weight; p.brdf_tv_weight = f->brdf_tv_weight;
+    p.tv_edge = (float*)(m + FL.tv_edge);
     p.nblk = ((c.width + DF_TW - 1) / DF_TW) * ((c.height + DF_TH - 1) / DF_TH);
 }
 

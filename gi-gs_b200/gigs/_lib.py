@@ -107,7 +107,7 @@ class GigsFrameLayout(C.Structure):
         "color", "opacity", "depth", "normal", "normal_view", "pos", "albedo", "roughness", "metallic",
         "normal_from_depth", "depth_pos", "occlusion", "shade_normal", "ssr_normal", "render_direct", "linear_rgb",
         "F0", "rough_remap", "metal_used", "ssr_color", "ssr_abd", "render_rgb", "g_rgb", "g_albedo", "g_roughness",
-        "g_metallic", "mask", "median_sel", "tex_scratch", "partials", "stats", "total_bytes")]
+        "g_metallic", "mask", "median_sel", "tex_scratch", "partials", "stats", "tv_edge", "total_bytes")]
 
 
 class GigsLightLayout(C.Structure):
@@ -136,7 +136,7 @@ class GigsFrame(C.Structure):
         ("diffuse_res", C.c_int32), ("diffuse", C.c_void_p), ("brdf_lut", C.c_void_p), ("lut_res", C.c_int32),
         ("min_roughness", C.c_float), ("max_roughness", C.c_float),
         ("canonical_rays", C.c_void_p), ("gt_image", C.c_void_p),
-        ("loss_scale", C.c_float), ("lamb_weight", C.c_float),
+        ("loss_scale", C.c_float), ("lamb_weight", C.c_float), ("brdf_tv_weight", C.c_float), ("_pad0", C.c_int32),
         ("geom", C.c_void_p), ("geom_bytes", C.c_uint64), ("img", C.c_void_p), ("img_bytes", C.c_uint64),
         ("binning", C.c_void_p), ("binning_bytes", C.c_uint64), ("sort", C.c_void_p), ("sort_bytes", C.c_uint64),
         ("maps", C.c_void_p), ("maps_bytes", C.c_uint64),
@@ -192,6 +192,7 @@ SYMBOLS = {
     "gigs_light_weights": (C.c_int, [C.POINTER(GigsLightLayout), _vp, _vp, _vp]),
     "gigs_light_build": (C.c_int, [C.POINTER(GigsLightLayout), _vp, _vp, _vp, _vp]),
     "gigs_light_backward": (C.c_int, [C.POINTER(GigsLightLayout), _vp, _vp, _vp, _i32, _i32, _vp]),
+    "gigs_env_tv": (C.c_int, [_i32, _vp, _vp, _i32, _i32, _f, _vp, C.POINTER(C.c_uint64), _vp, _vp, _i32, _vp]),
     "gigs_dist2": (C.c_int, [_i32, _vp, _vp, _vp, C.POINTER(C.c_uint64), _vp]),
     "gigs_ffma_peak": (C.c_int, [C.POINTER(C.c_double), _vp]),
     "gigs_profile_enable": (C.c_int, [_i32]),
@@ -215,7 +216,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the .so does not export it
         fn.restype = res
         fn.argtypes = args
-    if lib.gigs_abi_version() != 2:
+    if lib.gigs_abi_version() != 3:
         raise ImportError("gigs_b200: ABI version mismatch between the python binding and libgigs_b200.so")
     for which, st in enumerate((GigsCamera, GigsSizes, GigsLayout, GigsRasterFwd, GigsRasterBwd, GigsShade,
                                 GigsFrameLayout, GigsFrame, GigsLightLayout)):

@@ -215,6 +215,61 @@ class CubemapLight(nn.Module):
         self.specular[-1] = specular_cubemap(self.specular[-1], 1.0, cutoff)
 
 
+def envmap_dirs(res=(512, 1024), device="cuda") -> torch.Tensor:
+    """train.py:145-157 get_envmap_dirs: [H,W,3] directions of a lat-long grid (computed once, like train.py:209)."""
+    gy, gx = torch.meshgrid(torch.linspace(0.0 + 1.0 / res[0], 1.0 - 1.0 / res[0], res[0], device=device),
+                            torch.linspace(-1.0 + 1.0 / res[1], 1.0 - 1.0 / res[1], res[1], device=device),
+                            indexing="ij")
+    sintheta, costheta = torch.sin(gy * np.pi), torch.cos(gy * np.pi)
+    sinphi, cosphi = torch.sin(gx * np.pi), torch.cos(gx * np.pi)
+    return torch.stack((sintheta * sinphi, costheta, -sintheta * cosphi), dim=-1).contiguous()
+
+
+_env_scratch: Dict = {}
+
+
+def env_tv_fused(base: torch.Tensor, dirs: torch.Tensor, scale: float, grad_base: Optional[torch.Tensor] = None,
+                 loss_out: Optional[torch.Tensor] = None, accumulate_loss: bool = False) -> Optional[torch.Tensor]:
+    """gigs_env_tv: loss_out (+)= scale * env_tv(base), grad_base += scale * d env_tv / d base (either may be None)."""
+    EH, EW = int(dirs.shape[0]), int(dirs.shape[1])
+    key = (EH, EW, base.device.index or 0)
+    sc = _env_scratch.get(key)
+    if sc is None:
+        need = C.c_uint64(0)
+        check(_L.gigs_env_tv(int(base.shape[1]), None, None, EH, EW, 0.0, None, C.byref(need), None, None, 0, None),
+              "gigs_env_tv")
+        sc = _env_scratch[key] = torch.empty(need.value, dtype=torch.uint8, device=base.device)
+    nb = C.c_uint64(sc.numel())
+    with torch.cuda.device(base.device):
+        check(_L.gigs_env_tv(int(base.shape[1]), base.data_ptr(), dirs.data_ptr(), EH, EW, float(scale), sc.data_ptr(),
+                             C.byref(nb), None if grad_base is None else grad_base.data_ptr(),
+                             None if loss_out is None else loss_out.data_ptr(), int(accumulate_loss), _stream()),
+              "gigs_env_tv")
+    return loss_out
+
+
+class _EnvTV(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, base, dirs):
+        b = _cube(base, "base")
+        loss = torch.zeros(1, dtype=torch.float32, device=b.device)
+        env_tv_fused(b, dirs, 1.0, None, loss)
+        ctx.save_for_backward(b, dirs)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        b, dirs = ctx.saved_tensors
+        gb = torch.zeros_like(b)
+        env_tv_fused(b, dirs, 1.0, gb, None)
+        return gb * g, None
+
+
+def env_tv_loss(base: torch.Tensor, dirs: torch.Tensor) -> torch.Tensor:
+    """train.py:406-420: tv_h1 + tv_w1 of the lat-long unwrapping of the base cubemap (differentiable in `base`)."""
+    return _EnvTV.apply(base, dirs.float().contiguous())
+
+
 class PrefilteredLight:
     """build_mips (pbr/light.py:154-170) + its backward through gigs_light_build / gigs_light_backward.
 

@@ -135,13 +135,29 @@ def pbr_forward(cam, g: Dict, light, brdf_lut, canonical_rays, background, indir
     return rr
 
 
-def pbr_loss(res: Dict, gt_image: torch.Tensor, lamb_weight: float = 0.001) -> torch.Tensor:
-    """The rendering part of the PBR-stage loss (train.py:385-386, :402-404): L1 on render_direct + IRR, plus the
-    'lamb' prior. The BRDF / env-map TV terms (train.py:388-420) are loss-side image ops, not
-    part of the hot path, and are not included."""
+def masked_tv_loss(mask: torch.Tensor, gt_image: torch.Tensor, prediction: torch.Tensor) -> torch.Tensor:
+    """train.py:118-142 get_masked_tv_loss (erosion=False); with an all-true mask it equals get_tv_loss(pad=1, step=1)
+    (:83-115), which is the branch train.py:389-401 takes in that case."""
+    rgb_grad_h = torch.exp(-(gt_image[:, 1:, :] - gt_image[:, :-1, :]).abs().mean(dim=0, keepdim=True))
+    rgb_grad_w = torch.exp(-(gt_image[:, :, 1:] - gt_image[:, :, :-1]).abs().mean(dim=0, keepdim=True))
+    tv_h = torch.pow(prediction[:, 1:, :] - prediction[:, :-1, :], 2)
+    tv_w = torch.pow(prediction[:, :, 1:] - prediction[:, :, :-1], 2)
+    mask = mask.float()
+    mask_h = mask[:, 1:, :] * mask[:, :-1, :]
+    mask_w = mask[:, :, 1:] * mask[:, :, :-1]
+    return (tv_h * rgb_grad_h * mask_h).mean() + (tv_w * rgb_grad_w * mask_w).mean()
+
+
+def pbr_loss(res: Dict, gt_image: torch.Tensor, lamb_weight: float = 0.001, brdf_tv_weight: float = 0.0) -> torch.Tensor:
+    """The PBR-stage loss of one view (train.py:385-404): L1 on render_direct + IRR, the BRDF smoothness prior
+    (brdf_tv_weight, reference default 1.0) and the 'lamb' prior. The env-map TV term (train.py:406-420) does not
+    depend on the view: gigs.light.env_tv_loss."""
     loss = torch.abs(res["render_rgb"] - gt_image).mean()
     nm = res["normal_mask"].float()
     rough, metal = res["roughness_remap"], res["metallic_used"]
+    if brdf_tv_weight:
+        loss = loss + brdf_tv_weight * masked_tv_loss(res["normal_mask"], gt_image,
+                                                      torch.cat([res["albedo_map"], rough, metal], dim=0))
     cnt = nm.sum().clamp_min(1.0)  # masked means without a host sync (the reference indexes with the mask)
     loss = loss + lamb_weight * (((1.0 - rough) * nm).sum() / cnt + (metal * nm).sum() / cnt)
     return loss

@@ -148,6 +148,13 @@ class GaussianParams:
             return None
         return Light(specular=list(self.light_leaves[1:]), diffuse=self.light_leaves[0])
 
+    def env_dirs(self) -> torch.Tensor:
+        """The fixed lat-long directions of the env-map TV prior (train.py:209 computes them once as well)."""
+        if getattr(self, "_env_dirs", None) is None:
+            from .light import envmap_dirs
+            self._env_dirs = envmap_dirs(device=self.flat_grad.device)
+        return self._env_dirs
+
     def light_keys(self) -> List[str]:
         return ["light_base"] if self.prefiltered is not None else [f"light{i}" for i in range(len(self.light_leaves))]
 
@@ -168,12 +175,14 @@ class GaussianParams:
 def training_step(params: GaussianParams, cam, light, brdf_lut, rays, gt_image, background, gi: Dict,
                   metallic=True, gamma=True, tone=False, indirect=True, loss_scale: float = 1.0,
                   fused: bool = True, gt_ready=None, light_ready=None, build_light: bool = True,
-                  finish_light: bool = True) -> torch.Tensor:
+                  finish_light: bool = True, brdf_tv_weight: float = 0.0, env_tv_weight: float = 0.0) -> torch.Tensor:
     """forward + loss + backward for ONE view; gradients accumulate into params.flat_grad.
 
     When `light` is params.prefiltered (the light given as its trainable base cubemap), build_light rebuilds the mips
     first (train.py:340) and finish_light back-propagates the texture gradients into the base afterwards, on a side
     stream under the blend backward; a multi-view step builds once, finishes once (multi_view_step).
+    brdf_tv_weight / env_tv_weight: the two smoothness priors of the reference's PBR-stage loss (train.py:388-420,
+    defaults there 1.0 and 0.01); the env-map one needs the base cubemap (light_base=).
 
     fused=True (default) runs the frame as two C-ABI calls (gigs.frame: activations, rasterizer, deferred shading /
     SSR / loss kernels and the material-only backward, ~25 kernel launches). fused=False runs the same frame
@@ -190,9 +199,13 @@ def training_step(params: GaussianParams, cam, light, brdf_lut, rays, gt_image, 
             light_ready = torch.cuda.Event()
         loss = pbr_frame_step(params, cam, light, brdf_lut, rays, gt_image, background, gi, metallic=metallic,
                               gamma=gamma, tone=tone, indirect=indirect, loss_scale=loss_scale, gt_ready=gt_ready,
-                              light_ready=light_ready)
+                              light_ready=light_ready, brdf_tv_weight=brdf_tv_weight)
         if own_event:
             params.light_backward_overlapped(light_ready)
+        if pre is not None and env_tv_weight:
+            from .light import env_tv_fused
+            env_tv_fused(params.light_base.detach(), params.env_dirs(), env_tv_weight * loss_scale,
+                         grad_base=params.light_base.grad, loss_out=loss, accumulate_loss=True)
         return loss
     if gt_ready is not None:
         torch.cuda.current_stream().wait_event(gt_ready)
@@ -200,7 +213,10 @@ def training_step(params: GaussianParams, cam, light, brdf_lut, rays, gt_image, 
     g = params.activated()
     res = pbr_forward(cam, g, light, brdf_lut, rays, background, indirect=indirect, metallic=metallic, tone=tone,
                       gamma=gamma, gi=gi)
-    loss = pbr_loss(res, gt_image) * loss_scale
+    loss = pbr_loss(res, gt_image, brdf_tv_weight=brdf_tv_weight) * loss_scale
+    if pre is not None and env_tv_weight:
+        from .light import env_tv_loss
+        loss = loss + (env_tv_weight * loss_scale) * env_tv_loss(params.light_base, params.env_dirs())
     loss.backward()
     if pre is not None and finish_light:
         pre.backward(params.light_base.grad, accumulate=True)

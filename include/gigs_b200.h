@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define GIGS_ABI_VERSION 2
+#define GIGS_ABI_VERSION 3
 
 /* Per-view constants: the non-tensor fields of GaussianRasterizationSettings
  * (diff_gaussian_rasterization/__init__.py:31-51). Matrices are the transposed (column-major)
@@ -277,7 +277,8 @@ typedef struct GigsFrameLayout {
     uint64_t median_sel;     /* uint8 [3,H,W] window index the IRR median selected (255 = none) */
     uint64_t tex_scratch;    /* float scratch: private copies of the small light-gradient textures (backward) */
     uint64_t partials;       /* float scratch for the deterministic loss reduction */
-    uint64_t stats;          /* float[8]: loss, l1_mean, mask_count, sum((1-rough)*mask), sum(metal*mask), - */
+    uint64_t stats;          /* float[8]: loss, l1_mean, mask_count, sum((1-rough)*mask), sum(metal*mask), brdf_tv, - */
+    uint64_t tv_edge;        /* float[2,H,W]: edge weights of the BRDF TV prior (below / right of each pixel) */
     uint64_t total_bytes;
 } GigsFrameLayout;
 int gigs_frame_layout(int32_t W, int32_t H, GigsFrameLayout* out);
@@ -297,6 +298,8 @@ typedef struct GigsFrame {
     const float* canonical_rays; /* [H*W,3] (scene/__init__.py:157-167) */
     const float* gt_image;       /* [3,H,W]; NULL = forward only, no loss */
     float loss_scale, lamb_weight;
+    float brdf_tv_weight;        /* train.py:388-402 BRDF smoothness prior (get_masked_tv_loss); 0 = off */
+    int32_t _pad0;
     void* geom; uint64_t geom_bytes; void* img; uint64_t img_bytes;
     void* binning; uint64_t binning_bytes; void* sort; uint64_t sort_bytes;
     void* maps; uint64_t maps_bytes;
@@ -396,6 +399,15 @@ int gigs_light_weights(const GigsLightLayout* layout, void* workspace, void* wei
 int gigs_light_build(const GigsLightLayout* layout, const float* base, void* workspace, const void* weights, void* stream);
 int gigs_light_backward(const GigsLightLayout* layout, void* workspace, const void* weights, float* grad_base,
                         int32_t accumulate, int32_t clear_grads, void* stream);
+
+/* Env-map smoothness prior of the PBR-stage loss (/root/reference/train.py:406-420): a seamless bilinear lookup of the
+ * base cubemap [6,R,R,3] along `dirs` [env_h*env_w,3] (get_envmap_dirs, train.py:145-157: a 512x1024 lat-long grid),
+ * loss = mean((env[1:] - env[:-1])^2) + mean((env[:,1:] - env[:,:-1])^2).
+ * loss_out (device float, may be NULL) = [accumulate_loss ? loss_out : 0] + scale * loss; grad_base (may be NULL) +=
+ * scale * d loss / d base. scale = env_tv_weight * loss_scale. scratch == NULL: size query into *scratch_bytes. */
+int gigs_env_tv(int32_t base_res, const float* base, const float* dirs, int32_t env_h, int32_t env_w, float scale,
+                void* scratch, uint64_t* scratch_bytes, float* grad_base, float* loss_out, int32_t accumulate_loss,
+                void* stream);
 
 /* Replaces distCUDA2 / SimpleKNN::knn (/root/reference/submodules/simple-knn/spatial.cu,
  * simple_knn.cu:165-207): mean squared distance to the 3 nearest other points.

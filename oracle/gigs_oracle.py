@@ -1259,3 +1259,35 @@ def build_mips_backward(base_res: int, grad_specular, grad_diffuse, cutoff: floa
     for i in range(n - 1, 0, -1):
         g_chain[i - 1] = g_chain[i - 1] + cubemap_mip_backward(g_chain[i])
     return g_chain[0]
+
+
+# ------------------------------------------------------------------------------------------------
+# The two smoothness priors of the PBR-stage loss: /root/reference/train.py:118-142 (get_masked_tv_loss; with an
+# all-true mask identical to get_tv_loss(pad=1, step=1), :83-115) and :406-420 (env-map TV over get_envmap_dirs,
+# :145-157, with the nvdiffrast cube lookup restated above — that lookup is the unpinned part).
+# Differentiable torch ops: autograd of these is the oracle for the backward.
+# ------------------------------------------------------------------------------------------------
+def masked_tv_loss(mask, gt_image, prediction):
+    rgb_grad_h = torch.exp(-(gt_image[:, 1:, :] - gt_image[:, :-1, :]).abs().mean(dim=0, keepdim=True))
+    rgb_grad_w = torch.exp(-(gt_image[:, :, 1:] - gt_image[:, :, :-1]).abs().mean(dim=0, keepdim=True))
+    tv_h = torch.pow(prediction[:, 1:, :] - prediction[:, :-1, :], 2)
+    tv_w = torch.pow(prediction[:, :, 1:] - prediction[:, :, :-1], 2)
+    mask = mask.float()
+    mask_h = mask[:, 1:, :] * mask[:, :-1, :]
+    mask_w = mask[:, :, 1:] * mask[:, :, :-1]
+    return (tv_h * rgb_grad_h * mask_h).mean() + (tv_w * rgb_grad_w * mask_w).mean()
+
+
+def envmap_dirs(res=(512, 1024)):
+    gy, gx = torch.meshgrid(torch.linspace(0.0 + 1.0 / res[0], 1.0 - 1.0 / res[0], res[0]),
+                            torch.linspace(-1.0 + 1.0 / res[1], 1.0 - 1.0 / res[1], res[1]), indexing="ij")
+    sintheta, costheta = torch.sin(gy * math.pi), torch.cos(gy * math.pi)
+    sinphi, cosphi = torch.sin(gx * math.pi), torch.cos(gx * math.pi)
+    return torch.stack((sintheta * sinphi, costheta, -sintheta * cosphi), dim=-1)
+
+
+def env_tv_loss(base, dirs):
+    envmap = tex_cube(base, dirs)
+    tv_h1 = torch.pow(envmap[1:, :, :] - envmap[:-1, :, :], 2).mean()
+    tv_w1 = torch.pow(envmap[:, 1:, :] - envmap[:, :-1, :], 2).mean()
+    return tv_h1 + tv_w1

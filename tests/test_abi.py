@@ -33,7 +33,7 @@ def test_python_binding_covers_every_declared_symbol():
     from gigs import _lib
     assert sorted(_lib.SYMBOLS) == declared_symbols()
     lib = _lib.load()
-    assert lib.gigs_abi_version() == 2
+    assert lib.gigs_abi_version() == 3
 
 
 def test_workspace_sizes_are_a_pure_function_of_shape():
@@ -87,8 +87,8 @@ def test_frame_layout_is_aligned_disjoint_and_shape_determined():
     fields = offs[:-1]
     assert all(o % 256 == 0 for o in fields) and fields == sorted(fields) and len(set(fields)) == len(fields)
     assert a.total_bytes > fields[-1]
-    # 60 float planes + 4 byte planes at 800x800, the 9.4 MB private-texel scratch, plus small tails
-    assert 60 * 4 * 640000 + 4 * 640000 <= a.total_bytes <= 60 * 4 * 640000 + 4 * 640000 + (11 << 20)
+    # 62 float planes + 4 byte planes at 800x800, the 9.4 MB private-texel scratch, plus small tails
+    assert 62 * 4 * 640000 + 4 * 640000 <= a.total_bytes <= 62 * 4 * 640000 + 4 * 640000 + (11 << 20)
     assert L.gigs_frame_layout(0, 10, ctypes.byref(a)) < 0
     # frame entry points validate their arguments without touching the GPU
     f = _lib.GigsFrame()

@@ -241,3 +241,59 @@ def test_step_with_the_light_as_base_cubemap_matches_autograd_through_build_mips
         gstep.training_step(p, cam, p.light(), lut, rays, gt, bg, GI64, fused=fused)
         torch.cuda.synchronize()
         U.assert_grad_close(p.light_base.grad, 2.0 * g_ref, f"light_base, two steps (fused={fused})", 1e-3)
+
+
+@pytest.mark.parametrize("metallic", [True, False])
+def test_brdf_tv_prior_in_the_frame_matches_the_operator_path(metallic):
+    """train.py:388-402: the fused loss / backward kernels with brdf_tv_weight against the framework-op restatement
+    (renderer.masked_tv_loss) through autograd."""
+    P, W, H, base = 20000, 400, 300, 64
+    raw, cam, lut, rays, gt, bg = _setup(P, W, H)
+    # without the prior first (the frame workspace is shared per shape: read stats right after the step that wrote them)
+    p0 = gstep.GaussianParams(raw, DEV, light=scene.make_light(0, base_res=base))
+    l0 = float(gstep.training_step(p0, cam, p0.light(), lut, rays, gt, bg, GI64, fused=True, metallic=metallic))
+    out = {}
+    for fused in (False, True):
+        p = gstep.GaussianParams(raw, DEV, light=scene.make_light(0, base_res=base))
+        p.zero_grad()
+        out[fused] = (p, float(gstep.training_step(p, cam, p.light(), lut, rays, gt, bg, GI64, fused=fused,
+                                                   metallic=metallic, brdf_tv_weight=1.0)))
+    (pu, lu), (pf, lf) = out[False], out[True]
+    tv = float(pf.last_workspace.map("stats")[5])
+    # the prior is a visible part of the loss on this scene (not a no-op in the comparison)
+    assert lf - l0 > 1e-4 * l0
+    assert abs((lf - l0) - tv) <= 1e-3 * tv
+    assert abs(lf - lu) <= 1e-5 * abs(lu)
+    for k in ("albedo", "roughness") + (("metallic",) if metallic else ()):
+        U.assert_grad_close(pf.leaves[k].grad, pu.leaves[k].grad, f"{k} with the BRDF TV prior", 1e-3)
+        assert not torch.allclose(pf.leaves[k].grad, p0.leaves[k].grad)
+
+
+def test_env_tv_prior_matches_oracle_and_step_paths():
+    """train.py:406-420 on the base cubemap: C-ABI gigs_env_tv vs the CPU oracle (autograd), and through the step."""
+    import gigs_oracle as O
+    from gigs import light as GL
+    base = (torch.rand(6, 64, 64, 3, generator=torch.Generator().manual_seed(31)) * 0.5 + 0.25)
+    dirs = GL.envmap_dirs(device=DEV)
+    assert (dirs.cpu() - O.envmap_dirs()).abs().max().item() <= 1e-6
+    b = base.clone().to(DEV).requires_grad_(True)
+    loss = GL.env_tv_loss(b, dirs)
+    loss.backward()
+    bo = base.clone().requires_grad_(True)
+    lo = O.env_tv_loss(bo, dirs.cpu())
+    lo.backward()
+    assert abs(float(loss) - float(lo)) <= 1e-5 * abs(float(lo))
+    U.assert_grad_close(b.grad.cpu(), bo.grad, "env tv d/d base", 1e-4)
+    # through the training step: fused (direct accumulation) == operator path (autograd)
+    P, W, H = 20000, 400, 300
+    raw, cam, lut, rays, gt, bg = _setup(P, W, H)
+    res = {}
+    for fused in (False, True):
+        p = gstep.GaussianParams(raw, DEV, light_base=base.clone())
+        p.zero_grad()
+        l = gstep.training_step(p, cam, p.light(), lut, rays, gt, bg, GI64, fused=fused, brdf_tv_weight=1.0,
+                                env_tv_weight=0.01)
+        torch.cuda.synchronize()
+        res[fused] = (float(l), p.light_base.grad.clone())
+    assert abs(res[True][0] - res[False][0]) <= 1e-5 * abs(res[False][0])
+    U.assert_grad_close(res[True][1], res[False][1], "light_base with both priors", 1e-3)
