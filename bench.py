@@ -239,6 +239,8 @@ def run_ours(args):
             if light_ready is not None:
                 params.begin_light_all_reduce(light_ready)   # overlaps the blend backward
             params.all_reduce_grads(fused_only=fused)
+        if e2e == "async":
+            return loss          # the caller reads it back through a pinned buffer one step later
         if e2e:
             return float(loss.item())
         return loss
@@ -293,12 +295,57 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), clocks
 
+    def timed_e2e(gi, steps, warmup, flush=False):
+        """End to end through the public step API with HOST inputs: every step copies its camera and ground-truth image
+        from pinned host memory (H2D inside the region) and its loss goes back to the host through a pinned buffer
+        (D2H inside the region). The host consumes the loss of step i while the GPU already runs step i+1 — what a
+        trainer that logs its loss does — so the ~0.1 ms of per-step host work (Python + two ctypes calls) hides under
+        the GPU's 1 ms instead of adding to it. One wall-clock region around all the steps, closed by a full
+        synchronise after the last loss was read. No explicit L2 flush in this region: a frame's working set (maps
+        blob 166 MB + geom 45 MB + SH 58 MB + sort scratch 85 MB) is three times the 126 MB L2 and the views rotate."""
+        slots = [torch.zeros(1).pin_memory(), torch.zeros(1).pin_memory()]
+        evs = [None, None]
+        got = []
+
+        def launch(i):
+            loss = one_step(i, gi, "async", True)
+            slots[i & 1].copy_(loss.reshape(1), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            evs[i & 1] = ev
+
+        def collect(i):
+            evs[i & 1].synchronize()
+            got.append(float(slots[i & 1][0]))
+
+        for i in range(warmup):
+            launch(i)
+            collect(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            if flush:
+                flush_buf.fill_(float(i))      # optional: the 256 MiB L2 flush INSIDE the region (costs ~45 us a step)
+            launch(warmup + i)
+            if i > 0:
+                collect(warmup + i - 1)
+        collect(warmup + steps - 1)
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3
+        assert len(got) == warmup + steps and all(v == v for v in got)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     gi = dict(GI_BASE, start=args.start)
     tot_ms, clocks = timed(gi, args.steps, max(args.warmup, 3), sampler=sampler)
     ms_step = tot_ms / args.steps
     value = world * 1e3 / ms_step
-    e2e_ms, _ = timed(gi, args.steps, 2, e2e=True)
+    e2e_ms = timed_e2e(gi, args.steps, 3)
     e2e_val = world * args.steps * 1e3 / e2e_ms
+    e2e_sync_ms, _ = timed(gi, args.steps, 2, e2e=True)      # same, but the host blocks on every step's loss
+    e2e_flush_ms = timed_e2e(gi, args.steps, 2, flush=True)
     h2d = 3 * args.H * args.W * 4 + (16 + 16 + 3) * 4
 
     # ---- per-stage device times (CUDA events inside the C-ABI, on the launching stream) ----
@@ -324,7 +371,14 @@ def run_ours(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, world), "clocks": clocks,
-            "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}}
+            "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "note": "host inputs (pinned camera + ground-truth image) copied every step; every step's loss read "
+                            "back through a pinned buffer while the next step runs; one wall-clock region over all steps. "
+                            "`value` is device-timed per step with a 256 MiB L2 flush before each step (cold L2); this "
+                            "region has no explicit flush (a frame's working set is ~3x the L2), which is why it can read "
+                            "slightly above `value`; with_l2_flush_inside_region charges the flush to the region",
+                    "blocking_readback_value": world * args.steps * 1e3 / e2e_sync_ms,
+                    "with_l2_flush_inside_region": world * args.steps * 1e3 / e2e_flush_ms}}
 
     if rank == 0:
         # ---- roofline of the dominant kernel -------------------------------------------------------
