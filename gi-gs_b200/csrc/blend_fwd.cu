@@ -26,7 +26,9 @@ struct BlendSmem {
 
 // ARGMAX: track the heaviest contributor's depth / position (settings.argmax_depth); the training and evaluation
 // drivers leave it off, and then the three selects + two compares per contributing pair are dead weight.
-template <bool LITE, bool ARGMAX>
+// MATERIAL (GigsRasterFwd.material_only): the radiance image and the blended position are not wanted — 5 packed FMAs
+// and 3 record loads per contributing pair instead of 8 and 4; every other output is bit-identical.
+template <bool LITE, bool ARGMAX, bool MATERIAL = false>
 __global__ void __launch_bounds__(BL_THREADS)
 blend_forward_kernel(const int W, const int H, const uint2* __restrict__ ranges,
                      const uint32_t* __restrict__ point_list, const float* __restrict__ records,
@@ -134,9 +136,22 @@ blend_forward_kernel(const int W, const int H, const uint2* __restrict__ ranges,
                     continue;
                 }
                 const float weight = alpha * T;
-                const float4 q2 = *reinterpret_cast<const float4*>(&S.rec[s][j][8]);
                 const float depth = q1.z;
                 const float2 w2 = make_float2(weight, weight);
+                if (MATERIAL) {
+                    const float rough = S.rec[s][j][11];
+                    const float4 q3 = *reinterpret_cast<const float4*>(&S.rec[s][j][12]);
+                    const float4 q4 = *reinterpret_cast<const float4*>(&S.rec[s][j][16]);
+                    A01 = ffma2(make_float2(q3.x, q3.y), w2, A01);
+                    A2M = ffma2(make_float2(q3.z, q3.w), w2, A2M);
+                    N01 = ffma2(make_float2(q4.x, q4.y), w2, N01);
+                    C2R = ffma2(make_float2(q4.z, rough), w2, C2R);   // {N2, roughness} in this variant
+                    DO = ffma2(make_float2(depth, 1.0f), w2, DO);
+                    T = test_T;
+                    last_contributor = (uint32_t)(b * BL_BATCH + j + 1);
+                    continue;
+                }
+                const float4 q2 = *reinterpret_cast<const float4*>(&S.rec[s][j][8]);
                 // the 17 accumulations as 8 packed FMAs (FFMA2); halves round exactly like the scalar fma
                 C01 = ffma2(make_float2(q2.x, q2.y), w2, C01);
                 C2R = ffma2(make_float2(q2.z, q2.w), w2, C2R);
@@ -169,13 +184,14 @@ blend_forward_kernel(const int W, const int H, const uint2* __restrict__ ranges,
     }
 
     if (inside) {
-        const float C[3] = {C01.x, C01.y, C2R.x}, N[3] = {N01.x, N01.y, N2P.x}, A[3] = {A01.x, A01.y, A2M.x};
+        const float C[3] = {C01.x, C01.y, C2R.x}, N[3] = {N01.x, N01.y, MATERIAL ? C2R.x : N2P.x}, A[3] = {A01.x, A01.y, A2M.x};
         const float Rg = C2R.y, Mt = A2M.y, D = DO.x, O = DO.y;
         const float3 POS = make_float3(N2P.y, PYZ.x, PYZ.y);
         const int HW = H * W;
         final_T[pix_id] = T;
         n_contrib[pix_id] = last_contributor;
-        for (int ch = 0; ch < 3; ch++) out_color[ch * HW + pix_id] = C[ch] + T * bg_color[ch];
+        if (!MATERIAL)
+            for (int ch = 0; ch < 3; ch++) out_color[ch * HW + pix_id] = C[ch] + T * bg_color[ch];
         if (!LITE) {
             const float* V = viewmatrix;
             float3 Nv;
@@ -195,14 +211,14 @@ blend_forward_kernel(const int W, const int H, const uint2* __restrict__ ranges,
         }
         if (O > 1e-6) {
             out_depth[pix_id] = ARGMAX ? except_depth : D / O;
-            if (!LITE) {
+            if (!LITE && !MATERIAL) {
                 out_pos[pix_id] = ARGMAX ? except_pos.x : POS.x / O;
                 out_pos[HW + pix_id] = ARGMAX ? except_pos.y : POS.y / O;
                 out_pos[2 * HW + pix_id] = ARGMAX ? except_pos.z : POS.z / O;
             }
         } else {
             out_depth[pix_id] = 0.0f;
-            if (!LITE) {
+            if (!LITE && !MATERIAL) {
                 out_pos[pix_id] = 0.0f;
                 out_pos[HW + pix_id] = 0.0f;
                 out_pos[2 * HW + pix_id] = 0.0f;
@@ -226,6 +242,7 @@ int launch_blend_forward(const GigsRasterFwd* a, const Layout& L, bool lite, cud
         GIGS_CUDA(cudaFuncSetAttribute(blend_forward_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
         GIGS_CUDA(cudaFuncSetAttribute(blend_forward_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
         GIGS_CUDA(cudaFuncSetAttribute(blend_forward_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        GIGS_CUDA(cudaFuncSetAttribute(blend_forward_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
         attr_set = true;
     }
     const uint2* ranges = (const uint2*)(im + L.off.i_ranges);
@@ -242,6 +259,7 @@ int launch_blend_forward(const GigsRasterFwd* a, const Layout& L, bool lite, cud
     if (lite && am) blend_forward_kernel<true, true><<<grid, block, sizeof(BlendSmem), st>>>(BL_LITE_ARGS);
     else if (lite) blend_forward_kernel<true, false><<<grid, block, sizeof(BlendSmem), st>>>(BL_LITE_ARGS);
     else if (am) blend_forward_kernel<false, true><<<grid, block, sizeof(BlendSmem), st>>>(BL_FULL_ARGS);
+    else if (a->material_only) blend_forward_kernel<false, false, true><<<grid, block, sizeof(BlendSmem), st>>>(BL_FULL_ARGS);
     else blend_forward_kernel<false, false><<<grid, block, sizeof(BlendSmem), st>>>(BL_FULL_ARGS);
 #undef BL_LITE_ARGS
 #undef BL_FULL_ARGS

@@ -543,6 +543,7 @@ static void fill_raster_fwd(const GigsFrame* f, const GigsFrameLayout& FL, GigsR
     memset(&a, 0, sizeof(a));
     char* m = (char*)f->maps;
     a.P = f->P;
+    a.material_only = f->material_only;
     a.cam = f->cam;
     a.cam.prefiltered = 0; a.cam.argmax_depth = 0;   // cam.inference is honoured (eval / relight sweeps, forward only)
     a.means3D = f->means3D; a.shs = f->sh_dc; a.opacities = f->opacities; a.normal = f->normal; a.albedo = f->albedo;

@@ -139,7 +139,7 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
                   const float* __restrict__ viewmatrix, const float* __restrict__ projmatrix,
                   const float* __restrict__ cam_pos, const int W, const int H, const float tan_fovx,
                   const float tan_fovy, const float focal_x, const float focal_y, const uint32_t grid_x,
-                  const uint32_t grid_y, const bool prefiltered, const bool stage_sh,
+                  const uint32_t grid_y, const bool prefiltered, const bool stage_sh, const bool no_color,
                   // outputs
                   int* __restrict__ radii, float* __restrict__ records, float* __restrict__ cov3Ds,
                   uint8_t* __restrict__ clamped, uint32_t* __restrict__ tiles_touched,
@@ -229,7 +229,9 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
             if ((rect_max.x - rect_min.x) * (rect_max.y - rect_min.y) == 0) break;
 
             float3 rgb;
-            if (colors_precomp == nullptr) {
+            if (no_color) {
+                rgb = make_float3(0.f, 0.f, 0.f);   // material_only: nobody reads the radiance image
+            } else if (colors_precomp == nullptr) {
                 bool cl[3];
                 const float* sh0 = RAW ? shs + (size_t)idx * 3 : shs + (size_t)idx * M * 3;
                 const float* shr = RAW ? sh_rest + ((size_t)idx * (M - 1) - 1) * 3 : sh0;
@@ -469,13 +471,13 @@ int launch_preprocess(const GigsRasterFwd* a, const Layout& L, cudaStream_t st, 
     P, c.sh_degree, c.sh_coeffs, a->means3D, a->scales, c.scale_modifier, a->rotations, a->opacities, a->shs, sh_rest, \
         a->cov3D_precomp, a->colors_precomp, a->normal, a->albedo, a->roughness, a->metallic, c.viewmatrix,           \
         c.projmatrix, c.campos, c.width, c.height, c.tan_fovx, c.tan_fovy, focal_x, focal_y, L.tiles_x, L.tiles_y,    \
-        c.prefiltered != 0, stage_sh, a->radii, (float*)(g + L.off.g_record), (float*)(g + L.off.g_cov3D),            \
+        c.prefiltered != 0, stage_sh, a->material_only != 0, a->radii, (float*)(g + L.off.g_record), (float*)(g + L.off.g_cov3D),            \
         (uint8_t*)(g + L.off.g_clamped), (uint32_t*)(g + L.off.g_tiles_touched), (uint32_t*)(g + L.off.g_depth_keys), \
         (uint32_t*)(g + L.off.g_block_sums)
     // dynamic shared memory: the CTA's slab of SH coefficients (see the kernel); not staged if it would not fit
     const size_t sh_floats = (size_t)PRE_THREADS * (sh_rest ? (c.sh_coeffs - 1) * 3 : c.sh_coeffs * 3);
     static const bool no_stage = getenv("GIGS_PRE_NOSTAGE") != nullptr;
-    const bool stage_sh = !no_stage && a->colors_precomp == nullptr && sh_floats > 0 && sh_floats * 4 <= 96 * 1024;
+    const bool stage_sh = !no_stage && !a->material_only && a->colors_precomp == nullptr && sh_floats > 0 && sh_floats * 4 <= 96 * 1024;
     const size_t smem = stage_sh ? sh_floats * 4 : 0;
     static bool attr_set = false;
     if (!attr_set) {

@@ -154,7 +154,7 @@ def _rasterize(lite, background, means3D, colors, opacity, normal, albedo, rough
     if di not in _pinned:
         _pinned[di] = torch.zeros(1, dtype=torch.int32).pin_memory()
     a = GigsRasterFwd()
-    a.P = P; a.keep_unsorted = 0; a.cam = cam
+    a.P = P; a.material_only = 0; a.cam = cam
     a.means3D = ptr(means3D_c); a.shs = ptr(sh_c); a.colors_precomp = ptr(colors_c); a.opacities = ptr(opac_c)
     a.normal = ptr(normal_c); a.albedo = ptr(albedo_c); a.roughness = ptr(rough_c); a.metallic = ptr(metal_c)
     a.scales = ptr(scales_c); a.rotations = ptr(rot_c); a.cov3D_precomp = ptr(cov_c)

@@ -37,7 +37,7 @@ class GigsLayout(C.Structure):
 
 class GigsRasterFwd(C.Structure):
     _fields_ = [
-        ("P", C.c_int32), ("keep_unsorted", C.c_int32),
+        ("P", C.c_int32), ("material_only", C.c_int32),
         ("cam", GigsCamera),
         ("means3D", C.c_void_p), ("shs", C.c_void_p), ("colors_precomp", C.c_void_p), ("opacities", C.c_void_p),
         ("normal", C.c_void_p), ("albedo", C.c_void_p), ("roughness", C.c_void_p), ("metallic", C.c_void_p),
@@ -136,7 +136,7 @@ class GigsFrame(C.Structure):
         ("diffuse_res", C.c_int32), ("diffuse", C.c_void_p), ("brdf_lut", C.c_void_p), ("lut_res", C.c_int32),
         ("min_roughness", C.c_float), ("max_roughness", C.c_float),
         ("canonical_rays", C.c_void_p), ("gt_image", C.c_void_p),
-        ("loss_scale", C.c_float), ("lamb_weight", C.c_float), ("brdf_tv_weight", C.c_float), ("_pad0", C.c_int32),
+        ("loss_scale", C.c_float), ("lamb_weight", C.c_float), ("brdf_tv_weight", C.c_float), ("material_only", C.c_int32),
         ("geom", C.c_void_p), ("geom_bytes", C.c_uint64), ("img", C.c_void_p), ("img_bytes", C.c_uint64),
         ("binning", C.c_void_p), ("binning_bytes", C.c_uint64), ("sort", C.c_void_p), ("sort_bytes", C.c_uint64),
         ("maps", C.c_void_p), ("maps_bytes", C.c_uint64),

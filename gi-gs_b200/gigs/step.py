@@ -175,7 +175,8 @@ class GaussianParams:
 def training_step(params: GaussianParams, cam, light, brdf_lut, rays, gt_image, background, gi: Dict,
                   metallic=True, gamma=True, tone=False, indirect=True, loss_scale: float = 1.0,
                   fused: bool = True, gt_ready=None, light_ready=None, build_light: bool = True,
-                  finish_light: bool = True, brdf_tv_weight: float = 0.0, env_tv_weight: float = 0.0) -> torch.Tensor:
+                  finish_light: bool = True, brdf_tv_weight: float = 0.0, env_tv_weight: float = 0.0,
+                  radiance: bool = False) -> torch.Tensor:
     """forward + loss + backward for ONE view; gradients accumulate into params.flat_grad.
 
     When `light` is params.prefiltered (the light given as its trainable base cubemap), build_light rebuilds the mips
@@ -183,6 +184,8 @@ def training_step(params: GaussianParams, cam, light, brdf_lut, rays, gt_image, 
     stream under the blend backward; a multi-view step builds once, finishes once (multi_view_step).
     brdf_tv_weight / env_tv_weight: the two smoothness priors of the reference's PBR-stage loss (train.py:388-420,
     defaults there 1.0 and 0.01); the env-map one needs the base cubemap (light_base=).
+    radiance: also produce the SH radiance image and the blended position in the fused frame (the PBR stage reads
+    neither, so by default they are skipped: gigs.frame.pbr_frame_step).
 
     fused=True (default) runs the frame as two C-ABI calls (gigs.frame: activations, rasterizer, deferred shading /
     SSR / loss kernels and the material-only backward, ~25 kernel launches). fused=False runs the same frame
@@ -199,7 +202,7 @@ def training_step(params: GaussianParams, cam, light, brdf_lut, rays, gt_image, 
             light_ready = torch.cuda.Event()
         loss = pbr_frame_step(params, cam, light, brdf_lut, rays, gt_image, background, gi, metallic=metallic,
                               gamma=gamma, tone=tone, indirect=indirect, loss_scale=loss_scale, gt_ready=gt_ready,
-                              light_ready=light_ready, brdf_tv_weight=brdf_tv_weight)
+                              light_ready=light_ready, brdf_tv_weight=brdf_tv_weight, radiance=radiance)
         if own_event:
             params.light_backward_overlapped(light_ready)
         if pre is not None and env_tv_weight:

@@ -90,7 +90,9 @@ int gigs_raster_layout(int32_t P, int32_t W, int32_t H, uint64_t R, GigsLayout* 
  * Output maps are CHW planar float32, fully written by finish (no pre-fill needed). */
 typedef struct GigsRasterFwd {
     int32_t P;
-    int32_t keep_unsorted; /* unused (the sort is always out of place; emission-order pairs survive in the scratch) */
+    int32_t material_only; /* 1: the caller does not read out_color / out_pos (the PBR stage: train.py uses the SH radiance
+                              image only in the first stage and for logging): SH evaluation and those 6 blend channels are
+                              skipped, the two outputs are left untouched. 0 = everything, like the reference. */
     GigsCamera cam;
     const float* means3D;        /* [P,3] */
     const float* shs;            /* [P,M,3] or NULL */
@@ -299,7 +301,7 @@ typedef struct GigsFrame {
     const float* gt_image;       /* [3,H,W]; NULL = forward only, no loss */
     float loss_scale, lamb_weight;
     float brdf_tv_weight;        /* train.py:388-402 BRDF smoothness prior (get_masked_tv_loss); 0 = off */
-    int32_t _pad0;
+    int32_t material_only;       /* GigsRasterFwd.material_only for this frame: the `color` / `pos` maps are not produced */
     void* geom; uint64_t geom_bytes; void* img; uint64_t img_bytes;
     void* binning; uint64_t binning_bytes; void* sort; uint64_t sort_bytes;
     void* maps; uint64_t maps_bytes;

@@ -297,3 +297,25 @@ def test_env_tv_prior_matches_oracle_and_step_paths():
         res[fused] = (float(l), p.light_base.grad.clone())
     assert abs(res[True][0] - res[False][0]) <= 1e-5 * abs(res[False][0])
     U.assert_grad_close(res[True][1], res[False][1], "light_base with both priors", 1e-3)
+
+
+def test_material_only_frame_is_bit_identical_where_it_computes():
+    """GigsRasterFwd.material_only (the default of the fused training frame: no SH radiance image, no blended position)
+    changes nothing else: the loss and every other map are bit-for-bit those of the full frame; the gradients agree to
+    the order of the backward's atomic reductions (two runs of the SAME frame differ at that level)."""
+    P, W, H, base = 20000, 400, 300, 64
+    raw, cam, lut, rays, gt, bg = _setup(P, W, H)
+    res = {}
+    for radiance in (True, False):
+        p = gstep.GaussianParams(raw, DEV, light=scene.make_light(0, base_res=base))
+        p.zero_grad()
+        l = gstep.training_step(p, cam, p.light(), lut, rays, gt, bg, GI8, fused=True, brdf_tv_weight=1.0,
+                                radiance=radiance)
+        ws = p.last_workspace
+        res[radiance] = (float(l), p.flat_grad.clone(),
+                         {k: ws.map(k).clone() for k in ("albedo", "roughness", "metallic", "normal", "normal_view",
+                                                         "depth", "opacity", "occlusion", "render_rgb")})
+    assert res[True][0] == res[False][0]
+    assert ((res[True][1] - res[False][1]).norm() / res[True][1].norm()).item() <= 1e-6
+    for k, v in res[True][2].items():
+        assert torch.equal(v, res[False][2][k]), k
