@@ -200,16 +200,20 @@ def training_step(params: GaussianParams, cam, light, brdf_lut, rays, gt_image, 
         own_event = pre is not None and finish_light and light_ready is None
         if own_event:
             light_ready = torch.cuda.Event()
+        env_loss = None
+        if pre is not None and env_tv_weight:
+            # the env-map prior only needs the base cubemap: it goes FIRST, so that its accumulation into base.grad is
+            # ordered before the mips' backward / the all-reduce that later run on the side stream
+            from .light import env_tv_fused
+            env_loss = torch.empty(1, dtype=torch.float32, device=params.flat_grad.device)
+            env_tv_fused(params.light_base.detach(), params.env_dirs(), env_tv_weight * loss_scale,
+                         grad_base=params.light_base.grad, loss_out=env_loss)
         loss = pbr_frame_step(params, cam, light, brdf_lut, rays, gt_image, background, gi, metallic=metallic,
                               gamma=gamma, tone=tone, indirect=indirect, loss_scale=loss_scale, gt_ready=gt_ready,
                               light_ready=light_ready, brdf_tv_weight=brdf_tv_weight, radiance=radiance)
         if own_event:
             params.light_backward_overlapped(light_ready)
-        if pre is not None and env_tv_weight:
-            from .light import env_tv_fused
-            env_tv_fused(params.light_base.detach(), params.env_dirs(), env_tv_weight * loss_scale,
-                         grad_base=params.light_base.grad, loss_out=loss, accumulate_loss=True)
-        return loss
+        return loss if env_loss is None else loss + env_loss[0]
     if gt_ready is not None:
         torch.cuda.current_stream().wait_event(gt_ready)
     params.mark_dirty(None)

@@ -24,9 +24,13 @@ def _free_port():
     return p
 
 
-def _inputs(dev):
+def _inputs(dev, base_light=False):
     raw = scene.make_scene(P, seed=3)
-    params = gstep.GaussianParams(raw, dev, light=scene.make_light(0, base_res=64))
+    if base_light:   # the light as its trainable base cubemap: build_mips per step, its backward before the all-reduce
+        base = torch.rand(6, 64, 64, 3, generator=torch.Generator().manual_seed(9)) * 0.5 + 0.25
+        params = gstep.GaussianParams(raw, dev, light_base=base)
+    else:
+        params = gstep.GaussianParams(raw, dev, light=scene.make_light(0, base_res=64))
     lut = shade.make_brdf_lut(64, 64).to(dev)
     cams = [scene.orbit_camera(k, 8, W, H).to(dev) for k in range(K)]
     gen = torch.Generator().manual_seed(0)
@@ -34,16 +38,20 @@ def _inputs(dev):
     return params, lut, cams, gts, scene.canonical_rays(cams[0], dev), torch.zeros(3, device=dev)
 
 
-def _worker(rank, world, port, out):
+def _kw(base_light):
+    return dict(brdf_tv_weight=1.0, env_tv_weight=0.01) if base_light else {}
+
+
+def _worker(rank, world, port, out, base_light):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-    params, lut, cams, gts, rays, bg = _inputs(dev)
+    params, lut, cams, gts, rays, bg = _inputs(dev, base_light)
     for _ in range(2):   # twice: the second step exercises zero_grad(fused_only) + a reused comm stream
         total = gstep.multi_view_step(params, cams, params.light(), lut, lambda c: rays, gts, bg, GI, rank=rank,
-                                      world=world)
+                                      world=world, **_kw(base_light))
     torch.cuda.synchronize()
     if rank == 0:
         torch.save(dict(grad=params.flat_grad.cpu(), total=float(total)), out)
@@ -52,13 +60,14 @@ def _worker(rank, world, port, out):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_rank_multi_view_step_matches_single_process(tmp_path):
+@pytest.mark.parametrize("base_light", [False, True])
+def test_two_rank_multi_view_step_matches_single_process(tmp_path, base_light):
     out = str(tmp_path / "r.pt")
-    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), out, base_light), nprocs=2, join=True)
     r = torch.load(out)
     dev = torch.device("cuda", 0)
-    params, lut, cams, gts, rays, bg = _inputs(dev)
-    total = gstep.multi_view_step(params, cams, params.light(), lut, lambda c: rays, gts, bg, GI)
+    params, lut, cams, gts, rays, bg = _inputs(dev, base_light)
+    total = gstep.multi_view_step(params, cams, params.light(), lut, lambda c: rays, gts, bg, GI, **_kw(base_light))
     ref = params.flat_grad.cpu()
     assert abs(r["total"] - float(total)) <= 1e-6 * abs(float(total))
     rel = float((r["grad"] - ref).norm() / ref.norm())
