@@ -407,12 +407,15 @@ def run_ours(args):
         L.gigs_ffma_peak(C.byref(peak_tf), None)
         hbm_peak, hbm_src = measured_peaks()
         alg = {  # algorithmic bytes / flops per launch (DESIGN.md "Kernels")
-            "preprocess": ("hbm", args.P * (44 + 12 * 16 + 8) + vis * (96 + 24 + 4)),
+            # material-only frame: no SH read (the full preprocess adds 12 * M = 192 B per Gaussian at degree 3)
+            "preprocess": ("hbm", args.P * (44 + 12) + vis * (32 + 96 + 24)),
             "depth_sort": ("hbm", args.P * 4 + 4 * 16 * args.P),
             "emit_keys": ("hbm", args.P * 16 + vis * 16 + R * 8),
             "radix_sort": ("hbm", R * 4 + sort_passes * 16 * R),
             "tile_ranges": ("hbm", R * 4),
-            "blend_forward": ("fp32", 50.0 * pairs),
+            # 16 flop for power / alpha / T per visited pair + 2 per blended channel: 17 channels in the full G-buffer
+            # forward (50), 10 in the material-only forward the PBR-stage frame runs (36)
+            "blend_forward": ("fp32", 36.0 * pairs),
             "blend_backward": ("fp32", 30.0 * pairs),  # material-only path of the PBR stage (110 for the full path)
             "gaussian_backward": ("hbm", args.P * 84 + vis * (236 + 256)),
             "radix_sort_pass": ("hbm", 16 * R),
@@ -446,8 +449,9 @@ def run_ours(args):
             pass
         rf.update(kernel=dom, traffic=traffic,
                   peak_source=f"hbm: {hbm_src}; fp32: gigs_ffma_peak measured in this run",
-                  note="bound 'fp32' = FP32 FMA pipe (no tensor-core work on this path); algorithmic flops = 50 (fwd) "
-                       "/ 30 (material-only bwd) per visited (pixel,Gaussian) pair, pairs = sum(n_contrib); traffic = "
+                  note="bound 'fp32' = FP32 FMA pipe (no tensor-core work on this path); algorithmic flops = 36 (material-"
+                       "only fwd: 10 blended channels; the full 17-channel G-buffer forward is 50) / 30 (material-only "
+                       "bwd) per visited (pixel,Gaussian) pair, pairs = sum(n_contrib); traffic = "
                        "DRAM bytes per launch from profiles/traffic.json (ncu --set full), null if not captured")
         line["roofline"] = rf
         # the whole binning step against the REFERENCE algorithm's bytes (duplicate 20 B/Gaussian +

@@ -76,10 +76,16 @@ def cpu_step_sample(g: Dict, cam, bg, light: Dict, lut, gi: Dict, n_tiles: int =
                         occlusion=torch.ones(hs, W, 1), metallic=met, brdf_lut=lut)
     res["render_rgb"].abs().mean().backward()
     t["shade_sample"] = time.perf_counter() - t0
-    est = (t["per_gaussian_fwd"] + t["per_gaussian_bwd"] + t["filters_full"]
+    # BRDF smoothness prior of the loss (train.py:388-402), forward + backward on the full frame
+    pred = torch.cat([fwd["albedo"], fwd["roughness"] * 0.96 + 0.04, fwd["metallic"]], 0).clone().requires_grad_(True)
+    gt_img = torch.rand(3, H, W, generator=gen)
+    t0 = time.perf_counter()
+    O.masked_tv_loss(torch.ones(1, H, W, dtype=torch.bool), gt_img, pred).backward()
+    t["brdf_tv_full"] = time.perf_counter() - t0
+    est = (t["per_gaussian_fwd"] + t["per_gaussian_bwd"] + t["filters_full"] + t["brdf_tv_full"]
            + (t["blend_fwd_sample"] + t["blend_bwd_sample"]) * (T / n_tiles)
            + t["gi_sample"] * (N / n_pix) + t["shade_sample"] * (N / (hs * W)))
     return dict(times=t, est_frame_s=est, frames_per_s=1.0 / est, wall_s=sum(t.values()),
-                sample=f"per-Gaussian stages + 3x3 filter chain on the full {g['means3D'].shape[0]}-Gaussian {W}x{H} "
+                sample=f"per-Gaussian stages + 3x3 filter chain + BRDF TV prior on the full {g['means3D'].shape[0]}-Gaussian {W}x{H} "
                        f"frame; blend fwd+bwd on {n_tiles}/{T} tiles; SSAO+SSR on {n_pix}/{N} pixels; shade fwd+bwd on "
                        f"{hs * W}/{N} pixels; each scaled to the full frame")
