@@ -253,6 +253,7 @@ int gigs_sizeof(int32_t which)
         case 6: return (int)sizeof(GigsFrameLayout);
         case 7: return (int)sizeof(GigsFrame);
         case 8: return (int)sizeof(GigsLightLayout);
+        case 9: return (int)sizeof(GigsAdamGroup);
         default: return -1;
     }
 }

@@ -1,0 +1,271 @@
+// Image loss of the first training stage: (1 - lambda) * L1 + lambda * (1 - SSIM) with its gradient,
+// /root/reference/train.py:320-322 + utils/loss_utils.py:19-20,40-100. The reference runs 5 grouped 11x11
+// convolutions forward (mu1, mu2, E[xx], E[yy], E[xy]), ~15 elementwise kernels, and autograd replays all of them
+// backward; here the forward is ONE kernel (separable 11-tap Gaussian in shared memory on a 16x16 tile with a 5-pixel
+// zero-padded halo, SSIM map, L1, per-CTA partial sums, and the three partial-derivative maps the backward needs) and
+// the backward is ONE kernel (the same separable filter applied to the three derivative maps: the window is symmetric
+// and the padding is zero, so the adjoint of the convolution is the convolution).
+//
+//   S = A1*A2 / (B1*B2),  A1 = 2 mu1 mu2 + C1, A2 = 2 s12 + C2, B1 = mu1^2 + mu2^2 + C1, B2 = s11 + s22 + C2,
+//   s11 = E[xx] - mu1^2, s22 = E[yy] - mu2^2, s12 = E[xy] - mu1 mu2   (operation order of loss_utils.py:77-95)
+//   dS/dE[xx] = -S / B2,  dS/dE[xy] = 2 A1 / (B1 B2),
+//   dS/dmu1 (through s11 and s12 as well) = 2 mu2 (A2 - A1) / (B1 B2) + 2 mu1 S (1/B2 - 1/B1)
+//   dS/dx(p) = sum_q w(q - p) [ dS/dmu1(q) + 2 x(p) dS/dE[xx](q) + y(p) dS/dE[xy](q) ]
+// HBM-bound in principle (forward: 8 B read + 12 B written per element; backward: 20 B read + 4 B written), in
+// practice bound by the shared-memory passes; 800x800x3 is 1.9 M elements, the pair of kernels ~50 us.
+#include <cmath>
+#include "common.cuh"
+
+namespace gigs {
+
+constexpr int SS_T = 16;            // tile
+constexpr int SS_R = 5;             // window radius (window_size 11)
+constexpr int SS_E = SS_T + 2 * SS_R;   // 26
+
+__constant__ float c_ssim_w[11];
+
+struct SsimW { float w[11]; };
+
+// loss_utils.py:40-51: float32 tensor of exp(-(x-5)^2 / (2*1.5^2)) (evaluated in double), divided by its float32 sum
+static SsimW ssim_window()
+{
+    SsimW W;
+    float s = 0.f;
+    for (int i = 0; i < 11; i++) {
+        W.w[i] = (float)std::exp(-(double)((i - 5) * (i - 5)) / (2.0 * 1.5 * 1.5));
+    }
+    // torch.sum over 11 floats: a plain left-to-right float sum is within one ulp of any order; the weights' own
+    // rounding (2^-24 relative) is far below the test tolerance
+    for (int i = 0; i < 11; i++) s += W.w[i];
+    for (int i = 0; i < 11; i++) W.w[i] = W.w[i] / s;
+    return W;
+}
+
+// partial sums layout in scratch: float2 partial[n_ctas] (sum S, sum |x-y|), then uint32 ticket
+__global__ void __launch_bounds__(SS_T* SS_T) ssim_forward_kernel(int C, int W, int H, const float* __restrict__ X,
+                                                                   const float* __restrict__ Y,
+                                                                   float* __restrict__ dmu, float* __restrict__ dxx,
+                                                                   float* __restrict__ dxy, float2* __restrict__ partial)
+{
+    __shared__ float sx[SS_E][SS_E + 1], sy[SS_E][SS_E + 1];
+    __shared__ float h[5][SS_E][SS_T + 1];
+    __shared__ float red[2][SS_T * SS_T / 32];
+    const int c = blockIdx.z;
+    const int x0 = blockIdx.x * SS_T, y0 = blockIdx.y * SS_T;
+    const int tid = threadIdx.y * SS_T + threadIdx.x;
+    const size_t plane = (size_t)c * W * H;
+    for (int i = tid; i < SS_E * SS_E; i += SS_T * SS_T) {
+        const int ly = i / SS_E, lx = i - ly * SS_E;
+        const int gx = x0 + lx - SS_R, gy = y0 + ly - SS_R;
+        float a = 0.f, b = 0.f;
+        if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
+            a = X[plane + (size_t)gy * W + gx];
+            b = Y[plane + (size_t)gy * W + gx];
+        }
+        sx[ly][lx] = a;
+        sy[ly][lx] = b;
+    }
+    __syncthreads();
+    // horizontal pass: 26 rows x 16 columns
+    for (int i = tid; i < SS_E * SS_T; i += SS_T * SS_T) {
+        const int ly = i / SS_T, lx = i - ly * SS_T;
+        float m1 = 0.f, m2 = 0.f, xx = 0.f, yy = 0.f, xy = 0.f;
+#pragma unroll
+        for (int k = 0; k < 11; k++) {
+            const float w = c_ssim_w[k], a = sx[ly][lx + k], b = sy[ly][lx + k];
+            m1 = fmaf(w, a, m1);
+            m2 = fmaf(w, b, m2);
+            xx = fmaf(w, a * a, xx);
+            yy = fmaf(w, b * b, yy);
+            xy = fmaf(w, a * b, xy);
+        }
+        h[0][ly][lx] = m1; h[1][ly][lx] = m2; h[2][ly][lx] = xx; h[3][ly][lx] = yy; h[4][ly][lx] = xy;
+    }
+    __syncthreads();
+    const int lx = threadIdx.x, ly = threadIdx.y;
+    const int gx = x0 + lx, gy = y0 + ly;
+    float S = 0.f, l1 = 0.f;
+    if (gx < W && gy < H) {
+        float mu1 = 0.f, mu2 = 0.f, exx = 0.f, eyy = 0.f, exy = 0.f;
+#pragma unroll
+        for (int k = 0; k < 11; k++) {
+            const float w = c_ssim_w[k];
+            mu1 = fmaf(w, h[0][ly + k][lx], mu1);
+            mu2 = fmaf(w, h[1][ly + k][lx], mu2);
+            exx = fmaf(w, h[2][ly + k][lx], exx);
+            eyy = fmaf(w, h[3][ly + k][lx], eyy);
+            exy = fmaf(w, h[4][ly + k][lx], exy);
+        }
+        const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+        const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
+        const float s11 = exx - mu1_sq, s22 = eyy - mu2_sq, s12 = exy - mu12;
+        const float A1 = 2.f * mu12 + C1, A2 = 2.f * s12 + C2, B1 = mu1_sq + mu2_sq + C1, B2 = s11 + s22 + C2;
+        S = (A1 * A2) / (B1 * B2);
+        const float a = sx[ly + SS_R][lx + SS_R], b = sy[ly + SS_R][lx + SS_R];
+        l1 = fabsf(a - b);
+        if (dmu) {
+            const float inv = 1.f / (B1 * B2);
+            const size_t o = plane + (size_t)gy * W + gx;
+            dmu[o] = 2.f * mu2 * (A2 - A1) * inv + 2.f * mu1 * S * (1.f / B2 - 1.f / B1);
+            dxx[o] = -S / B2;
+            dxy[o] = 2.f * A1 * inv;
+        }
+    }
+    // deterministic CTA reduction (fixed shuffle tree, fixed order over warps)
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        S += __shfl_xor_sync(0xffffffffu, S, o);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+    }
+    if ((tid & 31) == 0) { red[0][tid >> 5] = S; red[1][tid >> 5] = l1; }
+    __syncthreads();
+    if (tid == 0) {
+        float a = 0.f, b = 0.f;
+        for (int i = 0; i < SS_T * SS_T / 32; i++) { a += red[0][i]; b += red[1][i]; }
+        partial[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = make_float2(a, b);
+    }
+}
+
+// one CTA: sums the per-CTA partials in a fixed order (double accumulators), writes loss_out[0..2] = loss, l1, ssim
+__global__ void __launch_bounds__(1024) ssim_finish_kernel(int n, const float2* __restrict__ partial, double inv_n,
+                                                           float lambda, float loss_scale, float* __restrict__ out,
+                                                           int accumulate)
+{
+    __shared__ double rs[32], rl[32];
+    double s = 0.0, l = 0.0;
+    for (int i = threadIdx.x; i < n; i += 1024) { s += (double)partial[i].x; l += (double)partial[i].y; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        l += __shfl_xor_sync(0xffffffffu, l, o);
+    }
+    if ((threadIdx.x & 31) == 0) { rs[threadIdx.x >> 5] = s; rl[threadIdx.x >> 5] = l; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s = 0.0; l = 0.0;
+        for (int i = 0; i < 32; i++) { s += rs[i]; l += rl[i]; }
+        const float ssim = (float)(s * inv_n), l1 = (float)(l * inv_n);
+        const float loss = loss_scale * ((1.f - lambda) * l1 + lambda * (1.f - ssim));
+        out[0] = accumulate ? out[0] + loss : loss;
+        out[1] = l1;
+        out[2] = ssim;
+    }
+}
+
+__global__ void __launch_bounds__(SS_T* SS_T) ssim_backward_kernel(int C, int W, int H, const float* __restrict__ X,
+                                                                    const float* __restrict__ Y,
+                                                                    const float* __restrict__ dmu,
+                                                                    const float* __restrict__ dxx,
+                                                                    const float* __restrict__ dxy, float k_ssim, float k_l1,
+                                                                    const float* __restrict__ upstream,
+                                                                    float* __restrict__ grad, int accumulate)
+{
+    __shared__ float s[3][SS_E][SS_E + 1];
+    __shared__ float h[3][SS_E][SS_T + 1];
+    const int c = blockIdx.z;
+    const int x0 = blockIdx.x * SS_T, y0 = blockIdx.y * SS_T;
+    const int tid = threadIdx.y * SS_T + threadIdx.x;
+    const size_t plane = (size_t)c * W * H;
+    for (int i = tid; i < SS_E * SS_E; i += SS_T * SS_T) {
+        const int ly = i / SS_E, lx = i - ly * SS_E;
+        const int gx = x0 + lx - SS_R, gy = y0 + ly - SS_R;
+        float a = 0.f, b = 0.f, d = 0.f;
+        if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
+            const size_t o = plane + (size_t)gy * W + gx;
+            a = dmu[o]; b = dxx[o]; d = dxy[o];
+        }
+        s[0][ly][lx] = a; s[1][ly][lx] = b; s[2][ly][lx] = d;
+    }
+    __syncthreads();
+    for (int i = tid; i < SS_E * SS_T; i += SS_T * SS_T) {
+        const int ly = i / SS_T, lx = i - ly * SS_T;
+        float a = 0.f, b = 0.f, d = 0.f;
+#pragma unroll
+        for (int k = 0; k < 11; k++) {
+            const float w = c_ssim_w[k];
+            a = fmaf(w, s[0][ly][lx + k], a);
+            b = fmaf(w, s[1][ly][lx + k], b);
+            d = fmaf(w, s[2][ly][lx + k], d);
+        }
+        h[0][ly][lx] = a; h[1][ly][lx] = b; h[2][ly][lx] = d;
+    }
+    __syncthreads();
+    const int lx = threadIdx.x, ly = threadIdx.y;
+    const int gx = x0 + lx, gy = y0 + ly;
+    if (gx >= W || gy >= H) return;
+    float a = 0.f, b = 0.f, d = 0.f;
+#pragma unroll
+    for (int k = 0; k < 11; k++) {
+        const float w = c_ssim_w[k];
+        a = fmaf(w, h[0][ly + k][lx], a);
+        b = fmaf(w, h[1][ly + k][lx], b);
+        d = fmaf(w, h[2][ly + k][lx], d);
+    }
+    const size_t o = plane + (size_t)gy * W + gx;
+    const float x = X[o], y = Y[o];
+    const float dS = a + 2.f * x * b + y * d;
+    const float df = x - y;
+    const float sg = df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f);
+    float g = k_ssim * dS + k_l1 * sg;
+    if (upstream) g *= upstream[0];
+    grad[o] = accumulate ? grad[o] + g : g;
+}
+
+}  // namespace gigs
+
+using namespace gigs;
+
+extern "C" {
+
+int gigs_image_loss(int32_t C, int32_t W, int32_t H, const float* image, const float* gt, float lambda_dssim,
+                    float loss_scale, void* scratch, uint64_t* scratch_bytes, float* loss_out, int32_t accumulate_loss,
+                    float* grad_image, int32_t accumulate_grad, const float* upstream, void* stream)
+{
+    if (C <= 0 || W <= 0 || H <= 0 || !scratch_bytes) { set_error("gigs_image_loss: bad arguments"); return -1; }
+    const dim3 grid((W + SS_T - 1) / SS_T, (H + SS_T - 1) / SS_T, C);
+    const uint64_t n_cta = (uint64_t)grid.x * grid.y * grid.z;
+    const uint64_t n = (uint64_t)C * W * H;
+    const uint64_t maps = grad_image ? align_up(n * 4, 256) : 0;
+    const uint64_t need = 3 * maps + align_up(n_cta * 8, 256);
+    if (!scratch) { *scratch_bytes = 3 * align_up(n * 4, 256) + align_up(n_cta * 8, 256); return 0; }
+    if (*scratch_bytes < need || !image || !gt || (!loss_out && !grad_image)) {
+        set_error("gigs_image_loss: scratch too small (%llu < %llu) or NULL input", (unsigned long long)*scratch_bytes,
+                  (unsigned long long)need);
+        return -1;
+    }
+    if (grid.z > 65535 || grid.y > 65535) { set_error("gigs_image_loss: image too large"); return -1; }
+    cudaStream_t st = (cudaStream_t)stream;
+    static bool w_set = false;   // the window is a constant of the algorithm; uploaded once per process and device
+    static int w_dev = -1;
+    int dev = 0;
+    GIGS_CUDA(cudaGetDevice(&dev));
+    if (!w_set || w_dev != dev) {
+        const SsimW Wt = ssim_window();
+        GIGS_CUDA(cudaMemcpyToSymbolAsync(c_ssim_w, Wt.w, sizeof(Wt.w), 0, cudaMemcpyHostToDevice, st));
+        w_set = true;
+        w_dev = dev;
+    }
+    char* base = (char*)scratch;
+    float* dmu = grad_image ? (float*)base : nullptr;
+    float* dxx = grad_image ? (float*)(base + maps) : nullptr;
+    float* dxy = grad_image ? (float*)(base + 2 * maps) : nullptr;
+    float2* partial = (float2*)(base + 3 * maps);
+    ProfScope prof(27, st);
+    ssim_forward_kernel<<<grid, dim3(SS_T, SS_T), 0, st>>>(C, W, H, image, gt, dmu, dxx, dxy, partial);
+    GIGS_LAUNCH_CHECK("ssim_forward_kernel");
+    if (loss_out) {
+        ssim_finish_kernel<<<1, 1024, 0, st>>>((int)n_cta, partial, 1.0 / (double)n, lambda_dssim, loss_scale, loss_out,
+                                               accumulate_loss);
+        GIGS_LAUNCH_CHECK("ssim_finish_kernel");
+    }
+    if (grad_image) {
+        const float k_ssim = (float)(-(double)loss_scale * (double)lambda_dssim / (double)n);
+        const float k_l1 = (float)((double)loss_scale * (1.0 - (double)lambda_dssim) / (double)n);
+        ssim_backward_kernel<<<grid, dim3(SS_T, SS_T), 0, st>>>(C, W, H, image, gt, dmu, dxx, dxy, k_ssim, k_l1, upstream,
+                                                                grad_image, accumulate_grad);
+        GIGS_LAUNCH_CHECK("ssim_backward_kernel");
+    }
+    return 0;
+}
+
+}  // extern "C"

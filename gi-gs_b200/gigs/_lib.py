@@ -151,6 +151,13 @@ class GigsFrame(C.Structure):
     ]
 
 
+class GigsAdamGroup(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("count", C.c_uint64), ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double),
+                ("eps", C.c_double), ("step", C.c_int32), ("clamp_min0", C.c_int32), ("clear_grad", C.c_int32),
+                ("pad_", C.c_int32)]
+
+
 GIGS_E_GROW = -5
 
 # every symbol include/gigs_b200.h declares: (name, restype, argtypes)
@@ -193,6 +200,10 @@ SYMBOLS = {
     "gigs_light_build": (C.c_int, [C.POINTER(GigsLightLayout), _vp, _vp, _vp, _vp]),
     "gigs_light_backward": (C.c_int, [C.POINTER(GigsLightLayout), _vp, _vp, _vp, _i32, _i32, _vp]),
     "gigs_env_tv": (C.c_int, [_i32, _vp, _vp, _i32, _i32, _f, _vp, C.POINTER(C.c_uint64), _vp, _vp, _i32, _vp]),
+    "gigs_adam_step": (C.c_int, [_i32, C.POINTER(GigsAdamGroup), _vp]),
+    "gigs_densify_stats": (C.c_int, [_i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gigs_image_loss": (C.c_int, [_i32, _i32, _i32, _vp, _vp, _f, _f, _vp, C.POINTER(C.c_uint64), _vp, _i32, _vp, _i32,
+                                  _vp, _vp]),
     "gigs_dist2": (C.c_int, [_i32, _vp, _vp, _vp, C.POINTER(C.c_uint64), _vp]),
     "gigs_ffma_peak": (C.c_int, [C.POINTER(C.c_double), _vp]),
     "gigs_profile_enable": (C.c_int, [_i32]),
@@ -219,7 +230,7 @@ def load():
     if lib.gigs_abi_version() != 3:
         raise ImportError("gigs_b200: ABI version mismatch between the python binding and libgigs_b200.so")
     for which, st in enumerate((GigsCamera, GigsSizes, GigsLayout, GigsRasterFwd, GigsRasterBwd, GigsShade,
-                                GigsFrameLayout, GigsFrame, GigsLightLayout)):
+                                GigsFrameLayout, GigsFrame, GigsLightLayout, GigsAdamGroup)):
         if lib.gigs_sizeof(which) != C.sizeof(st):
             raise ImportError(f"gigs_b200: struct {st.__name__} is {C.sizeof(st)} bytes in the python binding but "
                               f"{lib.gigs_sizeof(which)} in libgigs_b200.so")

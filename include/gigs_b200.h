@@ -48,7 +48,7 @@ int gigs_abi_version(void);
 const char* gigs_last_error(void);
 /* sizeof() of the argument structs, so a foreign-language binding can verify its mirror of the layout:
  * which = 0 GigsCamera, 1 GigsSizes, 2 GigsLayout, 3 GigsRasterFwd, 4 GigsRasterBwd, 5 GigsShade,
- * 6 GigsFrameLayout, 7 GigsFrame, 8 GigsLightLayout; negative for an unknown id. */
+ * 6 GigsFrameLayout, 7 GigsFrame, 8 GigsLightLayout, 9 GigsAdamGroup; negative for an unknown id. */
 int gigs_sizeof(int32_t which);
 int gigs_raster_sizes(int32_t P, int32_t W, int32_t H, uint64_t R, GigsSizes* out);
 
@@ -411,6 +411,52 @@ int gigs_env_tv(int32_t base_res, const float* base, const float* dirs, int32_t 
                 void* scratch, uint64_t* scratch_bytes, float* grad_base, float* loss_out, int32_t accumulate_loss,
                 void* stream);
 
+/* ---- The optimiser step -------------------------------------------------------------------------
+ * Replaces `gaussians.optimizer.step(); gaussians.optimizer.zero_grad(); light_optimizer.step();
+ * light_optimizer.zero_grad(); cubemap.clamp_(min=0.0)` of /root/reference/train.py:516-523 — torch.optim.Adam over
+ * the 10 groups of scene/gaussian_model.py:318-359 (eps 1e-15) and the light's base cubemap (train.py:215-218, eps
+ * 1e-8) — by ONE launch over all groups. Each group is one contiguous float tensor with its two moment tensors.
+ * grad == NULL says "this gradient is all zero" (what the reference's rasterizer backward returns for every
+ * non-material input in the PBR stage): the moments still decay and the parameter still moves exactly as torch's
+ * Adam moves it, but the gradient is neither read nor cleared. `step` is torch's state['step'] AFTER its increment
+ * (1 for the first update). Scalars are doubles because torch forms lr / (1 - beta1^t) and sqrt(1 - beta2^t) from
+ * Python floats. The group array is HOST memory; at most 24 groups per call. */
+typedef struct GigsAdamGroup {
+    float* param;
+    float* grad;        /* may be NULL (see above) */
+    float* exp_avg;
+    float* exp_avg_sq;
+    uint64_t count;     /* elements */
+    double lr, beta1, beta2, eps;
+    int32_t step;
+    int32_t clamp_min0; /* param.clamp_(min=0) after the update (the cubemap) */
+    int32_t clear_grad; /* write zeros over grad after reading it (zero_grad fused into the pass) */
+    int32_t pad_;
+} GigsAdamGroup;
+int gigs_adam_step(int32_t n_groups, const GigsAdamGroup* groups, void* stream);
+
+/* Densification statistics of one view (/root/reference/train.py:489-495 + GaussianModel.add_densification_stats,
+ * scene/gaussian_model.py:933-945) for the Gaussians with radii > 0: max_radii2D = max(max_radii2D, radii),
+ * xyz_gradient_accum += |grad2D.xy|, xyz_gradient_accum_abs += |gx| + |gy|, xyz_gradient_accum_abs_max =
+ * max(., |gx| + |gy|), denom += 1. grad2D is [P, grad_stride] (the reference's means2D gradient is [P,3]);
+ * the *_abs, *_abs_max and max_radii2D outputs may be NULL. */
+int gigs_densify_stats(int32_t P, const int32_t* radii, const float* grad2D, int32_t grad_stride,
+                       float* xyz_gradient_accum, float* xyz_gradient_accum_abs, float* xyz_gradient_accum_abs_max,
+                       float* denom, float* max_radii2D, void* stream);
+
+/* ---- Image loss of the first training stage -------------------------------------------------------
+ * Replaces `(1 - lambda_dssim) * l1_loss(image, gt) + lambda_dssim * (1 - ssim(image, gt))` and its autograd backward
+ * (/root/reference/train.py:320-322, utils/loss_utils.py:19-20 l1_loss, :40-100 ssim: 11x11 Gaussian window sigma 1.5,
+ * zero padding, per channel, mean over all elements) by one forward and one backward kernel. image, gt: [C,H,W].
+ * loss_out (device float[3], may be NULL): [0] = (accumulate_loss ? loss_out[0] : 0) + loss_scale * loss, [1] = the L1
+ * term, [2] = SSIM. grad_image (may be NULL): d(loss_scale * loss)/d image, times *upstream when upstream (a device
+ * scalar, e.g. autograd's grad_output) is given; added to grad_image when accumulate_grad. lambda_dssim = 1 and
+ * loss_scale = -1 give -(1 - ssim), i.e. plain SSIM's gradient up to the constant.
+ * scratch == NULL: size query into *scratch_bytes (3 derivative maps + per-CTA partial sums). */
+int gigs_image_loss(int32_t C, int32_t W, int32_t H, const float* image, const float* gt, float lambda_dssim,
+                    float loss_scale, void* scratch, uint64_t* scratch_bytes, float* loss_out, int32_t accumulate_loss,
+                    float* grad_image, int32_t accumulate_grad, const float* upstream, void* stream);
+
 /* Replaces distCUDA2 / SimpleKNN::knn (/root/reference/submodules/simple-knn/spatial.cu,
  * simple_knn.cu:165-207): mean squared distance to the 3 nearest other points.
  * scratch_bytes: call with scratch==NULL to query. */
@@ -422,7 +468,8 @@ int gigs_dist2(int32_t P, const float* points, float* mean_dist2, void* scratch,
  * 6 gaussian_backward, 7 geometry_chain, 8 ssao, 9 ssr, 10 shade_forward, 11 shade_backward, 12 median3x3,
  * 13 median3x3_backward, 14 bilateral3x3, 15 depth_to_normal, 16 ssr_backward, 17 dist2, 18 deferred_shade,
  * 19 deferred_loss, 20 deferred_backward, 21 param_grad, 22 one radix-sort pass (nested inside 2 / 23),
- * 23 depth argsort of the Gaussians, 24 cubemap prefilter forward, 25 cubemap prefilter backward.
+ * 23 depth argsort of the Gaussians, 24 cubemap prefilter forward, 25 cubemap prefilter backward, 26 Adam step,
+ * 27 image loss (L1 + SSIM forward, finish and backward).
  * gigs_profile_read synchronises the recorded events, writes up to cap (stage, ms) pairs, clears the log and
  * returns the number written (negative on error). Off by default; costs two event records per stage when on. */
 int gigs_profile_enable(int32_t on);

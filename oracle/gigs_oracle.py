@@ -1291,3 +1291,99 @@ def env_tv_loss(base, dirs):
     tv_h1 = torch.pow(envmap[1:, :, :] - envmap[:-1, :, :], 2).mean()
     tv_w1 = torch.pow(envmap[:, 1:, :] - envmap[:, :-1, :], 2).mean()
     return tv_h1 + tv_w1
+
+
+# ------------------------------------------------------------------------------------------------
+# Optimiser step. The reference calls torch.optim.Adam (scene/gaussian_model.py:346, train.py:218):
+# the algorithm lives in torch (pinned here: torch 2.11, torch/optim/adam.py `_single_tensor_adam`), restated in
+# float32 numpy-style tensor ops. PINNED against torch.optim.Adam itself (tests/test_optim.py) and against
+# tests/golden/optim_ref.npz (made by tests/make_golden_optim.py from torch.optim.Adam and the reference's
+# utils/general_utils.get_expon_lr_func).
+# ------------------------------------------------------------------------------------------------
+def adam_step(param, grad, exp_avg, exp_avg_sq, step: int, lr: float, beta1=0.9, beta2=0.999, eps=1e-8,
+              clamp_min0: bool = False):
+    """One update; `step` is state['step'] after its increment. Returns (param, exp_avg, exp_avg_sq), float32."""
+    f32 = torch.float32
+    g = grad.to(f32)
+    m = exp_avg.to(f32) + torch.tensor(1 - beta1, dtype=f32) * (g - exp_avg.to(f32))                 # lerp_
+    v = exp_avg_sq.to(f32) * torch.tensor(beta2, dtype=f32) + (torch.tensor(1 - beta2, dtype=f32) * g) * g  # mul_, addcmul_
+    bc1 = 1 - beta1 ** step
+    bc2 = 1 - beta2 ** step
+    step_size = lr / bc1
+    denom = v.sqrt() / torch.tensor(bc2 ** 0.5, dtype=f32) + torch.tensor(eps, dtype=f32)
+    p = param.to(f32) + torch.tensor(-step_size, dtype=f32) * (m / denom)                            # addcdiv_
+    if clamp_min0:
+        p = p.clamp(min=0.0)
+    return p, m, v
+
+
+def expon_lr(step: int, lr_init: float, lr_final: float, lr_delay_steps: int = 0, lr_delay_mult: float = 1.0,
+             max_steps: int = 1000000) -> float:
+    """utils/general_utils.py:33-70."""
+    if step < 0 or (lr_init == 0.0 and lr_final == 0.0):
+        return 0.0
+    delay = 1.0
+    if lr_delay_steps > 0:
+        delay = lr_delay_mult + (1 - lr_delay_mult) * math.sin(0.5 * math.pi * min(max(step / lr_delay_steps, 0), 1))
+    t = min(max(step / max_steps, 0), 1)
+    return delay * math.exp(math.log(lr_init) * (1 - t) + math.log(lr_final) * t)
+
+
+def densify_stats(radii, grad2D, accum, accum_abs, accum_abs_max, denom, max_radii2D):
+    """train.py:489-495 + scene/gaussian_model.py:933-945 on copies; returns the five updated tensors."""
+    vis = radii > 0
+    accum, accum_abs, accum_abs_max, denom, max_radii2D = (t.clone() for t in (accum, accum_abs, accum_abs_max, denom,
+                                                                                max_radii2D))
+    max_radii2D[vis] = torch.max(max_radii2D[vis], radii[vis].float())
+    accum[vis] += torch.norm(grad2D[vis, :2], dim=-1, keepdim=True)
+    a = torch.norm(torch.abs(grad2D[vis, :1]) + torch.abs(grad2D[vis, 1:2]), dim=-1, keepdim=True)
+    accum_abs[vis] += a
+    accum_abs_max[vis] = torch.max(accum_abs_max[vis], a)
+    denom[vis] += 1
+    return accum, accum_abs, accum_abs_max, denom, max_radii2D
+
+
+# ------------------------------------------------------------------------------------------------
+# Image loss of the first stage (SURVEY §8f-3): utils/loss_utils.py:19-20 (l1_loss), :40-100 (ssim) restated with
+# an explicit dense 11x11 window (no conv2d) so that the restatement shares nothing with the framework op; PINNED
+# against the reference's own loss_utils.ssim / l1_loss imported from /root/reference (tests/golden/loss_ref.npz, made
+# by tests/make_golden_loss.py), values and autograd gradients.
+# ------------------------------------------------------------------------------------------------
+def ssim_window(window_size: int = 11, sigma: float = 1.5):
+    g = torch.Tensor([math.exp(-((x - window_size // 2) ** 2) / float(2 * sigma ** 2)) for x in range(window_size)])
+    g = (g / g.sum()).unsqueeze(1)
+    return g.mm(g.t()).float()          # loss_utils.py:47-51
+
+
+def _window_filter(x, win):
+    """Zero-padded correlation of every channel of x [C,H,W] with win [k,k] (F.conv2d(..., padding=k//2, groups=C))."""
+    k = win.shape[0]
+    r = k // 2
+    Cn, H, W = x.shape
+    xp = torch.zeros(Cn, H + 2 * r, W + 2 * r, dtype=x.dtype)
+    xp[:, r:r + H, r:r + W] = x
+    out = torch.zeros_like(x)
+    for i in range(k):
+        for j in range(k):
+            out = out + win[i, j] * xp[:, i:i + H, j:j + W]
+    return out
+
+
+def ssim_map(img1, img2):
+    win = ssim_window().to(img1.dtype)
+    mu1, mu2 = _window_filter(img1, win), _window_filter(img2, win)
+    mu1_sq, mu2_sq, mu1_mu2 = mu1 * mu1, mu2 * mu2, mu1 * mu2
+    s11 = _window_filter(img1 * img1, win) - mu1_sq
+    s22 = _window_filter(img2 * img2, win) - mu2_sq
+    s12 = _window_filter(img1 * img2, win) - mu1_mu2
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    return ((2 * mu1_mu2 + C1) * (2 * s12 + C2)) / ((mu1_sq + mu2_sq + C1) * (s11 + s22 + C2))
+
+
+def ssim(img1, img2):
+    return ssim_map(img1, img2).mean()
+
+
+def l1_ssim_loss(image, gt, lambda_dssim: float = 0.2):
+    """train.py:320-322."""
+    return (1.0 - lambda_dssim) * torch.abs(image - gt).mean() + lambda_dssim * (1.0 - ssim(image, gt))
