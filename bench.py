@@ -32,13 +32,13 @@ STAGE_NAMES = ["preprocess", "emit_keys", "radix_sort", "tile_ranges", "blend_fo
                "gaussian_backward", "geometry_chain", "ssao", "ssr", "shade_forward", "shade_backward", "median3x3",
                "median3x3_backward", "bilateral3x3", "depth_to_normal", "ssr_backward", "dist2", "deferred_shade",
                "deferred_loss", "deferred_backward", "param_grad", "radix_sort_pass", "depth_sort", "light_build",
-               "light_backward", "adam", "image_loss"]
+               "light_backward", "adam", "image_loss", "normal_loss"]
 # kernels launched per stage record (radix_sort: histogram + scan + passes, filled in at run time)
 STAGE_LAUNCHES = {"preprocess": 2, "emit_keys": 1, "tile_ranges": 1, "blend_forward": 1, "blend_backward": 1,
                   "gaussian_backward": 1, "geometry_chain": 1, "ssao": 1, "ssr": 1, "shade_forward": 1,
                   "shade_backward": 1, "median3x3": 1, "median3x3_backward": 1, "bilateral3x3": 1,
                   "depth_to_normal": 1, "ssr_backward": 1, "dist2": 9, "deferred_shade": 1, "deferred_loss": 1,
-                  "deferred_backward": 4, "param_grad": 1, "radix_sort_pass": 0, "light_build": 2, "light_backward": 6, "adam": 1, "image_loss": 3}
+                  "deferred_backward": 4, "param_grad": 1, "radix_sort_pass": 0, "light_build": 2, "light_backward": 6, "adam": 1, "image_loss": 3, "normal_loss": 3}
 
 
 def parse():

@@ -211,6 +211,138 @@ __global__ void __launch_bounds__(SS_T* SS_T) ssim_backward_kernel(int C, int W,
     grad[o] = accumulate ? grad[o] + g : g;
 }
 
+// ---- geometry terms of the first-stage loss (train.py:323-328) ------------------------------------------------------
+//   normal_loss = F.l1_loss(normal_map[:, mask], normal_map_from_depth[:, mask])       (mask = normal_from_depth_mask)
+//   normal_tv   = get_tv_loss(gt_image, normal_map, pad=1, step=1)                      (train.py:83-100: edge-aware TV)
+// One pixel per thread; partial[cta] = (sum |n - nd| over masked pixels, masked pixel count, sum w_h*dh^2, sum w_w*dw^2).
+__device__ __forceinline__ float tv_edge_weight(const float* __restrict__ gt, size_t N, size_t a, size_t b)
+{
+    const float m = (fabsf(gt[b] - gt[a]) + fabsf(gt[N + b] - gt[N + a]) + fabsf(gt[2 * N + b] - gt[2 * N + a])) / 3.f;
+    return expf(-m);
+}
+
+__global__ void __launch_bounds__(256) normal_loss_forward_kernel(int W, int H, const float* __restrict__ nm,
+                                                                  const float* __restrict__ nd,
+                                                                  const uint8_t* __restrict__ mask,
+                                                                  const float* __restrict__ gt, float4* __restrict__ partial)
+{
+    __shared__ float red[4][8];
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const size_t N = (size_t)W * H;
+    float l1 = 0.f, cnt = 0.f, th = 0.f, tw = 0.f;
+    if (x < W && y < H) {
+        const size_t o = (size_t)y * W + x;
+        const float n0 = nm[o], n1 = nm[N + o], n2 = nm[2 * N + o];
+        if (!mask || mask[o]) {
+            l1 = fabsf(n0 - nd[o]) + fabsf(n1 - nd[N + o]) + fabsf(n2 - nd[2 * N + o]);
+            cnt = 1.f;
+        }
+        if (y + 1 < H) {
+            const size_t b = o + W;
+            const float d0 = nm[b] - n0, d1 = nm[N + b] - n1, d2 = nm[2 * N + b] - n2;
+            th = (d0 * d0 + d1 * d1 + d2 * d2) * tv_edge_weight(gt, N, o, b);
+        }
+        if (x + 1 < W) {
+            const size_t b = o + 1;
+            const float d0 = nm[b] - n0, d1 = nm[N + b] - n1, d2 = nm[2 * N + b] - n2;
+            tw = (d0 * d0 + d1 * d1 + d2 * d2) * tv_edge_weight(gt, N, o, b);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        th += __shfl_xor_sync(0xffffffffu, th, o);
+        tw += __shfl_xor_sync(0xffffffffu, tw, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = l1; red[1][threadIdx.x >> 5] = cnt;
+        red[2][threadIdx.x >> 5] = th; red[3][threadIdx.x >> 5] = tw;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 8; i++) { a.x += red[0][i]; a.y += red[1][i]; a.z += red[2][i]; a.w += red[3][i]; }
+        partial[blockIdx.y * gridDim.x + blockIdx.x] = a;
+    }
+}
+
+// scal[0] = normal_weight * loss_scale / (3 * count)  (NaN when the mask is empty: F.l1_loss of an empty selection)
+__global__ void __launch_bounds__(1024) normal_loss_finish_kernel(int n, const float4* __restrict__ partial, int W, int H,
+                                                                  float normal_weight, float tv_weight, float loss_scale,
+                                                                  float* __restrict__ out, int accumulate,
+                                                                  float* __restrict__ scal)
+{
+    __shared__ double r[4][32];
+    double a = 0, b = 0, c = 0, d = 0;
+    for (int i = threadIdx.x; i < n; i += 1024) {
+        const float4 p = partial[i];
+        a += (double)p.x; b += (double)p.y; c += (double)p.z; d += (double)p.w;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+        d += __shfl_xor_sync(0xffffffffu, d, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        r[0][threadIdx.x >> 5] = a; r[1][threadIdx.x >> 5] = b; r[2][threadIdx.x >> 5] = c; r[3][threadIdx.x >> 5] = d;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a = b = c = d = 0;
+        for (int i = 0; i < 32; i++) { a += r[0][i]; b += r[1][i]; c += r[2][i]; d += r[3][i]; }
+        const float l1 = (float)(a / (3.0 * b));       // 0/0 = NaN like the reference's mean over nothing
+        const double nh = 3.0 * (double)(H - 1) * W, nw = 3.0 * (double)H * (W - 1);
+        const float tv = (float)(c / nh) + (float)(d / nw);   // mean over an empty tensor (H or W == 1) is NaN too
+        if (out) {
+            const float loss = loss_scale * (normal_weight * l1 + tv_weight * tv);
+            out[0] = accumulate ? out[0] + loss : loss;
+            out[1] = l1;
+            out[2] = tv;
+        }
+        scal[0] = (float)((double)normal_weight * (double)loss_scale / (3.0 * b));
+    }
+}
+
+__global__ void __launch_bounds__(256) normal_loss_backward_kernel(int W, int H, const float* __restrict__ nm,
+                                                                   const float* __restrict__ nd,
+                                                                   const uint8_t* __restrict__ mask,
+                                                                   const float* __restrict__ gt,
+                                                                   const float* __restrict__ scal, float kh, float kw,
+                                                                   const float* __restrict__ upstream,
+                                                                   float* __restrict__ grad, int accumulate)
+{
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= W || y >= H) return;
+    const size_t N = (size_t)W * H, o = (size_t)y * W + x;
+    const float k1 = scal[0];
+    const bool m = !mask || mask[o];
+    // the four edges of this pixel: weight * (2/count) folded into kh / kw
+    const float wu = y > 0 ? kh * tv_edge_weight(gt, N, o - W, o) : 0.f;
+    const float wd = y + 1 < H ? kh * tv_edge_weight(gt, N, o, o + W) : 0.f;
+    const float wl = x > 0 ? kw * tv_edge_weight(gt, N, o - 1, o) : 0.f;
+    const float wr = x + 1 < W ? kw * tv_edge_weight(gt, N, o, o + 1) : 0.f;
+    const float up = upstream ? upstream[0] : 1.f;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const size_t q = c * N + o;
+        const float v = nm[q];
+        float g = 0.f;
+        if (m) {
+            const float df = v - nd[q];
+            g = df > 0.f ? k1 : (df < 0.f ? -k1 : 0.f);
+        }
+        if (y > 0) g += wu * (v - nm[q - W]);
+        if (y + 1 < H) g -= wd * (nm[q + W] - v);
+        if (x > 0) g += wl * (v - nm[q - 1]);
+        if (x + 1 < W) g -= wr * (nm[q + 1] - v);
+        g *= up;
+        grad[q] = accumulate ? grad[q] + g : g;
+    }
+}
+
 }  // namespace gigs
 
 using namespace gigs;
@@ -264,6 +396,39 @@ int gigs_image_loss(int32_t C, int32_t W, int32_t H, const float* image, const f
         ssim_backward_kernel<<<grid, dim3(SS_T, SS_T), 0, st>>>(C, W, H, image, gt, dmu, dxx, dxy, k_ssim, k_l1, upstream,
                                                                 grad_image, accumulate_grad);
         GIGS_LAUNCH_CHECK("ssim_backward_kernel");
+    }
+    return 0;
+}
+
+int gigs_normal_loss(int32_t W, int32_t H, const float* normal_map, const float* normal_from_depth, const uint8_t* mask,
+                     const float* gt_image, float normal_weight, float tv_weight, float loss_scale, void* scratch,
+                     uint64_t* scratch_bytes, float* loss_out, int32_t accumulate_loss, float* grad_normal,
+                     int32_t accumulate_grad, const float* upstream, void* stream)
+{
+    if (W <= 0 || H <= 0 || !scratch_bytes) { set_error("gigs_normal_loss: bad arguments"); return -1; }
+    const dim3 grid((W + 31) / 32, (H + 7) / 8);
+    const uint64_t n_cta = (uint64_t)grid.x * grid.y;
+    const uint64_t need = align_up(n_cta * 16, 256) + 256;
+    if (!scratch) { *scratch_bytes = need; return 0; }
+    if (*scratch_bytes < need || !normal_map || !normal_from_depth || !gt_image || (!loss_out && !grad_normal)) {
+        set_error("gigs_normal_loss: scratch too small or NULL input");
+        return -1;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    float4* partial = (float4*)scratch;
+    float* scal = (float*)((char*)scratch + align_up(n_cta * 16, 256));
+    ProfScope prof(28, st);
+    normal_loss_forward_kernel<<<grid, 256, 0, st>>>(W, H, normal_map, normal_from_depth, mask, gt_image, partial);
+    GIGS_LAUNCH_CHECK("normal_loss_forward_kernel");
+    normal_loss_finish_kernel<<<1, 1024, 0, st>>>((int)n_cta, partial, W, H, normal_weight, tv_weight, loss_scale, loss_out,
+                                                  accumulate_loss, scal);
+    GIGS_LAUNCH_CHECK("normal_loss_finish_kernel");
+    if (grad_normal) {
+        const float kh = (float)(2.0 * (double)tv_weight * (double)loss_scale / (3.0 * (double)(H - 1) * (double)W));
+        const float kw = (float)(2.0 * (double)tv_weight * (double)loss_scale / (3.0 * (double)H * (double)(W - 1)));
+        normal_loss_backward_kernel<<<grid, 256, 0, st>>>(W, H, normal_map, normal_from_depth, mask, gt_image, scal, kh, kw,
+                                                          upstream, grad_normal, accumulate_grad);
+        GIGS_LAUNCH_CHECK("normal_loss_backward_kernel");
     }
     return 0;
 }

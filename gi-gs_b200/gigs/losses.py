@@ -81,3 +81,43 @@ def ssim(img1: torch.Tensor, img2: torch.Tensor, window_size: int = 11, size_ave
 def l1_loss(network_output: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:
     """utils/loss_utils.py:19-20."""
     return torch.abs(network_output - gt).mean()
+
+
+class _NormalLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, normal_map, normal_from_depth, mask, gt, normal_weight, tv_weight, loss_scale):
+        L = _lib.load()
+        _, H, W = normal_map.shape
+        need = C.c_uint64(0)
+        _lib.check(L.gigs_normal_loss(W, H, None, None, None, None, normal_weight, tv_weight, loss_scale, None,
+                                      C.byref(need), None, 0, None, 0, None, None), "gigs_normal_loss(size)")
+        scratch = _scratch_for(normal_map.device, need.value)
+        out = torch.empty(3, dtype=torch.float32, device=normal_map.device)
+        want_grad = normal_map.requires_grad
+        grad = torch.empty_like(normal_map) if want_grad else None
+        with torch.cuda.device(normal_map.device):
+            _lib.check(L.gigs_normal_loss(W, H, normal_map.data_ptr(), normal_from_depth.data_ptr(),
+                                          mask.data_ptr() if mask is not None else None, gt.data_ptr(), normal_weight,
+                                          tv_weight, loss_scale, scratch.data_ptr(), C.byref(need), out.data_ptr(), 0,
+                                          grad.data_ptr() if want_grad else None, 0, None,
+                                          torch.cuda.current_stream().cuda_stream), "gigs_normal_loss")
+        ctx.grad = grad
+        ctx.mark_non_differentiable(out)
+        return out[0], out
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_terms):
+        return (ctx.grad * g_loss if ctx.grad is not None else None), None, None, None, None, None, None
+
+
+def normal_loss(normal_map: torch.Tensor, normal_from_depth: torch.Tensor, mask, gt_image: torch.Tensor,
+                normal_weight: float = 1.0, tv_weight: float = 1.0, loss_scale: float = 1.0, return_terms: bool = False):
+    """train.py:323-328: normal_weight * F.l1_loss(normal_map[:, mask], normal_map_from_depth[:, mask]) + tv_weight *
+    get_tv_loss(gt_image, normal_map, pad=1, step=1); differentiable in normal_map. mask: bool/uint8 [H,W] or None."""
+    normal_map, normal_from_depth = _check(normal_map, normal_from_depth.detach())
+    gt_image = gt_image.detach().float().contiguous()
+    if mask is not None:
+        mask = mask.reshape(normal_map.shape[1:]).to(torch.uint8).contiguous()
+    loss, terms = _NormalLoss.apply(normal_map, normal_from_depth, mask, gt_image, float(normal_weight),
+                                    float(tv_weight), float(loss_scale))
+    return (loss, terms) if return_terms else loss

@@ -5,6 +5,7 @@ TV losses are outside it. The light can be given as ready-made 
 trainable base cubemap (`light_base=`), in which case every step rebuilds the mips from it like train.py:340 does
 (gigs.light.PrefilteredLight: CubemapLight.build_mips and its backward).
 """
+import math
 from typing import Dict, List, Optional
 
 import torch
@@ -228,6 +229,57 @@ def training_step(params: GaussianParams, cam, light, brdf_lut, rays, gt_image, 
     if pre is not None and finish_light:
         pre.backward(params.light_base.grad, accumulate=True)
     return loss.detach()
+
+
+def _framework_first_stage_loss(res: Dict, gt_image: torch.Tensor, lambda_dssim: float, normal_weight: float,
+                                normal_tv_weight: float) -> torch.Tensor:
+    """The first-stage loss in framework ops exactly as train.py:318-328 + utils/loss_utils.py:54-100 write it: the
+    parity check of the fused loss kernels (fused_losses=False), not a fallback."""
+    image, nm, nd = res["render"], res["normal_map"], res["normal_map_from_depth"]
+    ch = image.shape[0]
+    w1 = torch.tensor([math.exp(-((x - 5) ** 2) / float(2 * 1.5 ** 2)) for x in range(11)])
+    w1 = (w1 / w1.sum()).unsqueeze(1)
+    win = w1.mm(w1.t()).float()[None, None].expand(ch, 1, 11, 11).contiguous().to(image.device)
+    a, b = image[None], gt_image[None]
+    mu1, mu2 = F.conv2d(a, win, padding=5, groups=ch), F.conv2d(b, win, padding=5, groups=ch)
+    mu1_sq, mu2_sq, mu12 = mu1.pow(2), mu2.pow(2), mu1 * mu2
+    s11 = F.conv2d(a * a, win, padding=5, groups=ch) - mu1_sq
+    s22 = F.conv2d(b * b, win, padding=5, groups=ch) - mu2_sq
+    s12 = F.conv2d(a * b, win, padding=5, groups=ch) - mu12
+    ssim = (((2 * mu12 + 0.01 ** 2) * (2 * s12 + 0.03 ** 2)) / ((mu1_sq + mu2_sq + 0.01 ** 2) * (s11 + s22 + 0.03 ** 2))).mean()
+    loss = (1.0 - lambda_dssim) * torch.abs(image - gt_image).mean() + lambda_dssim * (1.0 - ssim)
+    mask = res["normal_from_depth_mask"]
+    loss = loss + normal_weight * F.l1_loss(nm[:, mask], nd[:, mask])
+    wh = torch.exp(-(gt_image[:, 1:, :] - gt_image[:, :-1, :]).abs().mean(dim=0, keepdim=True))
+    ww = torch.exp(-(gt_image[:, :, 1:] - gt_image[:, :, :-1]).abs().mean(dim=0, keepdim=True))
+    tv = ((nm[:, 1:, :] - nm[:, :-1, :]).pow(2) * wh).mean() + ((nm[:, :, 1:] - nm[:, :, :-1]).pow(2) * ww).mean()
+    return loss + normal_tv_weight * tv
+
+
+def first_stage_step(params: GaussianParams, cam, gt_image, background, gi: Dict, lambda_dssim: float = 0.2,
+                     normal_weight: float = 1.0, normal_tv_weight: float = 1.0, loss_scale: float = 1.0,
+                     fused_losses: bool = True, stats=None):
+    """One view of the FIRST training stage (iteration <= pbr_iteration, train.py:266-328): render() with
+    derive_normal, loss = (1 - lambda) L1 + lambda (1 - SSIM) + normal L1 inside the normal-from-depth mask + edge-aware
+    TV of the normal map, backward through the rasterizer's general backward (all 10 parameter groups receive
+    gradients). The image and normal losses run as the fused kernels of csrc/loss.cu (gigs.losses).
+    `stats` (gigs.densify.DensifyState) receives this view's densification statistics (train.py:489-495).
+    Returns (loss, render result)."""
+    from .renderer import render
+    from . import losses
+    params.mark_dirty(None)
+    g = params.activated()
+    res = render(cam, g, background, derive_normal=True, **gi)
+    if fused_losses:
+        loss = losses.l1_ssim_loss(res["render"], gt_image, lambda_dssim)
+        loss = loss + losses.normal_loss(res["normal_map"], res["normal_map_from_depth"], res["normal_from_depth_mask"],
+                                         gt_image, normal_weight, normal_tv_weight)
+    else:
+        loss = _framework_first_stage_loss(res, gt_image, lambda_dssim, normal_weight, normal_tv_weight)
+    (loss * loss_scale).backward()
+    if stats is not None:
+        stats.add_view(res["viewspace_points"].grad, res["radii"])
+    return loss.detach() * loss_scale, res
 
 
 def multi_view_step(params: GaussianParams, cams: List, light: Light, brdf_lut, rays_of, gts: List, background,

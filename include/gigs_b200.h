@@ -457,6 +457,18 @@ int gigs_image_loss(int32_t C, int32_t W, int32_t H, const float* image, const f
                     float loss_scale, void* scratch, uint64_t* scratch_bytes, float* loss_out, int32_t accumulate_loss,
                     float* grad_image, int32_t accumulate_grad, const float* upstream, void* stream);
 
+/* Geometry terms of the first-stage loss (/root/reference/train.py:323-328):
+ *   normal_weight * F.l1_loss(normal_map[:, mask], normal_map_from_depth[:, mask])
+ * + tv_weight     * get_tv_loss(gt_image, normal_map, pad=1, step=1)       (train.py:83-100, edge-aware total variation)
+ * and the gradient with respect to normal_map (normal_map_from_depth comes from depth_to_normal, which the reference
+ * runs outside autograd). All maps are [3,H,W]; mask is uint8 [H,W] (NULL = every pixel). An empty mask gives NaN,
+ * like the reference's mean over an empty selection. loss_out (float[3], may be NULL) = [loss_scale * total (added to
+ * the existing value when accumulate_loss), normal L1 term, TV term]; grad_normal (may be NULL) as in gigs_image_loss. */
+int gigs_normal_loss(int32_t W, int32_t H, const float* normal_map, const float* normal_from_depth, const uint8_t* mask,
+                     const float* gt_image, float normal_weight, float tv_weight, float loss_scale, void* scratch,
+                     uint64_t* scratch_bytes, float* loss_out, int32_t accumulate_loss, float* grad_normal,
+                     int32_t accumulate_grad, const float* upstream, void* stream);
+
 /* Replaces distCUDA2 / SimpleKNN::knn (/root/reference/submodules/simple-knn/spatial.cu,
  * simple_knn.cu:165-207): mean squared distance to the 3 nearest other points.
  * scratch_bytes: call with scratch==NULL to query. */
@@ -469,7 +481,7 @@ int gigs_dist2(int32_t P, const float* points, float* mean_dist2, void* scratch,
  * 13 median3x3_backward, 14 bilateral3x3, 15 depth_to_normal, 16 ssr_backward, 17 dist2, 18 deferred_shade,
  * 19 deferred_loss, 20 deferred_backward, 21 param_grad, 22 one radix-sort pass (nested inside 2 / 23),
  * 23 depth argsort of the Gaussians, 24 cubemap prefilter forward, 25 cubemap prefilter backward, 26 Adam step,
- * 27 image loss (L1 + SSIM forward, finish and backward).
+ * 27 image loss (L1 + SSIM forward, finish and backward), 28 normal loss (L1 + TV forward, finish, backward).
  * gigs_profile_read synchronises the recorded events, writes up to cap (stage, ms) pairs, clears the log and
  * returns the number written (negative on error). Off by default; costs two event records per stage when on. */
 int gigs_profile_enable(int32_t on);

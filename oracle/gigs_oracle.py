@@ -1387,3 +1387,18 @@ def ssim(img1, img2):
 def l1_ssim_loss(image, gt, lambda_dssim: float = 0.2):
     """train.py:320-322."""
     return (1.0 - lambda_dssim) * torch.abs(image - gt).mean() + lambda_dssim * (1.0 - ssim(image, gt))
+
+
+def tv_loss(gt_image, prediction):
+    """train.py:83-100 get_tv_loss with pad=1, step=1 (its only call pattern): edge-aware total variation."""
+    wh = torch.exp(-(gt_image[:, 1:, :] - gt_image[:, :-1, :]).abs().mean(dim=0, keepdim=True))
+    ww = torch.exp(-(gt_image[:, :, 1:] - gt_image[:, :, :-1]).abs().mean(dim=0, keepdim=True))
+    th = (prediction[:, 1:, :] - prediction[:, :-1, :]) ** 2
+    tw = (prediction[:, :, 1:] - prediction[:, :, :-1]) ** 2
+    return (th * wh).mean() + (tw * ww).mean()
+
+
+def normal_loss(normal_map, normal_from_depth, mask, gt_image, normal_weight=1.0, tv_weight=1.0):
+    """train.py:323-328: L1 between the rendered normals and the normals from depth inside the mask + normal TV."""
+    l1 = (normal_map[:, mask] - normal_from_depth[:, mask]).abs().mean()
+    return normal_weight * l1 + tv_weight * tv_loss(gt_image, normal_map)

@@ -121,3 +121,46 @@ def test_image_loss_properties_at_full_size():
     losses.l1_ssim_loss(x2, gt, 1.0).backward()
     lin = float((x2.grad * d).sum())
     assert (lp - lm) / (2 * h) == pytest.approx(lin, rel=2e-2)
+
+
+# ---- geometry terms of the first stage: normal L1 inside the mask + edge-aware TV of the normal map ----------------
+from make_golden_loss import NCASES, normal_inputs
+
+
+def test_oracle_normal_loss_matches_reference_functions():
+    z = np.load(GOLD)
+    for i, (H, W, seed, frac) in enumerate(NCASES):
+        nm, nd, mask, gt = normal_inputs(H, W, seed, frac)
+        x = nm.clone().requires_grad_(True)
+        loss = O.normal_loss(x, nd, mask, gt)
+        loss.backward()
+        assert float(loss) == pytest.approx(z[f"nloss{i}"][0], rel=2e-6)
+        assert _grad_close(x.grad, torch.from_numpy(z[f"ngrad{i}"]), 2e-6), i
+
+
+@pytest.mark.gpu
+def test_normal_loss_matches_reference_goldens_and_oracle():
+    from gigs import losses
+    z = np.load(GOLD)
+    for i, (H, W, seed, frac) in enumerate(NCASES):
+        nm, nd, mask, gt = normal_inputs(H, W, seed, frac)
+        x = nm.cuda().requires_grad_(True)
+        loss, terms = losses.normal_loss(x, nd.cuda(), mask.cuda(), gt.cuda(), return_terms=True)
+        (2.0 * loss).backward()
+        want = z[f"nloss{i}"]
+        assert float(loss) == pytest.approx(want[0], rel=5e-6), i
+        assert float(terms[1]) == pytest.approx(want[1], rel=5e-6) and float(terms[2]) == pytest.approx(want[2], rel=5e-6)
+        assert _grad_close(x.grad.cpu() / 2.0, torch.from_numpy(z[f"ngrad{i}"]), 5e-6), i
+    # other weights, no mask, full size: against the oracle
+    nm, nd, mask, gt = normal_inputs(800, 800, 12, 0.7)
+    x = nm.clone().requires_grad_(True)
+    want = O.normal_loss(x, nd, torch.ones_like(mask), gt, normal_weight=0.5, tv_weight=2.0)
+    want.backward()
+    xg = nm.cuda().requires_grad_(True)
+    got = losses.normal_loss(xg, nd.cuda(), None, gt.cuda(), normal_weight=0.5, tv_weight=2.0)
+    got.backward()
+    assert float(got) == pytest.approx(float(want), rel=5e-6)
+    assert _grad_close(xg.grad.cpu(), x.grad, 5e-6)
+    # an empty mask is a mean over nothing: NaN, as in the reference
+    e = losses.normal_loss(nm.cuda(), nd.cuda(), torch.zeros_like(mask).cuda(), gt.cuda())
+    assert torch.isnan(e)
