@@ -254,6 +254,7 @@ int gigs_sizeof(int32_t which)
         case 7: return (int)sizeof(GigsFrame);
         case 8: return (int)sizeof(GigsLightLayout);
         case 9: return (int)sizeof(GigsAdamGroup);
+        case 10: return (int)sizeof(GigsDensifyGroup);
         default: return -1;
     }
 }

@@ -158,6 +158,12 @@ class GigsAdamGroup(C.Structure):
                 ("pad_", C.c_int32)]
 
 
+class GigsDensifyGroup(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("src_exp_avg", C.c_void_p), ("src_exp_avg_sq", C.c_void_p),
+                ("dst", C.c_void_p), ("dst_exp_avg", C.c_void_p), ("dst_exp_avg_sq", C.c_void_p),
+                ("width", C.c_int32), ("role", C.c_int32)]
+
+
 GIGS_E_GROW = -5
 
 # every symbol include/gigs_b200.h declares: (name, restype, argtypes)
@@ -206,6 +212,7 @@ SYMBOLS = {
                                   _vp, _vp]),
     "gigs_normal_loss": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _f, _f, _f, _vp, C.POINTER(C.c_uint64), _vp, _i32, _vp,
                                    _i32, _vp, _vp]),
+    "gigs_densify_gather": (C.c_int, [_i32, _vp, _vp, _vp, _vp, _vp, _f, _i32, C.POINTER(GigsDensifyGroup), _vp]),
     "gigs_dist2": (C.c_int, [_i32, _vp, _vp, _vp, C.POINTER(C.c_uint64), _vp]),
     "gigs_ffma_peak": (C.c_int, [C.POINTER(C.c_double), _vp]),
     "gigs_profile_enable": (C.c_int, [_i32]),
@@ -232,7 +239,8 @@ def load():
     if lib.gigs_abi_version() != 3:
         raise ImportError("gigs_b200: ABI version mismatch between the python binding and libgigs_b200.so")
     for which, st in enumerate((GigsCamera, GigsSizes, GigsLayout, GigsRasterFwd, GigsRasterBwd, GigsShade,
-                                GigsFrameLayout, GigsFrame, GigsLightLayout, GigsAdamGroup)):
+                                GigsFrameLayout, GigsFrame, GigsLightLayout, GigsAdamGroup,
+                                GigsDensifyGroup)):
         if lib.gigs_sizeof(which) != C.sizeof(st):
             raise ImportError(f"gigs_b200: struct {st.__name__} is {C.sizeof(st)} bytes in the python binding but "
                               f"{lib.gigs_sizeof(which)} in libgigs_b200.so")

@@ -184,6 +184,26 @@ class GaussianOptimizer:
         self.BRDF_scheduler_args = get_expon_lr_func(opt.opacity_lr, opt.BRDF_lr,
                                                      lr_delay_mult=opt.position_lr_delay_mult, max_steps=10000)
 
+    def _name_of(self, key: str) -> str:
+        return REFERENCE_GROUP_NAME.get(key, key)
+
+    def rebind(self, new_state: Optional[Dict[str, Dict]] = None) -> None:
+        """After GaussianParams.rebuild: point the Gaussian groups at the new leaves; new_state maps a GaussianParams key
+        to {'exp_avg', 'exp_avg_sq'} of the new size (step counts are kept, as the reference keeps state['step'] through
+        cat_tensors_to_optimizer / _prune_optimizer). A group without an entry restarts from empty state."""
+        for g in self.adam.param_groups:
+            key = self._key_of[g["name"]]
+            if key not in self.params.leaves:
+                continue
+            g["params"] = [self.params.leaves[key]]
+            st = self.adam.state.get(g["name"])
+            ns = (new_state or {}).get(key)
+            if ns is None:
+                self.adam.state.pop(g["name"], None)
+            else:
+                self.adam.state[g["name"]] = dict(step=st["step"] if st is not None else 0, exp_avg=ns["exp_avg"],
+                                                  exp_avg_sq=ns["exp_avg_sq"])
+
     def update_learning_rate(self, iteration: int) -> Optional[float]:
         """scene/gaussian_model.py:386-395, including its control flow: groups are visited in order, `xyz` gets its
         scheduled rate, and the first BRDF group met (`albedo`) gets BRDF_scheduler(iteration - 30000) and RETURNS, so

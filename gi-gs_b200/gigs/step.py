@@ -58,6 +58,29 @@ class GaussianParams:
             from .light import PrefilteredLight
             self.prefiltered = PrefilteredLight(self.light_base, cutoff=cutoff)
 
+    def rebuild(self, new_leaves: Dict[str, torch.Tensor]) -> None:
+        """Swap in a new set of Gaussians (densification / pruning / checkpoint restore change P): new leaf tensors, a
+        new flat gradient buffer of the new size with the light's gradient carried over, all gradients zero."""
+        dev = self.flat_grad.device
+        P = new_leaves["xyz"].shape[0]
+        self.P = P
+        self.leaves = {k: new_leaves[k].detach().to(dev).float().contiguous().requires_grad_(True) for k in PARAM_KEYS}
+        extra = [(f"light{i}", t) for i, t in enumerate(self.light_leaves)]
+        if self.light_base is not None:
+            extra = [("light_base", self.light_base)]
+        old = {k: t.grad.clone() for k, t in extra if t.grad is not None}
+        n = sum(t.numel() for t in self.leaves.values()) + sum(t.numel() for _, t in extra)
+        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        o = 0
+        self._span = {}
+        for k, t in list(self.leaves.items()) + extra:
+            t.grad = self.flat_grad[o:o + t.numel()].view_as(t)
+            if k in old:
+                t.grad.copy_(old[k])
+            self._span[k] = (o, o + t.numel())
+            o += t.numel()
+        self._dirty = None
+
     def mark_dirty(self, keys=None):
         if keys is None:
             self._dirty = None

@@ -48,7 +48,7 @@ int gigs_abi_version(void);
 const char* gigs_last_error(void);
 /* sizeof() of the argument structs, so a foreign-language binding can verify its mirror of the layout:
  * which = 0 GigsCamera, 1 GigsSizes, 2 GigsLayout, 3 GigsRasterFwd, 4 GigsRasterBwd, 5 GigsShade,
- * 6 GigsFrameLayout, 7 GigsFrame, 8 GigsLightLayout, 9 GigsAdamGroup; negative for an unknown id. */
+ * 6 GigsFrameLayout, 7 GigsFrame, 8 GigsLightLayout, 9 GigsAdamGroup, 10 GigsDensifyGroup; negative for an unknown id. */
 int gigs_sizeof(int32_t which);
 int gigs_raster_sizes(int32_t P, int32_t W, int32_t H, uint64_t R, GigsSizes* out);
 
@@ -468,6 +468,26 @@ int gigs_normal_loss(int32_t W, int32_t H, const float* normal_map, const float*
                      const float* gt_image, float normal_weight, float tv_weight, float loss_scale, void* scratch,
                      uint64_t* scratch_bytes, float* loss_out, int32_t accumulate_loss, float* grad_normal,
                      int32_t accumulate_grad, const float* upstream, void* stream);
+
+/* ---- Densification / pruning rebuild ------------------------------------------------------------------
+ * Replaces the tensor surgery of GaussianModel.densify_and_prune (/root/reference/scene/gaussian_model.py:905-931 with
+ * densify_and_clone :785-817, densify_and_split :741-783, cat_tensors_to_optimizer :639-662, _prune_optimizer
+ * :594-612): given the source map of the surviving rows — src_index[n_out] (row of the old model), kind[n_out] (0 kept
+ * point, 1 clone, 2 split child) — it writes every parameter tensor and both Adam moment tensors of the new model in
+ * one launch. Kept rows copy parameter and moments; new rows copy the parameter and get zero moments; in the group
+ * with role 1 (xyz, width 3) a new row is R(rot) * (noise * exp(log_scale)) + xyz of its source; in the group with
+ * role 2 (log-scale, width 3) a split child gets log(exp(log_scale) / split_div), split_div = 0.8 * N.
+ * noise: [n_out,3] standard normals (rows of kept points unused). The group array is HOST memory (<= 16 groups);
+ * moment pointers may be NULL (no optimiser state yet). */
+typedef struct GigsDensifyGroup {
+    const float* src; const float* src_exp_avg; const float* src_exp_avg_sq;
+    float* dst; float* dst_exp_avg; float* dst_exp_avg_sq;
+    int32_t width;   /* floats per Gaussian */
+    int32_t role;    /* 0 copy, 1 xyz, 2 log-scale */
+} GigsDensifyGroup;
+int gigs_densify_gather(int32_t n_out, const int32_t* src_index, const int8_t* kind, const float* noise,
+                        const float* src_log_scale, const float* src_rot, float split_div, int32_t n_groups,
+                        const GigsDensifyGroup* groups, void* stream);
 
 /* Replaces distCUDA2 / SimpleKNN::knn (/root/reference/submodules/simple-knn/spatial.cu,
  * simple_knn.cu:165-207): mean squared distance to the 3 nearest other points.

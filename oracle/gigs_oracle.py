@@ -1402,3 +1402,86 @@ def normal_loss(normal_map, normal_from_depth, mask, gt_image, normal_weight=1.0
     """train.py:323-328: L1 between the rendered normals and the normals from depth inside the mask + normal TV."""
     l1 = (normal_map[:, mask] - normal_from_depth[:, mask]).abs().mean()
     return normal_weight * l1 + tv_weight * tv_loss(gt_image, normal_map)
+
+
+# ------------------------------------------------------------------------------------------------
+# Densification / pruning (SURVEY §8f-4): scene/gaussian_model.py:905-931 restated round by round (clone -> append,
+# split -> append -> drop parents, prune), on dicts of CPU tensors keyed like gigs.step.PARAM_KEYS, with the sampled
+# noise injected. PINNED against tests/golden/densify_ref.npz, produced by the reference's own methods compiled from
+# its source file (tests/make_golden_densify.py).
+# ------------------------------------------------------------------------------------------------
+DENSIFY_KEYS = ("xyz", "f_dc", "f_rest", "opacity", "normal", "albedo", "roughness", "metallic", "log_scale", "rot")
+
+
+def build_rotation(r):
+    """utils/general_utils.py:89-110."""
+    norm = torch.sqrt(r[:, 0] * r[:, 0] + r[:, 1] * r[:, 1] + r[:, 2] * r[:, 2] + r[:, 3] * r[:, 3])
+    q = r / norm[:, None]
+    R = torch.zeros((q.size(0), 3, 3))
+    r, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    R[:, 0, 0] = 1 - 2 * (y * y + z * z)
+    R[:, 0, 1] = 2 * (x * y - r * z)
+    R[:, 0, 2] = 2 * (x * z + r * y)
+    R[:, 1, 0] = 2 * (x * y + r * z)
+    R[:, 1, 1] = 1 - 2 * (x * x + z * z)
+    R[:, 1, 2] = 2 * (y * z - r * x)
+    R[:, 2, 0] = 2 * (x * z - r * y)
+    R[:, 2, 1] = 2 * (y * z + r * x)
+    R[:, 2, 2] = 1 - 2 * (x * x + y * y)
+    return R
+
+
+def densify_and_prune(p: Dict, m: Dict, v: Dict, accum, accum_abs, denom, max_grad, min_opacity, extent,
+                      max_screen_size, noise_clone, noise_split, percent_dense=0.01, N=2):
+    """p / m / v: parameters and Adam moments. Returns new (p, m, v)."""
+    p, m, v = ({k: t.clone() for k, t in d.items()} for d in (p, m, v))
+
+    def append(new):                       # densification_postfix + cat_tensors_to_optimizer
+        for k in DENSIFY_KEYS:
+            p[k] = torch.cat((p[k], new[k]), dim=0)
+            m[k] = torch.cat((m[k], torch.zeros_like(new[k])), dim=0)
+            v[k] = torch.cat((v[k], torch.zeros_like(new[k])), dim=0)
+
+    def prune(mask):                       # prune_points + _prune_optimizer
+        keep = ~mask
+        for k in DENSIFY_KEYS:
+            p[k], m[k], v[k] = p[k][keep], m[k][keep], v[k][keep]
+
+    grads = accum / denom
+    grads[grads.isnan()] = 0.0
+    grads_abs = accum_abs / denom
+    grads_abs[grads_abs.isnan()] = 0.0
+    ratio = (torch.norm(grads, dim=-1) >= max_grad).float().mean()
+    Q = torch.quantile(grads_abs.reshape(-1), 1 - ratio)
+    # clone (:785-817)
+    sel = torch.logical_or(torch.norm(grads, dim=-1) >= max_grad, torch.norm(grads_abs, dim=-1) >= Q)
+    sel = torch.logical_and(sel, torch.exp(p["log_scale"]).max(dim=1).values <= percent_dense * extent)
+    stds = torch.exp(p["log_scale"])[sel]
+    samples = noise_clone * stds
+    new = {k: p[k][sel] for k in DENSIFY_KEYS}
+    new["xyz"] = torch.bmm(build_rotation(p["rot"][sel]), samples.unsqueeze(-1)).squeeze(-1) + p["xyz"][sel]
+    append(new)
+    # split (:741-783)
+    n_init = p["xyz"].shape[0]
+    pg = torch.zeros(n_init)
+    pg[:grads.shape[0]] = grads.squeeze()
+    pga = torch.zeros(n_init)
+    pga[:grads_abs.shape[0]] = grads_abs.squeeze()
+    sel = torch.logical_or(pg >= max_grad, pga >= Q)
+    sel = torch.logical_and(sel, torch.exp(p["log_scale"]).max(dim=1).values > percent_dense * extent)
+    stds = torch.exp(p["log_scale"])[sel].repeat(N, 1)
+    samples = noise_split * stds
+    rots = build_rotation(p["rot"][sel]).repeat(N, 1, 1)
+    new = {k: p[k][sel].repeat(N, *([1] * (p[k].dim() - 1))) for k in DENSIFY_KEYS}
+    new["xyz"] = torch.bmm(rots, samples.unsqueeze(-1)).squeeze(-1) + p["xyz"][sel].repeat(N, 1)
+    new["log_scale"] = torch.log(torch.exp(p["log_scale"])[sel].repeat(N, 1) / (0.8 * N))
+    append(new)
+    prune(torch.cat((sel, torch.zeros(N * int(sel.sum()), dtype=torch.bool))))
+    # final prune (:920-927); max_radii2D was zeroed by densification_postfix (:706)
+    mask = (torch.sigmoid(p["opacity"]) < min_opacity).squeeze()
+    if max_screen_size:
+        big_vs = torch.zeros(p["xyz"].shape[0]) > max_screen_size
+        big_ws = torch.exp(p["log_scale"]).max(dim=1).values > 0.1 * extent
+        mask = torch.logical_or(torch.logical_or(mask, big_vs), big_ws)
+    prune(mask)
+    return p, m, v
