@@ -32,7 +32,7 @@ STAGE_NAMES = ["preprocess", "emit_keys", "radix_sort", "tile_ranges", "blend_fo
                "gaussian_backward", "geometry_chain", "ssao", "ssr", "shade_forward", "shade_backward", "median3x3",
                "median3x3_backward", "bilateral3x3", "depth_to_normal", "ssr_backward", "dist2", "deferred_shade",
                "deferred_loss", "deferred_backward", "param_grad", "radix_sort_pass", "depth_sort", "light_build",
-               "light_backward", "adam", "image_loss", "normal_loss"]
+               "light_backward", "adam", "image_loss", "normal_loss", "stage1_normals", "stage1_normals_backward"]
 # kernels launched per stage record (radix_sort: histogram + scan + passes, filled in at run time)
 STAGE_LAUNCHES = {"preprocess": 2, "emit_keys": 1, "tile_ranges": 1, "blend_forward": 1, "blend_backward": 1,
                   "gaussian_backward": 1, "geometry_chain": 1, "ssao": 1, "ssr": 1, "shade_forward": 1,

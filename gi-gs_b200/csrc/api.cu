@@ -255,6 +255,8 @@ int gigs_sizeof(int32_t which)
         case 8: return (int)sizeof(GigsLightLayout);
         case 9: return (int)sizeof(GigsAdamGroup);
         case 10: return (int)sizeof(GigsDensifyGroup);
+        case 11: return (int)sizeof(GigsStage1Layout);
+        case 12: return (int)sizeof(GigsStage1);
         default: return -1;
     }
 }

@@ -84,6 +84,17 @@ uint32_t higher_msb(uint32_t n);
 int radix_digit_bits(int bits);
 int radix_sort_passes(int bits);
 
+// gaussian_backward_kernel<RAW> (gauss_bwd.cu): raw leaves in, gradients accumulated into the leaves' gradient tensors
+struct RawGrads {
+    const float* f_rest; const float* opacity; const float* normal; const float* albedo; const float* roughness;
+    const float* metallic;
+    float* g_xyz; float* g_f_dc; float* g_f_rest; float* g_opacity; float* g_normal; float* g_albedo; float* g_roughness;
+    float* g_metallic; float* g_log_scale; float* g_rot;
+};
+int launch_gaussian_backward_raw(int P, const GigsCamera& c, const void* geom, const Layout& L, const int32_t* radii,
+                                 const float* accum, const float* xyz, const float* f_dc, const float* log_scale,
+                                 const float* rot, float* g_means2D, const RawGrads& raw, cudaStream_t st);
+
 // ---------------------------------------------------------------------------------------------
 // Minimal column-major 3x3 matrix with the SAME expression shapes as the math library the
 // reference uses for mat3*mat3 / transpose, so that nvcc contracts FMAs identically and tile keys

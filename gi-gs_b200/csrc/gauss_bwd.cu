@@ -29,6 +29,29 @@ __device__ __forceinline__ float dotB(const B3& a, const B3& b) { return a.x * b
 
 constexpr int GB_THREADS = 128;
 
+// RAW variant (first-stage frame, csrc/stage1.cu): the parameter pointers are the trainer's pre-activation leaves
+// (means3D = xyz, shs = f_dc [P,1,3] + raw.f_rest [P,M-1,3], scales = log-scales, rotations = un-normalised quaternions)
+// — the same convention as preprocess_kernel<RAW> — and every result is chained through the getter
+// (scene/gaussian_model.py:178-266: exp, sigmoid, F.normalize) and ACCUMULATED (+=) into the leaves' gradient tensors,
+// which removes the activated copies, the 14 intermediate gradient tensors and the ~20 autograd launches of the getters.
+
+__device__ __forceinline__ float gb_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+// backward of F.normalize(v, eps=1e-12): y = v / max(|v|, eps)
+__device__ __forceinline__ void gb_normalize_bwd(const float* v, const float* g, int n, float* out)
+{
+    float nn = 0.f;
+    for (int i = 0; i < n; ++i) nn += v[i] * v[i];
+    nn = sqrtf(nn);
+    if (nn > 1e-12f) {
+        float d = 0.f;
+        for (int i = 0; i < n; ++i) d += (v[i] / nn) * g[i];
+        for (int i = 0; i < n; ++i) out[i] = (g[i] - (v[i] / nn) * d) / nn;
+    } else {
+        for (int i = 0; i < n; ++i) out[i] = g[i] / 1e-12f;
+    }
+}
+
+template <bool RAW>
 __global__ void __launch_bounds__(GB_THREADS)
 gaussian_backward_kernel(const int P, const int D, const int M, const float* __restrict__ means3D,
                          const int* __restrict__ radii, const float* __restrict__ shs,
@@ -44,7 +67,7 @@ gaussian_backward_kernel(const int P, const int D, const int M, const float* __r
                          float* __restrict__ dL_dnormal, float* __restrict__ dL_dalbedo,
                          float* __restrict__ dL_droughness, float* __restrict__ dL_dmetallic,
                          float* __restrict__ dL_dmean3D, float* __restrict__ dL_dcov3D, float* __restrict__ dL_dsh,
-                         float* __restrict__ dL_dscale, float* __restrict__ dL_drot)
+                         float* __restrict__ dL_dscale, float* __restrict__ dL_drot, const RawGrads raw)
 {
     const int idx = blockIdx.x * GB_THREADS + threadIdx.x;
     if (idx >= P) return;
@@ -64,9 +87,39 @@ gaussian_backward_kernel(const int P, const int D, const int M, const float* __r
     }
 
     // direct per-Gaussian outputs of the blend backward
-    dL_dmean2D[3 * idx + 0] = acc[A_M2X];
-    dL_dmean2D[3 * idx + 1] = acc[A_M2Y];
-    dL_dmean2D[3 * idx + 2] = acc[A_M2Z];
+    if (!RAW || dL_dmean2D) {
+        dL_dmean2D[3 * idx + 0] = acc[A_M2X];
+        dL_dmean2D[3 * idx + 1] = acc[A_M2Y];
+        dL_dmean2D[3 * idx + 2] = acc[A_M2Z];
+    }
+    if (RAW) {
+        if (!visible) return;
+        const float op = gb_sigmoid(raw.opacity[idx]);
+        raw.g_opacity[idx] += acc[A_OPAC] * ((1.0f - op) * op);
+        if (acc[A_ROUGH] != 0.f) {
+            const float y = gb_sigmoid(raw.roughness[idx]);
+            raw.g_roughness[idx] += acc[A_ROUGH] * ((1.0f - y) * y);
+        }
+        if (acc[A_METAL] != 0.f) {
+            const float y = gb_sigmoid(raw.metallic[idx]);
+            raw.g_metallic[idx] += acc[A_METAL] * ((1.0f - y) * y);
+        }
+        if (acc[A_ALB] != 0.f || acc[A_ALB + 1] != 0.f || acc[A_ALB + 2] != 0.f) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float y = gb_sigmoid(raw.albedo[3 * idx + c]);
+                raw.g_albedo[3 * idx + c] += acc[A_ALB + c] * ((1.0f - y) * y);
+            }
+        }
+        if (acc[A_NRM] != 0.f || acc[A_NRM + 1] != 0.f || acc[A_NRM + 2] != 0.f) {
+            const float v[3] = {raw.normal[3 * idx], raw.normal[3 * idx + 1], raw.normal[3 * idx + 2]};
+            const float g[3] = {acc[A_NRM], acc[A_NRM + 1], acc[A_NRM + 2]};
+            float o[3];
+            gb_normalize_bwd(v, g, 3, o);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) raw.g_normal[3 * idx + c] += o[c];
+        }
+    } else {
     if (dL_dconic_out) {
         *reinterpret_cast<float4*>(dL_dconic_out + 4 * (size_t)idx) = make_float4(acc[A_CX], acc[A_CY], 0.f, acc[A_CW]);
     }
@@ -78,6 +131,7 @@ gaussian_backward_kernel(const int P, const int D, const int M, const float* __r
         dL_dcolor[3 * idx + c] = acc[A_COL + c];
         dL_dnormal[3 * idx + c] = acc[A_NRM + c];
         dL_dalbedo[3 * idx + c] = acc[A_ALB + c];
+    }
     }
 
     if (!visible) {
@@ -145,8 +199,10 @@ gaussian_backward_kernel(const int P, const int D, const int M, const float* __r
 #pragma unroll
         for (int i = 0; i < 6; i++) dcov[i] = 0;
     }
+    if (!RAW) {
 #pragma unroll
-    for (int i = 0; i < 6; i++) dL_dcov3D[6 * (size_t)idx + i] = dcov[i];
+        for (int i = 0; i < 6; i++) dL_dcov3D[6 * (size_t)idx + i] = dcov[i];
+    }
 
     const float dL_dT00 = 2 * (T.m[0][0] * Vrk.m[0][0] + T.m[0][1] * Vrk.m[0][1] + T.m[0][2] * Vrk.m[0][2]) * dL_da +
                           (T.m[1][0] * Vrk.m[0][0] + T.m[1][1] * Vrk.m[0][1] + T.m[1][2] * Vrk.m[0][2]) * dL_db;
@@ -206,13 +262,21 @@ gaussian_backward_kernel(const int P, const int D, const int M, const float* __r
         const B3 dir_orig = {pos.x - cam.x, pos.y - cam.y, pos.z - cam.z};
         const float len = sqrtf(dotB(dir_orig, dir_orig));
         const B3 dir = {dir_orig.x / len, dir_orig.y / len, dir_orig.z / len};
-        const float* shp = shs + (size_t)idx * M * 3;
+        // RAW: coefficient 0 lives in f_dc, coefficient i >= 1 at f_rest + (idx*(M-1) + i-1)*3
+        const float* shp = RAW ? raw.f_rest + ((size_t)idx * (M - 1) - 1) * 3 : shs + (size_t)idx * M * 3;
         auto SH = [&](int i) -> B3 { return {shp[3 * i + 0], shp[3 * i + 1], shp[3 * i + 2]}; };
-        float* dshp = dL_dsh + (size_t)idx * M * 3;
+        float* dshp = RAW ? raw.g_f_rest + ((size_t)idx * (M - 1) - 1) * 3 : dL_dsh + (size_t)idx * M * 3;
         auto DSH = [&](int i, const B3& v) {
-            dshp[3 * i + 0] = v.x;
-            dshp[3 * i + 1] = v.y;
-            dshp[3 * i + 2] = v.z;
+            if (RAW) {
+                float* d = (i == 0) ? raw.g_f_dc + (size_t)idx * 3 : dshp + 3 * i;
+                d[0] += v.x;
+                d[1] += v.y;
+                d[2] += v.z;
+            } else {
+                dshp[3 * i + 0] = v.x;
+                dshp[3 * i + 1] = v.y;
+                dshp[3 * i + 2] = v.z;
+            }
         };
         const uchar4 cl = *reinterpret_cast<const uchar4*>(clamped + 4 * (size_t)idx);
         B3 dL_dRGB = {acc[A_COL + 0], acc[A_COL + 1], acc[A_COL + 2]};
@@ -270,7 +334,8 @@ gaussian_backward_kernel(const int P, const int D, const int M, const float* __r
             }
         }
         // coefficients above the active degree get no gradient (zeros in the reference's pre-filled tensor)
-        for (int i = written; i < M; ++i) DSH(i, B3{0.f, 0.f, 0.f});
+        if (!RAW)
+            for (int i = written; i < M; ++i) DSH(i, B3{0.f, 0.f, 0.f});
 
         const B3 dL_ddir = {dotB(dRGBdx, dL_dRGB), dotB(dRGBdy, dL_dRGB), dotB(dRGBdz, dL_dRGB)};
         // dnormvdv (auxiliary.h:120-131)
@@ -283,20 +348,32 @@ gaussian_backward_kernel(const int P, const int D, const int M, const float* __r
         dn.z = (-v.x * v.z * dv.x - v.y * v.z * dv.y + (sum2 - v.z * v.z) * dv.z) * invsum32;
         dmean += dn;
     }
-    dL_dmean3D[3 * idx + 0] = dmean.x;
-    dL_dmean3D[3 * idx + 1] = dmean.y;
-    dL_dmean3D[3 * idx + 2] = dmean.z;
+    if (RAW) {
+        raw.g_xyz[3 * idx + 0] += dmean.x;
+        raw.g_xyz[3 * idx + 1] += dmean.y;
+        raw.g_xyz[3 * idx + 2] += dmean.z;
+    } else {
+        dL_dmean3D[3 * idx + 0] = dmean.x;
+        dL_dmean3D[3 * idx + 1] = dmean.y;
+        dL_dmean3D[3 * idx + 2] = dmean.z;
+    }
 
     // ------------------------------------------------------------------ cov3D -> scale, quaternion
     if (scales) {
-        const float4 q = *reinterpret_cast<const float4*>(rotations + 4 * (size_t)idx);
+        float4 q = *reinterpret_cast<const float4*>(rotations + 4 * (size_t)idx);
+        const float4 q_raw = q;
+        float3 sc = {scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]};
+        if (RAW) {   // the getters, as preprocess_kernel<RAW> applies them
+            sc = make_float3(expf(sc.x), expf(sc.y), expf(sc.z));
+            const float qn = fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);
+            q = make_float4(q.x / qn, q.y / qn, q.z / qn, q.w / qn);
+        }
         const float r = q.x, x = q.y, y = q.z, z = q.w;
         Mat3 R = mat3_cols(1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y),
                            2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x),
                            2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y));
         Mat3 S = mat3_cols(1.0f, 0.0f, 0.0f, 0.0f, 1.0f, 0.0f, 0.0f, 0.0f, 1.0f);
-        const float3 s = {scale_modifier * scales[3 * idx], scale_modifier * scales[3 * idx + 1],
-                          scale_modifier * scales[3 * idx + 2]};
+        const float3 s = {scale_modifier * sc.x, scale_modifier * sc.y, scale_modifier * sc.z};
         S.m[0][0] = s.x;
         S.m[1][1] = s.y;
         S.m[2][2] = s.z;
@@ -313,9 +390,18 @@ gaussian_backward_kernel(const int P, const int D, const int M, const float* __r
         Mat3 Rt = mat3_transpose(R);
         Mat3 dL_dMt = mat3_transpose(dL_dM);
 
-        dL_dscale[3 * idx + 0] = Rt.m[0][0] * dL_dMt.m[0][0] + Rt.m[0][1] * dL_dMt.m[0][1] + Rt.m[0][2] * dL_dMt.m[0][2];
-        dL_dscale[3 * idx + 1] = Rt.m[1][0] * dL_dMt.m[1][0] + Rt.m[1][1] * dL_dMt.m[1][1] + Rt.m[1][2] * dL_dMt.m[1][2];
-        dL_dscale[3 * idx + 2] = Rt.m[2][0] * dL_dMt.m[2][0] + Rt.m[2][1] * dL_dMt.m[2][1] + Rt.m[2][2] * dL_dMt.m[2][2];
+        const float ds0 = Rt.m[0][0] * dL_dMt.m[0][0] + Rt.m[0][1] * dL_dMt.m[0][1] + Rt.m[0][2] * dL_dMt.m[0][2];
+        const float ds1 = Rt.m[1][0] * dL_dMt.m[1][0] + Rt.m[1][1] * dL_dMt.m[1][1] + Rt.m[1][2] * dL_dMt.m[1][2];
+        const float ds2 = Rt.m[2][0] * dL_dMt.m[2][0] + Rt.m[2][1] * dL_dMt.m[2][1] + Rt.m[2][2] * dL_dMt.m[2][2];
+        if (RAW) {   // exp backward: grad * exp(x)
+            raw.g_log_scale[3 * idx + 0] += ds0 * sc.x;
+            raw.g_log_scale[3 * idx + 1] += ds1 * sc.y;
+            raw.g_log_scale[3 * idx + 2] += ds2 * sc.z;
+        } else {
+            dL_dscale[3 * idx + 0] = ds0;
+            dL_dscale[3 * idx + 1] = ds1;
+            dL_dscale[3 * idx + 2] = ds2;
+        }
 
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -333,7 +419,16 @@ gaussian_backward_kernel(const int P, const int D, const int M, const float* __r
         dq.w = 2 * r * (dL_dMt.m[0][1] - dL_dMt.m[1][0]) + 2 * x * (dL_dMt.m[2][0] + dL_dMt.m[0][2]) +
                2 * y * (dL_dMt.m[1][2] + dL_dMt.m[2][1]) - 4 * z * (dL_dMt.m[1][1] + dL_dMt.m[0][0]);
         // no quaternion-normalisation Jacobian, as in the reference (backward.cu:345)
-        *reinterpret_cast<float4*>(dL_drot + 4 * (size_t)idx) = dq;
+        if (RAW) {
+            const float v[4] = {q_raw.x, q_raw.y, q_raw.z, q_raw.w};
+            const float g[4] = {dq.x, dq.y, dq.z, dq.w};
+            float o[4];
+            gb_normalize_bwd(v, g, 4, o);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) raw.g_rot[4 * (size_t)idx + k] += o[k];
+        } else {
+            *reinterpret_cast<float4*>(dL_drot + 4 * (size_t)idx) = dq;
+        }
     }
 }
 
@@ -344,12 +439,29 @@ int launch_gaussian_backward(const GigsRasterBwd* a, const Layout& L, cudaStream
     const float focal_y = c.height / (2.0f * c.tan_fovy);
     const float focal_x = c.width / (2.0f * c.tan_fovx);
     const float* cov3D_ptr = a->cov3D_precomp ? a->cov3D_precomp : (const float*)(g + L.off.g_cov3D);
-    gaussian_backward_kernel<<<(a->P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, st>>>(
+    gaussian_backward_kernel<false><<<(a->P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, st>>>(
         a->P, c.sh_degree, c.sh_coeffs, a->means3D, a->radii, a->shs, (const uint8_t*)(g + L.off.g_clamped), a->scales,
         a->rotations, c.scale_modifier, cov3D_ptr, c.viewmatrix, c.projmatrix, c.campos, focal_x, focal_y, c.tan_fovx,
         c.tan_fovy, a->accum, a->dL_dmean2D, a->dL_dconic, a->dL_dopacity, a->dL_dcolor, a->dL_dnormal, a->dL_dalbedo,
-        a->dL_droughness, a->dL_dmetallic, a->dL_dmean3D, a->dL_dcov3D, a->dL_dsh, a->dL_dscale, a->dL_drot);
+        a->dL_droughness, a->dL_dmetallic, a->dL_dmean3D, a->dL_dcov3D, a->dL_dsh, a->dL_dscale, a->dL_drot, RawGrads{});
     GIGS_LAUNCH_CHECK("gaussian_backward_kernel");
+    return 0;
+}
+
+// First-stage frame: raw leaves in, gradients accumulated into the leaves' gradient tensors (see RawGrads).
+int launch_gaussian_backward_raw(int P, const GigsCamera& c, const void* geom, const Layout& L, const int32_t* radii,
+                                 const float* accum, const float* xyz, const float* f_dc, const float* log_scale,
+                                 const float* rot, float* g_means2D, const RawGrads& raw, cudaStream_t st)
+{
+    const char* g = (const char*)geom;
+    const float focal_y = c.height / (2.0f * c.tan_fovy);
+    const float focal_x = c.width / (2.0f * c.tan_fovx);
+    gaussian_backward_kernel<true><<<(P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, st>>>(
+        P, c.sh_degree, c.sh_coeffs, xyz, radii, f_dc, (const uint8_t*)(g + L.off.g_clamped), log_scale, rot,
+        c.scale_modifier, (const float*)(g + L.off.g_cov3D), c.viewmatrix, c.projmatrix, c.campos, focal_x, focal_y,
+        c.tan_fovx, c.tan_fovy, accum, g_means2D, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+        nullptr, nullptr, nullptr, nullptr, raw);
+    GIGS_LAUNCH_CHECK("gaussian_backward_kernel<RAW>");
     return 0;
 }
 

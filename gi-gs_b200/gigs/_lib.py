@@ -164,6 +164,30 @@ class GigsDensifyGroup(C.Structure):
                 ("width", C.c_int32), ("role", C.c_int32)]
 
 
+class GigsStage1Layout(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in (
+        "color", "opacity", "depth", "normal", "normal_view", "pos", "albedo", "roughness", "metallic",
+        "normal_from_depth", "depth_pos", "normals_view", "nfd_unit", "g_color", "g_normals_view", "g_normal",
+        "median_sel", "mask", "loss_scratch", "loss_scratch_bytes", "nloss_scratch", "nloss_scratch_bytes", "stats",
+        "total_bytes")]
+
+
+class GigsStage1(C.Structure):
+    _fields_ = ([("P", C.c_int32), ("pad0_", C.c_int32), ("cam", GigsCamera)]
+                + [(n, C.c_void_p) for n in ("xyz", "f_dc", "f_rest", "opacity", "normal", "albedo", "roughness",
+                                             "metallic", "log_scale", "rot", "gt_image")]
+                + [(n, C.c_float) for n in ("lambda_dssim", "normal_weight", "normal_tv_weight", "loss_scale")]
+                + [("geom", C.c_void_p), ("geom_bytes", C.c_uint64), ("img", C.c_void_p), ("img_bytes", C.c_uint64),
+                   ("binning", C.c_void_p), ("binning_bytes", C.c_uint64), ("sort", C.c_void_p), ("sort_bytes", C.c_uint64),
+                   ("maps", C.c_void_p), ("maps_bytes", C.c_uint64),
+                   ("radii", C.c_void_p), ("accum", C.c_void_p), ("pinned_num_rendered", C.c_void_p),
+                   ("num_rendered", C.c_int64), ("resume", C.c_int32), ("pad1_", C.c_int32),
+                   ("need_binning_bytes", C.c_uint64), ("need_sort_bytes", C.c_uint64)]
+                + [(n, C.c_void_p) for n in ("g_xyz", "g_f_dc", "g_f_rest", "g_opacity", "g_normal", "g_albedo",
+                                             "g_roughness", "g_metallic", "g_log_scale", "g_rot", "g_means2D",
+                                             "gt_ready_event", "stream")])
+
+
 GIGS_E_GROW = -5
 
 # every symbol include/gigs_b200.h declares: (name, restype, argtypes)
@@ -206,6 +230,9 @@ SYMBOLS = {
     "gigs_light_build": (C.c_int, [C.POINTER(GigsLightLayout), _vp, _vp, _vp, _vp]),
     "gigs_light_backward": (C.c_int, [C.POINTER(GigsLightLayout), _vp, _vp, _vp, _i32, _i32, _vp]),
     "gigs_env_tv": (C.c_int, [_i32, _vp, _vp, _i32, _i32, _f, _vp, C.POINTER(C.c_uint64), _vp, _vp, _i32, _vp]),
+    "gigs_stage1_layout": (C.c_int, [_i32, _i32, C.POINTER(GigsStage1Layout)]),
+    "gigs_stage1_forward": (C.c_int, [C.POINTER(GigsStage1)]),
+    "gigs_stage1_backward": (C.c_int, [C.POINTER(GigsStage1)]),
     "gigs_adam_step": (C.c_int, [_i32, C.POINTER(GigsAdamGroup), _vp]),
     "gigs_densify_stats": (C.c_int, [_i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gigs_image_loss": (C.c_int, [_i32, _i32, _i32, _vp, _vp, _f, _f, _vp, C.POINTER(C.c_uint64), _vp, _i32, _vp, _i32,
@@ -240,7 +267,7 @@ def load():
         raise ImportError("gigs_b200: ABI version mismatch between the python binding and libgigs_b200.so")
     for which, st in enumerate((GigsCamera, GigsSizes, GigsLayout, GigsRasterFwd, GigsRasterBwd, GigsShade,
                                 GigsFrameLayout, GigsFrame, GigsLightLayout, GigsAdamGroup,
-                                GigsDensifyGroup)):
+                                GigsDensifyGroup, GigsStage1Layout, GigsStage1)):
         if lib.gigs_sizeof(which) != C.sizeof(st):
             raise ImportError(f"gigs_b200: struct {st.__name__} is {C.sizeof(st)} bytes in the python binding but "
                               f"{lib.gigs_sizeof(which)} in libgigs_b200.so")

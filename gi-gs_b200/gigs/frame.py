@@ -271,3 +271,102 @@ def pbr_frame_step(params, cam, light, brdf_lut, rays, gt_image, background, gi:
                        [_grad_of(t) for t in light.specular], light_ready=light_ready)
     params.last_workspace = ws
     return loss.clone()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The fused FIRST-STAGE frame (gigs_stage1_forward / gigs_stage1_backward, csrc/stage1.cu)
+# ------------------------------------------------------------------------------------------------------------------
+_S1_PLANES = dict(color=3, opacity=1, depth=1, normal=3, normal_view=3, pos=3, albedo=3, roughness=1, metallic=1,
+                  normal_from_depth=3, depth_pos=3, normals_view=3, nfd_unit=3, g_color=3, g_normals_view=3, g_normal=3)
+
+
+class Stage1Maps:
+    """The maps blob of the first-stage frame for one (W, H), carved by gigs_stage1_layout."""
+
+    def __init__(self, W: int, H: int, device):
+        self.W, self.H = W, H
+        self.layout = _lib.GigsStage1Layout()
+        check(_L.gigs_stage1_layout(W, H, C.byref(self.layout)), "gigs_stage1_layout")
+        self.blob = torch.empty(self.layout.total_bytes, dtype=torch.uint8, device=device)
+
+    def map(self, name: str) -> torch.Tensor:
+        off = getattr(self.layout, name)
+        N = self.W * self.H
+        if name in _S1_PLANES:
+            c = _S1_PLANES[name]
+            return self.blob[off:off + 4 * c * N].view(torch.float32).view(c, self.H, self.W)
+        if name == "mask":
+            return self.blob[off:off + N].view(self.H, self.W)
+        if name == "median_sel":
+            return self.blob[off:off + 3 * N].view(3, self.H, self.W)
+        if name == "stats":
+            return self.blob[off:off + 32].view(torch.float32)
+        raise KeyError(name)
+
+
+def stage1_frame_step(params, cam, gt_image, background, lambda_dssim: float = 0.2, normal_weight: float = 1.0,
+                      normal_tv_weight: float = 1.0, loss_scale: float = 1.0, backward: bool = True,
+                      gt_ready: Optional[torch.cuda.Event] = None, want_means2D: bool = True):
+    """forward (+ backward) of one FIRST-stage view for a gigs.step.GaussianParams: gradients of all ten parameter
+    groups accumulate into params.flat_grad exactly as autograd would through the operator path. Returns
+    (loss, means2D_grad [P,3] or None, radii [P] int32)."""
+    L = params.leaves
+    dev = L["xyz"].device
+    W, H = int(cam.image_width), int(cam.image_height)
+    ws = workspace(params.P, W, H, dev)
+    if getattr(ws, "s1", None) is None:
+        ws.s1 = Stage1Maps(W, H, dev)
+        ws.s1_means2D = torch.zeros((params.P, 3), dtype=torch.float32, device=dev)
+    keep = []
+
+    def c32(t):
+        t = t.detach()
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            t = t.float().contiguous()
+        keep.append(t)
+        return t
+
+    f = _lib.GigsStage1()
+    f.P = params.P
+    vm, pm, cp, bgc = c32(cam.world_view_transform), c32(cam.full_proj_transform), c32(cam.camera_center), c32(background)
+    M = 1 + L["f_rest"].shape[1]
+    f.cam = GigsCamera(W, H, float(cam.tanfovx), float(cam.tanfovy), 1.0, int(params.sh_degree), int(M), 0, 0, 0, 0,
+                       _p(vm), _p(pm), _p(cp), _p(bgc))
+    for k in ("xyz", "f_dc", "f_rest", "opacity", "normal", "albedo", "roughness", "metallic", "log_scale", "rot"):
+        if not _is_f32c(L[k]):
+            raise RuntimeError("first-stage frame: parameters must be contiguous float32 CUDA tensors")
+        setattr(f, k, L[k].data_ptr())
+    f.gt_image = _p(c32(gt_image)) if gt_image is not None else None
+    f.lambda_dssim, f.normal_weight = float(lambda_dssim), float(normal_weight)
+    f.normal_tv_weight, f.loss_scale = float(normal_tv_weight), float(loss_scale)
+    f.geom = ws.geom.data_ptr(); f.geom_bytes = ws.geom.numel()
+    f.img = ws.img.data_ptr(); f.img_bytes = ws.img.numel()
+    f.maps = ws.s1.blob.data_ptr(); f.maps_bytes = ws.s1.blob.numel()
+    f.radii = ws.radii.data_ptr(); f.accum = ws.accum.data_ptr()
+    f.pinned_num_rendered = ws.pinned.data_ptr()
+    if gt_ready is not None:
+        keep.append(gt_ready)
+        f.gt_ready_event = gt_ready.cuda_event
+    f.stream = torch.cuda.current_stream().cuda_stream
+    with torch.cuda.device(dev):
+        f.binning = _p(ws.binning); f.binning_bytes = 0 if ws.binning is None else ws.binning.numel()
+        f.sort = _p(ws.sort); f.sort_bytes = 0 if ws.sort is None else ws.sort.numel()
+        f.resume = 0
+        st = _L.gigs_stage1_forward(C.byref(f))
+        if st == GIGS_E_GROW:
+            ws.grow(f.need_binning_bytes, f.need_sort_bytes)
+            f.binning = _p(ws.binning); f.binning_bytes = ws.binning.numel()
+            f.sort = _p(ws.sort); f.sort_bytes = ws.sort.numel()
+            f.resume = 1
+            st = _L.gigs_stage1_forward(C.byref(f))
+        check(st, "gigs_stage1_forward")
+        ws.num_rendered = int(f.num_rendered)
+        stats = ws.s1.map("stats")
+        loss = (stats[0] + stats[4]) if gt_image is not None else None
+        if backward and gt_image is not None:
+            for k in ("xyz", "f_dc", "f_rest", "opacity", "normal", "albedo", "roughness", "metallic", "log_scale", "rot"):
+                setattr(f, "g_" + k, _grad_of(L[k]).data_ptr())
+            f.g_means2D = ws.s1_means2D.data_ptr() if want_means2D else None
+            check(_L.gigs_stage1_backward(C.byref(f)), "gigs_stage1_backward")
+    params.last_workspace = ws
+    return loss, (ws.s1_means2D if (backward and want_means2D) else None), ws.radii

@@ -281,16 +281,26 @@ def _framework_first_stage_loss(res: Dict, gt_image: torch.Tensor, lambda_dssim:
 
 def first_stage_step(params: GaussianParams, cam, gt_image, background, gi: Dict, lambda_dssim: float = 0.2,
                      normal_weight: float = 1.0, normal_tv_weight: float = 1.0, loss_scale: float = 1.0,
-                     fused_losses: bool = True, stats=None):
+                     fused_losses: bool = True, stats=None, fused: bool = False, gt_ready=None):
     """One view of the FIRST training stage (iteration <= pbr_iteration, train.py:266-328): render() with
     derive_normal, loss = (1 - lambda) L1 + lambda (1 - SSIM) + normal L1 inside the normal-from-depth mask + edge-aware
     TV of the normal map, backward through the rasterizer's general backward (all 10 parameter groups receive
     gradients). The image and normal losses run as the fused kernels of csrc/loss.cu (gigs.losses).
     `stats` (gigs.densify.DensifyState) receives this view's densification statistics (train.py:489-495).
+    fused=True runs the whole view as two C-ABI calls (gigs.frame.stage1_frame_step, csrc/stage1.cu: getters inside
+    preprocess, post-processing / loss / backward kernels, gradients written straight into the leaves' gradient
+    tensors); the result dict then holds only "radii" and "viewspace_grad".
     Returns (loss, render result)."""
     from .renderer import render
     from . import losses
     params.mark_dirty(None)
+    if fused:
+        from .frame import stage1_frame_step
+        loss, g2d, radii = stage1_frame_step(params, cam, gt_image, background, lambda_dssim, normal_weight,
+                                             normal_tv_weight, loss_scale, gt_ready=gt_ready)
+        if stats is not None:
+            stats.add_view(g2d, radii)
+        return loss.clone(), {"radii": radii, "viewspace_grad": g2d}
     g = params.activated()
     res = render(cam, g, background, derive_normal=True, **gi)
     if fused_losses:

@@ -35,7 +35,8 @@ class TrainConfig:
 
 class Trainer:
     def __init__(self, params: GaussianParams, brdf_lut: torch.Tensor, cameras_extent: float, cfg: Optional[TrainConfig] = None,
-                 spatial_lr_scale: float = 1.0, rays_of: Optional[Callable] = None):
+                 spatial_lr_scale: float = 1.0, rays_of: Optional[Callable] = None, fused: bool = True):
+        self.fused = fused          # False: operator path + autograd for both stages (the parity reference)
         self.params, self.lut, self.extent = params, brdf_lut, float(cameras_extent)
         self.cfg = cfg or TrainConfig()
         self.optimizer = GaussianOptimizer(params, self.cfg.opt, spatial_lr_scale)
@@ -52,14 +53,14 @@ class Trainer:
         first = it <= cfg.pbr_iteration
         if first:
             loss, _ = first_stage_step(p, cam, gt_image, self.bg, cfg.gi, lambda_dssim=opt.lambda_dssim,
-                                       normal_tv_weight=cfg.normal_tv_weight,
+                                       normal_tv_weight=cfg.normal_tv_weight, fused=self.fused,
                                        stats=self.stats if it < opt.densify_until_iter else None)
         else:
             if rays is None:
                 rays = self.rays_of(cam)
             loss = training_step(p, cam, p.light(), self.lut, rays, gt_image, torch.zeros_like(self.bg), cfg.gi,
                                  metallic=cfg.metallic, gamma=cfg.gamma, tone=cfg.tone, indirect=cfg.indirect,
-                                 brdf_tv_weight=cfg.brdf_tv_weight,
+                                 fused=self.fused, brdf_tv_weight=cfg.brdf_tv_weight,
                                  env_tv_weight=cfg.env_tv_weight if p.prefiltered is not None else 0.0)
         event = None
         with torch.no_grad():

@@ -48,7 +48,8 @@ int gigs_abi_version(void);
 const char* gigs_last_error(void);
 /* sizeof() of the argument structs, so a foreign-language binding can verify its mirror of the layout:
  * which = 0 GigsCamera, 1 GigsSizes, 2 GigsLayout, 3 GigsRasterFwd, 4 GigsRasterBwd, 5 GigsShade,
- * 6 GigsFrameLayout, 7 GigsFrame, 8 GigsLightLayout, 9 GigsAdamGroup, 10 GigsDensifyGroup; negative for an unknown id. */
+ * 6 GigsFrameLayout, 7 GigsFrame, 8 GigsLightLayout, 9 GigsAdamGroup, 10 GigsDensifyGroup,
+ * 11 GigsStage1Layout, 12 GigsStage1; negative for an unknown id. */
 int gigs_sizeof(int32_t which);
 int gigs_raster_sizes(int32_t P, int32_t W, int32_t H, uint64_t R, GigsSizes* out);
 
@@ -411,6 +412,48 @@ int gigs_env_tv(int32_t base_res, const float* base, const float* dirs, int32_t 
                 void* scratch, uint64_t* scratch_bytes, float* grad_base, float* loss_out, int32_t accumulate_loss,
                 void* stream);
 
+/* ---- The fused FIRST-STAGE frame ------------------------------------------------------------------------------------
+ * One view of /root/reference/train.py:266-328 (iteration <= pbr_iteration) as two calls: GaussianModel getters +
+ * gaussian_renderer.render(derive_normal=True) + loss = (1 - lambda_dssim) * L1 + lambda_dssim * (1 - SSIM)
+ * + normal_weight * F.l1_loss(normal_map[:, mask], normal_map_from_depth[:, mask]) + normal_tv_weight * get_tv_loss(gt,
+ * normal_map), then the whole backward into the gradient tensors of the ten raw parameter tensors (accumulated, +=,
+ * like autograd). Parameters are the trainer's PRE-activation leaves (scene/gaussian_model.py:55-66: _xyz,
+ * _features_dc [P,1,3], _features_rest [P,M-1,3], _opacity, _normal, _albedo, _roughness, _metallic, _scaling,
+ * _rotation). Workspaces as in GigsFrame; maps is sized by gigs_stage1_layout. stats (float[8] at layout.stats):
+ * [0] loss_scale * image loss, [1] L1, [2] SSIM, [4] loss_scale * normal loss, [5] normal L1, [6] normal TV; the
+ * step's loss is stats[0] + stats[4]. g_means2D ([P,3], written, may be NULL) is the screen-space gradient the
+ * densification statistics read (viewspace_point_tensor.grad). Returns GIGS_E_GROW (-5) like gigs_frame_forward. */
+typedef struct GigsStage1Layout {
+    uint64_t color, opacity, depth, normal, normal_view, pos, albedo, roughness, metallic;  /* rasterizer outputs */
+    uint64_t normal_from_depth, depth_pos;                  /* geometry chain */
+    uint64_t normals_view, nfd_unit;                        /* render()'s "normal_map" and "normal_map_from_depth" */
+    uint64_t g_color, g_normals_view, g_normal;             /* gradients of the image, normals_view, rasterizer normal */
+    uint64_t median_sel, mask;                              /* uint8 [3,H,W] / [H,W] */
+    uint64_t loss_scratch, loss_scratch_bytes, nloss_scratch, nloss_scratch_bytes, stats, total_bytes;
+} GigsStage1Layout;
+typedef struct GigsStage1 {
+    int32_t P; int32_t pad0_;
+    GigsCamera cam;
+    const float* xyz; const float* f_dc; const float* f_rest; const float* opacity; const float* normal;
+    const float* albedo; const float* roughness; const float* metallic; const float* log_scale; const float* rot;
+    const float* gt_image;           /* [3,H,W]; NULL = forward only, no loss */
+    float lambda_dssim, normal_weight, normal_tv_weight, loss_scale;
+    void* geom; uint64_t geom_bytes; void* img; uint64_t img_bytes;
+    void* binning; uint64_t binning_bytes; void* sort; uint64_t sort_bytes;
+    void* maps; uint64_t maps_bytes;
+    int32_t* radii; float* accum; void* pinned_num_rendered;
+    int64_t num_rendered; int32_t resume; int32_t pad1_;
+    uint64_t need_binning_bytes, need_sort_bytes;
+    float* g_xyz; float* g_f_dc; float* g_f_rest; float* g_opacity; float* g_normal; float* g_albedo;
+    float* g_roughness; float* g_metallic; float* g_log_scale; float* g_rot;
+    float* g_means2D;
+    void* gt_ready_event;
+    void* stream;
+} GigsStage1;
+int gigs_stage1_layout(int32_t W, int32_t H, GigsStage1Layout* out);
+int gigs_stage1_forward(GigsStage1* f);
+int gigs_stage1_backward(GigsStage1* f);
+
 /* ---- The optimiser step -------------------------------------------------------------------------
  * Replaces `gaussians.optimizer.step(); gaussians.optimizer.zero_grad(); light_optimizer.step();
  * light_optimizer.zero_grad(); cubemap.clamp_(min=0.0)` of /root/reference/train.py:516-523 — torch.optim.Adam over
@@ -501,7 +544,8 @@ int gigs_dist2(int32_t P, const float* points, float* mean_dist2, void* scratch,
  * 13 median3x3_backward, 14 bilateral3x3, 15 depth_to_normal, 16 ssr_backward, 17 dist2, 18 deferred_shade,
  * 19 deferred_loss, 20 deferred_backward, 21 param_grad, 22 one radix-sort pass (nested inside 2 / 23),
  * 23 depth argsort of the Gaussians, 24 cubemap prefilter forward, 25 cubemap prefilter backward, 26 Adam step,
- * 27 image loss (L1 + SSIM forward, finish and backward), 28 normal loss (L1 + TV forward, finish, backward).
+ * 27 image loss (L1 + SSIM forward, finish and backward), 28 normal loss (L1 + TV forward, finish, backward),
+ * 29 first-stage normal post-processing, 30 its backward.
  * gigs_profile_read synchronises the recorded events, writes up to cap (stage, ms) pairs, clears the log and
  * returns the number written (negative on error). Off by default; costs two event records per stage when on. */
 int gigs_profile_enable(int32_t on);

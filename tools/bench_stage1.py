@@ -29,15 +29,18 @@ def main():
     bg = torch.zeros(3, device=dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
     out = {"P": P, "W": W, "H": H}
-    for name, fused, with_opt in (("fused_losses", True, False), ("framework_losses", False, False),
-                                  ("fused_losses_and_optimizer", True, True)):
+    for name, fused, with_opt, frame in (("operators_fused_losses", True, False, False),
+                                         ("operators_framework_losses", False, False, False),
+                                         ("operators_fused_losses_and_optimizer", True, True, False),
+                                         ("fused_frame", True, False, True),
+                                         ("fused_frame_and_optimizer", True, True, True)):
         params = gstep.GaussianParams(raw, dev)
         opt = gopt.GaussianOptimizer(params) if with_opt else None
 
         def one(i):
             if opt is None:
                 params.zero_grad()
-            gstep.first_stage_step(params, cams[i % 8], gts[i % 8], bg, GI, fused_losses=fused)
+            gstep.first_stage_step(params, cams[i % 8], gts[i % 8], bg, GI, fused_losses=fused, fused=frame)
             if opt is not None:
                 opt.step(light=False)
         for i in range(3):
@@ -51,7 +54,7 @@ def main():
             ts.append(e0.elapsed_time(e1))
         ts.sort()
         out[name] = {"ms": ts[len(ts) // 2], "iterations/s": 1e3 / ts[len(ts) // 2]}
-        if name == "fused_losses_and_optimizer":
+        if with_opt:
             L.gigs_profile_enable(1)
             n = 4
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
@@ -67,9 +70,9 @@ def main():
             for j in range(cnt):
                 agg[STAGE_NAMES[st[j]]] = agg.get(STAGE_NAMES[st[j]], 0.0) + ms[j] / n
             agg.pop("radix_sort_pass", None)
-            out["our_kernels_ms"] = agg
-            out["our_kernels_total_ms"] = sum(agg.values())
-            out["wall_ms_warm_l2"] = e0.elapsed_time(e1) / n
+            out[name]["our_kernels_ms"] = agg
+            out[name]["our_kernels_total_ms"] = sum(agg.values())
+            out[name]["ms_warm_l2"] = e0.elapsed_time(e1) / n
     print(json.dumps(out))
 
 
