@@ -510,6 +510,270 @@ blend_backward_material_kernel(const int W, const int H, const uint2* __restrict
     if (q > 0) flush(q);
 }
 
+// ---------------------------------------------------------------------------------------------
+// General backward, hybrid reduction (default for MODE_FULL work). The 19 per-Gaussian sums split into
+//   * 12 SEPARABLE ones — colour3, depth, normal3, roughness, albedo3, metallic: sum_p w(p,g) * dL/dpixel_p[ch] with
+//     w = alpha*T — which are a small dense contraction: the pair's weight goes into the per-warp 32 x 16 queue of
+//     the material kernel above and is contracted against the per-pixel upstream gradients staged once in shared
+//     memory (accumulator slots 0..11 are laid out in exactly this order);
+//   * 7 NON-separable ones — mean2D.xy, |mean2D|, opacity, conic3 (slots 12..18), products of per-pair quantities —
+//     which keep the transposing butterfly, now over 8 values (9 shuffles) instead of 16 + 4 (22 shuffles).
+// The per-lane arithmetic (back-to-front recurrence, dL/dalpha) is the general kernel's, expression for expression.
+// GROUPS = how many float4 groups of upstream maps are present: 2 = {colour, depth} + {normal, roughness} (first
+// training stage: no material gradients), 3 = all.
+// ---------------------------------------------------------------------------------------------
+struct HybSmem {
+    float rec[2][BB_BATCH][12];
+    uint32_t ids[2][BB_BATCH];
+    float4 g4[3][BB_THREADS];              // per pixel: {col.xyz, depth}, {nrm.xyz, rough}, {alb.xyz, metal}
+    float w[BB_THREADS / 32][32][MQ + 1];
+    uint32_t qid[BB_THREADS / 32][MQ];
+    uint64_t bar[2];
+    int red[BB_THREADS / 32];
+};
+
+template <int GROUPS>
+__global__ void __launch_bounds__(BB_THREADS)
+blend_backward_hybrid_kernel(const int W, const int H, const uint2* __restrict__ ranges,
+                             const uint32_t* __restrict__ point_list, const float* __restrict__ records,
+                             const float* __restrict__ bg_color, const float* __restrict__ final_Ts,
+                             const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpix_depth,
+                             const float* __restrict__ dL_dpix, const float* __restrict__ dL_dpix_opacity,
+                             const float* __restrict__ dL_dpix_normal, const float* __restrict__ dL_dpix_albedo,
+                             const float* __restrict__ dL_dpix_roughness, const float* __restrict__ dL_dpix_metallic,
+                             float* __restrict__ accum)
+{
+    constexpr uint32_t RECB = 12 * 4;
+    extern __shared__ __align__(128) unsigned char bb_smem_raw[];
+    HybSmem& S = *reinterpret_cast<HybSmem*>(bb_smem_raw);
+
+    const int tid = threadIdx.y * TILE_X + threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const uint32_t horizontal_blocks = (W + TILE_X - 1) / TILE_X;
+    const uint2 pix = {blockIdx.x * TILE_X + threadIdx.x, blockIdx.y * TILE_Y + threadIdx.y};
+    const uint32_t pix_id = W * pix.y + pix.x;
+    const float2 pixf = {(float)pix.x, (float)pix.y};
+    const bool inside = pix.x < (uint32_t)W && pix.y < (uint32_t)H;
+    const int HW = H * W;
+
+    const uint2 range = ranges[blockIdx.y * horizontal_blocks + blockIdx.x];
+    const int last_contributor = inside ? (int)n_contrib[pix_id] : 0;
+
+    float g_col[3] = {0.f, 0.f, 0.f};
+    float g_op = 0.f;
+    {
+        float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), gb = ga, gc = ga;
+        if (inside) {
+            if (dL_dpix) { ga.x = dL_dpix[pix_id]; ga.y = dL_dpix[HW + pix_id]; ga.z = dL_dpix[2 * HW + pix_id]; }
+            ga.w = dL_dpix_depth ? dL_dpix_depth[pix_id] : 0.f;
+            // the reference zeroes the normal gradient of image-border pixels (backward.cu:497-501)
+            const bool border = pix.x == 0 || pix.x == (uint32_t)(W - 1) || pix.y == 0 || pix.y == (uint32_t)(H - 1);
+            if (dL_dpix_normal && !border) {
+                gb.x = dL_dpix_normal[pix_id]; gb.y = dL_dpix_normal[HW + pix_id]; gb.z = dL_dpix_normal[2 * HW + pix_id];
+            }
+            gb.w = dL_dpix_roughness ? dL_dpix_roughness[pix_id] : 0.f;
+            if (GROUPS > 2) {
+                if (dL_dpix_albedo) {
+                    gc.x = dL_dpix_albedo[pix_id]; gc.y = dL_dpix_albedo[HW + pix_id]; gc.z = dL_dpix_albedo[2 * HW + pix_id];
+                }
+                gc.w = dL_dpix_metallic ? dL_dpix_metallic[pix_id] : 0.f;
+            }
+            g_op = dL_dpix_opacity ? dL_dpix_opacity[pix_id] : 0.f;
+        }
+        g_col[0] = ga.x; g_col[1] = ga.y; g_col[2] = ga.z;
+        S.g4[0][tid] = ga;
+        S.g4[1][tid] = gb;
+        if (GROUPS > 2) S.g4[2][tid] = gc;
+    }
+
+    // the forward never went past max(n_contrib) in this tile: walk only that prefix, back to front
+    int wmax = last_contributor;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    if (lane == 0) S.red[warp] = wmax;
+    if (tid == 0) {
+        mbar_init(&S.bar[0], 1);
+        mbar_init(&S.bar[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    int n = 0;
+#pragma unroll
+    for (int w = 0; w < BB_THREADS / 32; ++w) n = max(n, S.red[w]);
+    n = min(n, (int)(range.y - range.x));
+    const int rounds = (n + BB_BATCH - 1) / BB_BATCH;
+
+    const float strip_x0 = (float)(blockIdx.x * TILE_X);
+    const float strip_y0 = (float)(blockIdx.y * TILE_Y + (threadIdx.y & ~1));
+
+    auto issue = [&](int b) {
+        const int s = b & 1;
+        const int cnt = min(BB_BATCH, n - b * BB_BATCH);
+        if (tid == 0) mbar_arrive_expect_tx(&S.bar[s], (uint32_t)cnt * RECB);
+        if (tid < cnt) {
+            const uint32_t id = point_list[range.x + (n - 1 - (b * BB_BATCH + tid))];
+            S.ids[s][tid] = id;
+            bulk_g2s(&S.rec[s][tid][0], records + (size_t)id * REC_FLOATS, RECB, &S.bar[s]);
+        }
+    };
+
+    // drain the warp's queue: q Gaussians (q <= MQ) x 32 pixels -> 4*GROUPS sums per Gaussian (accumulator slots 0..)
+    auto flush = [&](int q) {
+        __syncwarp();
+        const int slot = lane & (MQ - 1), half = lane >> 4;
+        float4 a[GROUPS];
+#pragma unroll
+        for (int g = 0; g < GROUPS; ++g) a[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int p = half * 16 + k;
+            const float wv = S.w[warp][p][slot];
+#pragma unroll
+            for (int g = 0; g < GROUPS; ++g) {
+                const float4 u = S.g4[g][warp * 32 + p];
+                a[g].x = fmaf(wv, u.x, a[g].x);
+                a[g].y = fmaf(wv, u.y, a[g].y);
+                a[g].z = fmaf(wv, u.z, a[g].z);
+                a[g].w = fmaf(wv, u.w, a[g].w);
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < GROUPS; ++g) {
+            a[g].x += __shfl_xor_sync(0xffffffffu, a[g].x, 16);
+            a[g].y += __shfl_xor_sync(0xffffffffu, a[g].y, 16);
+            a[g].z += __shfl_xor_sync(0xffffffffu, a[g].z, 16);
+            a[g].w += __shfl_xor_sync(0xffffffffu, a[g].w, 16);
+        }
+        if (slot < q) {
+            // the two half-warps hold the same totals: half 0 issues group 0 (and 2), half 1 group 1
+            float* row = accum + (size_t)S.qid[warp][slot] * ACC_FLOATS;
+#pragma unroll
+            for (int g = 0; g < GROUPS; ++g) {
+                if ((g & 1) == half) red_add_v4(row + 4 * g, a[g].x, a[g].y, a[g].z, a[g].w);
+            }
+        }
+        __syncwarp();
+    };
+
+    const float T_final = inside ? final_Ts[pix_id] : 0.f;
+    float T = T_final;
+    float last_alpha = 0.f, accum_opacity = 0.f;
+    float accum_rec[3] = {0.f, 0.f, 0.f}, last_color[3] = {0.f, 0.f, 0.f};
+    const float ddelx_dx = 0.5 * W;
+    const float ddely_dy = 0.5 * H;
+    float bg_dot_dpixel = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) bg_dot_dpixel += bg_color[i] * g_col[i];
+
+    int q = 0;
+    if (rounds > 0) issue(0);
+    __syncthreads();  // ids of batch 0 and the g4 staging are plain shared stores: make them visible
+    for (int b = 0; b < rounds; ++b) {
+        const int s = b & 1;
+        if (b + 1 < rounds) issue(b + 1);
+        mbar_wait(&S.bar[s], (uint32_t)((b >> 1) & 1));
+        const int cnt = min(BB_BATCH, n - b * BB_BATCH);
+        for (int jb = 0; jb < cnt; jb += 32) {
+            const int fwd_hi = n - 1 - (b * BB_BATCH + jb);  // largest forward index in this chunk
+            if (fwd_hi - 31 >= wmax) continue;               // whole chunk beyond this warp's reach
+            bool keep = false;
+            const int jl = jb + lane;
+            if (jl < cnt && (fwd_hi - lane) < wmax) {
+                const float4 t0 = *reinterpret_cast<const float4*>(&S.rec[s][jl][0]);
+                const float4 t1 = *reinterpret_cast<const float4*>(&S.rec[s][jl][4]);
+                const float cA = t0.z, cB = t0.w, cC = t1.x;
+                const float hx = t0.x - strip_x0;
+                const float hy = t0.y - strip_y0;
+                float qmin;
+                {
+                    const float dy = hy;
+                    const float dxs = fminf(hx, fmaxf(hx - 15.f, __fdividef(-cB * dy, cA)));
+                    const float ta = 0.5f * cA * dxs * dxs, tb = cB * dxs * dy, tc = 0.5f * cC * dy * dy;
+                    qmin = (ta + tb + tc) - 4e-6f * (fabsf(ta) + fabsf(tb) + fabsf(tc));
+                }
+                {
+                    const float dy = hy - 1.f;
+                    const float dxs = fminf(hx, fmaxf(hx - 15.f, __fdividef(-cB * dy, cA)));
+                    const float ta = 0.5f * cA * dxs * dxs, tb = cB * dxs * dy, tc = 0.5f * cC * dy * dy;
+                    qmin = fminf(qmin, (ta + tb + tc) - 4e-6f * (fabsf(ta) + fabsf(tb) + fabsf(tc)));
+                }
+                keep = !(cA > 0.f) || !(qmin > t1.w + 0.05f);
+            }
+            uint32_t mask = __ballot_sync(0xffffffffu, keep);
+            while (mask) {
+                const int jo = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const int j = jb + jo;
+                const int fwd_idx = fwd_hi - jo;
+
+                bool contrib = false;
+                float wgt = 0.f;
+                float v8[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v8[i] = 0.f;
+                if (fwd_idx < last_contributor) {
+                    const float4 q0 = *reinterpret_cast<const float4*>(&S.rec[s][j][0]);
+                    const float4 q1 = *reinterpret_cast<const float4*>(&S.rec[s][j][4]);
+                    const float2 d = {q0.x - pixf.x, q0.y - pixf.y};
+                    const float power = -0.5f * (q0.z * d.x * d.x + q1.x * d.y * d.y) - q0.w * d.x * d.y;
+                    if (!(power > 0.0f)) {
+                        const float G = expf(power);
+                        const float alpha = fminf(0.99f, q1.y * G);
+                        if (!(alpha < 1.0f / 255.0f)) {
+                            contrib = true;
+                            T = T / (1.f - alpha);
+                            wgt = alpha * T;
+                            const float4 q2 = *reinterpret_cast<const float4*>(&S.rec[s][j][8]);
+                            const float col[3] = {q2.x, q2.y, q2.z};
+                            float dL_dalpha = 0.0f;
+#pragma unroll
+                            for (int ch = 0; ch < 3; ++ch) {
+                                const float c = col[ch];
+                                accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
+                                last_color[ch] = c;
+                                dL_dalpha += (c - accum_rec[ch]) * g_col[ch];
+                            }
+                            accum_opacity = last_alpha + (1.f - last_alpha) * accum_opacity;
+                            dL_dalpha += (1.0f - accum_opacity) * g_op;
+                            dL_dalpha *= T;
+                            last_alpha = alpha;
+                            dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+
+                            const float dL_dG = q1.y * dL_dalpha;
+                            const float gdx = G * d.x;
+                            const float gdy = G * d.y;
+                            const float dG_ddelx = -gdx * q0.z - gdy * q0.w;
+                            const float dG_ddely = -gdy * q1.x - gdx * q0.w;
+                            const float m2x = dL_dG * dG_ddelx * ddelx_dx;
+                            const float m2y = dL_dG * dG_ddely * ddely_dy;
+                            v8[0] = m2x;
+                            v8[1] = m2y;
+                            v8[2] = fabsf(m2x) + fabsf(m2y);
+                            v8[3] = G * dL_dalpha;
+                            v8[4] = -0.5f * gdx * d.x * dL_dG;
+                            v8[5] = -0.5f * gdx * d.y * dL_dG;
+                            v8[6] = -0.5f * gdy * d.y * dL_dG;
+                        }
+                    }
+                }
+                if (__any_sync(0xffffffffu, contrib)) {
+                    const uint32_t gid = S.ids[s][j];
+                    const float r = warp_transpose_reduce8(v8, lane);
+                    if (lane < 7) red_add_f32(accum + (size_t)gid * ACC_FLOATS + A_M2X + lane, r);
+                    S.w[warp][lane][q] = wgt;
+                    if (lane == 0) S.qid[warp][q] = gid;
+                    if (++q == MQ) {
+                        flush(MQ);
+                        q = 0;
+                    }
+                }
+            }
+        }
+        __syncthreads();  // release stage s
+    }
+    if (q > 0) flush(q);
+}
+
 int launch_blend_backward(const GigsRasterBwd* a, const Layout& L, cudaStream_t st)
 {
     const GigsCamera& c = a->cam;
@@ -548,7 +812,26 @@ int launch_blend_backward(const GigsRasterBwd* a, const Layout& L, cudaStream_t 
             c.width, c.height, ranges, plist, recs, c.bg, finalT, ncontrib, a->dL_dpix_depth, a->dL_dpix,
             a->dL_dpix_opacity, a->dL_dpix_normal, a->dL_dpix_albedo, a->dL_dpix_roughness, a->dL_dpix_metallic,
             a->accum);
-    else
+    else if (!getenv("GIGS_BB_FULL_LEGACY")) {
+        static bool hattr = false;
+        if (!hattr) {
+            GIGS_CUDA(cudaFuncSetAttribute(blend_backward_hybrid_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sizeof(HybSmem)));
+            GIGS_CUDA(cudaFuncSetAttribute(blend_backward_hybrid_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sizeof(HybSmem)));
+            hattr = true;
+        }
+        if (!a->dL_dpix_albedo && !a->dL_dpix_metallic)
+            blend_backward_hybrid_kernel<2><<<grid, block, sizeof(HybSmem), st>>>(
+                c.width, c.height, ranges, plist, recs, c.bg, finalT, ncontrib, a->dL_dpix_depth, a->dL_dpix,
+                a->dL_dpix_opacity, a->dL_dpix_normal, a->dL_dpix_albedo, a->dL_dpix_roughness, a->dL_dpix_metallic,
+                a->accum);
+        else
+            blend_backward_hybrid_kernel<3><<<grid, block, sizeof(HybSmem), st>>>(
+                c.width, c.height, ranges, plist, recs, c.bg, finalT, ncontrib, a->dL_dpix_depth, a->dL_dpix,
+                a->dL_dpix_opacity, a->dL_dpix_normal, a->dL_dpix_albedo, a->dL_dpix_roughness, a->dL_dpix_metallic,
+                a->accum);
+    } else
         blend_backward_kernel<MODE_FULL><<<grid, block, sizeof(BwdSmem<12>), st>>>(
             c.width, c.height, ranges, plist, recs, c.bg, finalT, ncontrib, a->dL_dpix_depth, a->dL_dpix,
             a->dL_dpix_opacity, a->dL_dpix_normal, a->dL_dpix_albedo, a->dL_dpix_roughness, a->dL_dpix_metallic,

@@ -38,6 +38,16 @@ def test_first_stage_step_fused_losses_match_framework_ops(P, W, H):
     U.assert_grad_close(out[True][2], out[False][2], "viewspace_points", 1e-3)
 
 
+def _grad_close_with_flips(a, b, name, rel_tol):
+    """Norm-wise relative error per tensor as everywhere else; element-wise, all but 0.1 % of the elements within
+    rel_tol of the largest one (a flipped threshold decision moves the few Gaussians behind that pixel, not the rest)."""
+    a, b = a.float().reshape(-1), b.float().reshape(-1)
+    rel = ((a - b).norm() / (b.norm() + 1e-9 * a.numel() ** 0.5)).item()
+    assert rel <= rel_tol, f"{name}: relative error {rel} > {rel_tol}"
+    bad = ((a - b).abs() > rel_tol * b.abs().max() + 1e-8).float().mean().item()
+    assert bad <= 1e-3, f"{name}: {bad:.2e} of the elements off"
+
+
 @pytest.mark.parametrize("P,W,H,gtol", [(20000, 400, 300, 1e-3), (5000, 333, 257, 2e-3)])
 def test_fused_first_stage_frame_matches_the_operator_path(P, W, H, gtol):
     """gigs_stage1_forward / gigs_stage1_backward (getters inside preprocess, fused post-processing / losses / backward,
@@ -67,8 +77,8 @@ def test_fused_first_stage_frame_matches_the_operator_path(P, W, H, gtol):
     assert torch.equal(ra["radii"], rb["radii"])
     for k in gstep.PARAM_KEYS:
         lo, hi = pa._span[k]
-        U.assert_grad_close(pa.flat_grad[lo:hi], pb.flat_grad[lo:hi], k, gtol)
-    U.assert_grad_close(ra["viewspace_grad"], rb["viewspace_points"].grad, "viewspace_points", gtol)
+        _grad_close_with_flips(pa.flat_grad[lo:hi], pb.flat_grad[lo:hi], k, gtol)
+    _grad_close_with_flips(ra["viewspace_grad"], rb["viewspace_points"].grad, "viewspace_points", gtol)
     for a, b in ((sa.xyz_gradient_accum, sb.xyz_gradient_accum), (sa.denom, sb.denom), (sa.max_radii2D, sb.max_radii2D)):
         assert torch.allclose(a, b, rtol=1e-3, atol=1e-9)
     # a second view accumulates into the same gradient buffer (no zero_grad): twice the gradient
