@@ -545,6 +545,46 @@ def run_ours(args):
                     line["variants"]["with_build_mips"] = {"failed": str(ex)}
                 finally:
                     ctx.update(params=params, light=light, opt=None)
+                # ---- one iteration of the FIRST training stage (train.py:246-328 + 516-518): fused first-stage frame
+                # (render + L1/SSIM + normal losses + general backward into all 10 groups) + one-launch Adam ----
+                try:
+                    from gigs import optim as gopt
+                    p1 = gstep.GaussianParams(raw, dev)
+                    o1 = gopt.GaussianOptimizer(p1)
+                    n1 = max(5, args.steps // 2)
+
+                    def s1_step(i, fused=True):
+                        gstep.first_stage_step(p1, cams[i % K_cams], gts[i % K_cams], bg, gi, fused=fused)
+                        o1.step(light=False)
+                    for i in range(3):
+                        s1_step(i)
+                    t1 = 0.0
+                    for i in range(n1):
+                        flush_buf.fill_(float(i))
+                        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                        e0.record(); s1_step(i); e1.record()
+                        torch.cuda.synchronize()
+                        t1 += e0.elapsed_time(e1)
+                    L.gigs_profile_enable(1)
+                    for i in range(3):
+                        flush_buf.fill_(1.0)
+                        s1_step(i)
+                    torch.cuda.synchronize()
+                    st_ = (C.c_int32 * 4096)(); ms_ = (C.c_float * 4096)()
+                    cnt_ = L.gigs_profile_read(st_, ms_, 4096)
+                    L.gigs_profile_enable(0)
+                    agg1 = {}
+                    for j in range(cnt_):
+                        if STAGE_NAMES[st_[j]] != "radix_sort_pass":
+                            agg1[STAGE_NAMES[st_[j]]] = agg1.get(STAGE_NAMES[st_[j]], 0.0) + ms_[j] / 3
+                    line["variants"]["first_stage_iteration"] = {
+                        "value": 1e3 / (t1 / n1), "unit": "iterations/s", "ms_per_step": t1 / n1, "stage_ms": agg1,
+                        "note": "first training stage (iteration <= pbr_iteration): gigs_stage1_forward/backward (getters in "
+                                "preprocess, full G-buffer, normal post-processing, L1 + SSIM + normal L1 + normal TV, general "
+                                "blend backward, per-Gaussian backward through the getters into the leaves) + gigs_adam_step "
+                                "over all 10 groups"}
+                except Exception as ex:
+                    line["variants"]["first_stage_iteration"] = {"failed": str(ex)}
                 tu, _ = timed(gi, max(5, args.steps // 2), 3, fused=False)
                 msu = tu / max(5, args.steps // 2)
                 line["variants"]["unfused_operator_path"] = {
