@@ -84,9 +84,14 @@ def test_fused_first_stage_frame_matches_the_operator_path(P, W, H, gtol):
     # a second view accumulates into the same gradient buffer (no zero_grad): twice the gradient
     g1 = pa.flat_grad.clone()
     gstep.first_stage_step(pa, cam, gt, bg, GI, fused=True)
-    assert torch.allclose(pa.flat_grad, 2 * g1, rtol=1e-4, atol=1e-9)
+
+    def spans_close(a, b):      # per group, norm-wise: the blend backward's reductions are atomics-ordered
+        for k in gstep.PARAM_KEYS:
+            lo, hi = pa._span[k]
+            assert float((a[lo:hi] - b[lo:hi]).norm()) <= 1e-4 * float(b[lo:hi].norm()) + 1e-12, k
+    spans_close(pa.flat_grad, 2 * g1)
     # loss_scale scales loss and gradients
     pa.zero_grad()
     l2, _ = gstep.first_stage_step(pa, cam, gt, bg, GI, fused=True, loss_scale=0.25)
     assert float(l2) == pytest.approx(0.25 * float(la), rel=1e-5)
-    assert torch.allclose(pa.flat_grad, 0.25 * g1, rtol=1e-4, atol=1e-9)
+    spans_close(pa.flat_grad, 0.25 * g1)
