@@ -86,6 +86,33 @@ def main():
                                         "num_rendered": params.last_workspace.num_rendered}
         del params
         torch.cuda.empty_cache()
+        # the same scene through the FIRST-stage frame: every parameter group receives gradients (general blend backward,
+        # per-Gaussian backward through the getters), + the one-launch Adam over all 6M x 67 parameters
+        from gigs import optim as gopt
+        raw = scene.make_scene(P, seed=0, regime="trained", shape="bicycle")
+        params = gstep.GaussianParams(raw, dev)
+        del raw
+        opt = gopt.GaussianOptimizer(params)
+
+        def step1():
+            gstep.first_stage_step(params, cam, gt, bg, GI, fused=True)
+        params.zero_grad()
+        ms1 = ev_ms(step1, 5)
+
+        def step1o():
+            gstep.first_stage_step(params, cam, gt, bg, GI, fused=True)
+            opt.step(light=False)
+        ms1o = ev_ms(step1o, 5)
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        params.mark_dirty(None)
+        e0.record(); opt.step(light=False); e1.record()
+        torch.cuda.synchronize()
+        out["c3_bicycle_6M_first_stage"] = {"frame_fwd_bwd_ms": ms1, "iteration_with_adam_ms": ms1o,
+                                            "adam_ms": e0.elapsed_time(e1),
+                                            "adam_GBps": 32.0 * 67 * P / (e0.elapsed_time(e1) * 1e-3) / 1e9}
+        del params, opt
+        torch.cuda.empty_cache()
 
     if "c4" in only:
         # C4: K cameras per step sharded by view, replicated Gaussians, gradient all-reduce over NVLink
