@@ -187,7 +187,9 @@ def run_ours(args):
     import ctypes as C
 
     raw = scene.make_scene(args.P, seed=0, regime="trained")
-    params = gstep.GaussianParams(raw, dev, light=scene.make_light(0))
+    # N > 1: the gradient buffer is peer-mapped and the exchange is gigs_peer_allreduce (one kernel of ours over NVLink);
+    # GIGS_PEER_AR=0 selects the NCCL sequence instead
+    params = gstep.GaussianParams(raw, dev, light=scene.make_light(0), peer=world > 1)
     light = params.light()
     lut = shade.make_brdf_lut().to(dev)
     K_cams = 8

@@ -26,7 +26,7 @@ class GaussianParams:
     copy (autograd accumulates into an existing .grad in place)."""
 
     def __init__(self, raw: Dict, device, light: Optional[Dict] = None, light_base: Optional[torch.Tensor] = None,
-                 cutoff: float = 0.99):
+                 cutoff: float = 0.99, peer: bool = False):
         if light is not None and light_base is not None:
             raise ValueError("give the light either as textures (light=) or as the base cubemap (light_base=)")
         P = raw["xyz"].shape[0]
@@ -45,7 +45,19 @@ class GaussianParams:
             self.light_base = light_base.to(device).float().contiguous().requires_grad_(True)
             extra = [("light_base", self.light_base)]
         n = sum(t.numel() for t in self.leaves.values()) + sum(t.numel() for _, t in extra)
-        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=device)
+        # peer=True (view-sharded multi-GPU training): the gradient buffer is a symmetric allocation every rank of the
+        # node can address, and all_reduce_grads is ONE kernel of ours over NVLink (gigs.peer / csrc/peer_reduce.cu)
+        # instead of NCCL collectives. Falls back to a private buffer + NCCL when peer mapping is not available.
+        self._peer = None
+        if peer:
+            from . import peer as _peer
+            if _peer.available():
+                try:
+                    self._peer = _peer.PeerBuffer(n, device)
+                except Exception as ex:      # no P2P / IPC on this box: NCCL remains the exchange
+                    import warnings
+                    warnings.warn(f"gigs: peer-mapped gradient buffer unavailable ({ex}); using NCCL all-reduce")
+        self.flat_grad = self._peer.buf if self._peer is not None else torch.zeros(n, dtype=torch.float32, device=device)
         o = 0
         self._span = {}
         for k, t in list(self.leaves.items()) + extra:
@@ -70,7 +82,12 @@ class GaussianParams:
             extra = [("light_base", self.light_base)]
         old = {k: t.grad.clone() for k, t in extra if t.grad is not None}
         n = sum(t.numel() for t in self.leaves.values()) + sum(t.numel() for _, t in extra)
-        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        if self._peer is not None:       # collective: every rank rebuilds the same (replicated) model
+            from . import peer as _peer
+            self._peer = _peer.PeerBuffer(n, dev)
+            self.flat_grad = self._peer.buf
+        else:
+            self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
         o = 0
         self._span = {}
         for k, t in list(self.leaves.items()) + extra:
@@ -115,6 +132,12 @@ class GaussianParams:
         import torch.distributed as dist
         if not self.light_leaves and self.prefiltered is None:
             return
+        if self._peer is not None:
+            # peer mode: all spans go in ONE kernel at the end of the step (all_reduce_grads); only the mips' backward
+            # (texture gradients -> base cubemap gradient) still runs under the blend backward
+            if self.prefiltered is not None:
+                self.light_backward_overlapped(light_ready)
+            return
         if getattr(self, "_comm", None) is None:
             self._comm = torch.cuda.Stream(device=self.flat_grad.device)
         if self.prefiltered is not None:
@@ -134,6 +157,9 @@ class GaussianParams:
         With fused_only (same contract as zero_grad) only the spans the fused PBR path writes are exchanged:
         12.6 MB instead of 87 MB at 300k Gaussians; everything else is zero on every rank."""
         import torch.distributed as dist
+        if self._peer is not None:
+            self._peer.all_reduce(self._merged_dirty() if (fused_only and self._dirty is not None) else None)
+            return
         if not fused_only or self._dirty is None:
             pending = getattr(self, "_pending_light", None)
             if pending is not None:

@@ -532,6 +532,20 @@ int gigs_densify_gather(int32_t n_out, const int32_t* src_index, const int8_t* k
                         const float* src_log_scale, const float* src_rot, float split_div, int32_t n_groups,
                         const GigsDensifyGroup* groups, void* stream);
 
+/* ---- Gradient all-reduce over NVLink peer memory ------------------------------------------------------
+ * The exchange step of the view-sharded training step (the reference is single-GPU; /root/repo/BASELINE.json: "per-
+ * Gaussian gradient allreduce over NVLink") as one kernel per rank instead of a sequence of library collectives: a
+ * cross-rank barrier through flag words in peer memory, an in-place two-shot all-reduce (rank r sums slice r of every
+ * span over all ranks' buffers in rank order and stores it into all of them), a second barrier.
+ * peer_bufs[world] / peer_flags[world] (HOST arrays of device addresses): every rank's gradient buffer and flag block as
+ * mapped into THIS process (symmetric allocations; entry `rank` is the local one). A flag block is 2*world + 2 uint32,
+ * zero before the first call. epoch = 1, 2, 3, ... must advance by one per call and agree on all ranks, as must the
+ * spans (float offsets [begin, end) into the buffer) and n_ctas (0 = default 32; fixed for the lifetime of a flag block).
+ * Sums are bit-identical on all ranks and independent of timing. A peer that does not show up within ~2 s sets the
+ * local error word flags[2*world + 1] = epoch instead of hanging the device. */
+int gigs_peer_allreduce(int32_t world, int32_t rank, const uint64_t* peer_bufs, const uint64_t* peer_flags, uint32_t epoch,
+                        int32_t n_spans, const uint64_t* span_begin, const uint64_t* span_end, int32_t n_ctas, void* stream);
+
 /* Replaces distCUDA2 / SimpleKNN::knn (/root/reference/submodules/simple-knn/spatial.cu,
  * simple_knn.cu:165-207): mean squared distance to the 3 nearest other points.
  * scratch_bytes: call with scratch==NULL to query. */

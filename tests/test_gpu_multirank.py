@@ -24,13 +24,13 @@ def _free_port():
     return p
 
 
-def _inputs(dev, base_light=False):
+def _inputs(dev, base_light=False, peer=False):
     raw = scene.make_scene(P, seed=3)
     if base_light:   # the light as its trainable base cubemap: build_mips per step, its backward before the all-reduce
         base = torch.rand(6, 64, 64, 3, generator=torch.Generator().manual_seed(9)) * 0.5 + 0.25
-        params = gstep.GaussianParams(raw, dev, light_base=base)
+        params = gstep.GaussianParams(raw, dev, light_base=base, peer=peer)
     else:
-        params = gstep.GaussianParams(raw, dev, light=scene.make_light(0, base_res=64))
+        params = gstep.GaussianParams(raw, dev, light=scene.make_light(0, base_res=64), peer=peer)
     lut = shade.make_brdf_lut(64, 64).to(dev)
     cams = [scene.orbit_camera(k, 8, W, H).to(dev) for k in range(K)]
     gen = torch.Generator().manual_seed(0)
@@ -42,17 +42,26 @@ def _kw(base_light):
     return dict(brdf_tv_weight=1.0, env_tv_weight=0.01) if base_light else {}
 
 
-def _worker(rank, world, port, out, base_light):
+def _worker(rank, world, port, out, base_light, peer=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-    params, lut, cams, gts, rays, bg = _inputs(dev, base_light)
+    params, lut, cams, gts, rays, bg = _inputs(dev, base_light, peer)
+    if peer:
+        assert params._peer is not None, "peer-mapped gradient buffer not available on this box"
     for _ in range(2):   # twice: the second step exercises zero_grad(fused_only) + a reused comm stream
         total = gstep.multi_view_step(params, cams, params.light(), lut, lambda c: rays, gts, bg, GI, rank=rank,
                                       world=world, **_kw(base_light))
     torch.cuda.synchronize()
+    if peer:
+        assert params._peer.error_epoch() == 0
+        # the in-place two-shot sums are bit-identical on every rank
+        mine = params.flat_grad.clone()
+        other = mine.clone()
+        dist.broadcast(other, src=0)
+        assert torch.equal(mine, other)
     if rank == 0:
         torch.save(dict(grad=params.flat_grad.cpu(), total=float(total)), out)
     dist.barrier()
@@ -60,10 +69,11 @@ def _worker(rank, world, port, out, base_light):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("base_light", [False, True])
-def test_two_rank_multi_view_step_matches_single_process(tmp_path, base_light):
+@pytest.mark.parametrize("base_light,peer", [(False, False), (True, False), (False, True), (True, True)])
+def test_two_rank_multi_view_step_matches_single_process(tmp_path, base_light, peer):
+    """peer=True: the exchange is gigs_peer_allreduce (one kernel over NVLink peer memory) instead of NCCL."""
     out = str(tmp_path / "r.pt")
-    mp.spawn(_worker, args=(2, _free_port(), out, base_light), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), out, base_light, peer), nprocs=2, join=True)
     r = torch.load(out)
     dev = torch.device("cuda", 0)
     params, lut, cams, gts, rays, bg = _inputs(dev, base_light)
@@ -72,3 +82,36 @@ def test_two_rank_multi_view_step_matches_single_process(tmp_path, base_light):
     assert abs(r["total"] - float(total)) <= 1e-6 * abs(float(total))
     rel = float((r["grad"] - ref).norm() / ref.norm())
     assert rel <= 1e-4, rel
+
+
+def _peer_worker(rank, world, port):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from gigs import peer
+    n = 1_000_003                      # odd size: unaligned spans take the scalar path
+    pb = peer.PeerBuffer(n, dev)
+    g = torch.Generator().manual_seed(100 + rank)
+    for it, spans in enumerate(([(0, n)], [(0, 4096), (5000, 5003), (65536, 900000)], [(3, 1001)], [(0, n)])):
+        x = torch.randn(n, generator=g).to(dev)
+        pb.buf.copy_(x)
+        want = x.clone()
+        dist.all_reduce(want)          # NCCL, for comparison
+        pb.all_reduce(spans)
+        torch.cuda.synchronize()
+        assert pb.error_epoch() == 0
+        for lo, hi in spans:
+            assert torch.allclose(pb.buf[lo:hi], want[lo:hi], rtol=1e-6, atol=1e-6), (it, lo, hi)
+        mask = torch.ones(n, dtype=torch.bool, device=dev)
+        for lo, hi in spans:
+            mask[lo:hi] = False
+        assert torch.equal(pb.buf[mask], x[mask])          # outside the spans nothing moved
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_peer_allreduce_matches_nccl_on_arbitrary_spans():
+    mp.spawn(_peer_worker, args=(2, _free_port()), nprocs=2, join=True)
