@@ -353,7 +353,9 @@ blend_backward_material_kernel(const int W, const int H, const uint2* __restrict
     const int tid = threadIdx.y * TILE_X + threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const uint32_t horizontal_blocks = (W + TILE_X - 1) / TILE_X;
-    const uint2 pix = {blockIdx.x * TILE_X + threadIdx.x, blockIdx.y * TILE_Y + threadIdx.y};
+    int lx_, ly_;
+    warp_block_pixel(tid, lx_, ly_);
+    const uint2 pix = {blockIdx.x * TILE_X + lx_, blockIdx.y * TILE_Y + ly_};
     const uint32_t pix_id = W * pix.y + pix.x;
     const float2 pixf = {(float)pix.x, (float)pix.y};
     const bool inside = pix.x < (uint32_t)W && pix.y < (uint32_t)H;
@@ -393,8 +395,10 @@ blend_backward_material_kernel(const int W, const int H, const uint2* __restrict
     n = min(n, (int)(range.y - range.x));
     const int rounds = (n + BB_BATCH - 1) / BB_BATCH;
 
-    const float strip_x0 = (float)(blockIdx.x * TILE_X);
-    const float strip_y0 = (float)(blockIdx.y * TILE_Y + (threadIdx.y & ~1));
+    int ox_, oy_;
+    warp_block_origin(tid, ox_, oy_);
+    const float strip_x0 = (float)(blockIdx.x * TILE_X + ox_);   // d.x over the block: [hx - (COLS-1), hx], hx = mean.x - first column
+    const float strip_y0 = (float)(blockIdx.y * TILE_Y + oy_);
 
     auto issue = [&](int b) {
         const int s = b & 1;
@@ -460,19 +464,7 @@ blend_backward_material_kernel(const int W, const int H, const uint2* __restrict
                 const float cA = t0.z, cB = t0.w, cC = t1.x;
                 const float hx = t0.x - strip_x0;
                 const float hy = t0.y - strip_y0;
-                float qmin;
-                {
-                    const float dy = hy;
-                    const float dxs = fminf(hx, fmaxf(hx - 15.f, __fdividef(-cB * dy, cA)));
-                    const float ta = 0.5f * cA * dxs * dxs, tb = cB * dxs * dy, tc = 0.5f * cC * dy * dy;
-                    qmin = (ta + tb + tc) - 4e-6f * (fabsf(ta) + fabsf(tb) + fabsf(tc));
-                }
-                {
-                    const float dy = hy - 1.f;
-                    const float dxs = fminf(hx, fmaxf(hx - 15.f, __fdividef(-cB * dy, cA)));
-                    const float ta = 0.5f * cA * dxs * dxs, tb = cB * dxs * dy, tc = 0.5f * cC * dy * dy;
-                    qmin = fminf(qmin, (ta + tb + tc) - 4e-6f * (fabsf(ta) + fabsf(tb) + fabsf(tc)));
-                }
+                const float qmin = warp_block_qmin(cA, cB, cC, hx, hy);
                 keep = !(cA > 0.f) || !(qmin > t1.w + 0.05f);
             }
             uint32_t mask = __ballot_sync(0xffffffffu, keep);
@@ -550,7 +542,9 @@ blend_backward_hybrid_kernel(const int W, const int H, const uint2* __restrict__
     const int tid = threadIdx.y * TILE_X + threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const uint32_t horizontal_blocks = (W + TILE_X - 1) / TILE_X;
-    const uint2 pix = {blockIdx.x * TILE_X + threadIdx.x, blockIdx.y * TILE_Y + threadIdx.y};
+    int lx_, ly_;
+    warp_block_pixel(tid, lx_, ly_);
+    const uint2 pix = {blockIdx.x * TILE_X + lx_, blockIdx.y * TILE_Y + ly_};
     const uint32_t pix_id = W * pix.y + pix.x;
     const float2 pixf = {(float)pix.x, (float)pix.y};
     const bool inside = pix.x < (uint32_t)W && pix.y < (uint32_t)H;
@@ -603,8 +597,10 @@ blend_backward_hybrid_kernel(const int W, const int H, const uint2* __restrict__
     n = min(n, (int)(range.y - range.x));
     const int rounds = (n + BB_BATCH - 1) / BB_BATCH;
 
-    const float strip_x0 = (float)(blockIdx.x * TILE_X);
-    const float strip_y0 = (float)(blockIdx.y * TILE_Y + (threadIdx.y & ~1));
+    int ox_, oy_;
+    warp_block_origin(tid, ox_, oy_);
+    const float strip_x0 = (float)(blockIdx.x * TILE_X + ox_);   // d.x over the block: [hx - (COLS-1), hx], hx = mean.x - first column
+    const float strip_y0 = (float)(blockIdx.y * TILE_Y + oy_);
 
     auto issue = [&](int b) {
         const int s = b & 1;
@@ -684,19 +680,7 @@ blend_backward_hybrid_kernel(const int W, const int H, const uint2* __restrict__
                 const float cA = t0.z, cB = t0.w, cC = t1.x;
                 const float hx = t0.x - strip_x0;
                 const float hy = t0.y - strip_y0;
-                float qmin;
-                {
-                    const float dy = hy;
-                    const float dxs = fminf(hx, fmaxf(hx - 15.f, __fdividef(-cB * dy, cA)));
-                    const float ta = 0.5f * cA * dxs * dxs, tb = cB * dxs * dy, tc = 0.5f * cC * dy * dy;
-                    qmin = (ta + tb + tc) - 4e-6f * (fabsf(ta) + fabsf(tb) + fabsf(tc));
-                }
-                {
-                    const float dy = hy - 1.f;
-                    const float dxs = fminf(hx, fmaxf(hx - 15.f, __fdividef(-cB * dy, cA)));
-                    const float ta = 0.5f * cA * dxs * dxs, tb = cB * dxs * dy, tc = 0.5f * cC * dy * dy;
-                    qmin = fminf(qmin, (ta + tb + tc) - 4e-6f * (fabsf(ta) + fabsf(tb) + fabsf(tc)));
-                }
+                const float qmin = warp_block_qmin(cA, cB, cC, hx, hy);
                 keep = !(cA > 0.f) || !(qmin > t1.w + 0.05f);
             }
             uint32_t mask = __ballot_sync(0xffffffffu, keep);

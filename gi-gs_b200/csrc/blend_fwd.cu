@@ -45,7 +45,9 @@ blend_forward_kernel(const int W, const int H, const uint2* __restrict__ ranges,
     const int tid = threadIdx.y * TILE_X + threadIdx.x;
     const int lane = tid & 31;
     const uint32_t horizontal_blocks = (W + TILE_X - 1) / TILE_X;
-    const uint2 pix = {blockIdx.x * TILE_X + threadIdx.x, blockIdx.y * TILE_Y + threadIdx.y};
+    int lx_, ly_;
+    warp_block_pixel(tid, lx_, ly_);
+    const uint2 pix = {blockIdx.x * TILE_X + lx_, blockIdx.y * TILE_Y + ly_};
     const uint32_t pix_id = W * pix.y + pix.x;
     const float2 pixf = {(float)pix.x, (float)pix.y};
     const bool inside = pix.x < (uint32_t)W && pix.y < (uint32_t)H;
@@ -63,8 +65,10 @@ blend_forward_kernel(const int W, const int H, const uint2* __restrict__ ranges,
     __syncthreads();
 
     // strip bounds of this warp (2 rows x 16 columns) for the conservative rejection test
-    const float strip_x0 = (float)(blockIdx.x * TILE_X);
-    const float strip_y0 = (float)(blockIdx.y * TILE_Y + (threadIdx.y & ~1));
+    int ox_, oy_;
+    warp_block_origin(tid, ox_, oy_);
+    const float strip_x0 = (float)(blockIdx.x * TILE_X + ox_);   // d.x over the block: [hx - (COLS-1), hx], hx = mean.x - first column
+    const float strip_y0 = (float)(blockIdx.y * TILE_Y + oy_);
 
     auto issue = [&](int b) {
         const int s = b & 1;
@@ -102,19 +106,7 @@ blend_forward_kernel(const int W, const int H, const uint2* __restrict__ ranges,
                 const float cA = t0.z, cB = t0.w, cC = t1.x;
                 const float hx = t0.x - strip_x0;  // d.x over the strip: [hx-15, hx]
                 const float hy = t0.y - strip_y0;  // d.y over the strip: {hy, hy-1}
-                float qmin;
-                {
-                    const float dy = hy;
-                    const float dxs = fminf(hx, fmaxf(hx - 15.f, __fdividef(-cB * dy, cA)));
-                    const float ta = 0.5f * cA * dxs * dxs, tb = cB * dxs * dy, tc = 0.5f * cC * dy * dy;
-                    qmin = (ta + tb + tc) - 4e-6f * (fabsf(ta) + fabsf(tb) + fabsf(tc));
-                }
-                {
-                    const float dy = hy - 1.f;
-                    const float dxs = fminf(hx, fmaxf(hx - 15.f, __fdividef(-cB * dy, cA)));
-                    const float ta = 0.5f * cA * dxs * dxs, tb = cB * dxs * dy, tc = 0.5f * cC * dy * dy;
-                    qmin = fminf(qmin, (ta + tb + tc) - 4e-6f * (fabsf(ta) + fabsf(tb) + fabsf(tc)));
-                }
+                const float qmin = warp_block_qmin(cA, cB, cC, hx, hy);
                 // reject only when provably alpha < 1/255 on all 32 pixels; NaNs / non-convex -> keep
                 keep = !(cA > 0.f) || !(qmin > t1.w + 0.05f);
             }

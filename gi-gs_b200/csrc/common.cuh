@@ -84,6 +84,48 @@ uint32_t higher_msb(uint32_t n);
 int radix_digit_bits(int bits);
 int radix_sort_passes(int bits);
 
+// ---------------------------------------------------------------------------------------------
+// Pixel block of one warp inside the 16x16 tile. The blend kernels reject, once per warp, the Gaussians whose 1/255
+// iso-ellipse misses the warp's block; a compact 8x4 block is missed ~15-20 % more often than the 16x2 strip a
+// row-major thread layout gives (the Minkowski sum of block and footprint is smaller), so fewer (warp, Gaussian) pairs
+// are walked. Per pixel the blend order is unchanged, so the forward results are bit-identical either way.
+// ---------------------------------------------------------------------------------------------
+#ifndef GIGS_WARP_COLS
+#define GIGS_WARP_COLS 8
+#endif
+constexpr int WARP_COLS = GIGS_WARP_COLS, WARP_ROWS = 32 / WARP_COLS;
+// tile-local pixel of thread `tid` (0..255): warps tile the 16x16 block in WARP_COLS x WARP_ROWS pieces
+__device__ __forceinline__ void warp_block_pixel(int tid, int& lx, int& ly)
+{
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr int per_row = 16 / WARP_COLS;                 // warp blocks per tile row
+    lx = (warp % per_row) * WARP_COLS + (lane % WARP_COLS);
+    ly = (warp / per_row) * WARP_ROWS + (lane / WARP_COLS);
+}
+// tile-local origin of the warp's block
+__device__ __forceinline__ void warp_block_origin(int tid, int& ox, int& oy)
+{
+    const int warp = tid >> 5;
+    constexpr int per_row = 16 / WARP_COLS;
+    ox = (warp % per_row) * WARP_COLS;
+    oy = (warp / per_row) * WARP_ROWS;
+}
+// lower bound of the conic's quadratic form 0.5 d^T C d over the block, d = mean2D - pixel: d.x in [hx-(COLS-1), hx],
+// d.y in {hy, hy-1, ..., hy-(ROWS-1)}; exact per row (clamped vertex), with a rounding margin
+__device__ __forceinline__ float warp_block_qmin(float cA, float cB, float cC, float hx, float hy)
+{
+    float qmin;
+#pragma unroll
+    for (int r = 0; r < WARP_ROWS; ++r) {
+        const float dy = hy - (float)r;
+        const float dxs = fminf(hx, fmaxf(hx - (float)(WARP_COLS - 1), __fdividef(-cB * dy, cA)));
+        const float ta = 0.5f * cA * dxs * dxs, tb = cB * dxs * dy, tc = 0.5f * cC * dy * dy;
+        const float q = (ta + tb + tc) - 4e-6f * (fabsf(ta) + fabsf(tb) + fabsf(tc));
+        qmin = (r == 0) ? q : fminf(qmin, q);
+    }
+    return qmin;
+}
+
 // gaussian_backward_kernel<RAW> (gauss_bwd.cu): raw leaves in, gradients accumulated into the leaves' gradient tensors
 struct RawGrads {
     const float* f_rest; const float* opacity; const float* normal; const float* albedo; const float* roughness;
