@@ -100,6 +100,8 @@ class FusedAdam:
         and that is not in zero_grads is skipped, as torch does."""
         L = _lib.load()
         zero = set(zero_grads)
+        if any(not g["params"][0].is_cuda for g in self.param_groups):
+            raise RuntimeError("FusedAdam.step: parameters must be CUDA tensors (there is no CPU fallback)")
         arr = (_lib.GigsAdamGroup * len(self.param_groups))()
         n = 0
         keep = []

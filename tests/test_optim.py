@@ -85,6 +85,13 @@ def test_update_learning_rate_follows_the_reference_control_flow():
     assert cg["eps"] == 1e-8 and cg["lr"] == 0.05 and cg["clamp_min0"]   # train.py:215-218, :523
 
 
+def test_fused_adam_refuses_cpu_tensors():
+    p = torch.zeros(8)
+    fa = gopt.FusedAdam([dict(params=[p], name="x")])
+    with pytest.raises(RuntimeError, match="CUDA"):
+        fa.step(grads={"x": torch.zeros(8)})
+
+
 def test_densify_stats_oracle_shapes():
     g = torch.Generator().manual_seed(0)
     P = 50
