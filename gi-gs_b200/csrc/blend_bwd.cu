@@ -19,7 +19,10 @@
 namespace gigs {
 
 constexpr int BB_THREADS = 256;
-constexpr int BB_BATCH = 256;
+#ifndef GIGS_BB_BATCH
+#define GIGS_BB_BATCH 256
+#endif
+constexpr int BB_BATCH = GIGS_BB_BATCH;
 
 template <int RECF>
 struct BwdSmem {

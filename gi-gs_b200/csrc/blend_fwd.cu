@@ -16,7 +16,10 @@
 namespace gigs {
 
 constexpr int BL_THREADS = 256;
-constexpr int BL_BATCH = 256;
+#ifndef GIGS_BL_BATCH
+#define GIGS_BL_BATCH 256
+#endif
+constexpr int BL_BATCH = GIGS_BL_BATCH;
 constexpr uint32_t REC_BYTES = REC_FLOATS * 4;
 
 struct BlendSmem {

@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libgigs_b200.so")
+# GIGS_LIB: an alternative build of the same library (kernel-tuning experiments: tools/build_variant.sh)
+LIB_PATH = os.environ.get("GIGS_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libgigs_b200.so")
 
 c_f32p = C.c_void_p  # device pointers travel as integers
 
