@@ -74,6 +74,9 @@ def workspace(P: int, W: int, H: int, device) -> FrameWorkspace:
     key = (P, W, H, torch.device(device).index or 0)
     ws = _workspaces.get(key)
     if ws is None:
+        # densification changes P every 100 iterations: the buffers of the previous model size are dropped, not kept
+        for old in [k for k in _workspaces if k[1:] == key[1:] and k[0] != P]:
+            del _workspaces[old]
         ws = _workspaces[key] = FrameWorkspace(P, W, H, device)
     return ws
 
