@@ -22,16 +22,22 @@ constexpr int BL_THREADS = 256;
 constexpr int BL_BATCH = GIGS_BL_BATCH;
 constexpr uint32_t REC_BYTES = REC_FLOATS * 4;
 
-struct BlendSmem {
-    float rec[2][BL_BATCH][REC_FLOATS];  // 2 x 24 KB
+template <int BATCH>
+struct BlendSmemT {
+    float rec[2][BATCH][REC_FLOATS];  // 2 x 24 KB at 256 records
     uint64_t bar[2];
 };
+using BlendSmem = BlendSmemT<BL_BATCH>;
+// The MATERIAL forward (PBR-stage frame) runs 128-record batches: half the shared memory lifts it from 4 to 5 resident
+// CTAs per SM (then register bound), 0.179 -> 0.170 ms; the 17-channel forward and both backwards measured 1-3 % slower
+// with 128 and keep 256.
+constexpr int BL_BATCH_MATERIAL = 128;
 
 // ARGMAX: track the heaviest contributor's depth / position (settings.argmax_depth); the training and evaluation
 // drivers leave it off, and then the three selects + two compares per contributing pair are dead weight.
 // MATERIAL (GigsRasterFwd.material_only): the radiance image and the blended position are not wanted — 5 packed FMAs
 // and 3 record loads per contributing pair instead of 8 and 4; every other output is bit-identical.
-template <bool LITE, bool ARGMAX, bool MATERIAL = false>
+template <bool LITE, bool ARGMAX, bool MATERIAL = false, int BATCH = BL_BATCH>
 __global__ void __launch_bounds__(BL_THREADS)
 blend_forward_kernel(const int W, const int H, const uint2* __restrict__ ranges,
                      const uint32_t* __restrict__ point_list, const float* __restrict__ records,
@@ -43,7 +49,8 @@ blend_forward_kernel(const int W, const int H, const uint2* __restrict__ ranges,
                      float* __restrict__ out_metallic, const bool inference)
 {
     extern __shared__ __align__(128) unsigned char bl_smem_raw[];
-    BlendSmem& S = *reinterpret_cast<BlendSmem*>(bl_smem_raw);
+    using Smem = BlendSmemT<BATCH>;
+    Smem& S = *reinterpret_cast<Smem*>(bl_smem_raw);
 
     const int tid = threadIdx.y * TILE_X + threadIdx.x;
     const int lane = tid & 31;
@@ -58,7 +65,7 @@ blend_forward_kernel(const int W, const int H, const uint2* __restrict__ ranges,
 
     const uint2 range = ranges[blockIdx.y * horizontal_blocks + blockIdx.x];
     const int n = (int)(range.y - range.x);
-    const int rounds = (n + BL_BATCH - 1) / BL_BATCH;
+    const int rounds = (n + BATCH - 1) / BATCH;
 
     if (tid == 0) {
         mbar_init(&S.bar[0], 1);
@@ -75,10 +82,10 @@ blend_forward_kernel(const int W, const int H, const uint2* __restrict__ ranges,
 
     auto issue = [&](int b) {
         const int s = b & 1;
-        const int cnt = min(BL_BATCH, n - b * BL_BATCH);
+        const int cnt = min(BATCH, n - b * BATCH);
         if (tid == 0) mbar_arrive_expect_tx(&S.bar[s], (uint32_t)cnt * REC_BYTES);
         if (tid < cnt) {
-            const uint32_t id = point_list[range.x + b * BL_BATCH + tid];
+            const uint32_t id = point_list[range.x + b * BATCH + tid];
             bulk_g2s(&S.rec[s][tid][0], records + (size_t)id * REC_FLOATS, REC_BYTES, &S.bar[s]);
         }
     };
@@ -97,7 +104,7 @@ blend_forward_kernel(const int W, const int H, const uint2* __restrict__ ranges,
         if (b + 1 < rounds) issue(b + 1);  // stage s^1 was released by the barrier ending round b-1
         mbar_wait(&S.bar[s], (uint32_t)((b >> 1) & 1));
 
-        const int cnt = min(BL_BATCH, n - b * BL_BATCH);
+        const int cnt = min(BATCH, n - b * BATCH);
         bool warp_done = __all_sync(0xffffffffu, done);
         for (int jb = 0; jb < cnt && !warp_done; jb += 32) {
             // --- lane l tests Gaussian jb+l against this warp's 16x2 strip (conservative bound) ---
@@ -143,7 +150,7 @@ blend_forward_kernel(const int W, const int H, const uint2* __restrict__ ranges,
                     C2R = ffma2(make_float2(q4.z, rough), w2, C2R);   // {N2, roughness} in this variant
                     DO = ffma2(make_float2(depth, 1.0f), w2, DO);
                     T = test_T;
-                    last_contributor = (uint32_t)(b * BL_BATCH + j + 1);
+                    last_contributor = (uint32_t)(b * BATCH + j + 1);
                     continue;
                 }
                 const float4 q2 = *reinterpret_cast<const float4*>(&S.rec[s][j][8]);
@@ -167,7 +174,7 @@ blend_forward_kernel(const int W, const int H, const uint2* __restrict__ ranges,
                     max_weight = weight;
                 }
                 T = test_T;
-                last_contributor = (uint32_t)(b * BL_BATCH + j + 1);
+                last_contributor = (uint32_t)(b * BATCH + j + 1);
             }
             warp_done = __all_sync(0xffffffffu, done);
         }
@@ -237,7 +244,8 @@ int launch_blend_forward(const GigsRasterFwd* a, const Layout& L, bool lite, cud
         GIGS_CUDA(cudaFuncSetAttribute(blend_forward_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
         GIGS_CUDA(cudaFuncSetAttribute(blend_forward_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
         GIGS_CUDA(cudaFuncSetAttribute(blend_forward_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-        GIGS_CUDA(cudaFuncSetAttribute(blend_forward_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        GIGS_CUDA(cudaFuncSetAttribute(blend_forward_kernel<false, false, true, BL_BATCH_MATERIAL>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlendSmemT<BL_BATCH_MATERIAL>)));
         attr_set = true;
     }
     const uint2* ranges = (const uint2*)(im + L.off.i_ranges);
@@ -254,7 +262,8 @@ int launch_blend_forward(const GigsRasterFwd* a, const Layout& L, bool lite, cud
     if (lite && am) blend_forward_kernel<true, true><<<grid, block, sizeof(BlendSmem), st>>>(BL_LITE_ARGS);
     else if (lite) blend_forward_kernel<true, false><<<grid, block, sizeof(BlendSmem), st>>>(BL_LITE_ARGS);
     else if (am) blend_forward_kernel<false, true><<<grid, block, sizeof(BlendSmem), st>>>(BL_FULL_ARGS);
-    else if (a->material_only) blend_forward_kernel<false, false, true><<<grid, block, sizeof(BlendSmem), st>>>(BL_FULL_ARGS);
+    else if (a->material_only)
+        blend_forward_kernel<false, false, true, BL_BATCH_MATERIAL><<<grid, block, sizeof(BlendSmemT<BL_BATCH_MATERIAL>), st>>>(BL_FULL_ARGS);
     else blend_forward_kernel<false, false><<<grid, block, sizeof(BlendSmem), st>>>(BL_FULL_ARGS);
 #undef BL_LITE_ARGS
 #undef BL_FULL_ARGS
