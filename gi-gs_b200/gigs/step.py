@@ -370,6 +370,42 @@ def multi_view_step(params: GaussianParams, cams: List, light: Light, brdf_lut, 
     return total
 
 
+def multi_view_first_stage_step(params: GaussianParams, cams: List, gts: List, background, gi: Dict, rank: int = 0,
+                                world: int = 1, stats=None, **kw) -> torch.Tensor:
+    """K-view step of the FIRST training stage, views sharded round-robin over `world` ranks: every parameter group
+    receives gradients there, so the exchange is the whole flat buffer — 268 B per Gaussian — in one
+    gigs_peer_allreduce launch (GaussianParams(peer=True)) or one NCCL all-reduce. loss = mean over the K views.
+    `stats` accumulates the densification statistics of the LOCAL views (per-view norms: they are summed over ranks with
+    reduce_densify_stats, not derived from the reduced gradient — SURVEY §8e)."""
+    K = len(cams)
+    params.zero_grad()
+    total = torch.zeros((), device=params.flat_grad.device)
+    for k in range(rank, K, world):
+        loss, _ = first_stage_step(params, cams[k], gts[k], background, gi, loss_scale=1.0 / K, stats=stats,
+                                   fused=bool(kw.get("fused", True)),
+                                   **{a: b for a, b in kw.items() if a != "fused"})
+        total = total + loss
+    if world > 1:
+        import torch.distributed as dist
+        params.mark_dirty(None)
+        params.all_reduce_grads(fused_only=False)
+        dist.all_reduce(total, op=dist.ReduceOp.SUM)
+    return total
+
+
+def reduce_densify_stats(stats, world: int) -> None:
+    """Sum the per-view densification statistics over the ranks (xyz_gradient_accum*, denom) and take the maximum of
+    the per-view maxima (xyz_gradient_accum_abs_max, max_radii2D): afterwards every rank holds what a single process
+    that had rendered all K views would hold (scene/gaussian_model.py:933-945)."""
+    if world <= 1:
+        return
+    import torch.distributed as dist
+    for t in (stats.xyz_gradient_accum, stats.xyz_gradient_accum_abs, stats.denom):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    for t in (stats.xyz_gradient_accum_abs_max, stats.max_radii2D):
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+
+
 def shard_views(n_views: int, rank: int, world: int) -> List[int]:
     """Camera-sharded eval / relight sweep (BASELINE C5): independent views, round-robin, no data-path collective."""
     return list(range(rank, n_views, world))

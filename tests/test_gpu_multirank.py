@@ -115,3 +115,45 @@ def _peer_worker(rank, world, port):
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_peer_allreduce_matches_nccl_on_arbitrary_spans():
     mp.spawn(_peer_worker, args=(2, _free_port()), nprocs=2, join=True)
+
+
+def _stage1_worker(rank, world, port, out, peer):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from gigs import densify
+    params, lut, cams, gts, rays, bg = _inputs(dev, False, peer)
+    st = densify.DensifyState(P, dev)
+    total = gstep.multi_view_first_stage_step(params, cams, gts, bg, GI, rank=rank, world=world, stats=st)
+    gstep.reduce_densify_stats(st, world)
+    torch.cuda.synchronize()
+    if rank == 0:
+        torch.save(dict(grad=params.flat_grad.cpu(), total=float(total), accum=st.xyz_gradient_accum.cpu(),
+                        denom=st.denom.cpu(), radii=st.max_radii2D.cpu()), out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("peer", [False, True])
+def test_two_rank_first_stage_step_matches_single_process(tmp_path, peer):
+    """First stage: every group has gradients, the whole 268 B/Gaussian buffer is exchanged (peer kernel or NCCL), and the
+    per-view densification statistics are reduced over the ranks."""
+    from gigs import densify
+    out = str(tmp_path / "s1.pt")
+    mp.spawn(_stage1_worker, args=(2, _free_port(), out, peer), nprocs=2, join=True)
+    r = torch.load(out)
+    dev = torch.device("cuda", 0)
+    params, lut, cams, gts, rays, bg = _inputs(dev)
+    st = densify.DensifyState(P, dev)
+    total = gstep.multi_view_first_stage_step(params, cams, gts, bg, GI, stats=st)
+    ref = params.flat_grad.cpu()
+    assert abs(r["total"] - float(total)) <= 1e-6 * abs(float(total))
+    for k in gstep.PARAM_KEYS:
+        lo, hi = params._span[k]
+        if float(ref[lo:hi].norm()) > 0:
+            assert float((r["grad"][lo:hi] - ref[lo:hi]).norm() / ref[lo:hi].norm()) <= 1e-4, k
+    assert torch.allclose(r["accum"], st.xyz_gradient_accum.cpu(), rtol=1e-4, atol=1e-9)
+    assert torch.equal(r["denom"], st.denom.cpu()) and torch.equal(r["radii"], st.max_radii2D.cpu())
