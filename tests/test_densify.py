@@ -121,3 +121,30 @@ def test_densify_gather_argument_errors_and_default_noise():
     info = densify.densify_and_prune(params, None, st, 0.0002, 0.005, 5.0, None)
     assert info["P_after"] > 3000 and info["n_clone"] + info["n_split"] > 0
     assert torch.isfinite(params.leaves["xyz"]).all() and float(params.leaves["xyz"].abs().max()) < float(before.abs().max()) + 2.0
+
+
+@pytest.mark.gpu
+def test_densify_with_nothing_selected_only_prunes():
+    """Thresholds nobody reaches: no clones, no splits; the pass degenerates to the opacity prune, moments of the kept
+    rows are carried over bit for bit."""
+    from gigs import densify, optim as gopt, scene, step as gstep
+    dev = torch.device("cuda:0")
+    raw = scene.make_scene(2000, seed=5, regime="trained")
+    params = gstep.GaussianParams(raw, dev)
+    opt = gopt.GaussianOptimizer(params)
+    for k in gstep.PARAM_KEYS:
+        params.leaves[k].grad.normal_()
+    params.mark_dirty(None)
+    opt.step()
+    m_before = opt.adam.state["f_rest"]["exp_avg"].clone()
+    op = torch.sigmoid(params.leaves["opacity"].detach())[:, 0]
+    st = densify.DensifyState(2000, dev)
+    g = torch.rand(2000, 3, generator=torch.Generator().manual_seed(1)) * 1e-9      # distinct values: no ties at the maximum
+    st.add_view(g.to(dev), torch.ones(2000, dtype=torch.int32, device=dev))
+    info = densify.densify_and_prune(params, opt, st, 1e3, 0.05, 5.0, None)
+    keep = op >= 0.05
+    # grads_abs >= Q with Q = quantile(., 1 - 0) = max: the reference's rule still selects the maximum element(s)
+    assert info["n_clone"] + info["n_split"] <= 2
+    assert abs(info["P_after"] - int(keep.sum())) <= 4
+    if info["n_clone"] + info["n_split"] == 0:
+        assert torch.equal(opt.adam.state["f_rest"]["exp_avg"], m_before[keep])

@@ -164,3 +164,19 @@ def test_normal_loss_matches_reference_goldens_and_oracle():
     # an empty mask is a mean over nothing: NaN, as in the reference
     e = losses.normal_loss(nm.cuda(), nd.cuda(), torch.zeros_like(mask).cuda(), gt.cuda())
     assert torch.isnan(e)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("Cn,H,W", [(3, 5, 300), (1, 1, 17), (3, 17, 1), (2, 31, 33)])
+def test_image_loss_odd_shapes_match_oracle(Cn, H, W):
+    """Images thinner than the 11-tap window, single rows / columns, sizes that are not multiples of the 16-pixel tile."""
+    from gigs import losses
+    img, gt = images(Cn, H, W, 40 + H)
+    x = img.clone().requires_grad_(True)
+    want = O.l1_ssim_loss(x, gt, 0.2)
+    want.backward()
+    xg = img.cuda().requires_grad_(True)
+    got = losses.l1_ssim_loss(xg, gt.cuda(), 0.2)
+    got.backward()
+    assert float(got) == pytest.approx(float(want), abs=VAL_TOL)
+    assert _grad_close(xg.grad.cpu(), x.grad)
