@@ -51,8 +51,13 @@ __device__ __forceinline__ void gb_normalize_bwd(const float* v, const float* g,
     }
 }
 
+#ifdef GIGS_GB_MINB
+#define GB_BOUNDS __launch_bounds__(GB_THREADS, GIGS_GB_MINB)
+#else
+#define GB_BOUNDS __launch_bounds__(GB_THREADS)
+#endif
 template <bool RAW>
-__global__ void __launch_bounds__(GB_THREADS)
+__global__ void GB_BOUNDS
 gaussian_backward_kernel(const int P, const int D, const int M, const float* __restrict__ means3D,
                          const int* __restrict__ radii, const float* __restrict__ shs,
                          const uint8_t* __restrict__ clamped, const float* __restrict__ scales,
