@@ -6,6 +6,7 @@
 // cov2D -> cov3D -> (scale, quaternion), mean2D -> mean3D, colour -> SH (+ view-direction term),
 // and writes EVERY output element exactly once (zeros for Gaussians with radius <= 0), so the
 // caller can hand in uninitialised tensors.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace gigs {
@@ -56,9 +57,12 @@ __device__ __forceinline__ void gb_normalize_bwd(const float* v, const float* g,
 #else
 #define GB_BOUNDS __launch_bounds__(GB_THREADS)
 #endif
+// s_row: RAW fast path only — this Gaussian's 45 f_rest floats staged in shared memory by the kernel below; the SH
+// gradient is written back into the same row (in place: every read of the row precedes the first write)
 template <bool RAW>
-__global__ void GB_BOUNDS
-gaussian_backward_kernel(const int P, const int D, const int M, const float* __restrict__ means3D,
+__device__ __forceinline__ void
+gaussian_backward_body(const int idx, float* __restrict__ s_row,
+                       const int P, const int D, const int M, const float* __restrict__ means3D,
                          const int* __restrict__ radii, const float* __restrict__ shs,
                          const uint8_t* __restrict__ clamped, const float* __restrict__ scales,
                          const float* __restrict__ rotations, const float scale_modifier,
@@ -72,10 +76,8 @@ gaussian_backward_kernel(const int P, const int D, const int M, const float* __r
                          float* __restrict__ dL_dnormal, float* __restrict__ dL_dalbedo,
                          float* __restrict__ dL_droughness, float* __restrict__ dL_dmetallic,
                          float* __restrict__ dL_dmean3D, float* __restrict__ dL_dcov3D, float* __restrict__ dL_dsh,
-                         float* __restrict__ dL_dscale, float* __restrict__ dL_drot, const RawGrads raw)
+                         float* __restrict__ dL_dscale, float* __restrict__ dL_drot, const RawGrads& raw)
 {
-    const int idx = blockIdx.x * GB_THREADS + threadIdx.x;
-    if (idx >= P) return;
     const bool visible = radii[idx] > 0;
 
     float acc[ACC_FLOATS];
@@ -98,7 +100,11 @@ gaussian_backward_kernel(const int P, const int D, const int M, const float* __r
         dL_dmean2D[3 * idx + 2] = acc[A_M2Z];
     }
     if (RAW) {
-        if (!visible) return;
+        if (!visible) {
+            if (s_row)      // the staged row goes back as this Gaussian's (zero) SH gradient
+                for (int c = 0; c < 3 * (M - 1); ++c) s_row[c] = 0.f;
+            return;
+        }
         const float op = gb_sigmoid(raw.opacity[idx]);
         raw.g_opacity[idx] += acc[A_OPAC] * ((1.0f - op) * op);
         if (acc[A_ROUGH] != 0.f) {
@@ -267,16 +273,21 @@ gaussian_backward_kernel(const int P, const int D, const int M, const float* __r
         const B3 dir_orig = {pos.x - cam.x, pos.y - cam.y, pos.z - cam.z};
         const float len = sqrtf(dotB(dir_orig, dir_orig));
         const B3 dir = {dir_orig.x / len, dir_orig.y / len, dir_orig.z / len};
-        // RAW: coefficient 0 lives in f_dc, coefficient i >= 1 at f_rest + (idx*(M-1) + i-1)*3
-        const float* shp = RAW ? raw.f_rest + ((size_t)idx * (M - 1) - 1) * 3 : shs + (size_t)idx * M * 3;
+        // RAW: coefficient 0 lives in f_dc, coefficient i >= 1 at f_rest + (idx*(M-1) + i-1)*3 (or in the staged row)
+        const bool staged = RAW && s_row != nullptr;
+        const float* shp = staged ? s_row - 3 : (RAW ? raw.f_rest + ((size_t)idx * (M - 1) - 1) * 3 : shs + (size_t)idx * M * 3);
         auto SH = [&](int i) -> B3 { return {shp[3 * i + 0], shp[3 * i + 1], shp[3 * i + 2]}; };
-        float* dshp = RAW ? raw.g_f_rest + ((size_t)idx * (M - 1) - 1) * 3 : dL_dsh + (size_t)idx * M * 3;
+        float* dshp = staged ? s_row - 3 : (RAW ? raw.g_f_rest + ((size_t)idx * (M - 1) - 1) * 3 : dL_dsh + (size_t)idx * M * 3);
         auto DSH = [&](int i, const B3& v) {
-            if (RAW) {
-                float* d = (i == 0) ? raw.g_f_dc + (size_t)idx * 3 : dshp + 3 * i;
+            if (RAW && i == 0) {
+                float* d = raw.g_f_dc + (size_t)idx * 3;
                 d[0] += v.x;
                 d[1] += v.y;
                 d[2] += v.z;
+            } else if (RAW && !staged) {
+                dshp[3 * i + 0] += v.x;
+                dshp[3 * i + 1] += v.y;
+                dshp[3 * i + 2] += v.z;
             } else {
                 dshp[3 * i + 0] = v.x;
                 dshp[3 * i + 1] = v.y;
@@ -289,41 +300,22 @@ gaussian_backward_kernel(const int P, const int D, const int M, const float* __r
         dL_dRGB.y *= cl.y ? 0 : 1;
         dL_dRGB.z *= cl.z ? 0 : 1;
 
+        // pass 1: everything that READS the coefficients (the view-direction term), ...
         B3 dRGBdx = {0, 0, 0}, dRGBdy = {0, 0, 0}, dRGBdz = {0, 0, 0};
         const float x = dir.x, y = dir.y, z = dir.z;
-        DSH(0, bSH_C0 * dL_dRGB);
-        int written = 1;
+        const float xx = x * x, yy = y * y, zz = z * z;
+        const float xy = x * y, yz = y * z, xz = x * z;
         if (D > 0) {
-            DSH(1, (-bSH_C1 * y) * dL_dRGB);
-            DSH(2, (bSH_C1 * z) * dL_dRGB);
-            DSH(3, (-bSH_C1 * x) * dL_dRGB);
-            written = 4;
             dRGBdx = -bSH_C1 * SH(3);
             dRGBdy = -bSH_C1 * SH(1);
             dRGBdz = bSH_C1 * SH(2);
             if (D > 1) {
-                const float xx = x * x, yy = y * y, zz = z * z;
-                const float xy = x * y, yz = y * z, xz = x * z;
-                DSH(4, (bSH_C2[0] * xy) * dL_dRGB);
-                DSH(5, (bSH_C2[1] * yz) * dL_dRGB);
-                DSH(6, (bSH_C2[2] * (2.f * zz - xx - yy)) * dL_dRGB);
-                DSH(7, (bSH_C2[3] * xz) * dL_dRGB);
-                DSH(8, (bSH_C2[4] * (xx - yy)) * dL_dRGB);
-                written = 9;
                 dRGBdx += bSH_C2[0] * y * SH(4) + bSH_C2[2] * 2.f * -x * SH(6) + bSH_C2[3] * z * SH(7) +
                           bSH_C2[4] * 2.f * x * SH(8);
                 dRGBdy += bSH_C2[0] * x * SH(4) + bSH_C2[1] * z * SH(5) + bSH_C2[2] * 2.f * -y * SH(6) +
                           bSH_C2[4] * 2.f * -y * SH(8);
                 dRGBdz += bSH_C2[1] * y * SH(5) + bSH_C2[2] * 2.f * 2.f * z * SH(6) + bSH_C2[3] * x * SH(7);
                 if (D > 2) {
-                    DSH(9, (bSH_C3[0] * y * (3.f * xx - yy)) * dL_dRGB);
-                    DSH(10, (bSH_C3[1] * xy * z) * dL_dRGB);
-                    DSH(11, (bSH_C3[2] * y * (4.f * zz - xx - yy)) * dL_dRGB);
-                    DSH(12, (bSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy)) * dL_dRGB);
-                    DSH(13, (bSH_C3[4] * x * (4.f * zz - xx - yy)) * dL_dRGB);
-                    DSH(14, (bSH_C3[5] * z * (xx - yy)) * dL_dRGB);
-                    DSH(15, (bSH_C3[6] * x * (xx - 3.f * yy)) * dL_dRGB);
-                    written = 16;
                     dRGBdx += (bSH_C3[0] * SH(9) * 3.f * 2.f * xy + bSH_C3[1] * SH(10) * yz +
                                bSH_C3[2] * SH(11) * -2.f * xy + bSH_C3[3] * SH(12) * -3.f * 2.f * xz +
                                bSH_C3[4] * SH(13) * (-3.f * xx + 4.f * zz - yy) + bSH_C3[5] * SH(14) * 2.f * xz +
@@ -338,8 +330,35 @@ gaussian_backward_kernel(const int P, const int D, const int M, const float* __r
                 }
             }
         }
+        // ... pass 2: the coefficient gradients (the staged row is overwritten in place from here on)
+        DSH(0, bSH_C0 * dL_dRGB);
+        int written = 1;
+        if (D > 0) {
+            DSH(1, (-bSH_C1 * y) * dL_dRGB);
+            DSH(2, (bSH_C1 * z) * dL_dRGB);
+            DSH(3, (-bSH_C1 * x) * dL_dRGB);
+            written = 4;
+            if (D > 1) {
+                DSH(4, (bSH_C2[0] * xy) * dL_dRGB);
+                DSH(5, (bSH_C2[1] * yz) * dL_dRGB);
+                DSH(6, (bSH_C2[2] * (2.f * zz - xx - yy)) * dL_dRGB);
+                DSH(7, (bSH_C2[3] * xz) * dL_dRGB);
+                DSH(8, (bSH_C2[4] * (xx - yy)) * dL_dRGB);
+                written = 9;
+                if (D > 2) {
+                    DSH(9, (bSH_C3[0] * y * (3.f * xx - yy)) * dL_dRGB);
+                    DSH(10, (bSH_C3[1] * xy * z) * dL_dRGB);
+                    DSH(11, (bSH_C3[2] * y * (4.f * zz - xx - yy)) * dL_dRGB);
+                    DSH(12, (bSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy)) * dL_dRGB);
+                    DSH(13, (bSH_C3[4] * x * (4.f * zz - xx - yy)) * dL_dRGB);
+                    DSH(14, (bSH_C3[5] * z * (xx - yy)) * dL_dRGB);
+                    DSH(15, (bSH_C3[6] * x * (xx - 3.f * yy)) * dL_dRGB);
+                    written = 16;
+                }
+            }
+        }
         // coefficients above the active degree get no gradient (zeros in the reference's pre-filled tensor)
-        if (!RAW)
+        if (!RAW || staged)
             for (int i = written; i < M; ++i) DSH(i, B3{0.f, 0.f, 0.f});
 
         const B3 dL_ddir = {dotB(dRGBdx, dL_dRGB), dotB(dRGBdy, dL_dRGB), dotB(dRGBdz, dL_dRGB)};
@@ -437,6 +456,74 @@ gaussian_backward_kernel(const int P, const int D, const int M, const float* __r
     }
 }
 
+// The kernel. RAW fast path (M = 16, i.e. 45 f_rest floats per Gaussian, full warps, 16-B aligned tensors): a warp's 32
+// rows are 5760 contiguous bytes — it moves them with 12 coalesced 16-B loads per lane into its own shared-memory
+// region (flat layout: a 45-float row stride is conflict-free), the body reads its row and overwrites it with the SH
+// gradient, and the warp adds the region onto the leaf's gradient with 16-B loads / stores. Per lane that is 36
+// memory instructions instead of 135 scalar ones; the scalar kernel is bound by the LSU queue (ncu: lg_throttle +
+// long_scoreboard at 12 % issue utilisation). Only __syncwarp is needed: no CTA barrier, 23 KB of shared memory.
+template <bool RAW>
+__global__ void GB_BOUNDS
+gaussian_backward_kernel(const int P, const int D, const int M, const float* __restrict__ means3D,
+                         const int* __restrict__ radii, const float* __restrict__ shs,
+                         const uint8_t* __restrict__ clamped, const float* __restrict__ scales,
+                         const float* __restrict__ rotations, const float scale_modifier,
+                         const float* __restrict__ cov3Ds, const float* __restrict__ view_matrix,
+                         const float* __restrict__ proj, const float* __restrict__ campos, const float h_x,
+                         const float h_y, const float tan_fovx, const float tan_fovy,
+                         const float* __restrict__ accum,
+                         float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic_out,
+                         float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolor,
+                         float* __restrict__ dL_dnormal, float* __restrict__ dL_dalbedo,
+                         float* __restrict__ dL_droughness, float* __restrict__ dL_dmetallic,
+                         float* __restrict__ dL_dmean3D, float* __restrict__ dL_dcov3D, float* __restrict__ dL_dsh,
+                         float* __restrict__ dL_dscale, float* __restrict__ dL_drot, const RawGrads raw, const int stage_rows)
+{
+    extern __shared__ float4 gb_stage4[];
+    constexpr int ROW = 45, V4 = 32 * ROW / 4;                 // 360 float4 per warp
+    const int idx = blockIdx.x * GB_THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int idx0w = blockIdx.x * GB_THREADS + warp * 32;
+    float* s_row = nullptr;
+    bool fast = false;
+    if (RAW) {
+        fast = stage_rows && (idx0w + 32 <= P);                 // warp-uniform
+        if (fast) {
+            float4* sw = gb_stage4 + warp * V4;
+            const float4* g4 = reinterpret_cast<const float4*>(raw.f_rest + (size_t)idx0w * ROW);
+#pragma unroll
+            for (int j = 0; j < (V4 + 31) / 32; ++j) {
+                const int q = lane + 32 * j;
+                if (q < V4) sw[q] = g4[q];
+            }
+            __syncwarp();
+            s_row = reinterpret_cast<float*>(sw) + lane * ROW;
+        }
+    }
+    if (idx < P)
+        gaussian_backward_body<RAW>(idx, s_row, P, D, M, means3D, radii, shs, clamped, scales, rotations, scale_modifier,
+                                    cov3Ds, view_matrix, proj, campos, h_x, h_y, tan_fovx, tan_fovy, accum, dL_dmean2D,
+                                    dL_dconic_out, dL_dopacity, dL_dcolor, dL_dnormal, dL_dalbedo, dL_droughness,
+                                    dL_dmetallic, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, raw);
+    if (RAW && fast) {
+        __syncwarp();
+        const float4* sw = gb_stage4 + warp * V4;
+        float4* o4 = reinterpret_cast<float4*>(raw.g_f_rest + (size_t)idx0w * ROW);
+#pragma unroll
+        for (int j = 0; j < (V4 + 31) / 32; ++j) {
+            const int q = lane + 32 * j;
+            if (q < V4) {
+                const float4 v = sw[q];
+                if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) {
+                    float4 o = o4[q];
+                    o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
+                    o4[q] = o;
+                }
+            }
+        }
+    }
+}
+
 int launch_gaussian_backward(const GigsRasterBwd* a, const Layout& L, cudaStream_t st)
 {
     const GigsCamera& c = a->cam;
@@ -448,7 +535,7 @@ int launch_gaussian_backward(const GigsRasterBwd* a, const Layout& L, cudaStream
         a->P, c.sh_degree, c.sh_coeffs, a->means3D, a->radii, a->shs, (const uint8_t*)(g + L.off.g_clamped), a->scales,
         a->rotations, c.scale_modifier, cov3D_ptr, c.viewmatrix, c.projmatrix, c.campos, focal_x, focal_y, c.tan_fovx,
         c.tan_fovy, a->accum, a->dL_dmean2D, a->dL_dconic, a->dL_dopacity, a->dL_dcolor, a->dL_dnormal, a->dL_dalbedo,
-        a->dL_droughness, a->dL_dmetallic, a->dL_dmean3D, a->dL_dcov3D, a->dL_dsh, a->dL_dscale, a->dL_drot, RawGrads{});
+        a->dL_droughness, a->dL_dmetallic, a->dL_dmean3D, a->dL_dcov3D, a->dL_dsh, a->dL_dscale, a->dL_drot, RawGrads{}, 0);
     GIGS_LAUNCH_CHECK("gaussian_backward_kernel");
     return 0;
 }
@@ -461,11 +548,16 @@ int launch_gaussian_backward_raw(int P, const GigsCamera& c, const void* geom, c
     const char* g = (const char*)geom;
     const float focal_y = c.height / (2.0f * c.tan_fovy);
     const float focal_x = c.width / (2.0f * c.tan_fovx);
-    gaussian_backward_kernel<true><<<(P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, st>>>(
+    // staged SH rows: 45 floats per Gaussian (M = 16) and 16-B aligned leaves (GIGS_GB_STAGE=0 turns it off)
+    static const bool stage_env = !(getenv("GIGS_GB_STAGE") && atoi(getenv("GIGS_GB_STAGE")) == 0);
+    const int stage_rows = stage_env && c.sh_coeffs == 16 && raw.f_rest && raw.g_f_rest &&
+                           ((((uintptr_t)raw.f_rest | (uintptr_t)raw.g_f_rest) & 15) == 0);
+    const size_t smem = stage_rows ? (size_t)(GB_THREADS / 32) * (32 * 45 / 4) * sizeof(float4) : 0;
+    gaussian_backward_kernel<true><<<(P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, smem, st>>>(
         P, c.sh_degree, c.sh_coeffs, xyz, radii, f_dc, (const uint8_t*)(g + L.off.g_clamped), log_scale, rot,
         c.scale_modifier, (const float*)(g + L.off.g_cov3D), c.viewmatrix, c.projmatrix, c.campos, focal_x, focal_y,
         c.tan_fovx, c.tan_fovy, accum, g_means2D, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-        nullptr, nullptr, nullptr, nullptr, raw);
+        nullptr, nullptr, nullptr, nullptr, raw, stage_rows);
     GIGS_LAUNCH_CHECK("gaussian_backward_kernel<RAW>");
     return 0;
 }
