@@ -39,6 +39,7 @@ struct AdamGroupDev {
     float w2;          // 1 - beta2
     float neg_step_size;   // -(lr / (1 - beta1^t))
     float bc2_sqrt;        // sqrt(1 - beta2^t)
+    float bc2_rcp;         // rn(1 / bc2_sqrt): division by the per-group constant as a correctly rounded 3-FMA sequence
     float eps;
     int flags;             // bit 0: clamp param at >= 0 after the update; bit 1: clear grad; bit 2: pointers 16-B aligned
 };
@@ -52,7 +53,14 @@ __device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v,
 {
     m = __fmaf_rn(G.w1, __fsub_rn(g, m), m);
     v = __fmaf_rn(__fmul_rn(G.w2, g), g, __fmul_rn(v, G.beta2));
-    const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), G.bc2_sqrt), G.eps);
+    // sqrt(v) / bc2_sqrt with the divisor's reciprocal precomputed (Markstein: q = s*R, r = s - q*b exactly, q' = q + r*R
+    // is the correctly rounded quotient for a correctly rounded R; 3 instructions instead of the ~9 of an IEEE division —
+    // this kernel is issue bound: 84 % of issue slots busy at 5.5 TB/s)
+    const float sv = __fsqrt_rn(v);
+    const float q0 = __fmul_rn(sv, G.bc2_rcp);
+    float hat = __fmaf_rn(__fmaf_rn(-q0, G.bc2_sqrt, sv), G.bc2_rcp, q0);
+    if (!(q0 < 3.0e38f)) hat = q0;      // overflowed second moment: inf / b = inf (the residual would be inf - inf)
+    const float denom = __fadd_rn(hat, G.eps);
     p = __fmaf_rn(G.neg_step_size, __fdiv_rn(m, denom), p);
     if (G.flags & 1) p = (p < 0.f) ? 0.f : p;   // clamp_(min=0); a NaN stays a NaN as in torch (fmaxf would drop it)
 }
@@ -177,6 +185,7 @@ int gigs_adam_step(int32_t n_groups, const GigsAdamGroup* groups, void* stream)
         d.w2 = (float)(1.0 - b2);
         d.neg_step_size = (float)(-(s.lr / bc1));
         d.bc2_sqrt = (float)std::sqrt(bc2);
+        d.bc2_rcp = (float)(1.0 / (double)d.bc2_sqrt);
         d.eps = (float)s.eps;
         const uintptr_t al = (uintptr_t)s.param | (uintptr_t)s.exp_avg | (uintptr_t)s.exp_avg_sq | (uintptr_t)s.grad;
         d.flags = (s.clamp_min0 ? 1 : 0) | (s.clear_grad ? 2 : 0) | ((al & 15) == 0 ? 4 : 0);
