@@ -37,7 +37,9 @@ constexpr int BL_BATCH_MATERIAL = 128;
 // drivers leave it off, and then the three selects + two compares per contributing pair are dead weight.
 // MATERIAL (GigsRasterFwd.material_only): the radiance image and the blended position are not wanted — 5 packed FMAs
 // and 3 record loads per contributing pair instead of 8 and 4; every other output is bit-identical.
-template <bool LITE, bool ARGMAX, bool MATERIAL = false, int BATCH = BL_BATCH>
+// GEOM (material_only == 2, the first-stage frame): radiance, normal, depth and opacity only — the material channels,
+// the blended position and the view-space normal are neither accumulated nor written (5 packed FMAs per pair).
+template <bool LITE, bool ARGMAX, bool MATERIAL = false, int BATCH = BL_BATCH, bool GEOM = false>
 __global__ void __launch_bounds__(BL_THREADS)
 blend_forward_kernel(const int W, const int H, const uint2* __restrict__ ranges,
                      const uint32_t* __restrict__ point_list, const float* __restrict__ records,
@@ -157,7 +159,11 @@ blend_forward_kernel(const int W, const int H, const uint2* __restrict__ ranges,
                 // the 17 accumulations as 8 packed FMAs (FFMA2); halves round exactly like the scalar fma
                 C01 = ffma2(make_float2(q2.x, q2.y), w2, C01);
                 C2R = ffma2(make_float2(q2.z, q2.w), w2, C2R);
-                if (!LITE) {
+                if (GEOM) {
+                    const float4 q4 = *reinterpret_cast<const float4*>(&S.rec[s][j][16]);
+                    N01 = ffma2(make_float2(q4.x, q4.y), w2, N01);
+                    N2P = ffma2(make_float2(q4.z, q4.w), w2, N2P);
+                } else if (!LITE) {
                     const float4 q3 = *reinterpret_cast<const float4*>(&S.rec[s][j][12]);
                     const float4 q4 = *reinterpret_cast<const float4*>(&S.rec[s][j][16]);
                     const float2 q5 = *reinterpret_cast<const float2*>(&S.rec[s][j][20]);
@@ -194,7 +200,9 @@ blend_forward_kernel(const int W, const int H, const uint2* __restrict__ ranges,
         n_contrib[pix_id] = last_contributor;
         if (!MATERIAL)
             for (int ch = 0; ch < 3; ch++) out_color[ch * HW + pix_id] = C[ch] + T * bg_color[ch];
-        if (!LITE) {
+        if (GEOM) {
+            for (int ch = 0; ch < 3; ch++) out_normal[ch * HW + pix_id] = N[ch];
+        } else if (!LITE) {
             const float* V = viewmatrix;
             float3 Nv;
             Nv.x = V[0] * N[0] + V[4] * N[1] + V[8] * N[2];
@@ -213,14 +221,14 @@ blend_forward_kernel(const int W, const int H, const uint2* __restrict__ ranges,
         }
         if (O > 1e-6) {
             out_depth[pix_id] = ARGMAX ? except_depth : D / O;
-            if (!LITE && !MATERIAL) {
+            if (!LITE && !MATERIAL && !GEOM) {
                 out_pos[pix_id] = ARGMAX ? except_pos.x : POS.x / O;
                 out_pos[HW + pix_id] = ARGMAX ? except_pos.y : POS.y / O;
                 out_pos[2 * HW + pix_id] = ARGMAX ? except_pos.z : POS.z / O;
             }
         } else {
             out_depth[pix_id] = 0.0f;
-            if (!LITE && !MATERIAL) {
+            if (!LITE && !MATERIAL && !GEOM) {
                 out_pos[pix_id] = 0.0f;
                 out_pos[HW + pix_id] = 0.0f;
                 out_pos[2 * HW + pix_id] = 0.0f;
@@ -244,6 +252,8 @@ int launch_blend_forward(const GigsRasterFwd* a, const Layout& L, bool lite, cud
         GIGS_CUDA(cudaFuncSetAttribute(blend_forward_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
         GIGS_CUDA(cudaFuncSetAttribute(blend_forward_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
         GIGS_CUDA(cudaFuncSetAttribute(blend_forward_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        GIGS_CUDA(cudaFuncSetAttribute(blend_forward_kernel<false, false, false, BL_BATCH_MATERIAL, true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlendSmemT<BL_BATCH_MATERIAL>)));
         GIGS_CUDA(cudaFuncSetAttribute(blend_forward_kernel<false, false, true, BL_BATCH_MATERIAL>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlendSmemT<BL_BATCH_MATERIAL>)));
         attr_set = true;
@@ -262,6 +272,8 @@ int launch_blend_forward(const GigsRasterFwd* a, const Layout& L, bool lite, cud
     if (lite && am) blend_forward_kernel<true, true><<<grid, block, sizeof(BlendSmem), st>>>(BL_LITE_ARGS);
     else if (lite) blend_forward_kernel<true, false><<<grid, block, sizeof(BlendSmem), st>>>(BL_LITE_ARGS);
     else if (am) blend_forward_kernel<false, true><<<grid, block, sizeof(BlendSmem), st>>>(BL_FULL_ARGS);
+    else if (a->material_only == 2)
+        blend_forward_kernel<false, false, false, BL_BATCH_MATERIAL, true><<<grid, block, sizeof(BlendSmemT<BL_BATCH_MATERIAL>), st>>>(BL_FULL_ARGS);
     else if (a->material_only)
         blend_forward_kernel<false, false, true, BL_BATCH_MATERIAL><<<grid, block, sizeof(BlendSmemT<BL_BATCH_MATERIAL>), st>>>(BL_FULL_ARGS);
     else blend_forward_kernel<false, false><<<grid, block, sizeof(BlendSmem), st>>>(BL_FULL_ARGS);

@@ -471,13 +471,13 @@ int launch_preprocess(const GigsRasterFwd* a, const Layout& L, cudaStream_t st, 
     P, c.sh_degree, c.sh_coeffs, a->means3D, a->scales, c.scale_modifier, a->rotations, a->opacities, a->shs, sh_rest, \
         a->cov3D_precomp, a->colors_precomp, a->normal, a->albedo, a->roughness, a->metallic, c.viewmatrix,           \
         c.projmatrix, c.campos, c.width, c.height, c.tan_fovx, c.tan_fovy, focal_x, focal_y, L.tiles_x, L.tiles_y,    \
-        c.prefiltered != 0, stage_sh, a->material_only != 0, a->radii, (float*)(g + L.off.g_record), (float*)(g + L.off.g_cov3D),            \
+        c.prefiltered != 0, stage_sh, a->material_only == 1, a->radii, (float*)(g + L.off.g_record), (float*)(g + L.off.g_cov3D),            \
         (uint8_t*)(g + L.off.g_clamped), (uint32_t*)(g + L.off.g_tiles_touched), (uint32_t*)(g + L.off.g_depth_keys), \
         (uint32_t*)(g + L.off.g_block_sums)
     // dynamic shared memory: the CTA's slab of SH coefficients (see the kernel); not staged if it would not fit
     const size_t sh_floats = (size_t)PRE_THREADS * (sh_rest ? (c.sh_coeffs - 1) * 3 : c.sh_coeffs * 3);
     static const bool no_stage = getenv("GIGS_PRE_NOSTAGE") != nullptr;
-    const bool stage_sh = !no_stage && !a->material_only && a->colors_precomp == nullptr && sh_floats > 0 && sh_floats * 4 <= 96 * 1024;
+    const bool stage_sh = !no_stage && a->material_only != 1 && a->colors_precomp == nullptr && sh_floats > 0 && sh_floats * 4 <= 96 * 1024;
     const size_t smem = stage_sh ? sh_floats * 4 : 0;
     static bool attr_set = false;
     if (!attr_set) {

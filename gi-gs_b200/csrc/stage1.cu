@@ -213,6 +213,7 @@ int gigs_stage1_forward(GigsStage1* f)
     GigsRasterFwd a;
     memset(&a, 0, sizeof(a));
     a.P = f->P;
+    a.material_only = 2;   // radiance + normal + depth + opacity: the first-stage loss reads nothing else
     a.cam = c;
     a.cam.prefiltered = 0; a.cam.argmax_depth = 0; a.cam.inference = 0;
     a.means3D = f->xyz; a.shs = f->f_dc; a.opacities = f->opacity; a.normal = f->normal; a.albedo = f->albedo;

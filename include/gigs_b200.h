@@ -93,7 +93,9 @@ typedef struct GigsRasterFwd {
     int32_t P;
     int32_t material_only; /* 1: the caller does not read out_color / out_pos (the PBR stage: train.py uses the SH radiance
                               image only in the first stage and for logging): SH evaluation and those 6 blend channels are
-                              skipped, the two outputs are left untouched. 0 = everything, like the reference. */
+                              skipped, the two outputs are left untouched. 2: the caller reads out_color, out_normal, out_depth and
+                              out_opacity only (the first training stage): the material channels, out_pos and out_normal_view
+                              are neither blended nor written. 0 = everything, like the reference. */
     GigsCamera cam;
     const float* means3D;        /* [P,3] */
     const float* shs;            /* [P,M,3] or NULL */
