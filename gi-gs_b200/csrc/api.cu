@@ -3,7 +3,10 @@
 // (:676-803). No torch types; the caller owns every buffer.
 #include <cstdarg>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 #include "common.cuh"
 
@@ -25,6 +28,21 @@ int cuda_fail(cudaError_t e, const char* what)
 {
     set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
     return (int)e;
+}
+
+static std::mutex g_attr_mutex;
+static std::map<std::pair<int, const void*>, int> g_attr_set;  // (device, kernel) -> bytes already granted
+int ensure_dynamic_smem(const void* kernel, int bytes)
+{
+    int dev = 0;
+    GIGS_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_attr_mutex);
+    auto key = std::make_pair(dev, kernel);
+    auto it = g_attr_set.find(key);
+    if (it != g_attr_set.end() && it->second >= bytes) return 0;
+    GIGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    g_attr_set[key] = bytes;
+    return 0;
 }
 
 // ---- optional per-stage event timing -------------------------------------------------------------

@@ -771,14 +771,8 @@ int launch_blend_backward(const GigsRasterBwd* a, const Layout& L, cudaStream_t 
     const char* im = (const char*)a->img;
     const char* bn = (const char*)a->binning;
     dim3 grid(L.tiles_x, L.tiles_y, 1), block(TILE_X, TILE_Y, 1);
-    static bool attr_set = false;
-    if (!attr_set) {
-        GIGS_CUDA(cudaFuncSetAttribute(blend_backward_kernel<MODE_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sizeof(BwdSmem<12>)));
-        GIGS_CUDA(cudaFuncSetAttribute(blend_backward_kernel<MODE_MATERIAL>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem<8>)));
-        attr_set = true;
-    }
+    GIGS_SMEM_ATTR(blend_backward_kernel<MODE_FULL>, sizeof(BwdSmem<12>));
+    GIGS_SMEM_ATTR(blend_backward_kernel<MODE_MATERIAL>, sizeof(BwdSmem<8>));
     const uint2* ranges = (const uint2*)(im + L.off.i_ranges);
     const uint32_t* plist = (const uint32_t*)(bn + L.off.b_point_list);
     const float* recs = (const float*)(g + L.off.g_record);
@@ -788,12 +782,7 @@ int launch_blend_backward(const GigsRasterBwd* a, const Layout& L, cudaStream_t 
                                (a->dL_dpix_normal == nullptr) && (a->dL_dpix_depth == nullptr);
     static const bool legacy_material = getenv("GIGS_BB_LEGACY") != nullptr;
     if (material_only && !legacy_material) {
-        static bool mattr = false;
-        if (!mattr) {
-            GIGS_CUDA(cudaFuncSetAttribute(blend_backward_material_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)sizeof(MatSmem)));
-            mattr = true;
-        }
+        GIGS_SMEM_ATTR(blend_backward_material_kernel, sizeof(MatSmem));
         blend_backward_material_kernel<<<grid, block, sizeof(MatSmem), st>>>(
             c.width, c.height, ranges, plist, recs, ncontrib, a->dL_dpix_albedo, a->dL_dpix_roughness,
             a->dL_dpix_metallic, a->accum);
@@ -803,14 +792,8 @@ int launch_blend_backward(const GigsRasterBwd* a, const Layout& L, cudaStream_t 
             a->dL_dpix_opacity, a->dL_dpix_normal, a->dL_dpix_albedo, a->dL_dpix_roughness, a->dL_dpix_metallic,
             a->accum);
     else if (!getenv("GIGS_BB_FULL_LEGACY")) {
-        static bool hattr = false;
-        if (!hattr) {
-            GIGS_CUDA(cudaFuncSetAttribute(blend_backward_hybrid_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)sizeof(HybSmem)));
-            GIGS_CUDA(cudaFuncSetAttribute(blend_backward_hybrid_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)sizeof(HybSmem)));
-            hattr = true;
-        }
+        GIGS_SMEM_ATTR(blend_backward_hybrid_kernel<2>, sizeof(HybSmem));
+        GIGS_SMEM_ATTR(blend_backward_hybrid_kernel<3>, sizeof(HybSmem));
         if (!a->dL_dpix_albedo && !a->dL_dpix_metallic)
             blend_backward_hybrid_kernel<2><<<grid, block, sizeof(HybSmem), st>>>(
                 c.width, c.height, ranges, plist, recs, c.bg, finalT, ncontrib, a->dL_dpix_depth, a->dL_dpix,

@@ -245,18 +245,14 @@ int launch_blend_forward(const GigsRasterFwd* a, const Layout& L, bool lite, cud
     char* im = (char*)a->img;
     const char* bn = (const char*)a->binning;
     dim3 grid(L.tiles_x, L.tiles_y, 1), block(TILE_X, TILE_Y, 1);
-    static bool attr_set = false;
-    if (!attr_set) {
-        const int sm = (int)sizeof(BlendSmem);
-        GIGS_CUDA(cudaFuncSetAttribute(blend_forward_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-        GIGS_CUDA(cudaFuncSetAttribute(blend_forward_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-        GIGS_CUDA(cudaFuncSetAttribute(blend_forward_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-        GIGS_CUDA(cudaFuncSetAttribute(blend_forward_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-        GIGS_CUDA(cudaFuncSetAttribute(blend_forward_kernel<false, false, false, BL_BATCH_MATERIAL, true>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlendSmemT<BL_BATCH_MATERIAL>)));
-        GIGS_CUDA(cudaFuncSetAttribute(blend_forward_kernel<false, false, true, BL_BATCH_MATERIAL>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlendSmemT<BL_BATCH_MATERIAL>)));
-        attr_set = true;
+    {
+        const int sm = (int)sizeof(BlendSmem), smm = (int)sizeof(BlendSmemT<BL_BATCH_MATERIAL>);
+        GIGS_SMEM_ATTR((blend_forward_kernel<false, false>), sm);
+        GIGS_SMEM_ATTR((blend_forward_kernel<false, true>), sm);
+        GIGS_SMEM_ATTR((blend_forward_kernel<true, false>), sm);
+        GIGS_SMEM_ATTR((blend_forward_kernel<true, true>), sm);
+        GIGS_SMEM_ATTR((blend_forward_kernel<false, false, false, BL_BATCH_MATERIAL, true>), smm);
+        GIGS_SMEM_ATTR((blend_forward_kernel<false, false, true, BL_BATCH_MATERIAL>), smm);
     }
     const uint2* ranges = (const uint2*)(im + L.off.i_ranges);
     const uint32_t* plist = (const uint32_t*)(bn + L.off.b_point_list);

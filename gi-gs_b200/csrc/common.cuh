@@ -37,6 +37,13 @@ enum : int {
 
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute of a function: set it once per (device,
+// kernel) under a mutex (api.cu). Returns 0 or a cudaError_t (message in gigs_last_error()).
+int ensure_dynamic_smem(const void* kernel, int bytes);
+#define GIGS_SMEM_ATTR(kernel, bytes)                                                    \
+    do {                                                                                 \
+        if (int _e = gigs::ensure_dynamic_smem((const void*)(kernel), (int)(bytes))) return _e; \
+    } while (0)
 
 #define GIGS_CUDA(call)                                          \
     do {                                                         \

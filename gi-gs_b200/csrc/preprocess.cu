@@ -479,12 +479,8 @@ int launch_preprocess(const GigsRasterFwd* a, const Layout& L, cudaStream_t st, 
     static const bool no_stage = getenv("GIGS_PRE_NOSTAGE") != nullptr;
     const bool stage_sh = !no_stage && a->material_only != 1 && a->colors_precomp == nullptr && sh_floats > 0 && sh_floats * 4 <= 96 * 1024;
     const size_t smem = stage_sh ? sh_floats * 4 : 0;
-    static bool attr_set = false;
-    if (!attr_set) {
-        GIGS_CUDA(cudaFuncSetAttribute(preprocess_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        GIGS_CUDA(cudaFuncSetAttribute(preprocess_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr_set = true;
-    }
+    GIGS_SMEM_ATTR(preprocess_kernel<true>, 96 * 1024);
+    GIGS_SMEM_ATTR(preprocess_kernel<false>, 96 * 1024);
     if (sh_rest != nullptr)
         preprocess_kernel<true><<<L.num_blocks, PRE_THREADS, smem, st>>>(PRE_ARGS);
     else

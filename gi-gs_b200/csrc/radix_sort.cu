@@ -244,12 +244,7 @@ static int launch_passes(uint32_t n, int end_bit, const K* keys_u, const uint32_
 {
     using Smem = RsSmem<K, BITS, T, I>;
     static_assert(T * I <= 65536 && T * I >= RS_MIN_TILE, "tile must fit the u16 ranks and the status allocation");
-    static bool attr_set = false;
-    if (!attr_set) {
-        GIGS_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel<K, BITS, T, I>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sizeof(Smem)));
-        attr_set = true;
-    }
+    GIGS_SMEM_ATTR((rs_onesweep_kernel<K, BITS, T, I>), sizeof(Smem));
     const int passes = (end_bit + BITS - 1) / BITS;
     const uint32_t tiles = (n + T * I - 1) / (T * I);
     const K* kin = keys_u;

@@ -1,18 +1,13 @@
-// Screen-space passes over the G-buffer: 3x3 median / bilateral filters, depth -> pseudo-normal,
-// the fused geometry chain, SSAO and SSR (the "lightweight path tracer").
+// Screen-space passes over the G-buffer: 3x3 median / bilateral filters, depth -> pseudo-normal and
+// the fused geometry chain (SSAO and SSR, the "lightweight path tracer", live in gi_march.cu).
 //
 // Follows (reference, read-only):
-//   cuda_rasterizer/forward.cu:914-1032  depthmapToNormalCUDA     cuda_rasterizer/ssr.h:103-135
-//   cuda_rasterizer/forward.cu:635-724   SSAOCUDA                 cuda_rasterizer/forward.cu:726-909 SSRCUDA
+//   cuda_rasterizer/forward.cu:914-1032  depthmapToNormalCUDA     cuda_rasterizer/ssr.h:103-118
 //   diff_gaussian_rasterization/__init__.py:475-517  (filter -> depth_to_normal -> filter -> SSAO glue)
 // and the documented semantics of the two third-party filters the reference calls
 // (kornia median_blur / bilateral_blur, SURVEY.md A.10 — "parity unpinned": kornia is not installable here).
 //
-// What is ours: the 512-direction hemisphere table is built once per CTA in shared memory with the
-// reference's exact float-accumulated phi/theta sequences (the reference recomputes 5 trig calls per
-// direction per pixel); the four-launch filter chain is one tiled kernel with a 4-pixel halo.
-// The probe arithmetic keeps the reference's operation order because every probe ends in a
-// threshold test: one flipped hit moves a pixel's occlusion by up to 3e-3.
+// What is ours: the four-launch filter chain is one tiled kernel with a 4-pixel halo.
 #include "common.cuh"
 #include "filters.cuh"
 
@@ -315,224 +310,6 @@ geometry_chain_kernel(const int W, const int H, const float fx, const float fy, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Hemisphere direction table shared by SSAO and SSR.
-// The reference loops `for (float phi = 0; phi < 2.0*M_PIf; phi += d)` / `for (float theta = 0;
-// theta <= 0.5*M_PIf; theta += d*0.5)` with float accumulators and double comparisons; the host
-// replays exactly that to get the trip counts, the kernel replays it for the values.
-// ---------------------------------------------------------------------------------------------
-struct DirCounts {
-    int n_phi, n_theta;
-};
-static DirCounts count_dirs(float delta)
-{
-    DirCounts c{0, 0};
-    const float sampleDelta = delta * M_PIf;
-    if (!(sampleDelta > 0.f)) return c;
-    for (float phi = 0.0; phi < 2.0 * M_PIf; phi += sampleDelta) {
-        if (++c.n_phi > 4096) break;
-    }
-    for (float theta = 0.0; theta <= 0.5 * M_PIf; theta += sampleDelta * 0.5) {
-        if (++c.n_theta > 4096) break;
-    }
-    return c;
-}
-
-struct DirEntry {
-    float x, y, z, c, s;  // normalised tangent-space direction, cos(theta), sin(theta)
-};
-
-__device__ __forceinline__ void build_dir_table(DirEntry* tab, float* phis, float* thetas, int n_phi, int n_theta,
-                                                float delta, int tid, int nthreads)
-{
-    const float sampleDelta = delta * M_PIf;
-    if (tid == 0) {
-        float phi = 0.0;
-        for (int i = 0; i < n_phi; ++i) {
-            phis[i] = phi;
-            phi += sampleDelta;
-        }
-        float theta = 0.0;
-        for (int k = 0; k < n_theta; ++k) {
-            thetas[k] = theta;
-            theta += sampleDelta * 0.5;  // double multiply-add, float store
-        }
-    }
-    __syncthreads();
-    for (int e = tid; e < n_phi * n_theta; e += nthreads) {
-        const float phi = phis[e / n_theta], theta = thetas[e % n_theta];
-        const float3 t = normalize3(make_float3(sinf(theta) * cosf(phi), sinf(theta) * sinf(phi), cosf(theta)));
-        tab[e] = DirEntry{t.x, t.y, t.z, cosf(theta), sinf(theta)};
-    }
-    __syncthreads();
-}
-
-// reference ssr.h:120-135
-__device__ __forceinline__ int2 project_coord(float cx, float cy, float fx, float fy, const float3 pos)
-{
-    const float3 dir = make_float3(pos.x / (pos.z + 0.0000001f), pos.y / (pos.z + 0.0000001f), 1.0f);
-    int2 xy;
-    xy.x = (int)roundf(dir.x * fx + cx);
-    xy.y = (int)roundf(dir.y * fy + cy);
-    return xy;
-}
-
-struct Tbn {
-    float m[9];
-};
-__device__ __forceinline__ Tbn make_tbn(const float3 normal)
-{
-    const float3 up = {0.0f, 1.0f, 0.0f};
-    const float rndot = dot3(up, normal);
-    const float3 untangent = {up.x - normal.x * rndot, up.y - normal.y * rndot, up.z - normal.z * rndot};
-    const float3 tangent = normalize3(untangent);
-    const float3 bitangent = normalize3(cross3(normal, tangent));
-    Tbn t;
-    t.m[0] = tangent.x; t.m[1] = tangent.y; t.m[2] = tangent.z;
-    t.m[3] = bitangent.x; t.m[4] = bitangent.y; t.m[5] = bitangent.z;
-    t.m[6] = normal.x; t.m[7] = normal.y; t.m[8] = normal.z;
-    return t;
-}
-
-constexpr int GI_MAX_DIRS = 2048;
-
-template <bool IS_SSR, bool POW2_STEP>
-__global__ void __launch_bounds__(256)
-gi_march_kernel(const int W, const int H, const float focal_x, const float focal_y, const float radius,
-                const float bias, const float thick, const float delta, const int step, const int start,
-                const int n_phi, const int n_theta, const float* __restrict__ out_normal,
-                const float* __restrict__ out_pos, const float* __restrict__ out_rgb,
-                const float* __restrict__ out_albedo, const float* __restrict__ out_metallic,
-                const float* __restrict__ out_F0, float* __restrict__ out0 /*occlusion | color*/,
-                float* __restrict__ out1 /*- | abd*/)
-{
-    extern __shared__ __align__(16) unsigned char gi_smem_raw[];
-    DirEntry* tab = reinterpret_cast<DirEntry*>(gi_smem_raw);
-    float* phis = reinterpret_cast<float*>(tab + n_phi * n_theta);
-    float* thetas = phis + n_phi;
-    const int tid = threadIdx.y * TILE_X + threadIdx.x;
-    // start >= step (the README's --start 64 --step 16): the march loop body never runs, so no direction is ever
-    // used. SSAO's normaliser is then a positive sum and occ = 0 (occlusion exactly 1); SSR's is the direction count.
-    const bool no_march = start >= step;
-    if (!no_march) build_dir_table(tab, phis, thetas, n_phi, n_theta, delta, tid, 256);
-
-    const uint32_t px = blockIdx.x * TILE_X + threadIdx.x, py = blockIdx.y * TILE_Y + threadIdx.y;
-    if (px > (uint32_t)(W - 1) || py > (uint32_t)(H - 1)) return;
-    const int HW = H * W;
-    const uint32_t pix_id = W * py + px;
-
-    const float3 normal_un = {out_normal[pix_id], out_normal[HW + pix_id], out_normal[2 * HW + pix_id]};
-    const float3 normal = normalize3(normal_un);
-    const float3 pos = {out_pos[pix_id], out_pos[HW + pix_id], out_pos[2 * HW + pix_id]};
-    const Tbn tbn = make_tbn(normal);
-    const float* zbuf = out_pos + 2 * (size_t)HW;
-    const float cx = float(W) / 2.0f, cy = float(H) / 2.0f;
-    const float scale = (1 + pos.z / 100);
-    const float stepf = (float)step;
-    const float inv_stepf = 1.0f / stepf;
-    const int ndir = n_phi * n_theta;
-
-    float occ = 0.0f;
-    float nrSamples = 0.0f;
-    float3 diffuse = {0.0f, 0.0f, 0.0f};
-    if (no_march) nrSamples = IS_SSR ? (float)ndir : (ndir > 0 ? 1.0f : 0.0f);
-    for (int e = 0; e < (no_march ? 0 : ndir); ++e) {
-        const DirEntry de = tab[e];
-        float3 sv;
-        sv.x = tbn.m[0] * de.x + tbn.m[3] * de.y + tbn.m[6] * de.z;
-        sv.y = tbn.m[1] * de.x + tbn.m[4] * de.y + tbn.m[7] * de.z;
-        sv.z = tbn.m[2] * de.x + tbn.m[5] * de.y + tbn.m[8] * de.z;
-        if (IS_SSR)
-            nrSamples += 1;
-        else
-            nrSamples = __fmaf_rn(de.c, de.s, nrSamples);  // the reference's SASS contracts both accumulations
-        for (int j = start; j < step; ++j) {
-            float3 sp;
-            if (POW2_STEP) {
-                // step is a power of two: x / step == x * (1/step) bit-for-bit (both are the correctly rounded
-                // quotient), which removes three IEEE divisions per probe
-                sp.x = pos.x + sv.x * j * scale * scale * radius * inv_stepf;
-                sp.y = pos.y + sv.y * j * scale * scale * radius * inv_stepf;
-                sp.z = pos.z + sv.z * j * scale * scale * radius * inv_stepf;
-            } else {
-                sp.x = pos.x + sv.x * j * scale * scale * radius / stepf;
-                sp.y = pos.y + sv.y * j * scale * scale * radius / stepf;
-                sp.z = pos.z + sv.z * j * scale * scale * radius / stepf;
-            }
-            const int2 id = project_coord(cx, cy, focal_x, focal_y, sp);
-            if (id.x < 0) break;
-            else if (id.x > W - 1) break;
-            if (id.y < 0) break;
-            else if (id.y > H - 1) break;
-            const float sampleDepth = zbuf[W * id.y + id.x];
-            if (sampleDepth <= sp.z + bias && sampleDepth >= sp.z - thick) {
-                if (IS_SSR) {
-                    const float r = out_rgb[W * id.y + id.x], g = out_rgb[HW + W * id.y + id.x],
-                                b = out_rgb[2 * HW + W * id.y + id.x];
-                    diffuse.x += r * de.c * de.s;
-                    diffuse.y += g * de.c * de.s;
-                    diffuse.z += b * de.c * de.s;
-                } else {
-                    occ = __fmaf_rn(de.c, de.s, occ);
-                }
-                break;
-            }
-        }
-    }
-
-    if (!IS_SSR) {
-        if (nrSamples > 0.0)
-            out0[pix_id] = fmaxf(0.0f, fminf(1.0f, 1.0 - (occ / nrSamples)));
-        else
-            out0[pix_id] = 1.0;
-    } else {
-        const float3 albedo = {out_albedo[pix_id], out_albedo[HW + pix_id], out_albedo[2 * HW + pix_id]};
-        const float3 F0 = {out_F0[pix_id], out_F0[HW + pix_id], out_F0[2 * HW + pix_id]};
-        const float metallic = out_metallic[pix_id];
-        const float3 Vd = normalize3(make_float3(-pos.x, -pos.y, -pos.z));
-        // fresnelSchlick (ssr.h:13-16): the un-suffixed literals make the base a double subtraction and
-        // the power a double pow, rounded to float before the float3 multiply
-        const float cosTheta = fmaxf(dot3(normal, Vd), 0.0000001);
-        const float fbase = fminf(fmaxf(1.0 - cosTheta, 0.000001), 1.0);
-        const float fpow = pow((double)fbase, 5.0);
-        float3 F;
-        F.x = F0.x + (1.0f - F0.x) * fpow;
-        F.y = F0.y + (1.0f - F0.y) * fpow;
-        F.z = F0.z + (1.0f - F0.z) * fpow;
-        float3 kD = {(float)(1.0 - F.x), (float)(1.0 - F.y), (float)(1.0 - F.z)};
-        kD.x *= 1.0 - metallic;
-        kD.y *= 1.0 - metallic;
-        kD.z *= 1.0 - metallic;
-        float3 gd;
-        if (nrSamples > 0.0) {
-            gd.x = M_PIf * diffuse.x * (1.0 / float(nrSamples)) * kD.x;
-            gd.y = M_PIf * diffuse.y * (1.0 / float(nrSamples)) * kD.y;
-            gd.z = M_PIf * diffuse.z * (1.0 / float(nrSamples)) * kD.z;
-            diffuse.x = gd.x * albedo.x;
-            diffuse.y = gd.y * albedo.y;
-            diffuse.z = gd.z * albedo.z;
-        } else {
-            diffuse.x = diffuse.y = diffuse.z = 0.0000001;
-            gd.x = gd.y = gd.z = 0.0000001;
-        }
-        out0[pix_id] = diffuse.x; out0[HW + pix_id] = diffuse.y; out0[2 * HW + pix_id] = diffuse.z;
-        out1[pix_id] = gd.x; out1[HW + pix_id] = gd.y; out1[2 * HW + pix_id] = gd.z;
-    }
-}
-
-__global__ void __launch_bounds__(256)
-ssr_backward_kernel(const size_t n3, const size_t n1, const float* __restrict__ grad_color,
-                    const float* __restrict__ abd, float* __restrict__ g_albedo, float* __restrict__ g_rough,
-                    float* __restrict__ g_metal)
-{
-    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
-    if (i < n3) g_albedo[i] = grad_color[i] * abd[i];
-    if (i < n1) {
-        if (g_rough) g_rough[i] = 0.f;
-        if (g_metal) g_metal[i] = 0.f;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
 // FFMA-throughput microbenchmark: the FP32-pipe roofline denominator for blend / SSAO / SSR.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters)
@@ -622,71 +399,6 @@ int gigs_geometry_chain(int32_t W, int32_t H, float fx, float fy, const float* v
     geometry_chain_kernel<<<grid, block, 0, st>>>(W, H, fx, fy, viewmatrix, -0.5f / (1.f * 1.f), make_space_kernel(3.f),
                                                   depth, normal_from_depth, depth_pos_filter);
     GIGS_LAUNCH_CHECK("geometry_chain_kernel");
-    return 0;
-}
-
-static int gi_launch(bool is_ssr, int W, int H, float fx, float fy, float radius, float bias, float thick, float delta,
-                     int step, int start, const float* normal, const float* pos, const float* rgb, const float* albedo,
-                     const float* metallic, const float* F0, float* out0, float* out1, cudaStream_t st)
-{
-    DirCounts dc = count_dirs(delta);
-    if (dc.n_phi * dc.n_theta > GI_MAX_DIRS || dc.n_phi > 4096 || dc.n_theta > 4096) {
-        set_error("GI: delta=%g gives %d x %d directions, more than the %d supported", delta, dc.n_phi, dc.n_theta,
-                  GI_MAX_DIRS);
-        return -4;
-    }
-    const size_t smem = (size_t)dc.n_phi * dc.n_theta * sizeof(DirEntry) + (dc.n_phi + dc.n_theta) * sizeof(float) + 16;
-    dim3 grid((W + TILE_X - 1) / TILE_X, (H + TILE_Y - 1) / TILE_Y), block(TILE_X, TILE_Y);
-    ProfScope ps(is_ssr ? ST_SSR : ST_SSAO, st);
-    const bool pow2 = step > 0 && (step & (step - 1)) == 0;
-    static bool attr = false;
-    if (!attr) {
-        GIGS_CUDA(cudaFuncSetAttribute(gi_march_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        GIGS_CUDA(cudaFuncSetAttribute(gi_march_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        GIGS_CUDA(cudaFuncSetAttribute(gi_march_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        GIGS_CUDA(cudaFuncSetAttribute(gi_march_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        attr = true;
-    }
-#define GI_ARGS W, H, fx, fy, radius, bias, thick, delta, step, start, dc.n_phi, dc.n_theta, normal, pos, rgb, albedo, metallic, F0, out0, out1
-    if (is_ssr) {
-        if (pow2) gi_march_kernel<true, true><<<grid, block, smem, st>>>(GI_ARGS);
-        else gi_march_kernel<true, false><<<grid, block, smem, st>>>(GI_ARGS);
-    } else {
-        if (pow2) gi_march_kernel<false, true><<<grid, block, smem, st>>>(GI_ARGS);
-        else gi_march_kernel<false, false><<<grid, block, smem, st>>>(GI_ARGS);
-    }
-#undef GI_ARGS
-    GIGS_LAUNCH_CHECK("gi_march_kernel");
-    return 0;
-}
-
-int gigs_ssao(int32_t W, int32_t H, float fx, float fy, float radius, float bias, float thick, float delta,
-              int32_t step, int32_t start, const float* normal, const float* pos, float* occlusion, void* stream)
-{
-    if (W <= 0 || H <= 0 || !normal || !pos || !occlusion) { set_error("gigs_ssao: bad arguments"); return -1; }
-    return gi_launch(false, W, H, fx, fy, radius, bias, thick, delta, step, start, normal, pos, nullptr, nullptr, nullptr,
-                     nullptr, occlusion, nullptr, (cudaStream_t)stream);
-}
-
-int gigs_ssr(int32_t W, int32_t H, float fx, float fy, float radius, float bias, float thick, float delta, int32_t step,
-             int32_t start, const float* normal, const float* pos, const float* rgb, const float* albedo,
-             const float* roughness, const float* metallic, const float* F0, float* color, float* abd, void* stream)
-{
-    (void)roughness;  // read but unused by the reference kernel as well (forward.cu:781)
-    if (W <= 0 || H <= 0 || !normal || !pos || !rgb || !albedo || !metallic || !F0 || !color || !abd) { set_error("gigs_ssr: bad arguments"); return -1; }
-    return gi_launch(true, W, H, fx, fy, radius, bias, thick, delta, step, start, normal, pos, rgb, albedo, metallic, F0,
-                     color, abd, (cudaStream_t)stream);
-}
-
-int gigs_ssr_backward(int32_t W, int32_t H, const float* grad_color, const float* abd, float* grad_albedo,
-                      float* grad_roughness, float* grad_metallic, void* stream)
-{
-    if (W <= 0 || H <= 0 || !grad_color || !abd || !grad_albedo) { set_error("gigs_ssr_backward: bad arguments"); return -1; }
-    const size_t n1 = (size_t)W * H, n3 = 3 * n1;
-    ProfScope ps(ST_SSR_BWD, (cudaStream_t)stream);
-    ssr_backward_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n3, n1, grad_color, abd, grad_albedo,
-                                                                                      grad_roughness, grad_metallic);
-    GIGS_LAUNCH_CHECK("ssr_backward_kernel");
     return 0;
 }
 

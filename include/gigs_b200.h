@@ -210,6 +210,21 @@ int gigs_ssr(int32_t W, int32_t H, float fx, float fy, float radius, float bias,
              const float* rgb, const float* albedo, const float* roughness, const float* metallic,
              const float* F0, float* color, float* abd, void* stream);
 
+/* Number of probes (one sample position -> one depth test) the SSAO/SSR march of this G-buffer has to evaluate:
+ * the reference's loop (forward.cu:691-716 / :805-846) counted up to and including the probe that ends a direction,
+ * without the pixels whose sample positions are all NaN and the zero-weight directions (theta = 0), neither of which
+ * can change the result. Measurement helper (roofline numerator); count is two device words: [0] the probes,
+ * [1] (when block_minmax != NULL) the probes whose depth window intersects the (min, max) of pos.z over the
+ * block x block pixel block they land in — block_minmax is [ceil(H/block), ceil(W/block), 2] floats. */
+int gigs_gi_count_probes(int32_t W, int32_t H, float fx, float fy, float radius, float bias, float thick,
+                         float delta, int32_t step, int32_t start, const float* normal, const float* pos,
+                         const float* block_minmax, int32_t block, uint64_t* count, void* stream);
+
+/* Tuning knobs of the march: probe pairs evaluated per inner step (1 or 2; 0 = the reference-order loop for every
+ * pixel), and whether the block (min, max) depth test runs before a probe's depth gather. Results are bit-identical
+ * for every setting. Process-wide; defaults 1, 1. */
+int gigs_gi_tune(int32_t pairs_per_step, int32_t block_test);
+
 /* Replaces SSR_BACKWARD (rasterize_points.cu:479-510). The reference's Python never calls its
  * kernel (diff_gaussian_rasterization/__init__.py:666-673); the live semantics are
  * grad_albedo = grad_color * abd, zeros for roughness/metallic, which is what this computes. */
