@@ -8,6 +8,7 @@
 // Wraps (reference file:line):
 //   CudaRasterizer::Rasterizer::forward        cuda_rasterizer/rasterizer_impl.cu:486
 //   CudaRasterizer::Rasterizer::backward       cuda_rasterizer/rasterizer_impl.cu:676
+//   CudaRasterizer::Rasterizer::lite_forward   cuda_rasterizer/rasterizer_impl.cu:338
 //   CudaRasterizer::Rasterizer::depthToNormal  cuda_rasterizer/rasterizer_impl.cu:200
 //   CudaRasterizer::Rasterizer::SSAO           cuda_rasterizer/rasterizer_impl.cu:220
 //   CudaRasterizer::Rasterizer::SSR            cuda_rasterizer/rasterizer_impl.cu:250
@@ -82,6 +83,29 @@ int ref_forward(void* c, int P, int D, int M, const float* background, int W, in
             prefiltered != 0, argmax_depth != 0, inference != 0, out_color, out_opacity, out_depth,
             out_normal, out_normal_view, out_pos, out_albedo, out_roughness, out_metallic, radii,
             debug != 0);
+        ctx->P = P; ctx->R = R; ctx->N = W * H;
+        return R;
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
+// The radiance-only rasterizer (lite_rasterize_gaussians, rasterize_points.cu:40-128). Returns num_rendered or -1.
+int ref_lite_forward(void* c, int P, int D, int M, const float* background, int W, int H,
+                     const float* means3D, const float* shs, const float* colors_precomp,
+                     const float* opacities, const float* scales, float scale_modifier,
+                     const float* rotations, const float* cov3D_precomp, const float* viewmatrix,
+                     const float* projmatrix, const float* cam_pos, float tan_fovx, float tan_fovy,
+                     int prefiltered, int argmax_depth, float* out_color, float* out_opacity,
+                     float* out_depth, int* radii)
+{
+    RefCtx* ctx = (RefCtx*)c;
+    try {
+        std::function<char*(size_t)> gf = [ctx](size_t n) { return ctx->geom.ensure(n); };
+        std::function<char*(size_t)> bf = [ctx](size_t n) { return ctx->binning.ensure(n); };
+        std::function<char*(size_t)> imf = [ctx](size_t n) { return ctx->img.ensure(n); };
+        int R = Rasterizer::lite_forward(gf, bf, imf, P, D, M, background, W, H, means3D, shs,
+            colors_precomp, opacities, scales, scale_modifier, rotations, cov3D_precomp, viewmatrix,
+            projmatrix, cam_pos, tan_fovx, tan_fovy, prefiltered != 0, argmax_depth != 0, out_color,
+            out_opacity, out_depth, radii);
         ctx->P = P; ctx->R = R; ctx->N = W * H;
         return R;
     } catch (const std::exception& e) { g_err = e.what(); return -1; }

@@ -7,7 +7,7 @@ E = torch.Tensor([])
 
 
 def ours_forward(g, cam, bg, deg=3, inference=False, argmax=False, colors_precomp=None, cov3D_precomp=None,
-                 scale_modifier=1.0, debug=False):
+                 scale_modifier=1.0, debug=False, prefiltered=False):
     W, H = cam.image_width, cam.image_height
     shs = E if colors_precomp is not None else g["shs"]
     cp = colors_precomp if colors_precomp is not None else E
@@ -17,7 +17,7 @@ def ours_forward(g, cam, bg, deg=3, inference=False, argmax=False, colors_precom
     res = dgr._C.rasterize_gaussians(bg, g["means3D"], cp, g["opacity"], g["normal"], g["albedo"], g["roughness"],
                                      g["metallic"], sc, rt, cv, shs, cam.camera_center, cam.world_view_transform,
                                      cam.full_proj_transform, scale_modifier, cam.tanfovx, cam.tanfovy, H, W, deg,
-                                     False, argmax, inference, debug)
+                                     prefiltered, argmax, inference, debug)
     names = ("num_rendered", "color", "radii", "geom", "binning", "img", "opacity", "depth", "normal", "normal_view",
              "pos", "albedo", "roughness", "metallic")
     return dict(zip(names, res))

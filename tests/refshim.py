@@ -26,6 +26,7 @@ def load():
         _lib.ref_last_error.restype = C.c_char_p
         _lib.ref_forward.restype = C.c_int
         _lib.ref_backward.restype = C.c_int
+        _lib.ref_lite_forward.restype = C.c_int
     return _lib
 
 
@@ -48,8 +49,37 @@ class RefRasterizer:
             self.lib.ref_ctx_destroy(self.ctx)
             self.ctx = None
 
+    def lite_forward(self, g, cam, bg, sh_degree=3, scale_modifier=1.0, argmax_depth=False, prefiltered=False,
+                     colors_precomp=None, cov3D_precomp=None):
+        """The reference's radiance-only rasterizer (Rasterizer::lite_forward): colour, opacity, depth, radii."""
+        dev = g["means3D"].device
+        P = g["means3D"].shape[0]
+        H, W = cam.image_height, cam.image_width
+        f = dict(dtype=torch.float32, device=dev)
+        out = dict(color=torch.zeros(3, H, W, **f), opacity=torch.zeros(1, H, W, **f), depth=torch.zeros(1, H, W, **f),
+                   radii=torch.zeros(P, dtype=torch.int32, device=dev))
+        shs = None if colors_precomp is not None else g["shs"]
+        M = shs.shape[1] if shs is not None else 0
+        scales = None if cov3D_precomp is not None else g["scales"]
+        rots = None if cov3D_precomp is not None else g["rotations"]
+        keep = [t.contiguous() if t is not None else None for t in
+                (bg, g["means3D"], shs, colors_precomp, g["opacity"], scales, rots, cov3D_precomp,
+                 cam.world_view_transform, cam.full_proj_transform, cam.camera_center)]
+        (bg_, m3, sh_, cp_, op_, sc_, rt_, cv_, vm_, pm_, cc_) = keep
+        torch.cuda.synchronize()
+        R = self.lib.ref_lite_forward(self.ctx, C.c_int(P), C.c_int(sh_degree), C.c_int(M), _p(bg_), C.c_int(W),
+                                      C.c_int(H), _p(m3), _p(sh_), _p(cp_), _p(op_), _p(sc_), C.c_float(scale_modifier),
+                                      _p(rt_), _p(cv_), _p(vm_), _p(pm_), _p(cc_), C.c_float(cam.tanfovx),
+                                      C.c_float(cam.tanfovy), C.c_int(int(prefiltered)), C.c_int(int(argmax_depth)),
+                                      _p(out["color"]), _p(out["opacity"]), _p(out["depth"]), _p(out["radii"]))
+        if R < 0:
+            raise RuntimeError("reference lite_forward failed: " + self.lib.ref_last_error().decode())
+        torch.cuda.synchronize()
+        out["num_rendered"] = R
+        return out
+
     def forward(self, g, cam, bg, sh_degree=3, scale_modifier=1.0, inference=False, argmax_depth=False,
-                colors_precomp=None, cov3D_precomp=None, debug=False):
+                colors_precomp=None, cov3D_precomp=None, debug=False, prefiltered=False):
         dev = g["means3D"].device
         P = g["means3D"].shape[0]
         H, W = cam.image_height, cam.image_width
@@ -72,8 +102,8 @@ class RefRasterizer:
         R = self.lib.ref_forward(self.ctx, C.c_int(P), C.c_int(sh_degree), C.c_int(M), _p(bg_), C.c_int(W), C.c_int(H),
                                  _p(m3), _p(sh_), _p(cp_), _p(op_), _p(nr_), _p(al_), _p(ro_), _p(me_), _p(sc_),
                                  C.c_float(scale_modifier), _p(rt_), _p(cv_), _p(vm_), _p(pm_), _p(cc_),
-                                 C.c_float(cam.tanfovx), C.c_float(cam.tanfovy), C.c_int(0), C.c_int(int(argmax_depth)),
-                                 C.c_int(int(inference)), _p(out["color"]), _p(out["opacity"]), _p(out["depth"]),
+                                 C.c_float(cam.tanfovx), C.c_float(cam.tanfovy), C.c_int(int(prefiltered)),
+                                 C.c_int(int(argmax_depth)), C.c_int(int(inference)), _p(out["color"]), _p(out["opacity"]), _p(out["depth"]),
                                  _p(out["normal"]), _p(out["normal_view"]), _p(out["pos"]), _p(out["albedo"]),
                                  _p(out["roughness"]), _p(out["metallic"]), _p(out["radii"]), C.c_int(int(debug)))
         if R < 0:
