@@ -231,6 +231,28 @@ __device__ __forceinline__ float3 sub3(const float3& a, const float3& b) { retur
 __device__ __forceinline__ float3 add3(const float3& a, const float3& b) { return make_float3(a.x + b.x, a.y + b.y, a.z + b.z); }
 
 // ---------------------------------------------------------------------------------------------
+// L2 norms with the summation order of torch's CUDA reduction kernels (no fused multiply-add), so that the getters
+// fused into our kernels return the bits of F.normalize / torch.norm (measured against torch 2.11 on B200 over
+// 300k random vectors: 0 differing values; tools/raw_getter_check.py):
+//   reduction over a contiguous inner dim of 4 / 3 (rotation [P,4], normal [P,3], rays [HW,3]):
+//     threads along the reduced dim take a strided share, then a shuffle tree: (x0^2 + x2^2) + (x1^2 + x3^2),
+//     (x0^2 + x2^2) + x1^2
+//   reduction over the outer dim of a [3,H,W] map: one thread sums in order, (x0^2 + x1^2) + x2^2
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float torch_norm_inner4(float x0, float x1, float x2, float x3)
+{
+    return sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x0, x0), __fmul_rn(x2, x2)), __fadd_rn(__fmul_rn(x1, x1), __fmul_rn(x3, x3))));
+}
+__device__ __forceinline__ float torch_norm_inner3(float x0, float x1, float x2)
+{
+    return sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x0, x0), __fmul_rn(x2, x2)), __fmul_rn(x1, x1)));
+}
+__device__ __forceinline__ float torch_norm_outer3(float x0, float x1, float x2)
+{
+    return sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x0, x0), __fmul_rn(x1, x1)), __fmul_rn(x2, x2)));
+}
+
+// ---------------------------------------------------------------------------------------------
 // PTX: mbarrier + bulk async copy (TMA, SASS UBLKCP) + vector reductions
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

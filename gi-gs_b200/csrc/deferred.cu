@@ -67,7 +67,7 @@ __device__ __forceinline__ float srgb_to_linear_px(float s)
 // F.normalize(x, dim=0) where ||x|| > 0, x otherwise (gaussian_renderer/__init__.py:176-184)
 __device__ __forceinline__ float3 normalize_where_positive(float3 v)
 {
-    const float n = sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
+    const float n = torch_norm_outer3(v.x, v.y, v.z);
     if (n > 0.f) {
         const float d = fmaxf(n, 1e-12f);
         return make_float3(v.x / d, v.y / d, v.z / d);
@@ -94,7 +94,7 @@ __device__ __forceinline__ float3 view_dir_of(const DeferParams& p, const float*
 {
     // view_dirs = -(normalize(ray)[None,:] * c2w[:3,:3]).sum(-1)   (train.py:329-337)
     float3 r = make_float3(p.rays[3 * id], p.rays[3 * id + 1], p.rays[3 * id + 2]);
-    const float n = fmaxf(sqrtf(r.x * r.x + r.y * r.y + r.z * r.z), 1e-12f);
+    const float n = fmaxf(torch_norm_inner3(r.x, r.y, r.z), 1e-12f);
     r = make_float3(r.x / n, r.y / n, r.z / n);
     return make_float3(-(C[0] * r.x + C[1] * r.y + C[2] * r.z), -(C[3] * r.x + C[4] * r.y + C[5] * r.z),
                        -(C[6] * r.x + C[7] * r.y + C[8] * r.z));

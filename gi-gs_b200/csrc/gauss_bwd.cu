@@ -389,7 +389,7 @@ gaussian_backward_body(const int idx, float* __restrict__ s_row,
         float3 sc = {scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]};
         if (RAW) {   // the getters, as preprocess_kernel<RAW> applies them
             sc = make_float3(expf(sc.x), expf(sc.y), expf(sc.z));
-            const float qn = fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);
+            const float qn = fmaxf(torch_norm_inner4(q.x, q.y, q.z, q.w), 1e-12f);
             q = make_float4(q.x / qn, q.y / qn, q.z / qn, q.w / qn);
         }
         const float r = q.x, x = q.y, y = q.z, z = q.w;

@@ -85,9 +85,19 @@ __device__ __forceinline__ void cov3d_from_scale_rot(const float3 scale, float m
     S.m[2][2] = mod * scale.z;
     // quaternion used as given (the reference does not renormalise, forward.cu:136)
     float r = rot.x, x = rot.y, y = rot.z, z = rot.w;
-    Mat3 R = mat3_cols(1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y),
-                       2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x),
-                       2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y));
+    // R = (1 - 2(yy+zz), 2(xy-rz), 2(xz+ry) | 2(xy+rz), 1 - 2(xx+zz), 2(yz-rx) | 2(xz-ry), 2(yz+rx), 1 - 2(xx+yy))
+    // (forward.cu:140-144). The sums of two products are where the compiler has a choice (which product is rounded,
+    // which is fused) and it takes it per context: the two instantiations of this kernel came out different. Pinned
+    // to what the reference's build does (read off the SASS; 6M Gaussians bit-exact against it): the shared products
+    // yy, zz, xz, rz, rx are rounded, the other one of each sum goes into the fma.
+    const float yy = __fmul_rn(y, y), zz = __fmul_rn(z, z), xz = __fmul_rn(x, z), rz = __fmul_rn(r, z), rx = __fmul_rn(r, x);
+    const float s_yz = __fadd_rn(yy, zz), s_xz = __fmaf_rn(x, x, zz), s_xy = __fmaf_rn(x, x, yy);
+    const float d_xy_rz = __fmaf_rn(x, y, -rz), a_xy_rz = __fmaf_rn(x, y, rz);
+    const float a_xz_ry = __fmaf_rn(r, y, xz), d_xz_ry = __fmaf_rn(-r, y, xz);
+    const float d_yz_rx = __fmaf_rn(y, z, -rx), a_yz_rx = __fmaf_rn(y, z, rx);
+    Mat3 R = mat3_cols(__fsub_rn(1.f, __fadd_rn(s_yz, s_yz)), __fadd_rn(d_xy_rz, d_xy_rz), __fadd_rn(a_xz_ry, a_xz_ry),
+                       __fadd_rn(a_xy_rz, a_xy_rz), __fsub_rn(1.f, __fadd_rn(s_xz, s_xz)), __fadd_rn(d_yz_rx, d_yz_rx),
+                       __fadd_rn(d_xz_ry, d_xz_ry), __fadd_rn(a_yz_rx, a_yz_rx), __fsub_rn(1.f, __fadd_rn(s_xy, s_xy)));
     Mat3 M = mat3_mul(S, R);
     Mat3 Sigma = mat3_mul(mat3_transpose(M), M);
     cov3D[0] = Sigma.m[0][0];
@@ -204,7 +214,7 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
                 float4 rot = *reinterpret_cast<const float4*>(rotations + 4 * idx);
                 if (RAW) {
                     sc = make_float3(expf(sc.x), expf(sc.y), expf(sc.z));
-                    const float qn = fmaxf(sqrtf(rot.x * rot.x + rot.y * rot.y + rot.z * rot.z + rot.w * rot.w), 1e-12f);
+                    const float qn = fmaxf(torch_norm_inner4(rot.x, rot.y, rot.z, rot.w), 1e-12f);
                     rot = make_float4(rot.x / qn, rot.y / qn, rot.z / qn, rot.w / qn);
                 }
                 cov3d_from_scale_rot(sc, scale_modifier, rot, cov_local);
@@ -265,7 +275,7 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
                 float3 al = {albedo[3 * idx], albedo[3 * idx + 1], albedo[3 * idx + 2]};
                 float ro = roughness[idx], me = metallic[idx];
                 if (RAW) {
-                    const float nn = fmaxf(sqrtf(nr.x * nr.x + nr.y * nr.y + nr.z * nr.z), 1e-12f);
+                    const float nn = fmaxf(torch_norm_inner3(nr.x, nr.y, nr.z), 1e-12f);
                     nr = make_float3(nr.x / nn, nr.y / nn, nr.z / nn);
                     al = make_float3(act_sigmoid(al.x), act_sigmoid(al.y), act_sigmoid(al.z));
                     ro = act_sigmoid(ro);

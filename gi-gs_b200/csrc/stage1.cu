@@ -27,7 +27,7 @@ constexpr int ST_S1_NORMALS = 29, ST_S1_NORMALS_BWD = 30;
 
 __device__ __forceinline__ float3 s1_normalize_where_positive(float3 v)
 {
-    const float n = sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
+    const float n = torch_norm_outer3(v.x, v.y, v.z);
     if (n > 0.f) {
         const float d = fmaxf(n, 1e-12f);
         return make_float3(v.x / d, v.y / d, v.z / d);
