@@ -32,20 +32,24 @@ STAGE_NAMES = ["preprocess", "emit_keys", "radix_sort", "tile_ranges", "blend_fo
                "gaussian_backward", "geometry_chain", "ssao", "ssr", "shade_forward", "shade_backward", "median3x3",
                "median3x3_backward", "bilateral3x3", "depth_to_normal", "ssr_backward", "dist2", "deferred_shade",
                "deferred_loss", "deferred_backward", "param_grad", "radix_sort_pass", "depth_sort", "light_build",
-               "light_backward", "adam", "image_loss", "normal_loss", "stage1_normals", "stage1_normals_backward"]
+               "light_backward", "adam", "image_loss", "normal_loss", "stage1_normals", "stage1_normals_backward",
+               "deferred_backward_kernel", "peer_allreduce"]
 # kernels launched per stage record (radix_sort: histogram + scan + passes, filled in at run time)
 STAGE_LAUNCHES = {"preprocess": 2, "emit_keys": 1, "tile_ranges": 1, "blend_forward": 1, "blend_backward": 1,
                   "gaussian_backward": 1, "geometry_chain": 1, "ssao": 1, "ssr": 1, "shade_forward": 1,
                   "shade_backward": 1, "median3x3": 1, "median3x3_backward": 1, "bilateral3x3": 1,
                   "depth_to_normal": 1, "ssr_backward": 1, "dist2": 9, "deferred_shade": 1, "deferred_loss": 1,
-                  "deferred_backward": 4, "param_grad": 1, "radix_sort_pass": 0, "light_build": 2, "light_backward": 6, "adam": 1, "image_loss": 3, "normal_loss": 3}
+                  "deferred_backward": 4, "param_grad": 1, "radix_sort_pass": 0, "light_build": 2, "light_backward": 6,
+                  "adam": 1, "image_loss": 3, "normal_loss": 3,
+                  # nested inside another stage record (counted there)
+                  "deferred_backward_kernel": 0, "peer_allreduce": 1}
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--P", type=int, default=300000)
     ap.add_argument("--W", type=int, default=800)
@@ -128,32 +132,46 @@ def run_reference(args):
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import cpu_baseline as CB
-    from gigs import scene, shade
+    from gigs import scene          # synthetic-input generators only: this arm maps none of the repo's CUDA libraries
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     raw = scene.make_scene(args.P, seed=0, regime="trained")
     g = scene.activate(raw)
     light = scene.make_light(0)
-    lut = shade.make_brdf_lut()
+    lut = scene.make_brdf_lut()
     gi = dict(GI_BASE, start=args.start)
-    vals, sample = [], ""
-    for i in range(args.warmup + args.steps):
+    vals, walls, sample = [], [], ""
+    # each step is a bounded sample of the frame (oracle/cpu_baseline.py) that takes seconds on the host cores; the run
+    # is capped at ~4 minutes of samples whatever --steps says (the count actually timed is reported)
+    t_begin = time.perf_counter()
+    n_w = min(args.warmup, 1)
+    n_s = max(1, min(args.steps, 12))
+    for i in range(n_w + n_s):
         cam = scene.orbit_camera(i % 8, 8, args.W, args.H)
         r = CB.cpu_step_sample(g, cam, torch.zeros(3), light, lut, gi, seed=i)
-        if i >= args.warmup:
+        if i >= n_w:
             vals.append(r["est_frame_s"])
+            walls.append(r["wall_s"])
         sample = r["sample"]
+        if i >= n_w and time.perf_counter() - t_begin > 240.0:
+            break
     ms = 1e3 * sum(vals) / len(vals)
     v = 1e3 / ms
     line = {"impl": "reference", "metric": "fwd+bwd G-buffer+GI+PBR frames/s", "value": v, "unit": "frames/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "n_gpus": args.gpus, "steps": len(vals), "warmup": n_w, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, 1),
+            "extrapolated": True,
+            "sample_wall_ms_per_step": 1e3 * sum(walls) / len(walls),
+            "steps_requested": args.steps,
             "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
             "note": "the reference ships no CPU implementation of this path; this arm times the PyTorch-CPU "
-                    "transcription (oracle/) on a bounded sample extrapolated to the full frame"}
+                    "transcription (oracle/) on a bounded sample of the frame (sample_wall_ms_per_step is what ran) and "
+                    "EXTRAPOLATES it to the full frame (ms_per_step, value): an estimate of a CPU baseline, not a "
+                    "measurement of two comparable arms. The measured comparison against the reference's own CUDA "
+                    "kernels on the same GPU is the ref_cuda block of the other arm's line"}
     print(json.dumps(line), flush=True)
 
 
@@ -294,6 +312,7 @@ def run_ours(args):
                         "than the 100 ms sampling period)")
             clocks = sampler.stop(t_wall0, t_wall1)
             clocks["window"] = note if clocks.get("samples") else clocks.get("window")
+        timed.last_local_ms = tot_ms
         t = torch.tensor([tot_ms], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -343,9 +362,58 @@ def run_ours(args):
         return float(t.item())
 
     gi = dict(GI_BASE, start=args.start)
+
+    def exchange_check():
+        """N > 1, once, untimed: the exchanged gradient must be the sum of the ranks' gradients. Each rank checksums
+        its partial gradient (float64 sum and sum of squares weighted by position) before the exchange; NCCL sums the
+        checksums; after the exchange every rank's buffer must carry that checksum and all ranks the same bits."""
+        params = ctx["params"]
+        k = rank % K_cams
+        params.zero_grad(fused_only=True)
+        ev = torch.cuda.Event()
+        gstep.training_step(params, cams[k], ctx["light"], lut, rays, gts[k], bg, gi, loss_scale=1.0 / world,
+                            light_ready=ev, brdf_tv_weight=1.0)
+        spans = [sp for sp in params._merged_dirty()]
+        w = None
+        before = torch.zeros(2, dtype=torch.float64, device=dev)
+        for lo, hi in spans:
+            x = params.flat_grad[lo:hi].double()
+            w = torch.arange(hi - lo, device=dev, dtype=torch.float64) % 1021.0 + 1.0
+            before[0] += x.sum()
+            before[1] += (x * w).sum()
+        dist.all_reduce(before, op=dist.ReduceOp.SUM)
+        params.begin_light_all_reduce(ev)
+        params.all_reduce_grads(fused_only=True)
+        torch.cuda.synchronize()
+        after = torch.zeros(2, dtype=torch.float64, device=dev)
+        bits = torch.zeros(1, dtype=torch.int64, device=dev)
+        for lo, hi in spans:
+            x = params.flat_grad[lo:hi]
+            w = torch.arange(hi - lo, device=dev, dtype=torch.float64) % 1021.0 + 1.0
+            after[0] += x.double().sum()
+            after[1] += (x.double() * w).sum()
+            bits += x.view(torch.int32).long().sum()
+        allbits = [torch.zeros_like(bits) for _ in range(world)]
+        dist.all_gather(allbits, bits)
+        scale = float(before.abs().max()) + 1e-30
+        err = float((after - before).abs().max()) / scale
+        same = all(int(b.item()) == int(allbits[0].item()) for b in allbits)
+        return {"relative_checksum_error": err, "identical_bits_on_all_ranks": same, "ok": bool(err < 1e-5 and same),
+                "floats_exchanged": int(sum(hi - lo for lo, hi in spans)),
+                "path": "gigs_peer_allreduce" if getattr(params, "_peer", None) is not None else "nccl"}
+
+    allreduce_check = exchange_check() if world > 1 else None
     tot_ms, clocks = timed(gi, args.steps, max(args.warmup, 3), sampler=sampler)
     ms_step = tot_ms / args.steps
     value = world * 1e3 / ms_step
+    per_rank = None
+    if world > 1:
+        # every rank's own device time per step (the value above is the max): is the step bound by the slowest view?
+        mine = torch.tensor([timed.last_local_ms / args.steps], device=dev, dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        vals_r = [float(t.item()) for t in allr]
+        per_rank = {"ms_per_step_min": min(vals_r), "ms_per_step_mean": sum(vals_r) / world, "ms_per_step_max": max(vals_r)}
     e2e_ms = timed_e2e(gi, args.steps, 3)
     e2e_val = world * args.steps * 1e3 / e2e_ms
     e2e_sync_ms, _ = timed(gi, args.steps, 2, e2e=True)      # same, but the host blocks on every step's loss
@@ -384,7 +452,97 @@ def run_ours(args):
                     "blocking_readback_value": world * args.steps * 1e3 / e2e_sync_ms,
                     "with_l2_flush_inside_region": world * args.steps * 1e3 / e2e_flush_ms}}
 
+    if allreduce_check is not None:
+        line["allreduce_check"] = allreduce_check
+    if per_rank is not None:
+        per_rank["exchange_kernel_ms"] = stage_ms.get("peer_allreduce")
+        per_rank["note"] = ("device time of each rank's own steps (value uses the max over ranks); exchange_kernel_ms = "
+                            "gigs_peer_allreduce launches of one step on rank 0, barrier waits for the slowest rank included")
+        line["per_rank"] = per_rank
+
+    def ev_all(fn, reps, warm=1):
+        """max over ranks of the device time of fn(), barrier on both sides"""
+        for _ in range(warm):
+            fn()
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(t.item())
+
+    multi = {}
+    if not args.no_extras:
+        # ---- BASELINE configs[3] (C4): a K-view training step, views sharded over the ranks (strong scaling: K is
+        # fixed, each rank renders K / N views, then ONE gradient exchange) ----
+        from gigs import frame as gframe
+        gi8 = dict(GI_BASE, start=8)
+        for K in (8, 32):
+            try:
+                cams_k = [scene.orbit_camera(k, K, args.W, args.H).to(dev) for k in range(K)]
+                gk = torch.Generator().manual_seed(100 + K)
+                mine = list(range(rank, K, world))
+                gts_k = [torch.rand(3, args.H, args.W, generator=gk).to(dev) if k in mine else None for k in range(K)]
+
+                def c4_step():
+                    gstep.multi_view_step(params, cams_k, light, lut, lambda c: rays, gts_k, bg, gi, rank=rank,
+                                          world=world, brdf_tv_weight=1.0)
+                ms = ev_all(c4_step, 3)
+                multi[f"c4_k{K}"] = {"value": K * 1e3 / ms, "unit": "views/s", "ms_per_step": ms, "views_per_step": K,
+                                     "scaling": "strong", "gi_start": args.start,
+                                     "note": "one K-view PBR-stage training step (loss = mean over K views), views sharded "
+                                             "round-robin over the ranks, one gradient exchange per step"}
+                del cams_k, gts_k
+            except Exception as ex:
+                multi[f"c4_k{K}"] = {"failed": f"{type(ex).__name__}: {ex}"}
+        # ---- BASELINE configs[4] (C5): relight sweep as relight.py runs it: a 2k lat-long HDR map (host) ->
+        # latlong_to_cubemap(256) -> build_mips -> 200 test views forward only, camera-sharded, GI march running ----
+        try:
+            from gigs import light as glight
+            ghdr = torch.Generator().manual_seed(5)
+            hdr_host = (torch.rand(1024, 2048, 3, generator=ghdr) ** 4 * 8.0).pin_memory()
+            g_act = scene.activate(raw, dev)
+            for (Wv, Hv, tag) in ((800, 800, "800"), (3840, 2160, "4k")):
+                V = 200
+                my_views = gstep.shard_views(V, rank, world)
+                cams_v = [scene.orbit_camera(k, V, Wv, Hv).to(dev) for k in my_views]
+                rays_v = scene.canonical_rays(cams_v[0], dev)
+                barrier()
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e2 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                base = glight.latlong_to_cubemap(hdr_host.to(dev, non_blocking=True), [256, 256])
+                pl = glight.PrefilteredLight(base)
+                pl.build()
+                e1.record()
+                for c in cams_v:
+                    gframe.pbr_frame_eval(g_act, c, pl, lut, rays_v, bg, gi8, inference=True)
+                e2.record()
+                torch.cuda.synchronize()
+                t = torch.tensor([e0.elapsed_time(e2), e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+                if world > 1:
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                multi[f"c5_relight_{tag}"] = {"value": V * 1e3 / float(t[0]), "unit": "views/s", "views": V,
+                                              "total_ms": float(t[0]), "light_setup_ms": float(t[1]),
+                                              "resolution": [Wv, Hv], "gi_start": 8, "scaling": "strong",
+                                              "note": "H2D of a 1024x2048 HDR map + latlong_to_cubemap(256) + filter "
+                                                      "operators + build_mips (light_setup_ms, every rank) then the "
+                                                      "rank's share of 200 views: G-buffer + SSAO + shading + SSR"}
+                del pl, base, cams_v, rays_v
+                gframe._workspaces.clear()
+                torch.cuda.empty_cache()
+            del g_act
+        except Exception as ex:
+            multi["c5_relight"] = {"failed": f"{type(ex).__name__}: {ex}"}
+
     if rank == 0:
+        if multi:
+            line.setdefault("variants", {}).update(multi)
         # ---- roofline of the dominant kernel -------------------------------------------------------
         k = (0) % K_cams
         g = params.activated()
@@ -426,6 +584,7 @@ def run_ours(args):
             "deferred_shade": ("hbm", 129 * N),
             "deferred_loss": ("hbm", 63 * N),
             "deferred_backward": ("hbm", 108 * N),
+            "deferred_backward_kernel": ("hbm", 108 * N),
         }
         rooflines = {}
         for nm, (bound, amount) in alg.items():
@@ -439,14 +598,11 @@ def run_ours(args):
                     ach = amount / per_launch_s / 1e12
                     rooflines[nm] = {"bound": "fp32", "achieved": ach, "peak": peak_tf.value, "unit": "TFLOP/s",
                                      "frac": ach / peak_tf.value if peak_tf.value else None, "ms": per_launch_s * 1e3}
-        # dominant KERNEL = largest per-launch time among the single-kernel stages (the sort stage is 8 launches;
-        # its pass kernel is listed on its own as radix_sort_pass)
-        per_launch = {nm: stage_ms[nm] / max(stage_calls[nm], 1) for nm in stage_ms if nm != "radix_sort"}
-        # the deferred_backward STAGE is 5 launches: a memset, deferred_backward_kernel and three texel_fold kernels; the
-        # main kernel is 89 % of it (profiles/r1h_launch_list_summary.txt: 1403.7 us / 9 launches = 156 us against
-        # 3 x 5.4 us of folds and the clear) — compare KERNELS when picking the dominant one
-        if "deferred_backward" in per_launch:
-            per_launch["deferred_backward"] *= 0.89
+        # dominant KERNEL = largest per-launch time among the stage records that hold exactly ONE kernel launch
+        # (multi-launch stages are represented by their main kernel: radix_sort by radix_sort_pass, deferred_backward by
+        # deferred_backward_kernel, which has its own event pair inside the stage)
+        per_launch = {nm: stage_ms[nm] / max(stage_calls[nm], 1) for nm in stage_ms
+                      if STAGE_LAUNCHES.get(nm, 1) == 1 or nm in ("deferred_backward_kernel", "radix_sort_pass")}
         dom = max(per_launch, key=lambda s2: per_launch[s2])
         rf = dict(rooflines.get(dom, {"bound": "fp32", "achieved": None, "peak": peak_tf.value, "unit": "TFLOP/s",
                                       "frac": None}))
@@ -487,18 +643,33 @@ def run_ours(args):
                 t8, _ = timed(gi8, max(5, args.steps // 2), 3)
                 ms8 = t8 / max(5, args.steps // 2)
                 st8, _c = staged(gi8, 3)
-                pix = args.W * args.H
-                probes = 512.0 * 8 * pix
+                # probes the march has to evaluate on THIS G-buffer (gigs_gi_count_probes: the reference loop's probes
+                # up to the one that ends each direction, without NaN pixels and zero-weight directions), not the
+                # 512 x 8 upper bound
+                ws8 = params.last_workspace
+                fx8, fy8 = args.W / (2 * cams[0].tanfovx), args.H / (2 * cams[0].tanfovy)
+                cnt = torch.zeros(2, dtype=torch.int64, device=dev)
+                probes = {}
+                for nm, nrm in (("ssao", "normal_view"), ("ssr", "ssr_normal")):
+                    _lib.check(L.gigs_gi_count_probes(args.W, args.H, fx8, fy8, gi8["radius"], gi8["bias"], gi8["thick"],
+                                                      gi8["delta"], gi8["step"], 8, ws8.map(nrm).data_ptr(),
+                                                      ws8.map("depth_pos").data_ptr(), None, 0, cnt.data_ptr(),
+                                                      torch.cuda.current_stream().cuda_stream), "gigs_gi_count_probes")
+                    torch.cuda.synchronize()
+                    probes[nm] = float(cnt[0].item())
                 v8 = {"value": 1e3 / ms8, "unit": "frames/s", "ms_per_step": ms8, "gi_start": 8,
-                      "stage_ms": {k2: st8.get(k2) for k2 in ("ssao", "ssr")}}
-                for nm, fl in (("ssao", 30.0), ("ssr", 40.0)):
+                      "stage_ms": {k2: st8.get(k2) for k2 in ("ssao", "ssr")}, "probes": probes,
+                      "probes_upper_bound": 512.0 * 8 * args.W * args.H}
+                for nm in ("ssao", "ssr"):
                     if st8.get(nm):
-                        ach = fl * probes / (st8[nm] * 1e-3) / 1e12
-                        v8[nm + "_roofline"] = {"bound": "fp32", "achieved": ach, "peak": peak_tf.value,
-                                                "unit": "TFLOP/s", "frac": ach / peak_tf.value if peak_tf.value else None,
-                                                "note": "upper bound on probes (512 dirs x 8 steps per pixel, early "
-                                                        "exits not counted)"}
-                line["variants"] = {"gi_start8": v8}
+                        ach = 30.0 * probes[nm] / (st8[nm] * 1e-3) / 1e12
+                        rooflines[nm] = {"bound": "fp32", "achieved": ach, "peak": peak_tf.value, "unit": "TFLOP/s",
+                                         "frac": ach / peak_tf.value if peak_tf.value else None, "ms": st8[nm],
+                                         "probes": probes[nm], "config": "variants.gi_start8",
+                                         "note": "30 flop per EXECUTED probe of the reference's arithmetic (15 mul + 3 add "
+                                                 "sample position, 1 add, 2 div, 2 fma, 2 round, 2 add window, compares "
+                                                 "not counted)"}
+                line.setdefault("variants", {})["gi_start8"] = v8
                 # ---- the same frame with the light given as its trainable base cubemap: CubemapLight.build_mips
                 # (GGX / cosine prefilter of all mip levels) before the frame and its backward after, every step, as
                 # train.py:340 does (the headline keeps the light textures as inputs) ----
@@ -683,6 +854,12 @@ def ref_cuda_point(args, params, cam, bg, dev):
             a = (W, H, fx, fy, 0.8, 0.01, 0.05, 0.0625, 16, start, nv, pos)
             out[f"ref_ssao_start{start}_ms"] = ev_time(lambda: refshim.ssao(*a), 3)
             out[f"ours_ssao_start{start}_ms"] = ev_time(lambda: dgr._C.SSAO(*a), 3)
+        rgb = torch.rand(3, H, W, device=dev)
+        F0 = (1.0 - res[13]) * 0.04 + res[11] * res[13]
+        for start in (64, 8):
+            a = (W, H, fx, fy, 0.8, 0.01, 0.05, 0.0625, 16, start, nv, pos, rgb, res[11], res[12], res[13], F0)
+            out[f"ref_ssr_start{start}_ms"] = ev_time(lambda: refshim.ssr(*a), 3)
+            out[f"ours_ssr_start{start}_ms"] = ev_time(lambda: dgr._C.SSR(*a), 3)
         out["note"] = ("reference = /root/reference kernels compiled unmodified for sm_100a (oracle/Makefile), "
                        "launched through oracle/ref_shim.cu; reference timings include its cudaMemcpy D2H sync "
                        "and this shim's device synchronisations; upstream gradients dense (all 7 maps)")

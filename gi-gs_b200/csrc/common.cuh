@@ -60,7 +60,8 @@ int ensure_dynamic_smem(const void* kernel, int bytes);
 enum Stage : int {
     ST_PREPROCESS = 0, ST_EMIT_KEYS, ST_SORT, ST_RANGES, ST_BLEND_FWD, ST_BLEND_BWD, ST_GAUSS_BWD, ST_GEOM_CHAIN,
     ST_SSAO, ST_SSR, ST_SHADE_FWD, ST_SHADE_BWD, ST_MEDIAN, ST_MEDIAN_BWD, ST_BILATERAL, ST_D2N, ST_SSR_BWD, ST_DIST2,
-    ST_DEFER_SHADE, ST_DEFER_LOSS, ST_DEFER_BWD, ST_PARAM_GRAD, ST_SORT_PASS, ST_DEPTH_SORT, ST_CUBEMAP, ST_CUBEMAP_BWD
+    ST_DEFER_SHADE, ST_DEFER_LOSS, ST_DEFER_BWD, ST_PARAM_GRAD, ST_SORT_PASS, ST_DEPTH_SORT, ST_CUBEMAP, ST_CUBEMAP_BWD,
+    ST_DEFER_BWD_KERNEL = 31, ST_PEER_ALLREDUCE = 32
 };
 int prof_begin(int stage, cudaStream_t st);   // returns a token (<0 when profiling is off)
 void prof_end(int token, cudaStream_t st);

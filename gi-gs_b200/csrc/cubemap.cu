@@ -778,7 +778,61 @@ inline char* at(void* ws, uint64_t off) { return reinterpret_cast<char*>(ws) + o
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------
+// latlong_to_cubemap (relight.py:92-112, render.py:64-84): every cube texel looks its direction up in an
+// equirectangular HDR map, (u, v) = (atan2(x, -z) / 2pi + 0.5, acos(clamp(y)) / pi), bilinear, both axes wrapping
+// (the reference samples with nvdiffrast's dr.texture(filter_mode="linear"), whose default boundary mode is "wrap":
+// texel centres at (i + 0.5) / size).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+cm_latlong_kernel(const int EH, const int EW, const int Cn, const float* __restrict__ env, const int R,
+                  float* __restrict__ cube)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= 6 * R * R) return;
+    const int x = i % R, y = (i / R) % R, s = i / (R * R);
+    const float gx = -1.0f + (float)(2 * x + 1) / (float)R, gy = -1.0f + (float)(2 * y + 1) / (float)R;
+    float3 d;
+    switch (s) {
+        case 0: d = make_float3(1.f, -gy, -gx); break;
+        case 1: d = make_float3(-1.f, -gy, gx); break;
+        case 2: d = make_float3(gx, 1.f, gy); break;
+        case 3: d = make_float3(gx, -1.f, -gy); break;
+        case 4: d = make_float3(gx, -gy, 1.f); break;
+        default: d = make_float3(-gx, -gy, -1.f); break;
+    }
+    const float n = fmaxf(torch_norm_inner3(d.x, d.y, d.z), 1e-12f);   // F.normalize(dim=-1)
+    d = make_float3(d.x / n, d.y / n, d.z / n);
+    const float tu = atan2f(d.x, -d.z) / (2.0f * 3.14159265358979323846f) + 0.5f;
+    const float tv = acosf(fminf(fmaxf(d.y, -1.0f), 1.0f)) / 3.14159265358979323846f;
+    const float fxp = tu * (float)EW - 0.5f, fyp = tv * (float)EH - 0.5f;
+    const float x0f = floorf(fxp), y0f = floorf(fyp);
+    const float ax = fxp - x0f, ay = fyp - y0f;
+    int x0 = (int)x0f % EW, y0 = (int)y0f % EH;
+    if (x0 < 0) x0 += EW;
+    if (y0 < 0) y0 += EH;
+    const int x1 = (x0 + 1 == EW) ? 0 : x0 + 1, y1 = (y0 + 1 == EH) ? 0 : y0 + 1;
+    const float w00 = (1.f - ax) * (1.f - ay), w10 = ax * (1.f - ay), w01 = (1.f - ax) * ay, w11 = ax * ay;
+    const float* p00 = env + ((size_t)y0 * EW + x0) * Cn;
+    const float* p10 = env + ((size_t)y0 * EW + x1) * Cn;
+    const float* p01 = env + ((size_t)y1 * EW + x0) * Cn;
+    const float* p11 = env + ((size_t)y1 * EW + x1) * Cn;
+    float* o = cube + (size_t)i * Cn;
+    for (int c = 0; c < Cn; ++c) o[c] = p00[c] * w00 + p10[c] * w10 + p01[c] * w01 + p11[c] * w11;
+}
+
 extern "C" {
+
+int gigs_latlong_to_cubemap(int32_t env_h, int32_t env_w, int32_t channels, const float* env, int32_t res, float* cube,
+                             void* stream)
+{
+    if (env_h <= 0 || env_w <= 0 || channels <= 0 || res <= 0 || res > 4096 || !env || !cube) { set_error("gigs_latlong_to_cubemap: bad arguments"); return -1; }
+    const int n = 6 * res * res;
+    ProfScope ps(ST_CUBEMAP, (cudaStream_t)stream);
+    cm_latlong_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(env_h, env_w, channels, env, res, cube);
+    GIGS_LAUNCH_CHECK("cm_latlong_kernel");
+    return 0;
+}
 
 int gigs_cubemap_table(int32_t res, float* table, void* stream)
 {

@@ -664,8 +664,9 @@ int gigs_frame_forward(GigsFrame* f)
                                     (float*)(m + FL.depth_pos), f->stream)) return e;
     if (f->indirect) {
         if (int e = gigs_ssao(W, H, fx, fy, f->radius, f->bias, f->thick, f->delta, f->step, f->start,
-                              (float*)(m + FL.normal_view), (float*)(m + FL.depth_pos), (float*)(m + FL.occlusion), f->stream))
-            return e;
+                              (float*)(m + FL.normal_view), (float*)(m + FL.depth_pos), (float*)(m + FL.occlusion),
+                              m + FL.tex_scratch, gigs_gi_scratch_bytes(W, H), f->stream))
+            return e;   // the march's scratch: the head of the texel-gradient scratch, which only the backward uses
     }
     DeferParams p;
     fill_defer(f, FL, p, false);
@@ -677,7 +678,8 @@ int gigs_frame_forward(GigsFrame* f)
     }
     if (int e = gigs_ssr(W, H, fx, fy, f->radius, f->bias, f->thick, f->delta, f->step, f->start, p.ssr_normal,
                          (float*)(m + FL.depth_pos), p.linear_rgb, p.albedo, p.rough_remap, p.metal_used, p.F0,
-                         (float*)(m + FL.ssr_color), (float*)(m + FL.ssr_abd), f->stream))
+                         (float*)(m + FL.ssr_color), (float*)(m + FL.ssr_abd), m + FL.tex_scratch,
+                         gigs_gi_scratch_bytes(W, H), f->stream))
         return e;
     if (f->gt_ready_event) GIGS_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)f->gt_ready_event, 0));
     {
@@ -725,9 +727,12 @@ int gigs_frame_backward(GigsFrame* f)
         static const int variant = getenv("GIGS_DFB") ? atoi(getenv("GIGS_DFB")) : 3;  // 3 CTAs/SM measured best (203 vs 214 us)
         const int per_sm = variant == 3 ? 3 : (variant == 4 ? 4 : 2);
         const int blocks = ntiles < 148 * per_sm * 2 ? ntiles : 148 * per_sm * 2;
-        if (variant == 3) deferred_backward_kernel<3><<<blocks, dim3(DF_TW, DF_TH), smem, st>>>(p, tiles_x, ntiles);
-        else if (variant == 4) deferred_backward_kernel<4><<<blocks, dim3(DF_TW, DF_TH), smem, st>>>(p, tiles_x, ntiles);
-        else deferred_backward_kernel<2><<<blocks, dim3(DF_TW, DF_TH), smem, st>>>(p, tiles_x, ntiles);
+        {
+            ProfScope pk(ST_DEFER_BWD_KERNEL, st);   // the kernel alone (the stage around it adds the clear and the folds)
+            if (variant == 3) deferred_backward_kernel<3><<<blocks, dim3(DF_TW, DF_TH), smem, st>>>(p, tiles_x, ntiles);
+            else if (variant == 4) deferred_backward_kernel<4><<<blocks, dim3(DF_TW, DF_TH), smem, st>>>(p, tiles_x, ntiles);
+            else deferred_backward_kernel<2><<<blocks, dim3(DF_TW, DF_TH), smem, st>>>(p, tiles_x, ntiles);
+        }
         GIGS_LAUNCH_CHECK("deferred_backward_kernel");
         for (int k = 0; k < slots; ++k) {
             texel_fold_kernel<<<(fold_n[k] + 255) / 256, 256, 0, st>>>(

@@ -10,8 +10,10 @@
 //   (3) a second barrier ("my slice is written everywhere"), after which the kernel — and with it the stream — proceeds.
 // 12.6 MB of PBR-stage gradients (materials + light textures) at 8 GPUs: each rank moves 1.4 MB in and 1.4 MB out per
 // peer; the cost is the two barrier latencies plus ~10 us of transfers, against ~60-150 us for the NCCL sequence it
-// replaces (launch + protocol latency of each collective). Spin waits are bounded (2 s of GPU clock): a missing peer
-// sets an error word instead of hanging the device.
+// replaces (launch + protocol latency of each collective). A peer that has not arrived after PR_TIMEOUT_CYCLES (about a
+// minute of GPU clock: stragglers — a rank writing a checkpoint, evaluating, loading data — are waited for, like
+// NCCL does) is a fatal error: the error word is set and the kernel traps, so the next CUDA call of this process
+// fails instead of the ranks training on with unreduced, diverging gradients.
 #include "common.cuh"
 
 namespace gigs {
@@ -38,12 +40,13 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p)
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+constexpr long long PR_TIMEOUT_CYCLES = 120000000000ll;   // ~60 s at 1.9 GHz
 // wait until *p >= want (flags only grow); false on timeout
 __device__ __forceinline__ bool spin_ge(const unsigned int* p, unsigned int want)
 {
     const long long t0 = clock64();
     while ((int)(ld_acquire_sys(p) - want) < 0) {
-        if (clock64() - t0 > 4000000000ll) return false;   // ~2 s at 1.9 GHz
+        if (clock64() - t0 > PR_TIMEOUT_CYCLES) return false;
         __nanosleep(64);
     }
     return true;
@@ -65,8 +68,14 @@ __global__ void __launch_bounds__(PR_THREADS) peer_allreduce_kernel(const __grid
     if (threadIdx.x < W && !spin_ge(my + threadIdx.x, ready)) ok = 0;
     __syncthreads();
     if (!ok) {
-        if (threadIdx.x == 0) my[2 * W + 1] = A.epoch;    // error word
-        return;
+        // a peer never arrived: there is nothing to reduce and nothing sane to continue with. Record which call it
+        // was (host-readable: PeerBuffer.error_epoch) and abort the kernel; the context's next call returns the error.
+        if (threadIdx.x == 0) {
+            my[2 * W + 1] = A.epoch;
+            __threadfence_system();
+        }
+        __syncthreads();
+        __trap();
     }
     // (2) reduce my slice of every span and write it to everybody
     for (int s = 0; s < A.n_spans; ++s) {
@@ -109,7 +118,11 @@ __global__ void __launch_bounds__(PR_THREADS) peer_allreduce_kernel(const __grid
     if (threadIdx.x < W) {
         __threadfence_system();
         st_release_sys(A.flags[threadIdx.x] + W + r, done);
-        if (!spin_ge(my + W + threadIdx.x, done)) my[2 * W + 1] = A.epoch;
+        if (!spin_ge(my + W + threadIdx.x, done)) {
+            my[2 * W + 1] = A.epoch;
+            __threadfence_system();
+            __trap();
+        }
     }
 }
 
@@ -140,6 +153,7 @@ int gigs_peer_allreduce(int32_t world, int32_t rank, const uint64_t* peer_bufs, 
     }
     if (n_ctas <= 0) n_ctas = 32;       // the transfers are small: a few CTAs saturate the links without starving other streams
     if (n_ctas > 148) n_ctas = 148;     // every CTA of every call must be counted exactly once by the counter protocol
+    ProfScope ps(ST_PEER_ALLREDUCE, (cudaStream_t)stream);
     peer_allreduce_kernel<<<n_ctas, PR_THREADS, 0, (cudaStream_t)stream>>>(A);
     GIGS_LAUNCH_CHECK("peer_allreduce_kernel");
     return 0;

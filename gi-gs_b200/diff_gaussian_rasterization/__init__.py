@@ -288,10 +288,11 @@ class _CShim:
     def SSAO(width, height, focal_x, focal_y, radius, bias, thick, delta, step, start, out_normal, out_pos):
         n, p = _f32(out_normal, "out_normal"), _f32(out_pos, "out_pos")
         occlusion = torch.empty((1, height, width), dtype=torch.float32, device=n.device)
+        scratch = torch.empty(int(_L.gigs_gi_scratch_bytes(int(width), int(height))), dtype=torch.uint8, device=n.device)
         with torch.cuda.device(n.device):
             check(_L.gigs_ssao(int(width), int(height), float(focal_x), float(focal_y), float(radius), float(bias),
                                float(thick), float(delta), int(step), int(start), ptr(n), ptr(p),
-                               occlusion.data_ptr(), _stream()), "gigs_ssao")
+                               occlusion.data_ptr(), scratch.data_ptr(), scratch.numel(), _stream()), "gigs_ssao")
         return occlusion
 
     @staticmethod
@@ -303,10 +304,12 @@ class _CShim:
         dev = ts[0].device
         color = torch.empty((3, height, width), dtype=torch.float32, device=dev)
         abd = torch.empty((3, height, width), dtype=torch.float32, device=dev)
+        scratch = torch.empty(int(_L.gigs_gi_scratch_bytes(int(width), int(height))), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             check(_L.gigs_ssr(int(width), int(height), float(focal_x), float(focal_y), float(radius), float(bias),
                               float(thick), float(delta), int(step), int(start), *[ptr(t) for t in ts],
-                              color.data_ptr(), abd.data_ptr(), _stream()), "gigs_ssr")
+                              color.data_ptr(), abd.data_ptr(), scratch.data_ptr(), scratch.numel(), _stream()),
+                  "gigs_ssr")
         return color, abd
 
     @staticmethod

@@ -209,8 +209,9 @@ SYMBOLS = {
     "gigs_median3x3_backward": (C.c_int, [_i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "gigs_bilateral3x3": (C.c_int, [_i32, _i32, _i32, _f, _f, _vp, _vp, _vp]),
     "gigs_geometry_chain": (C.c_int, [_i32, _i32, _f, _f, _vp, _vp, _i32, _vp, _vp, _vp]),
-    "gigs_ssao": (C.c_int, [_i32, _i32, _f, _f, _f, _f, _f, _f, _i32, _i32, _vp, _vp, _vp, _vp]),
-    "gigs_ssr": (C.c_int, [_i32, _i32, _f, _f, _f, _f, _f, _f, _i32, _i32] + [_vp] * 10),
+    "gigs_gi_scratch_bytes": (C.c_uint64, [_i32, _i32]),
+    "gigs_ssao": (C.c_int, [_i32, _i32, _f, _f, _f, _f, _f, _f, _i32, _i32, _vp, _vp, _vp, _vp, _u64, _vp]),
+    "gigs_ssr": (C.c_int, [_i32, _i32, _f, _f, _f, _f, _f, _f, _i32, _i32] + [_vp] * 10 + [_u64, _vp]),
     "gigs_gi_count_probes": (C.c_int, [_i32, _i32, _f, _f, _f, _f, _f, _f, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp]),
     "gigs_gi_tune": (C.c_int, [_i32, _i32]),
     "gigs_ssr_backward": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -219,6 +220,7 @@ SYMBOLS = {
     "gigs_frame_layout": (C.c_int, [_i32, _i32, C.POINTER(GigsFrameLayout)]),
     "gigs_frame_forward": (C.c_int, [C.POINTER(GigsFrame)]),
     "gigs_frame_backward": (C.c_int, [C.POINTER(GigsFrame)]),
+    "gigs_latlong_to_cubemap": (C.c_int, [_i32, _i32, _i32, _vp, _i32, _vp, _vp]),
     "gigs_cubemap_table": (C.c_int, [_i32, _vp, _vp]),
     "gigs_specular_bounds": (C.c_int, [_i32, _f, _vp, _vp, _vp]),
     "gigs_cubemap_mip_forward": (C.c_int, [_i32, _vp, _vp, _vp]),
@@ -268,7 +270,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the .so does not export it
         fn.restype = res
         fn.argtypes = args
-    if lib.gigs_abi_version() != 3:
+    if lib.gigs_abi_version() != 4:
         raise ImportError("gigs_b200: ABI version mismatch between the python binding and libgigs_b200.so")
     for which, st in enumerate((GigsCamera, GigsSizes, GigsLayout, GigsRasterFwd, GigsRasterBwd, GigsShade,
                                 GigsFrameLayout, GigsFrame, GigsLightLayout, GigsAdamGroup,

@@ -30,13 +30,16 @@ class DensifyState:
         self.xyz_gradient_accum, self.xyz_gradient_accum_abs = z(P, 1), z(P, 1)
         self.xyz_gradient_accum_abs_max, self.denom, self.max_radii2D = z(P, 1), z(P, 1), z(P)
 
-    def add_view(self, grad2D: torch.Tensor, radii: torch.Tensor) -> None:
-        """train.py:489-495: max_radii2D[vis] = max(., radii[vis]); add_densification_stats(viewspace_points, vis)."""
+    def add_view(self, grad2D: torch.Tensor, radii: torch.Tensor, grad_scale: float = 1.0) -> None:
+        """train.py:489-495: max_radii2D[vis] = max(., radii[vis]); add_densification_stats(viewspace_points, vis).
+        grad_scale undoes a loss scale the view was rendered with (multi-view steps use 1/K)."""
         L = _lib.load()
         P = radii.shape[0]
         if grad2D is None:
             raise RuntimeError("DensifyState.add_view: the screen-space points carry no gradient (run backward first)")
         g = grad2D.detach().float().contiguous()
+        if grad_scale != 1.0:
+            g = g * float(grad_scale)
         r = radii.to(torch.int32).contiguous()
         with torch.cuda.device(g.device):
             _lib.check(L.gigs_densify_stats(P, r.data_ptr(), g.data_ptr(), g.shape[1], self.xyz_gradient_accum.data_ptr(),

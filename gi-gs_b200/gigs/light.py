@@ -215,6 +215,23 @@ class CubemapLight(nn.Module):
         self.specular[-1] = specular_cubemap(self.specular[-1], 1.0, cutoff)
 
 
+def latlong_to_cubemap(latlong_map: torch.Tensor, res) -> torch.Tensor:
+    """relight.py:92-112 / render.py:64-84: [H, W, C] lat-long environment map -> [6, res, res, C] cubemap (one launch;
+    the reference loops over the faces with meshgrid / normalize / atan2 / acos / a texture lookup each)."""
+    r = int(res[0]) if isinstance(res, (list, tuple)) else int(res)
+    if isinstance(res, (list, tuple)) and int(res[1]) != r:
+        raise RuntimeError("latlong_to_cubemap: square faces only")
+    if latlong_map.dim() != 3 or not latlong_map.is_cuda:
+        raise RuntimeError("latlong_to_cubemap: expected a CUDA tensor [H, W, C]")
+    env = latlong_map.detach().float().contiguous()
+    EH, EW, Cn = env.shape
+    cube = torch.empty(6, r, r, Cn, dtype=torch.float32, device=env.device)
+    with torch.cuda.device(env.device):
+        check(_L.gigs_latlong_to_cubemap(EH, EW, Cn, env.data_ptr(), r, cube.data_ptr(), _stream()),
+              "gigs_latlong_to_cubemap")
+    return cube
+
+
 def envmap_dirs(res=(512, 1024), device="cuda") -> torch.Tensor:
     """train.py:145-157 get_envmap_dirs: [H,W,3] directions of a lat-long grid (computed once, like train.py:209)."""
     gy, gx = torch.meshgrid(torch.linspace(0.0 + 1.0 / res[0], 1.0 - 1.0 / res[0], res[0], device=device),

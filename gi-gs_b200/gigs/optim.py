@@ -219,10 +219,12 @@ class GaussianOptimizer:
                 g["lr"] = self.xyz_scheduler_args(iteration)
         return None
 
-    def step(self, light: bool = True) -> None:
+    def step(self, light: bool = True, skip_groups=()) -> None:
         """optimizer.step() + zero_grad() (+ light_optimizer.step() + zero_grad() + clamp_ when `light`,
         train.py:516-523). Groups the fused frame is known not to have written since the last clear pass a NULL
-        gradient: same update as torch's (their gradients ARE zero), 4 B per element less traffic and no clear."""
+        gradient: same update as torch's (their gradients ARE zero), 4 B per element less traffic and no clear.
+        skip_groups: reference group names whose tensors torch's Adam would skip this iteration because their .grad is
+        None (a parameter replaced after backward, e.g. `opacity` by reset_opacity): not stepped, step count kept."""
         p = self.params
         zero = []
         if p._dirty is not None:
@@ -232,6 +234,7 @@ class GaussianOptimizer:
                     zero.append(g["name"])
         skip = [] if light else [g["name"] for g in self.adam.param_groups
                                  if g["name"] == "cubemap" or g["name"].startswith("light")]
+        skip += [n for n in skip_groups if n not in skip]
         if skip:
             saved = self.adam.param_groups
             self.adam.param_groups = [g for g in saved if g["name"] not in skip]
@@ -239,8 +242,14 @@ class GaussianOptimizer:
                 self.adam.step(zero_grads=zero, clear_grad=True)
             finally:
                 self.adam.param_groups = saved
+            # a skipped Gaussian group's gradient is dropped (the reference's new Parameter has none), the light's stays
+            for n in skip_groups:
+                t = self.params.leaves.get(self._key_of.get(n, n))
+                if t is not None and t.grad is not None:
+                    t.grad.zero_()
+            kept = [n for n in skip if n not in skip_groups]
             if p._dirty is not None:
-                p._dirty = [s for s in p._dirty if any(s == p._span[self._key_of[n]] for n in skip)]
+                p._dirty = [s for s in p._dirty if any(s == p._span[self._key_of[n]] for n in kept)]
         else:
             self.adam.step(zero_grads=zero, clear_grad=True)
             p._dirty = []

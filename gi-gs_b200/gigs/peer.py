@@ -55,7 +55,9 @@ class PeerBuffer:
                            "gigs_peer_allreduce")
 
     def error_epoch(self) -> int:
-        """0, or the epoch of a call in which a peer did not arrive within the timeout (synchronises the device)."""
+        """0, or the epoch of the call in which a peer did not arrive within the (about one minute) timeout. That call's
+        kernel traps, so in practice the process learns of it as a CUDA error on its next call; the word is for a
+        post-mortem (synchronises the device)."""
         return int(self.flags[2 * self.world + 1].item())
 
 

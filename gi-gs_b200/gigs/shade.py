@@ -152,45 +152,4 @@ class Light:
             (torch.clamp(roughness, self.MAX_ROUGHNESS, 1.0) - self.MAX_ROUGHNESS) / (1.0 - self.MAX_ROUGHNESS) + n - 2)
 
 
-_lut_cache = {}
-
-
-def make_brdf_lut(res: int = 256, samples: int = 512) -> torch.Tensor:
-    """A split-sum environment-BRDF LUT [1,res,res,2] (scale, bias of F0) by GGX importance sampling with a
-    Hammersley sequence (Karis 2013, height-correlated Smith visibility). x = NoV, y = roughness, texel centres at (i+0.5)/res. Synthetic stand-in
-    for the reference's data file pbr/brdf_256_256.bin, which is not copied into this repo."""
-    key = (res, samples)
-    if key in _lut_cache:
-        return _lut_cache[key]
-    nov = ((torch.arange(res, dtype=torch.float64) + 0.5) / res)[None, :, None]      # [1,res,1]
-    rough = ((torch.arange(res, dtype=torch.float64) + 0.5) / res)[:, None, None]    # [res,1,1]
-    i = torch.arange(samples, dtype=torch.int64)
-    bits = i.clone()
-    bits = ((bits << 16) | (bits >> 16)) & 0xFFFFFFFF
-    bits = (((bits & 0x55555555) << 1) | ((bits & 0xAAAAAAAA) >> 1)) & 0xFFFFFFFF
-    bits = (((bits & 0x33333333) << 2) | ((bits & 0xCCCCCCCC) >> 2)) & 0xFFFFFFFF
-    bits = (((bits & 0x0F0F0F0F) << 4) | ((bits & 0xF0F0F0F0) >> 4)) & 0xFFFFFFFF
-    bits = (((bits & 0x00FF00FF) << 8) | ((bits & 0xFF00FF00) >> 8)) & 0xFFFFFFFF
-    xi1 = ((i.double() + 0.5) / samples)[None, None, :]
-    xi2 = (bits.double() * 2.3283064365386963e-10)[None, None, :]
-    a = rough * rough
-    phi = 2.0 * math.pi * xi1
-    cos_t = torch.sqrt((1.0 - xi2) / (1.0 + (a * a - 1.0) * xi2))
-    sin_t = torch.sqrt(torch.clamp(1.0 - cos_t * cos_t, min=0.0))
-    hx, hz = sin_t * torch.cos(phi), cos_t
-    vx, vz = torch.sqrt(1.0 - nov * nov), nov
-    vdh = vx * hx + vz * hz
-    lz = 2.0 * vdh * hz - vz
-    nol, noh, vdh_c = lz.clamp(min=0.0), hz.clamp(min=0.0), vdh.clamp(min=0.0)
-    # height-correlated Smith-GGX visibility (the variant that reproduces the reference's data file to 1e-3)
-    lam_v = nol * torch.sqrt(nov * nov * (1.0 - a * a) + a * a)
-    lam_l = nov * torch.sqrt(nol * nol * (1.0 - a * a) + a * a)
-    g = (0.5 / (lam_v + lam_l + 1e-12)) * 4.0 * nol * nov
-    g_vis = g * vdh_c / (noh * nov + 1e-12)
-    fc = (1.0 - vdh_c) ** 5
-    ok = (nol > 0).double()
-    A = ((1.0 - fc) * g_vis * ok).mean(-1)
-    B = (fc * g_vis * ok).mean(-1)
-    lut = torch.stack([A, B], -1).float()[None].contiguous()
-    _lut_cache[key] = lut
-    return lut
+from .scene import make_brdf_lut  # noqa: E402,F401  (synthetic-input generator: lives with the other generators, no CUDA library needed)

@@ -31,7 +31,8 @@ class GaussianParams:
             raise ValueError("give the light either as textures (light=) or as the base cubemap (light_base=)")
         P = raw["xyz"].shape[0]
         self.P = P
-        self.sh_degree = raw["sh_degree"]
+        self.sh_degree = raw["sh_degree"]              # active degree (GaussianModel.active_sh_degree)
+        self.max_sh_degree = int(raw.get("max_sh_degree", raw["sh_degree"]))
         self.leaves: Dict[str, torch.Tensor] = {}
         for k in PARAM_KEYS:
             self.leaves[k] = raw[k].to(device).float().contiguous().requires_grad_(True)
@@ -325,7 +326,9 @@ def first_stage_step(params: GaussianParams, cam, gt_image, background, gi: Dict
         loss, g2d, radii = stage1_frame_step(params, cam, gt_image, background, lambda_dssim, normal_weight,
                                              normal_tv_weight, loss_scale, gt_ready=gt_ready)
         if stats is not None:
-            stats.add_view(g2d, radii)
+            # the statistics are per-view norms of the UNSCALED loss's screen-space gradient (train.py:489-495): a K-view
+            # step renders each view with loss_scale = 1/K, which must not shrink them against the fixed threshold
+            stats.add_view(g2d, radii, 1.0 / loss_scale)
         return loss.clone(), {"radii": radii, "viewspace_grad": g2d}
     g = params.activated()
     res = render(cam, g, background, derive_normal=True, **gi)
@@ -337,7 +340,7 @@ def first_stage_step(params: GaussianParams, cam, gt_image, background, gi: Dict
         loss = _framework_first_stage_loss(res, gt_image, lambda_dssim, normal_weight, normal_tv_weight)
     (loss * loss_scale).backward()
     if stats is not None:
-        stats.add_view(res["viewspace_points"].grad, res["radii"])
+        stats.add_view(res["viewspace_points"].grad, res["radii"], 1.0 / loss_scale)
     return loss.detach() * loss_scale, res
 
 

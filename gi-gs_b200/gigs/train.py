@@ -50,6 +50,9 @@ class Trainer:
     def iteration(self, it: int, cam, gt_image: torch.Tensor, rays: Optional[torch.Tensor] = None) -> torch.Tensor:
         """train.py:246-523 for iteration `it` (1-based) on one view. Returns the detached loss."""
         cfg, opt, p = self.cfg, self.cfg.opt, self.params
+        # "Every 1000 its we increase the levels of SH up to a maximum degree" (train.py:243-244, oneupSHdegree)
+        if it % 1000 == 0 and p.sh_degree < p.max_sh_degree:
+            p.sh_degree += 1
         first = it <= cfg.pbr_iteration
         if first:
             loss, _ = first_stage_step(p, cam, gt_image, self.bg, cfg.gi, lambda_dssim=opt.lambda_dssim,
@@ -78,7 +81,13 @@ class Trainer:
                 # a rebuilt model has fresh zero gradients (the reference also steps on the new, gradient-less tensors:
                 # torch's Adam skips parameters whose .grad is None)
                 if event is None or "P_after" not in event:
-                    self.optimizer.step(light=(it >= cfg.pbr_iteration))
+                    # torch's Adam skips a parameter whose .grad is None: `opacity` in the iteration that reset it
+                    # (reset_opacity swaps in a new Parameter after backward), and the light before the PBR stage has
+                    # produced its first gradient (at it == pbr_iteration the loop calls light_optimizer.step() on a
+                    # light that was never rendered: no update, no step count)
+                    reset = event is not None and event.get("reset_opacity")
+                    self.optimizer.step(light=(it >= cfg.pbr_iteration and not first),
+                                        skip_groups=("opacity",) if reset else ())
                 self.optimizer.update_learning_rate(it)
         self.log.append(dict(iteration=it, stage=1 if first else 2, loss=float(loss), P=p.P, event=event))
         return loss

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define GIGS_ABI_VERSION 3
+#define GIGS_ABI_VERSION 4
 
 /* Per-view constants: the non-tensor fields of GaussianRasterizationSettings
  * (diff_gaussian_rasterization/__init__.py:31-51). Matrices are the transposed (column-major)
@@ -199,16 +199,22 @@ int gigs_geometry_chain(int32_t W, int32_t H, float fx, float fy, const float* v
                         float* normal_from_depth /*[3,H,W]*/, float* depth_pos_filter /*[3,H,W]*/,
                         void* stream);
 
+/* Scratch of the SSAO / SSR march for a W x H frame: the block (min, max) table of the position map's depth plane
+ * that lets the march skip the depth gather of probes that cannot hit (<= 40 KB + 16). The caller owns it, 16-byte
+ * aligned; it is written by every call and holds nothing between calls. With scratch == NULL (or too small) the
+ * march runs without the block test: same result, slower. */
+uint64_t gigs_gi_scratch_bytes(int32_t W, int32_t H);
+
 /* Replaces SSAO (rasterize_points.cu:407-436, forward.cu:635-724). */
 int gigs_ssao(int32_t W, int32_t H, float fx, float fy, float radius, float bias, float thick,
               float delta, int32_t step, int32_t start, const float* normal, const float* pos,
-              float* occlusion, void* stream);
+              float* occlusion, void* scratch, uint64_t scratch_bytes, void* stream);
 
 /* Replaces SSR (rasterize_points.cu:438-477, forward.cu:726-909). */
 int gigs_ssr(int32_t W, int32_t H, float fx, float fy, float radius, float bias, float thick,
              float delta, int32_t step, int32_t start, const float* normal, const float* pos,
              const float* rgb, const float* albedo, const float* roughness, const float* metallic,
-             const float* F0, float* color, float* abd, void* stream);
+             const float* F0, float* color, float* abd, void* scratch, uint64_t scratch_bytes, void* stream);
 
 /* Number of probes (one sample position -> one depth test) the SSAO/SSR march of this G-buffer has to evaluate:
  * the reference's loop (forward.cu:691-716 / :805-846) counted up to and including the probe that ends a direction,
@@ -342,6 +348,13 @@ typedef struct GigsFrame {
 #define GIGS_E_GROW (-5) /* binning / sort workspace too small: grow to need_*_bytes and call again with resume=1 */
 int gigs_frame_forward(GigsFrame* f);
 int gigs_frame_backward(GigsFrame* f);
+
+/* Replaces latlong_to_cubemap (relight.py:92-112, render.py:64-84: the relight / eval sweeps turn a lat-long HDR
+ * environment map [env_h, env_w, channels] into the light's base cubemap [6, res, res, channels] before build_mips):
+ * per cube texel direction d = normalize(cube_to_dir), (u, v) = (atan2(d.x, -d.z) / 2pi + 0.5, acos(d.y) / pi),
+ * bilinear with both axes wrapping (nvdiffrast dr.texture, filter_mode "linear", boundary mode "wrap"). */
+int gigs_latlong_to_cubemap(int32_t env_h, int32_t env_w, int32_t channels, const float* env, int32_t res,
+                            float* cube, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Cubemap prefilter = CubemapLight.build_mips (/root/reference/pbr/light.py:154-170), SURVEY.md §8f-1: the producer of
@@ -576,7 +589,8 @@ int gigs_dist2(int32_t P, const float* points, float* mean_dist2, void* scratch,
  * 19 deferred_loss, 20 deferred_backward, 21 param_grad, 22 one radix-sort pass (nested inside 2 / 23),
  * 23 depth argsort of the Gaussians, 24 cubemap prefilter forward, 25 cubemap prefilter backward, 26 Adam step,
  * 27 image loss (L1 + SSIM forward, finish and backward), 28 normal loss (L1 + TV forward, finish, backward),
- * 29 first-stage normal post-processing, 30 its backward.
+ * 29 first-stage normal post-processing, 30 its backward, 31 deferred_backward_kernel alone (nested inside 20),
+ * 32 the peer all-reduce kernel.
  * gigs_profile_read synchronises the recorded events, writes up to cap (stage, ms) pairs, clears the log and
  * returns the number written (negative on error). Off by default; costs two event records per stage when on. */
 int gigs_profile_enable(int32_t on);

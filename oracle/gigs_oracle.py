@@ -1267,6 +1267,32 @@ def build_mips_backward(base_res: int, grad_specular, grad_diffuse, cutoff: floa
 # :145-157, with the nvdiffrast cube lookup restated above — that lookup is the unpinned part).
 # Differentiable torch ops: autograd of these is the oracle for the backward.
 # ------------------------------------------------------------------------------------------------
+def latlong_to_cubemap(latlong_map, res: int):
+    """relight.py:92-112: per face meshgrid(linspace(-1 + 1/res, 1 - 1/res, res)) -> cube_to_dir -> normalize ->
+    (atan2(x, -z) / 2pi + 0.5, acos(clamp(y)) / pi) -> bilinear lookup. The lookup is nvdiffrast's
+    dr.texture(filter_mode="linear") (absent here: "parity unpinned"), restated from its documented semantics: texel
+    centres at (i + 0.5) / size, boundary mode "wrap" on both axes."""
+    env = latlong_map.float()
+    EH, EW, Cn = env.shape
+    out = torch.zeros(6, res, res, Cn)
+    lin = torch.linspace(-1.0 + 1.0 / res, 1.0 - 1.0 / res, res)
+    gy, gx = torch.meshgrid(lin, lin, indexing="ij")
+    one = torch.ones_like(gx)
+    for s in range(6):
+        d = [(one, -gy, -gx), (-one, -gy, gx), (gx, one, gy), (gx, -one, -gy), (gx, -gy, one), (-gx, -gy, -one)][s]
+        v = torch.nn.functional.normalize(torch.stack(d, -1), p=2, dim=-1)
+        tu = torch.atan2(v[..., 0], -v[..., 2]) / (2 * math.pi) + 0.5
+        tv = torch.acos(torch.clamp(v[..., 1], -1, 1)) / math.pi
+        x, y = tu * EW - 0.5, tv * EH - 0.5
+        x0, y0 = torch.floor(x), torch.floor(y)
+        ax, ay = (x - x0)[..., None], (y - y0)[..., None]
+        x0, y0 = x0.long() % EW, y0.long() % EH
+        x1, y1 = (x0 + 1) % EW, (y0 + 1) % EH
+        out[s] = (env[y0, x0] * (1 - ax) * (1 - ay) + env[y0, x1] * ax * (1 - ay) + env[y1, x0] * (1 - ax) * ay
+                  + env[y1, x1] * ax * ay)
+    return out
+
+
 def masked_tv_loss(mask, gt_image, prediction):
     rgb_grad_h = torch.exp(-(gt_image[:, 1:, :] - gt_image[:, :-1, :]).abs().mean(dim=0, keepdim=True))
     rgb_grad_w = torch.exp(-(gt_image[:, :, 1:] - gt_image[:, :, :-1]).abs().mean(dim=0, keepdim=True))

@@ -33,7 +33,7 @@ def test_python_binding_covers_every_declared_symbol():
     from gigs import _lib
     assert sorted(_lib.SYMBOLS) == declared_symbols()
     lib = _lib.load()
-    assert lib.gigs_abi_version() == 3
+    assert lib.gigs_abi_version() == 4
 
 
 def test_workspace_sizes_are_a_pure_function_of_shape():

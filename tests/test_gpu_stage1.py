@@ -8,7 +8,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 import gpu_util as U
-from gigs import scene, step as gstep
+from gigs import densify, scene, step as gstep
 
 DEV = "cuda:0"
 GI = dict(radius=0.8, bias=0.01, thick=0.05, delta=0.0625, step=16, start=64)
@@ -95,3 +95,63 @@ def test_fused_first_stage_frame_matches_the_operator_path(P, W, H, gtol):
     l2, _ = gstep.first_stage_step(pa, cam, gt, bg, GI, fused=True, loss_scale=0.25)
     assert float(l2) == pytest.approx(0.25 * float(la), rel=1e-5)
     spans_close(pa.flat_grad, 0.25 * g1)
+
+
+def test_multi_view_stats_do_not_shrink_with_the_loss_scale():
+    """add_densification_stats accumulates per-view norms of the unscaled loss's screen-space gradient
+    (train.py:489-495): a K-view step renders every view with loss_scale 1/K and must hand the same statistics to
+    the fixed clone / split threshold as K single-view steps do."""
+    P, W, H, K = 4000, 160, 128, 4
+    raw = scene.make_scene(P, seed=4, regime="trained")
+    cams = [scene.orbit_camera(k, K, W, H).to(DEV) for k in range(K)]
+    gts = [torch.rand(3, H, W, generator=torch.Generator().manual_seed(k)).to(DEV) for k in range(K)]
+    bg = torch.zeros(3, device=DEV)
+    pa, pb = gstep.GaussianParams(raw, DEV), gstep.GaussianParams(raw, DEV)
+    sa, sb = densify.DensifyState(P, DEV), densify.DensifyState(P, DEV)
+    gstep.multi_view_first_stage_step(pa, cams, gts, bg, GI, stats=sa, fused=True)
+    for k in range(K):
+        pb.zero_grad()
+        gstep.first_stage_step(pb, cams[k], gts[k], bg, GI, fused=True, stats=sb)
+    torch.cuda.synchronize()
+    assert torch.equal(sa.denom, sb.denom) and torch.equal(sa.max_radii2D, sb.max_radii2D)
+    assert float(sb.xyz_gradient_accum.max()) > 0
+    for a, b in ((sa.xyz_gradient_accum, sb.xyz_gradient_accum), (sa.xyz_gradient_accum_abs, sb.xyz_gradient_accum_abs),
+                 (sa.xyz_gradient_accum_abs_max, sb.xyz_gradient_accum_abs_max)):
+        assert float((a - b).norm()) <= 1e-3 * float(b.norm()) + 1e-12
+
+
+def test_trainer_raises_the_sh_degree_and_skips_gradientless_groups():
+    """oneupSHdegree every 1000 iterations (train.py:243-244); torch's Adam skips a parameter whose .grad is None:
+    `opacity` in an iteration that reset it without a rebuild, the light before the PBR stage rendered it."""
+    from gigs import train as gtrain, shade
+    P, W, H = 2000, 96, 80
+    raw = scene.make_scene(P, seed=6, regime="trained")
+    raw["sh_degree"], raw["max_sh_degree"] = 0, 3
+    cam = scene.orbit_camera(0, 4, W, H).to(DEV)
+    gt = torch.rand(3, H, W, generator=torch.Generator().manual_seed(1)).to(DEV)
+    base = torch.rand(6, 64, 64, 3, generator=torch.Generator().manual_seed(2)) * 0.5 + 0.25
+    params = gstep.GaussianParams(raw, DEV, light_base=base)
+    cfg = gtrain.TrainConfig(pbr_iteration=1002, white_background=True)
+    cfg.opt.densify_from_iter = 1001      # white background: reset_opacity at it == densify_from_iter, no densification
+    cfg.opt.densification_interval = 10 ** 9
+    tr = gtrain.Trainer(params, shade.make_brdf_lut(64, 64).to(DEV), 3.0, cfg,
+                        rays_of=lambda c: scene.canonical_rays(c, DEV))
+    f_rest0 = params.leaves["f_rest"].detach().clone()
+    tr.iteration(999, cam, gt)
+    assert params.sh_degree == 0 and torch.equal(params.leaves["f_rest"].detach(), f_rest0)   # degree 0: f_rest frozen
+    tr.iteration(1000, cam, gt)
+    assert params.sh_degree == 1
+    assert not torch.equal(params.leaves["f_rest"].detach(), f_rest0)                         # degree 1 trains f_rest
+    st = tr.optimizer.adam.state
+    steps_before = {k: v["step"] for k, v in st.items()}
+    tr.iteration(1001, cam, gt)           # resets the opacity: its group is not stepped, everything else is
+    assert tr.log[-1]["event"] and tr.log[-1]["event"].get("reset_opacity")
+    assert st["opacity"]["step"] == steps_before["opacity"]
+    assert st["xyz"]["step"] == steps_before["xyz"] + 1
+    assert float(params.leaves["opacity"].grad.abs().max()) == 0.0
+    assert "cubemap" not in st or st["cubemap"]["step"] == 0
+    tr.iteration(1002, cam, gt)           # it == pbr_iteration: still the first stage, the light has no gradient yet
+    assert "cubemap" not in st or st["cubemap"]["step"] == 0
+    tr.iteration(1003, cam, gt)           # first PBR-stage iteration: the light's first step
+    assert st["cubemap"]["step"] == 1
+    assert params.sh_degree == 1

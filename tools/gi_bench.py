@@ -59,14 +59,15 @@ def main():
     col = torch.empty(3, H, W, device=dev)
     abd = torch.empty(3, H, W, device=dev)
     st = torch.cuda.current_stream().cuda_stream
+    scr = torch.empty(int(L.gigs_gi_scratch_bytes(W, H)), dtype=torch.uint8, device=dev)
 
     def ssao():
-        _lib.check(L.gigs_ssao(*args, m["normal_view"].data_ptr(), m["depth_pos"].data_ptr(), occ.data_ptr(), st), "ssao")
+        _lib.check(L.gigs_ssao(*args, m["normal_view"].data_ptr(), m["depth_pos"].data_ptr(), occ.data_ptr(), scr.data_ptr(), scr.numel(), st), "ssao")
 
     def ssr():
         _lib.check(L.gigs_ssr(*args, m["ssr_normal"].data_ptr(), m["depth_pos"].data_ptr(), m["linear_rgb"].data_ptr(),
                               m["albedo"].data_ptr(), m["rough_remap"].data_ptr(), m["metal_used"].data_ptr(),
-                              m["F0"].data_ptr(), col.data_ptr(), abd.data_ptr(), st), "ssr")
+                              m["F0"].data_ptr(), col.data_ptr(), abd.data_ptr(), scr.data_ptr(), scr.numel(), st), "ssr")
 
     out = {"P": P, "W": W, "H": H, "gi": gi, "variants": {}}
     if os.environ.get("GI_QUICK"):          # profiling runs: one SSAO + one SSR launch of the chosen variant
