@@ -478,6 +478,35 @@ def run_ours(args):
         return float(t.item())
 
     multi = {}
+    if world > 1 and getattr(params, "_peer", None) is not None:
+        # ---- the exchange alone, ranks aligned by a barrier first: the PBR stage's spans (materials + light textures) and
+        # the first stage's whole buffer (268 B per Gaussian), through our kernel with and without the NVSwitch
+        # multicast (NVLS) mapping, and through NCCL on the same buffer. bus GB/s = 2 (N-1)/N x bytes / time ----
+        pb = params._peer
+        fused_spans = [tuple(sp) for sp in params._merged_dirty()] or None
+        n_all = params.flat_grad.numel()
+        n_fused = sum(hi - lo for lo, hi in fused_spans) if fused_spans else n_all
+        mc_saved = int(getattr(pb._h, "multicast_ptr", 0) or 0)
+        ex = {"nvls_multicast_mapped": bool(mc_saved), "nvls_used_by_default": bool(pb.multicast_ptr)}
+        mc_default = pb.multicast_ptr
+
+        def bus(nfloats, ms):
+            return 2.0 * (world - 1) / world * nfloats * 4 / (ms * 1e-3) / 1e9
+        for tag, spans, nfl in (("pbr_stage_spans", fused_spans, n_fused), ("first_stage_whole_buffer", None, n_all)):
+            rec = {"bytes": int(nfl * 4)}
+            for mode in (("nvls",) if mc_saved else ()) + ("peer",):
+                pb.multicast_ptr = mc_saved if mode == "nvls" else 0
+                ms = ev_all(lambda: pb.all_reduce(spans), 20, warm=3)
+                rec[mode + "_ms"] = ms
+                rec[mode + "_bus_GBps"] = bus(nfl, ms)
+            pb.multicast_ptr = mc_default
+            if spans is None:
+                ms = ev_all(lambda: dist.all_reduce(params.flat_grad, op=dist.ReduceOp.SUM), 20, warm=3)
+                rec["nccl_ms"] = ms
+                rec["nccl_bus_GBps"] = bus(nfl, ms)
+            ex[tag] = rec
+        params.flat_grad.zero_()
+        multi["exchange_alone"] = ex
     if not args.no_extras:
         # ---- BASELINE configs[3] (C4): a K-view training step, views sharded over the ranks (strong scaling: K is
         # fixed, each rank renders K / N views, then ONE gradient exchange) ----
@@ -517,7 +546,8 @@ def run_ours(args):
                 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e2 = torch.cuda.Event(enable_timing=True)
                 e0.record()
                 base = glight.latlong_to_cubemap(hdr_host.to(dev, non_blocking=True), [256, 256])
-                pl = glight.PrefilteredLight(base)
+                # one build per environment map: the filter weights are evaluated on the fly (no stored operators)
+                pl = glight.PrefilteredLight(base, stored_operators=False)
                 pl.build()
                 e1.record()
                 for c in cams_v:
@@ -530,8 +560,8 @@ def run_ours(args):
                 multi[f"c5_relight_{tag}"] = {"value": V * 1e3 / float(t[0]), "unit": "views/s", "views": V,
                                               "total_ms": float(t[0]), "light_setup_ms": float(t[1]),
                                               "resolution": [Wv, Hv], "gi_start": 8, "scaling": "strong",
-                                              "note": "H2D of a 1024x2048 HDR map + latlong_to_cubemap(256) + filter "
-                                                      "operators + build_mips (light_setup_ms, every rank) then the "
+                                              "note": "H2D of a 1024x2048 HDR map + latlong_to_cubemap(256) + "
+                                                      "build_mips (light_setup_ms, every rank) then the "
                                                       "rank's share of 200 views: G-buffer + SSAO + shading + SSR"}
                 del pl, base, cams_v, rays_v
                 gframe._workspaces.clear()

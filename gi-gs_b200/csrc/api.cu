@@ -143,6 +143,7 @@ Layout make_layout(int P, int W, int H, uint64_t R)
     L.s_keys_b = take(R * 4);
     L.s_vals_b = take(R * 4);
     L.s_hist = take(8 * 256 * 4);
+    L.s_joint = take(radix_joint_bytes());     // joint tile-id histogram (digit histograms + tile ranges come from it)
     L.s_ticket = take(128);
     L.s_status = take((uint64_t)L.sort_passes * L.sort_tiles * 256 * 4);
     L.s_zero_bytes = (L.s_status - L.s_hist) + (uint64_t)L.sort_passes * L.sort_tiles * 256 * 4;
@@ -157,6 +158,10 @@ int launch_depth_argsort(const GigsRasterFwd* a, const Layout& L, cudaStream_t s
 int launch_emit_keys(const GigsRasterFwd* a, const Layout& L, uint32_t* keys, uint32_t* vals, cudaStream_t st);
 int launch_tile_ranges(uint64_t R, const uint32_t* tiles_sorted, uint2* ranges, uint32_t num_tiles, cudaStream_t st);
 int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t st);
+int launch_tile_sort(uint64_t R, int end_bit, const uint32_t* keys_u, const uint32_t* vals_u, uint32_t* keys_a,
+                     uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint32_t* hist, uint32_t* status,
+                     uint32_t* tickets, uint64_t zero_bytes, int pass_stage, uint32_t* joint, uint2* ranges,
+                     uint32_t num_tiles, int* ranges_done, cudaStream_t st);
 int launch_radix_sort32(uint64_t R, int end_bit, const uint32_t* keys_u, const uint32_t* vals_u, uint32_t* keys_a,
                         uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint32_t* hist, uint32_t* status,
                         uint32_t* tickets, uint64_t zero_bytes, int pass_stage, cudaStream_t st);
@@ -226,19 +231,22 @@ int forward_finish_impl(GigsRasterFwd* a, bool lite)
     char* bn = (char*)a->binning;
     uint32_t* keys_u = (uint32_t*)(sc + L.off.s_tiles_unsorted);
     uint32_t* vals_u = (uint32_t*)(sc + L.off.s_vals_unsorted);
+    int ranges_done = 0;
     if (a->P > 0 && R > 0) {
         {
             ProfScope ps(ST_EMIT_KEYS, st);
             if (int e = launch_emit_keys(a, L, keys_u, vals_u, st)) return e;
         }
         ProfScope ps(ST_SORT, st);
-        if (int e = launch_radix_sort32(R, (int)L.sort_bits, keys_u, vals_u, (uint32_t*)(sc + L.s_keys_a),
-                                        (uint32_t*)(bn + L.off.b_point_list), (uint32_t*)(sc + L.s_keys_b),
-                                        (uint32_t*)(sc + L.s_vals_b), (uint32_t*)(sc + L.s_hist),
-                                        (uint32_t*)(sc + L.s_status), (uint32_t*)(sc + L.s_ticket), L.s_zero_bytes, ST_SORT_PASS, st))
+        if (int e = launch_tile_sort(R, (int)L.sort_bits, keys_u, vals_u, (uint32_t*)(sc + L.s_keys_a),
+                                     (uint32_t*)(bn + L.off.b_point_list), (uint32_t*)(sc + L.s_keys_b),
+                                     (uint32_t*)(sc + L.s_vals_b), (uint32_t*)(sc + L.s_hist),
+                                     (uint32_t*)(sc + L.s_status), (uint32_t*)(sc + L.s_ticket), L.s_zero_bytes,
+                                     ST_SORT_PASS, (uint32_t*)(sc + L.s_joint), (uint2*)(im + L.off.i_ranges), L.num_tiles,
+                                     &ranges_done, st))
             return e;
     }
-    {
+    if (!ranges_done) {
         ProfScope ps(ST_RANGES, st);
         if (int e = launch_tile_ranges(R, (const uint32_t*)(sc + L.s_keys_a), (uint2*)(im + L.off.i_ranges), L.num_tiles, st))
             return e;

@@ -82,7 +82,7 @@ struct Layout {
     GigsSizes size;
     uint32_t tiles_x, tiles_y, num_tiles, num_blocks;
     // instance sort (by tile id) scratch internals
-    uint64_t s_keys_a, s_keys_b, s_vals_b, s_hist, s_status, s_ticket, s_zero_bytes;
+    uint64_t s_keys_a, s_keys_b, s_vals_b, s_hist, s_joint, s_status, s_ticket, s_zero_bytes;
     uint32_t sort_tiles, sort_passes, sort_bits;
     // Gaussian depth argsort internals (geom blob) + block sums of tiles_touched in depth order
     uint64_t p_keys_a, p_keys_b, p_vals_b, p_hist, p_status, p_ticket, p_zero_bytes, g_block_sums2;
@@ -91,6 +91,7 @@ Layout make_layout(int P, int W, int H, uint64_t R);
 uint32_t higher_msb(uint32_t n);
 int radix_digit_bits(int bits);
 int radix_sort_passes(int bits);
+uint64_t radix_joint_bytes();
 
 // ---------------------------------------------------------------------------------------------
 // Pixel block of one warp inside the 16x16 tile. The blend kernels reject, once per warp, the Gaussians whose 1/255

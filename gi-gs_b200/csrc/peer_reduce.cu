@@ -26,6 +26,7 @@ struct PeerArgs {
     int world, rank, n_spans;
     unsigned int epoch;                       // call counter, starts at 1
     float* buf[PR_MAX_WORLD];                 // the symmetric gradient buffer of every rank (buf[rank] is local)
+    float* mc;                                // multicast (NVLS) mapping of the same buffer, or NULL
     unsigned int* flags[PR_MAX_WORLD];        // every rank's flag block: [0..W) ready, [W..2W) done, [2W] local CTA counter, [2W+1] error
     unsigned long long lo[PR_MAX_SPANS], hi[PR_MAX_SPANS];   // float offsets
 };
@@ -50,6 +51,22 @@ __device__ __forceinline__ bool spin_ge(const unsigned int* p, unsigned int want
         __nanosleep(64);
     }
     return true;
+}
+
+// NVLS: one load that the NVSwitch answers with the SUM of the addressed 16 bytes over every rank's copy of the buffer,
+// and one store that the switch writes into every rank's copy (PTX multimem.*, sm_90+). Per rank and slice the links
+// carry the slice once out and once in instead of (N-1) times each way.
+__device__ __forceinline__ float4 multimem_ld_reduce_f4(const float* mc_addr)
+{
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc_addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void multimem_st_f4(float* mc_addr, const float4 v)
+{
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(mc_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
 __global__ void __launch_bounds__(PR_THREADS) peer_allreduce_kernel(const __grid_constant__ PeerArgs A)
@@ -85,14 +102,39 @@ __global__ void __launch_bounds__(PR_THREADS) peer_allreduce_kernel(const __grid
             const unsigned long long n4 = n >> 2;
             const unsigned long long per = (n4 + W - 1) / W;
             const unsigned long long b = (unsigned long long)r * per, e = (b + per < n4) ? b + per : n4;
-            for (unsigned long long i = b + (unsigned long long)blockIdx.x * PR_THREADS + threadIdx.x; i < e;
-                 i += (unsigned long long)gridDim.x * PR_THREADS) {
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int p = 0; p < W; ++p) {
-                    const float4 v = reinterpret_cast<const float4*>(A.buf[p] + lo)[i];
-                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            if (A.mc != nullptr) {
+                // the switch adds (order fixed by the fabric, the same for every element of a run) and broadcasts
+                for (unsigned long long i = b + (unsigned long long)blockIdx.x * PR_THREADS + threadIdx.x; i < e;
+                     i += (unsigned long long)gridDim.x * PR_THREADS) {
+                    const float4 acc = multimem_ld_reduce_f4(A.mc + lo + 4 * i);
+                    multimem_st_f4(A.mc + lo + 4 * i, acc);
                 }
-                for (int p = 0; p < W; ++p) reinterpret_cast<float4*>(A.buf[p] + lo)[i] = acc;
+                continue;
+            }
+            // U elements per thread and trip: U * W independent 16-byte peer loads in flight (at W = 2 one element per
+            // trip leaves the links waiting on latency)
+            constexpr int U = 4;
+            const unsigned long long stride = (unsigned long long)gridDim.x * PR_THREADS;
+            for (unsigned long long i0 = b + (unsigned long long)blockIdx.x * PR_THREADS + threadIdx.x; i0 < e;
+                 i0 += U * stride) {
+                float4 acc[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int p = 0; p < W; ++p) {
+                    const float4* src = reinterpret_cast<const float4*>(A.buf[p] + lo);
+                    float4 v[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        v[u] = (i0 + u * stride < e) ? src[i0 + u * stride] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) { acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w; }
+                }
+                for (int p = 0; p < W; ++p) {
+                    float4* dst = reinterpret_cast<float4*>(A.buf[p] + lo);
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (i0 + u * stride < e) dst[i0 + u * stride] = acc[u];
+                }
             }
         } else {
             const unsigned long long per = (n + W - 1) / W;
@@ -110,8 +152,11 @@ __global__ void __launch_bounds__(PR_THREADS) peer_allreduce_kernel(const __grid
     __syncthreads();
     __shared__ int last;
     if (threadIdx.x == 0) {
+        // calls on one flag block are stream-ordered (never concurrent), so the last CTA can hand the counter back at 0:
+        // the grid size may differ from call to call
         const unsigned int c = atomicAdd(my + 2 * W, 1u) + 1u;
-        last = (c == A.epoch * gridDim.x);          // the counter is never reset: epoch * grid size after this call
+        last = (c == gridDim.x);
+        if (last) my[2 * W] = 0u;
     }
     __syncthreads();
     if (!last) return;
@@ -132,8 +177,9 @@ using namespace gigs;
 
 extern "C" {
 
-int gigs_peer_allreduce(int32_t world, int32_t rank, const uint64_t* peer_bufs, const uint64_t* peer_flags, uint32_t epoch,
-                        int32_t n_spans, const uint64_t* span_begin, const uint64_t* span_end, int32_t n_ctas, void* stream)
+int gigs_peer_allreduce(int32_t world, int32_t rank, const uint64_t* peer_bufs, const uint64_t* peer_flags,
+                        uint64_t multicast_buf, uint32_t epoch, int32_t n_spans, const uint64_t* span_begin,
+                        const uint64_t* span_end, int32_t n_ctas, void* stream)
 {
     if (world < 1 || world > PR_MAX_WORLD || rank < 0 || rank >= world || n_spans < 0 || n_spans > PR_MAX_SPANS ||
         !peer_bufs || !peer_flags || epoch == 0 || (n_spans && (!span_begin || !span_end))) {
@@ -142,6 +188,7 @@ int gigs_peer_allreduce(int32_t world, int32_t rank, const uint64_t* peer_bufs, 
     }
     PeerArgs A;
     A.world = world; A.rank = rank; A.n_spans = n_spans; A.epoch = epoch;
+    A.mc = (float*)multicast_buf;
     for (int p = 0; p < world; ++p) {
         if (!peer_bufs[p] || !peer_flags[p]) { set_error("gigs_peer_allreduce: peer %d has a NULL pointer", p); return -1; }
         A.buf[p] = (float*)peer_bufs[p];
@@ -151,7 +198,14 @@ int gigs_peer_allreduce(int32_t world, int32_t rank, const uint64_t* peer_bufs, 
         if (span_end[s] < span_begin[s]) { set_error("gigs_peer_allreduce: span %d is reversed", s); return -1; }
         A.lo[s] = span_begin[s]; A.hi[s] = span_end[s];
     }
-    if (n_ctas <= 0) n_ctas = 32;       // the transfers are small: a few CTAs saturate the links without starving other streams
+    if (n_ctas <= 0) {
+        // scale with the bytes: ~128 KB of span per CTA, between 8 (latency-bound small exchanges: fewer CTAs to
+        // gather at the barriers) and 128 (an 80 MB first-stage buffer needs the loads of many SMs in flight)
+        uint64_t floats = 0;
+        for (int s = 0; s < n_spans; ++s) floats += span_end[s] - span_begin[s];
+        const uint64_t want = (floats * 4 / (uint64_t)world) / (128 * 1024) + 1;
+        n_ctas = (int)(want < 8 ? 8 : (want > 128 ? 128 : want));
+    }
     if (n_ctas > 148) n_ctas = 148;     // every CTA of every call must be counted exactly once by the counter protocol
     ProfScope ps(ST_PEER_ALLREDUCE, (cudaStream_t)stream);
     peer_allreduce_kernel<<<n_ctas, PR_THREADS, 0, (cudaStream_t)stream>>>(A);

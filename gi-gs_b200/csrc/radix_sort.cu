@@ -53,6 +53,103 @@ rs_histogram_kernel(const K* __restrict__ keys, const uint32_t n, const int pass
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Instance sort by tile id (<= RS_JOINT_BITS key bits): ONE histogram over the whole key gives everything the sort and
+// the blend need — the digit histogram of every pass (sum of the joint bins sharing that digit) and the tile ranges
+// (exclusive scan of the bins: in the sorted list tile t occupies [sum of bins < t, + bin t)), which the reference
+// finds by comparing neighbours of the sorted keys in a launch of its own (identifyTileRanges,
+// rasterizer_impl.cu:117-138).
+// ---------------------------------------------------------------------------------------------
+constexpr int RS_JOINT_BITS = 13;
+constexpr int RS_JOINT_BINS = 1 << RS_JOINT_BITS;
+
+__global__ void __launch_bounds__(512)
+rs_joint_histogram_kernel(const uint32_t* __restrict__ keys, const uint32_t n, const int bins, uint32_t* __restrict__ joint)
+{
+    extern __shared__ uint32_t s_joint[];
+    for (int i = threadIdx.x; i < bins; i += 512) s_joint[i] = 0;
+    __syncthreads();
+    const uint32_t stride = gridDim.x * 512 * 4;
+    for (uint32_t i = (blockIdx.x * 512 + threadIdx.x) * 4; i < n; i += stride) {
+        if (i + 3 < n) {
+            const uint4 k = *reinterpret_cast<const uint4*>(keys + i);
+            atomicAdd(&s_joint[k.x], 1u); atomicAdd(&s_joint[k.y], 1u); atomicAdd(&s_joint[k.z], 1u); atomicAdd(&s_joint[k.w], 1u);
+        } else {
+            for (uint32_t j = i; j < n; ++j) atomicAdd(&s_joint[keys[j]], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < bins; i += 512) {
+        const uint32_t v = s_joint[i];
+        if (v) atomicAdd(&joint[i], v);
+    }
+}
+
+// one CTA: joint -> per-pass digit bases (exclusive scans, written to hist[p][*]) and tile ranges
+__global__ void __launch_bounds__(1024)
+rs_joint_scan_kernel(const uint32_t* __restrict__ joint, const int bins, const int passes, const int digit_bits,
+                     const int end_bit, uint32_t* __restrict__ hist, uint2* __restrict__ ranges, const uint32_t num_tiles)
+{
+    __shared__ uint32_t s_hist[RS_MAX_PASSES][RS_MAX_RADIX];
+    __shared__ uint32_t s_warp[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < passes * RS_MAX_RADIX; i += 1024) (&s_hist[0][0])[i] = 0;
+    __syncthreads();
+    // each thread owns a run of consecutive bins: ranges need the running sum in bin order
+    const int per = (bins + 1023) / 1024;
+    const int b0 = tid * per;
+    uint32_t local = 0;
+    for (int k = 0; k < per; ++k) {
+        const int b = b0 + k;
+        if (b < bins) {
+            const uint32_t c = joint[b];
+            local += c;
+            if (c) {
+                for (int p = 0; p < passes; ++p) {
+                    const int shift = p * digit_bits;
+                    const int bits = min(digit_bits, end_bit - shift);
+                    atomicAdd(&s_hist[p][(b >> shift) & ((1 << bits) - 1)], c);
+                }
+            }
+        }
+    }
+    uint32_t inc = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t run = inc - local;
+    for (int w = 0; w < warp; ++w) run += s_warp[w];
+    for (int k = 0; k < per; ++k) {
+        const int b = b0 + k;
+        if (b < bins) {
+            const uint32_t c = joint[b];
+            // an empty tile keeps the (0, 0) the reference's zero-initialised ranges hold
+            if ((uint32_t)b < num_tiles) ranges[b] = c ? make_uint2(run, run + c) : make_uint2(0u, 0u);
+            run += c;
+        }
+    }
+    __syncthreads();
+    // exclusive scan of every pass's digit histogram: warp w handles pass w
+    if (warp < passes) {
+        uint32_t carry = 0;
+        for (int c0 = 0; c0 < RS_MAX_RADIX; c0 += 32) {
+            const uint32_t v = s_hist[warp][c0 + lane];
+            uint32_t in2 = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, in2, o);
+                if (lane >= o) in2 += t;
+            }
+            hist[warp * RS_MAX_RADIX + c0 + lane] = carry + in2 - v;
+            carry += __shfl_sync(0xffffffffu, in2, 31);
+        }
+    }
+}
+
 // exclusive scan of each pass's 256-bin histogram (in place)
 __global__ void __launch_bounds__(RS_MAX_RADIX) rs_scan_hist_kernel(uint32_t* __restrict__ hist)
 {
@@ -287,7 +384,8 @@ int radix_sort_passes(int bits) { return (bits + 7) / 8; }
 template <typename K>
 static int sort_pairs(uint64_t R, int end_bit, const K* keys_u, const uint32_t* vals_u, K* keys_a, uint32_t* vals_a,
                       K* keys_b, uint32_t* vals_b, uint32_t* hist, uint32_t* status, uint32_t* tickets,
-                      uint64_t zero_bytes, int pass_stage, cudaStream_t st)
+                      uint64_t zero_bytes, int pass_stage, cudaStream_t st, uint32_t* joint = nullptr,
+                      uint2* ranges = nullptr, uint32_t num_tiles = 0)
 {
     if (R == 0) return 0;
     if (R >= (1ull << 30)) {
@@ -300,11 +398,21 @@ static int sort_pairs(uint64_t R, int end_bit, const K* keys_u, const uint32_t* 
     const uint32_t status_tiles = (n + RS_MIN_TILE - 1) / RS_MIN_TILE;
     // hist, tickets and status are contiguous in the scratch blob: one memset
     GIGS_CUDA(cudaMemsetAsync(hist, 0, zero_bytes, st));
-    const uint32_t hblocks = min((n + 4095u) / 4096u, 148u * 8u);
-    rs_histogram_kernel<K><<<hblocks, RS_HTHREADS, 0, st>>>(keys_u, n, passes, digit_bits, end_bit, hist);
-    GIGS_LAUNCH_CHECK("rs_histogram_kernel");
-    rs_scan_hist_kernel<<<passes, RS_MAX_RADIX, 0, st>>>(hist);
-    GIGS_LAUNCH_CHECK("rs_scan_hist_kernel");
+    if (joint != nullptr && sizeof(K) == 4 && end_bit <= RS_JOINT_BITS) {
+        const int bins = 1 << end_bit;
+        const uint32_t hblocks = min((n + 16383u) / 16384u, 148u * 2u);
+        GIGS_SMEM_ATTR(rs_joint_histogram_kernel, RS_JOINT_BINS * 4);
+        rs_joint_histogram_kernel<<<hblocks, 512, (size_t)bins * 4, st>>>((const uint32_t*)keys_u, n, bins, joint);
+        GIGS_LAUNCH_CHECK("rs_joint_histogram_kernel");
+        rs_joint_scan_kernel<<<1, 1024, 0, st>>>(joint, bins, passes, digit_bits, end_bit, hist, ranges, num_tiles);
+        GIGS_LAUNCH_CHECK("rs_joint_scan_kernel");
+    } else {
+        const uint32_t hblocks = min((n + 4095u) / 4096u, 148u * 8u);
+        rs_histogram_kernel<K><<<hblocks, RS_HTHREADS, 0, st>>>(keys_u, n, passes, digit_bits, end_bit, hist);
+        GIGS_LAUNCH_CHECK("rs_histogram_kernel");
+        rs_scan_hist_kernel<<<passes, RS_MAX_RADIX, 0, st>>>(hist);
+        GIGS_LAUNCH_CHECK("rs_scan_hist_kernel");
+    }
     static const int cfg = env_int("GIGS_RS_CFG", 0);
 #define RS_GO(B, T, I) \
     return launch_passes<K, B, T, I>(n, end_bit, keys_u, vals_u, keys_a, vals_a, keys_b, vals_b, hist, status, tickets, status_tiles, pass_stage, st)
@@ -348,6 +456,18 @@ int launch_radix_sort32(uint64_t R, int end_bit, const uint32_t* keys_u, const u
 {
     return sort_pairs<uint32_t>(R, end_bit, keys_u, vals_u, keys_a, vals_a, keys_b, vals_b, hist, status, tickets, zero_bytes, pass_stage, st);
 }
+// the instance sort: keys are tile ids. joint = RS_JOINT_BINS zeroed words inside the zeroed scratch region. Returns 1
+// in *ranges_done when the tile ranges were produced from the histogram (keys of at most RS_JOINT_BITS bits).
+int launch_tile_sort(uint64_t R, int end_bit, const uint32_t* keys_u, const uint32_t* vals_u, uint32_t* keys_a,
+                     uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint32_t* hist, uint32_t* status,
+                     uint32_t* tickets, uint64_t zero_bytes, int pass_stage, uint32_t* joint, uint2* ranges,
+                     uint32_t num_tiles, int* ranges_done, cudaStream_t st)
+{
+    *ranges_done = (R > 0 && joint != nullptr && end_bit <= RS_JOINT_BITS) ? 1 : 0;
+    return sort_pairs<uint32_t>(R, end_bit, keys_u, vals_u, keys_a, vals_a, keys_b, vals_b, hist, status, tickets, zero_bytes,
+                                pass_stage, st, joint, ranges, num_tiles);
+}
+uint64_t radix_joint_bytes() { return (uint64_t)RS_JOINT_BINS * 4; }
 
 
 uint32_t radix_sort_tiles(uint64_t R) { return (uint32_t)((R + RS_MIN_TILE - 1) / RS_MIN_TILE); }

@@ -245,7 +245,7 @@ SYMBOLS = {
     "gigs_normal_loss": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _f, _f, _f, _vp, C.POINTER(C.c_uint64), _vp, _i32, _vp,
                                    _i32, _vp, _vp]),
     "gigs_densify_gather": (C.c_int, [_i32, _vp, _vp, _vp, _vp, _vp, _f, _i32, C.POINTER(GigsDensifyGroup), _vp]),
-    "gigs_peer_allreduce": (C.c_int, [_i32, _i32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_uint32, _i32,
+    "gigs_peer_allreduce": (C.c_int, [_i32, _i32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), _u64, C.c_uint32, _i32,
                                       C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), _i32, _vp]),
     "gigs_dist2": (C.c_int, [_i32, _vp, _vp, _vp, C.POINTER(C.c_uint64), _vp]),
     "gigs_ffma_peak": (C.c_int, [C.POINTER(C.c_double), _vp]),

@@ -15,7 +15,7 @@ from . import _lib
 class PeerBuffer:
     """A float32 buffer of `numel` elements per rank, peer-mapped, plus the flag block of the barrier protocol."""
 
-    N_CTAS = 32
+    N_CTAS = 0          # 0: the kernel scales its grid with the bytes of the call
 
     def __init__(self, numel: int, device, group=None):
         import torch.distributed as dist
@@ -32,6 +32,16 @@ class PeerBuffer:
         self._hf = symm.rendezvous(self.flags, group)
         self._bufs = (C.c_uint64 * self.world)(*[int(p) for p in self._h.buffer_ptrs])
         self._flags = (C.c_uint64 * self.world)(*[int(p) for p in self._hf.buffer_ptrs])
+        # NVLS: the allocator also maps the buffer through the NVSwitch multicast object when the fabric has one
+        self.multicast_ptr = 0
+        # (measured on 2 B200s the switch path is the slower one — the traffic is the same and multimem loads issue
+        # more slowly than plain peer loads; it pays from 4 ranks on, where it divides the link traffic by ~N/2)
+        want = os.environ.get("GIGS_PEER_NVLS", "auto")
+        if want == "1" or (want == "auto" and self.world >= 4):
+            try:
+                self.multicast_ptr = int(getattr(self._h, "multicast_ptr", 0) or 0)
+            except Exception:
+                self.multicast_ptr = 0
         self.epoch = 0
         torch.cuda.synchronize(device)
         dist.barrier(group)          # every rank's buffers are zeroed before anybody's first call can touch them
@@ -50,8 +60,9 @@ class PeerBuffer:
             hi = (C.c_uint64 * len(part))(*[b for _, b in part])
             self.epoch += 1
             with torch.cuda.device(self.buf.device):
-                _lib.check(L.gigs_peer_allreduce(self.world, self.rank, self._bufs, self._flags, self.epoch, len(part), lo,
-                                                 hi, self.N_CTAS, torch.cuda.current_stream().cuda_stream),
+                _lib.check(L.gigs_peer_allreduce(self.world, self.rank, self._bufs, self._flags, self.multicast_ptr,
+                                                 self.epoch, len(part), lo, hi, self.N_CTAS,
+                                                 torch.cuda.current_stream().cuda_stream),
                            "gigs_peer_allreduce")
 
     def error_epoch(self) -> int:

@@ -569,12 +569,18 @@ int gigs_densify_gather(int32_t n_out, const int32_t* src_index, const int8_t* k
  * span over all ranks' buffers in rank order and stores it into all of them), a second barrier.
  * peer_bufs[world] / peer_flags[world] (HOST arrays of device addresses): every rank's gradient buffer and flag block as
  * mapped into THIS process (symmetric allocations; entry `rank` is the local one). A flag block is 2*world + 2 uint32,
- * zero before the first call. epoch = 1, 2, 3, ... must advance by one per call and agree on all ranks, as must the
- * spans (float offsets [begin, end) into the buffer) and n_ctas (0 = default 32; fixed for the lifetime of a flag block).
- * Sums are bit-identical on all ranks and independent of timing. A peer that does not show up within ~2 s sets the
- * local error word flags[2*world + 1] = epoch instead of hanging the device. */
-int gigs_peer_allreduce(int32_t world, int32_t rank, const uint64_t* peer_bufs, const uint64_t* peer_flags, uint32_t epoch,
-                        int32_t n_spans, const uint64_t* span_begin, const uint64_t* span_end, int32_t n_ctas, void* stream);
+ * zero before the first call; calls on one flag block must be stream-ordered. multicast_buf: the NVLS multicast mapping
+ * of the same buffer (0 if the fabric offers none): 16-byte-aligned spans are then reduced by the switch
+ * (multimem.ld_reduce / multimem.st) instead of N peer loads and N peer stores per element. epoch = 1, 2, 3, ... must
+ * advance by one per call and agree on all ranks, as must the spans (float offsets [begin, end) into the buffer).
+ * n_ctas: 0 = scaled with the bytes (8 .. 128). Without multicast the sums are formed in rank order: bit-identical on
+ * all ranks and independent of timing; with it every rank still receives the same bits (one rank reduces a slice and
+ * broadcasts it). A peer that has not arrived after about a minute of GPU clock is fatal: the error word
+ * flags[2*world + 1] = epoch is set and the kernel traps (the process's next CUDA call fails) instead of the ranks
+ * training on with unreduced gradients. */
+int gigs_peer_allreduce(int32_t world, int32_t rank, const uint64_t* peer_bufs, const uint64_t* peer_flags,
+                        uint64_t multicast_buf, uint32_t epoch, int32_t n_spans, const uint64_t* span_begin,
+                        const uint64_t* span_end, int32_t n_ctas, void* stream);
 
 /* Replaces distCUDA2 / SimpleKNN::knn (/root/reference/submodules/simple-knn/spatial.cu,
  * simple_knn.cu:165-207): mean squared distance to the 3 nearest other points.

@@ -49,11 +49,17 @@ def test_oracle_matches_grid_sample_away_from_the_seam():
 @pytest.mark.parametrize("EH,EW,R", [(1024, 2048, 256), (64, 128, 16), (100, 333, 512)])
 def test_kernel_matches_oracle(EH, EW, R):
     from gigs import light
-    g = torch.Generator().manual_seed(EH)
-    env = torch.rand(EH, EW, 3, generator=g) * 4.0
+    # a smooth HDR-like map: the lookup's (u, v) come out of atan2 / acos, whose last bits differ between the CPU and
+    # CUDA math libraries; on smooth data that moves a texel value by ~1e-6
+    yy, xx = torch.meshgrid(torch.linspace(0, 1, EH), torch.linspace(0, 1, EW), indexing="ij")
+    env = torch.stack([2.0 + torch.sin(6.28 * xx) * torch.cos(3.0 * yy), 1.0 + xx * yy, 3.0 * torch.exp(-4.0 * (yy - 0.3) ** 2)],
+                      -1).contiguous()
     want = O.latlong_to_cubemap(env, R)
     got = light.latlong_to_cubemap(env.cuda(), [R, R]).cpu()
-    d = (got - want).abs()
-    # atan2 / acos differ between the CPU and CUDA math libraries in the last bits: a texel whose (u, v) sits on a
-    # pixel boundary may take the neighbouring pair of samples with weight ~0, which is the same value to 1e-4
-    assert float(d.max()) < 2e-3 and float((d > 1e-4).float().mean()) < 1e-4, float(d.max())
+    assert float((got - want).abs().max()) < 2e-5
+    # white noise up to 4.0 (neighbouring texels unrelated): an error of 3e-7 in u is 6e-4 of a texel at 2048 columns,
+    # times the difference of two neighbours
+    g = torch.Generator().manual_seed(EH)
+    noise = torch.rand(EH, EW, 3, generator=g) * 4.0
+    d = (light.latlong_to_cubemap(noise.cuda(), [R, R]).cpu() - O.latlong_to_cubemap(noise, R)).abs()
+    assert float(d.max()) < 4.0 * EW * 2e-6 + 1e-5, float(d.max())
