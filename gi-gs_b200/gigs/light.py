@@ -299,9 +299,17 @@ class PrefilteredLight:
     MIN_ROUGHNESS = 0.08
     MAX_ROUGHNESS = 0.5
 
-    def __init__(self, base: torch.Tensor, cutoff: float = 0.99, stored_operators: bool = True):
-        """stored_operators: evaluate the filter weights once into HBM (layout.weights_bytes, 1.3 GB at base_res 256)
-        and stream them every step; False recomputes them on the fly (no extra memory, several times slower)."""
+    # "auto": store the operators only when they fit this share of the device's FREE memory and this absolute budget
+    # (1.4 GB at base_res 256, ~4x per doubling of the resolution: 5.6 GB at 512, 22 GB at 1024)
+    STORED_FREE_FRACTION = 0.25
+    STORED_MAX_BYTES = 12 << 30
+
+    def __init__(self, base: torch.Tensor, cutoff: float = 0.99, stored_operators="auto"):
+        """stored_operators: True evaluates the filter weights once into HBM (layout.weights_bytes, 1.4 GB at base_res
+        256) and streams them every step; False recomputes them on the fly (no extra memory, ~4x slower per build:
+        right for a relight sweep that builds once). "auto" (default) stores them when layout.weights_bytes is within
+        STORED_FREE_FRACTION of the free device memory and STORED_MAX_BYTES, and says which it chose in
+        `self.stored_operators` / `self.stored_operator_bytes`."""
         if base.dim() != 4 or base.shape[0] != 6 or base.shape[1] != base.shape[2] or base.shape[3] != 3:
             raise RuntimeError(f"Bad shape for base: {tuple(base.shape)} (expected [6,res,res,3])")
         if not base.is_cuda or base.dtype != torch.float32 or not base.is_contiguous():
@@ -326,6 +334,12 @@ class PrefilteredLight:
         with torch.cuda.device(self.device):
             check(_L.gigs_light_prepare(C.byref(lay), self.ws.data_ptr(), _stream()), "gigs_light_prepare")
             self.weights = None
+            if stored_operators == "auto":
+                free, _total = torch.cuda.mem_get_info(self.device)
+                stored_operators = (int(lay.weights_bytes) <= self.STORED_MAX_BYTES
+                                    and int(lay.weights_bytes) <= self.STORED_FREE_FRACTION * free)
+            self.stored_operators = bool(stored_operators)
+            self.stored_operator_bytes = int(lay.weights_bytes) if stored_operators else 0
             if stored_operators:
                 self.weights = torch.empty(lay.weights_bytes, dtype=torch.uint8, device=self.device)
                 check(_L.gigs_light_weights(C.byref(lay), self.ws.data_ptr(), self.weights.data_ptr(), _stream()),

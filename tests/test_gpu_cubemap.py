@@ -236,3 +236,32 @@ def test_stored_operator_matches_reference_wsum_bit_for_bit():
         assert torch.equal(o[..., 3], fl.wsum[lvl]), f"level {lvl}: wsum differs in {(o[..., 3] != fl.wsum[lvl]).sum().item()} texels"
         r = o[..., 0:3] / o[..., 3:]
         assert (fl.specular[lvl] - r).abs().max().item() <= TEX_TOL * r.abs().max().item()
+
+
+def test_prefiltered_light_storage_policy_and_base_res_512():
+    """The stored filter operators grow ~4x per doubling of the base resolution (1.4 GB at 256, 5.6 GB at 512):
+    "auto" stores them only inside its memory budget and falls back to the on-the-fly filter otherwise; both variants
+    give the same textures at base_res 512."""
+    dev = "cuda:0"
+    base = _cube(512, 21, dev)
+    auto = GL.PrefilteredLight(base)
+    assert auto.stored_operators and 4 << 30 < auto.stored_operator_bytes < 8 << 30
+    fly = GL.PrefilteredLight(base, stored_operators=False)
+    assert not fly.stored_operators and fly.stored_operator_bytes == 0 and fly.weights is None
+    auto.build(); fly.build()
+    torch.cuda.synchronize()
+    assert len(auto.specular) == 6 and auto.specular[0].shape[1] == 512
+    for a, b in zip(auto.specular + [auto.diffuse], fly.specular + [fly.diffuse]):
+        assert float((a.detach() - b.detach()).abs().max()) <= 5e-6 * float(b.detach().abs().max()) + 1e-7
+    const = GL.PrefilteredLight(torch.full((6, 512, 512, 3), 0.7, device=dev), stored_operators=False)
+    const.build()
+    for t in const.specular + [const.diffuse]:
+        assert float((t.detach() - 0.7).abs().max()) < 2e-5
+    # a budget below the operators' size: automatic fall-back
+    old = GL.PrefilteredLight.STORED_MAX_BYTES
+    try:
+        GL.PrefilteredLight.STORED_MAX_BYTES = 1 << 30
+        small = GL.PrefilteredLight(_cube(256, 3, dev))
+        assert not small.stored_operators
+    finally:
+        GL.PrefilteredLight.STORED_MAX_BYTES = old
