@@ -300,9 +300,9 @@ class PrefilteredLight:
     MAX_ROUGHNESS = 0.5
 
     # "auto": store the operators only when they fit this share of the device's FREE memory and this absolute budget
-    # (1.4 GB at base_res 256, ~4x per doubling of the resolution: 5.6 GB at 512, 22 GB at 1024)
+    # (1.4 GB at base_res 256, 11.3 GB at 512: ~8x per doubling — more texels, each with a cone of more texels)
     STORED_FREE_FRACTION = 0.25
-    STORED_MAX_BYTES = 12 << 30
+    STORED_MAX_BYTES = 8 << 30
 
     def __init__(self, base: torch.Tensor, cutoff: float = 0.99, stored_operators="auto"):
         """stored_operators: True evaluates the filter weights once into HBM (layout.weights_bytes, 1.4 GB at base_res

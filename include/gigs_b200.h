@@ -226,16 +226,9 @@ int gigs_gi_count_probes(int32_t W, int32_t H, float fx, float fy, float radius,
                          float delta, int32_t step, int32_t start, const float* normal, const float* pos,
                          const float* block_minmax, int32_t block, uint64_t* count, void* stream);
 
-/* gigs_ssao through the queued march with its work counters: stats5 (device) = {directions queued, unsure probes,
- * exact probes evaluated, phase-B rounds, phase-B probe trips (warp level)}. Measurement helper. */
-int gigs_gi_queue_stats(int32_t W, int32_t H, float fx, float fy, float radius, float bias, float thick, float delta,
-                        int32_t step, int32_t start, const float* normal, const float* pos, float* occlusion,
-                        void* scratch, uint64_t scratch_bytes, uint64_t* stats5, void* stream);
-
-/* Tuning knobs of the march: 3 = the queued march (approximate classification of every probe, exact evaluation of the
- * compacted unsure ones; default), 1 / 2 = that many probe pairs evaluated exactly per inner step, 0 = the
- * reference-order loop for every pixel; block_test: whether variants 1 / 2 test the block (min, max) of the depth plane
- * before a probe's depth gather. Results are bit-identical for every setting. Process-wide; defaults 3, 1. */
+/* Tuning knobs of the march: probe pairs evaluated per inner step (1 or 2; 0 = the reference-order loop for every
+ * pixel), and whether the block (min, max) depth test runs before a probe's depth gather. Results are bit-identical
+ * for every setting. Process-wide; defaults 1, 1. */
 int gigs_gi_tune(int32_t pairs_per_step, int32_t block_test);
 
 /* Replaces SSR_BACKWARD (rasterize_points.cu:479-510). The reference's Python never calls its

@@ -210,10 +210,9 @@ def test_c2_full_size_forward_backward_and_gi_vs_reference():
 
 
 @needs_ref
-@pytest.mark.parametrize("pairs,block_test", [(0, 0), (1, 0), (1, 1), (2, 1)])
+@pytest.mark.parametrize("pairs,block_test", [(0, 0), (1, 0), (2, 1)])
 def test_gi_march_tuning_variants_are_bit_identical(pairs, block_test):
-    """Every setting of gigs_gi_tune gives the reference's bits (the default, the queued march (3, 1), is what the
-    other tests run)."""
+    """Every setting of gigs_gi_tune gives the reference's bits (default (1, 1) is covered by the other tests)."""
     import diff_gaussian_rasterization as dgr
     from gigs import _lib
     L = _lib.load()
@@ -234,7 +233,7 @@ def test_gi_march_tuning_variants_are_bit_identical(pairs, block_test):
         c_o, a_o = dgr._C.SSR(W, H, fx, fy, *gi, fo["normal_view"], p_o, rgb, fo["albedo"], fo["roughness"],
                               fo["metallic"], F0)
     finally:
-        _lib.check(L.gigs_gi_tune(3, 1), "gigs_gi_tune")
+        _lib.check(L.gigs_gi_tune(1, 1), "gigs_gi_tune")
     assert torch.equal(occ_o, occ_r) and torch.equal(c_o, c_r) and torch.equal(a_o, a_r)
     # odd trip counts (step - start not a multiple of the probes per inner step) and a step that is not a power of two
     for step, start in ((16, 9), (16, 13), (12, 5)):

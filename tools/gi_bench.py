@@ -102,17 +102,10 @@ def main():
                                                   mm.data_ptr(), B, cnt.data_ptr(), st), "count")
                 torch.cuda.synchronize()
                 out["hiz_kept_fraction"][f"B{B}_{prec}"] = int(cnt[1].item()) / max(1, int(cnt[0].item()))
-    st5 = torch.zeros(5, dtype=torch.int64, device=dev)
-    _lib.check(L.gigs_gi_tune(3, 1), "tune")
-    _lib.check(L.gigs_gi_queue_stats(*args, m["normal_view"].data_ptr(), m["depth_pos"].data_ptr(), occ.data_ptr(),
-                                     scr.data_ptr(), scr.numel(), st5.data_ptr(), st), "stats")
-    torch.cuda.synchronize()
-    out["queue_stats_ssao"] = dict(zip(("directions_queued", "unsure_probes", "exact_probes", "phaseB_rounds", "phaseB_trips"),
-                                       [int(v) for v in st5.tolist()]))
     out["probes_upper_bound"] = W * H * 512 * (gi["step"] - gi["start"])
     base = None
     outs = {}
-    for v in (0, 1, 11, 13):              # variant; +10 = with the block (min, max) test; 13 = the queued march
+    for v in (0, 1, 2, 11, 12):           # pairs per step; +10 = with the block (min, max) test
         _lib.check(L.gigs_gi_tune(v % 10, v // 10), "tune")
         ssao(); ssr(); torch.cuda.synchronize()
         cur = (occ.clone(), col.clone(), abd.clone())
@@ -124,7 +117,7 @@ def main():
             rec["bit_identical_to_variant0"] = [same(a, b) for a, b in zip(cur, base)]
             rec["max_abs_diff"] = [float((a - b).abs().nan_to_num(0).max()) for a, b in zip(cur, base)]
         out["variants"][str(v)] = rec
-    _lib.check(L.gigs_gi_tune(3, 1), "tune")
+    _lib.check(L.gigs_gi_tune(1, 1), "tune")
     try:
         import refshim
         if refshim.available():

@@ -1,76 +1,41 @@
 #!/usr/bin/env python
-"""Summarise an .ncu-rep (ncu --set full) into the few numbers the design decisions rest on.
-usage: python tools/ncu_summary.py gpurun_out/x.ncu-rep [more.ncu-rep ...] > profiles/x.txt"""
+"""Key metrics of every kernel launch in an .ncu-rep (ncu --set full), as the text summary kept under profiles/.
+usage: python tools/ncu_summary.py x.ncu-rep > profiles/x_ncu.txt"""
 import csv
 import io
 import subprocess
 import sys
 
-KEYS = [
-    ("gpu__time_duration.sum", "duration"),
-    ("launch__grid_size", "grid"), ("launch__block_size", "block"), ("launch__registers_per_thread", "regs/thread"),
-    ("launch__shared_mem_per_block_dynamic", "dyn smem/block"), ("launch__shared_mem_per_block_static", "static smem/block"),
-    ("launch__occupancy_limit_registers", "occ limit regs (blocks)"), ("launch__occupancy_limit_shared_mem", "occ limit smem (blocks)"),
-    ("launch__occupancy_limit_warps", "occ limit warps (blocks)"),
-    ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"),
-    ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput %"),
-    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy %"),
-    ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "FMA pipe % (inst)"),
-    ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "FMA pipe cycles active %"),
-    ("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "ALU pipe cycles active %"),
-    ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "XU (MUFU) pipe %"),
-    ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "LSU pipe %"),
-    ("smsp__inst_executed.sum", "warp instructions"),
-    ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "L1/TEX throughput %"),
-    ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem bank conflicts"),
-    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem wavefronts"),
-    ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 throughput %"),
-    ("lts__t_sector_hit_rate.pct", "L2 hit rate %"),
-    ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "DRAM throughput %"),
-    ("dram__bytes_read.sum", "DRAM read"), ("dram__bytes_write.sum", "DRAM write"),
-    ("lts__t_sectors_op_atom.sum", "L2 atomic sectors"), ("lts__t_sectors_op_red.sum", "L2 red sectors"),
-    ("smsp__thread_inst_executed_per_inst_executed.ratio", "active threads / warp inst"),
+WANT = [
+    "gpu__time_duration.sum", "launch__registers_per_thread", "launch__occupancy_limit_registers",
+    "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+    "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.sum",
+    "l1tex__throughput.avg.pct_of_peak_sustained_active", "l1tex__t_sector_hit_rate.pct",
+    "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sectors.sum", "lts__t_sector_hit_rate.pct", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
 ]
-
-
-def raw_rows(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(io.StringIO(out)))
-    i0 = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
-    return rows[i0], rows[i0 + 1], rows[i0 + 2:]
+STALLS = "smsp__average_warps_issue_stalled_"
 
 
 def main():
-    for path in sys.argv[1:]:
-        hdr, units, rows = raw_rows(path)
-        col = {h: i for i, h in enumerate(hdr)}
-        for r in rows:
-            print(f"== {path.split('/')[-1]} :: {r[col['Kernel Name']][:110]}")
-            for k, label in KEYS:
-                if k in col and r[col[k]] != "":
-                    print(f"   {label:32s} {r[col[k]]:>16s} {units[col[k]]}")
-            stalls = []
-            for h, i in col.items():
-                if h.startswith("smsp__average_warp") and h.endswith("_per_issue_active.ratio") and "latency_issue_stalled" in h:
-                    try:
-                        stalls.append((float(r[i]), h.split("issue_stalled_")[1].replace("_per_issue_active.ratio", "")))
-                    except ValueError:
-                        pass
-                elif h.startswith("smsp__average_warps_issue_stalled") and h.endswith("_per_issue_active.ratio"):
-                    try:
-                        stalls.append((float(r[i]), h.split("issue_stalled_")[1].replace("_per_issue_active.ratio", "")))
-                    except ValueError:
-                        pass
-            stalls.sort(reverse=True)
-            if stalls:
-                print("   warp stall reasons (warps per issue-active cycle): " +
-                      ", ".join(f"{n}={v:.2f}" for v, n in stalls[:7]))
-            dr, dw = col.get("dram__bytes_read.sum"), col.get("dram__bytes_write.sum")
-            if dr is not None and r[dr]:
-                mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-                tot = float(r[dr]) * mult.get(units[dr], 1.0) + float(r[dw]) * mult.get(units[dw], 1.0)
-                print(f"   traffic (DRAM read+write)        {tot / 1e6:16.3f} MB per launch")
-            print()
+    out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    col = {h: i for i, h in enumerate(hdr)}
+    print(f"# {sys.argv[1]}: ncu --set full --clock-control none; one block per captured launch")
+    for r in rows[2:]:
+        print(f"\n== {r[col['Kernel Name']]}  grid {r[col['Grid Size']]} block {r[col['Block Size']]}")
+        for w in WANT:
+            if w in col:
+                print(f"  {w:78s} {r[col[w]]} {units[col[w]]}")
+        st = sorted(((float(r[i] or 0), h) for h, i in col.items() if h.startswith(STALLS) and h.endswith("per_issue_active.ratio")),
+                    reverse=True)
+        print("  stall reasons (warps per issue-active cycle): " +
+              ", ".join(f"{h[len(STALLS):-len('_per_issue_active.ratio')]} {v:.2f}" for v, h in st[:7]))
 
 
 if __name__ == "__main__":
