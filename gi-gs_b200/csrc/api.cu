@@ -181,8 +181,14 @@ static int check_common(int P, const GigsCamera& c)
 // depend on num_rendered) is queued behind the copy, so the GPU keeps working while the host sizes the binning blob.
 int read_back_num_rendered(GigsRasterFwd* a, const Layout& L, cudaStream_t st)
 {
-    static thread_local cudaEvent_t ev = nullptr;
-    if (!ev) GIGS_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    // an event belongs to the device that was current when it was created: one per (thread, device)
+    constexpr int MAX_DEV = 64;
+    static thread_local cudaEvent_t evs[MAX_DEV] = {};
+    int dev = 0;
+    GIGS_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= MAX_DEV) { set_error("device index %d out of range", dev); return -1; }
+    if (!evs[dev]) GIGS_CUDA(cudaEventCreateWithFlags(&evs[dev], cudaEventDisableTiming));
+    cudaEvent_t ev = evs[dev];
     static thread_local uint32_t* pinned = nullptr;
     if (!a->pinned_num_rendered && !pinned) GIGS_CUDA(cudaMallocHost((void**)&pinned, 64));
     uint32_t* dst = a->pinned_num_rendered ? a->pinned_num_rendered : pinned;

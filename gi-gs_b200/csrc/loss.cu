@@ -14,6 +14,7 @@
 // HBM-bound in principle (forward: 8 B read + 12 B written per element; backward: 20 B read + 4 B written), in
 // practice bound by the shared-memory passes; 800x800x3 is 1.9 M elements, the pair of kernels ~50 us.
 #include <cmath>
+#include <mutex>
 #include "common.cuh"
 
 namespace gigs {
@@ -409,15 +410,19 @@ int gigs_image_loss(int32_t C, int32_t W, int32_t H, const float* image, const f
     }
     if (grid.z > 65535 || grid.y > 65535) { set_error("gigs_image_loss: image too large"); return -1; }
     cudaStream_t st = (cudaStream_t)stream;
-    static bool w_set = false;   // the window is a constant of the algorithm; uploaded once per process and device
-    static int w_dev = -1;
-    int dev = 0;
-    GIGS_CUDA(cudaGetDevice(&dev));
-    if (!w_set || w_dev != dev) {
-        const SsimW Wt = ssim_window();
-        GIGS_CUDA(cudaMemcpyToSymbolAsync(c_ssim_w, Wt.w, sizeof(Wt.w), 0, cudaMemcpyHostToDevice, st));
-        w_set = true;
-        w_dev = dev;
+    // the window is a constant of the algorithm: uploaded once per device (blocking copy, so that no stream of that
+    // device can run the kernel before the constant is there), under a mutex
+    {
+        static std::mutex w_mutex;
+        static unsigned long long w_devices = 0ull;
+        int dev = 0;
+        GIGS_CUDA(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lock(w_mutex);
+        if (dev < 0 || dev >= 64 || !((w_devices >> dev) & 1ull)) {
+            const SsimW Wt = ssim_window();
+            GIGS_CUDA(cudaMemcpyToSymbol(c_ssim_w, Wt.w, sizeof(Wt.w), 0, cudaMemcpyHostToDevice));
+            if (dev >= 0 && dev < 64) w_devices |= 1ull << dev;
+        }
     }
     char* base = (char*)scratch;
     float* dmu = grad_image ? (float*)base : nullptr;

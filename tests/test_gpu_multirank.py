@@ -157,3 +157,31 @@ def test_two_rank_first_stage_step_matches_single_process(tmp_path, peer):
             assert float((r["grad"][lo:hi] - ref[lo:hi]).norm() / ref[lo:hi].norm()) <= 1e-4, k
     assert torch.allclose(r["accum"], st.xyz_gradient_accum.cpu(), rtol=1e-4, atol=1e-9)
     assert torch.equal(r["denom"], st.denom.cpu()) and torch.equal(r["radii"], st.max_radii2D.cpu())
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_second_device_in_the_same_process():
+    """cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: the frame on cuda:1 after cuda:0 in ONE
+    process (round 1 kept one process-wide flag per kernel and would have launched with the 48 KB default there)."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gi-gs_b200"))
+    from gigs import scene, shade, step as gstep
+    P, W, H = 5000, 160, 128
+    raw = scene.make_scene(P, seed=1, regime="trained")
+    gi = dict(radius=0.8, bias=0.01, thick=0.05, delta=0.0625, step=16, start=8)
+    out = []
+    for d in (0, 1, 0):
+        dev = torch.device("cuda", d)
+        torch.cuda.set_device(dev)
+        params = gstep.GaussianParams(raw, dev, light=scene.make_light(0, base_res=64))
+        cam = scene.orbit_camera(1, 8, W, H).to(dev)
+        lut = shade.make_brdf_lut(64, 64).to(dev)
+        rays = scene.canonical_rays(cam, dev)
+        gt = torch.rand(3, H, W, generator=torch.Generator().manual_seed(3)).to(dev)
+        loss = gstep.training_step(params, cam, params.light(), lut, rays, gt, torch.zeros(3, device=dev), gi)
+        torch.cuda.synchronize(dev)
+        out.append((float(loss), params.last_workspace.map("render_rgb").cpu(), params.flat_grad.cpu()))
+    torch.cuda.set_device(0)
+    assert out[0][0] == out[1][0] == out[2][0]
+    assert torch.equal(out[0][1], out[1][1]) and torch.equal(out[0][1], out[2][1])
+    assert float((out[0][2] - out[1][2]).norm()) <= 1e-4 * float(out[0][2].norm())
