@@ -798,6 +798,48 @@ def run_ours(args):
                 line["variants"]["unfused_operator_path"] = {
                     "value": 1e3 / msu, "unit": "frames/s", "ms_per_step": msu,
                     "note": "same frame through GaussianRasterizer / pbr_shading / Gaussian_SSR modules + autograd"}
+            # ---- BASELINE configs[0] (C1) and configs[2] (C3) as timings on one GPU (parity of both: tests/) ----
+            if world == 1:
+                try:
+                    from gigs import frame as gframe2, renderer as grend
+                    raw1 = scene.make_scene(100000, seed=0)
+                    g1 = scene.activate(raw1, dev)
+                    c1 = {}
+                    for st_ in (64, 8):
+                        gi1 = dict(GI_BASE, start=st_)
+
+                        def c1_eval():
+                            gframe2.pbr_frame_eval(g1, cams[0], light, lut, rays, bg, gi1, inference=False)
+                        c1[f"fused_frame_start{st_}_ms"] = ev_all(c1_eval, 10, warm=2)
+                    with torch.no_grad():
+                        c1["operator_path_start64_ms"] = ev_all(
+                            lambda: grend.pbr_forward(cams[0], g1, light, lut, rays, bg, gi=dict(GI_BASE, start=64)), 5, warm=2)
+                    c1["note"] = ("100k Gaussians, 800x800: G-buffer forward + SSAO + shading + SSR, forward only (the "
+                                  "configuration the CPU transcription is checked on)")
+                    line["variants"]["c1_100k_forward_gi"] = c1
+                    del raw1, g1
+                    Pb, Wb, Hb = 6_000_000, 1237, 822
+                    rawb = scene.make_scene(Pb, seed=0, regime="trained", shape="bicycle")
+                    pb_ = gstep.GaussianParams(rawb, dev, light=scene.make_light(0))
+                    del rawb
+                    camb = scene.look_at_camera([4.0, 0.0, 1.0], [0.0, 0.0, 0.0], Wb, Hb, fx=1040.0).to(dev)
+                    raysb = scene.canonical_rays(camb, dev)
+                    gtb = torch.rand(3, Hb, Wb, device=dev)
+
+                    def c3_step():
+                        pb_.zero_grad(fused_only=True)
+                        gstep.training_step(pb_, camb, pb_.light(), lut, raysb, gtb, bg, gi, brdf_tv_weight=1.0)
+                    ms3 = ev_all(c3_step, 5, warm=2)
+                    line["variants"]["c3_bicycle_6m"] = {
+                        "value": 1e3 / ms3, "unit": "frames/s", "ms_per_step": ms3,
+                        "num_rendered": int(pb_.last_workspace.num_rendered), "resolution": [Wb, Hb],
+                        "note": "bicycle-shaped synthetic scene, 6M Gaussians, SH degree 3, --metallic, 1237x822, PBR-stage "
+                                "training frame fwd+bwd"}
+                    del pb_, camb, raysb, gtb
+                    gframe2._workspaces.clear()
+                    torch.cuda.empty_cache()
+                except Exception as ex:
+                    line["variants"]["c1_c3"] = {"failed": f"{type(ex).__name__}: {ex}"}
             # ---- the reference's own CUDA kernels on the same inputs (second reported point) ----
             if world == 1:
                 line["ref_cuda"] = ref_cuda_point(args, params, cams[0], bg, dev)
