@@ -5,7 +5,7 @@
 
 The inputs are regenerated from (P, seed, regime, W, H, camera k/K) by gigs.scene, so only the outputs and the
 upstream gradients (seeded) are stored. These fixtures pin the CPU oracle (tests/test_oracle_golden.py) and
-are re-checked against our kernels on the GPU (tests/test_gpu_golden.py).
+are re-checked against our kernels on the GPU (tests/test_gpu_parity.py::test_against_committed_golden_vectors).
 """
 import os
 import sys

@@ -73,7 +73,8 @@ def main():
         tot += s
     srcs = {}
     print(f"== {name[:110]}   total stall samples {tot}")
-    for (f, l), (s, n) in sorted(per_line.items(), key=lambda kv: -kv[1][0])[:top]:
+    by_inst = os.environ.get("BY_INST") is not None      # BY_INST=1: rank by executed instructions instead of stalls
+    for (f, l), (s, n) in sorted(per_line.items(), key=lambda kv: -kv[1][1 if by_inst else 0])[:top]:
         if f not in srcs:
             p = os.path.join(ROOT, "gi-gs_b200", "csrc", f)
             srcs[f] = open(p).read().splitlines() if os.path.exists(p) else []
