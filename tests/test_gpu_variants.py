@@ -240,3 +240,57 @@ def test_gi_march_tuning_variants_are_bit_identical(pairs, block_test):
         gi2 = (0.8, 0.01, 0.05, 0.0625, step, start)
         assert torch.equal(dgr._C.SSAO(W, H, fx, fy, *gi2, fo["normal_view"], p_o),
                            refshim.ssao(W, H, fx, fy, *gi2, fo["normal_view"], p_o)), (step, start)
+
+
+@needs_ref
+@pytest.mark.parametrize("W,H", [(333, 257), (1920, 1080), (64, 48)])
+def test_gi_march_special_values_and_sizes_vs_reference(W, H):
+    """The march on synthetic G-buffers that exercise every exit of the fast path: NaN / zero / infinite normals,
+    normals parallel to the up vector (NaN tangent frame), positions that are NaN, infinite, huge (beyond the fast
+    path's range), exactly zero, behind the camera, and depths for which z + 1e-7 is exactly 0 or denormal (the shared
+    reciprocal's range test) — at sizes that are not multiples of the tile, and at one large enough for 32-pixel
+    blocks in the block test. Everything must equal the reference's kernels bit for bit."""
+    import diff_gaussian_rasterization as dgr
+    g = torch.Generator().manual_seed(W * 7 + H)
+    fx, fy = 0.9 * W, 0.9 * W
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    z = 3.0 + 0.8 * torch.sin(xs / 37.0) * torch.cos(ys / 23.0) + 0.05 * torch.rand(H, W, generator=g)
+    pos = torch.stack([(xs - W / 2) / fx * z, (ys - H / 2) / fy * z, z])
+    nrm = torch.nn.functional.normalize(torch.randn(3, H, W, generator=g) * 0.3 + torch.tensor([0.0, 0.0, -1.0])[:, None, None], dim=0)
+    n = H * W
+    idx = torch.randperm(n, generator=g)
+    flat_n, flat_p = nrm.reshape(3, n).clone(), pos.reshape(3, n).clone()
+    k = max(4, n // 400)
+
+    def take(i):
+        return idx[i * k:(i + 1) * k]
+    flat_n[:, take(0)] = float("nan")
+    flat_n[:, take(1)] = 0.0
+    flat_n[0, take(2)] = float("inf")
+    flat_n[:, take(3)] = torch.tensor([0.0, 1.0, 0.0])[:, None]          # parallel to `up`: NaN tangent
+    flat_n[:, take(4)] = torch.tensor([0.0, -2.5, 0.0])[:, None]
+    flat_p[2, take(5)] = float("nan")
+    flat_p[0, take(6)] = float("nan")
+    flat_p[1, take(7)] = float("inf")
+    flat_p[:, take(8)] = 0.0
+    flat_p[:, take(9)] = torch.tensor([1.0e8, -3.0e7, 5.0e8])[:, None]  # beyond the fast path's bounds
+    flat_p[2, take(10)] = -2.0                                           # behind the camera
+    flat_p[2, take(11)] = -0.0000001                                     # z + 1e-7 == 0 at the pixel itself
+    flat_p[2, take(12)] = 1.0e-30
+    flat_p[:, take(13)] = torch.tensor([3.0e5, 2.0e5, 9.0e5])[:, None]  # large but inside the fast path's bounds
+    nrm, pos = flat_n.reshape(3, H, W).to(DEV).contiguous(), flat_p.reshape(3, H, W).to(DEV).contiguous()
+    rgb = torch.rand(3, H, W, generator=g).to(DEV)
+    rgb[:, 5, 7] = float("nan")                                           # a radiance texel that poisons what hits it
+    alb = torch.rand(3, H, W, generator=g).to(DEV)
+    rough = torch.rand(1, H, W, generator=g).to(DEV)
+    met = torch.rand(1, H, W, generator=g).to(DEV)
+    F0 = (1.0 - met) * 0.04 + alb * met
+    for gi in ((0.8, 0.01, 0.05, 0.0625, 16, 8), (0.3, 0.02, 0.1, 0.125, 8, 3), (0.8, 0.01, 0.05, 0.0625, 16, 64)):
+        occ_r = refshim.ssao(W, H, fx, fy, *gi, nrm, pos)
+        occ_o = dgr._C.SSAO(W, H, fx, fy, *gi, nrm, pos)
+        assert torch.equal(torch.nan_to_num(occ_o, nan=-7.0), torch.nan_to_num(occ_r, nan=-7.0)), ("ssao", gi)
+        c_r, a_r = refshim.ssr(W, H, fx, fy, *gi, nrm, pos, rgb, alb, rough, met, F0)
+        c_o, a_o = dgr._C.SSR(W, H, fx, fy, *gi, nrm, pos, rgb, alb, rough, met, F0)
+        for x, y, nm in ((c_o, c_r, "ssr color"), (a_o, a_r, "ssr abd")):
+            assert torch.equal(torch.isnan(x), torch.isnan(y)), (nm, gi)
+            assert torch.equal(torch.nan_to_num(x, nan=-7.0), torch.nan_to_num(y, nan=-7.0)), (nm, gi)
