@@ -45,6 +45,17 @@ int ensure_dynamic_smem(const void* kernel, int bytes)
     return 0;
 }
 
+// ---- programmatic dependent launch (common.cuh: launch_k) -------------------------------------------
+static int g_pdl = -1;   // -1: not decided yet (env GIGS_PDL, default on)
+bool pdl_enabled()
+{
+    if (g_pdl < 0) {
+        const char* e = getenv("GIGS_PDL");
+        g_pdl = (e && e[0] == '0') ? 0 : 1;
+    }
+    return g_pdl != 0;
+}
+
 // ---- optional per-stage event timing -------------------------------------------------------------
 struct ProfRec { int stage; cudaEvent_t e0, e1; };
 static bool g_prof_on = false;
@@ -272,6 +283,13 @@ using namespace gigs;
 extern "C" {
 
 int gigs_abi_version(void) { return GIGS_ABI_VERSION; }
+
+int gigs_set_dependent_launch(int32_t on)
+{
+    const int prev = gigs::pdl_enabled() ? 1 : 0;
+    if (on >= 0) gigs::g_pdl = on ? 1 : 0;
+    return prev;
+}
 
 int gigs_sizeof(int32_t which)
 {

@@ -100,6 +100,7 @@ blend_backward_kernel(const int W, const int H, const uint2* __restrict__ ranges
                       const float* __restrict__ dL_dpix_roughness, const float* __restrict__ dL_dpix_metallic,
                       float* __restrict__ accum)
 {
+    pdl_enter();
     constexpr int RECF = (MODE == MODE_FULL) ? 12 : 8;
     constexpr uint32_t RECB = RECF * 4;
     using Smem = BwdSmem<RECF>;
@@ -349,6 +350,7 @@ blend_backward_material_kernel(const int W, const int H, const uint2* __restrict
                                const float* __restrict__ dL_dpix_roughness, const float* __restrict__ dL_dpix_metallic,
                                float* __restrict__ accum)
 {
+    pdl_enter();
     constexpr uint32_t RECB = 32;
     extern __shared__ __align__(128) unsigned char bb_smem_raw[];
     MatSmem& S = *reinterpret_cast<MatSmem*>(bb_smem_raw);
@@ -538,6 +540,7 @@ blend_backward_hybrid_kernel(const int W, const int H, const uint2* __restrict__
                              const float* __restrict__ dL_dpix_roughness, const float* __restrict__ dL_dpix_metallic,
                              float* __restrict__ accum)
 {
+    pdl_enter();
     constexpr uint32_t RECB = 12 * 4;
     extern __shared__ __align__(128) unsigned char bb_smem_raw[];
     HybSmem& S = *reinterpret_cast<HybSmem*>(bb_smem_raw);
@@ -783,32 +786,32 @@ int launch_blend_backward(const GigsRasterBwd* a, const Layout& L, cudaStream_t 
     static const bool legacy_material = getenv("GIGS_BB_LEGACY") != nullptr;
     if (material_only && !legacy_material) {
         GIGS_SMEM_ATTR(blend_backward_material_kernel, sizeof(MatSmem));
-        blend_backward_material_kernel<<<grid, block, sizeof(MatSmem), st>>>(
+        GIGS_CUDA(launch_k(blend_backward_material_kernel, dim3(grid), dim3(block), (size_t)(sizeof(MatSmem)), st, 
             c.width, c.height, ranges, plist, recs, ncontrib, a->dL_dpix_albedo, a->dL_dpix_roughness,
-            a->dL_dpix_metallic, a->accum);
+            a->dL_dpix_metallic, a->accum));
     } else if (material_only)
-        blend_backward_kernel<MODE_MATERIAL><<<grid, block, sizeof(BwdSmem<8>), st>>>(
+        GIGS_CUDA(launch_k(blend_backward_kernel<MODE_MATERIAL>, dim3(grid), dim3(block), (size_t)(sizeof(BwdSmem<8>)), st, 
             c.width, c.height, ranges, plist, recs, c.bg, finalT, ncontrib, a->dL_dpix_depth, a->dL_dpix,
             a->dL_dpix_opacity, a->dL_dpix_normal, a->dL_dpix_albedo, a->dL_dpix_roughness, a->dL_dpix_metallic,
-            a->accum);
+            a->accum));
     else if (!getenv("GIGS_BB_FULL_LEGACY")) {
         GIGS_SMEM_ATTR(blend_backward_hybrid_kernel<2>, sizeof(HybSmem));
         GIGS_SMEM_ATTR(blend_backward_hybrid_kernel<3>, sizeof(HybSmem));
         if (!a->dL_dpix_albedo && !a->dL_dpix_metallic)
-            blend_backward_hybrid_kernel<2><<<grid, block, sizeof(HybSmem), st>>>(
+            GIGS_CUDA(launch_k(blend_backward_hybrid_kernel<2>, dim3(grid), dim3(block), (size_t)(sizeof(HybSmem)), st, 
                 c.width, c.height, ranges, plist, recs, c.bg, finalT, ncontrib, a->dL_dpix_depth, a->dL_dpix,
                 a->dL_dpix_opacity, a->dL_dpix_normal, a->dL_dpix_albedo, a->dL_dpix_roughness, a->dL_dpix_metallic,
-                a->accum);
+                a->accum));
         else
-            blend_backward_hybrid_kernel<3><<<grid, block, sizeof(HybSmem), st>>>(
+            GIGS_CUDA(launch_k(blend_backward_hybrid_kernel<3>, dim3(grid), dim3(block), (size_t)(sizeof(HybSmem)), st, 
                 c.width, c.height, ranges, plist, recs, c.bg, finalT, ncontrib, a->dL_dpix_depth, a->dL_dpix,
                 a->dL_dpix_opacity, a->dL_dpix_normal, a->dL_dpix_albedo, a->dL_dpix_roughness, a->dL_dpix_metallic,
-                a->accum);
+                a->accum));
     } else
-        blend_backward_kernel<MODE_FULL><<<grid, block, sizeof(BwdSmem<12>), st>>>(
+        GIGS_CUDA(launch_k(blend_backward_kernel<MODE_FULL>, dim3(grid), dim3(block), (size_t)(sizeof(BwdSmem<12>)), st, 
             c.width, c.height, ranges, plist, recs, c.bg, finalT, ncontrib, a->dL_dpix_depth, a->dL_dpix,
             a->dL_dpix_opacity, a->dL_dpix_normal, a->dL_dpix_albedo, a->dL_dpix_roughness, a->dL_dpix_metallic,
-            a->accum);
+            a->accum));
     GIGS_LAUNCH_CHECK("blend_backward_kernel");
     return 0;
 }

@@ -50,6 +50,7 @@ blend_forward_kernel(const int W, const int H, const uint2* __restrict__ ranges,
                      float* __restrict__ out_albedo, float* __restrict__ out_roughness,
                      float* __restrict__ out_metallic, const bool inference)
 {
+    pdl_enter();
     extern __shared__ __align__(128) unsigned char bl_smem_raw[];
     using Smem = BlendSmemT<BATCH>;
     Smem& S = *reinterpret_cast<Smem*>(bl_smem_raw);
@@ -265,14 +266,14 @@ int launch_blend_forward(const GigsRasterFwd* a, const Layout& L, bool lite, cud
 #define BL_FULL_ARGS c.width, c.height, ranges, plist, recs, c.viewmatrix, c.bg, ncontrib, finalT, a->out_color, a->out_opacity, \
                      a->out_depth, a->out_normal, a->out_normal_view, a->out_pos, a->out_albedo, a->out_roughness,             \
                      a->out_metallic, c.inference != 0
-    if (lite && am) blend_forward_kernel<true, true><<<grid, block, sizeof(BlendSmem), st>>>(BL_LITE_ARGS);
-    else if (lite) blend_forward_kernel<true, false><<<grid, block, sizeof(BlendSmem), st>>>(BL_LITE_ARGS);
-    else if (am) blend_forward_kernel<false, true><<<grid, block, sizeof(BlendSmem), st>>>(BL_FULL_ARGS);
+    if (lite && am) GIGS_CUDA(launch_k(blend_forward_kernel<true, true>, dim3(grid), dim3(block), (size_t)(sizeof(BlendSmem)), st, BL_LITE_ARGS));
+    else if (lite) GIGS_CUDA(launch_k(blend_forward_kernel<true, false>, dim3(grid), dim3(block), (size_t)(sizeof(BlendSmem)), st, BL_LITE_ARGS));
+    else if (am) GIGS_CUDA(launch_k(blend_forward_kernel<false, true>, dim3(grid), dim3(block), (size_t)(sizeof(BlendSmem)), st, BL_FULL_ARGS));
     else if (a->material_only == 2)
-        blend_forward_kernel<false, false, false, BL_BATCH_MATERIAL, true><<<grid, block, sizeof(BlendSmemT<BL_BATCH_MATERIAL>), st>>>(BL_FULL_ARGS);
+        GIGS_CUDA(launch_k(blend_forward_kernel<false, false, false, BL_BATCH_MATERIAL, true>, dim3(grid), dim3(block), (size_t)(sizeof(BlendSmemT<BL_BATCH_MATERIAL>)), st, BL_FULL_ARGS));
     else if (a->material_only)
-        blend_forward_kernel<false, false, true, BL_BATCH_MATERIAL><<<grid, block, sizeof(BlendSmemT<BL_BATCH_MATERIAL>), st>>>(BL_FULL_ARGS);
-    else blend_forward_kernel<false, false><<<grid, block, sizeof(BlendSmem), st>>>(BL_FULL_ARGS);
+        GIGS_CUDA(launch_k(blend_forward_kernel<false, false, true, BL_BATCH_MATERIAL>, dim3(grid), dim3(block), (size_t)(sizeof(BlendSmemT<BL_BATCH_MATERIAL>)), st, BL_FULL_ARGS));
+    else GIGS_CUDA(launch_k(blend_forward_kernel<false, false>, dim3(grid), dim3(block), (size_t)(sizeof(BlendSmem)), st, BL_FULL_ARGS));
 #undef BL_LITE_ARGS
 #undef BL_FULL_ARGS
     GIGS_LAUNCH_CHECK("blend_forward_kernel");

@@ -45,6 +45,32 @@ int ensure_dynamic_smem(const void* kernel, int bytes);
         if (int _e = gigs::ensure_dynamic_smem((const void*)(kernel), (int)(bytes))) return _e; \
     } while (0)
 
+// Programmatic dependent launch (PTX griddepcontrol): a kernel launched through launch_k may be scheduled while the
+// previous kernel of the stream is still draining; it calls pdl_wait() FIRST (every thread, before any global access:
+// the wait returns once the previous grid has completed and its writes are visible) and pdl_trigger() right after (lets
+// the next launch_k kernel be scheduled). Both are no-ops in a kernel launched the ordinary way. Only kernels that
+// start with pdl_wait() may be launched with launch_k: completion then stays transitive along the stream.
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_wait(); pdl_trigger(); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 #define GIGS_CUDA(call)                                          \
     do {                                                         \
         cudaError_t _e = (call);                                 \

@@ -116,6 +116,7 @@ __device__ __forceinline__ float block_sum_256(float v, float* s_red /*[8]*/, in
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) deferred_shade_kernel(const DeferParams p)
 {
+    pdl_enter();
     __shared__ float s_n[3][DF_HH1][DF_HW1];   // normalised normal_map (world)
     __shared__ float s_v[3][DF_HH1][DF_HW1];   // normalised out_normal_view
     __shared__ float s_C[9], s_R[9];
@@ -218,6 +219,7 @@ __global__ void __launch_bounds__(256) deferred_shade_kernel(const DeferParams p
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) deferred_loss_kernel(const DeferParams p)
 {
+    pdl_enter();
     __shared__ float s_i[3][DF_HH1][DF_HW1];   // linear_to_srgb(SSR radiance), zero padded
     __shared__ float s_red[8];
     __shared__ bool s_last;
@@ -342,6 +344,7 @@ __global__ void __launch_bounds__(256) deferred_loss_kernel(const DeferParams p)
 template <int MINB>
 __global__ void __launch_bounds__(256, MINB) deferred_backward_kernel(const DeferParams p, const int tiles_x, const int ntiles)
 {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char dfb_raw[];
     float* s_dtex = reinterpret_cast<float*>(dfb_raw);                              // [SHB_MAX_DIFFUSE]
     float (*s_g)[DF_HH1][DF_HW1] = reinterpret_cast<float (*)[DF_HH1][DF_HW1]>(s_dtex + SHB_MAX_DIFFUSE);
@@ -454,6 +457,7 @@ __global__ void __launch_bounds__(256, MINB) deferred_backward_kernel(const Defe
 __global__ void __launch_bounds__(256)
 texel_fold_kernel(const float* __restrict__ priv, const int n, float* __restrict__ grad)
 {
+    pdl_enter();
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
     float s = 0.f;
@@ -469,6 +473,7 @@ material_param_grad_kernel(const int P, const float* __restrict__ accum, const f
                            const float* __restrict__ roughness, const float* __restrict__ metallic,
                            float* __restrict__ g_albedo, float* __restrict__ g_roughness, float* __restrict__ g_metallic)
 {
+    pdl_enter();
     const int idx = blockIdx.x * 256 + threadIdx.x;
     if (idx >= P) return;
     const float* row = accum + (size_t)idx * ACC_FLOATS;
@@ -673,7 +678,7 @@ int gigs_frame_forward(GigsFrame* f)
     dim3 grid((W + DF_TW - 1) / DF_TW, (H + DF_TH - 1) / DF_TH), block(DF_TW, DF_TH);
     {
         ProfScope ps(ST_DEFER_SHADE, st);
-        deferred_shade_kernel<<<grid, block, 0, st>>>(p);
+        GIGS_CUDA(launch_k(deferred_shade_kernel, dim3(grid), dim3(block), (size_t)(0), st, p));
         GIGS_LAUNCH_CHECK("deferred_shade_kernel");
     }
     if (int e = gigs_ssr(W, H, fx, fy, f->radius, f->bias, f->thick, f->delta, f->step, f->start, p.ssr_normal,
@@ -684,7 +689,7 @@ int gigs_frame_forward(GigsFrame* f)
     if (f->gt_ready_event) GIGS_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)f->gt_ready_event, 0));
     {
         ProfScope ps(ST_DEFER_LOSS, st);
-        deferred_loss_kernel<<<grid, block, 0, st>>>(p);
+        GIGS_CUDA(launch_k(deferred_loss_kernel, dim3(grid), dim3(block), (size_t)(0), st, p));
         GIGS_LAUNCH_CHECK("deferred_loss_kernel");
     }
     if (c.debug) GIGS_CUDA(cudaStreamSynchronize(st));
@@ -729,14 +734,14 @@ int gigs_frame_backward(GigsFrame* f)
         const int blocks = ntiles < 148 * per_sm * 2 ? ntiles : 148 * per_sm * 2;
         {
             ProfScope pk(ST_DEFER_BWD_KERNEL, st);   // the kernel alone (the stage around it adds the clear and the folds)
-            if (variant == 3) deferred_backward_kernel<3><<<blocks, dim3(DF_TW, DF_TH), smem, st>>>(p, tiles_x, ntiles);
-            else if (variant == 4) deferred_backward_kernel<4><<<blocks, dim3(DF_TW, DF_TH), smem, st>>>(p, tiles_x, ntiles);
-            else deferred_backward_kernel<2><<<blocks, dim3(DF_TW, DF_TH), smem, st>>>(p, tiles_x, ntiles);
+            if (variant == 3) GIGS_CUDA(launch_k(deferred_backward_kernel<3>, dim3(blocks), dim3(dim3(DF_TW, DF_TH)), (size_t)(smem), st, p, tiles_x, ntiles));
+            else if (variant == 4) GIGS_CUDA(launch_k(deferred_backward_kernel<4>, dim3(blocks), dim3(dim3(DF_TW, DF_TH)), (size_t)(smem), st, p, tiles_x, ntiles));
+            else GIGS_CUDA(launch_k(deferred_backward_kernel<2>, dim3(blocks), dim3(dim3(DF_TW, DF_TH)), (size_t)(smem), st, p, tiles_x, ntiles));
         }
         GIGS_LAUNCH_CHECK("deferred_backward_kernel");
         for (int k = 0; k < slots; ++k) {
-            texel_fold_kernel<<<(fold_n[k] + 255) / 256, 256, 0, st>>>(
-                scratch + (size_t)k * TEX_PRIV_FLOATS * TEX_COPIES, fold_n[k], fold_dst[k]);
+            GIGS_CUDA(launch_k(texel_fold_kernel, dim3((fold_n[k] + 255) / 256), dim3(256), (size_t)(0), st, 
+                scratch + (size_t)k * TEX_PRIV_FLOATS * TEX_COPIES, fold_n[k], fold_dst[k]));
             GIGS_LAUNCH_CHECK("texel_fold_kernel");
         }
     }
@@ -759,13 +764,13 @@ int gigs_frame_backward(GigsFrame* f)
         ProfScope ps(ST_PARAM_GRAD, st);
         const int blocks = (f->P + 255) / 256;
         if (f->raw_params)
-            material_param_grad_kernel<true><<<blocks, 256, 0, st>>>(f->P, f->accum, f->albedo, f->roughness, f->metallic,
+            GIGS_CUDA(launch_k(material_param_grad_kernel<true>, dim3(blocks), dim3(256), (size_t)(0), st, f->P, f->accum, f->albedo, f->roughness, f->metallic,
                                                                      f->g_albedo, f->g_roughness,
-                                                                     f->use_metallic ? f->g_metallic : nullptr);
+                                                                     f->use_metallic ? f->g_metallic : nullptr));
         else
-            material_param_grad_kernel<false><<<blocks, 256, 0, st>>>(f->P, f->accum, f->albedo, f->roughness, f->metallic,
+            GIGS_CUDA(launch_k(material_param_grad_kernel<false>, dim3(blocks), dim3(256), (size_t)(0), st, f->P, f->accum, f->albedo, f->roughness, f->metallic,
                                                                       f->g_albedo, f->g_roughness,
-                                                                      f->use_metallic ? f->g_metallic : nullptr);
+                                                                      f->use_metallic ? f->g_metallic : nullptr));
         GIGS_LAUNCH_CHECK("material_param_grad_kernel");
     }
     if (c.debug) GIGS_CUDA(cudaStreamSynchronize(st));

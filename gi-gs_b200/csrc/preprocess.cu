@@ -155,6 +155,7 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
                   uint8_t* __restrict__ clamped, uint32_t* __restrict__ tiles_touched,
                   uint32_t* __restrict__ depth_keys, uint32_t* __restrict__ block_sums)
 {
+    pdl_enter();
     __shared__ float sV[16], sPM[16], sCam[3];
     __shared__ uint32_t s_warp_sum[PRE_THREADS / 32];
     if (threadIdx.x < 16) {
@@ -318,6 +319,7 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
 __global__ void __launch_bounds__(1024) scan_block_sums_kernel(uint32_t* __restrict__ block_sums, int nb,
                                                                uint32_t* __restrict__ total)
 {
+    pdl_enter();
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_carry;
     if (threadIdx.x == 0) s_carry = 0;
@@ -361,6 +363,7 @@ __global__ void __launch_bounds__(PRE_THREADS)
 ordered_block_sums_kernel(const int P, const uint32_t* __restrict__ order, const uint32_t* __restrict__ tiles_touched,
                           uint32_t* __restrict__ block_sums)
 {
+    pdl_enter();
     __shared__ uint32_t s_warp_sum[PRE_THREADS / 32];
     const int i = blockIdx.x * PRE_THREADS + threadIdx.x;
     uint32_t v = (i < P) ? tiles_touched[order[i]] : 0u;
@@ -387,6 +390,7 @@ emit_keys_kernel(const int P, const uint32_t* __restrict__ order, const int* __r
                  const uint32_t* __restrict__ block_offsets, const uint32_t grid_x, const uint32_t grid_y,
                  uint32_t* __restrict__ keys, uint32_t* __restrict__ vals)
 {
+    pdl_enter();
     __shared__ uint32_t s_warp_tot[PRE_THREADS / 32];
     __shared__ uint32_t s_pref[PRE_THREADS / 32][32];
     __shared__ uint4 s_info[PRE_THREADS / 32][32];  // rect_min.x, rect_min.y, rect width, Gaussian id
@@ -492,13 +496,13 @@ int launch_preprocess(const GigsRasterFwd* a, const Layout& L, cudaStream_t st, 
     GIGS_SMEM_ATTR(preprocess_kernel<true>, 96 * 1024);
     GIGS_SMEM_ATTR(preprocess_kernel<false>, 96 * 1024);
     if (sh_rest != nullptr)
-        preprocess_kernel<true><<<L.num_blocks, PRE_THREADS, smem, st>>>(PRE_ARGS);
+        GIGS_CUDA(launch_k(preprocess_kernel<true>, dim3(L.num_blocks), dim3(PRE_THREADS), (size_t)(smem), st, PRE_ARGS));
     else
-        preprocess_kernel<false><<<L.num_blocks, PRE_THREADS, smem, st>>>(PRE_ARGS);
+        GIGS_CUDA(launch_k(preprocess_kernel<false>, dim3(L.num_blocks), dim3(PRE_THREADS), (size_t)(smem), st, PRE_ARGS));
 #undef PRE_ARGS
     GIGS_LAUNCH_CHECK("preprocess_kernel");
-    scan_block_sums_kernel<<<1, 1024, 0, st>>>((uint32_t*)(g + L.off.g_block_sums), (int)L.num_blocks,
-                                               (uint32_t*)(g + L.off.g_num_rendered));
+    GIGS_CUDA(launch_k(scan_block_sums_kernel, dim3(1), dim3(1024), (size_t)(0), st, (uint32_t*)(g + L.off.g_block_sums), (int)L.num_blocks,
+                                               (uint32_t*)(g + L.off.g_num_rendered)));
     GIGS_LAUNCH_CHECK("scan_block_sums_kernel");
     return 0;
 }
@@ -523,12 +527,12 @@ int launch_emit_keys(const GigsRasterFwd* a, const Layout& L, uint32_t* keys, ui
     const uint32_t* order = (const uint32_t*)(g + L.off.g_order);
     const uint32_t* touched = (const uint32_t*)(g + L.off.g_tiles_touched);
     uint32_t* sums2 = (uint32_t*)(g + L.g_block_sums2);
-    ordered_block_sums_kernel<<<L.num_blocks, PRE_THREADS, 0, st>>>(a->P, order, touched, sums2);
+    GIGS_CUDA(launch_k(ordered_block_sums_kernel, dim3(L.num_blocks), dim3(PRE_THREADS), (size_t)(0), st, a->P, order, touched, sums2));
     GIGS_LAUNCH_CHECK("ordered_block_sums_kernel");
-    scan_block_sums_kernel<<<1, 1024, 0, st>>>(sums2, (int)L.num_blocks, sums2 + L.num_blocks);
+    GIGS_CUDA(launch_k(scan_block_sums_kernel, dim3(1), dim3(1024), (size_t)(0), st, sums2, (int)L.num_blocks, sums2 + L.num_blocks));
     GIGS_LAUNCH_CHECK("scan_block_sums_kernel");
-    emit_keys_kernel<<<L.num_blocks, PRE_THREADS, 0, st>>>(a->P, order, a->radii, (const float*)(g + L.off.g_record),
-                                                          touched, sums2, L.tiles_x, L.tiles_y, keys, vals);
+    GIGS_CUDA(launch_k(emit_keys_kernel, dim3(L.num_blocks), dim3(PRE_THREADS), (size_t)(0), st, a->P, order, a->radii, (const float*)(g + L.off.g_record),
+                                                          touched, sums2, L.tiles_x, L.tiles_y, keys, vals));
     GIGS_LAUNCH_CHECK("emit_keys_kernel");
     return 0;
 }

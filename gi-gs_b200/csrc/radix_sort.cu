@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(RS_HTHREADS)
 rs_histogram_kernel(const K* __restrict__ keys, const uint32_t n, const int passes, const int digit_bits, const int end_bit,
                     uint32_t* __restrict__ hist /*[passes][256]*/)
 {
+    pdl_enter();
     __shared__ uint32_t s_hist[RS_MAX_PASSES][RS_MAX_RADIX];
     for (int i = threadIdx.x; i < passes * RS_MAX_RADIX; i += RS_HTHREADS) (&s_hist[0][0])[i] = 0;
     __syncthreads();
@@ -66,6 +67,7 @@ constexpr int RS_JOINT_BINS = 1 << RS_JOINT_BITS;
 __global__ void __launch_bounds__(512)
 rs_joint_histogram_kernel(const uint32_t* __restrict__ keys, const uint32_t n, const int bins, uint32_t* __restrict__ joint)
 {
+    pdl_enter();
     extern __shared__ uint32_t s_joint[];
     for (int i = threadIdx.x; i < bins; i += 512) s_joint[i] = 0;
     __syncthreads();
@@ -90,6 +92,7 @@ __global__ void __launch_bounds__(1024)
 rs_joint_scan_kernel(const uint32_t* __restrict__ joint, const int bins, const int passes, const int digit_bits,
                      const int end_bit, uint32_t* __restrict__ hist, uint2* __restrict__ ranges, const uint32_t num_tiles)
 {
+    pdl_enter();
     __shared__ uint32_t s_hist[RS_MAX_PASSES][RS_MAX_RADIX];
     __shared__ uint32_t s_warp[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -153,6 +156,7 @@ rs_joint_scan_kernel(const uint32_t* __restrict__ joint, const int bins, const i
 // exclusive scan of each pass's 256-bin histogram (in place)
 __global__ void __launch_bounds__(RS_MAX_RADIX) rs_scan_hist_kernel(uint32_t* __restrict__ hist)
 {
+    pdl_enter();
     __shared__ uint32_t s_warp[RS_MAX_RADIX / 32];
     uint32_t* h = hist + blockIdx.x * RS_MAX_RADIX;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -192,6 +196,7 @@ rs_onesweep_kernel(const K* __restrict__ keys_in, K* __restrict__ keys_out, cons
                    const uint32_t* __restrict__ digit_base, volatile uint32_t* __restrict__ status /*[tiles][RADIX]*/,
                    uint32_t* __restrict__ ticket)
 {
+    pdl_enter();
     using Smem = RsSmem<K, BITS, THREADS, ITEMS>;
     constexpr int RADIX = Smem::RADIX, WARPS = Smem::WARPS, TILE = Smem::TILE;
     static_assert(RADIX % 32 == 0 && RADIX <= THREADS, "digit threads must be whole warps of the block");
@@ -354,9 +359,9 @@ static int launch_passes(uint32_t n, int end_bit, const K* keys_u, const uint32_
         const int shift = p * BITS;
         const int bits = (end_bit - shift) < BITS ? (end_bit - shift) : BITS;
         ProfScope ps(pass_stage, st);
-        rs_onesweep_kernel<K, BITS, T, I><<<tiles, T, sizeof(Smem), st>>>(
+        GIGS_CUDA(launch_k(rs_onesweep_kernel<K, BITS, T, I>, dim3(tiles), dim3(T), (size_t)(sizeof(Smem)), st, 
             kin, kout, vin, vout, n, shift, (1u << bits) - 1u, hist + p * RS_MAX_RADIX,
-            status + (size_t)p * status_tiles * RS_MAX_RADIX, tickets + p);
+            status + (size_t)p * status_tiles * RS_MAX_RADIX, tickets + p));
         GIGS_LAUNCH_CHECK("rs_onesweep_kernel");
         kin = kout;
         vin = vout;
@@ -402,15 +407,15 @@ static int sort_pairs(uint64_t R, int end_bit, const K* keys_u, const uint32_t* 
         const int bins = 1 << end_bit;
         const uint32_t hblocks = min((n + 16383u) / 16384u, 148u * 2u);
         GIGS_SMEM_ATTR(rs_joint_histogram_kernel, RS_JOINT_BINS * 4);
-        rs_joint_histogram_kernel<<<hblocks, 512, (size_t)bins * 4, st>>>((const uint32_t*)keys_u, n, bins, joint);
+        GIGS_CUDA(launch_k(rs_joint_histogram_kernel, dim3(hblocks), dim3(512), (size_t)((size_t)bins * 4), st, (const uint32_t*)keys_u, n, bins, joint));
         GIGS_LAUNCH_CHECK("rs_joint_histogram_kernel");
-        rs_joint_scan_kernel<<<1, 1024, 0, st>>>(joint, bins, passes, digit_bits, end_bit, hist, ranges, num_tiles);
+        GIGS_CUDA(launch_k(rs_joint_scan_kernel, dim3(1), dim3(1024), (size_t)(0), st, joint, bins, passes, digit_bits, end_bit, hist, ranges, num_tiles));
         GIGS_LAUNCH_CHECK("rs_joint_scan_kernel");
     } else {
         const uint32_t hblocks = min((n + 4095u) / 4096u, 148u * 8u);
-        rs_histogram_kernel<K><<<hblocks, RS_HTHREADS, 0, st>>>(keys_u, n, passes, digit_bits, end_bit, hist);
+        GIGS_CUDA(launch_k(rs_histogram_kernel<K>, dim3(hblocks), dim3(RS_HTHREADS), (size_t)(0), st, keys_u, n, passes, digit_bits, end_bit, hist));
         GIGS_LAUNCH_CHECK("rs_histogram_kernel");
-        rs_scan_hist_kernel<<<passes, RS_MAX_RADIX, 0, st>>>(hist);
+        GIGS_CUDA(launch_k(rs_scan_hist_kernel, dim3(passes), dim3(RS_MAX_RADIX), (size_t)(0), st, hist));
         GIGS_LAUNCH_CHECK("rs_scan_hist_kernel");
     }
     static const int cfg = env_int("GIGS_RS_CFG", 0);

@@ -227,6 +227,7 @@ geometry_chain_kernel(const int W, const int H, const float fx, const float fy, 
                       const float color_coef, const SpaceKernel K, const float* __restrict__ depth,
                       float* __restrict__ normal_out, float* __restrict__ pos_out)
 {
+    pdl_enter();
     __shared__ float s_raw[GC_RH][GC_RW];
     __shared__ float s_df[GC_FH][GC_FW];
     __shared__ float s_pos[3][GC_NH][GC_NW];
@@ -396,8 +397,8 @@ int gigs_geometry_chain(int32_t W, int32_t H, float fx, float fy, const float* v
     if (!viewmatrix || !depth) { set_error("gigs_geometry_chain: bad arguments"); return -1; }
     dim3 grid((W + GC_TW - 1) / GC_TW, (H + GC_TH - 1) / GC_TH), block(32, 8);
     ProfScope ps(ST_GEOM_CHAIN, st);
-    geometry_chain_kernel<<<grid, block, 0, st>>>(W, H, fx, fy, viewmatrix, -0.5f / (1.f * 1.f), make_space_kernel(3.f),
-                                                  depth, normal_from_depth, depth_pos_filter);
+    GIGS_CUDA(launch_k(geometry_chain_kernel, dim3(grid), dim3(block), (size_t)(0), st, W, H, fx, fy, viewmatrix, -0.5f / (1.f * 1.f), make_space_kernel(3.f),
+                                                  depth, normal_from_depth, depth_pos_filter));
     GIGS_LAUNCH_CHECK("geometry_chain_kernel");
     return 0;
 }

@@ -231,6 +231,12 @@ int gigs_gi_count_probes(int32_t W, int32_t H, float fx, float fy, float radius,
  * for every setting. Process-wide; defaults 1, 1. */
 int gigs_gi_tune(int32_t pairs_per_step, int32_t block_test);
 
+/* The kernels of the frame are launched with programmatic stream serialization (PTX griddepcontrol): each waits for
+ * the previous grid before its first global access, so results do not change; only the launch latency between the
+ * ~30 dependent kernels of a frame is hidden. on = 0 / 1 switches it for the process (default 1, or the environment
+ * variable GIGS_PDL=0); on < 0 only queries. Returns the previous setting. */
+int gigs_set_dependent_launch(int32_t on);
+
 /* Replaces SSR_BACKWARD (rasterize_points.cu:479-510). The reference's Python never calls its
  * kernel (diff_gaussian_rasterization/__init__.py:666-673); the live semantics are
  * grad_albedo = grad_color * abd, zeros for roughness/metallic, which is what this computes. */
