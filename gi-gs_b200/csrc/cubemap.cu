@@ -168,6 +168,7 @@ __device__ __forceinline__ float3 cm_load3(const void* src, const int j)
 template <bool BACKWARD, bool PACKED>
 __global__ void __launch_bounds__(256) cm_filter_kernel(const __grid_constant__ CmPlan plan)
 {
+    pdl_enter();
     int k = 0;
     for (int q = 1; q < plan.nseg; ++q)
         if ((int)blockIdx.x >= plan.seg[q].cta_begin) k = q;
@@ -282,6 +283,7 @@ struct CmChainArgs {
 template <bool SRC4>
 __global__ void __launch_bounds__(256) cm_chain_kernel(const __grid_constant__ CmChainArgs a)
 {
+    pdl_enter();
     __shared__ float sm[3][16][17];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int f = blockIdx.z, R = a.R;
@@ -319,6 +321,7 @@ __global__ void __launch_bounds__(256) cm_chain_kernel(const __grid_constant__ C
 // plain (unpadded) 2x2 pool for the stand-alone cubemap_mip op
 __global__ void __launch_bounds__(256) cm_mip_forward_kernel(const int No, const float* __restrict__ in, float* __restrict__ out)
 {
+    pdl_enter();
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= 6 * No * No) return;
     const int x = i % No, y = (i / No) % No, s = i / (No * No);
@@ -336,6 +339,7 @@ __global__ void __launch_bounds__(256)
 cm_mip_backward_kernel(const int Nc, const float* __restrict__ coarse_a, const float* __restrict__ coarse_b,
                        const float* __restrict__ add, float* __restrict__ out, const bool accumulate)
 {
+    pdl_enter();
     const int Nf = 2 * Nc;
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= 6 * Nf * Nf) return;
@@ -376,6 +380,7 @@ struct CmPrepArgs {
 
 __global__ void __launch_bounds__(256) cm_prep_kernel(const __grid_constant__ CmPrepArgs a)
 {
+    pdl_enter();
     const int t = blockIdx.x * 256 + threadIdx.x;
     if (t >= a.begin[a.n]) return;
     int k = 0;
@@ -394,6 +399,7 @@ __global__ void __launch_bounds__(256) cm_prep_kernel(const __grid_constant__ Cm
 __global__ void __launch_bounds__(256)
 cm_add_kernel(const int n, const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, const bool accumulate)
 {
+    pdl_enter();
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
     float r = a[i] + (b ? b[i] : 0.f);
@@ -595,6 +601,7 @@ struct CmSpPlan {
 template <int U, int MINB>
 __global__ void __launch_bounds__(256, MINB) cm_sparse_kernel(const __grid_constant__ CmSpPlan plan)
 {
+    pdl_enter();
     int k = 0;
     for (int q = 1; q < plan.nseg; ++q)
         if ((int)blockIdx.x >= plan.seg[q].cta_begin) k = q;
@@ -685,6 +692,7 @@ __global__ void __launch_bounds__(256, MINB) cm_sparse_kernel(const __grid_const
 __global__ void __launch_bounds__(256)
 env_lookup_kernel(const int N, const float* __restrict__ base, const float* __restrict__ dirs, const int n, float* __restrict__ env)
 {
+    pdl_enter();
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
     const CubeTaps T = cube_taps(dirs[3 * (size_t)i], dirs[3 * (size_t)i + 1], dirs[3 * (size_t)i + 2], N);
@@ -698,6 +706,7 @@ __global__ void __launch_bounds__(256)
 env_tv_kernel(const int N, const int EH, const int EW, const float* __restrict__ env, const float* __restrict__ dirs,
               const float scale /*weight * loss_scale*/, float* __restrict__ partials, float* __restrict__ grad_base)
 {
+    pdl_enter();
     __shared__ float s_red[8];
     const int i = blockIdx.x * 256 + threadIdx.x;
     const int n = EH * EW;
@@ -743,6 +752,7 @@ __global__ void __launch_bounds__(256)
 env_tv_sum_kernel(const int nblk, const float* __restrict__ partials, const float scale, float* __restrict__ loss_out,
                   const bool accumulate)
 {
+    pdl_enter();
     __shared__ float s_red[8];
     float a = 0.f;
     for (int i = threadIdx.x; i < nblk; i += 256) a += partials[i];
@@ -767,7 +777,7 @@ namespace {
 template <bool BACKWARD, bool PACKED>
 int cm_launch_plan(const CmPlan& plan, int ctas, cudaStream_t st)
 {
-    cm_filter_kernel<BACKWARD, PACKED><<<ctas, 256, 0, st>>>(plan);
+    GIGS_CUDA(launch_k(cm_filter_kernel<BACKWARD, PACKED>, dim3(ctas), dim3(256), (size_t)(0), st, plan));
     GIGS_LAUNCH_CHECK("cm_filter_kernel");
     return 0;
 }
@@ -856,7 +866,7 @@ int gigs_cubemap_mip_forward(int32_t res_out, const float* in, float* out, void*
 {
     if (res_out <= 0 || !in || !out) { set_error("gigs_cubemap_mip_forward: bad arguments"); return -1; }
     const int n = 6 * res_out * res_out;
-    cm_mip_forward_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(res_out, in, out);
+    GIGS_CUDA(launch_k(cm_mip_forward_kernel, dim3((n + 255) / 256), dim3(256), (size_t)(0), (cudaStream_t)stream, res_out, in, out));
     GIGS_LAUNCH_CHECK("cm_mip_forward_kernel");
     return 0;
 }
@@ -865,8 +875,8 @@ int gigs_cubemap_mip_backward(int32_t res_coarse, const float* grad_coarse, floa
 {
     if (res_coarse <= 0 || !grad_coarse || !grad_fine) { set_error("gigs_cubemap_mip_backward: bad arguments"); return -1; }
     const int n = 6 * 4 * res_coarse * res_coarse;
-    cm_mip_backward_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(res_coarse, grad_coarse, nullptr, nullptr, grad_fine,
-                                                                              accumulate != 0);
+    GIGS_CUDA(launch_k(cm_mip_backward_kernel, dim3((n + 255) / 256), dim3(256), (size_t)(0), (cudaStream_t)stream, res_coarse, grad_coarse, nullptr, nullptr, grad_fine,
+                                                                              accumulate != 0));
     GIGS_LAUNCH_CHECK("cm_mip_backward_kernel");
     return 0;
 }
@@ -1084,7 +1094,7 @@ static int cm_sparse_launch(const GigsLightLayout* L, void* ws, void* weights, b
     // 2 pieces per iteration, 4 CTAs per SM: measured equal (within 3 %) to 3-4 pieces at 3 CTAs and better than 1 piece
     // at 6 CTAs or 2 at 5; with the weight loads stubbed out the kernel still takes 76 % of its time, so it is bound by
     // the gathers and the ~30 instructions per piece, not by the HBM stream (3.6 TB/s)
-    cm_sparse_kernel<2, 4><<<ctas, 256, 0, st>>>(plan);
+    GIGS_CUDA(launch_k(cm_sparse_kernel<2, 4>, dim3(ctas), dim3(256), (size_t)(0), st, plan));
     GIGS_LAUNCH_CHECK("cm_sparse_kernel");
     return 0;
 }
@@ -1125,8 +1135,8 @@ int gigs_light_build(const GigsLightLayout* L, const float* base, void* ws, cons
         a.pack0 = first == 0 ? (float4*)at(ws, L->chain[0]) : nullptr;
         for (int h = 0; h < a.nh; ++h) a.out[h] = (float4*)at(ws, L->chain[first + 1 + h]);
         const dim3 grid(a.R / 16, a.R / 16, 6);
-        if (first == 0) cm_chain_kernel<false><<<grid, 256, 0, st>>>(a);
-        else cm_chain_kernel<true><<<grid, 256, 0, st>>>(a);
+        if (first == 0) GIGS_CUDA(launch_k(cm_chain_kernel<false>, dim3(grid), dim3(256), (size_t)(0), st, a));
+        else GIGS_CUDA(launch_k(cm_chain_kernel<true>, dim3(grid), dim3(256), (size_t)(0), st, a));
         GIGS_LAUNCH_CHECK("cm_chain_kernel");
     }
     return weights ? cm_sparse_launch(L, ws, const_cast<void*>(weights), false, st) : cm_compute_launch(L, ws, false, st);
@@ -1153,15 +1163,15 @@ int gigs_light_backward(const GigsLightLayout* L, void* ws, const void* weights,
         tot += 6 * r * r;
     }
     pa.begin[n + 1] = tot;
-    cm_prep_kernel<<<(tot + 255) / 256, 256, 0, st>>>(pa);
+    GIGS_CUDA(launch_k(cm_prep_kernel, dim3((tot + 255) / 256), dim3(256), (size_t)(0), st, pa));
     GIGS_LAUNCH_CHECK("cm_prep_kernel");
     const int rc = weights ? cm_sparse_launch(L, ws, const_cast<void*>(weights), true, st) : cm_compute_launch(L, ws, true, st);
     if (rc) return rc;
     // down the chain, coarse to fine; the last step lands in grad_base
     if (n == 1) {
         const int m = 18 * L->res[0] * L->res[0];
-        cm_add_kernel<<<(m + 255) / 256, 256, 0, st>>>(m, (const float*)at(ws, L->g_chain[0]), (const float*)at(ws, L->g_diffuse_in),
-                                                       grad_base, accumulate != 0);
+        GIGS_CUDA(launch_k(cm_add_kernel, dim3((m + 255) / 256), dim3(256), (size_t)(0), st, m, (const float*)at(ws, L->g_chain[0]), (const float*)at(ws, L->g_diffuse_in),
+                                                       grad_base, accumulate != 0));
         GIGS_LAUNCH_CHECK("cm_add_kernel");
     }
     for (int i = n - 1; i >= 1; --i) {
@@ -1170,10 +1180,10 @@ int gigs_light_backward(const GigsLightLayout* L, void* ws, const void* weights,
         const float* ca = (const float*)at(ws, L->g_chain[i]);
         const float* cb = i == n - 1 ? (const float*)at(ws, L->g_diffuse_in) : nullptr;
         if (i > 1)
-            cm_mip_backward_kernel<<<(m + 255) / 256, 256, 0, st>>>(Nc, ca, cb, nullptr, (float*)at(ws, L->g_chain[i - 1]), true);
+            GIGS_CUDA(launch_k(cm_mip_backward_kernel, dim3((m + 255) / 256), dim3(256), (size_t)(0), st, Nc, ca, cb, nullptr, (float*)at(ws, L->g_chain[i - 1]), true));
         else
-            cm_mip_backward_kernel<<<(m + 255) / 256, 256, 0, st>>>(Nc, ca, cb, (const float*)at(ws, L->g_chain[0]), grad_base,
-                                                                    accumulate != 0);
+            GIGS_CUDA(launch_k(cm_mip_backward_kernel, dim3((m + 255) / 256), dim3(256), (size_t)(0), st, Nc, ca, cb, (const float*)at(ws, L->g_chain[0]), grad_base,
+                                                                    accumulate != 0));
         GIGS_LAUNCH_CHECK("cm_mip_backward_kernel");
     }
     if (clear_grads)
@@ -1193,12 +1203,12 @@ int gigs_env_tv(int32_t base_res, const float* base, const float* dirs, int32_t 
     cudaStream_t st = (cudaStream_t)stream;
     float* env = (float*)scratch;
     float* partials = (float*)((char*)scratch + ((uint64_t)n * 12 + 255) / 256 * 256);
-    env_lookup_kernel<<<nblk, 256, 0, st>>>(base_res, base, dirs, n, env);
+    GIGS_CUDA(launch_k(env_lookup_kernel, dim3(nblk), dim3(256), (size_t)(0), st, base_res, base, dirs, n, env));
     GIGS_LAUNCH_CHECK("env_lookup_kernel");
-    env_tv_kernel<<<nblk, 256, 0, st>>>(base_res, env_h, env_w, env, dirs, scale, partials, grad_base);
+    GIGS_CUDA(launch_k(env_tv_kernel, dim3(nblk), dim3(256), (size_t)(0), st, base_res, env_h, env_w, env, dirs, scale, partials, grad_base));
     GIGS_LAUNCH_CHECK("env_tv_kernel");
     if (loss_out) {
-        env_tv_sum_kernel<<<1, 256, 0, st>>>(nblk, partials, scale, loss_out, accumulate_loss != 0);
+        GIGS_CUDA(launch_k(env_tv_sum_kernel, dim3(1), dim3(256), (size_t)(0), st, nblk, partials, scale, loss_out, accumulate_loss != 0));
         GIGS_LAUNCH_CHECK("env_tv_sum_kernel");
     }
     return 0;

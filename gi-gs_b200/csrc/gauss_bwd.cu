@@ -479,6 +479,7 @@ gaussian_backward_kernel(const int P, const int D, const int M, const float* __r
                          float* __restrict__ dL_dmean3D, float* __restrict__ dL_dcov3D, float* __restrict__ dL_dsh,
                          float* __restrict__ dL_dscale, float* __restrict__ dL_drot, const RawGrads raw, const int stage_rows)
 {
+    pdl_enter();
     extern __shared__ float4 gb_stage4[];
     constexpr int ROW = 45, V4 = 32 * ROW / 4;                 // 360 float4 per warp
     const int idx = blockIdx.x * GB_THREADS + threadIdx.x;
@@ -531,11 +532,11 @@ int launch_gaussian_backward(const GigsRasterBwd* a, const Layout& L, cudaStream
     const float focal_y = c.height / (2.0f * c.tan_fovy);
     const float focal_x = c.width / (2.0f * c.tan_fovx);
     const float* cov3D_ptr = a->cov3D_precomp ? a->cov3D_precomp : (const float*)(g + L.off.g_cov3D);
-    gaussian_backward_kernel<false><<<(a->P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, st>>>(
+    GIGS_CUDA(launch_k(gaussian_backward_kernel<false>, dim3((a->P + GB_THREADS - 1) / GB_THREADS), dim3(GB_THREADS), (size_t)(0), st, 
         a->P, c.sh_degree, c.sh_coeffs, a->means3D, a->radii, a->shs, (const uint8_t*)(g + L.off.g_clamped), a->scales,
         a->rotations, c.scale_modifier, cov3D_ptr, c.viewmatrix, c.projmatrix, c.campos, focal_x, focal_y, c.tan_fovx,
         c.tan_fovy, a->accum, a->dL_dmean2D, a->dL_dconic, a->dL_dopacity, a->dL_dcolor, a->dL_dnormal, a->dL_dalbedo,
-        a->dL_droughness, a->dL_dmetallic, a->dL_dmean3D, a->dL_dcov3D, a->dL_dsh, a->dL_dscale, a->dL_drot, RawGrads{}, 0);
+        a->dL_droughness, a->dL_dmetallic, a->dL_dmean3D, a->dL_dcov3D, a->dL_dsh, a->dL_dscale, a->dL_drot, RawGrads{}, 0));
     GIGS_LAUNCH_CHECK("gaussian_backward_kernel");
     return 0;
 }
@@ -553,11 +554,11 @@ int launch_gaussian_backward_raw(int P, const GigsCamera& c, const void* geom, c
     const int stage_rows = stage_env && c.sh_coeffs == 16 && raw.f_rest && raw.g_f_rest &&
                            ((((uintptr_t)raw.f_rest | (uintptr_t)raw.g_f_rest) & 15) == 0);
     const size_t smem = stage_rows ? (size_t)(GB_THREADS / 32) * (32 * 45 / 4) * sizeof(float4) : 0;
-    gaussian_backward_kernel<true><<<(P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, smem, st>>>(
+    GIGS_CUDA(launch_k(gaussian_backward_kernel<true>, dim3((P + GB_THREADS - 1) / GB_THREADS), dim3(GB_THREADS), (size_t)(smem), st, 
         P, c.sh_degree, c.sh_coeffs, xyz, radii, f_dc, (const uint8_t*)(g + L.off.g_clamped), log_scale, rot,
         c.scale_modifier, (const float*)(g + L.off.g_cov3D), c.viewmatrix, c.projmatrix, c.campos, focal_x, focal_y,
         c.tan_fovx, c.tan_fovy, accum, g_means2D, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-        nullptr, nullptr, nullptr, nullptr, raw, stage_rows);
+        nullptr, nullptr, nullptr, nullptr, raw, stage_rows));
     GIGS_LAUNCH_CHECK("gaussian_backward_kernel<RAW>");
     return 0;
 }

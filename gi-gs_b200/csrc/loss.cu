@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(SS_NT) ssim_forward_kernel(int C, int W, int H
                                                              float* __restrict__ dxx, float* __restrict__ dxy,
                                                              float2* __restrict__ partial)
 {
+    pdl_enter();
     __shared__ float sx[SS_E][SS_E + 1], sy[SS_E][SS_E + 1];
     __shared__ float h[5][SS_E][SS_HS];
     __shared__ float red[2][SS_NT / 32];
@@ -158,6 +159,7 @@ __global__ void __launch_bounds__(1024) ssim_finish_kernel(int n, const float2* 
                                                            float lambda, float loss_scale, float* __restrict__ out,
                                                            int accumulate)
 {
+    pdl_enter();
     __shared__ double rs[32], rl[32];
     double s = 0.0, l = 0.0;
     for (int i = threadIdx.x; i < n; i += 1024) { s += (double)partial[i].x; l += (double)partial[i].y; }
@@ -185,6 +187,7 @@ __global__ void __launch_bounds__(SS_NT) ssim_backward_kernel(int C, int W, int 
                                                               float k_ssim, float k_l1, const float* __restrict__ upstream,
                                                               float* __restrict__ grad, int accumulate)
 {
+    pdl_enter();
     __shared__ float s[3][SS_E][SS_E + 1];
     __shared__ float h[3][SS_E][SS_HS];
     const int c = blockIdx.z;
@@ -269,6 +272,7 @@ __global__ void __launch_bounds__(256) normal_loss_forward_kernel(int W, int H, 
                                                                   const uint8_t* __restrict__ mask,
                                                                   const float* __restrict__ gt, float4* __restrict__ partial)
 {
+    pdl_enter();
     __shared__ float red[4][8];
     const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
     const size_t N = (size_t)W * H;
@@ -316,6 +320,7 @@ __global__ void __launch_bounds__(1024) normal_loss_finish_kernel(int n, const f
                                                                   float* __restrict__ out, int accumulate,
                                                                   float* __restrict__ scal)
 {
+    pdl_enter();
     __shared__ double r[4][32];
     double a = 0, b = 0, c = 0, d = 0;
     for (int i = threadIdx.x; i < n; i += 1024) {
@@ -357,6 +362,7 @@ __global__ void __launch_bounds__(256) normal_loss_backward_kernel(int W, int H,
                                                                    const float* __restrict__ upstream,
                                                                    float* __restrict__ grad, int accumulate)
 {
+    pdl_enter();
     const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= W || y >= H) return;
     const size_t N = (size_t)W * H, o = (size_t)y * W + x;
@@ -430,18 +436,18 @@ int gigs_image_loss(int32_t C, int32_t W, int32_t H, const float* image, const f
     float* dxy = grad_image ? (float*)(base + 2 * maps) : nullptr;
     float2* partial = (float2*)(base + 3 * maps);
     ProfScope prof(27, st);
-    ssim_forward_kernel<<<grid, dim3(SS_T, 4), 0, st>>>(C, W, H, image, gt, dmu, dxx, dxy, partial);
+    GIGS_CUDA(launch_k(ssim_forward_kernel, dim3(grid), dim3(dim3(SS_T, 4)), (size_t)(0), st, C, W, H, image, gt, dmu, dxx, dxy, partial));
     GIGS_LAUNCH_CHECK("ssim_forward_kernel");
     if (loss_out) {
-        ssim_finish_kernel<<<1, 1024, 0, st>>>((int)n_cta, partial, 1.0 / (double)n, lambda_dssim, loss_scale, loss_out,
-                                               accumulate_loss);
+        GIGS_CUDA(launch_k(ssim_finish_kernel, dim3(1), dim3(1024), (size_t)(0), st, (int)n_cta, partial, 1.0 / (double)n, lambda_dssim, loss_scale, loss_out,
+                                               accumulate_loss));
         GIGS_LAUNCH_CHECK("ssim_finish_kernel");
     }
     if (grad_image) {
         const float k_ssim = (float)(-(double)loss_scale * (double)lambda_dssim / (double)n);
         const float k_l1 = (float)((double)loss_scale * (1.0 - (double)lambda_dssim) / (double)n);
-        ssim_backward_kernel<<<grid, dim3(SS_T, 4), 0, st>>>(C, W, H, image, gt, dmu, dxx, dxy, k_ssim, k_l1, upstream,
-                                                                grad_image, accumulate_grad);
+        GIGS_CUDA(launch_k(ssim_backward_kernel, dim3(grid), dim3(dim3(SS_T, 4)), (size_t)(0), st, C, W, H, image, gt, dmu, dxx, dxy, k_ssim, k_l1, upstream,
+                                                                grad_image, accumulate_grad));
         GIGS_LAUNCH_CHECK("ssim_backward_kernel");
     }
     return 0;
@@ -465,16 +471,16 @@ int gigs_normal_loss(int32_t W, int32_t H, const float* normal_map, const float*
     float4* partial = (float4*)scratch;
     float* scal = (float*)((char*)scratch + align_up(n_cta * 16, 256));
     ProfScope prof(28, st);
-    normal_loss_forward_kernel<<<grid, 256, 0, st>>>(W, H, normal_map, normal_from_depth, mask, gt_image, partial);
+    GIGS_CUDA(launch_k(normal_loss_forward_kernel, dim3(grid), dim3(256), (size_t)(0), st, W, H, normal_map, normal_from_depth, mask, gt_image, partial));
     GIGS_LAUNCH_CHECK("normal_loss_forward_kernel");
-    normal_loss_finish_kernel<<<1, 1024, 0, st>>>((int)n_cta, partial, W, H, normal_weight, tv_weight, loss_scale, loss_out,
-                                                  accumulate_loss, scal);
+    GIGS_CUDA(launch_k(normal_loss_finish_kernel, dim3(1), dim3(1024), (size_t)(0), st, (int)n_cta, partial, W, H, normal_weight, tv_weight, loss_scale, loss_out,
+                                                  accumulate_loss, scal));
     GIGS_LAUNCH_CHECK("normal_loss_finish_kernel");
     if (grad_normal) {
         const float kh = (float)(2.0 * (double)tv_weight * (double)loss_scale / (3.0 * (double)(H - 1) * (double)W));
         const float kw = (float)(2.0 * (double)tv_weight * (double)loss_scale / (3.0 * (double)H * (double)(W - 1)));
-        normal_loss_backward_kernel<<<grid, 256, 0, st>>>(W, H, normal_map, normal_from_depth, mask, gt_image, scal, kh, kw,
-                                                          upstream, grad_normal, accumulate_grad);
+        GIGS_CUDA(launch_k(normal_loss_backward_kernel, dim3(grid), dim3(256), (size_t)(0), st, W, H, normal_map, normal_from_depth, mask, gt_image, scal, kh, kw,
+                                                          upstream, grad_normal, accumulate_grad));
         GIGS_LAUNCH_CHECK("normal_loss_backward_kernel");
     }
     return 0;

@@ -68,6 +68,7 @@ __device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v,
 template <int ADAM_VEC_PER_THREAD>
 __global__ void __launch_bounds__(ADAM_THREADS) adam_kernel(const __grid_constant__ AdamArgs A)
 {
+    pdl_enter();
     constexpr int ADAM_CHUNK = ADAM_THREADS * ADAM_VEC_PER_THREAD * 4;   // floats per CTA
     // group of this CTA: the table is tiny and uniform over the CTA
     int gi = 0;
@@ -130,6 +131,7 @@ __global__ void densify_stats_kernel(int P, const int* __restrict__ radii, const
                                      float* __restrict__ accum_abs_max, float* __restrict__ denom,
                                      float* __restrict__ max_radii2D)
 {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
     const int r = radii[i];
@@ -195,9 +197,9 @@ int gigs_adam_step(int32_t n_groups, const GigsAdamGroup* groups, void* stream)
     if (!blocks) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     ProfScope prof(26, st);
-    if (vec == 1) adam_kernel<1><<<(unsigned int)blocks, ADAM_THREADS, 0, st>>>(A);
-    else if (vec == 2) adam_kernel<2><<<(unsigned int)blocks, ADAM_THREADS, 0, st>>>(A);
-    else adam_kernel<4><<<(unsigned int)blocks, ADAM_THREADS, 0, st>>>(A);
+    if (vec == 1) GIGS_CUDA(launch_k(adam_kernel<1>, dim3((unsigned int)blocks), dim3(ADAM_THREADS), (size_t)(0), st, A));
+    else if (vec == 2) GIGS_CUDA(launch_k(adam_kernel<2>, dim3((unsigned int)blocks), dim3(ADAM_THREADS), (size_t)(0), st, A));
+    else GIGS_CUDA(launch_k(adam_kernel<4>, dim3((unsigned int)blocks), dim3(ADAM_THREADS), (size_t)(0), st, A));
     GIGS_LAUNCH_CHECK("adam_kernel");
     return 0;
 }
@@ -210,9 +212,9 @@ int gigs_densify_stats(int32_t P, const int32_t* radii, const float* grad2D, int
     if (P == 0) return 0;
     if (!radii || !grad2D || !xyz_gradient_accum || !denom) { set_error("gigs_densify_stats: NULL input"); return -1; }
     cudaStream_t st = (cudaStream_t)stream;
-    densify_stats_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, radii, grad2D, grad_stride, xyz_gradient_accum,
+    GIGS_CUDA(launch_k(densify_stats_kernel, dim3((P + 255) / 256), dim3(256), (size_t)(0), st, P, radii, grad2D, grad_stride, xyz_gradient_accum,
                                                           xyz_gradient_accum_abs, xyz_gradient_accum_abs_max, denom,
-                                                          max_radii2D);
+                                                          max_radii2D));
     GIGS_LAUNCH_CHECK("densify_stats_kernel");
     return 0;
 }

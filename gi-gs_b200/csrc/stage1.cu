@@ -44,6 +44,7 @@ stage1_normals_forward_kernel(const int W, const int H, const float* __restrict_
                               float* __restrict__ normals_view, float* __restrict__ nfd_unit, uint8_t* __restrict__ sel,
                               uint8_t* __restrict__ mask)
 {
+    pdl_enter();
     __shared__ float s_n[3][S1_HH][S1_HW];
     __shared__ float s_R[9];
     const int tid = threadIdx.y * S1_TW + threadIdx.x;
@@ -92,6 +93,7 @@ stage1_normals_backward_kernel(const int W, const int H, const float* __restrict
                                const float* __restrict__ normal_map, const float* __restrict__ g_view,
                                const uint8_t* __restrict__ sel, float* __restrict__ g_normal)
 {
+    pdl_enter();
     __shared__ float s_g[3][S1_HH][S1_HW];      // gradient w.r.t. the median's output (world frame)
     __shared__ uint8_t s_sel[3][S1_HH][S1_HW];
     __shared__ float s_R[9];
@@ -256,10 +258,10 @@ int gigs_stage1_forward(GigsStage1* f)
     dim3 grid((W + S1_TW - 1) / S1_TW, (H + S1_TH - 1) / S1_TH), block(S1_TW, S1_TH);
     {
         ProfScope ps(ST_S1_NORMALS, st);
-        stage1_normals_forward_kernel<<<grid, block, 0, st>>>(W, H, c.viewmatrix, (float*)(m + FL.normal),
+        GIGS_CUDA(launch_k(stage1_normals_forward_kernel, dim3(grid), dim3(block), (size_t)(0), st, W, H, c.viewmatrix, (float*)(m + FL.normal),
                                                               (float*)(m + FL.normal_from_depth), (float*)(m + FL.normals_view),
                                                               (float*)(m + FL.nfd_unit), (uint8_t*)(m + FL.median_sel),
-                                                              (uint8_t*)(m + FL.mask));
+                                                              (uint8_t*)(m + FL.mask)));
         GIGS_LAUNCH_CHECK("stage1_normals_forward_kernel");
     }
     if (f->gt_image) {
@@ -296,9 +298,9 @@ int gigs_stage1_backward(GigsStage1* f)
     dim3 grid((W + S1_TW - 1) / S1_TW, (H + S1_TH - 1) / S1_TH), block(S1_TW, S1_TH);
     {
         ProfScope ps(ST_S1_NORMALS_BWD, st);
-        stage1_normals_backward_kernel<<<grid, block, 0, st>>>(W, H, c.viewmatrix, (float*)(m + FL.normal),
+        GIGS_CUDA(launch_k(stage1_normals_backward_kernel, dim3(grid), dim3(block), (size_t)(0), st, W, H, c.viewmatrix, (float*)(m + FL.normal),
                                                                (float*)(m + FL.g_normals_view), (uint8_t*)(m + FL.median_sel),
-                                                               (float*)(m + FL.g_normal));
+                                                               (float*)(m + FL.g_normal)));
         GIGS_LAUNCH_CHECK("stage1_normals_backward_kernel");
     }
     GigsRasterBwd b;
