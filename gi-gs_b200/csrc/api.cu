@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstring>
 #include <map>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <utility>
@@ -47,6 +48,8 @@ int ensure_dynamic_smem(const void* kernel, int bytes)
 
 // ---- programmatic dependent launch (common.cuh: launch_k) -------------------------------------------
 static int g_pdl = -1;   // -1: not decided yet (env GIGS_PDL, default on)
+static std::atomic<uint64_t> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 bool pdl_enabled()
 {
     if (g_pdl < 0) {
@@ -166,7 +169,8 @@ Layout make_layout(int P, int W, int H, uint64_t R)
 // launchers defined in the kernel files
 int launch_preprocess(const GigsRasterFwd* a, const Layout& L, cudaStream_t st, const float* sh_rest);
 int launch_depth_argsort(const GigsRasterFwd* a, const Layout& L, cudaStream_t st);
-int launch_emit_keys(const GigsRasterFwd* a, const Layout& L, uint32_t* keys, uint32_t* vals, cudaStream_t st);
+int launch_emit_keys(const GigsRasterFwd* a, const Layout& L, uint32_t* keys, uint32_t* vals, void* clear,
+                     uint64_t clear_bytes, int* cleared, cudaStream_t st);
 int launch_tile_ranges(uint64_t R, const uint32_t* tiles_sorted, uint2* ranges, uint32_t num_tiles, cudaStream_t st);
 int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t st);
 int launch_tile_sort(uint64_t R, int end_bit, const uint32_t* keys_u, const uint32_t* vals_u, uint32_t* keys_a,
@@ -188,10 +192,56 @@ static int check_common(int P, const GigsCamera& c)
     return 0;
 }
 
-// Copies num_rendered to the host and waits for THAT copy only: the depth argsort of the Gaussians (which does not
-// depend on num_rendered) is queued behind the copy, so the GPU keeps working while the host sizes the binning blob.
+// The page-locked word num_rendered is delivered in: the caller's (GigsRasterFwd.pinned_num_rendered) or one of this
+// thread's own. dev = its device alias when the word is mapped into the device's address space (page-locked memory
+// is, under unified addressing): the preprocess scan kernel then stores the total straight into host memory.
+int host_total_slot(const GigsRasterFwd* a, HostSlot* s)
+{
+    static thread_local uint32_t* pinned = nullptr;
+    if (!a->pinned_num_rendered && !pinned) GIGS_CUDA(cudaMallocHost((void**)&pinned, 64));
+    s->host = a->pinned_num_rendered ? a->pinned_num_rendered : pinned;
+    void* d = nullptr;
+    static const bool no_map = getenv("GIGS_NO_MAPPED_READBACK") != nullptr;
+    if (no_map || cudaHostGetDevicePointer(&d, s->host, 0) != cudaSuccess) {
+        cudaGetLastError();
+        d = nullptr;
+    }
+    s->dev = (uint32_t*)d;
+    return 0;
+}
+
+// num_rendered to the host. The depth argsort of the Gaussians (which does not depend on num_rendered) is queued
+// first, so the GPU keeps working while the host sizes the binning blob. Mapped word: the host polls it (the scan
+// kernel stored the total there; launch_preprocess armed it with NUM_RENDERED_PENDING) - no copy or event node in
+// the stream. Otherwise: a 4-byte copy and an event, waiting for THAT copy only.
 int read_back_num_rendered(GigsRasterFwd* a, const Layout& L, cudaStream_t st)
 {
+    HostSlot slot;
+    if (int e = host_total_slot(a, &slot)) return e;
+    if (slot.dev) {
+        {
+            ProfScope ps(ST_DEPTH_SORT, st);
+            if (int e = launch_depth_argsort(a, L, st)) return e;
+        }
+        volatile uint32_t* w = slot.host;
+        uint32_t v = *w;
+        for (uint32_t spins = 1; v == NUM_RENDERED_PENDING; ++spins) {
+            if ((spins & 0x3fffu) == 0) {   // a failed launch / sticky error must not spin for ever
+                const cudaError_t q = cudaStreamQuery(st);
+                if (q != cudaSuccess && q != cudaErrorNotReady) return cuda_fail(q, "cudaStreamQuery (num_rendered)");
+                if (q == cudaSuccess && *w == NUM_RENDERED_PENDING) {
+                    set_error("num_rendered was not delivered although the stream is idle");
+                    return -1;
+                }
+            }
+#if defined(__x86_64__) || defined(__i386__)
+            __builtin_ia32_pause();
+#endif
+            v = *w;
+        }
+        a->num_rendered = (int64_t)v;
+        return 0;
+    }
     // an event belongs to the device that was current when it was created: one per (thread, device)
     constexpr int MAX_DEV = 64;
     static thread_local cudaEvent_t evs[MAX_DEV] = {};
@@ -200,17 +250,14 @@ int read_back_num_rendered(GigsRasterFwd* a, const Layout& L, cudaStream_t st)
     if (dev < 0 || dev >= MAX_DEV) { set_error("device index %d out of range", dev); return -1; }
     if (!evs[dev]) GIGS_CUDA(cudaEventCreateWithFlags(&evs[dev], cudaEventDisableTiming));
     cudaEvent_t ev = evs[dev];
-    static thread_local uint32_t* pinned = nullptr;
-    if (!a->pinned_num_rendered && !pinned) GIGS_CUDA(cudaMallocHost((void**)&pinned, 64));
-    uint32_t* dst = a->pinned_num_rendered ? a->pinned_num_rendered : pinned;
-    GIGS_CUDA(cudaMemcpyAsync(dst, (char*)a->geom + L.off.g_num_rendered, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    GIGS_CUDA(cudaMemcpyAsync(slot.host, (char*)a->geom + L.off.g_num_rendered, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     GIGS_CUDA(cudaEventRecord(ev, st));
     {
         ProfScope ps(ST_DEPTH_SORT, st);
         if (int e = launch_depth_argsort(a, L, st)) return e;
     }
     GIGS_CUDA(cudaEventSynchronize(ev));
-    a->num_rendered = (int64_t)*dst;
+    a->num_rendered = (int64_t)*slot.host;
     return 0;
 }
 
@@ -248,17 +295,18 @@ int forward_finish_impl(GigsRasterFwd* a, bool lite)
     char* bn = (char*)a->binning;
     uint32_t* keys_u = (uint32_t*)(sc + L.off.s_tiles_unsorted);
     uint32_t* vals_u = (uint32_t*)(sc + L.off.s_vals_unsorted);
-    int ranges_done = 0;
+    int ranges_done = 0, sort_cleared = 0;
     if (a->P > 0 && R > 0) {
         {
             ProfScope ps(ST_EMIT_KEYS, st);
-            if (int e = launch_emit_keys(a, L, keys_u, vals_u, st)) return e;
+            if (int e = launch_emit_keys(a, L, keys_u, vals_u, sc + L.s_hist, L.s_zero_bytes, &sort_cleared, st)) return e;
         }
         ProfScope ps(ST_SORT, st);
         if (int e = launch_tile_sort(R, (int)L.sort_bits, keys_u, vals_u, (uint32_t*)(sc + L.s_keys_a),
                                      (uint32_t*)(bn + L.off.b_point_list), (uint32_t*)(sc + L.s_keys_b),
                                      (uint32_t*)(sc + L.s_vals_b), (uint32_t*)(sc + L.s_hist),
-                                     (uint32_t*)(sc + L.s_status), (uint32_t*)(sc + L.s_ticket), L.s_zero_bytes,
+                                     (uint32_t*)(sc + L.s_status), (uint32_t*)(sc + L.s_ticket),
+                                     sort_cleared ? 0 : L.s_zero_bytes,   // 0: the emit kernel cleared them
                                      ST_SORT_PASS, (uint32_t*)(sc + L.s_joint), (uint2*)(im + L.off.i_ranges), L.num_tiles,
                                      &ranges_done, st))
             return e;
@@ -283,6 +331,8 @@ using namespace gigs;
 extern "C" {
 
 int gigs_abi_version(void) { return GIGS_ABI_VERSION; }
+
+uint64_t gigs_launch_count(void) { return gigs::g_launches.load(std::memory_order_relaxed); }
 
 int gigs_set_dependent_launch(int32_t on)
 {

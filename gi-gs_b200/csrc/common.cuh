@@ -45,12 +45,18 @@ int ensure_dynamic_smem(const void* kernel, int bytes);
         if (int _e = gigs::ensure_dynamic_smem((const void*)(kernel), (int)(bytes))) return _e; \
     } while (0)
 
+// num_rendered reaches the host through a page-locked word the preprocess scan kernel stores to directly (api.cu)
+constexpr uint32_t NUM_RENDERED_PENDING = 0xffffffffu;
+struct HostSlot { uint32_t* host; uint32_t* dev; };   // dev == nullptr: the word is not mapped, use a copy
+int host_total_slot(const GigsRasterFwd* a, HostSlot* s);
+
 // Programmatic dependent launch (PTX griddepcontrol): a kernel launched through launch_k may be scheduled while the
 // previous kernel of the stream is still draining; it calls pdl_wait() FIRST (every thread, before any global access:
 // the wait returns once the previous grid has completed and its writes are visible) and pdl_trigger() right after (lets
 // the next launch_k kernel be scheduled). Both are no-ops in a kernel launched the ordinary way. Only kernels that
 // start with pdl_wait() may be launched with launch_k: completion then stays transitive along the stream.
 bool pdl_enabled();
+void note_launch();   // counts the kernels launched through launch_k (gigs_launch_count)
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_enter() { pdl_wait(); pdl_trigger(); }
@@ -68,6 +74,7 @@ inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    note_launch();
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 

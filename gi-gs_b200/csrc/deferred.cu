@@ -54,6 +54,10 @@ struct DeferParams {
     float* tv_edge;          // [2,H,W]: exp(-mean_c |d gt|) * mask * mask of the edge below / right of each pixel
     float loss_scale, lamb_weight, brdf_tv_weight;
     int nblk;
+    int occl_const;          // shade kernel only: SSAO does not march (start >= step): occlusion is the constant 1, which
+                             // this kernel writes to the map itself instead of reading a map a fill kernel wrote
+    uint4* clear_ptr;        // backward kernel only: a 16-B aligned region it zeroes on entry (the blend backward's
+    uint32_t clear_n16;      // per-Gaussian accumulator rows), in place of a memset node between the two kernels
 };
 
 __device__ __forceinline__ float srgb_to_linear_px(float s)
@@ -178,7 +182,8 @@ __global__ void __launch_bounds__(256) deferred_shade_kernel(const DeferParams p
         in.rough = p.roughness[id] * (1.0f - 0.04f) + 0.04f;   // train.py:297-299
         const float metal_map = p.metallic[id];
         in.metal = p.use_metallic ? metal_map : 0.f;
-        in.occ = p.occlusion ? p.occlusion[id] : 1.f;
+        in.occ = (p.occlusion && !p.occl_const) ? p.occlusion[id] : 1.f;
+        if (p.occl_const) const_cast<float*>(p.occlusion)[id] = 1.f;
         // normal_mask is taken on the RAW rasterizer normal (gaussian_renderer/__init__.py:158)
         const bool m = (p.normal_map[id] != 0.f) && (p.normal_map[HW + id] != 0.f) && (p.normal_map[2 * HW + id] != 0.f);
         PixelShade S;
@@ -352,6 +357,7 @@ __global__ void __launch_bounds__(256, MINB) deferred_backward_kernel(const Defe
     __shared__ float s_C[9];
     const int tid = threadIdx.y * DF_TW + threadIdx.x;
     const int lane = tid & 31;
+    for (uint32_t i = blockIdx.x * 256u + tid; i < p.clear_n16; i += gridDim.x * 256u) p.clear_ptr[i] = make_uint4(0u, 0u, 0u, 0u);
     const int W = p.W, H = p.H;
     const size_t HW = (size_t)W * H;
     const int ndt = 6 * p.sh.diffuse_res * p.sh.diffuse_res * 3;
@@ -453,12 +459,30 @@ __global__ void __launch_bounds__(256, MINB) deferred_backward_kernel(const Defe
     }
 }
 
-// grad[i] += sum over the TEX_COPIES private copies (fixed order: deterministic given the copies)
-__global__ void __launch_bounds__(256)
-texel_fold_kernel(const float* __restrict__ priv, const int n, float* __restrict__ grad)
+// grad[i] += sum over the TEX_COPIES private copies (fixed order: deterministic given the copies); every privatised
+// level in ONE launch: block b belongs to the segment whose [first_block, first_block + blocks) holds it
+struct TexelFoldArgs {
+    const float* priv[TEX_PRIV_MAX];
+    float* grad[TEX_PRIV_MAX];
+    int n[TEX_PRIV_MAX];
+    int first_block[TEX_PRIV_MAX + 1];
+    int segments;
+};
+__global__ void __launch_bounds__(256) texel_fold_kernel(const TexelFoldArgs a)
 {
     pdl_enter();
-    const int i = blockIdx.x * 256 + threadIdx.x;
+    const float* __restrict__ priv = a.priv[0];
+    float* __restrict__ grad = a.grad[0];
+    int n = a.n[0], first = 0;
+#pragma unroll
+    for (int j = 1; j < TEX_PRIV_MAX; ++j)
+        if (j < a.segments && (int)blockIdx.x >= a.first_block[j]) {
+            priv = a.priv[j];
+            grad = a.grad[j];
+            n = a.n[j];
+            first = a.first_block[j];
+        }
+    const int i = ((int)blockIdx.x - first) * 256 + threadIdx.x;
     if (i >= n) return;
     float s = 0.f;
 #pragma unroll 8
@@ -667,7 +691,8 @@ int gigs_frame_forward(GigsFrame* f)
     const float fx = W / (2.0f * c.tan_fovx), fy = H / (2.0f * c.tan_fovy);
     if (int e = gigs_geometry_chain(W, H, fx, fy, c.viewmatrix, (float*)(m + FL.depth), 1, (float*)(m + FL.normal_from_depth),
                                     (float*)(m + FL.depth_pos), f->stream)) return e;
-    if (f->indirect) {
+    const bool ssao_marches = f->start < f->step;   // otherwise the constant 1 (gi_march.cu: gi_launch), written by the shade kernel
+    if (f->indirect && ssao_marches) {
         if (int e = gigs_ssao(W, H, fx, fy, f->radius, f->bias, f->thick, f->delta, f->step, f->start,
                               (float*)(m + FL.normal_view), (float*)(m + FL.depth_pos), (float*)(m + FL.occlusion),
                               m + FL.tex_scratch, gigs_gi_scratch_bytes(W, H), f->stream))
@@ -675,6 +700,7 @@ int gigs_frame_forward(GigsFrame* f)
     }
     DeferParams p;
     fill_defer(f, FL, p, false);
+    p.occl_const = (f->indirect && !ssao_marches) ? 1 : 0;
     dim3 grid((W + DF_TW - 1) / DF_TW, (H + DF_TH - 1) / DF_TH), block(DF_TW, DF_TH);
     {
         ProfScope ps(ST_DEFER_SHADE, st);
@@ -710,6 +736,7 @@ int gigs_frame_backward(GigsFrame* f)
     fill_defer(f, FL, p, true);
     const int tiles_x = (W + DF_TW - 1) / DF_TW, ntiles = p.nblk;
     const size_t smem = SHB_MAX_DIFFUSE * sizeof(float) + 3 * DF_HH1 * DF_HW1 * (sizeof(float) + 1) + 16;
+    bool accum_cleared = false;
     {
         ProfScope ps(ST_DEFER_BWD, st);
         char* m = (char*)f->maps;
@@ -729,6 +756,11 @@ int gigs_frame_backward(GigsFrame* f)
         }
         if (slots > 0)
             GIGS_CUDA(cudaMemsetAsync(scratch, 0, (size_t)slots * TEX_PRIV_FLOATS * TEX_COPIES * sizeof(float), st));
+        // the blend backward's accumulator rows are cleared by this kernel's first instructions (no memset node)
+        const size_t accum_bytes = (size_t)f->P * ACC_FLOATS * sizeof(float);
+        accum_cleared = ((uintptr_t)f->accum % 16 == 0) && (accum_bytes % 16 == 0) && (accum_bytes / 16 < (1ull << 32));
+        p.clear_ptr = accum_cleared ? (uint4*)f->accum : nullptr;
+        p.clear_n16 = accum_cleared ? (uint32_t)(accum_bytes / 16) : 0u;
         static const int variant = getenv("GIGS_DFB") ? atoi(getenv("GIGS_DFB")) : 3;  // 3 CTAs/SM measured best (203 vs 214 us)
         const int per_sm = variant == 3 ? 3 : (variant == 4 ? 4 : 2);
         const int blocks = ntiles < 148 * per_sm * 2 ? ntiles : 148 * per_sm * 2;
@@ -739,9 +771,19 @@ int gigs_frame_backward(GigsFrame* f)
             else GIGS_CUDA(launch_k(deferred_backward_kernel<2>, dim3(blocks), dim3(dim3(DF_TW, DF_TH)), (size_t)(smem), st, p, tiles_x, ntiles));
         }
         GIGS_LAUNCH_CHECK("deferred_backward_kernel");
-        for (int k = 0; k < slots; ++k) {
-            GIGS_CUDA(launch_k(texel_fold_kernel, dim3((fold_n[k] + 255) / 256), dim3(256), (size_t)(0), st, 
-                scratch + (size_t)k * TEX_PRIV_FLOATS * TEX_COPIES, fold_n[k], fold_dst[k]));
+        if (slots > 0) {
+            TexelFoldArgs fa;
+            fa.segments = slots;
+            int nb = 0;
+            for (int k = 0; k < slots; ++k) {
+                fa.priv[k] = scratch + (size_t)k * TEX_PRIV_FLOATS * TEX_COPIES;
+                fa.grad[k] = fold_dst[k];
+                fa.n[k] = fold_n[k];
+                fa.first_block[k] = nb;
+                nb += (fold_n[k] + 255) / 256;
+            }
+            fa.first_block[slots] = nb;
+            GIGS_CUDA(launch_k(texel_fold_kernel, dim3(nb), dim3(256), (size_t)0, st, fa));
             GIGS_LAUNCH_CHECK("texel_fold_kernel");
         }
     }
@@ -756,7 +798,7 @@ int gigs_frame_backward(GigsFrame* f)
     const Layout L = make_layout(f->P, W, H, (uint64_t)f->num_rendered);
     {
         ProfScope ps(ST_BLEND_BWD, st);
-        GIGS_CUDA(cudaMemsetAsync(f->accum, 0, (size_t)f->P * ACC_FLOATS * sizeof(float), st));
+        if (!accum_cleared) GIGS_CUDA(cudaMemsetAsync(f->accum, 0, (size_t)f->P * ACC_FLOATS * sizeof(float), st));
         if (f->num_rendered > 0)
             if (int e = launch_blend_backward(&b, L, st)) return e;
     }

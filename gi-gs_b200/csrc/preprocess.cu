@@ -153,9 +153,13 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
                   // outputs
                   int* __restrict__ radii, float* __restrict__ records, float* __restrict__ cov3Ds,
                   uint8_t* __restrict__ clamped, uint32_t* __restrict__ tiles_touched,
-                  uint32_t* __restrict__ depth_keys, uint32_t* __restrict__ block_sums)
+                  uint32_t* __restrict__ depth_keys, uint32_t* __restrict__ block_sums,
+                  uint4* __restrict__ clear_ptr, const uint32_t clear_n16)
 {
     pdl_enter();
+    // the depth argsort's histogram / look-back words, cleared here instead of by a memset node in front of the sort
+    for (uint32_t i = blockIdx.x * PRE_THREADS + threadIdx.x; i < clear_n16; i += gridDim.x * PRE_THREADS)
+        clear_ptr[i] = make_uint4(0u, 0u, 0u, 0u);
     __shared__ float sV[16], sPM[16], sCam[3];
     __shared__ uint32_t s_warp_sum[PRE_THREADS / 32];
     if (threadIdx.x < 16) {
@@ -316,8 +320,11 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
 
 // Exclusive scan of the per-block sums (in place) + total. One block; nb = ceil(P/256) is small
 // (23k at 6M Gaussians).
+// total_host (may be NULL): device alias of a page-locked host word that also receives the total, so that the host
+// can read num_rendered without a copy node in the stream.
 __global__ void __launch_bounds__(1024) scan_block_sums_kernel(uint32_t* __restrict__ block_sums, int nb,
-                                                               uint32_t* __restrict__ total)
+                                                               uint32_t* __restrict__ total,
+                                                               uint32_t* __restrict__ total_host)
 {
     pdl_enter();
     __shared__ uint32_t s_warp[32];
@@ -354,7 +361,13 @@ __global__ void __launch_bounds__(1024) scan_block_sums_kernel(uint32_t* __restr
         if (threadIdx.x == 1023) s_carry = excl + v;
         __syncthreads();
     }
-    if (threadIdx.x == 0) *total = s_carry;
+    if (threadIdx.x == 0) {
+        *total = s_carry;
+        if (total_host) {
+            *reinterpret_cast<volatile uint32_t*>(total_host) = s_carry;
+            __threadfence_system();
+        }
+    }
 }
 
 // Block sums of tiles_touched taken in DEPTH order (order[] = argsort of the depth keys): feeds the same
@@ -388,9 +401,13 @@ __global__ void __launch_bounds__(PRE_THREADS)
 emit_keys_kernel(const int P, const uint32_t* __restrict__ order, const int* __restrict__ radii,
                  const float* __restrict__ records, const uint32_t* __restrict__ tiles_touched,
                  const uint32_t* __restrict__ block_offsets, const uint32_t grid_x, const uint32_t grid_y,
-                 uint32_t* __restrict__ keys, uint32_t* __restrict__ vals)
+                 uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                 uint4* __restrict__ clear_ptr, const uint32_t clear_n16)
 {
     pdl_enter();
+    // the instance sort's histogram / look-back words (see preprocess_kernel)
+    for (uint32_t i = blockIdx.x * PRE_THREADS + threadIdx.x; i < clear_n16; i += gridDim.x * PRE_THREADS)
+        clear_ptr[i] = make_uint4(0u, 0u, 0u, 0u);
     __shared__ uint32_t s_warp_tot[PRE_THREADS / 32];
     __shared__ uint32_t s_pref[PRE_THREADS / 32][32];
     __shared__ uint4 s_info[PRE_THREADS / 32][32];  // rect_min.x, rect_min.y, rect width, Gaussian id
@@ -471,6 +488,13 @@ mark_visible_kernel(const int P, const float* __restrict__ means3D, const float*
 
 // ------------------------------------------------------------------------------------------------
 // host launchers
+// The depth argsort's zeroed words live in the geometry blob; preprocess_kernel clears them when they can be written
+// as whole 16-byte units (then launch_depth_argsort passes zero_bytes = 0: nothing left to clear).
+static bool depth_scratch_cleared_by_preprocess(const char* g, const Layout& L)
+{
+    return ((uintptr_t)(g + L.p_hist) % 16 == 0) && (L.p_zero_bytes % 16 == 0) && (L.p_zero_bytes / 16 < (1ull << 32));
+}
+
 // ------------------------------------------------------------------------------------------------
 // sh_rest != nullptr selects the RAW variant: a->shs is then f_dc [P,1,3], sh_rest is f_rest [P,M-1,3], and
 // opacities / normal / albedo / roughness / metallic / scales / rotations are pre-activation leaves.
@@ -487,12 +511,15 @@ int launch_preprocess(const GigsRasterFwd* a, const Layout& L, cudaStream_t st, 
         c.projmatrix, c.campos, c.width, c.height, c.tan_fovx, c.tan_fovy, focal_x, focal_y, L.tiles_x, L.tiles_y,    \
         c.prefiltered != 0, stage_sh, a->material_only == 1, a->radii, (float*)(g + L.off.g_record), (float*)(g + L.off.g_cov3D),            \
         (uint8_t*)(g + L.off.g_clamped), (uint32_t*)(g + L.off.g_tiles_touched), (uint32_t*)(g + L.off.g_depth_keys), \
-        (uint32_t*)(g + L.off.g_block_sums)
+        (uint32_t*)(g + L.off.g_block_sums), clear_ptr, clear_n16
     // dynamic shared memory: the CTA's slab of SH coefficients (see the kernel); not staged if it would not fit
     const size_t sh_floats = (size_t)PRE_THREADS * (sh_rest ? (c.sh_coeffs - 1) * 3 : c.sh_coeffs * 3);
     static const bool no_stage = getenv("GIGS_PRE_NOSTAGE") != nullptr;
     const bool stage_sh = !no_stage && a->material_only != 1 && a->colors_precomp == nullptr && sh_floats > 0 && sh_floats * 4 <= 96 * 1024;
     const size_t smem = stage_sh ? sh_floats * 4 : 0;
+    const bool clears = depth_scratch_cleared_by_preprocess(g, L);
+    uint4* clear_ptr = clears ? (uint4*)(g + L.p_hist) : nullptr;
+    const uint32_t clear_n16 = clears ? (uint32_t)(L.p_zero_bytes / 16) : 0u;
     GIGS_SMEM_ATTR(preprocess_kernel<true>, 96 * 1024);
     GIGS_SMEM_ATTR(preprocess_kernel<false>, 96 * 1024);
     if (sh_rest != nullptr)
@@ -501,8 +528,11 @@ int launch_preprocess(const GigsRasterFwd* a, const Layout& L, cudaStream_t st, 
         GIGS_CUDA(launch_k(preprocess_kernel<false>, dim3(L.num_blocks), dim3(PRE_THREADS), (size_t)(smem), st, PRE_ARGS));
 #undef PRE_ARGS
     GIGS_LAUNCH_CHECK("preprocess_kernel");
+    HostSlot slot;
+    if (int e = host_total_slot(a, &slot)) return e;
+    if (slot.dev) *reinterpret_cast<volatile uint32_t*>(slot.host) = NUM_RENDERED_PENDING;   // read_back_num_rendered polls it
     GIGS_CUDA(launch_k(scan_block_sums_kernel, dim3(1), dim3(1024), (size_t)(0), st, (uint32_t*)(g + L.off.g_block_sums), (int)L.num_blocks,
-                                               (uint32_t*)(g + L.off.g_num_rendered)));
+                       (uint32_t*)(g + L.off.g_num_rendered), slot.dev));
     GIGS_LAUNCH_CHECK("scan_block_sums_kernel");
     return 0;
 }
@@ -518,21 +548,28 @@ int launch_depth_argsort(const GigsRasterFwd* a, const Layout& L, cudaStream_t s
     return launch_radix_sort32((uint64_t)a->P, 32, (const uint32_t*)(g + L.off.g_depth_keys), nullptr,
                                (uint32_t*)(g + L.p_keys_a), (uint32_t*)(g + L.off.g_order), (uint32_t*)(g + L.p_keys_b),
                                (uint32_t*)(g + L.p_vals_b), (uint32_t*)(g + L.p_hist), (uint32_t*)(g + L.p_status),
-                               (uint32_t*)(g + L.p_ticket), L.p_zero_bytes, -1, st);
+                               (uint32_t*)(g + L.p_ticket),
+                               depth_scratch_cleared_by_preprocess(g, L) ? 0 : L.p_zero_bytes, -1, st);
 }
 
-int launch_emit_keys(const GigsRasterFwd* a, const Layout& L, uint32_t* keys, uint32_t* vals, cudaStream_t st)
+// clear / clear_bytes: the instance sort's zeroed words; *cleared = 1 when the emit kernel cleared them
+int launch_emit_keys(const GigsRasterFwd* a, const Layout& L, uint32_t* keys, uint32_t* vals, void* clear,
+                     uint64_t clear_bytes, int* cleared, cudaStream_t st)
 {
+    *cleared = (clear && (uintptr_t)clear % 16 == 0 && clear_bytes % 16 == 0 && clear_bytes / 16 < (1ull << 32)) ? 1 : 0;
     char* g = (char*)a->geom;
     const uint32_t* order = (const uint32_t*)(g + L.off.g_order);
     const uint32_t* touched = (const uint32_t*)(g + L.off.g_tiles_touched);
     uint32_t* sums2 = (uint32_t*)(g + L.g_block_sums2);
     GIGS_CUDA(launch_k(ordered_block_sums_kernel, dim3(L.num_blocks), dim3(PRE_THREADS), (size_t)(0), st, a->P, order, touched, sums2));
     GIGS_LAUNCH_CHECK("ordered_block_sums_kernel");
-    GIGS_CUDA(launch_k(scan_block_sums_kernel, dim3(1), dim3(1024), (size_t)(0), st, sums2, (int)L.num_blocks, sums2 + L.num_blocks));
+    GIGS_CUDA(launch_k(scan_block_sums_kernel, dim3(1), dim3(1024), (size_t)(0), st, sums2, (int)L.num_blocks, sums2 + L.num_blocks,
+                       (uint32_t*)nullptr));
     GIGS_LAUNCH_CHECK("scan_block_sums_kernel");
     GIGS_CUDA(launch_k(emit_keys_kernel, dim3(L.num_blocks), dim3(PRE_THREADS), (size_t)(0), st, a->P, order, a->radii, (const float*)(g + L.off.g_record),
-                                                          touched, sums2, L.tiles_x, L.tiles_y, keys, vals));
+                                                          touched, sums2, L.tiles_x, L.tiles_y, keys, vals,
+                                                          *cleared ? (uint4*)clear : (uint4*)nullptr,
+                                                          *cleared ? (uint32_t)(clear_bytes / 16) : 0u));
     GIGS_LAUNCH_CHECK("emit_keys_kernel");
     return 0;
 }

@@ -401,8 +401,9 @@ static int sort_pairs(uint64_t R, int end_bit, const K* keys_u, const uint32_t* 
     const int digit_bits = radix_digit_bits(end_bit);
     const int passes = (end_bit + digit_bits - 1) / digit_bits;
     const uint32_t status_tiles = (n + RS_MIN_TILE - 1) / RS_MIN_TILE;
-    // hist, tickets and status are contiguous in the scratch blob: one memset
-    GIGS_CUDA(cudaMemsetAsync(hist, 0, zero_bytes, st));
+    // hist, tickets and status are contiguous in the scratch blob: one memset (zero_bytes == 0: the caller's previous
+    // kernel already cleared them)
+    if (zero_bytes) GIGS_CUDA(cudaMemsetAsync(hist, 0, zero_bytes, st));
     if (joint != nullptr && sizeof(K) == 4 && end_bit <= RS_JOINT_BITS) {
         const int bins = 1 << end_bit;
         const uint32_t hblocks = min((n + 16383u) / 16384u, 148u * 2u);

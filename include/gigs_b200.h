@@ -237,6 +237,10 @@ int gigs_gi_tune(int32_t pairs_per_step, int32_t block_test);
  * variable GIGS_PDL=0); on < 0 only queries. Returns the previous setting. */
 int gigs_set_dependent_launch(int32_t on);
 
+/* Kernels this library has launched in this process so far (frame, first-stage, loss, optimiser and light-build
+ * paths; a benchmark reads it before and after its timed region). */
+uint64_t gigs_launch_count(void);
+
 /* Replaces SSR_BACKWARD (rasterize_points.cu:479-510). The reference's Python never calls its
  * kernel (diff_gaussian_rasterization/__init__.py:666-673); the live semantics are
  * grad_albedo = grad_color * abd, zeros for roughness/metallic, which is what this computes. */
