@@ -21,12 +21,14 @@
 #include <cstring>
 #include "filters.cuh"
 #include "shade_core.cuh"
+#include "gi_epilogue.cuh"
 
 namespace gigs {
 
 int launch_preprocess(const GigsRasterFwd* a, const Layout& L, cudaStream_t st, const float* sh_rest);
 int forward_finish_impl(GigsRasterFwd* a, bool lite);
 int read_back_num_rendered(GigsRasterFwd* a, const Layout& L, cudaStream_t st);
+int gi_direction_count(float delta, int* n);
 int launch_blend_backward(const GigsRasterBwd* a, const Layout& L, cudaStream_t st);
 
 constexpr int TEX_PRIV_RES = 32;                                   // textures up to this face size are privatised
@@ -54,6 +56,9 @@ struct DeferParams {
     float* tv_edge;          // [2,H,W]: exp(-mean_c |d gt|) * mask * mask of the edge below / right of each pixel
     float loss_scale, lamb_weight, brdf_tv_weight;
     int nblk;
+    int ssr_const;           // shade kernel only: SSR does not march either: its per-pixel epilogue (gi_epilogue.cuh) over a
+    float ssr_dirs;          // zero gathered radiance and ssr_dirs directions is evaluated here; depth_pos = positions
+    const float* depth_pos;
     int occl_const;          // shade kernel only: SSAO does not march (start >= step): occlusion is the constant 1, which
                              // this kernel writes to the map itself instead of reading a map a fill kernel wrote
     uint4* clear_ptr;        // backward kernel only: a 16-B aligned region it zeroes on entry (the blend backward's
@@ -190,6 +195,7 @@ __global__ void __launch_bounds__(256) deferred_shade_kernel(const DeferParams p
         shade_eval(p.sh, in, S);
         const float lin[3] = {S.lin.x, S.lin.y, S.lin.z};
         const float alb[3] = {in.alb.x, in.alb.y, in.alb.z};
+        float f0[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             float xk = lin[k];
@@ -199,11 +205,24 @@ __global__ void __launch_bounds__(256) deferred_shade_kernel(const DeferParams p
             p.render_direct[k * HW + id] = direct;
             p.linear_rgb[k * HW + id] = srgb_to_linear_px(direct);
             // train.py:374-378
-            p.F0[k * HW + id] = p.use_metallic ? ((1.0f - metal_map) * 0.04f + alb[k] * metal_map) : 0.04f;
+            f0[k] = p.use_metallic ? ((1.0f - metal_map) * 0.04f + alb[k] * metal_map) : 0.04f;
+            p.F0[k * HW + id] = f0[k];
         }
         p.rough_remap[id] = in.rough;
         p.metal_used[id] = in.metal;
         p.mask[id] = m ? 1 : 0;
+        if (p.ssr_const) {
+            // what ssr_nomarch_kernel (gi_march.cu) computes from the maps written above, for this pixel
+            const float3 F0v = make_float3(f0[0], f0[1], f0[2]);
+            const float3 posv = make_float3(p.depth_pos[id], p.depth_pos[HW + id], p.depth_pos[2 * HW + id]);
+            float3 col, abd;
+            ssr_epilogue_px(normalize3(make_float3(mv[0], mv[1], mv[2])), posv, in.alb, F0v, in.metal,
+                            make_float3(0.f, 0.f, 0.f), p.ssr_dirs, col, abd);
+            float* oc = const_cast<float*>(p.ssr_color);
+            float* oa = const_cast<float*>(p.ssr_abd);
+            oc[id] = col.x; oc[HW + id] = col.y; oc[2 * HW + id] = col.z;
+            oa[id] = abd.x; oa[HW + id] = abd.y; oa[2 * HW + id] = abd.z;
+        }
         if (m) {
             cnt = 1.f;
             s1 = 1.0f - in.rough;
@@ -701,12 +720,18 @@ int gigs_frame_forward(GigsFrame* f)
     DeferParams p;
     fill_defer(f, FL, p, false);
     p.occl_const = (f->indirect && !ssao_marches) ? 1 : 0;
+    int ssr_dirs = 0;
+    const bool ssr_fused = !ssao_marches && gi_direction_count(f->delta, &ssr_dirs) == 0;
+    p.ssr_const = ssr_fused ? 1 : 0;
+    p.ssr_dirs = (float)ssr_dirs;
+    p.depth_pos = (const float*)(m + FL.depth_pos);
     dim3 grid((W + DF_TW - 1) / DF_TW, (H + DF_TH - 1) / DF_TH), block(DF_TW, DF_TH);
     {
         ProfScope ps(ST_DEFER_SHADE, st);
         GIGS_CUDA(launch_k(deferred_shade_kernel, dim3(grid), dim3(block), (size_t)(0), st, p));
         GIGS_LAUNCH_CHECK("deferred_shade_kernel");
     }
+    if (!ssr_fused)
     if (int e = gigs_ssr(W, H, fx, fy, f->radius, f->bias, f->thick, f->delta, f->step, f->start, p.ssr_normal,
                          (float*)(m + FL.depth_pos), p.linear_rgb, p.albedo, p.rough_remap, p.metal_used, p.F0,
                          (float*)(m + FL.ssr_color), (float*)(m + FL.ssr_abd), m + FL.tex_scratch,

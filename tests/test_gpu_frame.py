@@ -328,3 +328,39 @@ def test_material_only_frame_is_bit_identical_where_it_computes():
     assert ((res[True][1] - res[False][1]).norm() / res[True][1].norm()).item() <= 1e-6
     for k, v in res[True][2].items():
         assert torch.equal(v, res[False][2][k]), k
+
+
+@pytest.mark.parametrize("gi", [GI8, GI64])
+def test_dependent_launch_changes_no_result(gi):
+    """gigs_set_dependent_launch: the frame's kernels launched with programmatic stream serialization (each waits for
+    the previous grid before its first global access) against ordinary stream-ordered launches: loss and every map are
+    bit-for-bit the same, the gradients agree to the order of the backward's atomic reductions; the launch counter
+    (gigs_launch_count) sees the same number of kernels either way."""
+    from gigs import _lib
+    L = _lib.load()
+    P, W, H, base = 20000, 400, 300, 64
+    raw, cam, lut, rays, gt, bg = _setup(P, W, H)
+    res = {}
+    prev = L.gigs_set_dependent_launch(-1)
+    try:
+        for on in (0, 1):
+            assert L.gigs_set_dependent_launch(on) in (0, 1)
+            assert L.gigs_set_dependent_launch(-1) == on
+            p = gstep.GaussianParams(raw, DEV, light=scene.make_light(0, base_res=base))
+            p.zero_grad()
+            c0 = int(L.gigs_launch_count())
+            for _ in range(3):      # back-to-back frames: the next frame's first kernels run behind this one's last
+                p.zero_grad()
+                l = gstep.training_step(p, cam, p.light(), lut, rays, gt, bg, gi, fused=True, brdf_tv_weight=1.0)
+            torch.cuda.synchronize()
+            ws = p.last_workspace
+            res[on] = (float(l), p.flat_grad.clone(), int(L.gigs_launch_count()) - c0,
+                       {k: ws.map(k).clone() for k in ("albedo", "roughness", "metallic", "normal", "normal_view", "depth",
+                                                       "opacity", "occlusion", "render_rgb", "ssr_color", "ssr_abd")})
+    finally:
+        L.gigs_set_dependent_launch(prev)
+    assert res[0][0] == res[1][0]
+    assert res[0][2] == res[1][2] and res[0][2] > 0
+    assert ((res[0][1] - res[1][1]).norm() / res[0][1].norm()).item() <= 1e-6
+    for k, v in res[0][3].items():
+        assert torch.equal(v, res[1][3][k]), k
