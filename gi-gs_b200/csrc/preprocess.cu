@@ -402,13 +402,20 @@ emit_keys_kernel(const int P, const uint32_t* __restrict__ order, const int* __r
                  const float* __restrict__ records, const uint32_t* __restrict__ tiles_touched,
                  const uint32_t* __restrict__ block_offsets, const uint32_t grid_x, const uint32_t grid_y,
                  uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                 uint4* __restrict__ clear_ptr, const uint32_t clear_n16)
+                 uint4* __restrict__ clear_ptr, const uint32_t clear_n16, const bool self_prefix)
 {
     pdl_enter();
+    // self_prefix: block_offsets holds the UNSCANNED block sums and this CTA adds up its predecessors' itself (a few
+    // loads per thread for up to EMIT_SELF_PREFIX_BLOCKS blocks, issued first so that they overlap the gathers below)
+    // instead of a one-CTA scan kernel sitting between the block sums and this kernel
+    uint32_t part = 0;
+    if (self_prefix)
+        for (uint32_t j = threadIdx.x; j < blockIdx.x; j += PRE_THREADS) part += block_offsets[j];
     // the instance sort's histogram / look-back words (see preprocess_kernel)
     for (uint32_t i = blockIdx.x * PRE_THREADS + threadIdx.x; i < clear_n16; i += gridDim.x * PRE_THREADS)
         clear_ptr[i] = make_uint4(0u, 0u, 0u, 0u);
     __shared__ uint32_t s_warp_tot[PRE_THREADS / 32];
+    __shared__ uint32_t s_part[PRE_THREADS / 32];
     __shared__ uint32_t s_pref[PRE_THREADS / 32][32];
     __shared__ uint4 s_info[PRE_THREADS / 32][32];  // rect_min.x, rect_min.y, rect width, Gaussian id
 
@@ -436,8 +443,17 @@ emit_keys_kernel(const int P, const uint32_t* __restrict__ order, const int* __r
     if (lane == 31) s_warp_tot[warp] = inc;
     s_pref[warp][lane] = inc - cnt;
     s_info[warp][lane] = info;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) s_part[warp] = part;
     __syncthreads();
-    uint32_t warp_off = block_offsets[blockIdx.x];
+    uint32_t warp_off = 0;
+    if (self_prefix) {
+#pragma unroll
+        for (int w = 0; w < PRE_THREADS / 32; ++w) warp_off += s_part[w];
+    } else {
+        warp_off = block_offsets[blockIdx.x];
+    }
     for (int w = 0; w < warp; ++w) warp_off += s_warp_tot[w];
 
     const uint32_t E = s_warp_tot[warp];
@@ -552,6 +568,7 @@ int launch_depth_argsort(const GigsRasterFwd* a, const Layout& L, cudaStream_t s
                                depth_scratch_cleared_by_preprocess(g, L) ? 0 : L.p_zero_bytes, -1, st);
 }
 
+constexpr uint32_t EMIT_SELF_PREFIX_BLOCKS = 4096;   // up to 1M Gaussians (<= 16 loads per thread)
 // clear / clear_bytes: the instance sort's zeroed words; *cleared = 1 when the emit kernel cleared them
 int launch_emit_keys(const GigsRasterFwd* a, const Layout& L, uint32_t* keys, uint32_t* vals, void* clear,
                      uint64_t clear_bytes, int* cleared, cudaStream_t st)
@@ -563,13 +580,16 @@ int launch_emit_keys(const GigsRasterFwd* a, const Layout& L, uint32_t* keys, ui
     uint32_t* sums2 = (uint32_t*)(g + L.g_block_sums2);
     GIGS_CUDA(launch_k(ordered_block_sums_kernel, dim3(L.num_blocks), dim3(PRE_THREADS), (size_t)(0), st, a->P, order, touched, sums2));
     GIGS_LAUNCH_CHECK("ordered_block_sums_kernel");
-    GIGS_CUDA(launch_k(scan_block_sums_kernel, dim3(1), dim3(1024), (size_t)(0), st, sums2, (int)L.num_blocks, sums2 + L.num_blocks,
-                       (uint32_t*)nullptr));
-    GIGS_LAUNCH_CHECK("scan_block_sums_kernel");
+    const bool self_prefix = L.num_blocks <= EMIT_SELF_PREFIX_BLOCKS;
+    if (!self_prefix) {
+        GIGS_CUDA(launch_k(scan_block_sums_kernel, dim3(1), dim3(1024), (size_t)(0), st, sums2, (int)L.num_blocks, sums2 + L.num_blocks,
+                           (uint32_t*)nullptr));
+        GIGS_LAUNCH_CHECK("scan_block_sums_kernel");
+    }
     GIGS_CUDA(launch_k(emit_keys_kernel, dim3(L.num_blocks), dim3(PRE_THREADS), (size_t)(0), st, a->P, order, a->radii, (const float*)(g + L.off.g_record),
                                                           touched, sums2, L.tiles_x, L.tiles_y, keys, vals,
                                                           *cleared ? (uint4*)clear : (uint4*)nullptr,
-                                                          *cleared ? (uint32_t)(clear_bytes / 16) : 0u));
+                                                          *cleared ? (uint32_t)(clear_bytes / 16) : 0u, self_prefix));
     GIGS_LAUNCH_CHECK("emit_keys_kernel");
     return 0;
 }

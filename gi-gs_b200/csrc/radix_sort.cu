@@ -20,6 +20,7 @@
 namespace gigs {
 
 constexpr int RS_HTHREADS = 256;   // histogram kernel
+constexpr int RS_HU = 8;           // keys fetched per thread before any is counted
 constexpr int RS_MAX_RADIX = 256;  // histogram / status rows are laid out for 8-bit digits
 constexpr int RS_MAX_PASSES = 8;
 constexpr int RS_MIN_TILE = 2048;  // smallest tile of any configuration: sizes the look-back status array
@@ -37,14 +38,25 @@ rs_histogram_kernel(const K* __restrict__ keys, const uint32_t n, const int pass
     __shared__ uint32_t s_hist[RS_MAX_PASSES][RS_MAX_RADIX];
     for (int i = threadIdx.x; i < passes * RS_MAX_RADIX; i += RS_HTHREADS) (&s_hist[0][0])[i] = 0;
     __syncthreads();
+    // RS_HU independent loads in flight per thread (the one-key-per-iteration loop was a chain of DRAM round trips:
+    // 13.5 us for 300k keys, long-scoreboard bound)
     const uint32_t stride = gridDim.x * RS_HTHREADS;
-    for (uint32_t i = blockIdx.x * RS_HTHREADS + threadIdx.x; i < n; i += stride) {
-        const K k = keys[i];
-        for (int p = 0; p < passes; ++p) {
-            const int shift = p * digit_bits;
-            const int bits = min(digit_bits, end_bit - shift);
-            const uint32_t d = (uint32_t)(k >> shift) & ((1u << bits) - 1u);
-            atomicAdd(&s_hist[p][d], 1u);
+    for (uint32_t i0 = blockIdx.x * RS_HTHREADS + threadIdx.x; i0 < n; i0 += stride * RS_HU) {
+        K k[RS_HU];
+#pragma unroll
+        for (int u = 0; u < RS_HU; ++u) {
+            const uint32_t i = i0 + u * stride;
+            k[u] = (i < n) ? keys[i] : (K)0;
+        }
+#pragma unroll
+        for (int u = 0; u < RS_HU; ++u) {
+            if (i0 + u * stride >= n) break;
+            for (int p = 0; p < passes; ++p) {
+                const int shift = p * digit_bits;
+                const int bits = min(digit_bits, end_bit - shift);
+                const uint32_t d = (uint32_t)(k[u] >> shift) & ((1u << bits) - 1u);
+                atomicAdd(&s_hist[p][d], 1u);
+            }
         }
     }
     __syncthreads();
@@ -153,27 +165,6 @@ rs_joint_scan_kernel(const uint32_t* __restrict__ joint, const int bins, const i
     }
 }
 
-// exclusive scan of each pass's 256-bin histogram (in place)
-__global__ void __launch_bounds__(RS_MAX_RADIX) rs_scan_hist_kernel(uint32_t* __restrict__ hist)
-{
-    pdl_enter();
-    __shared__ uint32_t s_warp[RS_MAX_RADIX / 32];
-    uint32_t* h = hist + blockIdx.x * RS_MAX_RADIX;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t v = h[threadIdx.x];
-    uint32_t inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) s_warp[warp] = inc;
-    __syncthreads();
-    uint32_t off = 0;
-    for (int w = 0; w < warp; ++w) off += s_warp[w];
-    h[threadIdx.x] = off + inc - v;
-}
-
 template <typename K, int BITS, int THREADS, int ITEMS>
 struct RsSmem {
     static constexpr int RADIX = 1 << BITS;
@@ -185,6 +176,7 @@ struct RsSmem {
     uint32_t digit_start[RADIX];
     uint32_t global_off[RADIX];
     uint32_t warp_tot[RADIX / 32];
+    uint32_t warp_tot_h[RADIX / 32];
     uint32_t tile;
 };
 
@@ -194,7 +186,7 @@ __global__ void __launch_bounds__(THREADS)
 rs_onesweep_kernel(const K* __restrict__ keys_in, K* __restrict__ keys_out, const uint32_t* __restrict__ vals_in,
                    uint32_t* __restrict__ vals_out, const uint32_t n, const int shift, const uint32_t digit_mask,
                    const uint32_t* __restrict__ digit_base, volatile uint32_t* __restrict__ status /*[tiles][RADIX]*/,
-                   uint32_t* __restrict__ ticket)
+                   uint32_t* __restrict__ ticket, const bool raw_hist)
 {
     pdl_enter();
     using Smem = RsSmem<K, BITS, THREADS, ITEMS>;
@@ -293,21 +285,35 @@ rs_onesweep_kernel(const K* __restrict__ keys_in, K* __restrict__ keys_out, cons
             }
             *my_status = ((excl + sum) << 2) | FLAG_INC;
         }
-        // exclusive scan of the tile's digit totals -> position of each digit inside the tile
-        uint32_t inc = sum;
+        // exclusive scan of the tile's digit totals -> position of each digit inside the tile; with raw_hist the
+        // same shuffles also scan the global digit counts (digit_base then holds the histogram itself, not its
+        // exclusive scan: one launch fewer in front of the passes)
+        const uint32_t hv = digit_base[d];
+        uint32_t inc = sum, hinc = hv;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
+            uint32_t th = __shfl_up_sync(0xffffffffu, hinc, o);
+            if (lane >= o) {
+                inc += t;
+                hinc += th;
+            }
         }
-        if (lane == 31) S.warp_tot[warp] = inc;
+        if (lane == 31) {
+            S.warp_tot[warp] = inc;
+            S.warp_tot_h[warp] = hinc;
+        }
         // barrier among the RADIX digit threads only (the block is larger)
         asm volatile("bar.sync 1, %0;" ::"n"(RADIX) : "memory");
-        uint32_t woff = 0;
-        for (int w = 0; w < warp; ++w) woff += S.warp_tot[w];
+        uint32_t woff = 0, hoff = 0;
+        for (int w = 0; w < warp; ++w) {
+            woff += S.warp_tot[w];
+            hoff += S.warp_tot_h[w];
+        }
         const uint32_t dstart = woff + inc - sum;
+        const uint32_t dbase = raw_hist ? (hoff + hinc - hv) : hv;
         S.digit_start[d] = dstart;
-        S.global_off[d] = digit_base[d] + excl - dstart;  // wraps mod 2^32 on purpose
+        S.global_off[d] = dbase + excl - dstart;  // wraps mod 2^32 on purpose
     }
     __syncthreads();
 
@@ -342,7 +348,7 @@ rs_onesweep_kernel(const K* __restrict__ keys_in, K* __restrict__ keys_out, cons
 template <typename K, int BITS, int T, int I>
 static int launch_passes(uint32_t n, int end_bit, const K* keys_u, const uint32_t* vals_u, K* keys_a, uint32_t* vals_a,
                          K* keys_b, uint32_t* vals_b, uint32_t* hist, uint32_t* status, uint32_t* tickets,
-                         uint32_t status_tiles, int pass_stage, cudaStream_t st)
+                         uint32_t status_tiles, int pass_stage, bool raw_hist, cudaStream_t st)
 {
     using Smem = RsSmem<K, BITS, T, I>;
     static_assert(T * I <= 65536 && T * I >= RS_MIN_TILE, "tile must fit the u16 ranks and the status allocation");
@@ -361,7 +367,7 @@ static int launch_passes(uint32_t n, int end_bit, const K* keys_u, const uint32_
         ProfScope ps(pass_stage, st);
         GIGS_CUDA(launch_k(rs_onesweep_kernel<K, BITS, T, I>, dim3(tiles), dim3(T), (size_t)(sizeof(Smem)), st, 
             kin, kout, vin, vout, n, shift, (1u << bits) - 1u, hist + p * RS_MAX_RADIX,
-            status + (size_t)p * status_tiles * RS_MAX_RADIX, tickets + p));
+            status + (size_t)p * status_tiles * RS_MAX_RADIX, tickets + p, raw_hist));
         GIGS_LAUNCH_CHECK("rs_onesweep_kernel");
         kin = kout;
         vin = vout;
@@ -401,6 +407,7 @@ static int sort_pairs(uint64_t R, int end_bit, const K* keys_u, const uint32_t* 
     const int digit_bits = radix_digit_bits(end_bit);
     const int passes = (end_bit + digit_bits - 1) / digit_bits;
     const uint32_t status_tiles = (n + RS_MIN_TILE - 1) / RS_MIN_TILE;
+    bool raw_hist = false;
     // hist, tickets and status are contiguous in the scratch blob: one memset (zero_bytes == 0: the caller's previous
     // kernel already cleared them)
     if (zero_bytes) GIGS_CUDA(cudaMemsetAsync(hist, 0, zero_bytes, st));
@@ -413,15 +420,14 @@ static int sort_pairs(uint64_t R, int end_bit, const K* keys_u, const uint32_t* 
         GIGS_CUDA(launch_k(rs_joint_scan_kernel, dim3(1), dim3(1024), (size_t)(0), st, joint, bins, passes, digit_bits, end_bit, hist, ranges, num_tiles));
         GIGS_LAUNCH_CHECK("rs_joint_scan_kernel");
     } else {
-        const uint32_t hblocks = min((n + 4095u) / 4096u, 148u * 8u);
+        const uint32_t hblocks = min((n + 2047u) / 2048u, 148u * 8u);
         GIGS_CUDA(launch_k(rs_histogram_kernel<K>, dim3(hblocks), dim3(RS_HTHREADS), (size_t)(0), st, keys_u, n, passes, digit_bits, end_bit, hist));
         GIGS_LAUNCH_CHECK("rs_histogram_kernel");
-        GIGS_CUDA(launch_k(rs_scan_hist_kernel, dim3(passes), dim3(RS_MAX_RADIX), (size_t)(0), st, hist));
-        GIGS_LAUNCH_CHECK("rs_scan_hist_kernel");
+        raw_hist = true;   // the passes scan the digit counts themselves (no scan launch in front of them)
     }
     static const int cfg = env_int("GIGS_RS_CFG", 0);
 #define RS_GO(B, T, I) \
-    return launch_passes<K, B, T, I>(n, end_bit, keys_u, vals_u, keys_a, vals_a, keys_b, vals_b, hist, status, tickets, status_tiles, pass_stage, st)
+    return launch_passes<K, B, T, I>(n, end_bit, keys_u, vals_u, keys_a, vals_a, keys_b, vals_b, hist, status, tickets, status_tiles, pass_stage, raw_hist, st)
     // small inputs: small tiles so that every SM gets work; large inputs: big tiles for long coalesced runs
     const bool small = n < 148u * 8192u;
     if (digit_bits == 6) {
