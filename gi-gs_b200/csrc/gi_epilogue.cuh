@@ -12,6 +12,18 @@ __device__ __forceinline__ void ssr_epilogue_px(const float3 normal, const float
                                                 const float metallic, float3 diffuse, const float nrSamples,
                                                 float3& color, float3& abd)
 {
+    // Nothing gathered (every component +0.0: always the case when no direction is marched) and F0, metallic inside
+    // [0, 1] (activated parameters are): the chain below is then +0 exactly, whatever the normal and the position are -
+    // fpow lies in (0, 1] for every input (the base is clamped to [1e-6, 1]), so F = F0 + (1 - F0) * fpow <= 1 in float
+    // with or without the contraction (rn(F0 + rn(1 - F0)) == 1), kD = (1 - F)(1 - metallic) is a finite value >= +0,
+    // and pi * (+0) * (1/n) * kD = +0. The double-precision pow is skipped; NaN / out-of-range inputs take the full path.
+    if (nrSamples > 0.0f && __float_as_uint(diffuse.x) == 0u && __float_as_uint(diffuse.y) == 0u &&
+        __float_as_uint(diffuse.z) == 0u && F0.x >= 0.f && F0.x <= 1.f && F0.y >= 0.f && F0.y <= 1.f && F0.z >= 0.f &&
+        F0.z <= 1.f && metallic >= 0.f && metallic <= 1.f) {
+        abd = make_float3(0.f, 0.f, 0.f);
+        color = make_float3(0.f * albedo.x, 0.f * albedo.y, 0.f * albedo.z);
+        return;
+    }
     const float3 Vd = normalize3(make_float3(-pos.x, -pos.y, -pos.z));
     // fresnelSchlick (ssr.h:13-16): the un-suffixed literals make the base a double subtraction and
     // the power a double pow, rounded to float before the float3 multiply
