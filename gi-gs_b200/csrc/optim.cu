@@ -149,6 +149,31 @@ __global__ void densify_stats_kernel(int P, const int* __restrict__ radii, const
 
 using namespace gigs;
 
+// ---- zero_grad of selected spans of the flat gradient buffer, one launch (optimizer.zero_grad(), train.py:518,522) ----
+constexpr int CLEAR_MAX_SPANS = 8;
+struct ClearArgs {
+    float* base;
+    unsigned long long begin[CLEAR_MAX_SPANS], end[CLEAR_MAX_SPANS];
+    int n;
+};
+__global__ void __launch_bounds__(256) clear_spans_kernel(const ClearArgs a)
+{
+    pdl_enter();
+    const size_t gtid = (size_t)blockIdx.x * 256 + threadIdx.x, gstride = (size_t)gridDim.x * 256;
+    for (int s = 0; s < a.n; ++s) {
+        float* p = a.base + a.begin[s];
+        const size_t len = a.end[s] - a.begin[s];
+        size_t head = ((16 - ((uintptr_t)p & 15)) & 15) / 4;   // floats up to the next 16-byte boundary
+        if (head > len) head = len;
+        if (gtid < head) p[gtid] = 0.f;
+        float4* q = reinterpret_cast<float4*>(p + head);
+        const size_t n4 = (len - head) / 4;
+        for (size_t i = gtid; i < n4; i += gstride) q[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const size_t done = head + 4 * n4;
+        if (gtid < len - done) p[done + gtid] = 0.f;
+    }
+}
+
 extern "C" {
 
 int gigs_adam_step(int32_t n_groups, const GigsAdamGroup* groups, void* stream)
@@ -216,6 +241,31 @@ int gigs_densify_stats(int32_t P, const int32_t* radii, const float* grad2D, int
                                                           xyz_gradient_accum_abs, xyz_gradient_accum_abs_max, denom,
                                                           max_radii2D));
     GIGS_LAUNCH_CHECK("densify_stats_kernel");
+    return 0;
+}
+
+int gigs_clear_spans(float* base, int32_t n_spans, const uint64_t* begin, const uint64_t* end, void* stream)
+{
+    if (n_spans < 0 || n_spans > CLEAR_MAX_SPANS) { set_error("gigs_clear_spans: at most %d spans", CLEAR_MAX_SPANS); return -1; }
+    if (n_spans == 0) return 0;
+    if (!base || !begin || !end) { set_error("gigs_clear_spans: NULL argument"); return -1; }
+    ClearArgs a;
+    a.base = base;
+    a.n = n_spans;
+    size_t total = 0;
+    for (int s = 0; s < n_spans; ++s) {
+        if (end[s] < begin[s]) { set_error("gigs_clear_spans: span %d ends before it begins", s); return -1; }
+        a.begin[s] = begin[s];
+        a.end[s] = end[s];
+        total += (size_t)(end[s] - begin[s]);
+    }
+    if (total == 0) return 0;
+    size_t blocks = (total / 4 + 256 * 4 - 1) / (256 * 4);   // ~4 x 16 bytes per thread
+    if (blocks < 1) blocks = 1;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    cudaStream_t st = (cudaStream_t)stream;
+    GIGS_CUDA(launch_k(clear_spans_kernel, dim3((unsigned)blocks), dim3(256), (size_t)0, st, a));
+    GIGS_LAUNCH_CHECK("clear_spans_kernel");
     return 0;
 }
 

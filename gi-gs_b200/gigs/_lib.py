@@ -241,6 +241,7 @@ SYMBOLS = {
     "gigs_stage1_forward": (C.c_int, [C.POINTER(GigsStage1)]),
     "gigs_stage1_backward": (C.c_int, [C.POINTER(GigsStage1)]),
     "gigs_adam_step": (C.c_int, [_i32, C.POINTER(GigsAdamGroup), _vp]),
+    "gigs_clear_spans": (C.c_int, [_vp, _i32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), _vp]),
     "gigs_densify_stats": (C.c_int, [_i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gigs_image_loss": (C.c_int, [_i32, _i32, _i32, _vp, _vp, _f, _f, _vp, C.POINTER(C.c_uint64), _vp, _i32, _vp, _i32,
                                   _vp, _vp]),

@@ -111,9 +111,22 @@ class GaussianParams:
         produces material and light gradients (train.py:343-351 detaches everything else), so 12.6 MB are cleared
         instead of the whole 87 MB buffer (300k Gaussians). Falls back to a full clear whenever that is not known."""
         if not fused_only or self._dirty is None:
-            self.flat_grad.zero_()
+            spans = [(0, self.flat_grad.numel())]
         else:
-            for lo, hi in self._merged_dirty():
+            spans = self._merged_dirty()
+        if self.flat_grad.is_cuda and 0 < len(spans) <= 8:
+            # one launch of ours (chains with the frame's kernels) instead of one framework fill per span
+            import ctypes as C
+            from . import _lib
+            _L = _lib.load()
+            n = len(spans)
+            lo = (C.c_uint64 * n)(*[int(a) for a, _ in spans])
+            hi = (C.c_uint64 * n)(*[int(b) for _, b in spans])
+            with torch.cuda.device(self.flat_grad.device):
+                _lib.check(_L.gigs_clear_spans(self.flat_grad.data_ptr(), n, lo, hi,
+                                               torch.cuda.current_stream(self.flat_grad.device).cuda_stream), "gigs_clear_spans")
+        else:
+            for lo, hi in spans:
                 self.flat_grad[lo:hi].zero_()
         self._dirty = []
 

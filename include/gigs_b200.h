@@ -518,6 +518,11 @@ typedef struct GigsAdamGroup {
 } GigsAdamGroup;
 int gigs_adam_step(int32_t n_groups, const GigsAdamGroup* groups, void* stream);
 
+/* optimizer.zero_grad() (train.py:518,522) of up to 8 spans [begin, end) (element offsets) of one float buffer, in one
+ * launch that chains with the frame's kernels (the fused frame path writes material and light gradients only, so a
+ * training step clears those two spans instead of the whole buffer). */
+int gigs_clear_spans(float* base, int32_t n_spans, const uint64_t* begin, const uint64_t* end, void* stream);
+
 /* Densification statistics of one view (/root/reference/train.py:489-495 + GaussianModel.add_densification_stats,
  * scene/gaussian_model.py:933-945) for the Gaussians with radii > 0: max_radii2D = max(max_radii2D, radii),
  * xyz_gradient_accum += |grad2D.xy|, xyz_gradient_accum_abs += |gx| + |gy|, xyz_gradient_accum_abs_max =

@@ -364,3 +364,27 @@ def test_dependent_launch_changes_no_result(gi):
     assert ((res[0][1] - res[1][1]).norm() / res[0][1].norm()).item() <= 1e-6
     for k, v in res[0][3].items():
         assert torch.equal(v, res[1][3][k]), k
+
+
+def test_clear_spans_zeroes_exactly_the_spans():
+    """gigs_clear_spans (zero_grad of the spans a step wrote, one launch): odd offsets and lengths, empty spans,
+    a span shorter than one 16-byte unit, and nothing outside the spans touched."""
+    from gigs import _lib
+    L = _lib.load()
+    n = 1 << 20
+    buf = torch.arange(1, n + 1, dtype=torch.float32, device=DEV)
+    ref = buf.clone()
+    spans = [(0, 1), (3, 3), (5, 7), (13, 1000), (4099, 4099 + 65537), (n - 9, n), (200001, 200002), (300000, 300019)]
+    lo = (C.c_uint64 * len(spans))(*[a for a, _ in spans])
+    hi = (C.c_uint64 * len(spans))(*[b for _, b in spans])
+    _lib.check(L.gigs_clear_spans(buf.data_ptr(), len(spans), lo, hi, torch.cuda.current_stream().cuda_stream), "clear")
+    for a, b in spans:
+        ref[a:b] = 0
+    assert torch.equal(buf, ref)
+    # the same through GaussianParams.zero_grad on an offset view of the buffer
+    view = buf[1:]            # 4-byte aligned only
+    view.fill_(1.0)
+    lo1 = (C.c_uint64 * 1)(2); hi1 = (C.c_uint64 * 1)(n - 3)
+    _lib.check(L.gigs_clear_spans(view.data_ptr(), 1, lo1, hi1, torch.cuda.current_stream().cuda_stream), "clear")
+    assert view[:2].eq(1).all() and view[n - 3:].eq(1).all() and view[2:n - 3].eq(0).all()
+    assert L.gigs_clear_spans(buf.data_ptr(), 9, lo, hi, None) != 0     # more than 8 spans: refused
