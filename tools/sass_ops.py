@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Per-kernel counts of the SASS mnemonics that show what a kernel is built from (cuobjdump -sass of the built library):
 UBLKCP / SYNCS = TMA bulk copies completing on mbarriers, FFMA2 / FMUL2 / FADD2 = packed FP32, RED / REDG = reductions
-to global memory (scalar and vector), ATOMS = shared-memory atomics, LDGMC = multimem (NVLS) load-reduce, MUFU, LDS/LDG.
+to global memory (scalar and vector), ATOMS = shared-memory atomics, LDGMC = multimem (NVLS) load-reduce, ACQBULK /
+PREEXIT = griddepcontrol.wait / launch_dependents (programmatic dependent launch), MUFU, LDS/LDG.
 usage: python tools/sass_ops.py > profiles/sass_ops.txt"""
 import collections
 import os
@@ -10,7 +11,7 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "gi-gs_b200", "lib", "libgigs_b200.so")
-OPS = ["UBLKCP", "SYNCS", "FFMA2", "FMUL2", "FADD2", "FFMA", "MUFU", "REDG", "RED", "ATOMS", "ATOMG", "LDGMC", "STG", "LDG",
+OPS = ["UBLKCP", "SYNCS", "ACQBULK", "PREEXIT", "FFMA2", "FMUL2", "FADD2", "FFMA", "MUFU", "REDG", "RED", "ATOMS", "ATOMG", "LDGMC", "STG", "LDG",
        "LDS", "STS", "SHFL", "VOTE", "BAR", "LDL", "STL"]
 
 
