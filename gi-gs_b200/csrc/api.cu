@@ -142,9 +142,10 @@ Layout make_layout(int P, int W, int H, uint64_t R)
     L.off.i_n_contrib = take(N * 4);
     L.off.i_ranges = take((uint64_t)L.num_tiles * 8);
     L.size.img_bytes = align_up(o, 128) + 128;
-    // binning (kept for backward): sorted Gaussian ids only
+    // binning (kept for backward): sorted Gaussian ids + the forward's footprint-test masks
     o = 0;
     L.off.b_point_list = take(R * 4);
+    L.b_warp_masks = take(((R >> 5) + (uint64_t)L.num_tiles + 1) * WARP_MASK_WORDS * 4);
     L.size.binning_bytes = align_up(o, 128) + 128;
     // instance sort scratch: (tile id, Gaussian id) pairs, tile-id bits only
     o = 0;

@@ -348,7 +348,7 @@ blend_backward_material_kernel(const int W, const int H, const uint2* __restrict
                                const uint32_t* __restrict__ point_list, const float* __restrict__ records,
                                const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpix_albedo,
                                const float* __restrict__ dL_dpix_roughness, const float* __restrict__ dL_dpix_metallic,
-                               float* __restrict__ accum)
+                               float* __restrict__ accum, const uint32_t* __restrict__ warp_masks)
 {
     pdl_enter();
     constexpr uint32_t RECB = 32;
@@ -367,6 +367,7 @@ blend_backward_material_kernel(const int W, const int H, const uint2* __restrict
     const int HW = H * W;
 
     const uint2 range = ranges[blockIdx.y * horizontal_blocks + blockIdx.x];
+    const uint32_t mask_chunk0 = (range.x >> 5) + (blockIdx.y * horizontal_blocks + blockIdx.x);
     const int last_contributor = inside ? (int)n_contrib[pix_id] : 0;
     {
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -456,23 +457,35 @@ blend_backward_material_kernel(const int W, const int H, const uint2* __restrict
     for (int b = 0; b < rounds; ++b) {
         const int s = b & 1;
         if (b + 1 < rounds) issue(b + 1);
+        // lane l fetches the forward's mask of chunk l of this batch (issued before the wait on the records)
+        uint32_t batch_masks = 0u;
+        if (warp_masks != nullptr && lane < BB_BATCH / 32 && b * BB_BATCH + lane * 32 < wmax)
+            batch_masks = warp_masks[((size_t)mask_chunk0 + (b * (BB_BATCH / 32) + lane)) * WARP_MASK_WORDS + warp];
         mbar_wait(&S.bar[s], (uint32_t)((b >> 1) & 1));
         const int cnt = min(BB_BATCH, n - b * BB_BATCH);
         for (int jb = 0; jb < cnt; jb += 32) {
             const int fwd_lo = b * BB_BATCH + jb;  // forward index of the first entry of this chunk
             if (fwd_lo >= wmax) break;             // this warp's pixels were all finished before this chunk
-            bool keep = false;
-            const int jl = jb + lane;
-            if (jl < cnt && (fwd_lo + lane) < wmax) {
-                const float4 t0 = *reinterpret_cast<const float4*>(&S.rec[s][jl][0]);
-                const float4 t1 = *reinterpret_cast<const float4*>(&S.rec[s][jl][4]);
-                const float cA = t0.z, cB = t0.w, cC = t1.x;
-                const float hx = t0.x - strip_x0;
-                const float hy = t0.y - strip_y0;
-                const float qmin = warp_block_qmin(cA, cB, cC, hx, hy);
-                keep = !(cA > 0.f) || !(qmin > t1.w + 0.05f);
+            uint32_t mask;
+            if (warp_masks != nullptr) {
+                // the forward ran this very test for this warp's block on this chunk: take its result
+                mask = __shfl_sync(0xffffffffu, batch_masks, jb >> 5);
+                const int reach = wmax - fwd_lo;   // entries of the chunk this warp's pixels got to (> 0)
+                if (reach < 32) mask &= (1u << reach) - 1u;
+            } else {
+                bool keep = false;
+                const int jl = jb + lane;
+                if (jl < cnt && (fwd_lo + lane) < wmax) {
+                    const float4 t0 = *reinterpret_cast<const float4*>(&S.rec[s][jl][0]);
+                    const float4 t1 = *reinterpret_cast<const float4*>(&S.rec[s][jl][4]);
+                    const float cA = t0.z, cB = t0.w, cC = t1.x;
+                    const float hx = t0.x - strip_x0;
+                    const float hy = t0.y - strip_y0;
+                    const float qmin = warp_block_qmin(cA, cB, cC, hx, hy);
+                    keep = !(cA > 0.f) || !(qmin > t1.w + 0.05f);
+                }
+                mask = __ballot_sync(0xffffffffu, keep);
             }
-            uint32_t mask = __ballot_sync(0xffffffffu, keep);
             while (mask) {
                 const int jo = __ffs(mask) - 1;
                 mask &= mask - 1;
@@ -538,7 +551,7 @@ blend_backward_hybrid_kernel(const int W, const int H, const uint2* __restrict__
                              const float* __restrict__ dL_dpix, const float* __restrict__ dL_dpix_opacity,
                              const float* __restrict__ dL_dpix_normal, const float* __restrict__ dL_dpix_albedo,
                              const float* __restrict__ dL_dpix_roughness, const float* __restrict__ dL_dpix_metallic,
-                             float* __restrict__ accum)
+                             float* __restrict__ accum, const uint32_t* __restrict__ warp_masks)
 {
     pdl_enter();
     constexpr uint32_t RECB = 12 * 4;
@@ -557,6 +570,7 @@ blend_backward_hybrid_kernel(const int W, const int H, const uint2* __restrict__
     const int HW = H * W;
 
     const uint2 range = ranges[blockIdx.y * horizontal_blocks + blockIdx.x];
+    const uint32_t mask_chunk0 = (range.x >> 5) + (blockIdx.y * horizontal_blocks + blockIdx.x);
     const int last_contributor = inside ? (int)n_contrib[pix_id] : 0;
 
     float g_col[3] = {0.f, 0.f, 0.f};
@@ -601,7 +615,11 @@ blend_backward_hybrid_kernel(const int W, const int H, const uint2* __restrict__
 #pragma unroll
     for (int w = 0; w < BB_THREADS / 32; ++w) n = max(n, S.red[w]);
     n = min(n, (int)(range.y - range.x));
-    const int rounds = (n + BB_BATCH - 1) / BB_BATCH;
+    // The list is walked back to front in chunks of 32 that coincide with the FORWARD's chunks (so that its
+    // footprint-test masks apply): slot k of the walk is forward index n_pad - 1 - k, n_pad = n rounded up to 32; the
+    // first n_pad - n slots are padding (no record is loaded for them and no lane ever selects them: they are >= wmax).
+    const int n_pad = (n + 31) & ~31;
+    const int rounds = (n_pad + BB_BATCH - 1) / BB_BATCH;
 
     int ox_, oy_;
     warp_block_origin(tid, ox_, oy_);
@@ -610,10 +628,11 @@ blend_backward_hybrid_kernel(const int W, const int H, const uint2* __restrict__
 
     auto issue = [&](int b) {
         const int s = b & 1;
-        const int cnt = min(BB_BATCH, n - b * BB_BATCH);
-        if (tid == 0) mbar_arrive_expect_tx(&S.bar[s], (uint32_t)cnt * RECB);
-        if (tid < cnt) {
-            const uint32_t id = point_list[range.x + (n - 1 - (b * BB_BATCH + tid))];
+        const int cnt = min(BB_BATCH, n_pad - b * BB_BATCH);
+        const int pad = (b == 0) ? (n_pad - n) : 0;          // padding slots sit at the head of batch 0
+        if (tid == 0) mbar_arrive_expect_tx(&S.bar[s], (uint32_t)(cnt - pad) * RECB);
+        if (tid >= pad && tid < cnt) {
+            const uint32_t id = point_list[range.x + (n_pad - 1 - (b * BB_BATCH + tid))];
             S.ids[s][tid] = id;
             bulk_g2s(&S.rec[s][tid][0], records + (size_t)id * REC_FLOATS, RECB, &S.bar[s]);
         }
@@ -673,23 +692,38 @@ blend_backward_hybrid_kernel(const int W, const int H, const uint2* __restrict__
     for (int b = 0; b < rounds; ++b) {
         const int s = b & 1;
         if (b + 1 < rounds) issue(b + 1);
+        // lane l fetches the forward's mask of this batch's chunk l (forward chunk n_pad/32 - 1 - (b*BATCH/32 + l))
+        uint32_t batch_masks = 0u;
+        {
+            const int fc = (n_pad >> 5) - 1 - (b * (BB_BATCH / 32) + lane);
+            if (warp_masks != nullptr && lane < BB_BATCH / 32 && fc >= 0 && fc * 32 < wmax)
+                batch_masks = warp_masks[((size_t)mask_chunk0 + fc) * WARP_MASK_WORDS + warp];
+        }
         mbar_wait(&S.bar[s], (uint32_t)((b >> 1) & 1));
-        const int cnt = min(BB_BATCH, n - b * BB_BATCH);
+        const int cnt = min(BB_BATCH, n_pad - b * BB_BATCH);
         for (int jb = 0; jb < cnt; jb += 32) {
-            const int fwd_hi = n - 1 - (b * BB_BATCH + jb);  // largest forward index in this chunk
-            if (fwd_hi - 31 >= wmax) continue;               // whole chunk beyond this warp's reach
-            bool keep = false;
-            const int jl = jb + lane;
-            if (jl < cnt && (fwd_hi - lane) < wmax) {
-                const float4 t0 = *reinterpret_cast<const float4*>(&S.rec[s][jl][0]);
-                const float4 t1 = *reinterpret_cast<const float4*>(&S.rec[s][jl][4]);
-                const float cA = t0.z, cB = t0.w, cC = t1.x;
-                const float hx = t0.x - strip_x0;
-                const float hy = t0.y - strip_y0;
-                const float qmin = warp_block_qmin(cA, cB, cC, hx, hy);
-                keep = !(cA > 0.f) || !(qmin > t1.w + 0.05f);
+            const int fwd_hi = n_pad - 1 - (b * BB_BATCH + jb);  // largest forward index in this chunk (= 31 mod 32)
+            if (fwd_hi - 31 >= wmax) continue;                   // whole chunk beyond this warp's reach
+            uint32_t mask;
+            if (warp_masks != nullptr) {
+                // lane jo of this walk is the forward's lane 31 - jo of the same chunk
+                mask = __brev(__shfl_sync(0xffffffffu, batch_masks, jb >> 5));
+                const int skip = fwd_hi - wmax + 1;              // lanes below this are past the warp's reach
+                if (skip > 0) mask &= ~((1u << skip) - 1u);
+            } else {
+                bool keep = false;
+                const int jl = jb + lane;
+                if (jl < cnt && (fwd_hi - lane) < wmax) {
+                    const float4 t0 = *reinterpret_cast<const float4*>(&S.rec[s][jl][0]);
+                    const float4 t1 = *reinterpret_cast<const float4*>(&S.rec[s][jl][4]);
+                    const float cA = t0.z, cB = t0.w, cC = t1.x;
+                    const float hx = t0.x - strip_x0;
+                    const float hy = t0.y - strip_y0;
+                    const float qmin = warp_block_qmin(cA, cB, cC, hx, hy);
+                    keep = !(cA > 0.f) || !(qmin > t1.w + 0.05f);
+                }
+                mask = __ballot_sync(0xffffffffu, keep);
             }
-            uint32_t mask = __ballot_sync(0xffffffffu, keep);
             while (mask) {
                 const int jo = __ffs(mask) - 1;
                 mask &= mask - 1;
@@ -781,6 +815,9 @@ int launch_blend_backward(const GigsRasterBwd* a, const Layout& L, cudaStream_t 
     const float* recs = (const float*)(g + L.off.g_record);
     const uint32_t* ncontrib = (const uint32_t*)(im + L.off.i_n_contrib);
     const float* finalT = (const float*)(im + L.off.i_final_T);
+    // the forward's footprint-test masks (binning blob); GIGS_BB_NOMASKS=1: every kernel runs the test itself
+    static const bool no_masks = getenv("GIGS_BB_NOMASKS") != nullptr;
+    const uint32_t* masks = no_masks ? nullptr : (const uint32_t*)(bn + L.b_warp_masks);
     const bool material_only = (a->dL_dpix == nullptr) && (a->dL_dpix_opacity == nullptr) &&
                                (a->dL_dpix_normal == nullptr) && (a->dL_dpix_depth == nullptr);
     static const bool legacy_material = getenv("GIGS_BB_LEGACY") != nullptr;
@@ -788,7 +825,7 @@ int launch_blend_backward(const GigsRasterBwd* a, const Layout& L, cudaStream_t 
         GIGS_SMEM_ATTR(blend_backward_material_kernel, sizeof(MatSmem));
         GIGS_CUDA(launch_k(blend_backward_material_kernel, dim3(grid), dim3(block), (size_t)(sizeof(MatSmem)), st, 
             c.width, c.height, ranges, plist, recs, ncontrib, a->dL_dpix_albedo, a->dL_dpix_roughness,
-            a->dL_dpix_metallic, a->accum));
+            a->dL_dpix_metallic, a->accum, masks));
     } else if (material_only)
         GIGS_CUDA(launch_k(blend_backward_kernel<MODE_MATERIAL>, dim3(grid), dim3(block), (size_t)(sizeof(BwdSmem<8>)), st, 
             c.width, c.height, ranges, plist, recs, c.bg, finalT, ncontrib, a->dL_dpix_depth, a->dL_dpix,
@@ -801,12 +838,12 @@ int launch_blend_backward(const GigsRasterBwd* a, const Layout& L, cudaStream_t 
             GIGS_CUDA(launch_k(blend_backward_hybrid_kernel<2>, dim3(grid), dim3(block), (size_t)(sizeof(HybSmem)), st, 
                 c.width, c.height, ranges, plist, recs, c.bg, finalT, ncontrib, a->dL_dpix_depth, a->dL_dpix,
                 a->dL_dpix_opacity, a->dL_dpix_normal, a->dL_dpix_albedo, a->dL_dpix_roughness, a->dL_dpix_metallic,
-                a->accum));
+                a->accum, masks));
         else
             GIGS_CUDA(launch_k(blend_backward_hybrid_kernel<3>, dim3(grid), dim3(block), (size_t)(sizeof(HybSmem)), st, 
                 c.width, c.height, ranges, plist, recs, c.bg, finalT, ncontrib, a->dL_dpix_depth, a->dL_dpix,
                 a->dL_dpix_opacity, a->dL_dpix_normal, a->dL_dpix_albedo, a->dL_dpix_roughness, a->dL_dpix_metallic,
-                a->accum));
+                a->accum, masks));
     } else
         GIGS_CUDA(launch_k(blend_backward_kernel<MODE_FULL>, dim3(grid), dim3(block), (size_t)(sizeof(BwdSmem<12>)), st, 
             c.width, c.height, ranges, plist, recs, c.bg, finalT, ncontrib, a->dL_dpix_depth, a->dL_dpix,

@@ -48,7 +48,7 @@ blend_forward_kernel(const int W, const int H, const uint2* __restrict__ ranges,
                      float* __restrict__ out_opacity, float* __restrict__ out_depth, float* __restrict__ out_normal,
                      float* __restrict__ out_normal_view, float* __restrict__ out_pos,
                      float* __restrict__ out_albedo, float* __restrict__ out_roughness,
-                     float* __restrict__ out_metallic, const bool inference)
+                     float* __restrict__ out_metallic, const bool inference, uint32_t* __restrict__ warp_masks)
 {
     pdl_enter();
     extern __shared__ __align__(128) unsigned char bl_smem_raw[];
@@ -69,6 +69,7 @@ blend_forward_kernel(const int W, const int H, const uint2* __restrict__ ranges,
     const uint2 range = ranges[blockIdx.y * horizontal_blocks + blockIdx.x];
     const int n = (int)(range.y - range.x);
     const int rounds = (n + BATCH - 1) / BATCH;
+    const uint32_t mask_chunk0 = (range.x >> 5) + (blockIdx.y * horizontal_blocks + blockIdx.x);
 
     if (tid == 0) {
         mbar_init(&S.bar[0], 1);
@@ -124,6 +125,9 @@ blend_forward_kernel(const int W, const int H, const uint2* __restrict__ ranges,
                 keep = !(cA > 0.f) || !(qmin > t1.w + 0.05f);
             }
             uint32_t mask = __ballot_sync(0xffffffffu, keep);
+            // kept for the backward kernels, which walk the same list against the same pixel block (common.cuh: Layout)
+            if (warp_masks != nullptr && lane == 0)
+                warp_masks[((size_t)mask_chunk0 + ((b * BATCH + jb) >> 5)) * WARP_MASK_WORDS + (tid >> 5)] = mask;
             while (mask) {
                 const int j = jb + __ffs(mask) - 1;
                 mask &= mask - 1;
@@ -261,11 +265,12 @@ int launch_blend_forward(const GigsRasterFwd* a, const Layout& L, bool lite, cud
     uint32_t* ncontrib = (uint32_t*)(im + L.off.i_n_contrib);
     float* finalT = (float*)(im + L.off.i_final_T);
     const bool am = c.argmax_depth != 0;
+    uint32_t* masks = (uint32_t*)(const_cast<char*>(bn) + L.b_warp_masks);
 #define BL_LITE_ARGS c.width, c.height, ranges, plist, recs, c.viewmatrix, c.bg, ncontrib, finalT, a->out_color, a->out_opacity, \
-                     a->out_depth, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, false
+                     a->out_depth, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, false, (uint32_t*)nullptr
 #define BL_FULL_ARGS c.width, c.height, ranges, plist, recs, c.viewmatrix, c.bg, ncontrib, finalT, a->out_color, a->out_opacity, \
                      a->out_depth, a->out_normal, a->out_normal_view, a->out_pos, a->out_albedo, a->out_roughness,             \
-                     a->out_metallic, c.inference != 0
+                     a->out_metallic, c.inference != 0, masks
     if (lite && am) GIGS_CUDA(launch_k(blend_forward_kernel<true, true>, dim3(grid), dim3(block), (size_t)(sizeof(BlendSmem)), st, BL_LITE_ARGS));
     else if (lite) GIGS_CUDA(launch_k(blend_forward_kernel<true, false>, dim3(grid), dim3(block), (size_t)(sizeof(BlendSmem)), st, BL_LITE_ARGS));
     else if (am) GIGS_CUDA(launch_k(blend_forward_kernel<false, true>, dim3(grid), dim3(block), (size_t)(sizeof(BlendSmem)), st, BL_FULL_ARGS));

@@ -15,6 +15,7 @@ constexpr int TILE_X = 16;       // reference config.h:16-17 (the tile size is p
 constexpr int TILE_Y = 16;
 constexpr int TILE_PIX = TILE_X * TILE_Y;
 constexpr int REC_FLOATS = 24;   // packed blend record, 96 B, 16-B aligned (DESIGN.md "HBM layout")
+constexpr int WARP_MASK_WORDS = 8;   // warps of a 16x16 tile
 constexpr int ACC_FLOATS = 20;   // packed per-Gaussian gradient accumulator, 80 B
 
 // record slots
@@ -119,6 +120,9 @@ struct Layout {
     uint32_t sort_tiles, sort_passes, sort_bits;
     // Gaussian depth argsort internals (geom blob) + block sums of tiles_touched in depth order
     uint64_t p_keys_a, p_keys_b, p_vals_b, p_hist, p_status, p_ticket, p_zero_bytes, g_block_sums2;
+    // binning blob: the forward blend's per-(chunk of 32 list entries, warp) footprint-test results, reused by the
+    // backward kernels (WARP_MASK_WORDS words per chunk; chunk index of tile t = (range.x >> 5) + t + chunk in tile)
+    uint64_t b_warp_masks;
 };
 Layout make_layout(int P, int W, int H, uint64_t R);
 uint32_t higher_msb(uint32_t n);
