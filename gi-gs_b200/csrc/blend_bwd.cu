@@ -747,7 +747,13 @@ blend_backward_hybrid_kernel(const int W, const int H, const uint2* __restrict__
                             contrib = true;
                             // one reciprocal serves both divisions by (1 - alpha) of backward.cu:545,584 (the general
                             // kernel above keeps the two IEEE divisions: 54 M of its 230 M warp instructions)
-                            const float inv1a = 1.f / (1.f - alpha);
+                            // 1 - alpha lies in [0.01, 1): the special-case guard of the IEEE division (FCHK + slow
+                            // path, ~7 instructions, 7 % of this kernel) is not needed; reciprocal + one Newton step
+                            // gives the same correctly rounded quotient on that range
+                            const float oma = 1.f - alpha;
+                            float inv1a;
+                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv1a) : "f"(oma));
+                            inv1a = fmaf(inv1a, fmaf(-oma, inv1a, 1.f), inv1a);
                             T = T * inv1a;
                             wgt = alpha * T;
                             const float4 q2 = *reinterpret_cast<const float4*>(&S.rec[s][j][8]);
