@@ -130,6 +130,20 @@ static int fill_params(const GigsShade* a, ShadeParams& p, bool backward)
     return 0;
 }
 
+// every tap a bilinear footprint can produce on a level of resolution w (coordinates in [-1, w]): the table-driven
+// fold (cube_texel) against the reference statement (cube_wrap_texel)
+__global__ void __launch_bounds__(256) cube_wrap_selfcheck_kernel(const int w, int* __restrict__ mismatches)
+{
+    const int side = w + 2;
+    const long long n = 6ll * side * side;
+    for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < n; t += (long long)gridDim.x * 256) {
+        const int face = (int)(t / ((long long)side * side));
+        const int r = (int)(t % ((long long)side * side));
+        const int iu = r % side - 1, iv = r / side - 1;
+        if (cube_texel(face, iu, iv, w) != cube_wrap_texel(face, iu, iv, w)) atomicAdd(mismatches, 1);
+    }
+}
+
 }  // namespace gigs
 
 using namespace gigs;
@@ -160,6 +174,16 @@ int gigs_shade_backward(GigsShade* a)
     ProfScope ps(ST_SHADE_BWD, (cudaStream_t)a->stream);
     shade_backward_kernel<<<blocks, 256, SHB_MAX_DIFFUSE * sizeof(float), (cudaStream_t)a->stream>>>(p);
     GIGS_LAUNCH_CHECK("shade_backward_kernel");
+    return 0;
+}
+
+int gigs_cube_wrap_selfcheck(int32_t res, int32_t* mismatches, void* stream)
+{
+    if (res < 2 || res > 8192 || !mismatches) { set_error("gigs_cube_wrap_selfcheck: bad arguments"); return -1; }
+    cudaStream_t st = (cudaStream_t)stream;
+    GIGS_CUDA(cudaMemsetAsync(mismatches, 0, sizeof(int32_t), st));
+    cube_wrap_selfcheck_kernel<<<148 * 4, 256, 0, st>>>(res, mismatches);
+    GIGS_LAUNCH_CHECK("cube_wrap_selfcheck_kernel");
     return 0;
 }
 

@@ -33,7 +33,8 @@ __device__ __forceinline__ int cube_face_uv(float x, float y, float z, float& u,
 
 // texel (iu,iv) of `face`, possibly one step outside the face, -> linear index on the adjacent face.
 // Works in doubled integer coordinates: texel centres are the odd integers in [-w+1, w-1], face planes at +-w.
-// (kept out of line: taken only by taps that straddle a face edge, and inlining it 12x blew the instruction cache)
+// (the reference statement of the fold; the kernels use cube_texel below, which gigs_cube_wrap_selfcheck checks
+// against this function)
 static __device__ __noinline__ int cube_wrap_texel(int face, int iu, int iv, int w)
 {
     const bool ou = (iu < 0 || iu >= w), ov = (iv < 0 || iv >= w);
@@ -71,6 +72,29 @@ static __device__ __noinline__ int cube_wrap_texel(int face, int iu, int iv, int
     return (nf * w + iv2) * w + iu2;
 }
 
+// The same map as cube_wrap_texel for the taps the bilinear footprint can produce (at most one step outside the face),
+// from a 24-entry table: across edge e of face f the texel at position i along the edge lands on face nf at
+// (iu2, iv2) = (ku (w-1) + bu i, kv (w-1) + bv i) with bu, bv in {-1, 0, 1} - affine in i for every face, edge and
+// resolution (the table was derived from cube_wrap_texel itself; gigs_cube_wrap_selfcheck compares the two on every
+// tap of a level). ~15 instructions inline instead of a ~50-instruction call: a warp pays the edge path whenever ONE
+// of its lanes straddles an edge, which at the small mip levels is nearly always (measured with the folding compiled
+// out: 0.020 ms of the deferred backward and 0.017 ms of the shade kernel were this path).
+// entry: nf | ku << 3 | (bu + 1) << 4 | kv << 6 | (bv + 1) << 7, index face * 4 + {iu < 0, iu >= w, iv < 0, iv >= w}
+static __device__ const uint32_t CUBE_EDGE[24] = {0x11c, 0x115, 0x05a, 0x11b, 0x11d, 0x114, 0x112, 0x053, 0x0a1, 0x088, 0x08d, 0x0a4, 0x0c9, 0x0e0, 0x0e4, 0x0cd, 0x119, 0x110, 0x0e2, 0x0a3, 0x118, 0x111, 0x08a, 0x0cb};
+__device__ __forceinline__ int cube_texel(int face, int iu, int iv, int w)
+{
+    const bool ou = (unsigned)iu >= (unsigned)w, ov = (unsigned)iv >= (unsigned)w;
+    if (!(ou || ov)) return (face * w + iv) * w + iu;
+    if (ou && ov) return -1;  // cube corner: no such texel
+    const int edge = ou ? (iu < 0 ? 0 : 1) : (iv < 0 ? 2 : 3);
+    const int i = ou ? iv : iu;
+    const uint32_t e = CUBE_EDGE[face * 4 + edge];
+    const int nf = (int)(e & 7u);
+    const int iu2 = (int)((e >> 3) & 1u) * (w - 1) + ((int)((e >> 4) & 3u) - 1) * i;
+    const int iv2 = (int)((e >> 6) & 1u) * (w - 1) + ((int)((e >> 7) & 3u) - 1) * i;
+    return (nf * w + iv2) * w + iu2;
+}
+
 __device__ __forceinline__ CubeTaps cube_taps(float dx, float dy, float dz, int w)
 {
     CubeTaps T;
@@ -94,10 +118,10 @@ __device__ __forceinline__ CubeTaps cube_taps(float dx, float dy, float dz, int 
         T.idx[3] = base + w + 1; T.w[3] = fu * fv;
         return T;
     }
-    T.idx[0] = cube_wrap_texel(face, iu0, iv0, w);         T.w[0] = (1.f - fu) * (1.f - fv);
-    T.idx[1] = cube_wrap_texel(face, iu0 + 1, iv0, w);     T.w[1] = fu * (1.f - fv);
-    T.idx[2] = cube_wrap_texel(face, iu0, iv0 + 1, w);     T.w[2] = (1.f - fu) * fv;
-    T.idx[3] = cube_wrap_texel(face, iu0 + 1, iv0 + 1, w); T.w[3] = fu * fv;
+    T.idx[0] = cube_texel(face, iu0, iv0, w);             T.w[0] = (1.f - fu) * (1.f - fv);
+    T.idx[1] = cube_texel(face, iu0 + 1, iv0, w);         T.w[1] = fu * (1.f - fv);
+    T.idx[2] = cube_texel(face, iu0, iv0 + 1, w);         T.w[2] = (1.f - fu) * fv;
+    T.idx[3] = cube_texel(face, iu0 + 1, iv0 + 1, w); T.w[3] = fu * fv;
     // at a cube corner the missing texel is the mean of the other three
     int missing = -1;
 #pragma unroll

@@ -215,6 +215,7 @@ SYMBOLS = {
     "gigs_gi_count_probes": (C.c_int, [_i32, _i32, _f, _f, _f, _f, _f, _f, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp]),
     "gigs_gi_tune": (C.c_int, [_i32, _i32]),
     "gigs_set_dependent_launch": (C.c_int, [_i32]),
+    "gigs_cube_wrap_selfcheck": (C.c_int, [_i32, _vp, _vp]),
     "gigs_launch_count": (C.c_uint64, []),
     "gigs_ssr_backward": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gigs_shade_forward": (C.c_int, [C.POINTER(GigsShade)]),

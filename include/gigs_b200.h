@@ -231,6 +231,12 @@ int gigs_gi_count_probes(int32_t W, int32_t H, float fx, float fy, float radius,
  * for every setting. Process-wide; defaults 1, 1. */
 int gigs_gi_tune(int32_t pairs_per_step, int32_t block_test);
 
+/* Self-check of the cube-map seam handling: the shading kernels fold a bilinear tap that steps over a face edge onto
+ * the adjacent face with a 24-entry table; this compares the table against the reference statement of the fold for
+ * every tap position of a level of resolution res (coordinates in [-1, res]) and writes the number of mismatches to
+ * *mismatches (device, one int32). */
+int gigs_cube_wrap_selfcheck(int32_t res, int32_t* mismatches, void* stream);
+
 /* The kernels of the frame are launched with programmatic stream serialization (PTX griddepcontrol): each waits for
  * the previous grid before its first global access, so results do not change; only the launch latency between the
  * ~30 dependent kernels of a frame is hidden. on = 0 / 1 switches it for the process (default 1, or the environment

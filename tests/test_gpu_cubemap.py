@@ -267,3 +267,14 @@ def test_prefiltered_light_storage_policy_and_base_res_512():
         assert not small.stored_operators
     finally:
         GL.PrefilteredLight.STORED_MAX_BYTES = old
+
+
+@pytest.mark.parametrize("res", [2, 3, 16, 32, 100, 256, 512])
+def test_cube_seam_table_matches_the_reference_fold(res):
+    """The 24-entry edge table the shading kernels use for taps that step over a cube-face edge (shade_core.cuh:
+    cube_texel) against the reference statement of the fold (cube_wrap_texel), on every tap position of a level."""
+    from gigs import _lib
+    L = _lib.load()
+    bad = torch.full((1,), -1, dtype=torch.int32, device="cuda:0")
+    _lib.check(L.gigs_cube_wrap_selfcheck(res, bad.data_ptr(), torch.cuda.current_stream().cuda_stream), "selfcheck")
+    assert int(bad.item()) == 0
