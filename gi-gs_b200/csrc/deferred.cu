@@ -59,6 +59,9 @@ struct DeferParams {
     int ssr_const;           // shade kernel only: SSR does not march either: its per-pixel epilogue (gi_epilogue.cuh) over a
     float ssr_dirs;          // zero gathered radiance and ssr_dirs directions is evaluated here; depth_pos = positions
     const float* depth_pos;
+    int geom_skipped;        // the geometry chain did not run (GigsFrame.skip_geometry): depth_pos holds nothing; a pixel
+    const float* depth;      // whose epilogue needs its position evaluates it from the depth map (filters.cuh)
+    float fx, fy;
     int occl_const;          // shade kernel only: SSAO does not march (start >= step): occlusion is the constant 1, which
                              // this kernel writes to the map itself instead of reading a map a fill kernel wrote
     uint4* clear_ptr;        // backward kernel only: a 16-B aligned region it zeroes on entry (the blend backward's
@@ -214,7 +217,11 @@ __global__ void __launch_bounds__(256) deferred_shade_kernel(const DeferParams p
         if (p.ssr_const) {
             // what ssr_nomarch_kernel (gi_march.cu) computes from the maps written above, for this pixel
             const float3 F0v = make_float3(f0[0], f0[1], f0[2]);
-            const float3 posv = make_float3(p.depth_pos[id], p.depth_pos[HW + id], p.depth_pos[2 * HW + id]);
+            float3 posv = make_float3(0.f, 0.f, 0.f);
+            if (!p.geom_skipped)
+                posv = make_float3(p.depth_pos[id], p.depth_pos[HW + id], p.depth_pos[2 * HW + id]);
+            else if (!ssr_epilogue_is_zero(F0v, in.metal, make_float3(0.f, 0.f, 0.f), p.ssr_dirs))
+                posv = depth_pos_pixel(x, y, W, H, p.fx, p.fy, p.depth);
             float3 col, abd;
             ssr_epilogue_px(normalize3(make_float3(mv[0], mv[1], mv[2])), posv, in.alb, F0v, in.metal,
                             make_float3(0.f, 0.f, 0.f), p.ssr_dirs, col, abd);
@@ -708,9 +715,13 @@ int gigs_frame_forward(GigsFrame* f)
     char* m = (char*)f->maps;
     const int W = c.width, H = c.height;
     const float fx = W / (2.0f * c.tan_fovx), fy = H / (2.0f * c.tan_fovy);
-    if (int e = gigs_geometry_chain(W, H, fx, fy, c.viewmatrix, (float*)(m + FL.depth), 1, (float*)(m + FL.normal_from_depth),
-                                    (float*)(m + FL.depth_pos), f->stream)) return e;
     const bool ssao_marches = f->start < f->step;   // otherwise the constant 1 (gi_march.cu: gi_launch), written by the shade kernel
+    // normal_from_depth is a first-stage loss term and depth_pos only feeds the march (train.py:290-381): without a
+    // march nothing the loss or the gradients depend on reads the chain's outputs, and skip_geometry leaves it out
+    const bool geom_skipped = f->skip_geometry && !ssao_marches;
+    if (!geom_skipped)
+        if (int e = gigs_geometry_chain(W, H, fx, fy, c.viewmatrix, (float*)(m + FL.depth), 1, (float*)(m + FL.normal_from_depth),
+                                        (float*)(m + FL.depth_pos), f->stream)) return e;
     if (f->indirect && ssao_marches) {
         if (int e = gigs_ssao(W, H, fx, fy, f->radius, f->bias, f->thick, f->delta, f->step, f->start,
                               (float*)(m + FL.normal_view), (float*)(m + FL.depth_pos), (float*)(m + FL.occlusion),
@@ -725,6 +736,9 @@ int gigs_frame_forward(GigsFrame* f)
     p.ssr_const = ssr_fused ? 1 : 0;
     p.ssr_dirs = (float)ssr_dirs;
     p.depth_pos = (const float*)(m + FL.depth_pos);
+    p.geom_skipped = geom_skipped ? 1 : 0;
+    p.depth = (const float*)(m + FL.depth);
+    p.fx = fx; p.fy = fy;
     dim3 grid((W + DF_TW - 1) / DF_TW, (H + DF_TH - 1) / DF_TH), block(DF_TW, DF_TH);
     {
         ProfScope ps(ST_DEFER_SHADE, st);

@@ -37,4 +37,36 @@ __device__ __forceinline__ int median9_select(const float v[9], const float m)
     return sel;
 }
 
+// pixel -> view-space point at `depth` (reference depth_to_normal: forward.cu back-projection of the pixel grid)
+__device__ __forceinline__ float3 back_project(int x, int y, float cx, float cy, float fx, float fy, float depth)
+{
+    const float3 dir = make_float3((float(x) - cx) / fx, (float(y) - cy) / fy, 1.0f);
+    return make_float3(dir.x * depth, dir.y * depth, dir.z * depth);
+}
+
+// One pixel of the geometry chain's position output, median3x3(position(median3x3(depth))), evaluated straight from the
+// raw depth map with the chain's own expressions and padding rules (screen.cu: geometry_chain_kernel): the fused frame
+// uses it for the rare pixel that needs its position when the chain itself was skipped (GigsFrame.skip_geometry).
+static __device__ __noinline__ float3 depth_pos_pixel(int x, int y, int W, int H, float fx, float fy, const float* __restrict__ depth)
+{
+    const float cx = float(W) / 2.0f, cy = float(H) / 2.0f;
+    float px[9], py[9], pz[9];
+#pragma unroll 1
+    for (int k = 0; k < 9; ++k) {
+        const int qx = x + (k % 3) - 1, qy = y + (k / 3) - 1;
+        float3 pos = make_float3(0.f, 0.f, 0.f);                      // outside the image / on its border: zero
+        if (qx > 0 && qx < W - 1 && qy > 0 && qy < H - 1) {
+            float v[9];
+#pragma unroll
+            for (int j = 0; j < 9; ++j) {
+                const int rx = qx + (j % 3) - 1, ry = qy + (j / 3) - 1;   // inside the image here (qx, qy are interior)
+                v[j] = depth[(size_t)ry * W + rx];
+            }
+            pos = back_project(qx, qy, cx, cy, fx, fy, median9(v));
+        }
+        px[k] = pos.x; py[k] = pos.y; pz[k] = pos.z;
+    }
+    return make_float3(median9(px), median9(py), median9(pz));
+}
+
 }  // namespace gigs

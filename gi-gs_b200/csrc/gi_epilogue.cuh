@@ -6,6 +6,15 @@
 
 namespace gigs {
 
+// true when ssr_epilogue_px returns +0 whatever the normal and the position are (see the comment inside it)
+__device__ __forceinline__ bool ssr_epilogue_is_zero(const float3 F0, const float metallic, const float3 diffuse,
+                                                     const float nrSamples)
+{
+    return nrSamples > 0.0f && __float_as_uint(diffuse.x) == 0u && __float_as_uint(diffuse.y) == 0u &&
+           __float_as_uint(diffuse.z) == 0u && F0.x >= 0.f && F0.x <= 1.f && F0.y >= 0.f && F0.y <= 1.f && F0.z >= 0.f &&
+           F0.z <= 1.f && metallic >= 0.f && metallic <= 1.f;
+}
+
 // diffuse: the radiance gathered over the marched directions; nrSamples: their number.
 // color = diffuse' * albedo, abd = diffuse' (the factor the backward multiplies the colour gradient with).
 __device__ __forceinline__ void ssr_epilogue_px(const float3 normal, const float3 pos, const float3 albedo, const float3 F0,
@@ -17,9 +26,7 @@ __device__ __forceinline__ void ssr_epilogue_px(const float3 normal, const float
     // fpow lies in (0, 1] for every input (the base is clamped to [1e-6, 1]), so F = F0 + (1 - F0) * fpow <= 1 in float
     // with or without the contraction (rn(F0 + rn(1 - F0)) == 1), kD = (1 - F)(1 - metallic) is a finite value >= +0,
     // and pi * (+0) * (1/n) * kD = +0. The double-precision pow is skipped; NaN / out-of-range inputs take the full path.
-    if (nrSamples > 0.0f && __float_as_uint(diffuse.x) == 0u && __float_as_uint(diffuse.y) == 0u &&
-        __float_as_uint(diffuse.z) == 0u && F0.x >= 0.f && F0.x <= 1.f && F0.y >= 0.f && F0.y <= 1.f && F0.z >= 0.f &&
-        F0.z <= 1.f && metallic >= 0.f && metallic <= 1.f) {
+    if (ssr_epilogue_is_zero(F0, metallic, diffuse, nrSamples)) {
         abd = make_float3(0.f, 0.f, 0.f);
         color = make_float3(0.f * albedo.x, 0.f * albedo.y, 0.f * albedo.z);
         return;

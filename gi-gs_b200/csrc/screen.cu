@@ -148,11 +148,6 @@ bilateral3x3_kernel(const int C, const int W, const int H, const float color_coe
 // depth -> view-space position and pseudo-normal. DepthAt(x,y) returns the (filtered) depth of an
 // in-image pixel. Returns pos (0 on the border) and normal (0 unless all validity tests pass).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float3 back_project(int x, int y, float cx, float cy, float fx, float fy, float depth)
-{
-    const float3 dir = make_float3((float(x) - cx) / fx, (float(y) - cy) / fy, 1.0f);
-    return make_float3(dir.x * depth, dir.y * depth, dir.z * depth);
-}
 
 template <typename DepthAt>
 __device__ __forceinline__ void depth_to_normal_pixel(int x, int y, int W, int H, float fx, float fy,

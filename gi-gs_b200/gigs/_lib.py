@@ -142,7 +142,7 @@ class GigsFrame(C.Structure):
         ("binning", C.c_void_p), ("binning_bytes", C.c_uint64), ("sort", C.c_void_p), ("sort_bytes", C.c_uint64),
         ("maps", C.c_void_p), ("maps_bytes", C.c_uint64),
         ("radii", C.c_void_p), ("accum", C.c_void_p), ("pinned_num_rendered", C.c_void_p),
-        ("num_rendered", C.c_int64), ("resume", C.c_int32), ("_pad", C.c_int32),
+        ("num_rendered", C.c_int64), ("resume", C.c_int32), ("skip_geometry", C.c_int32),
         ("need_binning_bytes", C.c_uint64), ("need_sort_bytes", C.c_uint64),
         ("g_albedo", C.c_void_p), ("g_roughness", C.c_void_p), ("g_metallic", C.c_void_p),
         ("g_diffuse_tex", C.c_void_p), ("g_spec", C.c_void_p * 8),

@@ -88,7 +88,7 @@ def _p(t):
 def make_frame(ws: FrameWorkspace, cam, bg, params: Dict, raw: bool, sh_degree: int, light, brdf_lut, rays, gt,
                gi: Dict, indirect: bool, metallic: bool, tone: bool, gamma: bool, loss_scale: float, lamb_weight: float,
                keep: list, gt_ready: Optional[torch.cuda.Event] = None, inference: bool = False,
-               brdf_tv_weight: float = 0.0, material_only: bool = False) -> GigsFrame:
+               brdf_tv_weight: float = 0.0, material_only: bool = False, skip_geometry: bool = False) -> GigsFrame:
     """Fill the C-ABI argument struct of one frame. `keep` receives every tensor whose pointer went into the struct
     (hold it until the calls are done). gt_ready: an event recorded on the stream that copies `gt` to the device; the
     frame's stream waits on it only right before the loss kernel, so the copy overlaps the rasterizer.
@@ -139,6 +139,7 @@ def make_frame(ws: FrameWorkspace, cam, bg, params: Dict, raw: bool, sh_degree: 
     f.gt_image = _p(c32(gt)) if gt is not None else None
     f.loss_scale = float(loss_scale); f.lamb_weight = float(lamb_weight); f.brdf_tv_weight = float(brdf_tv_weight)
     f.material_only = int(bool(material_only))
+    f.skip_geometry = int(bool(skip_geometry))
     f.geom = ws.geom.data_ptr(); f.geom_bytes = ws.geom.numel()
     f.img = ws.img.data_ptr(); f.img_bytes = ws.img.numel()
     f.maps = ws.maps.data_ptr(); f.maps_bytes = ws.maps.numel()
@@ -232,9 +233,11 @@ def pbr_frame_step(params, cam, light, brdf_lut, rays, gt_image, background, gi:
                    radiance: bool = False) -> torch.Tensor:
     """forward (+ backward) of one PBR-stage view for a gigs.step.GaussianParams: gradients accumulate into
     params.flat_grad exactly as autograd would through the unfused path. Returns the (detached) loss scalar.
-    radiance=False: the SH radiance image (`color`) and the blended position (`pos`) are not produced — the PBR stage
-    reads neither (train.py:302-420 uses `render` only in its first stage and for logging); loss and gradients are
-    unchanged, preprocess skips the SH evaluation and the blend 6 of its 17 channels."""
+    radiance=False: only what the PBR-stage loss reads is produced. The SH radiance image (`color`) and the blended
+    position (`pos`) are not (train.py:302-420 uses `render` only in its first stage and for logging): preprocess skips
+    the SH evaluation and the blend 6 of its 17 channels. Without a GI march (start >= step) the depth -> normal /
+    position chain is left out as well (`normal_from_depth` is a first-stage loss term, `depth_pos` only feeds the
+    march, train.py:290-381): those two maps are then not written. Loss, gradients and every other map are unchanged."""
     L = params.leaves
     dev = L["xyz"].device
     ws = workspace(params.P, int(cam.image_width), int(cam.image_height), dev)
@@ -262,7 +265,7 @@ def pbr_frame_step(params, cam, light, brdf_lut, rays, gt_image, background, gi:
         keep: list = []
         f = make_frame(ws, cam, background, L, True, params.sh_degree, light, brdf_lut, rays, gt_image, gi, indirect,
                        metallic, tone, gamma, loss_scale, lamb_weight, keep, gt_ready=gt_ready,
-                       brdf_tv_weight=brdf_tv_weight, material_only=not radiance)
+                       brdf_tv_weight=brdf_tv_weight, material_only=not radiance, skip_geometry=not radiance)
         keep.extend([None] * 6)
         # cache only pointer-stable frames: had make_frame needed a contiguous / float32 COPY of a parameter, the copy
         # would go stale as soon as the optimiser updates the original in place

@@ -388,3 +388,62 @@ def test_clear_spans_zeroes_exactly_the_spans():
     _lib.check(L.gigs_clear_spans(view.data_ptr(), 1, lo1, hi1, torch.cuda.current_stream().cuda_stream), "clear")
     assert view[:2].eq(1).all() and view[n - 3:].eq(1).all() and view[2:n - 3].eq(0).all()
     assert L.gigs_clear_spans(buf.data_ptr(), 9, lo, hi, None) != 0     # more than 8 spans: refused
+
+
+def test_lean_frame_without_a_march_leaves_the_geometry_chain_out():
+    """radiance=False and start >= step: normal_from_depth / depth_pos are not consumed by anything (train.py:290-381)
+    and the depth -> normal / position chain is not run (GigsFrame.skip_geometry): the two maps stay untouched, the
+    loss and every other map are bit-for-bit those of the full frame, the gradients agree to the order of the atomics."""
+    P, W, H, base = 20000, 400, 300, 64
+    raw, cam, lut, rays, gt, bg = _setup(P, W, H)
+    res = {}
+    for radiance in (True, False):
+        p = gstep.GaussianParams(raw, DEV, light=scene.make_light(0, base_res=base))
+        p.zero_grad()
+        ws = gframe.workspace(P, W, H, DEV)
+        ws.map("depth_pos").fill_(123.0)
+        ws.map("normal_from_depth").fill_(-7.0)
+        l = gstep.training_step(p, cam, p.light(), lut, rays, gt, bg, GI64, fused=True, brdf_tv_weight=1.0,
+                                radiance=radiance)
+        assert p.last_workspace is ws
+        res[radiance] = (float(l), p.flat_grad.clone(),
+                         {k: ws.map(k).clone() for k in ("albedo", "roughness", "metallic", "normal", "normal_view", "depth",
+                                                         "opacity", "occlusion", "render_direct", "render_rgb",
+                                                         "ssr_color", "ssr_abd", "F0", "g_rgb")},
+                         ws.map("depth_pos").clone(), ws.map("normal_from_depth").clone())
+    assert float(res[False][3].min()) == 123.0 and float(res[False][3].max()) == 123.0      # not written
+    assert float(res[False][4].min()) == -7.0 and float(res[False][4].max()) == -7.0
+    assert float(res[True][3].max()) != 123.0                                               # the full frame ran it
+    assert res[True][0] == res[False][0]
+    assert ((res[True][1] - res[False][1]).norm() / res[True][1].norm()).item() <= 1e-6
+    for k, v in res[True][2].items():
+        assert torch.equal(v, res[False][2][k]) or bool(((v == res[False][2][k]) | (v.isnan() & res[False][2][k].isnan())).all()), k
+
+
+def test_lean_frame_takes_a_pixel_position_from_the_depth_map_when_its_epilogue_needs_one():
+    """SSR's epilogue is +0 without its position only for F0, metallic in [0, 1]; with albedo > 1 (activated inputs,
+    metallic 1 -> F0 = albedo) the full expression runs and needs the pixel's position, which the lean frame then
+    evaluates from the depth map with the chain's own expressions (filters.cuh: depth_pos_pixel): every map equals the
+    full frame's bit for bit."""
+    P, W, H, base = 20000, 400, 300, 64
+    raw, cam, lut, rays, gt, bg = _setup(P, W, H)
+    ref = gstep.GaussianParams(raw, DEV, light=scene.make_light(0, base_res=base))
+    g = {k: (v.detach() if torch.is_tensor(v) else v) for k, v in ref.activated().items()}
+    g["albedo"] = (g["albedo"] * 3.0).contiguous()           # blended albedo well above 1 on most pixels
+    g["metallic"] = torch.ones_like(g["metallic"])
+    light = ref.light()
+    out = {}
+    for skip in (False, True):
+        ws = gframe.workspace(P, W, H, DEV)
+        keep = []
+        f = gframe._fill(ws, cam, bg, g, False, 3, light, lut, rays, gt, GI64, True, True, False, True, 1.0, 0.001, keep,
+                         skip_geometry=skip)
+        loss = float(gframe.frame_forward(ws, f))
+        out[skip] = (loss, {k: ws.map(k).clone() for k in ("ssr_color", "ssr_abd", "render_rgb", "F0", "occlusion")})
+    assert float(out[False][1]["F0"].max()) > 1.0
+    assert out[False][0] == out[True][0]
+    for k, v in out[False][1].items():
+        w = out[True][1][k]
+        assert bool(((v == w) | (v.isnan() & w.isnan())).all()), k
+    # and the epilogue really depended on the position there: its sign pattern is not all +0
+    assert bool((torch.signbit(out[False][1]["ssr_abd"]) | out[False][1]["ssr_abd"].isnan()).any())
