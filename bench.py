@@ -6,9 +6,13 @@
     python bench.py --impl reference ...     # the CPU oracle port timed on the host cores (the reference has no CPU path)
 
 A "step" is ONE PBR-stage training frame per GPU (train.py:240-422 semantics on the hot path): activations,
-rasterize -> G-buffer, fused depth/normal filter chain, SSAO, split-sum shading, SSR, loss, full backward, run
-through the repo's public step API (gigs.step.training_step -> the fused frame path, two C-ABI calls per view;
-"variants.unfused_operator_path" times the same frame through the reference-shaped operator modules + autograd).
+rasterize -> G-buffer, SSAO, split-sum shading, SSR, loss, full backward, run through the repo's public step API
+(gigs.step.training_step -> the fused frame path, two C-ABI calls per view). The frame produces what the PBR-stage
+loss reads: the SH radiance image, the blended position and - when nothing marches - the depth -> normal / position
+filter chain are outputs of render() that train.py:290-420 never uses in this stage, and they are left out (same loss,
+same gradients, bit for bit; "variants.all_render_outputs" times the frame with all of them, "variants.gi_start8" the
+frame with the march and therefore the chain running, "variants.unfused_operator_path" the same frame through the
+reference-shaped operator modules + autograd).
 Workload = BASELINE configs[1]: lego-shaped synthetic scene, 300k random Gaussians (trained-like regime),
 800x800, SH degree 3, --metallic --indirect --gamma, GI radius 0.8 / bias 0.01 / thick 0.05 / delta 0.0625 /
 step 16 / start 64 (the README flags, under which the march loop runs zero iterations — the same frame with
@@ -254,7 +258,8 @@ def run_ours(args):
         # env-map one needs the base cubemap, i.e. only the build_mips variant has it
         loss = gstep.training_step(params, cam, light, lut, rays, gt, bg, gi, loss_scale=1.0 / world, fused=fused,
                                    gt_ready=gt_ready, light_ready=light_ready, brdf_tv_weight=1.0,
-                                   env_tv_weight=0.01 if params.prefiltered is not None else 0.0)
+                                   env_tv_weight=0.01 if params.prefiltered is not None else 0.0,
+                                   radiance=bool(ctx.get("radiance", False)))
         if world > 1:
             if light_ready is not None:
                 params.begin_light_all_reduce(light_ready)   # overlaps the blend backward
@@ -795,6 +800,20 @@ def run_ours(args):
                                 "over all 10 groups"}
                 except Exception as ex:
                     line["variants"]["first_stage_iteration"] = {"failed": str(ex)}
+                # ---- the same frame with EVERY map of render() produced: the SH radiance image, the blended position
+                # and (although nothing marches) the depth -> normal / position chain, none of which the PBR-stage loss
+                # reads (the headline frame leaves them out; loss and gradients are bit-identical) ----
+                ctx["radiance"] = True
+                try:
+                    tr_, _ = timed(gi, max(5, args.steps // 2), 3)
+                    msr = tr_ / max(5, args.steps // 2)
+                    line["variants"]["all_render_outputs"] = {
+                        "value": 1e3 / msr, "unit": "frames/s", "ms_per_step": msr,
+                        "note": "training_step(radiance=True): also the SH radiance image, the blended position and the "
+                                "depth->normal/position chain, which the PBR-stage loss never reads "
+                                "(train.py:290-420); same loss and gradients as the headline frame"}
+                finally:
+                    ctx["radiance"] = False
                 tu, _ = timed(gi, max(5, args.steps // 2), 3, fused=False)
                 msu = tu / max(5, args.steps // 2)
                 line["variants"]["unfused_operator_path"] = {
