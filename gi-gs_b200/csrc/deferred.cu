@@ -125,6 +125,28 @@ __device__ __forceinline__ float block_sum_256(float v, float* s_red /*[8]*/, in
     return t;
 }
 
+// One pixel of the 3x3 median of the normalised view-space normal map (what the shade kernel stages and filters for
+// SSR's normal input), straight from the map: for the rare pixel that needs it when the lean frame skipped that filter.
+// (arguments by value: a reference to the kernel's parameter struct would move the whole struct to local memory)
+static __device__ __noinline__ float3 median_view_normal_pixel(const float* __restrict__ normal_view_raw, const int W,
+                                                              const int H, const int x, const int y)
+{
+    const size_t HW = (size_t)W * H;
+    float a[9], b[9], c[9];
+#pragma unroll 1
+    for (int k = 0; k < 9; ++k) {
+        const int gx = x + (k % 3) - 1, gy = y + (k / 3) - 1;
+        float3 v = make_float3(0.f, 0.f, 0.f);
+        if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
+            const size_t id = (size_t)gy * W + gx;
+            v = normalize_where_positive(
+                make_float3(normal_view_raw[id], normal_view_raw[HW + id], normal_view_raw[2 * HW + id]));
+        }
+        a[k] = v.x; b[k] = v.y; c[k] = v.z;
+    }
+    return make_float3(median9(a), median9(b), median9(c));
+}
+
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) deferred_shade_kernel(const DeferParams p)
 {
@@ -152,11 +174,14 @@ __global__ void __launch_bounds__(256) deferred_shade_kernel(const DeferParams p
         if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
             const size_t id = (size_t)gy * W + gx;
             n = normalize_where_positive(make_float3(p.normal_map[id], p.normal_map[HW + id], p.normal_map[2 * HW + id]));
-            v = normalize_where_positive(
-                make_float3(p.normal_view_raw[id], p.normal_view_raw[HW + id], p.normal_view_raw[2 * HW + id]));
+            // SSR's normal input: only a march (or an epilogue that is not provably zero) reads it; the lean frame
+            // without a march (geom_skipped) leaves the filter out and evaluates single pixels on demand
+            if (!p.geom_skipped)
+                v = normalize_where_positive(
+                    make_float3(p.normal_view_raw[id], p.normal_view_raw[HW + id], p.normal_view_raw[2 * HW + id]));
         }
         s_n[0][ly][lx] = n.x; s_n[1][ly][lx] = n.y; s_n[2][ly][lx] = n.z;
-        s_v[0][ly][lx] = v.x; s_v[1][ly][lx] = v.y; s_v[2][ly][lx] = v.z;
+        if (!p.geom_skipped) { s_v[0][ly][lx] = v.x; s_v[1][ly][lx] = v.y; s_v[2][ly][lx] = v.z; }
     }
     __syncthreads();
 
@@ -164,20 +189,27 @@ __global__ void __launch_bounds__(256) deferred_shade_kernel(const DeferParams p
     float cnt = 0.f, s1 = 0.f, s2 = 0.f;
     if (x < W && y < H) {
         const size_t id = (size_t)y * W + x;
-        float mn[3], mv[3];
+        float mn[3], mv[3] = {0.f, 0.f, 0.f};
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            float a[9], b[9];
+            float a[9];
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-                for (int dx = 0; dx < 3; ++dx) {
-                    a[dy * 3 + dx] = s_n[c][threadIdx.y + dy][threadIdx.x + dx];
-                    b[dy * 3 + dx] = s_v[c][threadIdx.y + dy][threadIdx.x + dx];
-                }
+                for (int dx = 0; dx < 3; ++dx) a[dy * 3 + dx] = s_n[c][threadIdx.y + dy][threadIdx.x + dx];
             mn[c] = median9(a);
-            mv[c] = median9(b);
-            p.ssr_normal[c * HW + id] = mv[c];
+        }
+        if (!p.geom_skipped) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float b[9];
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) b[dy * 3 + dx] = s_v[c][threadIdx.y + dy][threadIdx.x + dx];
+                mv[c] = median9(b);
+                p.ssr_normal[c * HW + id] = mv[c];
+            }
         }
         // normals_view = -(normal_map^T @ R)   (gaussian_renderer/__init__.py:188-190)
         ShadeIn in;
@@ -220,8 +252,11 @@ __global__ void __launch_bounds__(256) deferred_shade_kernel(const DeferParams p
             float3 posv = make_float3(0.f, 0.f, 0.f);
             if (!p.geom_skipped)
                 posv = make_float3(p.depth_pos[id], p.depth_pos[HW + id], p.depth_pos[2 * HW + id]);
-            else if (!ssr_epilogue_is_zero(F0v, in.metal, make_float3(0.f, 0.f, 0.f), p.ssr_dirs))
+            else if (!ssr_epilogue_is_zero(F0v, in.metal, make_float3(0.f, 0.f, 0.f), p.ssr_dirs)) {
                 posv = depth_pos_pixel(x, y, W, H, p.fx, p.fy, p.depth);
+                const float3 m3 = median_view_normal_pixel(p.normal_view_raw, W, H, x, y);
+                mv[0] = m3.x; mv[1] = m3.y; mv[2] = m3.z;
+            }
             float3 col, abd;
             ssr_epilogue_px(normalize3(make_float3(mv[0], mv[1], mv[2])), posv, in.alb, F0v, in.metal,
                             make_float3(0.f, 0.f, 0.f), p.ssr_dirs, col, abd);
