@@ -187,6 +187,8 @@ __global__ void __launch_bounds__(256) deferred_shade_kernel(const DeferParams p
 
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
     float cnt = 0.f, s1 = 0.f, s2 = 0.f;
+    // does this tile hold an SSR radiance that is not +0.0? (unknown = yes when SSR runs as its own kernel afterwards)
+    bool ssr_any = !p.ssr_const;
     if (x < W && y < H) {
         const size_t id = (size_t)y * W + x;
         float mn[3], mv[3] = {0.f, 0.f, 0.f};
@@ -264,6 +266,7 @@ __global__ void __launch_bounds__(256) deferred_shade_kernel(const DeferParams p
             float* oa = const_cast<float*>(p.ssr_abd);
             oc[id] = col.x; oc[HW + id] = col.y; oc[2 * HW + id] = col.z;
             oa[id] = abd.x; oa[HW + id] = abd.y; oa[2 * HW + id] = abd.z;
+            ssr_any = (__float_as_uint(col.x) | __float_as_uint(col.y) | __float_as_uint(col.z)) != 0u;
         }
         if (m) {
             cnt = 1.f;
@@ -272,6 +275,7 @@ __global__ void __launch_bounds__(256) deferred_shade_kernel(const DeferParams p
         }
     }
     const int blk = blockIdx.y * gridDim.x + blockIdx.x;
+    const int tile_ssr_any = __syncthreads_or(ssr_any ? 1 : 0);
     const float t0 = block_sum_256(cnt, s_red, tid);
     const float t1 = block_sum_256(s1, s_red, tid);
     const float t2 = block_sum_256(s2, s_red, tid);
@@ -279,6 +283,7 @@ __global__ void __launch_bounds__(256) deferred_shade_kernel(const DeferParams p
         p.partials[4 * blk + 0] = t0;
         p.partials[4 * blk + 1] = t1;
         p.partials[4 * blk + 2] = t2;
+        p.partials[4 * blk + 3] = tile_ssr_any ? 1.f : 0.f;   // read by the loss kernel of this tile and its neighbours
     }
 }
 
@@ -293,16 +298,29 @@ __global__ void __launch_bounds__(256) deferred_loss_kernel(const DeferParams p)
     const int W = p.W, H = p.H;
     const size_t HW = (size_t)W * H;
     const int x0 = blockIdx.x * DF_TW, y0 = blockIdx.y * DF_TH;
-    for (int i = tid; i < DF_HH1 * DF_HW1; i += 256) {
-        const int lx = i % DF_HW1, ly = i / DF_HW1;
-        const int gx = x0 - 1 + lx, gy = y0 - 1 + ly;
-        float v[3] = {0.f, 0.f, 0.f};
-        if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
-            const size_t id = (size_t)gy * W + gx;
+    // The SSR radiance of this tile and of its eight neighbours is +0.0 everywhere (always so when nothing marches and
+    // the materials are in range; the shade kernel, which then evaluates SSR's epilogue itself, left one flag per tile):
+    // linear_to_srgb(+0) = +0, the 3x3 median of zeros is +0 and the first window element equal to it is element 0 -
+    // the staging and the two median networks per channel are skipped with exactly that result.
+    bool nb_any = false;
+    if (tid < 9) {
+        const int nbx = (int)blockIdx.x + tid % 3 - 1, nby = (int)blockIdx.y + tid / 3 - 1;
+        if (nbx >= 0 && nbx < (int)gridDim.x && nby >= 0 && nby < (int)gridDim.y)
+            nb_any = p.partials[4 * (nby * (int)gridDim.x + nbx) + 3] != 0.f;
+    }
+    const bool ssr_live = __syncthreads_or(nb_any ? 1 : 0) != 0;
+    if (ssr_live) {
+        for (int i = tid; i < DF_HH1 * DF_HW1; i += 256) {
+            const int lx = i % DF_HW1, ly = i / DF_HW1;
+            const int gx = x0 - 1 + lx, gy = y0 - 1 + ly;
+            float v[3] = {0.f, 0.f, 0.f};
+            if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
+                const size_t id = (size_t)gy * W + gx;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) v[c] = srgb_fwd(p.ssr_color[c * HW + id]);   // train.py:381 (linear_to_srgb)
+                for (int c = 0; c < 3; ++c) v[c] = srgb_fwd(p.ssr_color[c * HW + id]);   // train.py:381 (linear_to_srgb)
+            }
+            s_i[0][ly][lx] = v[0]; s_i[1][ly][lx] = v[1]; s_i[2][ly][lx] = v[2];
         }
-        s_i[0][ly][lx] = v[0]; s_i[1][ly][lx] = v[1]; s_i[2][ly][lx] = v[2];
     }
     __syncthreads();
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
@@ -312,13 +330,17 @@ __global__ void __launch_bounds__(256) deferred_loss_kernel(const DeferParams p)
         const float gscale = p.loss_scale / (float)(3 * HW);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            float a[9], b[9];
+            float irr = 0.f;
+            int sel = 0;
+            if (ssr_live) {
+                float a[9], b[9];
 #pragma unroll
-            for (int dy = 0; dy < 3; ++dy)
+                for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-                for (int dx = 0; dx < 3; ++dx) a[dy * 3 + dx] = b[dy * 3 + dx] = s_i[c][threadIdx.y + dy][threadIdx.x + dx];
-            const float irr = median9(b);
-            const int sel = median9_select(a, irr);
+                    for (int dx = 0; dx < 3; ++dx) a[dy * 3 + dx] = b[dy * 3 + dx] = s_i[c][threadIdx.y + dy][threadIdx.x + dx];
+                irr = median9(b);
+                sel = median9_select(a, irr);
+            }
             const float rgb = p.render_direct[c * HW + id] + irr;   // train.py:383
             p.render_rgb[c * HW + id] = rgb;
             if (p.gt) {
