@@ -49,7 +49,7 @@ struct DeferParams {
     float *render_rgb, *g_rgb;
     float *g_albedo, *g_roughness, *g_metallic;
     uint8_t *mask, *median_sel;
-    float* partials;         // [0 .. 4*nblk): shade partials {cnt, s1, s2, -}; [4*nblk .. 5*nblk): L1 partials;
+    float* partials;         // [0 .. 4*nblk): shade partials {cnt, s1, s2, SSR radiance not +0 on the tile}; [4*nblk .. 5*nblk): L1 partials;
                              // [5*nblk .. 7*nblk): BRDF TV partials {vertical, horizontal}
     uint32_t* counter;       // CTAs of the loss kernel that have finished
     float* stats;
@@ -240,10 +240,12 @@ __global__ void __launch_bounds__(256) deferred_shade_kernel(const DeferParams p
             if (p.sh.gamma) xk = srgb_fwd(xk);
             const float direct = m ? xk : p.bg[k];   // train.py:367-372
             p.render_direct[k * HW + id] = direct;
-            p.linear_rgb[k * HW + id] = srgb_to_linear_px(direct);
             // train.py:374-378
             f0[k] = p.use_metallic ? ((1.0f - metal_map) * 0.04f + alb[k] * metal_map) : 0.04f;
-            p.F0[k * HW + id] = f0[k];
+            if (!p.geom_skipped) {   // inputs of the SSR march only (the lean frame without a march leaves them out)
+                p.linear_rgb[k * HW + id] = srgb_to_linear_px(direct);
+                p.F0[k * HW + id] = f0[k];
+            }
         }
         p.rough_remap[id] = in.rough;
         p.metal_used[id] = in.metal;
@@ -457,15 +459,22 @@ __global__ void __launch_bounds__(256, MINB) deferred_backward_kernel(const Defe
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int x0 = (tile % tiles_x) * DF_TW, y0 = (tile / tiles_x) * DF_TH;
         __syncthreads();   // previous tile's readers are done (also orders the s_dtex / s_C initialisation)
-        for (int i = tid; i < DF_HH1 * DF_HW1; i += 256) {
-            const int lx = i % DF_HW1, ly = i / DF_HW1;
-            const int gx = x0 - 1 + lx, gy = y0 - 1 + ly;
-            const bool in = gx >= 0 && gx < W && gy >= 0 && gy < H;
-            const size_t id = (size_t)gy * W + gx;
+        // The shade kernel's flag of this tile (deferred_loss_kernel): 0 = SSR's radiance, and with it the factor the
+        // colour gradient is multiplied by (ssr_abd), is +0.0 on every pixel of the tile, so the gradient routed back
+        // through the median and linear_to_srgb contributes g * (+0) to the albedo gradient: nothing. The gather over
+        // the neighbours' selections is then skipped (the albedo gradient map may differ in the sign of a zero).
+        const bool ssr_live = p.partials[4 * tile + 3] != 0.f;
+        if (ssr_live) {
+            for (int i = tid; i < DF_HH1 * DF_HW1; i += 256) {
+                const int lx = i % DF_HW1, ly = i / DF_HW1;
+                const int gx = x0 - 1 + lx, gy = y0 - 1 + ly;
+                const bool in = gx >= 0 && gx < W && gy >= 0 && gy < H;
+                const size_t id = (size_t)gy * W + gx;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                s_g[c][ly][lx] = in ? p.g_rgb[c * HW + id] : 0.f;
-                s_sel[c][ly][lx] = in ? p.median_sel[c * HW + id] : (uint8_t)255;
+                for (int c = 0; c < 3; ++c) {
+                    s_g[c][ly][lx] = in ? p.g_rgb[c * HW + id] : 0.f;
+                    s_sel[c][ly][lx] = in ? p.median_sel[c * HW + id] : (uint8_t)255;
+                }
             }
         }
         __syncthreads();
@@ -481,6 +490,11 @@ __global__ void __launch_bounds__(256, MINB) deferred_backward_kernel(const Defe
             float g_alb_ssr[3], g_ren[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
+                if (!ssr_live) {
+                    g_alb_ssr[c] = 0.f;
+                    g_ren[c] = m ? p.g_rgb[c * HW + id] : 0.f;
+                    continue;
+                }
                 float gi = 0.f;
 #pragma unroll
                 for (int dy = 0; dy < 3; ++dy)

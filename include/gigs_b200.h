@@ -353,7 +353,7 @@ typedef struct GigsFrame {
     int32_t skip_geometry;       /* in: 1 = when no GI march runs (start >= step) the depth -> normal / position chain is
                                     left out: normal_from_depth is a first-stage loss term and depth_pos only feeds the
                                     march (train.py:290-381), so loss, gradients and every other map are unchanged; the
-                                    two maps and SSR's filtered normal input (ssr_normal) are then not written.
+                                    two maps and the march's other inputs (ssr_normal, linear_rgb, F0) are then not written.
                                     0 (what a zero-filled struct says): always run it */
     uint64_t need_binning_bytes, need_sort_bytes; /* out: sizes this frame needs (set when returning GIGS_E_GROW) */
     /* backward outputs, accumulated (+=); per-Gaussian ones are in raw-parameter space when raw_params */
