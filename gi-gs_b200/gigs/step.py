@@ -252,7 +252,7 @@ def training_step(params: GaussianParams, cam, light, brdf_lut, rays, gt_image, 
     neither, so by default they are skipped: gigs.frame.pbr_frame_step).
 
     fused=True (default) runs the frame as two C-ABI calls (gigs.frame: activations, rasterizer, deferred shading /
-    SSR / loss kernels and the material-only backward, ~25 kernel launches). fused=False runs the same frame
+    SSR / loss kernels and the material-only backward, ~20 kernel launches). fused=False runs the same frame
     operator by operator through the drop-in modules and autograd (~200 launches): same result to float rounding,
     kept as the reference-shaped path and as the parity check of the fused one."""
     pre = params.prefiltered if (params.prefiltered is not None and light is params.prefiltered) else None
