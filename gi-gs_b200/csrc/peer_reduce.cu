@@ -14,6 +14,7 @@
 // minute of GPU clock: stragglers — a rank writing a checkpoint, evaluating, loading data — are waited for, like
 // NCCL does) is a fatal error: the error word is set and the kernel traps, so the next CUDA call of this process
 // fails instead of the ranks training on with unreduced, diverging gradients.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace gigs {
@@ -104,10 +105,18 @@ __global__ void __launch_bounds__(PR_THREADS) peer_allreduce_kernel(const __grid
             const unsigned long long b = (unsigned long long)r * per, e = (b + per < n4) ? b + per : n4;
             if (A.mc != nullptr) {
                 // the switch adds (order fixed by the fabric, the same for every element of a run) and broadcasts
-                for (unsigned long long i = b + (unsigned long long)blockIdx.x * PR_THREADS + threadIdx.x; i < e;
-                     i += (unsigned long long)gridDim.x * PR_THREADS) {
-                    const float4 acc = multimem_ld_reduce_f4(A.mc + lo + 4 * i);
-                    multimem_st_f4(A.mc + lo + 4 * i, acc);
+                // UM load-reduces in flight per thread: one at a time left a thread waiting a switch round trip per 16 bytes
+                constexpr int UM = 4;
+                const unsigned long long mstride = (unsigned long long)gridDim.x * PR_THREADS;
+                for (unsigned long long i0 = b + (unsigned long long)blockIdx.x * PR_THREADS + threadIdx.x; i0 < e;
+                     i0 += UM * mstride) {
+                    float4 acc[UM];
+#pragma unroll
+                    for (int u = 0; u < UM; ++u)
+                        if (i0 + u * mstride < e) acc[u] = multimem_ld_reduce_f4(A.mc + lo + 4 * (i0 + u * mstride));
+#pragma unroll
+                    for (int u = 0; u < UM; ++u)
+                        if (i0 + u * mstride < e) multimem_st_f4(A.mc + lo + 4 * (i0 + u * mstride), acc[u]);
                 }
                 continue;
             }
@@ -203,7 +212,8 @@ int gigs_peer_allreduce(int32_t world, int32_t rank, const uint64_t* peer_bufs, 
         // gather at the barriers) and 128 (an 80 MB first-stage buffer needs the loads of many SMs in flight)
         uint64_t floats = 0;
         for (int s = 0; s < n_spans; ++s) floats += span_end[s] - span_begin[s];
-        const uint64_t want = (floats * 4 / (uint64_t)world) / (128 * 1024) + 1;
+        static const uint64_t kb_per_cta = getenv("GIGS_PEER_KB_PER_CTA") ? (uint64_t)atoi(getenv("GIGS_PEER_KB_PER_CTA")) : 128;
+        const uint64_t want = (floats * 4 / (uint64_t)world) / ((kb_per_cta ? kb_per_cta : 128) * 1024) + 1;
         n_ctas = (int)(want < 8 ? 8 : (want > 128 ? 128 : want));
     }
     if (n_ctas > 148) n_ctas = 148;     // every CTA of every call must be counted exactly once by the counter protocol
