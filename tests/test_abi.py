@@ -94,3 +94,29 @@ def test_frame_layout_is_aligned_disjoint_and_shape_determined():
     f = _lib.GigsFrame()
     assert L.gigs_frame_forward(ctypes.byref(f)) < 0 and L.gigs_frame_backward(ctypes.byref(f)) < 0
     assert L.gigs_frame_forward(None) < 0
+
+
+def test_binning_blob_has_room_for_the_forward_footprint_masks():
+    """The binning blob holds the sorted ids (4 R bytes) and, for the backward kernels, the forward's footprint-test
+    ballots: 8 words per 32-entry chunk, chunk index of tile t = range.x/32 + t + chunk in tile, which needs at most
+    R/32 + T + 1 chunks whatever the tile lengths are (csrc/common.cuh: Layout.b_warp_masks)."""
+    from gigs import _lib
+    L = _lib.load()
+    s = _lib.GigsSizes()
+    for (P, W, H, R) in [(1000, 800, 800, 0), (1000, 800, 800, 12345), (300000, 800, 800, 4227388),
+                         (6000000, 1237, 822, 31991500), (10, 16, 16, 1), (10, 3840, 2160, 77)]:
+        assert L.gigs_raster_sizes(P, W, H, R, ctypes.byref(s)) == 0
+        T = ((W + 15) // 16) * ((H + 15) // 16)
+        assert s.binning_bytes >= 4 * R + 32 * (R // 32 + T + 1), (P, W, H, R, s.binning_bytes)
+
+
+def test_dependent_launch_switch_and_launch_counter_are_host_side():
+    """gigs_set_dependent_launch / gigs_launch_count touch no device: usable (and consistent) on a CPU-only box."""
+    from gigs import _lib
+    L = _lib.load()
+    prev = L.gigs_set_dependent_launch(-1)
+    assert prev in (0, 1)
+    assert L.gigs_set_dependent_launch(0) == prev and L.gigs_set_dependent_launch(-1) == 0
+    assert L.gigs_set_dependent_launch(1) == 0 and L.gigs_set_dependent_launch(-1) == 1
+    L.gigs_set_dependent_launch(prev)
+    assert int(L.gigs_launch_count()) >= 0
