@@ -324,11 +324,32 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
 // can read num_rendered without a copy node in the stream.
 __global__ void __launch_bounds__(1024) scan_block_sums_kernel(uint32_t* __restrict__ block_sums, int nb,
                                                                uint32_t* __restrict__ total,
-                                                               uint32_t* __restrict__ total_host)
+                                                               uint32_t* __restrict__ total_host, const bool total_only)
 {
     pdl_enter();
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_carry;
+    if (total_only) {
+        // only the sum is wanted (preprocess: num_rendered; the per-block offsets of the emission come from the
+        // depth-ordered block sums later): a plain reduction, no scan rounds
+        uint32_t v = 0;
+        for (int i = threadIdx.x; i < nb; i += 1024) v += block_sums[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t t = 0;
+#pragma unroll
+            for (int w = 0; w < 32; ++w) t += s_warp[w];
+            *total = t;
+            if (total_host) {
+                *reinterpret_cast<volatile uint32_t*>(total_host) = t;
+                __threadfence_system();
+            }
+        }
+        return;
+    }
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -555,7 +576,7 @@ int launch_preprocess(const GigsRasterFwd* a, const Layout& L, cudaStream_t st, 
     if (int e = host_total_slot(a, &slot)) return e;
     if (slot.dev) *reinterpret_cast<volatile uint32_t*>(slot.host) = NUM_RENDERED_PENDING;   // read_back_num_rendered polls it
     GIGS_CUDA(launch_k(scan_block_sums_kernel, dim3(1), dim3(1024), (size_t)(0), st, (uint32_t*)(g + L.off.g_block_sums), (int)L.num_blocks,
-                       (uint32_t*)(g + L.off.g_num_rendered), slot.dev));
+                       (uint32_t*)(g + L.off.g_num_rendered), slot.dev, true));
     GIGS_LAUNCH_CHECK("scan_block_sums_kernel");
     return 0;
 }
@@ -591,7 +612,7 @@ int launch_emit_keys(const GigsRasterFwd* a, const Layout& L, uint32_t* keys, ui
     const bool self_prefix = L.num_blocks <= EMIT_SELF_PREFIX_BLOCKS;
     if (!self_prefix) {
         GIGS_CUDA(launch_k(scan_block_sums_kernel, dim3(1), dim3(1024), (size_t)(0), st, sums2, (int)L.num_blocks, sums2 + L.num_blocks,
-                           (uint32_t*)nullptr));
+                           (uint32_t*)nullptr, false));
         GIGS_LAUNCH_CHECK("scan_block_sums_kernel");
     }
     GIGS_CUDA(launch_k(emit_keys_kernel, dim3(L.num_blocks), dim3(PRE_THREADS), (size_t)(0), st, a->P, order, a->radii, (const float*)(g + L.off.g_record),
